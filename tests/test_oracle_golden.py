@@ -1,0 +1,152 @@
+"""Pins the oracle (oracle/relgat_oracle.py) to outputs of the UNMODIFIED reference.
+
+The fixtures under tests/golden were produced by oracle/gen_golden.py, which imports the
+reference's own Python files.  CPU only."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import relgat_oracle as O
+from tests.helpers import GOLDEN_DIR, Case, MODEL_CASES, rel_err
+
+
+@pytest.mark.parametrize("name", MODEL_CASES)
+def test_port_reproduces_reference_step(name):
+    c = Case(name)
+    layers = c.layer_params(requires_grad=True)
+    rel_emb = c.rel_emb(requires_grad=True)
+    proj = c.proj_params(requires_grad=True)
+    x0 = c.t("x0")
+    ei, et = c.edge_index(), c.t("rel")
+    # layer 0 output and final node representations: same op order => bit-identical on CPU
+    with torch.no_grad():
+        l0 = O.layer_forward_port(x0, layers[0]["W"], layers[0]["A"], layers[0]["beta"], ei, et)
+        xf = O.projection_port(O.gat_stack_port(x0, layers, ei, et), proj)
+    assert np.array_equal(l0.numpy(), c.z["layer0_out"])
+    assert rel_err(xf.numpy(), c.z["x_final"]) < 1e-6
+    loss, pos, neg = O.train_step_port(
+        x0, layers, rel_emb, ei, et, c.t("src_ids"), c.t("rel_ids"), c.t("dst_ids"),
+        scorer=c.scorer, b=c.b, k=c.k, margin=1.0,
+        loss_type="margin" if c.loss_type == "margin" else "self_adv", self_adv_alpha=0.7,
+        proj=proj, weights=c.weights)
+    tol = 1e-12 if c.dtype == torch.float64 else 1e-6
+    assert rel_err(pos.detach().numpy(), c.z["pos"]) < tol
+    assert rel_err(neg.detach().numpy(), c.z["neg"]) < tol
+    assert abs(float(loss.detach()) - float(c.z["loss"])) < tol * max(1.0, abs(float(c.z["loss"])))
+    loss.backward()
+    gtol = 1e-10 if c.dtype == torch.float64 else 2e-5
+    for li in range(c.layers):
+        p = "grad/" + c.layer_prefix(li)
+        for h in range(c.h):
+            assert rel_err(layers[li]["W"][h].grad.numpy(), c.z[f"{p}proj.{h}.weight"]) < gtol
+            assert rel_err(layers[li]["A"][h].grad.numpy(), c.z[f"{p}attn_vec.{h}"]) < gtol
+        assert rel_err(layers[li]["beta"].grad.numpy(), c.z[f"{p}rel_bias"]) < gtol
+    assert rel_err(rel_emb.grad.numpy(), c.z["grad/scorer.rel_emb.weight"]) < gtol
+    mrr, hits = O.mrr_hits_port(pos.detach(), neg.detach(), tuple(range(1, c.k + 1)))
+    assert mrr == pytest.approx(float(c.z["mrr"]), abs=1e-12)
+    assert [hits[i] for i in range(1, c.k + 1)] == pytest.approx(list(c.z["hits"]), abs=1e-12)
+
+
+@pytest.mark.parametrize("name", ["tiny_fp64", "adversarial_fp32", "transe_fp64"])
+def test_closed_form_matches_reference_layer(name):
+    """SURVEY.md Appendix A closed forms (fwd and analytic bwd) against reference autograd."""
+    c = Case(name)
+    lp = c.layer_params(requires_grad=True)[0]
+    x0 = c.t("x0").double()
+    ei, et = c.edge_index(), c.t("rel")
+    W = [w.detach().double().requires_grad_(True) for w in lp["W"]]
+    A = [a.detach().double().requires_grad_(True) for a in lp["A"]]
+    beta = lp["beta"].detach().double().requires_grad_(True)
+    y, logits, alphas = O.layer_forward_port(x0, W, A, beta, ei, et, return_attention=True)
+    g = O.graph_index_np(c.z["src"], c.z["dst"], c.z["rel"], c.n, c.r)
+    P = torch.stack([x0 @ w.t() for w in W], 1).detach().numpy()  # [N,H,F]
+    An = torch.stack(A, 0).detach().numpy()
+    out, z, alpha, bias = O.layer_forward_closed(P, An, beta.detach().numpy(), g)
+    perm = g["csr_perm"]
+    assert rel_err(out.reshape(c.n, -1), y.detach().numpy()) < 1e-12
+    assert rel_err(alpha, alphas.detach().numpy()[perm]) < 1e-12
+    eps = np.where(z > 0, z, 0.2 * z)
+    assert rel_err(eps, logits.detach().numpy()[perm]) < 1e-12
+    # nodes without in-edges are exactly zero
+    deg = np.diff(g["rowptr"])
+    assert np.all(out[deg == 0] == 0.0)
+    G = np.random.default_rng(0).standard_normal(out.shape)
+    (y * torch.from_numpy(G.reshape(c.n, -1))).sum().backward()
+    dP, dA, dbeta, _ = O.layer_backward_closed(G, P, An, g, z, alpha)
+    dW_ref = torch.stack([w.grad for w in W], 0).numpy()  # [H,F,D]
+    dW = np.einsum("nhf,nd->hfd", dP, x0.numpy())
+    assert rel_err(dW, dW_ref) < 1e-10
+    assert rel_err(dA, torch.stack([a.grad for a in A], 0).numpy()) < 1e-10
+    assert rel_err(dbeta, beta.grad.numpy()) < 1e-10
+
+
+def test_graph_index_is_stable_by_destination():
+    rng = np.random.default_rng(3)
+    n, e, r = 37, 500, 5
+    src, dst, rel = rng.integers(0, n, e), rng.integers(0, n - 4, e), rng.integers(0, r, e)
+    g = O.graph_index_np(src, dst, rel, n, r)
+    assert g["rowptr"][0] == 0 and g["rowptr"][-1] == e
+    for j in range(n):
+        seg = g["csr_perm"][g["rowptr"][j]:g["rowptr"][j + 1]]
+        assert np.all(dst[seg] == j)
+        assert np.all(np.diff(seg) > 0)  # original edge order inside a destination
+    assert np.array_equal(g["csr_src"], src[g["csr_perm"]])
+    assert np.array_equal(g["csr_rel"], rel[g["csr_perm"]])
+    for i in range(n):
+        slots = g["csc_slot"][g["colptr"][i]:g["colptr"][i + 1]]
+        assert np.all(g["csr_src"][slots] == i) and np.all(np.diff(slots) > 0)
+    for q in range(r):
+        slots = g["rel_slot"][g["relptr"][q]:g["relptr"][q + 1]]
+        assert np.all(g["csr_rel"][slots] == q) and np.all(np.diff(slots) > 0)
+
+
+def test_partition_concat_equals_whole():
+    """dst-range buckets: per-rank layer outputs concatenated == unpartitioned output."""
+    c = Case("tiny_fp64")
+    lp = c.layer_params()[0]
+    x0, ei, et = c.t("x0"), c.edge_index(), c.t("rel")
+    whole = O.layer_forward_port(x0, lp["W"], lp["A"], lp["beta"], ei, et)
+    for world in (2, 3):
+        for balance in ("nodes", "edges"):
+            bounds = O.partition_bounds_np(c.z["dst"], c.n, world, balance)
+            assert bounds[0] == 0 and bounds[-1] == c.n and np.all(np.diff(bounds) >= 0)
+            parts = O.bucket_edges_np(c.z["src"], c.z["dst"], c.z["rel"], bounds)
+            assert sum(len(p[0]) for p in parts) == c.e
+            rows = []
+            for gidx, (s, d, r, eid) in enumerate(parts):
+                assert np.all(np.diff(eid) > 0)
+                y = O.layer_forward_port(x0, lp["W"], lp["A"], lp["beta"],
+                                         torch.from_numpy(np.stack([s, d])), torch.from_numpy(r))
+                rows.append(y[bounds[gidx]:bounds[gidx + 1]])
+            assert np.array_equal(torch.cat(rows).numpy(), whole.numpy())
+
+
+def test_negative_sampling_matches_reference_stream():
+    """Seeded shuffle/split/negatives are bit-exact with the reference's dataset classes."""
+    z = np.load(os.path.join(GOLDEN_DIR, "sampling.npz"))
+    n, t, r, d, k, bs, seed = [int(v) for v in z["meta"]]
+    raw = list(zip(z["raw_src"].tolist(), z["raw_dst"].tolist(), z["raw_rel"].tolist()))
+    # reference order of RNG consumption: RandomSeed (utils/random_seed.py:18-22) then
+    # random.shuffle of the raw triples (dataset/relgat_dataset.py:72)
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    random.shuffle(raw)
+    n_train = int(0.9 * len(raw))
+    train = raw[:n_train]
+    assert np.array_equal(np.array([e[0] for e in train]), z["edge_index"][0])
+    assert np.array_equal(np.array([e[1] for e in train]), z["edge_index"][1])
+    assert np.array_equal(np.array([e[2] for e in train]), z["edge_type"])
+    assert np.array_equal(np.array(raw[n_train:]), z["eval_edges"])
+    # DataLoader(shuffle=True) index order comes from torch's own sampler; negatives from `random`
+    loader = torch.utils.data.DataLoader(range(n_train), batch_size=bs, shuffle=True, collate_fn=list)
+    for bi, idxs in enumerate(loader):
+        if bi >= 3:
+            break
+        s, rr, dd = O.sample_batch_port(train, idxs, n, k)
+        assert np.array_equal(s, z[f"batch{bi}_src"])
+        assert np.array_equal(rr, z[f"batch{bi}_rel"])
+        assert np.array_equal(dd, z[f"batch{bi}_dst"])
