@@ -1,0 +1,127 @@
+/* relgat_b200.h — C ABI of librelgat_b200.so: the B200-native RelGAT message-passing hot path.
+ *
+ * The reference (radlab-dev-group/relgat-projector v0.2.1) has no FFI or plugin interface: its
+ * hot path is Python calling torch and torch_scatter.  Each entry point below therefore names
+ * the reference code it replaces (file:line under the reference root); INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions (every function):
+ *   - all pointers are DEVICE pointers unless stated; the caller owns every buffer (inputs,
+ *     outputs, workspaces); the library keeps no device memory and no mutable global state;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises;
+ *   - returns 0 on success, a negative RG_ERR_* code for argument errors detected on the host,
+ *     or a positive cudaError_t if a launch failed; no C++ exception crosses the boundary;
+ *   - node features are row-major [rows, H*F] with column = h*F + f (head-major concat,
+ *     reference core/model/layer.py:321); edge-wise arrays are in CSR slot order.
+ */
+#ifndef RELGAT_B200_H_
+#define RELGAT_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RG_OK 0
+#define RG_ERR_ARG (-1)
+#define RG_ERR_SHAPE (-2)
+#define RG_ERR_ALIGN (-3)
+#define RG_ERR_WORKSPACE (-4)
+#define RG_ERR_DTYPE (-5)
+#define RG_ERR_DRIVER (-6)
+
+#define RG_SCORER_DISTMULT 0
+#define RG_SCORER_TRANSE 1
+
+/* ABI version (bumped on any signature change). */
+int relgat_abi_version(void);
+
+/* ---- graph index ------------------------------------------------------------------------
+ * Replaces nothing in the reference (it keeps COO int64: dataset/relgat_dataset.py:123-137);
+ * defines the stable by-destination (CSR), by-source (CSC) and by-relation orderings of that
+ * COO which every kernel below consumes.  src/dst/rel: int64[E].  All outputs int32.
+ * N = number of destination rows, N_src = number of source rows (equal on one GPU; a
+ * destination-range partition owns N local destinations but reads all N_src global sources).
+ *   rowptr[N+1], csr_perm[E] (original edge id of each CSR slot), csr_src/csr_rel/csr_dst[E];
+ *   colptr[N_src+1], csc_slot[E] (CSR slot of the t-th by-source edge), csc_dst/csc_rel[E];
+ *   relptr[R+1], rel_slot[E] (CSR slots ordered by relation). */
+long long relgat_graph_index_workspace_bytes(long long E);
+int relgat_graph_index_build(const long long* src, const long long* dst, const long long* rel,
+                             long long E, long long N, long long N_src, long long R,
+                             int* rowptr, int* csr_perm, int* csr_src, int* csr_rel, int* csr_dst,
+                             int* colptr, int* csc_slot, int* csc_dst, int* csc_rel,
+                             int* relptr, int* rel_slot,
+                             void* workspace, long long workspace_bytes, void* stream);
+
+/* ---- dense feature transform (tcgen05 + TMA) ---------------------------------------------
+ * Replaces `lin(node_emb)` of core/model/layer.py:220 (all heads in one GEMM) and its autograd
+ * GEMMs.  D[M,N] fp32 = A·Bᵀ, bf16 operands, fp32 accumulation in tensor memory.
+ *   a_mn/b_mn = 0: operand stored [rows = M|N, K] (K contiguous); 1: stored [K, M|N].
+ *   a_lo/b_lo != NULL selects the fp32-parity mode: operands are (hi, lo) bf16 planes of an
+ *   fp32 matrix (relgat_split_bf16) and hi·hi + hi·lo + lo·hi is accumulated.
+ *   splits_k > 1: split-K with an ordered reduction (needs relgat_gemm_workspace_bytes). */
+int relgat_split_bf16(const float* x, void* hi, void* lo, long long n, void* stream);
+long long relgat_gemm_workspace_bytes(int M, int N, int K, int a_mn, int b_mn, int splits_k);
+int relgat_gemm_bf16(const void* a_hi, const void* a_lo, long long lda, int a_mn,
+                     const void* b_hi, const void* b_lo, long long ldb, int b_mn,
+                     float* d, long long ldd, int M, int N, int K, int splits_k,
+                     void* workspace, long long workspace_bytes, int sm_count, void* stream);
+
+/* ---- RelGAT layer, edge part, forward ------------------------------------------------------
+ * Replaces core/model/layer.py:220 (the [src] gather) through :318: logits + LeakyReLU(0.2),
+ * per-destination stable softmax (torch_scatter.scatter_max / scatter_add), weighted
+ * aggregation and the relation bias.  P: projected features [N_src, H*F] (row stride ldp),
+ * A: [H, R, F] (stacked attn_vec), beta: [R] or NULL.
+ * Outputs: out [N, H*F] fp32 pre-activation (may be NULL), optional bf16 (hi, lo) planes of
+ * act(out) for the next layer's GEMM (act = ELU if apply_elu, reference model.py:286-287),
+ * alpha/z [E, H] (attention weights / raw logits, saved for backward), bias_out [N].
+ * Destinations with more than max_deg in-edges are skipped (hub path); max_deg <= 0: none. */
+int relgat_layer_fwd(const void* P, int p_is_bf16, long long ldp, const float* A, const float* beta,
+                     const int* rowptr, const int* csr_src, const int* csr_rel,
+                     float* out, void* act_hi, void* act_lo, int apply_elu,
+                     float* alpha, float* z, float* bias_out,
+                     int N, int H, int F, int R, int max_deg, void* stream);
+
+/* ---- RelGAT layer, edge part, backward (replaces the autograd replay of layer.py:220-318) ---
+ * bwd_prep: G = dY * act'(out) (in place allowed), t[N,H] = <G, out - bias>, hsum[N,H] = sum_f G.
+ * bwd_src : by-source pass: dP [N_src, H*F] (fp32 and/or bf16 hi/lo planes) and dz [E, H].
+ * bwd_rel : by-relation pass over chunks [chunk_lo, chunk_hi) of rel_slot (a chunk never spans
+ *           two relations; rel_chunk_ptr[R+1] gives each relation's chunk range):
+ *           dA [H, R, F] and dbeta [R] (NULL to skip) with an ordered reduction of the partials
+ *           partA [n_chunks, H*F], partB [n_chunks]. */
+int relgat_layer_bwd_prep(const float* dY, const float* out, const float* bias, float* G, float* t,
+                          float* hsum, int N, int H, int F, int apply_elu, void* stream);
+int relgat_layer_bwd_src(const float* P, long long ldp, const float* G, const float* A,
+                         const float* alpha, const float* z, const float* t,
+                         const int* colptr, const int* csc_slot, const int* csc_dst, const int* csc_rel,
+                         float* dP, void* dP_hi, void* dP_lo, float* dz,
+                         int N_src, int H, int F, int R, int max_deg, void* stream);
+int relgat_layer_bwd_rel(const float* P, long long ldp, const float* dz, const float* hsum,
+                         const int* rel_slot, const int* csr_src, const int* csr_dst,
+                         const int* chunk_lo, const int* chunk_hi, const int* rel_chunk_ptr,
+                         int n_chunks, float* partA, float* partB, float* dA, float* dbeta,
+                         int H, int F, int R, void* stream);
+
+/* ---- scorers (replaces core/scorer.py:58-94 DistMult, :154-201 TransE, and the row gathers
+ * x[src_ids] / x[dst_ids] of core/model/model.py:136-137) -------------------------------------
+ * xs/xd: [*, D]; src_idx/dst_idx: int64[B] or NULL (row b); rel_ids: int64[B]; rel_emb [R, D].
+ * fwd: score [B]; optional transform [Bt, D] for the first Bt triples (scorer.transform);
+ *      optional gathered copies src_vec/dst_vec [B, D].
+ * bwd: given dscore [B] (NULL = 0) and dtransform [Bt, D] (NULL = 0) writes one gradient row per
+ *      triple: d_src, d_dst, d_rel [B, D] (any may be NULL).
+ * relgat_index_add_sorted: ordered segmented row sum used to fold those rows per node / per
+ *      relation.  sorted_keys int64[M] ascending (stable sort of the keys), perm int64[M] the
+ *      matching row ids: out[key, :] (+)= sum_{p: sorted_keys[p]==key} rows[perm[p], :]. */
+int relgat_score_fwd(int kind, int normalize, const float* xs, const long long* src_idx, const float* xd,
+                     const long long* dst_idx, const float* rel_emb, const long long* rel_ids, int B, int D,
+                     float* score, float* transform, int Bt, float* src_vec, float* dst_vec, void* stream);
+int relgat_score_bwd(int kind, int normalize, const float* xs, const long long* src_idx, const float* xd,
+                     const long long* dst_idx, const float* rel_emb, const long long* rel_ids, int B, int D,
+                     const float* dscore, const float* dtransform, int Bt,
+                     float* d_src, float* d_dst, float* d_rel, void* stream);
+int relgat_index_add_sorted(const float* rows, const long long* perm, const long long* sorted_keys,
+                            float* out, int M, int D, int accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RELGAT_B200_H_ */

@@ -1,0 +1,164 @@
+// Shared device helpers for the RelGAT sm_100a kernels.
+//
+// Row layout convention used by every edge kernel: a node row is [H, F] elements
+// (column = h*F + f, the head-major concat order of reference layer.py:321).  One warp
+// serves one (node, head-group) task: the group holds `hg` heads (power of two, divides H),
+// each head is owned by lph = 32/hg consecutive lanes, and a lane walks its head in
+// 128-bit vectors q = sub + lph*k, k < KMAX.  Because a lane only ever touches one head,
+// per-head reductions are log2(lph) xor-shuffles shared by all heads of the group.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace relgat {
+
+constexpr int kMaxVecPerLane = 8;  // KMAX: 128-bit vectors a lane may own per row
+constexpr float kLeakySlope = 0.2f;  // reference layer.py:233
+
+// ---- error codes of the C ABI (include/relgat_b200.h) ------------------------------
+enum : int {
+  RG_OK = 0,
+  RG_ERR_ARG = -1,        // null pointer / negative size
+  RG_ERR_SHAPE = -2,      // shape not supported by the lane mapping
+  RG_ERR_ALIGN = -3,      // pointer not 16-byte aligned
+  RG_ERR_WORKSPACE = -4,  // workspace too small
+  RG_ERR_DTYPE = -5,
+  RG_ERR_DRIVER = -6,     // driver entry point (tensor-map encode) unavailable
+};
+
+inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? RG_OK : static_cast<int>(e); }
+
+// ---- 128-bit (or scalar) row-vector access, values widened to fp32 ------------------
+template <typename T, int V>
+struct RowVec;
+
+template <>
+struct RowVec<float, 4> {
+  static __device__ __forceinline__ void load_stream(const float* p, float (&v)[4]) {
+    // gathered rows are touched ~degree times chip-wide, never twice by one SM: keep them out of L1
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
+  }
+  static __device__ __forceinline__ void load_cached(const float* p, float (&v)[4]) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+
+template <>
+struct RowVec<float, 1> {
+  static __device__ __forceinline__ void load_stream(const float* p, float (&v)[1]) { v[0] = __ldg(p); }
+  static __device__ __forceinline__ void load_cached(const float* p, float (&v)[1]) { v[0] = __ldg(p); }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[1]) { *p = v[0]; }
+};
+
+template <>
+struct RowVec<__nv_bfloat16, 8> {
+  static __device__ __forceinline__ void unpack(const uint4& t, float (&v)[8]) {
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  static __device__ __forceinline__ void load_stream(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 t;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(p));
+    unpack(t, v);
+  }
+  static __device__ __forceinline__ void load_cached(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+    unpack(t, v);
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 t;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+
+// ---- fp32 -> bf16 (hi, lo) split stores: x ~= hi + lo with hi = rn(x), lo = rn(x - hi) --------
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+template <int V>
+__device__ __forceinline__ void store_split_bf16(__nv_bfloat16* hi, __nv_bfloat16* lo, const float (&v)[V]) {
+  if constexpr (V == 4) {
+    const float h0 = bf16_round(v[0]), h1 = bf16_round(v[1]), h2 = bf16_round(v[2]), h3 = bf16_round(v[3]);
+    *reinterpret_cast<uint2*>(hi) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+    if (lo) *reinterpret_cast<uint2*>(lo) = make_uint2(pack_bf16x2(v[0] - h0, v[1] - h1), pack_bf16x2(v[2] - h2, v[3] - h3));
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float h = bf16_round(v[i]);
+      hi[i] = __float2bfloat16_rn(h);
+      if (lo) lo[i] = __float2bfloat16_rn(v[i] - h);
+    }
+  }
+}
+
+// ---- lane mapping ------------------------------------------------------------------
+struct LaneMap {
+  int hh;        // absolute head owned by this lane
+  int sub;       // lane index inside the head's lane set
+  int lph;       // lanes per head
+  int vph;       // vectors per head (F / V)
+  int head_off;  // hh * F (elements)
+};
+
+template <int V>
+__device__ __forceinline__ LaneMap make_lane_map(int lane, int group, int hg, int F) {
+  LaneMap m;
+  m.lph = 32 / hg;
+  const int hl = lane / m.lph;
+  m.sub = lane - hl * m.lph;
+  m.hh = group * hg + hl;
+  m.vph = F / V;
+  m.head_off = m.hh * F;
+  return m;
+}
+
+// Sum over the lanes that own the same head (lph is a power of two <= 32).
+__device__ __forceinline__ float head_sum(float x, int lph) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float y = __shfl_xor_sync(0xffffffffu, x, o);
+    if (o < lph) x += y;
+  }
+  return x;
+}
+
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+// Host side: heads per warp for (H, F, V).  Largest power of two dividing H such that a
+// head's F/V vectors fit kMaxVecPerLane per lane.  Returns 0 when no mapping exists.
+inline int pick_heads_per_warp(int H, int F, int V) {
+  if (H <= 0 || F <= 0 || F % V != 0) return 0;
+  const int vph = F / V;
+  for (int hg = 32; hg >= 1; hg >>= 1) {
+    if (H % hg != 0) continue;
+    const int lph = 32 / hg;
+    if ((vph + lph - 1) / lph <= kMaxVecPerLane) return hg;
+  }
+  return 0;
+}
+
+}  // namespace relgat

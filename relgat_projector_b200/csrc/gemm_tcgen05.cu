@@ -1,0 +1,449 @@
+// G1/G2/G3 — the dense feature transforms of the RelGAT layer on the 5th-gen tensor cores:
+//   G1  P  = X  · Wᵀ   (reference layer.py:220, all heads concatenated: W = cat_h proj[h].weight)
+//   G2  dW = dPᵀ · X   (autograd of G1, K20 in SURVEY.md §2.2) — split-K, both operands MN-major
+//   G3  dX = dP · W    (layers >= 1)                           — B operand MN-major
+//
+// One persistent, warp-specialised kernel (sm_100a only):
+//   warp 0   : TMA producer   (cp.async.bulk.tensor.2d, 128B swizzle, mbarrier complete_tx)
+//   warp 1   : MMA issuer     (one elected lane: tcgen05.mma.cta_group::1.kind::f16, fp32 accum in TMEM)
+//   warp 2   : TMEM allocator (512 columns = two accumulator stages of up to 256 columns)
+//   warps 4-7: epilogue       (tcgen05.ld 32x32b -> registers -> 128-bit global stores)
+//
+// fp32-parity mode ("split"): each fp32 operand is carried as two bf16 planes (hi = rn(x),
+// lo = rn(x - hi)); the kernel issues hi·hi + hi·lo + lo·hi into the same fp32 accumulator,
+// which reproduces an fp32 GEMM to ~2^-16 relative per product (the dropped lo·lo term),
+// well inside the 1e-4 budget, at 3 tensor-core passes over ONE smem fill.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace relgat {
+
+constexpr int kBM = 128;       // UMMA M (cta_group::1)
+constexpr int kBK = 64;        // one 128-byte swizzle atom of bf16 along the contiguous dim
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 256;
+constexpr int kTmemCols = 512;
+constexpr int kMaxStages = 8;
+
+struct GemmParams {
+  int M, N, K;           // D[M,N] = sum_k A[m,k] * B[n,k]
+  int BN;                // N tile (multiple of 16, <= 256)
+  int a_mn, b_mn;        // operand major-ness: 0 = K-major (K contiguous), 1 = MN-major
+  int split;             // 1: operands carry hi and lo planes (3 MMA passes), 0: single plane
+  int stages;
+  int splits_k;          // split-K factor (partials written at d + s * d_split_stride)
+  int kb_per_split;      // k-blocks per split
+  float* d;
+  long long ldd;
+  long long d_split_stride;
+  int a_tile_bytes, b_tile_bytes;   // per plane
+  int b_boxes;           // MN-major B: number of 64-wide boxes per tile
+};
+
+// ---------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(addr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(addr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (sm_100 "version 1"), 128-byte swizzle.
+//   K-major  tile [rows][64 bf16]: SBO = 1024 B between 8-row groups, LBO unused (1)
+//   MN-major tile [k rows][64 bf16] x boxes: SBO = 1024 B between 8-k groups, LBO = bytes between 64-wide MN boxes
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3ffff) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= static_cast<uint64_t>(1) << 46;  // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;  // SWIZZLE_128B
+  return d;
+}
+
+// ---------------------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                         const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                         const GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tmem_full[2], tmem_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int planes = p.split ? 2 : 1;
+  const int stage_bytes = planes * (p.a_tile_bytes + p.b_tile_bytes);
+
+  const int mt = (p.M + kBM - 1) / kBM;
+  const int nt = (p.N + p.BN - 1) / p.BN;
+  const int total_kb = (p.K + kBK - 1) / kBK;
+  const long long units = static_cast<long long>(mt) * nt * p.splits_k;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_hi)));
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b_hi)));
+    if (p.split) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_lo)));
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b_lo)));
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+        const int n_tile = static_cast<int>(u % nt);
+        const int m_tile = static_cast<int>((u / nt) % mt);
+        const int ks = static_cast<int>(u / (static_cast<long long>(nt) * mt));
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + static_cast<size_t>(stage) * stage_bytes;
+          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          for (int pl = 0; pl < planes; ++pl) {
+            const CUtensorMap* ma = pl ? &map_a_lo : &map_a_hi;
+            const CUtensorMap* mb = pl ? &map_b_lo : &map_b_hi;
+            uint8_t* sa = st + pl * p.a_tile_bytes;
+            uint8_t* sb = st + planes * p.a_tile_bytes + pl * p.b_tile_bytes;
+            if (!p.a_mn) {
+              tma_load_2d(sa, ma, &full_bar[stage], kb * kBK, m_tile * kBM);
+            } else {
+              for (int bx = 0; bx < kBM / 64; ++bx)
+                tma_load_2d(sa + bx * (kBK * 128), ma, &full_bar[stage], m_tile * kBM + bx * 64, kb * kBK);
+            }
+            if (!p.b_mn) {
+              tma_load_2d(sb, mb, &full_bar[stage], kb * kBK, n_tile * p.BN);
+            } else {
+              for (int bx = 0; bx < p.b_boxes; ++bx)
+                tma_load_2d(sb + bx * (kBK * 128), mb, &full_bar[stage], n_tile * p.BN + bx * 64, kb * kBK);
+            }
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(p.a_mn) << 15) |
+                             (static_cast<uint32_t>(p.b_mn) << 16) | (static_cast<uint32_t>(p.BN >> 3) << 17) |
+                             (static_cast<uint32_t>(kBM >> 4) << 24);
+      const uint32_t a_lbo = p.a_mn ? kBK * 128 : 16, b_lbo = p.b_mn ? kBK * 128 : 16;
+      const uint32_t a_kstep = p.a_mn ? kUmmaK * 128 : kUmmaK * 2;  // bytes per UMMA_K step
+      const uint32_t b_kstep = p.b_mn ? kUmmaK * 128 : kUmmaK * 2;
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+        const int ks = static_cast<int>(u / (static_cast<long long>(nt) * mt));
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_d = tmem_base + acc * 256;
+        uint32_t accumulate = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t st = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
+          const uint32_t sa_hi = st, sa_lo = st + p.a_tile_bytes;
+          const uint32_t sb_hi = st + planes * p.a_tile_bytes, sb_lo = sb_hi + p.b_tile_bytes;
+          const int passes = p.split ? 3 : 1;
+          for (int ps = 0; ps < passes; ++ps) {
+            const uint32_t sa = (ps == 2) ? sa_lo : sa_hi;   // hi·hi, hi·lo, lo·hi
+            const uint32_t sb = (ps == 1) ? sb_lo : sb_hi;
+#pragma unroll
+            for (int k = 0; k < kBK / kUmmaK; ++k) {
+              const uint64_t da = make_desc(sa + k * a_kstep, a_lbo, 1024);
+              const uint64_t db = make_desc(sb + k * b_kstep, b_lbo, 1024);
+              umma_bf16(tmem_d, da, db, idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage when the MMAs above retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        if (kb1 <= kb0) {
+          // empty K range (possible for the last split): publish a zero tile via the epilogue flag
+        }
+        umma_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+    int acc = 0; uint32_t acc_phase = 0;
+    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+      const int n_tile = static_cast<int>(u % nt);
+      const int m_tile = static_cast<int>((u / nt) % mt);
+      const int ks = static_cast<int>(u / (static_cast<long long>(nt) * mt));
+      const bool empty_k = (ks * p.kb_per_split >= total_kb);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row = m_tile * kBM + ew * 32 + lane;
+      float* drow = p.d + static_cast<long long>(ks) * p.d_split_stride + static_cast<long long>(row) * p.ldd;
+      const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(ew * 32) << 16);
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t r[32];
+        const int width = min(32, p.BN - c0);   // BN is a multiple of 16: width is 32 or 16
+        if (width == 32) tmem_ld32(taddr + c0, r); else tmem_ld16(taddr + c0, r);
+        const int col = n_tile * p.BN + c0;
+        if (row < p.M) {
+          if (col + width <= p.N && (p.ldd & 3) == 0) {
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+              if (v * 4 < width) {
+                float4 o = empty_k ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                   : make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
+                                                 __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+                *reinterpret_cast<float4*>(drow + col + 4 * v) = o;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int v = 0; v < 32; ++v)
+              if (v < width && col + v < p.N) drow[col + v] = empty_k ? 0.f : __uint_as_float(r[v]);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+  }
+}
+
+// ordered split-K reduction: out[i] = sum_s part[s, i]
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, long long n, int splits,
+                                     long long stride) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int k = 0; k < splits; ++k) s += part[k * stride + i];
+  out[i] = s;
+}
+
+// fp32 -> bf16 hi (+ lo residual) planes
+__global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, long long n) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(x + i);
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    store_split_bf16<4>(hi + i, lo ? lo + i : nullptr, f);
+  } else {
+    for (long long k = i; k < n; ++k) {
+      const float f[1] = {x[k]};
+      store_split_bf16<1>(hi + k, lo ? lo + k : nullptr, f);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+    if (q != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// bf16 matrix [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], 128B swizzle
+static int make_map(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return RG_ERR_DRIVER;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? RG_OK : RG_ERR_DRIVER;
+}
+
+static int pick_bn(int N) {
+  if (N <= 256) return (N + 15) / 16 * 16;
+  for (int bn = 256; bn >= 128; bn -= 16)
+    if (N % bn == 0) return bn;
+  return 256;
+}
+
+}  // namespace relgat
+
+using namespace relgat;
+
+extern "C" int relgat_split_bf16(const float* x, void* hi, void* lo, long long n, void* stream) {
+  if (!x || !hi || n < 0) return RG_ERR_ARG;
+  if (n == 0) return RG_OK;
+  if (reinterpret_cast<uintptr_t>(x) % 16 || reinterpret_cast<uintptr_t>(hi) % 8 || (lo && reinterpret_cast<uintptr_t>(lo) % 8))
+    return RG_ERR_ALIGN;
+  const int th = 256;
+  const long long blocks = ((n + 3) / 4 + th - 1) / th;
+  split_bf16_kernel<<<static_cast<unsigned>(blocks), th, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), n);
+  return cuda_status(cudaGetLastError());
+}
+
+extern "C" long long relgat_gemm_workspace_bytes(int M, int N, int K, int a_mn, int b_mn, int splits_k) {
+  (void)K; (void)a_mn; (void)b_mn;
+  if (splits_k <= 1) return 0;
+  return static_cast<long long>(splits_k) * M * N * 4;
+}
+
+// D[M,N] (fp32, row stride ldd) = A · Bᵀ with bf16 operands, fp32 accumulation.
+//   a_mn == 0: A is [M, K] row-major (stride lda);  a_mn == 1: A is stored [K, M] row-major (stride lda)
+//   b_mn == 0: B is [N, K] row-major (stride ldb);  b_mn == 1: B is stored [K, N] row-major (stride ldb)
+//   a_lo / b_lo: residual planes of the fp32 split (both or neither); nullptr = plain bf16 GEMM
+extern "C" int relgat_gemm_bf16(const void* a_hi, const void* a_lo, long long lda, int a_mn,
+                                const void* b_hi, const void* b_lo, long long ldb, int b_mn,
+                                float* d, long long ldd, int M, int N, int K, int splits_k,
+                                void* workspace, long long workspace_bytes, int sm_count, void* stream) {
+  if (!a_hi || !b_hi || !d || M <= 0 || N <= 0 || K <= 0 || splits_k < 1) return RG_ERR_ARG;
+  if ((a_lo == nullptr) != (b_lo == nullptr)) return RG_ERR_ARG;
+  if (lda % 8 || ldb % 8) return RG_ERR_ALIGN;  // TMA: 16-byte global strides
+  if (reinterpret_cast<uintptr_t>(a_hi) % 16 || reinterpret_cast<uintptr_t>(b_hi) % 16 ||
+      reinterpret_cast<uintptr_t>(a_lo) % 16 || reinterpret_cast<uintptr_t>(b_lo) % 16)
+    return RG_ERR_ALIGN;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.BN = pick_bn(N);
+  p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
+  p.split = a_lo ? 1 : 0;
+  const int total_kb = (K + kBK - 1) / kBK;
+  if (splits_k > total_kb) splits_k = total_kb;
+  p.splits_k = splits_k;
+  p.kb_per_split = (total_kb + splits_k - 1) / splits_k;
+  p.a_tile_bytes = kBM * kBK * 2;
+  p.b_boxes = (p.BN + 63) / 64;
+  p.b_tile_bytes = p.b_mn ? p.b_boxes * kBK * 128 : p.BN * kBK * 2;
+  const int planes = p.split ? 2 : 1;
+  const int stage_bytes = planes * (p.a_tile_bytes + p.b_tile_bytes);
+  const int smem_budget = 227 * 1024 - 2048;
+  int stages = smem_budget / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return RG_ERR_SHAPE;
+  p.stages = stages;
+  if (splits_k > 1) {
+    if (!workspace || workspace_bytes < relgat_gemm_workspace_bytes(M, N, K, a_mn, b_mn, splits_k)) return RG_ERR_WORKSPACE;
+    p.d = static_cast<float*>(workspace);
+    p.ldd = N;
+    p.d_split_stride = static_cast<long long>(M) * N;
+  } else {
+    p.d = d; p.ldd = ldd; p.d_split_stride = 0;
+  }
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int rc;
+  // K-major: matrix [MN rows, K cols], box rows = tile MN extent.  MN-major: matrix [K rows, MN cols], box rows = BK.
+  const long long a_rows = p.a_mn ? K : M, a_cols = p.a_mn ? M : K;
+  const long long b_rows = p.b_mn ? K : N, b_cols = p.b_mn ? N : K;
+  const int a_box = p.a_mn ? kBK : kBM, b_box = p.b_mn ? kBK : p.BN;
+  if ((rc = make_map(&ma_hi, a_hi, a_rows, a_cols, lda, a_box)) != RG_OK) return rc;
+  if ((rc = make_map(&mb_hi, b_hi, b_rows, b_cols, ldb, b_box)) != RG_OK) return rc;
+  if (p.split) {
+    if ((rc = make_map(&ma_lo, a_lo, a_rows, a_cols, lda, a_box)) != RG_OK) return rc;
+    if ((rc = make_map(&mb_lo, b_lo, b_rows, b_cols, ldb, b_box)) != RG_OK) return rc;
+  } else {
+    ma_lo = ma_hi; mb_lo = mb_hi;
+  }
+  const long long units = static_cast<long long>((M + kBM - 1) / kBM) * ((N + p.BN - 1) / p.BN) * splits_k;
+  if (sm_count <= 0) sm_count = 148;
+  const int grid = static_cast<int>(units < sm_count ? units : sm_count);
+  const int smem_bytes = stages * stage_bytes + 1024;
+  cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e != cudaSuccess) return cuda_status(e);
+  gemm_bf16_tcgen05_kernel<<<grid, kGemmThreads, smem_bytes, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  if ((e = cudaGetLastError()) != cudaSuccess) return cuda_status(e);
+  if (splits_k > 1) {
+    const long long n = static_cast<long long>(M) * N;
+    if (ldd != N) return RG_ERR_SHAPE;
+    splitk_reduce_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(p.d, d, n, splits_k, p.d_split_stride);
+    return cuda_status(cudaGetLastError());
+  }
+  return RG_OK;
+}

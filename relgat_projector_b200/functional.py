@@ -1,0 +1,155 @@
+"""Autograd wiring of the RelGAT hot path over the sm_100a kernels.
+
+``RelGATStackFunction`` runs L RelGAT layers (with the inter-layer ELU of reference
+core/model/model.py:286-287 fused into the edge kernel's epilogue) as ONE autograd node:
+forward = [split W -> tcgen05 GEMM -> fused edge kernel] per layer, backward = the closed
+form of SURVEY.md §A.2 with the by-source / by-relation passes and the tcgen05 dW / dX GEMMs.
+Nothing here does arithmetic in torch; torch allocates and orders the launches.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import ops
+from .graph import GraphIndex
+
+PRECISIONS = ("fp32", "bf16")
+
+
+class RelGATStackFunction(torch.autograd.Function):
+    """out = RelGAT_L(... ELU(RelGAT_1(x0)) ...) for layers sharing one graph.
+
+    args: x0 [N, D_in] fp32, then per layer (W [H*F, D_in_l], A [H, R, F], beta [R] or None).
+    ``x0_planes`` may carry a cached bf16 split of a frozen x0 (reference model.py:32 keeps the
+    input embeddings as a buffer, so the split is paid once, not per step).
+    """
+
+    @staticmethod
+    def forward(ctx, x0, graph: GraphIndex, heads: int, out_dim: int, precision: str, x0_planes, *params):
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {PRECISIONS}")
+        if len(params) % 3 != 0 or not params:
+            raise ValueError("params must be (W, A, beta) per layer")
+        L = len(params) // 3
+        H, F = heads, out_dim
+        C = H * F
+        N = graph.N
+        with_lo = precision == "fp32"
+        if x0.size(0) != N:
+            raise ValueError(f"node_emb has {x0.size(0)} rows but the graph has {N} nodes")
+        planes = x0_planes if x0_planes is not None else ops.split_bf16(x0, with_lo)
+        saved = []
+        out = None
+        for l in range(L):
+            W, A, beta = params[3 * l], params[3 * l + 1], params[3 * l + 2]
+            d_in = W.size(1)
+            if W.size(0) != C:
+                raise ValueError(f"layer {l}: W must be [{C}, D_in]")
+            Wp = ops.split_bf16(W.detach(), with_lo)
+            P = ops.gemm(planes, False, Wp, False, N, C, d_in)
+            last = l == L - 1
+            out, act, alpha, z, bias = ops.edge_fwd(P, A.detach(), None if beta is None else beta.detach(), graph,
+                                                    H, F, want_act=not last, apply_elu=True, act_lo=with_lo)
+            saved.append(dict(xp=planes, Wp=Wp, P=P, out=out, alpha=alpha, z=z, bias=bias, A=A.detach(),
+                              d_in=d_in, has_beta=beta is not None))
+            planes = act
+        ctx.saved = saved
+        ctx.graph = graph
+        ctx.cfg = (H, F, L, with_lo)
+        ctx.x0_needs_grad = bool(x0.requires_grad)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        H, F, L, with_lo = ctx.cfg
+        g = ctx.graph
+        C = H * F
+        N = g.N
+        grads: List[Optional[torch.Tensor]] = [None] * (3 * L)
+        dY = grad_out.contiguous()
+        owned = False
+        dX = None
+        for l in reversed(range(L)):
+            s = ctx.saved[l]
+            G, t, hsum = ops.edge_bwd_prep(dY, s["out"], s["bias"], H, F, apply_elu=(l < L - 1), inplace=owned)
+            _, dPp, dz = ops.edge_bwd_src(s["P"], G, s["A"], s["alpha"], s["z"], t, g, H, F,
+                                          want_fp32=False, want_planes=True, planes_lo=with_lo)
+            dA, dbeta = ops.edge_bwd_rel(s["P"], dz, hsum, g, H, F, want_dbeta=s["has_beta"])
+            d_in = s["d_in"]
+            splits = ops.pick_splits_k(C, d_in, N, dY.device)
+            dW = ops.gemm(dPp, True, s["xp"], True, C, d_in, N, splits_k=splits)
+            grads[3 * l], grads[3 * l + 1], grads[3 * l + 2] = dW, dA, dbeta
+            if l > 0 or ctx.x0_needs_grad:
+                dX = ops.gemm(dPp, False, s["Wp"], True, N, d_in, C)
+                dY, owned = dX, True
+            del G, dPp, dz
+        ctx.saved = None
+        return (dX if ctx.x0_needs_grad else None, None, None, None, None, None, *grads)
+
+
+def relgat_stack(x0, graph, heads, out_dim, layer_params: Sequence, precision="fp32", x0_planes=None):
+    flat = []
+    for W, A, beta in layer_params:
+        flat += [W, A, beta]
+    return RelGATStackFunction.apply(x0, graph, heads, out_dim, precision, x0_planes, *flat)
+
+
+class GatherScoreFunction(torch.autograd.Function):
+    """scores = scorer(x[src_ids], rel_ids, x[dst_ids]) without materialising the gathers
+    (reference model.py:136-141); optional side outputs: transform rows for the first
+    ``n_transform`` triples (scorer.transform) and the gathered destination rows."""
+
+    @staticmethod
+    def forward(ctx, kind, normalize, x, src_ids, dst_ids, rel_emb, rel_ids, n_transform, want_dst_vec):
+        ctx.set_materialize_grads(False)
+        score, tr, _, dv = ops.score_fwd(kind, normalize, x.detach(), src_ids, x.detach(), dst_ids, rel_emb.detach(),
+                                         rel_ids, n_transform=n_transform, want_dst_vec=want_dst_vec)
+        ctx.save_for_backward(x, src_ids, dst_ids, rel_emb, rel_ids)
+        ctx.meta = (kind, normalize)
+        return score, (tr if tr is not None else x.new_empty((0,))), (dv if dv is not None else x.new_empty((0,)))
+
+    @staticmethod
+    def backward(ctx, dscore, dtr, ddv):
+        x, src_ids, dst_ids, rel_emb, rel_ids = ctx.saved_tensors
+        kind, normalize = ctx.meta
+        need_x, need_r = ctx.needs_input_grad[2], ctx.needs_input_grad[5]
+        d_src, d_dst, d_rel = ops.score_bwd(kind, normalize, x, src_ids, x, dst_ids, rel_emb, rel_ids,
+                                            dscore, dtr, want_src=need_x, want_dst=need_x, want_rel=need_r)
+        dx = drel = None
+        if need_x:
+            if ddv is not None:
+                d_dst = d_dst + ddv
+            dx = ops.index_add_sorted(torch.cat([d_src, d_dst], 0), torch.cat([src_ids, dst_ids], 0), x.size(0))
+        if need_r:
+            drel = ops.index_add_sorted(d_rel, rel_ids, rel_emb.size(0))
+        return None, None, dx, None, None, drel, None, None, None
+
+
+class ScoreRowsFunction(torch.autograd.Function):
+    """Module-level scorer call on already gathered rows (reference scorer.py:58-84, 154-186)
+    and/or the relation operator ``transform`` (scorer.py:86-94, 188-201)."""
+
+    @staticmethod
+    def forward(ctx, kind, normalize, src_emb, dst_emb, rel_emb, rel_ids, want_score, want_transform):
+        ctx.set_materialize_grads(False)
+        B = int(rel_ids.numel())
+        xd = dst_emb if dst_emb is not None else src_emb
+        score, tr, _, _ = ops.score_fwd(kind, normalize, src_emb.detach(), None, xd.detach(), None, rel_emb.detach(),
+                                        rel_ids, n_transform=B if want_transform else 0)
+        ctx.save_for_backward(src_emb, xd, rel_emb, rel_ids)
+        ctx.meta = (kind, normalize, dst_emb is not None)
+        empty = src_emb.new_empty((0,))
+        return (score if want_score else empty), (tr if tr is not None else empty)
+
+    @staticmethod
+    def backward(ctx, dscore, dtr):
+        src_emb, xd, rel_emb, rel_ids = ctx.saved_tensors
+        kind, normalize, has_dst = ctx.meta
+        d_src, d_dst, d_rel = ops.score_bwd(kind, normalize, src_emb, None, xd, None, rel_emb, rel_ids, dscore, dtr,
+                                            want_src=ctx.needs_input_grad[2],
+                                            want_dst=has_dst and ctx.needs_input_grad[3],
+                                            want_rel=ctx.needs_input_grad[4])
+        drel = ops.index_add_sorted(d_rel, rel_ids, rel_emb.size(0)) if d_rel is not None else None
+        return None, None, d_src, d_dst, drel, None, None, None

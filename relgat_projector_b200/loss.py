@@ -1,0 +1,111 @@
+"""Ranking and reconstruction losses over the scorer outputs (reference
+relgat_projector/core/loss/{relgat_loss,multi_objective_loss,cosine,mse}.py).
+
+These act on ``[B]`` / ``[B, K]`` score tensors and ``[B, D]`` rows — a few kilobytes next to the
+full-graph message passing — and are expressed with torch tensor ops; the class names,
+constructor arguments and call signatures match the reference so the reference trainer can use
+either implementation.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+
+class CosineLoss:
+    @staticmethod
+    def calculate(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        """mean(1 - cos(pred, target)) (cosine.py:10-13); broadcasts [B, D] against [K, B, D]."""
+        p = F.normalize(pred, p=2, dim=-1)
+        t = F.normalize(target, p=2, dim=-1)
+        return (1.0 - (p * t).sum(dim=-1)).mean()
+
+
+class MSELoss:
+    @staticmethod
+    def calculate(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        return F.mse_loss(a, b)
+
+
+class RelGATLoss:
+    def __init__(self, loss_type: str, self_adv_alpha: Optional[float], margin: Optional[float],
+                 clamp_limit: Optional[float], run_config: Dict[str, Any]):
+        self.loss_type = loss_type
+        self.clamp_limit = clamp_limit
+        self.margin = run_config.get("margin", margin)
+        if self.margin is not None:
+            self.margin = float(self.margin)
+        self.self_adv_alpha = run_config.get("self_adv_alpha", self_adv_alpha)
+        if self.self_adv_alpha is not None:
+            self.self_adv_alpha = float(self.self_adv_alpha)
+        self.use_self_adv_neg = loss_type == "self_adversarial_loss"
+
+    def prepare_scores_and_compute_loss(self, pos_score: torch.Tensor, neg_score: torch.Tensor) -> torch.Tensor:
+        if self.use_self_adv_neg:
+            return self._self_adversarial_loss(pos_score, neg_score)
+        return self._margin_ranking_loss(pos_score, neg_score)
+
+    def _margin_ranking_loss(self, pos_score, neg_score):
+        """mean_{b,k} relu(margin + neg[b,k] - pos[b]) (relgat_loss.py:51-54)."""
+        return F.relu(self.margin + neg_score - pos_score.unsqueeze(1)).mean()
+
+    def _self_adversarial_loss(self, pos_score, neg_score):
+        """-mean logsig(pos) - mean_b sum_k softmax_k(alpha*neg).detach() * logsig(-neg) (relgat_loss.py:56-71)."""
+        with torch.no_grad():
+            w = torch.softmax(self.self_adv_alpha * neg_score, dim=1)
+        return -F.logsigmoid(pos_score).mean() - (w * F.logsigmoid(-neg_score)).sum(dim=1).mean()
+
+
+class MultiObjectiveRelLoss:
+    """Weighted mean of ranking + positive cosine + (1 - negative cosine) + MSE terms
+    (multi_objective_loss.py:47-83); zero-weight terms leave numerator and denominator."""
+
+    def __init__(self, *, relgat_loss: RelGATLoss, run_config: Dict[str, Any], pos_cosine_weight: float = 1.0,
+                 neg_cosine_weight: float = 1.0, mse_weight: float = 0.0, relgat_weight: float = 1.0):
+        self.ranking_weight = run_config.get("relgat_weight", relgat_weight)
+        self.pos_cosine_weight = run_config.get("pos_cosine_weight", pos_cosine_weight)
+        self.neg_cosine_weight = run_config.get("neg_cosine_weight", neg_cosine_weight)
+        self.mse_weight = run_config.get("mse_weight", mse_weight)
+        self.relgat_loss = relgat_loss
+
+    def relgat_ranking_loss(self, pos_score, neg_score):
+        return self.relgat_loss.prepare_scores_and_compute_loss(pos_score=pos_score, neg_score=neg_score)
+
+    def __call__(self, *, pos_score, neg_score, transformed_src, dst_vec, neg_dst_vec):
+        terms = [
+            (self.ranking_weight, lambda: self.relgat_ranking_loss(pos_score, neg_score)),
+            (self.pos_cosine_weight, lambda: CosineLoss.calculate(transformed_src, dst_vec)),
+            (self.neg_cosine_weight, lambda: 1.0 - CosineLoss.calculate(transformed_src, neg_dst_vec)),
+            (self.mse_weight, lambda: MSELoss.calculate(transformed_src, dst_vec)),
+        ]
+        active = [(w, fn) for w, fn in terms if w != 0.0]
+        if not active:
+            raise ValueError("At least one loss weight must be non-zero.")
+        return torch.stack([w * fn() for w, fn in active]).sum() / sum(w for w, _ in active)
+
+
+def split_scores(scores: torch.Tensor, num_pos: int, num_neg: int, projection_path: bool = False):
+    """Flat scores [B*(1+K)] (positives, then K-major negative blocks — reference
+    trainer/components/relgat_batching.py:5-19) -> (pos [B], neg [B, K]).
+
+    ``projection_path=False``: view(K, B).T (reference trainer/relgat_projector.py:657-676).
+    ``projection_path=True`` : view(B, K), the pairing the reference's projection branch uses
+    (trainer/relgat_projector.py:628-630)."""
+    pos, flat = scores[:num_pos], scores[num_pos:]
+    if projection_path:
+        return pos, flat.view(num_pos, num_neg)
+    return pos, flat.view(num_neg, num_pos).transpose(0, 1).contiguous()
+
+
+def compute_mrr_hits(pos_score: torch.Tensor, neg_score: torch.Tensor, ks, pessimistic: bool = True):
+    """MRR / Hits@k against the sampled negatives, pessimistic ties (reference core/eval.py:8-37)."""
+    if pos_score.shape[0] == 0:
+        return 0.0, {k: 0.0 for k in ks}
+    p = torch.nan_to_num(pos_score, nan=-1e9, neginf=-1e9, posinf=1e9)
+    q = torch.nan_to_num(neg_score, nan=-1e9, neginf=-1e9, posinf=1e9)
+    worse = (q >= p.unsqueeze(1)) if pessimistic else (q > p.unsqueeze(1))
+    ranks = 1.0 + worse.to(p.dtype).sum(dim=1)
+    mrr = (1.0 / torch.clamp(ranks, min=1.0)).mean().item()
+    return mrr, {k: (ranks <= float(k)).to(p.dtype).mean().item() for k in ks}

@@ -1,0 +1,197 @@
+"""Drop-in ``RelGATModel`` (reference relgat_projector/core/model/model.py:13-292): frozen node
+embeddings -> L RelGAT layers (+ELU between) -> optional ProjectionHead -> KG scorer, with the
+GAT stack and the gather-score fused over the sm_100a kernels."""
+from __future__ import annotations
+
+import json
+import os
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import functional as RF
+from . import ops
+from .graph import get_graph_index
+from .layer import RelGATLayer
+from .projection import ProjectionHead
+from .scorer import DistMultScorer, TransEScorer
+
+
+class RelGATModel(nn.Module):
+    def __init__(
+        self,
+        node_emb: torch.Tensor,  # [N, D_in] frozen
+        edge_index: torch.Tensor,  # [2, E]
+        edge_type: torch.Tensor,  # [E]
+        num_rel: int,
+        scorer_type: str = "distmult",
+        gat_out_dim: int = 200,
+        gat_heads: int = 4,
+        dropout: float = 0.2,
+        relation_attn_dropout: float = 0.0,
+        gat_num_layers: int = 1,
+        project_to_input_size: bool = False,
+        projection_layers: int = 1,
+        projection_dropout: float = 0.0,
+        projection_hidden_dim: int = 0,
+        precision: str = "fp32",
+    ):
+        super().__init__()
+        self.register_buffer("node_emb_fixed", node_emb)  # buffer, saved in state_dict (model.py:32)
+        self.edge_index = edge_index  # plain attributes like the reference (model.py:34-35)
+        self.edge_type = edge_type
+        self.num_rel = num_rel
+        self.gat_num_layers = gat_num_layers
+        self.projection_layers = projection_layers
+        self.project_to_input_size = project_to_input_size
+        self.precision = precision
+        if project_to_input_size and self.projection_layers < 1:
+            raise ValueError("projection_layers must be >= 1 when project_to_input_size=True")
+        self._config = dict(
+            input_dim=int(node_emb.size(1)), num_rel=int(num_rel), scorer_type=str(scorer_type),
+            gat_out_dim=int(gat_out_dim), gat_heads=int(gat_heads), dropout=float(dropout),
+            relation_attn_dropout=float(relation_attn_dropout), gat_num_layers=int(gat_num_layers),
+            project_to_input_size=bool(project_to_input_size), projection_layers=int(projection_layers),
+            projection_dropout=float(projection_dropout), projection_hidden_dim=int(projection_hidden_dim),
+        )
+
+        def make_layer(in_dim):
+            return RelGATLayer(in_dim=in_dim, out_dim=gat_out_dim, num_rel=num_rel, heads=gat_heads,
+                               dropout=dropout, relation_attn_dropout=relation_attn_dropout, use_bias=True,
+                               precision=precision)
+
+        if gat_num_layers == 1:  # attribute names follow the reference (model.py:44-73)
+            self.gat_layer = make_layer(node_emb.size(1))
+            self.act = None
+        else:
+            self.gat_layers = nn.ModuleList()
+            in_dim = node_emb.size(1)
+            for _ in range(max(1, gat_num_layers)):
+                self.gat_layers.append(make_layer(in_dim))
+                in_dim = gat_out_dim * gat_heads
+            self.act = nn.ELU()
+
+        scorer_dim = gat_out_dim * gat_heads
+        if self.project_to_input_size:
+            self.projection = ProjectionHead(in_dim=scorer_dim, out_dim=node_emb.size(1),
+                                             hidden_dim=projection_hidden_dim, num_layers=self.projection_layers,
+                                             dropout=projection_dropout)
+            scorer_dim = node_emb.size(1)
+        else:
+            self.projection = None
+
+        self.scorer_type = scorer_type
+        if scorer_type.lower() == "distmult":
+            self.scorer = DistMultScorer(num_rel, rel_dim=scorer_dim)
+        elif scorer_type.lower() == "transe":
+            self.scorer = TransEScorer(num_rel, rel_dim=scorer_dim, normalize=True)
+        else:
+            raise ValueError(f"Unknown scorer_type: {scorer_type}")
+        self._x0_planes = None  # cached bf16 split of the frozen input embeddings
+
+    # -- helpers ------------------------------------------------------------------------------
+    def _layers(self) -> List[RelGATLayer]:
+        return [self.gat_layer] if self.gat_num_layers == 1 else list(self.gat_layers)
+
+    def _input_planes(self):
+        x = self.node_emb_fixed
+        key = (x.data_ptr(), x._version, tuple(x.shape), self.precision)
+        if self._x0_planes is None or self._x0_planes[0] != key:
+            self._x0_planes = (key, ops.split_bf16(x, with_lo=(self.precision == "fp32")))
+        return self._x0_planes[1]
+
+    def _graph(self):
+        return get_graph_index(self.edge_index, self.edge_type, self.node_emb_fixed.size(0), self.num_rel)
+
+    # -- reference API ------------------------------------------------------------------------
+    def single_gat_step(self) -> torch.Tensor:
+        """Full-graph node representations, optionally projected (reference model.py:274-292)."""
+        layers = self._layers()
+        for lyr in layers:
+            lyr.check_supported()
+        inter_dropout = self.training and any(lyr.dropout.p > 0.0 for lyr in layers[:-1])
+        if not inter_dropout:
+            # one autograd node for the whole stack; ELU between layers fused into the edge kernel
+            x = RF.relgat_stack(self.node_emb_fixed, self._graph(), layers[0].heads, layers[0].out_dim,
+                                [lyr.kernel_params() for lyr in layers], precision=self.precision,
+                                x0_planes=self._input_planes())
+            x = layers[-1].dropout(x)
+        else:
+            x = self.node_emb_fixed
+            for li, gat in enumerate(layers):
+                x = gat(x, self.edge_index, self.edge_type)
+                if self.act is not None and li < len(layers) - 1:
+                    x = self.act(x)
+        if self.project_to_input_size:
+            x = self.projection(x)
+        return x
+
+    def forward(self, src_ids: torch.Tensor, rel_ids: torch.Tensor, dst_ids: torch.Tensor,
+                transform_to_input_if_possible: bool = True
+                ) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
+        """Scores for a batch of triples (reference model.py:99-142): returns
+        (scores [B], transformed [B, D_sc] or None, dst_vec [B, D_sc])."""
+        x = self.single_gat_step()
+        want_tr = self.project_to_input_size and transform_to_input_if_possible
+        scores, transformed, dst_vec = self.scorer.gather_score(
+            x, src_ids, rel_ids, dst_ids, n_transform=int(src_ids.numel()) if want_tr else 0, want_dst_vec=True)
+        return scores, (transformed if want_tr else None), dst_vec
+
+    @torch.no_grad()
+    def get_node_repr(self) -> torch.Tensor:
+        return self.single_gat_step()
+
+    @torch.no_grad()
+    def transform(self, src_ids: torch.Tensor, rel_ids: torch.Tensor) -> torch.Tensor:
+        x = self.single_gat_step()
+        return self.transform_from_vectors(src_vectors=x[src_ids], rel_ids=rel_ids)
+
+    @torch.no_grad()
+    def transform_from_vectors(self, src_vectors: torch.Tensor, rel_ids: torch.Tensor) -> torch.Tensor:
+        if rel_ids.dim() == 0:
+            rel_ids = rel_ids.view(1)
+        if rel_ids.numel() == 1 and src_vectors.size(0) > 1:
+            rel_ids = rel_ids.expand(src_vectors.size(0))
+        return self.scorer.transform(src_vectors, rel_ids)
+
+    def get_config(self) -> dict:
+        """Constructor arguments needed to rebuild the model (the reference reads an attribute it
+        never assigns, model.py:188-194; here it is populated so save/load round-trips)."""
+        return dict(self._config)
+
+    def save_pretrained(self, output_dir: str, add_files: Optional[List[Tuple[str, Dict[str, Any]]]] = None) -> None:
+        add_files = [] if add_files is None else list(add_files)
+        os.makedirs(output_dir, exist_ok=True)
+        add_files.append(("config.json", self.get_config()))
+        for name, content in add_files:
+            with open(os.path.join(output_dir, name), "w", encoding="utf-8") as f:
+                json.dump(content, f, ensure_ascii=False, indent=2)
+        torch.save(self.state_dict(), os.path.join(output_dir, "pytorch_model.bin"))
+
+    @staticmethod
+    def load_from_pretrained(input_dir: str, *, node_emb: Optional[torch.Tensor] = None,
+                             edge_index: Optional[torch.Tensor] = None, edge_type: Optional[torch.Tensor] = None,
+                             map_location=None, precision: str = "fp32") -> "RelGATModel":
+        cfg_path = os.path.join(input_dir, "config.json")
+        w_path = os.path.join(input_dir, "pytorch_model.bin")
+        if not os.path.isfile(cfg_path):
+            raise FileNotFoundError(f"Config file not found: {cfg_path}")
+        if not os.path.isfile(w_path):
+            raise FileNotFoundError(f"Weights file not found: {w_path}")
+        with open(cfg_path, "r", encoding="utf-8") as f:
+            cfg = json.load(f)
+        if int(cfg.get("input_dim")) != int(node_emb.size(1)):
+            raise ValueError(f"Input dim mismatch: config={cfg.get('input_dim')} vs node_emb={node_emb.size(1)}")
+        model = RelGATModel(
+            node_emb=node_emb, edge_index=edge_index, edge_type=edge_type, num_rel=int(cfg["num_rel"]),
+            scorer_type=str(cfg["scorer_type"]), gat_out_dim=int(cfg["gat_out_dim"]),
+            gat_heads=int(cfg["gat_heads"]), dropout=float(cfg["dropout"]),
+            relation_attn_dropout=float(cfg["relation_attn_dropout"]), gat_num_layers=int(cfg["gat_num_layers"]),
+            project_to_input_size=bool(cfg["project_to_input_size"]), projection_layers=int(cfg["projection_layers"]),
+            projection_dropout=float(cfg["projection_dropout"]),
+            projection_hidden_dim=int(cfg["projection_hidden_dim"]), precision=precision)
+        state = torch.load(w_path, map_location=map_location)
+        model.load_state_dict(state, strict=True)
+        model.eval()
+        return model

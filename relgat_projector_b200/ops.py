@@ -1,0 +1,246 @@
+"""Thin tensor-level wrappers over the C ABI (one function per entry point).
+
+PyTorch is plumbing here: it owns device memory and streams.  Every function launches on the
+current stream of the tensors' device and returns torch tensors; no arithmetic is done in
+torch.  CPU tensors are rejected (no fallback).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from .graph import GraphIndex
+
+Planes = Tuple[torch.Tensor, Optional[torch.Tensor]]  # (hi, lo) bf16 planes of an fp32 matrix
+
+SCORER_KIND = {"distmult": 0, "transe": 1}
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    _lib.require_cuda(t)
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def sm_count(device) -> int:
+    return torch.cuda.get_device_properties(device).multi_processor_count
+
+
+# ------------------------------------------------------------------------------------------
+# dense transforms
+# ------------------------------------------------------------------------------------------
+def split_bf16(x: torch.Tensor, with_lo: bool = True) -> Planes:
+    """fp32 matrix -> bf16 (hi, lo) planes, hi = rn(x), lo = rn(x - hi)."""
+    x = _f32c(x, "x")
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if with_lo else None
+    with torch.cuda.device(x.device):
+        rc = _lib.load().relgat_split_bf16(_lib.ptr(x), _lib.ptr(hi), _lib.ptr(lo), x.numel(), _stream(x))
+    _lib.check(rc, "relgat_split_bf16")
+    return hi, lo
+
+
+def gemm(a: Planes, a_mn: bool, b: Planes, b_mn: bool, M: int, N: int, K: int,
+         splits_k: int = 1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """D[M, N] fp32 = A · Bᵀ on tcgen05.  Operands are 2-D bf16 planes:
+    a_mn False: A stored [M, K]; True: stored [K, M].  Same for B with N."""
+    a_hi, a_lo = a
+    b_hi, b_lo = b
+    _lib.require_cuda(a_hi, b_hi)
+    for t in (a_hi, a_lo, b_hi, b_lo):
+        if t is not None and (t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1):
+            raise TypeError("gemm operands must be 2-D bf16 tensors with unit inner stride")
+    exp_a = (K, M) if a_mn else (M, K)
+    exp_b = (K, N) if b_mn else (N, K)
+    if tuple(a_hi.shape) != exp_a or tuple(b_hi.shape) != exp_b:
+        raise ValueError(f"gemm shapes: A {tuple(a_hi.shape)} != {exp_a} or B {tuple(b_hi.shape)} != {exp_b}")
+    if (a_lo is None) != (b_lo is None):
+        raise ValueError("either both operands carry a lo plane (fp32-parity mode) or neither")
+    dev = a_hi.device
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    ws = None
+    ws_bytes = 0
+    if splits_k > 1:
+        ws_bytes = int(lib.relgat_gemm_workspace_bytes(M, N, K, int(a_mn), int(b_mn), splits_k))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.relgat_gemm_bf16(
+            _lib.ptr(a_hi), _lib.ptr(a_lo), a_hi.stride(0), int(a_mn),
+            _lib.ptr(b_hi), _lib.ptr(b_lo), b_hi.stride(0), int(b_mn),
+            _lib.ptr(out), out.stride(0), M, N, K, splits_k, _lib.ptr(ws), ws_bytes, sm_count(dev), _stream(out))
+    _lib.check(rc, "relgat_gemm_bf16")
+    return out
+
+
+def pick_splits_k(M: int, N: int, K: int, device) -> int:
+    """Split-K factor that fills the SMs when the output has few tiles (the dW GEMM)."""
+    bn = (N + 15) // 16 * 16 if N <= 256 else next((b for b in range(256, 127, -16) if N % b == 0), 256)
+    tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
+    kb = (K + 63) // 64
+    return max(1, min(kb, sm_count(device) // max(tiles, 1)))
+
+
+# ------------------------------------------------------------------------------------------
+# edge kernels
+# ------------------------------------------------------------------------------------------
+def edge_fwd(P: torch.Tensor, A: torch.Tensor, beta: Optional[torch.Tensor], g: GraphIndex, H: int, F: int,
+             want_act: bool = False, apply_elu: bool = False, act_lo: bool = True, want_out: bool = True):
+    """Returns (out [N, H*F] fp32 or None, act planes or None, alpha [E,H], z [E,H], bias [N])."""
+    P = _f32c(P, "P")
+    A = _f32c(A, "A")
+    if beta is not None:
+        beta = _f32c(beta, "beta")
+    dev = P.device
+    N, E, R, C = g.N, g.E, g.R, H * F
+    if P.dim() != 2 or P.size(1) != C:
+        raise ValueError(f"P must be [N_src, {C}]")
+    if tuple(A.shape) != (H, R, F):
+        raise ValueError(f"A must be [{H}, {R}, {F}], got {tuple(A.shape)}")
+    out = torch.empty((N, C), dtype=torch.float32, device=dev) if want_out else None
+    hi = torch.empty((N, C), dtype=torch.bfloat16, device=dev) if want_act else None
+    lo = torch.empty((N, C), dtype=torch.bfloat16, device=dev) if (want_act and act_lo) else None
+    alpha = torch.empty((E, H), dtype=torch.float32, device=dev)
+    z = torch.empty((E, H), dtype=torch.float32, device=dev)
+    bias = torch.empty((N,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().relgat_layer_fwd(
+            _lib.ptr(P), 0, P.stride(0), _lib.ptr(A), _lib.ptr(beta),
+            _lib.ptr(g.rowptr), _lib.ptr(g.csr_src), _lib.ptr(g.csr_rel),
+            _lib.ptr(out), _lib.ptr(hi), _lib.ptr(lo), int(apply_elu),
+            _lib.ptr(alpha), _lib.ptr(z), _lib.ptr(bias), N, H, F, R, 0, _stream(P))
+    _lib.check(rc, "relgat_layer_fwd")
+    return out, ((hi, lo) if want_act else None), alpha, z, bias
+
+
+def edge_bwd_prep(dY: torch.Tensor, out: torch.Tensor, bias: torch.Tensor, H: int, F: int,
+                  apply_elu: bool, inplace: bool = False):
+    """Returns (G [N,C], t [N,H], hsum [N,H])."""
+    dY = _f32c(dY, "dY")
+    out = _f32c(out, "out")
+    N = out.size(0)
+    G = dY if inplace else torch.empty_like(dY)
+    t = torch.empty((N, H), dtype=torch.float32, device=dY.device)
+    hsum = torch.empty((N, H), dtype=torch.float32, device=dY.device)
+    with torch.cuda.device(dY.device):
+        rc = _lib.load().relgat_layer_bwd_prep(_lib.ptr(dY), _lib.ptr(out), _lib.ptr(bias), _lib.ptr(G), _lib.ptr(t),
+                                               _lib.ptr(hsum), N, H, F, int(apply_elu), _stream(dY))
+    _lib.check(rc, "relgat_layer_bwd_prep")
+    return G, t, hsum
+
+
+def edge_bwd_src(P, G, A, alpha, z, t, g: GraphIndex, H: int, F: int, want_fp32: bool = True,
+                 want_planes: bool = False, planes_lo: bool = True):
+    """Returns (dP fp32 or None, dP planes or None, dz [E,H])."""
+    P = _f32c(P, "P")
+    G = _f32c(G, "G")
+    A = _f32c(A, "A")
+    dev = P.device
+    n_src, C = P.size(0), H * F
+    dP = torch.empty((n_src, C), dtype=torch.float32, device=dev) if want_fp32 else None
+    hi = torch.empty((n_src, C), dtype=torch.bfloat16, device=dev) if want_planes else None
+    lo = torch.empty((n_src, C), dtype=torch.bfloat16, device=dev) if (want_planes and planes_lo) else None
+    dz = torch.empty((g.E, H), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().relgat_layer_bwd_src(
+            _lib.ptr(P), P.stride(0), _lib.ptr(G), _lib.ptr(A), _lib.ptr(alpha), _lib.ptr(z), _lib.ptr(t),
+            _lib.ptr(g.colptr), _lib.ptr(g.csc_slot), _lib.ptr(g.csc_dst), _lib.ptr(g.csc_rel),
+            _lib.ptr(dP), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dz), n_src, H, F, g.R, 0, _stream(P))
+    _lib.check(rc, "relgat_layer_bwd_src")
+    return dP, ((hi, lo) if want_planes else None), dz
+
+
+def edge_bwd_rel(P, dz, hsum, g: GraphIndex, H: int, F: int, want_dbeta: bool = True):
+    """Returns (dA [H,R,F], dbeta [R] or None)."""
+    P = _f32c(P, "P")
+    dev = P.device
+    C = H * F
+    partA = torch.empty((max(g.n_chunks, 1), C), dtype=torch.float32, device=dev)
+    partB = torch.empty((max(g.n_chunks, 1),), dtype=torch.float32, device=dev)
+    dA = torch.empty((H, g.R, F), dtype=torch.float32, device=dev)
+    dbeta = torch.empty((g.R,), dtype=torch.float32, device=dev) if want_dbeta else None
+    with torch.cuda.device(dev):
+        rc = _lib.load().relgat_layer_bwd_rel(
+            _lib.ptr(P), P.stride(0), _lib.ptr(dz), _lib.ptr(hsum), _lib.ptr(g.rel_slot), _lib.ptr(g.csr_src),
+            _lib.ptr(g.csr_dst), _lib.ptr(g.chunk_lo), _lib.ptr(g.chunk_hi), _lib.ptr(g.rel_chunk_ptr),
+            g.n_chunks, _lib.ptr(partA), _lib.ptr(partB), _lib.ptr(dA), _lib.ptr(dbeta), H, F, g.R, _stream(P))
+    _lib.check(rc, "relgat_layer_bwd_rel")
+    return dA, dbeta
+
+
+# ------------------------------------------------------------------------------------------
+# scorers
+# ------------------------------------------------------------------------------------------
+def _ids(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    _lib.require_cuda(t)
+    if t.dtype != torch.int64:
+        raise TypeError(f"{name} must be int64")
+    return t.contiguous()
+
+
+def score_fwd(kind: str, normalize: bool, xs, src_idx, xd, dst_idx, rel_emb, rel_ids, *,
+              n_transform: int = 0, want_src_vec: bool = False, want_dst_vec: bool = False):
+    xs, xd, rel_emb = _f32c(xs, "xs"), _f32c(xd, "xd"), _f32c(rel_emb, "rel_emb")
+    src_idx, dst_idx, rel_ids = _ids(src_idx, "src_idx"), _ids(dst_idx, "dst_idx"), _ids(rel_ids, "rel_ids")
+    B, D = int(rel_ids.numel()), int(rel_emb.size(1))
+    dev = xs.device
+    score = torch.empty((B,), dtype=torch.float32, device=dev)
+    tr = torch.empty((n_transform, D), dtype=torch.float32, device=dev) if n_transform > 0 else None
+    sv = torch.empty((B, D), dtype=torch.float32, device=dev) if want_src_vec else None
+    dv = torch.empty((B, D), dtype=torch.float32, device=dev) if want_dst_vec else None
+    with torch.cuda.device(dev):
+        rc = _lib.load().relgat_score_fwd(
+            SCORER_KIND[kind], int(normalize), _lib.ptr(xs), _lib.ptr(src_idx), _lib.ptr(xd), _lib.ptr(dst_idx),
+            _lib.ptr(rel_emb), _lib.ptr(rel_ids), B, D, _lib.ptr(score), _lib.ptr(tr), n_transform,
+            _lib.ptr(sv), _lib.ptr(dv), _stream(xs))
+    _lib.check(rc, "relgat_score_fwd")
+    return score, tr, sv, dv
+
+
+def score_bwd(kind: str, normalize: bool, xs, src_idx, xd, dst_idx, rel_emb, rel_ids, dscore, dtransform, *,
+              want_src: bool = True, want_dst: bool = True, want_rel: bool = True):
+    xs, xd, rel_emb = _f32c(xs, "xs"), _f32c(xd, "xd"), _f32c(rel_emb, "rel_emb")
+    B, D = int(rel_ids.numel()), int(rel_emb.size(1))
+    dev = xs.device
+    if dscore is not None:
+        dscore = _f32c(dscore, "dscore")
+    n_tr = 0
+    if dtransform is not None:
+        dtransform = _f32c(dtransform, "dtransform")
+        n_tr = int(dtransform.size(0))
+    mk = lambda w: torch.empty((B, D), dtype=torch.float32, device=dev) if w else None  # noqa: E731
+    d_src, d_dst, d_rel = mk(want_src), mk(want_dst), mk(want_rel)
+    with torch.cuda.device(dev):
+        rc = _lib.load().relgat_score_bwd(
+            SCORER_KIND[kind], int(normalize), _lib.ptr(xs), _lib.ptr(src_idx), _lib.ptr(xd), _lib.ptr(dst_idx),
+            _lib.ptr(rel_emb), _lib.ptr(rel_ids), B, D, _lib.ptr(dscore), _lib.ptr(dtransform), n_tr,
+            _lib.ptr(d_src), _lib.ptr(d_dst), _lib.ptr(d_rel), _stream(xs))
+    _lib.check(rc, "relgat_score_bwd")
+    return d_src, d_dst, d_rel
+
+
+def index_add_sorted(rows: torch.Tensor, keys: torch.Tensor, n_out: int, out: Optional[torch.Tensor] = None):
+    """out[k] (+)= ordered sum of rows whose key == k.  ``keys`` int64 [M]; rows [M, D]."""
+    rows = _f32c(rows, "rows")
+    M, D = rows.shape
+    accumulate = out is not None
+    if out is None:
+        out = torch.zeros((n_out, D), dtype=torch.float32, device=rows.device)
+    if M == 0:
+        return out
+    sorted_keys, perm = torch.sort(keys, stable=True)  # plumbing: stable order = deterministic sum order
+    with torch.cuda.device(rows.device):
+        rc = _lib.load().relgat_index_add_sorted(_lib.ptr(rows), _lib.ptr(perm), _lib.ptr(sorted_keys), _lib.ptr(out),
+                                                 M, D, int(accumulate), _stream(rows))
+    _lib.check(rc, "relgat_index_add_sorted")
+    return out
