@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""Benchmark of the RelGAT message-passing hot path (BASELINE.json metric: train edges/s, fwd+bwd).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config c2] [--precision fp32]
+
+One "step" = one full training step of the hot path over one batch: full-graph GAT forward
+(L layers), fused gather-score of B*(1+K) triples, margin-ranking loss, backward to every
+parameter gradient and the Adam update (reference trainer/relgat_projector.py:442-469).
+``value`` = message-passing edges processed per second by the whole job = E / t_step.
+
+Rank 0 prints ONE JSON line.  ``--impl reference`` times the CPU restatement of the reference's
+own torch/torch_scatter path (oracle/relgat_oracle.py, kind "port": the reference itself is not
+present on the GPU box) on the host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "relgat_train_edges_per_sec_fwd_bwd"
+UNIT = "edges/s"
+CPU_SAMPLE_SCALE = 20  # the CPU arms run the named config at 1/20 of the nodes and edges
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=float(p["hbm_gbs"]), tflops=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                    source="measured (MEASURED_PEAKS.json; sustained bf16 figure: kernel timed inside a long step)")
+    return dict(hbm_gbs=6650.0, tflops=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# per-kernel event timing (monkeypatches the ops wrappers for a few extra steps)
+# ---------------------------------------------------------------------------------------------
+class KernelProfiler:
+    NAMES = ["split_bf16", "gemm", "edge_fwd", "edge_bwd_prep", "edge_bwd_src", "edge_bwd_rel", "score_fwd",
+             "score_bwd", "index_add_sorted"]
+
+    def __init__(self):
+        from relgat_projector_b200 import ops
+        self.ops = ops
+        self.records = []  # (name, tag, start, end)
+        self.orig = {}
+
+    def __enter__(self):
+        for name in self.NAMES:
+            fn = getattr(self.ops, name)
+            self.orig[name] = fn
+            setattr(self.ops, name, self._wrap(name, fn))
+        return self
+
+    def _wrap(self, name, fn):
+        def wrapped(*a, **kw):
+            tag = name
+            if name == "gemm":
+                tag = f"gemm[M={a[4]},N={a[5]},K={a[6]},{'mn' if a[1] else 'k'}{'mn' if a[3] else 'k'}]"
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = fn(*a, **kw)
+            e.record()
+            self.records.append((name, tag, s, e))
+            return out
+        return wrapped
+
+    def __exit__(self, *exc):
+        for name, fn in self.orig.items():
+            setattr(self.ops, name, fn)
+
+    def table(self, steps: int):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, tag, s, e in self.records:
+            d = agg.setdefault(tag, {"kernel": name, "calls": 0, "ms": 0.0})
+            d["calls"] += 1
+            d["ms"] += s.elapsed_time(e)
+        for d in agg.values():
+            d["ms_per_step"] = d["ms"] / steps
+            d["avg_ms"] = d["ms"] / d["calls"]
+        return agg
+
+
+# ---------------------------------------------------------------------------------------------
+# algorithmic bytes / flops (SURVEY.md §8(d) conventions; stated in DESIGN.md)
+# ---------------------------------------------------------------------------------------------
+def kernel_work(cfg, E, n_chunks, precision):
+    N, H, F, R = cfg["N"], cfg["H"], cfg["F"], cfg["R"]
+    C = H * F
+    s = 4
+    plane_b = 4 if precision == "fp32" else 2  # bytes per element of the bf16 (hi[, lo]) planes
+    w = {
+        # gathers P[src] + (src, rel) ids; writes out, act planes, alpha and z; rowptr and bias
+        "edge_fwd": E * (C * s + 8) + N * (C * s + 4 + 4) + 2 * E * H * 4,
+        "edge_fwd_act": N * C * plane_b,
+        # own P row + gather G[dst] + (slot, dst, rel) ids + alpha, z, t; writes dP planes and dz
+        "edge_bwd_src": N * C * s + E * (C * s + 12 + 3 * H * 4) + N * C * plane_b + E * H * 4,
+        # gathers P[src] + (slot, src, dst) ids + dz + hsum; writes chunk partials
+        "edge_bwd_rel": E * (C * s + 12 + 2 * H * 4) + n_chunks * C * s * 2,
+        "edge_bwd_prep": 2 * N * C * s + 2 * N * H * 4,
+    }
+    return w
+
+
+def step_bytes_survey(cfg, E, precision):
+    """bytes_step of SURVEY.md §8(d): sum over layers of FWD_l + BWD_l (s = 4 bytes)."""
+    N, H, F, L, D = cfg["N"], cfg["H"], cfg["F"], cfg["L"], cfg["D_in"]
+    C, s, tot = H * F, 4, 0
+    for l in range(L):
+        d_in = D if l == 0 else C
+        fwd = N * d_in * s + N * C * s + E * (C * s + 8) + N * (C * s + 4)
+        bwd = E * (2 * C * s + 16 + 8 * H) + N * 2 * C * s + N * (d_in * s + C * s)
+        if l > 0:
+            bwd += N * (C * s + d_in * s)
+        tot += fwd + bwd
+    return tot
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference path on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_port_setup(cfg, scale, seed=42):
+    from relgat_projector_b200 import synthetic as S
+    from relgat_projector_b200.layer import RelGATLayer
+    n, t = max(cfg["N"] // scale, 64), max(cfg["T"] // scale, 256)
+    kg = S.tensor_kg(n, t, cfg["R"], cfg["D_in"], seed=seed, device="cpu")
+    torch.manual_seed(seed)
+    H, F, L = cfg["H"], cfg["F"], cfg["L"]
+    layers, in_dim = [], cfg["D_in"]
+    for _ in range(L):
+        lyr = RelGATLayer(in_dim, F, cfg["R"], heads=H, dropout=0.0)  # same init as the product / reference
+        layers.append({"W": [p.weight for p in lyr.proj], "A": list(lyr.attn_vec), "beta": lyr.rel_bias})
+        in_dim = H * F
+    rel_emb = torch.nn.Parameter(torch.empty(cfg["R"], H * F))
+    torch.nn.init.xavier_uniform_(rel_emb)
+    params = [p for lp in layers for p in (*lp["W"], *lp["A"], lp["beta"])] + [rel_emb]
+    opt = torch.optim.Adam(params, lr=2e-4)
+    g = torch.Generator().manual_seed(seed)
+    return kg, layers, rel_emb, params, opt, g
+
+
+def cpu_port_step(cfg, kg, layers, rel_emb, opt, g):
+    from oracle import relgat_oracle as O  # bench.py's cpu_baseline / --impl reference legs only
+    from relgat_projector_b200 import synthetic as S
+    b, k = cfg["B"], cfg["K"]
+    src, rel, dst = S.sample_batch(kg.train_triples, kg.node_emb.size(0), b, k, g)
+    opt.zero_grad(set_to_none=True)
+    loss, _, _ = O.train_step_port(kg.node_emb, layers, rel_emb, kg.edge_index, kg.edge_type, src, rel, dst,
+                                   scorer=cfg["scorer"], b=b, k=k, margin=1.0)
+    loss.backward()
+    opt.step()
+    return float(loss.detach())
+
+
+def run_cpu_port(cfg, steps, warmup, scale):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    kg, layers, rel_emb, params, opt, g = cpu_port_setup(cfg, scale)
+    E = int(kg.edge_index.size(1))
+    for _ in range(warmup):
+        cpu_port_step(cfg, kg, layers, rel_emb, opt, g)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_port_step(cfg, kg, layers, rel_emb, opt, g)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    sample = (f"{cfg['name']} at 1/{scale} scale: N={kg.node_emb.size(0)} nodes, E={E} edges, R={cfg['R']}, "
+              f"D_in={cfg['D_in']}, L={cfg['L']}, H={cfg['H']}, F={cfg['F']}, B={cfg['B']}, K={cfg['K']}; "
+              f"{warmup} warm-up + {steps} timed steps, fp32, torch {torch.__version__} CPU")
+    return dict(value=E / dt, unit=UNIT, cores=cores, kind="port", sample=sample, ms_per_step=dt * 1e3, edges=E)
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=None, help="c1|c2|c3|c4|tiny (default: c2 on 1 GPU, c4 sharded on >1)")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=3)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from relgat_projector_b200 import synthetic as S
+    cfg_name = args.config or "c2"
+    cfg = dict(S.CONFIGS[cfg_name], name=cfg_name)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        scale = CPU_SAMPLE_SCALE if cfg["N"] >= 100_000 else 1
+        r = run_cpu_port(cfg, args.steps, max(args.warmup, 1), scale)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": f"{cfg_name}: synthetic KG {cfg['N']} nodes / {cfg['T']} triplets, bounded sample",
+                       "precision": "fp32", "sample": r["sample"]},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device: there is no CPU fallback")
+    if world > 1:
+        from relgat_projector_b200 import dist as RD  # destination-range partitioned path
+        return RD.bench_main(args, cfg, rank, world, local_rank, METRIC, UNIT, load_peaks, ClockSampler)
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    import relgat_projector_b200 as R
+    from relgat_projector_b200 import loss as L, ops
+
+    kg = S.tensor_kg(cfg["N"], cfg["T"], cfg["R"], cfg["D_in"], seed=42, device=str(dev))
+    E = int(kg.edge_index.size(1))
+    torch.manual_seed(42)
+    model = R.RelGATModel(kg.node_emb, kg.edge_index, kg.edge_type, num_rel=cfg["R"], scorer_type=cfg["scorer"],
+                          gat_out_dim=cfg["F"], gat_heads=cfg["H"], dropout=0.0, gat_num_layers=cfg["L"],
+                          project_to_input_size=cfg["proj"], projection_layers=2, precision=args.precision).to(dev)
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=2e-4)
+    rank_loss = L.RelGATLoss("margin", None, 1.0, None, {})
+    b, k = cfg["B"], cfg["K"]
+    gen = torch.Generator().manual_seed(42)
+    n_pool = 8
+    host_batches = [tuple(t.pin_memory() for t in S.sample_batch(kg.train_triples.cpu(), cfg["N"], b, k, gen))
+                    for _ in range(n_pool)]
+    dev_batches = [tuple(t.to(dev) for t in hb) for hb in host_batches]
+
+    def train_step(src, rel, dst):
+        opt.zero_grad(set_to_none=True)
+        if not cfg["proj"]:
+            scores, _, _ = model(src, rel, dst, transform_to_input_if_possible=False)
+            pos, neg = L.split_scores(scores, b, k)
+            loss = rank_loss.prepare_scores_and_compute_loss(pos, neg)
+        else:
+            scores, tr, dst_vec = model(src, rel, dst)
+            pos, neg = L.split_scores(scores, b, k, projection_path=True)
+            multi = L.MultiObjectiveRelLoss(relgat_loss=rank_loss, run_config={})
+            ndv = dst_vec[b:].view(b, k, -1).permute(1, 0, 2).contiguous()
+            loss = multi(pos_score=pos, neg_score=neg, transformed_src=tr[:b], dst_vec=dst_vec[:b], neg_dst_vec=ndv)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(steps):
+            fn(i)
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / max(steps, 1)
+
+    warm = max(args.warmup, 3)
+    for i in range(warm):
+        train_step(*dev_batches[i % n_pool])
+    ops.LAUNCHES = 0
+    with ClockSampler(local_rank) as clocks:
+        ms = timed(lambda i: train_step(*dev_batches[i % n_pool]), args.steps)
+    launches = ops.LAUNCHES
+
+    # end to end through the public API: ids come from pinned host memory, the loss goes back
+    def e2e_step(i):
+        hb = host_batches[i % n_pool]
+        src, rel, dst = (t.to(dev, non_blocking=True) for t in hb)
+        return float(train_step(src, rel, dst).item())
+    e2e_step(0)
+    ms_e2e = timed(e2e_step, args.steps)
+    h2d = 3 * b * (1 + k) * 8
+
+    # per-kernel device times (extra steps, CUDA events around every C-ABI call on the launch stream)
+    psteps = max(args.profile_steps, 1)
+    with KernelProfiler() as prof:
+        for i in range(psteps):
+            train_step(*dev_batches[i % n_pool])
+        table = prof.table(psteps)
+    g = model._graph()
+    work = kernel_work(cfg, E, g.n_chunks, args.precision)
+    peaks = load_peaks()
+    kernels = {}
+    for tag, d in sorted(table.items(), key=lambda kv: -kv[1]["ms_per_step"]):
+        ent = {"calls_per_step": d["calls"] / psteps, "avg_ms": round(d["avg_ms"], 4),
+               "ms_per_step": round(d["ms_per_step"], 4), "share_of_step": round(d["ms_per_step"] / ms, 4)}
+        if d["kernel"] in work:
+            bytes_ = work[d["kernel"]] + (work["edge_fwd_act"] * (cfg["L"] - 1) / cfg["L"] if d["kernel"] == "edge_fwd" else 0)
+            ent["algorithmic_bytes"] = int(bytes_)
+            ent["gbs"] = round(bytes_ / (d["avg_ms"] * 1e-3) / 1e9, 1)
+            ent["frac_hbm"] = round(ent["gbs"] / peaks["hbm_gbs"], 4)
+        elif d["kernel"] == "gemm":
+            dims = dict(kv.split("=") for kv in tag[tag.index("[") + 1:tag.rindex(",")].split(","))
+            flops = 2.0 * int(dims["M"]) * int(dims["N"]) * int(dims["K"]) * (3 if args.precision == "fp32" else 1)
+            ent["tensor_flops"] = flops
+            ent["tflops"] = round(flops / (d["avg_ms"] * 1e-3) / 1e12, 1)
+            ent["frac_tensor"] = round(ent["tflops"] / peaks["tflops"], 4)
+        kernels[tag] = ent
+    top_tag = next(iter(kernels))
+    top = kernels[top_tag]
+    if "tflops" in top:
+        roofline = {"kernel": top_tag, "bound": "tensor", "achieved": top["tflops"], "peak": peaks["tflops"],
+                    "unit": "TFLOP/s", "frac": top["frac_tensor"], "traffic": None}
+    else:
+        roofline = {"kernel": top_tag, "bound": "hbm", "achieved": top.get("gbs"), "peak": peaks["hbm_gbs"],
+                    "unit": "GB/s", "frac": top.get("frac_hbm"), "traffic": None}
+    roofline["peak_source"] = peaks["source"]
+    sbytes = step_bytes_survey(cfg, E, args.precision)
+    step_roof = {"algorithmic_bytes_per_step": sbytes, "achieved_gbs": round(sbytes / (ms * 1e-3) / 1e9, 1),
+                 "frac_of_hbm_peak": round(sbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                 "formula": "SURVEY.md §8(d) bytes_step, fp32"}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        scale = CPU_SAMPLE_SCALE if cfg["N"] >= 100_000 else 1
+        r = run_cpu_port(cfg, steps=2, warmup=1, scale=scale)
+        cpu = {kk: r[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
+
+    line = {
+        "metric": METRIC, "value": E / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": warm,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+        "config": {"workload": f"{cfg_name}: synthetic KG {cfg['N']} nodes / {cfg['T']} triplets ({E} message-passing "
+                               f"edges) / {cfg['R']} relations, {cfg['D_in']}-d, {cfg['L']} layers, {cfg['H']} heads, "
+                               f"gat-out-dim {cfg['F']}, {cfg['scorer']}, batch {b}, num-neg {k}",
+                   "precision": ("fp32 storage; tensor-core GEMMs on bf16 hi/lo splits (3 passes, ~fp32 accuracy)"
+                                 if args.precision == "fp32" else "fp32 storage; single-pass bf16 tensor-core GEMMs"),
+                   "step": "full-graph GAT fwd + gather-score + margin loss + bwd + Adam", "layer_edges_per_sec":
+                   cfg["L"] * E / (ms * 1e-3), "l2": "inputs_exceed_L2 (P and G are ~1 GB each vs 126 MB L2)"},
+        "clocks": clocks.summary(),
+        "e2e": {"value": E / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "roofline": roofline, "step_roofline": step_roof, "kernels": kernels, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

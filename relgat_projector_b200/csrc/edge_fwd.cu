@@ -211,7 +211,6 @@ extern "C" int relgat_layer_fwd(
     float* alpha, float* z, float* bias_out,
     int N, int H, int F, int R, int max_deg, void* stream) {
   if (!P || !A || !rowptr || !alpha || !z || N < 0 || H <= 0 || F <= 0 || R <= 0) return RG_ERR_ARG;
-  if (N > 0 && (!csr_src || !csr_rel)) return RG_ERR_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool vec_ok = (reinterpret_cast<uintptr_t>(P) % 16 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0) &&
                       (!out || reinterpret_cast<uintptr_t>(out) % 16 == 0);

@@ -17,6 +17,13 @@ Planes = Tuple[torch.Tensor, Optional[torch.Tensor]]  # (hi, lo) bf16 planes of 
 
 SCORER_KIND = {"distmult": 0, "transe": 1}
 
+LAUNCHES = 0  # kernels of librelgat_b200.so launched so far (bench.py reports the per-run delta)
+
+
+def _count(n: int) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
 
 def _stream(t: torch.Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
@@ -44,7 +51,19 @@ def split_bf16(x: torch.Tensor, with_lo: bool = True) -> Planes:
     with torch.cuda.device(x.device):
         rc = _lib.load().relgat_split_bf16(_lib.ptr(x), _lib.ptr(hi), _lib.ptr(lo), x.numel(), _stream(x))
     _lib.check(rc, "relgat_split_bf16")
+    _count(1)
     return hi, lo
+
+
+def _tma_ready(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """TMA needs 16-byte aligned bases and row strides: pad the row stride to a multiple of 8 bf16
+    (view of a zero-padded copy) in the rare case the feature width is not a multiple of 8."""
+    if t is None or (t.stride(0) % 8 == 0 and t.data_ptr() % 16 == 0):
+        return t
+    cols = t.size(1)
+    padded = torch.zeros((t.size(0), (cols + 7) // 8 * 8), dtype=t.dtype, device=t.device)
+    padded[:, :cols].copy_(t)
+    return padded[:, :cols]
 
 
 def gemm(a: Planes, a_mn: bool, b: Planes, b_mn: bool, M: int, N: int, K: int,
@@ -63,6 +82,7 @@ def gemm(a: Planes, a_mn: bool, b: Planes, b_mn: bool, M: int, N: int, K: int,
         raise ValueError(f"gemm shapes: A {tuple(a_hi.shape)} != {exp_a} or B {tuple(b_hi.shape)} != {exp_b}")
     if (a_lo is None) != (b_lo is None):
         raise ValueError("either both operands carry a lo plane (fp32-parity mode) or neither")
+    a_hi, a_lo, b_hi, b_lo = _tma_ready(a_hi), _tma_ready(a_lo), _tma_ready(b_hi), _tma_ready(b_lo)
     dev = a_hi.device
     if out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=dev)
@@ -78,6 +98,7 @@ def gemm(a: Planes, a_mn: bool, b: Planes, b_mn: bool, M: int, N: int, K: int,
             _lib.ptr(b_hi), _lib.ptr(b_lo), b_hi.stride(0), int(b_mn),
             _lib.ptr(out), out.stride(0), M, N, K, splits_k, _lib.ptr(ws), ws_bytes, sm_count(dev), _stream(out))
     _lib.check(rc, "relgat_gemm_bf16")
+    _count(2 if splits_k > 1 else 1)
     return out
 
 
@@ -118,6 +139,7 @@ def edge_fwd(P: torch.Tensor, A: torch.Tensor, beta: Optional[torch.Tensor], g: 
             _lib.ptr(out), _lib.ptr(hi), _lib.ptr(lo), int(apply_elu),
             _lib.ptr(alpha), _lib.ptr(z), _lib.ptr(bias), N, H, F, R, 0, _stream(P))
     _lib.check(rc, "relgat_layer_fwd")
+    _count(1)
     return out, ((hi, lo) if want_act else None), alpha, z, bias
 
 
@@ -134,6 +156,7 @@ def edge_bwd_prep(dY: torch.Tensor, out: torch.Tensor, bias: torch.Tensor, H: in
         rc = _lib.load().relgat_layer_bwd_prep(_lib.ptr(dY), _lib.ptr(out), _lib.ptr(bias), _lib.ptr(G), _lib.ptr(t),
                                                _lib.ptr(hsum), N, H, F, int(apply_elu), _stream(dY))
     _lib.check(rc, "relgat_layer_bwd_prep")
+    _count(1)
     return G, t, hsum
 
 
@@ -155,6 +178,7 @@ def edge_bwd_src(P, G, A, alpha, z, t, g: GraphIndex, H: int, F: int, want_fp32:
             _lib.ptr(g.colptr), _lib.ptr(g.csc_slot), _lib.ptr(g.csc_dst), _lib.ptr(g.csc_rel),
             _lib.ptr(dP), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dz), n_src, H, F, g.R, 0, _stream(P))
     _lib.check(rc, "relgat_layer_bwd_src")
+    _count(1)
     return dP, ((hi, lo) if want_planes else None), dz
 
 
@@ -173,6 +197,7 @@ def edge_bwd_rel(P, dz, hsum, g: GraphIndex, H: int, F: int, want_dbeta: bool = 
             _lib.ptr(g.csr_dst), _lib.ptr(g.chunk_lo), _lib.ptr(g.chunk_hi), _lib.ptr(g.rel_chunk_ptr),
             g.n_chunks, _lib.ptr(partA), _lib.ptr(partB), _lib.ptr(dA), _lib.ptr(dbeta), H, F, g.R, _stream(P))
     _lib.check(rc, "relgat_layer_bwd_rel")
+    _count(2)
     return dA, dbeta
 
 
@@ -204,6 +229,7 @@ def score_fwd(kind: str, normalize: bool, xs, src_idx, xd, dst_idx, rel_emb, rel
             _lib.ptr(rel_emb), _lib.ptr(rel_ids), B, D, _lib.ptr(score), _lib.ptr(tr), n_transform,
             _lib.ptr(sv), _lib.ptr(dv), _stream(xs))
     _lib.check(rc, "relgat_score_fwd")
+    _count(1)
     return score, tr, sv, dv
 
 
@@ -226,6 +252,7 @@ def score_bwd(kind: str, normalize: bool, xs, src_idx, xd, dst_idx, rel_emb, rel
             _lib.ptr(rel_emb), _lib.ptr(rel_ids), B, D, _lib.ptr(dscore), _lib.ptr(dtransform), n_tr,
             _lib.ptr(d_src), _lib.ptr(d_dst), _lib.ptr(d_rel), _stream(xs))
     _lib.check(rc, "relgat_score_bwd")
+    _count(1)
     return d_src, d_dst, d_rel
 
 
@@ -243,4 +270,5 @@ def index_add_sorted(rows: torch.Tensor, keys: torch.Tensor, n_out: int, out: Op
         rc = _lib.load().relgat_index_add_sorted(_lib.ptr(rows), _lib.ptr(perm), _lib.ptr(sorted_keys), _lib.ptr(out),
                                                  M, D, int(accumulate), _stream(rows))
     _lib.check(rc, "relgat_index_add_sorted")
+    _count(1)
     return out
