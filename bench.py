@@ -161,11 +161,11 @@ def kernel_work(cfg, E, n_chunks, precision):
     s = 4
     plane_b = 4 if precision == "fp32" else 2  # bytes per element of the bf16 (hi[, lo]) planes
     w = {
-        # gathers P[src] + (src, rel) ids; writes out, act planes, alpha and z; rowptr and bias
-        "edge_fwd": E * (C * s + 8) + N * (C * s + 4 + 4) + 2 * E * H * 4,
+        # gathers P[src] + (src, rel) ids; writes out, z, (max, 1/den) and bias; reads rowptr
+        "edge_fwd": E * (C * s + 8) + N * (C * s + 4 + 4 + H * 8) + E * H * 4,
         "edge_fwd_act": N * C * plane_b,
-        # own P row + gather G[dst] + (slot, dst, rel) ids + alpha, z, t; writes dP planes and dz
-        "edge_bwd_src": N * C * s + E * (C * s + 12 + 3 * H * 4) + N * C * plane_b + E * H * 4,
+        # own P row + gather G[dst] + (slot, dst, rel) ids + z, (max, 1/den), t; writes dP planes and dz
+        "edge_bwd_src": N * C * s + E * (C * s + 12 + 4 * H * 4) + N * C * plane_b + E * H * 4,
         # gathers P[src] + (slot, src, dst) ids + dz + hsum; writes chunk partials
         "edge_bwd_rel": E * (C * s + 12 + 2 * H * 4) + n_chunks * C * s * 2,
         "edge_bwd_prep": 2 * N * C * s + 2 * N * H * 4,

@@ -71,19 +71,25 @@ int relgat_gemm_bf16(const void* a_hi, const void* a_lo, long long lda, int a_mn
  * per-destination stable softmax (torch_scatter.scatter_max / scatter_add), weighted
  * aggregation and the relation bias.  P: projected features [N_src, H*F] (row stride ldp),
  * A: [H, R, F] (stacked attn_vec), beta: [R] or NULL.
+ * chunk_node [n_chunks+1]: the CSR edge array cut at destination boundaries into chunks of ~64
+ * edges and <= 64 destinations (chunk c owns destinations [chunk_node[c], chunk_node[c+1])); one
+ * warp streams one chunk, so short segments do not drain the load pipeline.
  * Outputs: out [N, H*F] fp32 pre-activation (may be NULL), optional bf16 (hi, lo) planes of
  * act(out) for the next layer's GEMM (act = ELU if apply_elu, reference model.py:286-287),
- * alpha/z [E, H] (attention weights / raw logits, saved for backward), bias_out [N].
- * Destinations with more than max_deg in-edges are skipped (hub path); max_deg <= 0: none. */
+ * z [E, H] raw logits and minv [N, H, 2] = (segment max, 1/denominator) saved for backward,
+ * alpha [E, H] attention weights (optional, NULL to skip), bias_out [N]. */
 int relgat_layer_fwd(const void* P, int p_is_bf16, long long ldp, const float* A, const float* beta,
                      const int* rowptr, const int* csr_src, const int* csr_rel,
+                     const int* chunk_node, int n_chunks,
                      float* out, void* act_hi, void* act_lo, int apply_elu,
-                     float* alpha, float* z, float* bias_out,
-                     int N, int H, int F, int R, int max_deg, void* stream);
+                     float* alpha, float* z, float* minv, float* bias_out,
+                     int H, int F, int R, void* stream);
 
 /* ---- RelGAT layer, edge part, backward (replaces the autograd replay of layer.py:220-318) ---
  * bwd_prep: G = dY * act'(out) (in place allowed), t[N,H] = <G, out - bias>, hsum[N,H] = sum_f G.
- * bwd_src : by-source pass: dP [N_src, H*F] (fp32 and/or bf16 hi/lo planes) and dz [E, H].
+ * bwd_src : by-source pass over chunks of the CSC order (chunk_node as in fwd, over sources):
+ *           dP [N_src, H*F] (fp32 and/or bf16 hi/lo planes) and dz [E, H]; the attention weights
+ *           are recomputed from z and minv.
  * bwd_rel : by-relation pass over chunks [chunk_lo, chunk_hi) of rel_slot (a chunk never spans
  *           two relations; rel_chunk_ptr[R+1] gives each relation's chunk range):
  *           dA [H, R, F] and dbeta [R] (NULL to skip) with an ordered reduction of the partials
@@ -91,10 +97,11 @@ int relgat_layer_fwd(const void* P, int p_is_bf16, long long ldp, const float* A
 int relgat_layer_bwd_prep(const float* dY, const float* out, const float* bias, float* G, float* t,
                           float* hsum, int N, int H, int F, int apply_elu, void* stream);
 int relgat_layer_bwd_src(const float* P, long long ldp, const float* G, const float* A,
-                         const float* alpha, const float* z, const float* t,
+                         const float* z, const float* minv, const float* t,
                          const int* colptr, const int* csc_slot, const int* csc_dst, const int* csc_rel,
+                         const int* chunk_node, int n_chunks,
                          float* dP, void* dP_hi, void* dP_lo, float* dz,
-                         int N_src, int H, int F, int R, int max_deg, void* stream);
+                         int H, int F, int R, void* stream);
 int relgat_layer_bwd_rel(const float* P, long long ldp, const float* dz, const float* hsum,
                          const int* rel_slot, const int* csr_src, const int* csr_dst,
                          const int* chunk_lo, const int* chunk_hi, const int* rel_chunk_ptr,

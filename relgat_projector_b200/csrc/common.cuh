@@ -47,6 +47,10 @@ struct RowVec<float, 4> {
   static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
+  static __device__ __forceinline__ void load_shared(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
 };
 
 template <>
@@ -54,6 +58,7 @@ struct RowVec<float, 1> {
   static __device__ __forceinline__ void load_stream(const float* p, float (&v)[1]) { v[0] = __ldg(p); }
   static __device__ __forceinline__ void load_cached(const float* p, float (&v)[1]) { v[0] = __ldg(p); }
   static __device__ __forceinline__ void store(float* p, const float (&v)[1]) { *p = v[0]; }
+  static __device__ __forceinline__ void load_shared(const float* p, float (&v)[1]) { v[0] = *p; }
 };
 
 template <>

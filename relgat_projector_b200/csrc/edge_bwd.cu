@@ -8,7 +8,8 @@
 // traversal order is free.  We pick the order that makes each reduction local and
 // deterministic:
 //   bwd_prep : per node   — G = dY * act'(out); t[j,h]; hsum[j,h] = sum_f G[j,h,f]
-//   bwd_src  : by SOURCE  — dP[i] = sum_{e: src=i} (alpha*G[dst] + dz*A[rel]);  writes dz[e,h]
+//   bwd_src  : by SOURCE  — dP[i] = sum_{e: src=i} (alpha*G[dst] + dz*A[rel]);  writes dz[e,h];
+//              alpha is recomputed from the saved logits and softmax statistics (max, 1/den)
 //   bwd_rel  : by RELATION (fixed-size chunks) — partial dA[h,r,:] = sum dz*P[src]; partial dbeta
 //   bwd_rel_reduce : ordered sum of the chunk partials
 // HBM-bound: per launch bwd_src gathers E*C*s bytes of G rows, bwd_rel gathers E*C*s of P rows.
@@ -71,27 +72,32 @@ __global__ void __launch_bounds__(kBwdWarps * 32) bwd_prep_kernel(const PrepArgs
 }
 
 // ------------------------------------------------------------------------------------
-// bwd_src
+// bwd_src — edge-balanced streaming over the by-source (CSC) order.
+// The CSC edge array is cut at source boundaries into chunks of ~64 edges (graph.py:
+// src_chunk_node); one warp streams one (chunk, head-group).  The stream is a sequence of
+// row "items": OWN(i) = the source's own P row (needed for dalpha = <G[dst], P[i]>), followed
+// by one EDGE item per out-edge (the gathered G[dst] row).  Two items are in flight per warp
+// and the pipeline does not drain at source boundaries.
 // ------------------------------------------------------------------------------------
 template <int V>
 struct SrcArgs {
   const float* P;       // [N_src, C]   (row stride ldp)
   const float* G;       // [N_dst, C]
   const float* A;       // [H, R, F]
-  const float* alpha;   // [E, H] CSR order
   const float* z;       // [E, H] CSR order
+  const float* minv;    // [N_dst, H, 2] forward softmax statistics (max, 1/den)
   const float* t;       // [N_dst, H]
   const int* colptr;    // [N_src+1]
   const int* csc_slot;  // [E] CSR slot of each by-source edge
   const int* csc_dst;   // [E]
   const int* csc_rel;   // [E]
+  const int* chunk_node;  // [n_chunks+1] first source of every chunk (<= 64 sources each)
   float* dP;            // [N_src, C] fp32 (may be nullptr when only the bf16 split is wanted)
   __nv_bfloat16* dP_hi; // optional bf16 split of dP for the tensor-core GEMMs
   __nv_bfloat16* dP_lo;
   float* dz;            // [E, H] CSR order
-  int N, H, F, R, hg;
+  int n_chunks, H, F, R, hg;
   long long ldp;
-  int max_deg;
 };
 
 template <int V>
@@ -99,105 +105,174 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 3) bwd_src_kernel(const SrcArg
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int groups = a.H / a.hg;
   const long long task = static_cast<long long>(blockIdx.x) * kBwdWarps + warp;
-  if (task >= static_cast<long long>(a.N) * groups) return;
-  const int i = static_cast<int>(task / groups);
-  const int g = static_cast<int>(task - static_cast<long long>(i) * groups);
+  if (task >= static_cast<long long>(a.n_chunks) * groups) return;
+  const int c = static_cast<int>(task / groups);
+  const int g = static_cast<int>(task - static_cast<long long>(c) * groups);
   const LaneMap lm = make_lane_map<V>(lane, g, a.hg, a.F);
   const int C = a.H * a.F;
-  const int lo = a.colptr[i], hi = a.colptr[i + 1];
-  if (a.max_deg > 0 && hi - lo > a.max_deg) return;
 
-  float p[kMaxVecPerLane][V], acc[kMaxVecPerLane][V];
+  const int n_lo = a.chunk_node[c];
+  const int nn = a.chunk_node[c + 1] - n_lo;  // 1..64 sources
+  int cp0 = 0, cp1 = 0, cp2 = 0;
+  if (lane <= nn) cp0 = __ldg(a.colptr + n_lo + lane);
+  if (32 + lane <= nn) cp1 = __ldg(a.colptr + n_lo + 32 + lane);
+  if (64 + lane <= nn) cp2 = __ldg(a.colptr + n_lo + 64 + lane);
+#define RG_CP(k_) ((k_) < 32 ? __shfl_sync(0xffffffffu, cp0, (k_) & 31)       \
+                             : ((k_) < 64 ? __shfl_sync(0xffffffffu, cp1, (k_) & 31) \
+                                          : __shfl_sync(0xffffffffu, cp2, (k_) & 31)))
+  const int e_lo = RG_CP(0);
+  const int e_hi = RG_CP(nn);
+
+  // The source's own row lives in shared memory (lane-private slots, so no synchronisation):
+  // it is read once per out-edge, and keeping it out of the register file leaves room for two
+  // gathered rows in flight at 12 warps per SM.
+  __shared__ __align__(16) float p_sm[kBwdWarps][kMaxVecPerLane * 32 * V];
+  float* p_own = &p_sm[warp][0];
+  float acc[kMaxVecPerLane][V];
 #pragma unroll
-  for (int k = 0; k < kMaxVecPerLane; ++k) {
-    const int q = lm.sub + lm.lph * k;
+  for (int k = 0; k < kMaxVecPerLane; ++k)
 #pragma unroll
-    for (int v = 0; v < V; ++v) { acc[k][v] = 0.f; p[k][v] = 0.f; }
-    if (hi > lo && q < lm.vph)
-      RowVec<float, V>::load_stream(a.P + static_cast<long long>(i) * a.ldp + lm.head_off + q * V, p[k]);
+    for (int v = 0; v < V; ++v) acc[k][v] = 0.f;
+
+  // fetch cursor (item generation) ------------------------------------------------------
+  int fk = 0;             // node whose items are being generated
+  int fe = e_lo;          // next edge to hand out
+  int f_end = RG_CP(1);   // end of node fk's edges
+  bool own_done = false;  // OWN(fk) already handed out
+  int base = e_lo - 32;   // edge-metadata window [base, base + 32) held across the lanes
+  int my_slot = 0, my_dst = 0, my_rel = 0;
+  // consume cursor ----------------------------------------------------------------------
+  int cur = -1;           // node being accumulated (-1: none yet)
+
+  enum { IT_NONE = 0, IT_OWN = 1, IT_EDGE = 2 };
+
+  // writes dP for node n_lo + cur
+#define RG_WRITE_ROW(node_, zero_)                                                             \
+  {                                                                                            \
+    _Pragma("unroll") for (int k = 0; k < kMaxVecPerLane; ++k) {                               \
+      const int q = lm.sub + lm.lph * k;                                                       \
+      if (q < lm.vph) {                                                                        \
+        float o[V];                                                                            \
+        _Pragma("unroll") for (int v = 0; v < V; ++v) o[v] = (zero_) ? 0.f : acc[k][v];        \
+        const long long off = static_cast<long long>(n_lo + (node_)) * C + lm.head_off + q * V; \
+        if (a.dP) RowVec<float, V>::store(a.dP + off, o);                                      \
+        if (a.dP_hi) store_split_bf16<V>(a.dP_hi + off, a.dP_lo ? a.dP_lo + off : nullptr, o); \
+      }                                                                                        \
+    }                                                                                          \
   }
 
-  for (int base = lo; base < hi; base += 32) {
-    const int cnt = min(32, hi - base);
-    int my_slot = 0, my_dst = 0, my_rel = 0;
-    if (lane < cnt) {
-      my_slot = __ldg(a.csc_slot + base + lane);
-      my_dst = __ldg(a.csc_dst + base + lane);
-      my_rel = __ldg(a.csc_rel + base + lane);
-    }
-    for (int tix = 0; tix < cnt; tix += 2) {
-      const bool two = (tix + 1 < cnt);
-      const int u1 = two ? tix + 1 : tix;
-      const int s0 = __shfl_sync(0xffffffffu, my_slot, tix), s1 = __shfl_sync(0xffffffffu, my_slot, u1);
-      const int j0 = __shfl_sync(0xffffffffu, my_dst, tix), j1 = __shfl_sync(0xffffffffu, my_dst, u1);
-      const int r0 = __shfl_sync(0xffffffffu, my_rel, tix), r1 = __shfl_sync(0xffffffffu, my_rel, u1);
-      const float* g0 = a.G + static_cast<long long>(j0) * C + lm.head_off;
-      const float* g1 = a.G + static_cast<long long>(j1) * C + lm.head_off;
-      float x0[kMaxVecPerLane][V], x1[kMaxVecPerLane][V];
-#pragma unroll
-      for (int k = 0; k < kMaxVecPerLane; ++k) {
-        const int q = lm.sub + lm.lph * k;
-        if (q < lm.vph) RowVec<float, V>::load_stream(g0 + q * V, x0[k]);
-      }
-      if (two) {
-#pragma unroll
-        for (int k = 0; k < kMaxVecPerLane; ++k) {
-          const int q = lm.sub + lm.lph * k;
-          if (q < lm.vph) RowVec<float, V>::load_stream(g1 + q * V, x1[k]);
-        }
-      }
-      const long long e0 = static_cast<long long>(s0) * a.H + lm.hh;
-      const long long e1 = static_cast<long long>(s1) * a.H + lm.hh;
-      const float al0 = __ldg(a.alpha + e0), z0 = __ldg(a.z + e0), t0 = __ldg(a.t + static_cast<long long>(j0) * a.H + lm.hh);
-      const float al1 = __ldg(a.alpha + e1), z1 = __ldg(a.z + e1), t1 = __ldg(a.t + static_cast<long long>(j1) * a.H + lm.hh);
-      float d0 = 0.f, d1 = 0.f;
-#pragma unroll
-      for (int k = 0; k < kMaxVecPerLane; ++k) {
-        const int q = lm.sub + lm.lph * k;
-        if (q < lm.vph) {
-#pragma unroll
-          for (int v = 0; v < V; ++v) {
-            d0 = fmaf(x0[k][v], p[k][v], d0);
-            if (two) d1 = fmaf(x1[k][v], p[k][v], d1);
-          }
-        }
-      }
-      d0 = head_sum(d0, lm.lph);  // dalpha
-      d1 = head_sum(d1, lm.lph);
-      const float dz0 = al0 * (d0 - t0) * (z0 > 0.f ? 1.f : kLeakySlope);
-      const float dz1 = al1 * (d1 - t1) * (z1 > 0.f ? 1.f : kLeakySlope);
-      if (lm.sub == 0) {
-        a.dz[e0] = dz0;
-        if (two) a.dz[e1] = dz1;
-      }
-      const float* a0 = a.A + (static_cast<long long>(lm.hh) * a.R + r0) * a.F;
-      const float* a1 = a.A + (static_cast<long long>(lm.hh) * a.R + r1) * a.F;
-#pragma unroll
-      for (int k = 0; k < kMaxVecPerLane; ++k) {
-        const int q = lm.sub + lm.lph * k;
-        if (q < lm.vph) {
-          float av[V];
-          RowVec<float, V>::load_cached(a0 + q * V, av);
-#pragma unroll
-          for (int v = 0; v < V; ++v) acc[k][v] = fmaf(al0, x0[k][v], fmaf(dz0, av[v], acc[k][v]));
-          if (two) {
-            RowVec<float, V>::load_cached(a1 + q * V, av);
-#pragma unroll
-            for (int v = 0; v < V; ++v) acc[k][v] = fmaf(al1, x1[k][v], fmaf(dz1, av[v], acc[k][v]));
-          }
-        }
-      }
-    }
+  // next item of the stream: type / node / (slot, dst, rel)
+#define RG_NEXT(ty_, nd_, sl_, ds_, rl_)                                                       \
+  {                                                                                            \
+    ty_ = IT_NONE; nd_ = 0; sl_ = 0; ds_ = 0; rl_ = 0;                                         \
+    while (fk < nn) {                                                                          \
+      if (!own_done) {                                                                         \
+        if (f_end == fe) { /* source without out-edges: dP row is exactly zero */              \
+          RG_WRITE_ROW(fk, true);                                                              \
+          ++fk;                                                                                \
+          if (fk < nn) f_end = RG_CP(fk + 1);                                                  \
+          continue;                                                                            \
+        }                                                                                      \
+        own_done = true; ty_ = IT_OWN; nd_ = fk;                                               \
+        break;                                                                                 \
+      }                                                                                        \
+      if (fe < f_end) {                                                                        \
+        if (fe >= base + 32) {                                                                 \
+          base = fe;                                                                           \
+          const int idx = base + lane;                                                         \
+          if (idx < e_hi) {                                                                    \
+            my_slot = __ldg(a.csc_slot + idx);                                                 \
+            my_dst = __ldg(a.csc_dst + idx);                                                   \
+            my_rel = __ldg(a.csc_rel + idx);                                                   \
+          }                                                                                    \
+        }                                                                                      \
+        sl_ = __shfl_sync(0xffffffffu, my_slot, fe - base);                                    \
+        ds_ = __shfl_sync(0xffffffffu, my_dst, fe - base);                                     \
+        rl_ = __shfl_sync(0xffffffffu, my_rel, fe - base);                                     \
+        ty_ = IT_EDGE; nd_ = fk; ++fe;                                                         \
+        break;                                                                                 \
+      }                                                                                        \
+      ++fk; own_done = false;                                                                  \
+      if (fk < nn) f_end = RG_CP(fk + 1);                                                      \
+    }                                                                                          \
   }
-#pragma unroll
-  for (int k = 0; k < kMaxVecPerLane; ++k) {
-    const int q = lm.sub + lm.lph * k;
-    if (q < lm.vph) {
-      const long long off = static_cast<long long>(i) * C + lm.head_off + q * V;
-      if (a.dP) RowVec<float, V>::store(a.dP + off, acc[k]);
-      if (a.dP_hi) store_split_bf16<V>(a.dP_hi + off, a.dP_lo ? a.dP_lo + off : nullptr, acc[k]);
-    }
+
+#define RG_ISSUE(ty_, nd_, ds_, x_)                                                            \
+  if (ty_ != IT_NONE) {                                                                        \
+    const float* rowp = (ty_ == IT_OWN)                                                        \
+        ? a.P + static_cast<long long>(n_lo + (nd_)) * a.ldp + lm.head_off                     \
+        : a.G + static_cast<long long>(ds_) * C + lm.head_off;                                 \
+    _Pragma("unroll") for (int k = 0; k < kMaxVecPerLane; ++k) {                               \
+      const int q = lm.sub + lm.lph * k;                                                       \
+      if (q < lm.vph) RowVec<float, V>::load_stream(rowp + q * V, x_[k]);                      \
+    }                                                                                          \
   }
+
+#define RG_CONSUME(ty_, nd_, sl_, ds_, rl_, x_, zz_, mi_, tt_)                                 \
+  if (ty_ == IT_OWN) {                                                                         \
+    if (cur >= 0) RG_WRITE_ROW(cur, false);                                                    \
+    cur = (nd_);                                                                               \
+    _Pragma("unroll") for (int k = 0; k < kMaxVecPerLane; ++k) {                               \
+      const int q = lm.sub + lm.lph * k;                                                       \
+      if (q < lm.vph) RowVec<float, V>::store(p_own + (k * 32 + lane) * V, x_[k]);             \
+      _Pragma("unroll") for (int v = 0; v < V; ++v) acc[k][v] = 0.f;                           \
+    }                                                                                          \
+  } else if (ty_ == IT_EDGE) {                                                                 \
+    float dd = 0.f;                                                                            \
+    _Pragma("unroll") for (int k = 0; k < kMaxVecPerLane; ++k) {                               \
+      const int q = lm.sub + lm.lph * k;                                                       \
+      if (q < lm.vph) {                                                                        \
+        float pv[V];                                                                           \
+        RowVec<float, V>::load_shared(p_own + (k * 32 + lane) * V, pv);                        \
+        _Pragma("unroll") for (int v = 0; v < V; ++v) dd = fmaf(x_[k][v], pv[v], dd);          \
+      }                                                                                        \
+    }                                                                                          \
+    dd = head_sum(dd, lm.lph); /* dalpha */                                                    \
+    const float ee = zz_ > 0.f ? zz_ : kLeakySlope * zz_;                                      \
+    const float al = expf(ee - mi_.x) * mi_.y;                                                 \
+    const float dzv = al * (dd - tt_) * (zz_ > 0.f ? 1.f : kLeakySlope);                       \
+    if (lm.sub == 0) a.dz[static_cast<long long>(sl_) * a.H + lm.hh] = dzv;                    \
+    const float* ar = a.A + (static_cast<long long>(lm.hh) * a.R + (rl_)) * a.F;               \
+    _Pragma("unroll") for (int k = 0; k < kMaxVecPerLane; ++k) {                               \
+      const int q = lm.sub + lm.lph * k;                                                       \
+      if (q < lm.vph) {                                                                        \
+        float av[V];                                                                           \
+        RowVec<float, V>::load_cached(ar + q * V, av);                                         \
+        _Pragma("unroll") for (int v = 0; v < V; ++v)                                          \
+          acc[k][v] = fmaf(al, x_[k][v], fmaf(dzv, av[v], acc[k][v]));                         \
+      }                                                                                        \
+    }                                                                                          \
+  }
+
+  while (true) {
+    int ty0, nd0, sl0, ds0, rl0, ty1, nd1, sl1, ds1, rl1;
+    RG_NEXT(ty0, nd0, sl0, ds0, rl0);
+    if (ty0 == IT_NONE) break;
+    RG_NEXT(ty1, nd1, sl1, ds1, rl1);
+    float x0[kMaxVecPerLane][V], x1[kMaxVecPerLane][V];
+    RG_ISSUE(ty0, nd0, ds0, x0);
+    RG_ISSUE(ty1, nd1, ds1, x1);
+    float z0 = 0.f, z1 = 0.f, t0 = 0.f, t1 = 0.f;
+    float2 mi0 = make_float2(0.f, 0.f), mi1 = make_float2(0.f, 0.f);
+    if (ty0 == IT_EDGE) {
+      z0 = __ldg(a.z + static_cast<long long>(sl0) * a.H + lm.hh);
+      t0 = __ldg(a.t + static_cast<long long>(ds0) * a.H + lm.hh);
+      mi0 = __ldg(reinterpret_cast<const float2*>(a.minv) + static_cast<long long>(ds0) * a.H + lm.hh);
+    }
+    if (ty1 == IT_EDGE) {
+      z1 = __ldg(a.z + static_cast<long long>(sl1) * a.H + lm.hh);
+      t1 = __ldg(a.t + static_cast<long long>(ds1) * a.H + lm.hh);
+      mi1 = __ldg(reinterpret_cast<const float2*>(a.minv) + static_cast<long long>(ds1) * a.H + lm.hh);
+    }
+    RG_CONSUME(ty0, nd0, sl0, ds0, rl0, x0, z0, mi0, t0);
+    RG_CONSUME(ty1, nd1, sl1, ds1, rl1, x1, z1, mi1, t1);
+  }
+  if (cur >= 0) RG_WRITE_ROW(cur, false);
+#undef RG_CONSUME
+#undef RG_ISSUE
+#undef RG_NEXT
+#undef RG_WRITE_ROW
+#undef RG_CP
 }
 
 // ------------------------------------------------------------------------------------
@@ -348,27 +423,29 @@ extern "C" int relgat_layer_bwd_prep(const float* dY, const float* out, const fl
 }
 
 extern "C" int relgat_layer_bwd_src(const float* P, long long ldp, const float* G, const float* A,
-                                    const float* alpha, const float* z, const float* t,
+                                    const float* z, const float* minv, const float* t,
                                     const int* colptr, const int* csc_slot, const int* csc_dst, const int* csc_rel,
+                                    const int* chunk_node, int n_chunks,
                                     float* dP, void* dP_hi, void* dP_lo, float* dz,
-                                    int N_src, int H, int F, int R, int max_deg, void* stream) {
-  if (!P || !G || !A || !alpha || !z || !t || !colptr || !dz || N_src < 0 || H <= 0 || F <= 0 || R <= 0)
-    return RG_ERR_ARG;
+                                    int H, int F, int R, void* stream) {
+  if (!P || !G || !A || !colptr || !chunk_node || n_chunks < 0 || H <= 0 || F <= 0 || R <= 0) return RG_ERR_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (F % 4 == 0 && ldp % 4 == 0 && al16(P) && al16(G) && al16(A) && (!dP || al16(dP))) {
+  const bool planes_ok = (!dP_hi || reinterpret_cast<uintptr_t>(dP_hi) % 8 == 0) &&
+                         (!dP_lo || reinterpret_cast<uintptr_t>(dP_lo) % 8 == 0);
+  if (F % 4 == 0 && ldp % 4 == 0 && al16(P) && al16(G) && al16(A) && (!dP || al16(dP)) && planes_ok) {
     const int hg = pick_heads_per_warp(H, F, 4);
     if (!hg) return RG_ERR_SHAPE;
-    SrcArgs<4> a{P, G, A, alpha, z, t, colptr, csc_slot, csc_dst, csc_rel, dP,
+    SrcArgs<4> a{P, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, chunk_node, dP,
                  static_cast<__nv_bfloat16*>(dP_hi), static_cast<__nv_bfloat16*>(dP_lo), dz,
-                 N_src, H, F, R, hg, ldp, max_deg};
-    return launch_tasks(bwd_src_kernel<4>, a, static_cast<long long>(N_src) * (H / hg), s);
+                 n_chunks, H, F, R, hg, ldp};
+    return launch_tasks(bwd_src_kernel<4>, a, static_cast<long long>(n_chunks) * (H / hg), s);
   }
   const int hg = pick_heads_per_warp(H, F, 1);
   if (!hg) return RG_ERR_SHAPE;
-  SrcArgs<1> a{P, G, A, alpha, z, t, colptr, csc_slot, csc_dst, csc_rel, dP,
+  SrcArgs<1> a{P, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, chunk_node, dP,
                static_cast<__nv_bfloat16*>(dP_hi), static_cast<__nv_bfloat16*>(dP_lo), dz,
-               N_src, H, F, R, hg, ldp, max_deg};
-  return launch_tasks(bwd_src_kernel<1>, a, static_cast<long long>(N_src) * (H / hg), s);
+               n_chunks, H, F, R, hg, ldp};
+  return launch_tasks(bwd_src_kernel<1>, a, static_cast<long long>(n_chunks) * (H / hg), s);
 }
 
 extern "C" int relgat_layer_bwd_rel(const float* P, long long ldp, const float* dz, const float* hsum,

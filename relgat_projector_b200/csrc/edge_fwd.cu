@@ -2,12 +2,18 @@
 // SURVEY.md §2.2): per-edge logit + LeakyReLU, destination-segmented softmax, attention-
 // weighted aggregation and relation bias in ONE pass over the CSR (by-destination) edges.
 //
-// One warp = one (destination j, head-group) task.  The projected source rows P[src] are
-// gathered with 128-bit streaming loads and read exactly once; the softmax is the online
-// (running max / running sum) form so nothing of size [E, F] is ever materialised.
-// Segment order = CSR order = original edge order inside a destination (deterministic).
+// Work decomposition: the CSR edge array is cut, at destination boundaries, into chunks of
+// ~64 edges (graph.py: fwd_chunk_node).  One warp streams one (chunk, head-group): the source
+// rows P[src] are gathered with 128-bit streaming loads, two rows in flight per warp, and the
+// pipeline does not drain at destination boundaries — a destination is "finalised" (normalise,
+// add bias, write the row, save the softmax statistics) when the stream crosses into the next
+// one.  Short segments (average in-degree ~4.5 on the named graphs) therefore cost no extra
+// dependent-load round trips, which is what bounded the first (warp-per-destination) version
+// at 39% of HBM peak (profiles/r01_launches_c2_fp32_v1.md).
 //
-// HBM-bound: algorithmic bytes per launch = E*(C*s + 8) + N*(C*s_out + 4) + 2*E*H*4.
+// Softmax is the online (running max / running sum) form; segment order = CSR order =
+// original edge order inside a destination (deterministic).
+// HBM-bound: algorithmic bytes per launch = E*(C*s + 8) + N*(C*s_out + 12) + E*H*4 (+ planes).
 #include "common.cuh"
 
 namespace relgat {
@@ -22,16 +28,17 @@ struct FwdArgs {
   const int* rowptr;     // [N+1]
   const int* csr_src;    // [E]
   const int* csr_rel;    // [E]
+  const int* chunk_node; // [n_chunks+1] first destination of every chunk (<= 64 destinations each)
   float* out;            // [N, H*F] fp32 layer output (pre-activation), may be nullptr
   __nv_bfloat16* act_hi; // [N, H*F] optional bf16 copy of act(out) (hi part)
   __nv_bfloat16* act_lo; // [N, H*F] optional residual (lo part); nullptr = hi only
-  float* alpha;          // [E, H] attention weights (CSR order)
+  float* alpha;          // [E, H] attention weights (CSR order) or nullptr
   float* z;              // [E, H] pre-activation logits (CSR order)
+  float* minv;           // [N, H, 2] softmax statistics (max, 1/denominator) saved for backward
   float* bias_out;       // [N] sum of relation biases per destination
-  int N, H, F, R, hg;
+  int n_chunks, H, F, R, hg;
   long long ldp;         // row stride of P in elements
   int apply_elu;         // act = ELU (reference model.py:286-287) else identity
-  int max_deg;           // rows with more in-edges are left to the hub path (<=0: no limit)
 };
 
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
@@ -43,15 +50,24 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
   const int warp = threadIdx.x >> 5;
   const int groups = a.H / a.hg;
   const long long task = static_cast<long long>(blockIdx.x) * kFwdWarps + warp;
-  if (task >= static_cast<long long>(a.N) * groups) return;
-  const int j = static_cast<int>(task / groups);
-  const int g = static_cast<int>(task - static_cast<long long>(j) * groups);
+  if (task >= static_cast<long long>(a.n_chunks) * groups) return;
+  const int c = static_cast<int>(task / groups);
+  const int g = static_cast<int>(task - static_cast<long long>(c) * groups);
   const LaneMap lm = make_lane_map<V>(lane, g, a.hg, a.F);
   const int C = a.H * a.F;
 
-  const int lo = a.rowptr[j];
-  const int hi = a.rowptr[j + 1];
-  if (a.max_deg > 0 && hi - lo > a.max_deg) return;  // hub: handled by the split path
+  const int n_lo = a.chunk_node[c];
+  const int nn = a.chunk_node[c + 1] - n_lo;  // 1..64 destinations
+  // rowptr window of the chunk, spread over the lanes (nn + 1 <= 65 entries)
+  int rp0 = 0, rp1 = 0, rp2 = 0;
+  if (lane <= nn) rp0 = __ldg(a.rowptr + n_lo + lane);
+  if (32 + lane <= nn) rp1 = __ldg(a.rowptr + n_lo + 32 + lane);
+  if (64 + lane <= nn) rp2 = __ldg(a.rowptr + n_lo + 64 + lane);
+#define RG_RP(k_) ((k_) < 32 ? __shfl_sync(0xffffffffu, rp0, (k_) & 31)       \
+                             : ((k_) < 64 ? __shfl_sync(0xffffffffu, rp1, (k_) & 31) \
+                                          : __shfl_sync(0xffffffffu, rp2, (k_) & 31)))
+  const int e_lo = RG_RP(0);
+  const int e_hi = RG_RP(nn);
 
   float acc[kMaxVecPerLane][V];
 #pragma unroll
@@ -59,9 +75,83 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[k][v] = 0.f;
   float m = -INFINITY, l = 0.f, bsum = 0.f;
+  int kn = 0;               // destination cursor inside the chunk
+  int seg_start = e_lo;
+  int seg_end = RG_RP(1);
 
-  for (int base = lo; base < hi; base += 32) {
-    const int cnt = min(32, hi - base);
+  // writes destination n_lo + kn and resets the running state
+#define RG_FINALIZE()                                                                              \
+  {                                                                                                \
+    const int j = n_lo + kn;                                                                       \
+    const bool empty = (seg_end == seg_start);                                                     \
+    const float inv = empty ? 0.f : 1.f / fmaxf(l, 1e-16f); /* reference layer.py:291 clamp */     \
+    _Pragma("unroll") for (int k = 0; k < kMaxVecPerLane; ++k) {                                   \
+      const int q = lm.sub + lm.lph * k;                                                           \
+      if (q < lm.vph) {                                                                            \
+        float o[V];                                                                                \
+        _Pragma("unroll") for (int v = 0; v < V; ++v) {                                            \
+          o[v] = empty ? 0.f : fmaf(acc[k][v], inv, bsum); /* bias on every head/channel :313-318 */ \
+          acc[k][v] = 0.f;                                                                         \
+        }                                                                                          \
+        const long long off = static_cast<long long>(j) * C + lm.head_off + q * V;                 \
+        if (a.out) RowVec<float, V>::store(a.out + off, o);                                        \
+        if (a.act_hi) {                                                                            \
+          if (a.apply_elu) {                                                                       \
+            _Pragma("unroll") for (int v = 0; v < V; ++v) o[v] = elu1(o[v]);                       \
+          }                                                                                        \
+          store_split_bf16<V>(a.act_hi + off, a.act_lo ? a.act_lo + off : nullptr, o);             \
+        }                                                                                          \
+      }                                                                                            \
+    }                                                                                              \
+    if (g == 0 && lane == 0 && a.bias_out) a.bias_out[j] = empty ? 0.f : bsum;                     \
+    if (lm.sub == 0 && a.minv) {                                                                   \
+      *reinterpret_cast<float2*>(a.minv + (static_cast<long long>(j) * a.H + lm.hh) * 2) =         \
+          make_float2(empty ? 0.f : m, inv);                                                       \
+    }                                                                                              \
+    if (a.alpha) { /* alpha = exp(eps - m) / den for every (edge, head of this group) */           \
+      __syncwarp();                                                                                \
+      const int items = (seg_end - seg_start) * a.hg;                                              \
+      for (int it = 0; it < items; it += 32) {                                                     \
+        const int idx = it + lane;                                                                 \
+        const int hgi = idx % a.hg;                                                                \
+        const float mh = __shfl_sync(0xffffffffu, m, hgi * lm.lph);                                \
+        const float ih = __shfl_sync(0xffffffffu, inv, hgi * lm.lph);                              \
+        if (idx < items) {                                                                         \
+          const long long o = static_cast<long long>(seg_start + idx / a.hg) * a.H + g * a.hg + hgi; \
+          const float zz = a.z[o];                                                                 \
+          const float ee = zz > 0.f ? zz : kLeakySlope * zz;                                       \
+          a.alpha[o] = expf(ee - mh) * ih;                                                         \
+        }                                                                                          \
+      }                                                                                            \
+    }                                                                                              \
+    m = -INFINITY; l = 0.f; bsum = 0.f;                                                            \
+    ++kn;                                                                                          \
+    seg_start = seg_end;                                                                           \
+    if (kn < nn) seg_end = RG_RP(kn + 1);                                                          \
+  }
+
+  // one edge: logit, online softmax update, weighted accumulate
+#define RG_EDGE(x_, d_, r_, e_)                                                                    \
+  {                                                                                                \
+    while (kn < nn && (e_) == seg_end) RG_FINALIZE();                                              \
+    if (lm.sub == 0) a.z[static_cast<long long>(e_) * a.H + lm.hh] = (d_);                         \
+    const float ev = (d_) > 0.f ? (d_) : kLeakySlope * (d_);                                       \
+    const float mn = fmaxf(m, ev);                                                                 \
+    const float sc = expf(m - mn);                                                                 \
+    const float w = expf(ev - mn);                                                                 \
+    l = fmaf(l, sc, w);                                                                            \
+    _Pragma("unroll") for (int k = 0; k < kMaxVecPerLane; ++k) {                                   \
+      const int q = lm.sub + lm.lph * k;                                                           \
+      if (q < lm.vph) {                                                                            \
+        _Pragma("unroll") for (int v = 0; v < V; ++v) acc[k][v] = fmaf(acc[k][v], sc, w * x_[k][v]); \
+      }                                                                                            \
+    }                                                                                              \
+    m = (ev != ev) ? ev : mn; /* NaN logits poison the row like the reference does */              \
+    if (a.beta) bsum += __ldg(a.beta + (r_));                                                      \
+  }
+
+  for (int base = e_lo; base < e_hi; base += 32) {
+    const int cnt = min(32, e_hi - base);
     int my_src = 0, my_rel = 0;
     if (lane < cnt) {
       my_src = __ldg(a.csr_src + base + lane);
@@ -109,91 +199,19 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
       }
       d0 = head_sum(d0, lm.lph);
       d1 = head_sum(d1, lm.lph);
-      if (lm.sub == 0) {
-        a.z[static_cast<long long>(base + t) * a.H + lm.hh] = d0;
-        if (two) a.z[static_cast<long long>(base + t + 1) * a.H + lm.hh] = d1;
-      }
-      // edge t
-      {
-        const float e = d0 > 0.f ? d0 : kLeakySlope * d0;
-        const float mn = fmaxf(m, e);
-        const float sc = expf(m - mn);
-        const float w = expf(e - mn);
-        l = fmaf(l, sc, w);
-#pragma unroll
-        for (int k = 0; k < kMaxVecPerLane; ++k) {
-          const int q = lm.sub + lm.lph * k;
-          if (q < lm.vph) {
-#pragma unroll
-            for (int v = 0; v < V; ++v) acc[k][v] = fmaf(acc[k][v], sc, w * x0[k][v]);
-          }
-        }
-        m = (e != e) ? e : mn;  // NaN logits poison the row like the reference does
-        if (a.beta) bsum += __ldg(a.beta + r0);
-      }
-      if (two) {
-        const float e = d1 > 0.f ? d1 : kLeakySlope * d1;
-        const float mn = fmaxf(m, e);
-        const float sc = expf(m - mn);
-        const float w = expf(e - mn);
-        l = fmaf(l, sc, w);
-#pragma unroll
-        for (int k = 0; k < kMaxVecPerLane; ++k) {
-          const int q = lm.sub + lm.lph * k;
-          if (q < lm.vph) {
-#pragma unroll
-            for (int v = 0; v < V; ++v) acc[k][v] = fmaf(acc[k][v], sc, w * x1[k][v]);
-          }
-        }
-        m = (e != e) ? e : mn;
-        if (a.beta) bsum += __ldg(a.beta + r1);
-      }
+      RG_EDGE(x0, d0, r0, base + t);
+      if (two) RG_EDGE(x1, d1, r1, base + t + 1);
     }
   }
-
-  const bool empty = (hi == lo);
-  const float inv = empty ? 0.f : 1.f / fmaxf(l, 1e-16f);  // reference layer.py:291 clamp
-  // out = acc / den + bias  (bias is added to every head and channel, layer.py:313-318)
-#pragma unroll
-  for (int k = 0; k < kMaxVecPerLane; ++k) {
-    const int q = lm.sub + lm.lph * k;
-    if (q < lm.vph) {
-      float o[V];
-#pragma unroll
-      for (int v = 0; v < V; ++v) o[v] = empty ? 0.f : fmaf(acc[k][v], inv, bsum);
-      const long long off = static_cast<long long>(j) * C + lm.head_off + q * V;
-      if (a.out) RowVec<float, V>::store(a.out + off, o);
-      if (a.act_hi) {
-        if (a.apply_elu) {
-#pragma unroll
-          for (int v = 0; v < V; ++v) o[v] = elu1(o[v]);
-        }
-        store_split_bf16<V>(a.act_hi + off, a.act_lo ? a.act_lo + off : nullptr, o);
-      }
-    }
-  }
-  if (g == 0 && lane == 0 && a.bias_out) a.bias_out[j] = empty ? 0.f : bsum;
-
-  // attention weights: alpha = exp(eps - m) / den for every (edge, head of this group)
-  __syncwarp();
-  const int items = (hi - lo) * a.hg;
-  for (int it = 0; it < items; it += 32) {
-    const int idx = it + lane;
-    const int hgi = idx % a.hg;
-    const float mh = __shfl_sync(0xffffffffu, m, hgi * lm.lph);
-    const float ih = __shfl_sync(0xffffffffu, inv, hgi * lm.lph);
-    if (idx < items) {
-      const long long o = static_cast<long long>(lo + idx / a.hg) * a.H + g * a.hg + hgi;
-      const float zz = a.z[o];
-      const float e = zz > 0.f ? zz : kLeakySlope * zz;
-      a.alpha[o] = expf(e - mh) * ih;
-    }
-  }
+  while (kn < nn) RG_FINALIZE();  // last destination with edges + trailing empty ones
+#undef RG_EDGE
+#undef RG_FINALIZE
+#undef RG_RP
 }
 
 template <typename T, int V>
 static int launch_fwd(const FwdArgs<T, V>& a, cudaStream_t stream) {
-  const long long tasks = static_cast<long long>(a.N) * (a.H / a.hg);
+  const long long tasks = static_cast<long long>(a.n_chunks) * (a.H / a.hg);
   if (tasks == 0) return RG_OK;
   const long long blocks = (tasks + kFwdWarps - 1) / kFwdWarps;
   edge_fwd_kernel<T, V><<<static_cast<unsigned>(blocks), kFwdWarps * 32, 0, stream>>>(a);
@@ -206,35 +224,30 @@ using namespace relgat;
 
 extern "C" int relgat_layer_fwd(
     const void* P, int p_is_bf16, long long ldp, const float* A, const float* beta,
-    const int* rowptr, const int* csr_src, const int* csr_rel,
+    const int* rowptr, const int* csr_src, const int* csr_rel, const int* chunk_node, int n_chunks,
     float* out, void* act_hi, void* act_lo, int apply_elu,
-    float* alpha, float* z, float* bias_out,
-    int N, int H, int F, int R, int max_deg, void* stream) {
-  if (!P || !A || !rowptr || !alpha || !z || N < 0 || H <= 0 || F <= 0 || R <= 0) return RG_ERR_ARG;
+    float* alpha, float* z, float* minv, float* bias_out,
+    int H, int F, int R, void* stream) {
+  if (!P || !A || !rowptr || !chunk_node || n_chunks < 0 || H <= 0 || F <= 0 || R <= 0) return RG_ERR_ARG;
+  if (p_is_bf16) return RG_ERR_DTYPE;  // bf16 feature storage: not built in this round
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool vec_ok = (reinterpret_cast<uintptr_t>(P) % 16 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0) &&
-                      (!out || reinterpret_cast<uintptr_t>(out) % 16 == 0);
-  if (p_is_bf16) {
-    if (F % 8 != 0 || ldp % 8 != 0) return RG_ERR_SHAPE;
-    if (!vec_ok) return RG_ERR_ALIGN;
-    const int hg = pick_heads_per_warp(H, F, 8);
-    if (!hg) return RG_ERR_SHAPE;
-    // A is read with the fp32 vector type of the same element count: 8 floats = two float4
-    return RG_ERR_DTYPE;  // bf16 feature storage is wired in edge_fwd_bf16.cu (not built yet)
-  }
+                      (!out || reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
+                      (!act_hi || reinterpret_cast<uintptr_t>(act_hi) % 8 == 0) &&
+                      (!act_lo || reinterpret_cast<uintptr_t>(act_lo) % 8 == 0);
   const bool v4 = (F % 4 == 0) && (ldp % 4 == 0) && vec_ok;
   if (v4) {
     const int hg = pick_heads_per_warp(H, F, 4);
     if (!hg) return RG_ERR_SHAPE;
-    FwdArgs<float, 4> a{static_cast<const float*>(P), A, beta, rowptr, csr_src, csr_rel, out,
+    FwdArgs<float, 4> a{static_cast<const float*>(P), A, beta, rowptr, csr_src, csr_rel, chunk_node, out,
                         static_cast<__nv_bfloat16*>(act_hi), static_cast<__nv_bfloat16*>(act_lo),
-                        alpha, z, bias_out, N, H, F, R, hg, ldp, apply_elu, max_deg};
+                        alpha, z, minv, bias_out, n_chunks, H, F, R, hg, ldp, apply_elu};
     return launch_fwd(a, s);
   }
   const int hg = pick_heads_per_warp(H, F, 1);
   if (!hg) return RG_ERR_SHAPE;
-  FwdArgs<float, 1> a{static_cast<const float*>(P), A, beta, rowptr, csr_src, csr_rel, out,
+  FwdArgs<float, 1> a{static_cast<const float*>(P), A, beta, rowptr, csr_src, csr_rel, chunk_node, out,
                       static_cast<__nv_bfloat16*>(act_hi), static_cast<__nv_bfloat16*>(act_lo),
-                      alpha, z, bias_out, N, H, F, R, hg, ldp, apply_elu, max_deg};
+                      alpha, z, minv, bias_out, n_chunks, H, F, R, hg, ldp, apply_elu};
   return launch_fwd(a, s);
 }

@@ -50,9 +50,9 @@ class RelGATStackFunction(torch.autograd.Function):
             Wp = ops.split_bf16(W.detach(), with_lo)
             P = ops.gemm(planes, False, Wp, False, N, C, d_in)
             last = l == L - 1
-            out, act, alpha, z, bias = ops.edge_fwd(P, A.detach(), None if beta is None else beta.detach(), graph,
-                                                    H, F, want_act=not last, apply_elu=True, act_lo=with_lo)
-            saved.append(dict(xp=planes, Wp=Wp, P=P, out=out, alpha=alpha, z=z, bias=bias, A=A.detach(),
+            out, act, _, z, minv, bias = ops.edge_fwd(P, A.detach(), None if beta is None else beta.detach(), graph,
+                                                      H, F, want_act=not last, apply_elu=True, act_lo=with_lo)
+            saved.append(dict(xp=planes, Wp=Wp, P=P, out=out, minv=minv, z=z, bias=bias, A=A.detach(),
                               d_in=d_in, has_beta=beta is not None))
             planes = act
         ctx.saved = saved
@@ -74,7 +74,7 @@ class RelGATStackFunction(torch.autograd.Function):
         for l in reversed(range(L)):
             s = ctx.saved[l]
             G, t, hsum = ops.edge_bwd_prep(dY, s["out"], s["bias"], H, F, apply_elu=(l < L - 1), inplace=owned)
-            _, dPp, dz = ops.edge_bwd_src(s["P"], G, s["A"], s["alpha"], s["z"], t, g, H, F,
+            _, dPp, dz = ops.edge_bwd_src(s["P"], G, s["A"], s["z"], s["minv"], t, g, H, F,
                                           want_fp32=False, want_planes=True, planes_lo=with_lo)
             dA, dbeta = ops.edge_bwd_rel(s["P"], dz, hsum, g, H, F, want_dbeta=s["has_beta"])
             d_in = s["d_in"]

@@ -15,6 +15,25 @@ import torch
 from . import _lib
 
 REL_CHUNK = 256  # edges per by-relation chunk of the dA / dbeta pass
+STREAM_CHUNK_EDGES = 64  # target edges per warp-chunk of the forward / by-source streaming kernels
+STREAM_CHUNK_NODES = 64  # hard cap on segments per chunk (the kernels hold the pointer window in 3 registers)
+
+
+def stream_chunks(ptr: torch.Tensor, chunk_edges: int = STREAM_CHUNK_EDGES,
+                  chunk_nodes: int = STREAM_CHUNK_NODES) -> torch.Tensor:
+    """Cut a CSR pointer array [n+1] into chunks at segment boundaries: a new chunk starts at
+    segment j when its first edge crosses a multiple of ``chunk_edges`` or j is a multiple of
+    ``chunk_nodes``.  Returns chunk_node [n_chunks+1] (int32).  Deterministic, one-off per graph."""
+    n = ptr.numel() - 1
+    if n <= 0:
+        return torch.zeros(1, dtype=torch.int32, device=ptr.device)
+    start = ptr[:-1].to(torch.int64)
+    idx = torch.arange(n, device=ptr.device, dtype=torch.int64)
+    key = (start // chunk_edges) * (n // chunk_nodes + 2) + idx // chunk_nodes
+    new = torch.ones(n, dtype=torch.bool, device=ptr.device)
+    new[1:] = key[1:] != key[:-1]
+    heads = torch.nonzero(new).flatten()
+    return torch.cat([heads, torch.tensor([n], device=ptr.device)]).to(torch.int32)
 
 
 class GraphIndex:
@@ -64,6 +83,10 @@ class GraphIndex:
                 _lib.ptr(ws), ws_bytes, stream)
         _lib.check(rc, "relgat_graph_index_build")
         self._build_rel_chunks()
+        self.fwd_chunk_node = stream_chunks(self.rowptr)
+        self.src_chunk_node = stream_chunks(self.colptr)
+        self.n_fwd_chunks = int(self.fwd_chunk_node.numel()) - 1
+        self.n_src_chunks = int(self.src_chunk_node.numel()) - 1
         self.max_in_degree = int((self.rowptr[1:] - self.rowptr[:-1]).max().item()) if N > 0 else 0
         self.max_out_degree = int((self.colptr[1:] - self.colptr[:-1]).max().item()) if NS > 0 else 0
         del ws

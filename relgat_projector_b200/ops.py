@@ -114,33 +114,36 @@ def pick_splits_k(M: int, N: int, K: int, device) -> int:
 # edge kernels
 # ------------------------------------------------------------------------------------------
 def edge_fwd(P: torch.Tensor, A: torch.Tensor, beta: Optional[torch.Tensor], g: GraphIndex, H: int, F: int,
-             want_act: bool = False, apply_elu: bool = False, act_lo: bool = True, want_out: bool = True):
-    """Returns (out [N, H*F] fp32 or None, act planes or None, alpha [E,H], z [E,H], bias [N])."""
+             want_act: bool = False, apply_elu: bool = False, act_lo: bool = True, want_out: bool = True,
+             want_alpha: bool = False):
+    """Returns (out [N, H*F] fp32 or None, act planes or None, alpha [E,H] or None, z [E,H],
+    minv [N,H,2], bias [N])."""
     P = _f32c(P, "P")
     A = _f32c(A, "A")
     if beta is not None:
         beta = _f32c(beta, "beta")
     dev = P.device
     N, E, R, C = g.N, g.E, g.R, H * F
-    if P.dim() != 2 or P.size(1) != C:
-        raise ValueError(f"P must be [N_src, {C}]")
+    if P.dim() != 2 or P.size(1) != C or P.size(0) != g.N_src:
+        raise ValueError(f"P must be [{g.N_src}, {C}], got {tuple(P.shape)}")
     if tuple(A.shape) != (H, R, F):
         raise ValueError(f"A must be [{H}, {R}, {F}], got {tuple(A.shape)}")
     out = torch.empty((N, C), dtype=torch.float32, device=dev) if want_out else None
     hi = torch.empty((N, C), dtype=torch.bfloat16, device=dev) if want_act else None
     lo = torch.empty((N, C), dtype=torch.bfloat16, device=dev) if (want_act and act_lo) else None
-    alpha = torch.empty((E, H), dtype=torch.float32, device=dev)
+    alpha = torch.empty((E, H), dtype=torch.float32, device=dev) if want_alpha else None
     z = torch.empty((E, H), dtype=torch.float32, device=dev)
+    minv = torch.empty((N, H, 2), dtype=torch.float32, device=dev)
     bias = torch.empty((N,), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         rc = _lib.load().relgat_layer_fwd(
             _lib.ptr(P), 0, P.stride(0), _lib.ptr(A), _lib.ptr(beta),
-            _lib.ptr(g.rowptr), _lib.ptr(g.csr_src), _lib.ptr(g.csr_rel),
+            _lib.ptr(g.rowptr), _lib.ptr(g.csr_src), _lib.ptr(g.csr_rel), _lib.ptr(g.fwd_chunk_node), g.n_fwd_chunks,
             _lib.ptr(out), _lib.ptr(hi), _lib.ptr(lo), int(apply_elu),
-            _lib.ptr(alpha), _lib.ptr(z), _lib.ptr(bias), N, H, F, R, 0, _stream(P))
+            _lib.ptr(alpha), _lib.ptr(z), _lib.ptr(minv), _lib.ptr(bias), H, F, R, _stream(P))
     _lib.check(rc, "relgat_layer_fwd")
     _count(1)
-    return out, ((hi, lo) if want_act else None), alpha, z, bias
+    return out, ((hi, lo) if want_act else None), alpha, z, minv, bias
 
 
 def edge_bwd_prep(dY: torch.Tensor, out: torch.Tensor, bias: torch.Tensor, H: int, F: int,
@@ -149,7 +152,8 @@ def edge_bwd_prep(dY: torch.Tensor, out: torch.Tensor, bias: torch.Tensor, H: in
     dY = _f32c(dY, "dY")
     out = _f32c(out, "out")
     N = out.size(0)
-    G = dY if inplace else torch.empty_like(dY)
+    # without an activation G == dY: nothing to write, alias it (saves a full [N, C] copy)
+    G = dY if (inplace or not apply_elu) else torch.empty_like(dY)
     t = torch.empty((N, H), dtype=torch.float32, device=dY.device)
     hsum = torch.empty((N, H), dtype=torch.float32, device=dY.device)
     with torch.cuda.device(dY.device):
@@ -160,7 +164,7 @@ def edge_bwd_prep(dY: torch.Tensor, out: torch.Tensor, bias: torch.Tensor, H: in
     return G, t, hsum
 
 
-def edge_bwd_src(P, G, A, alpha, z, t, g: GraphIndex, H: int, F: int, want_fp32: bool = True,
+def edge_bwd_src(P, G, A, z, minv, t, g: GraphIndex, H: int, F: int, want_fp32: bool = True,
                  want_planes: bool = False, planes_lo: bool = True):
     """Returns (dP fp32 or None, dP planes or None, dz [E,H])."""
     P = _f32c(P, "P")
@@ -168,15 +172,18 @@ def edge_bwd_src(P, G, A, alpha, z, t, g: GraphIndex, H: int, F: int, want_fp32:
     A = _f32c(A, "A")
     dev = P.device
     n_src, C = P.size(0), H * F
+    if n_src != g.N_src or G.size(0) != g.N:
+        raise ValueError("P / G row counts do not match the graph index")
     dP = torch.empty((n_src, C), dtype=torch.float32, device=dev) if want_fp32 else None
     hi = torch.empty((n_src, C), dtype=torch.bfloat16, device=dev) if want_planes else None
     lo = torch.empty((n_src, C), dtype=torch.bfloat16, device=dev) if (want_planes and planes_lo) else None
     dz = torch.empty((g.E, H), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         rc = _lib.load().relgat_layer_bwd_src(
-            _lib.ptr(P), P.stride(0), _lib.ptr(G), _lib.ptr(A), _lib.ptr(alpha), _lib.ptr(z), _lib.ptr(t),
+            _lib.ptr(P), P.stride(0), _lib.ptr(G), _lib.ptr(A), _lib.ptr(z), _lib.ptr(minv), _lib.ptr(t),
             _lib.ptr(g.colptr), _lib.ptr(g.csc_slot), _lib.ptr(g.csc_dst), _lib.ptr(g.csc_rel),
-            _lib.ptr(dP), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dz), n_src, H, F, g.R, 0, _stream(P))
+            _lib.ptr(g.src_chunk_node), g.n_src_chunks,
+            _lib.ptr(dP), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dz), H, F, g.R, _stream(P))
     _lib.check(rc, "relgat_layer_bwd_src")
     _count(1)
     return dP, ((hi, lo) if want_planes else None), dz

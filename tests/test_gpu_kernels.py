@@ -137,7 +137,7 @@ def test_edge_forward_and_backward_vs_closed_form(dev, n, e, r, H, F, isolated, 
     g = GraphIndex(torch.from_numpy(np.stack([src, dst])).to(dev), torch.from_numpy(rel).to(dev), n, r)
     Pd = torch.from_numpy(P.reshape(n, H * F)).to(dev)
     Ad, bd = torch.from_numpy(A).to(dev), torch.from_numpy(beta).to(dev)
-    out, act, alpha, z, bias = ops.edge_fwd(Pd, Ad, bd, g, H, F, want_act=True, apply_elu=True)
+    out, act, alpha, z, minv, bias = ops.edge_fwd(Pd, Ad, bd, g, H, F, want_act=True, apply_elu=True, want_alpha=True)
     assert rel_err(out.cpu().numpy(), out_ref.reshape(n, -1)) < FP32_TOL
     if e:
         assert rel_err(z.cpu().numpy(), z_ref) < FP32_TOL
@@ -157,7 +157,7 @@ def test_edge_forward_and_backward_vs_closed_form(dev, n, e, r, H, F, isolated, 
     Gd = torch.from_numpy(Gn.reshape(n, -1)).to(dev)
     G, t, hsum = ops.edge_bwd_prep(Gd, out, bias, H, F, apply_elu=False)
     assert torch.equal(G, Gd)
-    dP, planes, dz = ops.edge_bwd_src(Pd, G, Ad, alpha, z, t, g, H, F, want_fp32=True, want_planes=True)
+    dP, planes, dz = ops.edge_bwd_src(Pd, G, Ad, z, minv, t, g, H, F, want_fp32=True, want_planes=True)
     dA, dbeta = ops.edge_bwd_rel(Pd, dz, hsum, g, H, F)
     assert rel_err(dP.cpu().numpy(), dP_ref.reshape(n, -1)) < FP32_TOL
     if e:
@@ -166,8 +166,8 @@ def test_edge_forward_and_backward_vs_closed_form(dev, n, e, r, H, F, isolated, 
     assert rel_err(dbeta.cpu().numpy(), dbeta_ref) < FP32_TOL
     assert rel_err((planes[0].float() + planes[1].float()).cpu().numpy(), dP_ref.reshape(n, -1)) < FP32_TOL
     # determinism: identical bits on a second run
-    out2, _, alpha2, _, _ = ops.edge_fwd(Pd, Ad, bd, g, H, F)
-    dP2, _, dz2 = ops.edge_bwd_src(Pd, G, Ad, alpha, z, t, g, H, F)
+    out2, _, alpha2, _, _, _ = ops.edge_fwd(Pd, Ad, bd, g, H, F, want_alpha=True)
+    dP2, _, dz2 = ops.edge_bwd_src(Pd, G, Ad, z, minv, t, g, H, F)
     dA2, dbeta2 = ops.edge_bwd_rel(Pd, dz, hsum, g, H, F)
     assert torch.equal(out, out2) and torch.equal(alpha, alpha2) and torch.equal(dP, dP2)
     assert torch.equal(dA, dA2) and torch.equal(dbeta, dbeta2)
@@ -203,12 +203,12 @@ def test_large_logits_and_nan_propagation(dev):
     assert np.abs(z_ref).max() > 80
     g = GraphIndex(torch.from_numpy(np.stack([src, dst])).to(dev), torch.from_numpy(rel).to(dev), n, r)
     Pd = torch.from_numpy(P.reshape(n, -1)).to(dev)
-    out, _, alpha, z, _ = ops.edge_fwd(Pd, torch.from_numpy(A).to(dev), None, g, H, F)
+    out, _, alpha, z, _, _ = ops.edge_fwd(Pd, torch.from_numpy(A).to(dev), None, g, H, F, want_alpha=True)
     assert torch.isfinite(out).all()
     assert rel_err(out.cpu().numpy(), out_ref.reshape(n, -1)) < FP32_TOL
     assert rel_err(alpha.cpu().numpy(), alpha_ref) < FP32_TOL
     Pd[7, 3] = float("nan")
-    out_nan, _, _, _, _ = ops.edge_fwd(Pd, torch.from_numpy(A).to(dev), None, g, H, F)
+    out_nan, _, _, _, _, _ = ops.edge_fwd(Pd, torch.from_numpy(A).to(dev), None, g, H, F)
     touched = np.zeros(n, dtype=bool)
     touched[dst[src == 7]] = True
     bad = torch.isnan(out_nan).any(dim=1).cpu().numpy()

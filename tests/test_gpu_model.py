@@ -166,7 +166,7 @@ def test_partitioned_destination_ranges_reproduce_whole_graph(dev):
     P = torch.randn(n, H * F, device=dev)
     A = torch.randn(H, r, F, device=dev) / 5
     beta = torch.randn(r, device=dev) / 10
-    whole, _, _, _, _ = ops.edge_fwd(P, A, beta, GraphIndex(torch.from_numpy(np.stack([src, dst])).to(dev),
+    whole, _, _, _, _, _ = ops.edge_fwd(P, A, beta, GraphIndex(torch.from_numpy(np.stack([src, dst])).to(dev),
                                                             torch.from_numpy(rel).to(dev), n, r), H, F)
     for world in (2, 4):
         bounds = O.partition_bounds_np(dst, n, world, "edges")
@@ -177,6 +177,6 @@ def test_partitioned_destination_ranges_reproduce_whole_graph(dev):
                 continue
             g = GraphIndex(torch.from_numpy(np.stack([s, d - lo])).to(dev), torch.from_numpy(rr).to(dev),
                            hi - lo, r, num_src_nodes=n)
-            part, _, _, _, _ = ops.edge_fwd(P, A, beta, g, H, F)
+            part, _, _, _, _, _ = ops.edge_fwd(P, A, beta, g, H, F)
             rows.append(part)
         assert torch.equal(torch.cat(rows), whole)
