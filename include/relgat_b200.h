@@ -73,7 +73,8 @@ int relgat_gemm_bf16(const void* a_hi, const void* a_lo, long long lda, int a_mn
  * A: [H, R, F] (stacked attn_vec), beta: [R] or NULL.
  * chunk_node [n_chunks+1]: the CSR edge array cut at destination boundaries into chunks of ~64
  * edges and <= 64 destinations (chunk c owns destinations [chunk_node[c], chunk_node[c+1])); one
- * warp streams one chunk, so short segments do not drain the load pipeline.
+ * warp streams one chunk, so short segments do not drain the load pipeline.  The kernels are
+ * persistent (sm_count CTAs; <= 0 means 148) and stage the attention vectors in shared memory.
  * Outputs: out [N, H*F] fp32 pre-activation (may be NULL), optional bf16 (hi, lo) planes of
  * act(out) for the next layer's GEMM (act = ELU if apply_elu, reference model.py:286-287),
  * z [E, H] raw logits and minv [N, H, 2] = (segment max, 1/denominator) saved for backward,
@@ -83,7 +84,7 @@ int relgat_layer_fwd(const void* P, int p_is_bf16, long long ldp, const float* A
                      const int* chunk_node, int n_chunks,
                      float* out, void* act_hi, void* act_lo, int apply_elu,
                      float* alpha, float* z, float* minv, float* bias_out,
-                     int H, int F, int R, void* stream);
+                     int H, int F, int R, int sm_count, void* stream);
 
 /* ---- RelGAT layer, edge part, backward (replaces the autograd replay of layer.py:220-318) ---
  * bwd_prep: G = dY * act'(out) (in place allowed), t[N,H] = <G, out - bias>, hsum[N,H] = sum_f G.
@@ -101,7 +102,7 @@ int relgat_layer_bwd_src(const float* P, long long ldp, const float* G, const fl
                          const int* colptr, const int* csc_slot, const int* csc_dst, const int* csc_rel,
                          const int* chunk_node, int n_chunks,
                          float* dP, void* dP_hi, void* dP_lo, float* dz,
-                         int H, int F, int R, void* stream);
+                         int H, int F, int R, int sm_count, void* stream);
 int relgat_layer_bwd_rel(const float* P, long long ldp, const float* dz, const float* hsum,
                          const int* rel_slot, const int* csr_src, const int* csr_dst,
                          const int* chunk_lo, const int* chunk_hi, const int* rel_chunk_ptr,

@@ -15,6 +15,9 @@ namespace relgat {
 
 constexpr int kMaxVecPerLane = 8;  // KMAX: 128-bit vectors a lane may own per row
 constexpr float kLeakySlope = 0.2f;  // reference layer.py:233
+// shared-memory budget for a head-group's attention vectors (hg*R*F fp32) in the edge kernels;
+// leaves room for the by-source kernel's per-warp own-row slots (12 x 4 KB) inside 227 KB
+constexpr size_t kSmemBudgetA = 176 * 1024;
 
 // ---- error codes of the C ABI (include/relgat_b200.h) ------------------------------
 enum : int {
@@ -51,6 +54,11 @@ struct RowVec<float, 4> {
     const float4 t = *reinterpret_cast<const float4*>(p);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
+  // generic pointer (shared or global): plain 128-bit load
+  static __device__ __forceinline__ void load_any(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
 };
 
 template <>
@@ -59,6 +67,7 @@ struct RowVec<float, 1> {
   static __device__ __forceinline__ void load_cached(const float* p, float (&v)[1]) { v[0] = __ldg(p); }
   static __device__ __forceinline__ void store(float* p, const float (&v)[1]) { *p = v[0]; }
   static __device__ __forceinline__ void load_shared(const float* p, float (&v)[1]) { v[0] = *p; }
+  static __device__ __forceinline__ void load_any(const float* p, float (&v)[1]) { v[0] = *p; }
 };
 
 template <>
@@ -153,17 +162,23 @@ __device__ __forceinline__ float warp_sum(float x) {
   return x;
 }
 
-// Host side: heads per warp for (H, F, V).  Largest power of two dividing H such that a
-// head's F/V vectors fit kMaxVecPerLane per lane.  Returns 0 when no mapping exists.
-inline int pick_heads_per_warp(int H, int F, int V) {
+// Host side: heads per warp for (H, F, V).  Largest power of two dividing H such that a head's
+// F/V vectors fit kMaxVecPerLane per lane and, when R is given, the group's attention vectors
+// (hg*R*F fp32) fit the shared-memory budget; if no group fits the budget the largest
+// register-feasible group is used and the kernels read A through L1/L2 instead.
+// Returns 0 when no mapping exists.
+inline int pick_heads_per_warp(int H, int F, int V, int R = 0) {
   if (H <= 0 || F <= 0 || F % V != 0) return 0;
   const int vph = F / V;
+  int best = 0;
   for (int hg = 32; hg >= 1; hg >>= 1) {
     if (H % hg != 0) continue;
     const int lph = 32 / hg;
-    if ((vph + lph - 1) / lph <= kMaxVecPerLane) return hg;
+    if ((vph + lph - 1) / lph > kMaxVecPerLane) continue;
+    if (!best) best = hg;
+    if (R <= 0 || static_cast<size_t>(hg) * R * F * sizeof(float) <= kSmemBudgetA) return hg;
   }
-  return 0;
+  return best;
 }
 
 }  // namespace relgat

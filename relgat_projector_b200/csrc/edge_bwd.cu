@@ -74,11 +74,14 @@ __global__ void __launch_bounds__(kBwdWarps * 32) bwd_prep_kernel(const PrepArgs
 // ------------------------------------------------------------------------------------
 // bwd_src — edge-balanced streaming over the by-source (CSC) order.
 // The CSC edge array is cut at source boundaries into chunks of ~64 edges (graph.py:
-// src_chunk_node); one warp streams one (chunk, head-group).  The stream is a sequence of
-// row "items": OWN(i) = the source's own P row (needed for dalpha = <G[dst], P[i]>), followed
-// by one EDGE item per out-edge (the gathered G[dst] row).  Two items are in flight per warp
-// and the pipeline does not drain at source boundaries.
+// src_chunk_node).  Persistent CTAs (one per SM, 12 warps) own one head-group and keep its
+// attention vectors in shared memory; a warp streams one chunk at a time as a sequence of row
+// "items": OWN(i) = the source's own P row (needed for dalpha = <G[dst], P[i]>; parked in a
+// lane-private shared-memory slot), followed by one EDGE item per out-edge (the gathered G[dst]
+// row).  Two items are in flight per warp and the pipeline does not drain at source boundaries.
 // ------------------------------------------------------------------------------------
+constexpr int kSrcWarps = 12;
+
 template <int V>
 struct SrcArgs {
   const float* P;       // [N_src, C]   (row stride ldp)
@@ -98,82 +101,80 @@ struct SrcArgs {
   float* dz;            // [E, H] CSR order
   int n_chunks, H, F, R, hg;
   long long ldp;
+  int a_in_smem;
 };
 
 template <int V>
-__global__ void __launch_bounds__(kBwdWarps * 32, 3) bwd_src_kernel(const SrcArgs<V> a) {
+__global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArgs<V> a) {
+  extern __shared__ __align__(16) float dyn_sm[];
+  constexpr int kOwnFloats = kMaxVecPerLane * 32 * V;  // lane-private slots of one warp's own row
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int groups = a.H / a.hg;
-  const long long task = static_cast<long long>(blockIdx.x) * kBwdWarps + warp;
-  if (task >= static_cast<long long>(a.n_chunks) * groups) return;
-  const int c = static_cast<int>(task / groups);
-  const int g = static_cast<int>(task - static_cast<long long>(c) * groups);
+  const int g = blockIdx.y;
   const LaneMap lm = make_lane_map<V>(lane, g, a.hg, a.F);
   const int C = a.H * a.F;
+  const int hl = lm.hh - g * a.hg;
+  float* p_own = dyn_sm + warp * kOwnFloats;
+  float* a_sm = dyn_sm + kSrcWarps * kOwnFloats;
 
-  const int n_lo = a.chunk_node[c];
-  const int nn = a.chunk_node[c + 1] - n_lo;  // 1..64 sources
-  int cp0 = 0, cp1 = 0, cp2 = 0;
-  if (lane <= nn) cp0 = __ldg(a.colptr + n_lo + lane);
-  if (32 + lane <= nn) cp1 = __ldg(a.colptr + n_lo + 32 + lane);
-  if (64 + lane <= nn) cp2 = __ldg(a.colptr + n_lo + 64 + lane);
+  const float* a_base;
+  if (a.a_in_smem) {
+    const float* src = a.A + static_cast<long long>(g) * a.hg * a.R * a.F;
+    const int n = a.hg * a.R * a.F;
+    if ((n & 3) == 0) {
+      for (int i = threadIdx.x * 4; i < n; i += blockDim.x * 4)
+        *reinterpret_cast<float4*>(a_sm + i) = __ldg(reinterpret_cast<const float4*>(src + i));
+    } else {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) a_sm[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    a_base = a_sm + static_cast<long long>(hl) * a.R * a.F;
+  } else {
+    a_base = a.A + static_cast<long long>(lm.hh) * a.R * a.F;
+  }
+
+  enum { IT_NONE = 0, IT_OWN = 1, IT_EDGE = 2, IT_ZERO = 3, IT_END = 4 };
+
+  for (int c = blockIdx.x * kSrcWarps + warp; c < a.n_chunks; c += gridDim.x * kSrcWarps) {
+    const int n_lo = a.chunk_node[c];
+    const int nn = a.chunk_node[c + 1] - n_lo;  // 1..64 sources
+    int cp0 = 0, cp1 = 0, cp2 = 0;
+    if (lane <= nn) cp0 = __ldg(a.colptr + n_lo + lane);
+    if (32 + lane <= nn) cp1 = __ldg(a.colptr + n_lo + 32 + lane);
+    if (64 + lane <= nn) cp2 = __ldg(a.colptr + n_lo + 64 + lane);
 #define RG_CP(k_) ((k_) < 32 ? __shfl_sync(0xffffffffu, cp0, (k_) & 31)       \
                              : ((k_) < 64 ? __shfl_sync(0xffffffffu, cp1, (k_) & 31) \
                                           : __shfl_sync(0xffffffffu, cp2, (k_) & 31)))
-  const int e_lo = RG_CP(0);
-  const int e_hi = RG_CP(nn);
+    const int e_lo = RG_CP(0);
+    const int e_hi = RG_CP(nn);
 
-  // The source's own row lives in shared memory (lane-private slots, so no synchronisation):
-  // it is read once per out-edge, and keeping it out of the register file leaves room for two
-  // gathered rows in flight at 12 warps per SM.
-  __shared__ __align__(16) float p_sm[kBwdWarps][kMaxVecPerLane * 32 * V];
-  float* p_own = &p_sm[warp][0];
-  float acc[kMaxVecPerLane][V];
+    float acc[kMaxVecPerLane][V];
 #pragma unroll
-  for (int k = 0; k < kMaxVecPerLane; ++k)
+    for (int k = 0; k < kMaxVecPerLane; ++k)
 #pragma unroll
-    for (int v = 0; v < V; ++v) acc[k][v] = 0.f;
+      for (int v = 0; v < V; ++v) acc[k][v] = 0.f;
 
-  // fetch cursor (item generation) ------------------------------------------------------
-  int fk = 0;             // node whose items are being generated
-  int fe = e_lo;          // next edge to hand out
-  int f_end = RG_CP(1);   // end of node fk's edges
-  bool own_done = false;  // OWN(fk) already handed out
-  int base = e_lo - 32;   // edge-metadata window [base, base + 32) held across the lanes
-  int my_slot = 0, my_dst = 0, my_rel = 0;
-  // consume cursor ----------------------------------------------------------------------
-  int cur = -1;           // node being accumulated (-1: none yet)
+    // fetch cursor (item generation)
+    int fk = 0;             // source whose items are being generated
+    int fe = e_lo;          // next edge to hand out
+    int f_end = RG_CP(1);   // end of source fk's edges
+    bool own_done = false;  // OWN(fk) already handed out
+    bool end_done = false;  // the closing IT_END item already handed out
+    int base = e_lo - 32;   // edge-metadata window [base, base + 32) held across the lanes
+    int my_slot = 0, my_dst = 0, my_rel = 0;
+    int cur = -1;           // source being accumulated by the consumer (-1: none yet)
 
-  enum { IT_NONE = 0, IT_OWN = 1, IT_EDGE = 2 };
-
-  // writes dP for node n_lo + cur
-#define RG_WRITE_ROW(node_, zero_)                                                             \
-  {                                                                                            \
-    _Pragma("unroll") for (int k = 0; k < kMaxVecPerLane; ++k) {                               \
-      const int q = lm.sub + lm.lph * k;                                                       \
-      if (q < lm.vph) {                                                                        \
-        float o[V];                                                                            \
-        _Pragma("unroll") for (int v = 0; v < V; ++v) o[v] = (zero_) ? 0.f : acc[k][v];        \
-        const long long off = static_cast<long long>(n_lo + (node_)) * C + lm.head_off + q * V; \
-        if (a.dP) RowVec<float, V>::store(a.dP + off, o);                                      \
-        if (a.dP_hi) store_split_bf16<V>(a.dP_hi + off, a.dP_lo ? a.dP_lo + off : nullptr, o); \
-      }                                                                                        \
-    }                                                                                          \
-  }
-
-  // next item of the stream: type / node / (slot, dst, rel)
+    // next item of the stream: OWN(k) | ZERO(k) (source without out-edges) | EDGE | END | NONE
 #define RG_NEXT(ty_, nd_, sl_, ds_, rl_)                                                       \
   {                                                                                            \
     ty_ = IT_NONE; nd_ = 0; sl_ = 0; ds_ = 0; rl_ = 0;                                         \
-    while (fk < nn) {                                                                          \
+    while (true) {                                                                             \
+      if (fk >= nn) {                                                                          \
+        if (!end_done) { end_done = true; ty_ = IT_END; }                                      \
+        break;                                                                                 \
+      }                                                                                        \
       if (!own_done) {                                                                         \
-        if (f_end == fe) { /* source without out-edges: dP row is exactly zero */              \
-          RG_WRITE_ROW(fk, true);                                                              \
-          ++fk;                                                                                \
-          if (fk < nn) f_end = RG_CP(fk + 1);                                                  \
-          continue;                                                                            \
-        }                                                                                      \
-        own_done = true; ty_ = IT_OWN; nd_ = fk;                                               \
+        own_done = true; nd_ = fk;                                                             \
+        ty_ = (f_end == fe) ? IT_ZERO : IT_OWN;                                                \
         break;                                                                                 \
       }                                                                                        \
       if (fe < f_end) {                                                                        \
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 3) bwd_src_kernel(const SrcArg
   }
 
 #define RG_ISSUE(ty_, nd_, ds_, x_)                                                            \
-  if (ty_ != IT_NONE) {                                                                        \
+  if (ty_ == IT_OWN || ty_ == IT_EDGE) {                                                       \
     const float* rowp = (ty_ == IT_OWN)                                                        \
         ? a.P + static_cast<long long>(n_lo + (nd_)) * a.ldp + lm.head_off                     \
         : a.G + static_cast<long long>(ds_) * C + lm.head_off;                                 \
@@ -208,16 +209,8 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 3) bwd_src_kernel(const SrcArg
     }                                                                                          \
   }
 
-#define RG_CONSUME(ty_, nd_, sl_, ds_, rl_, x_, zz_, mi_, tt_)                                 \
-  if (ty_ == IT_OWN) {                                                                         \
-    if (cur >= 0) RG_WRITE_ROW(cur, false);                                                    \
-    cur = (nd_);                                                                               \
-    _Pragma("unroll") for (int k = 0; k < kMaxVecPerLane; ++k) {                               \
-      const int q = lm.sub + lm.lph * k;                                                       \
-      if (q < lm.vph) RowVec<float, V>::store(p_own + (k * 32 + lane) * V, x_[k]);             \
-      _Pragma("unroll") for (int v = 0; v < V; ++v) acc[k][v] = 0.f;                           \
-    }                                                                                          \
-  } else if (ty_ == IT_EDGE) {                                                                 \
+#define RG_EDGE_ITEM(sl_, rl_, x_, zz_, mi_, tt_)                                              \
+  {                                                                                            \
     float dd = 0.f;                                                                            \
     _Pragma("unroll") for (int k = 0; k < kMaxVecPerLane; ++k) {                               \
       const int q = lm.sub + lm.lph * k;                                                       \
@@ -229,50 +222,83 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 3) bwd_src_kernel(const SrcArg
     }                                                                                          \
     dd = head_sum(dd, lm.lph); /* dalpha */                                                    \
     const float ee = zz_ > 0.f ? zz_ : kLeakySlope * zz_;                                      \
-    const float al = expf(ee - mi_.x) * mi_.y;                                                 \
+    const float al = __expf(ee - mi_.x) * mi_.y;                                               \
     const float dzv = al * (dd - tt_) * (zz_ > 0.f ? 1.f : kLeakySlope);                       \
     if (lm.sub == 0) a.dz[static_cast<long long>(sl_) * a.H + lm.hh] = dzv;                    \
-    const float* ar = a.A + (static_cast<long long>(lm.hh) * a.R + (rl_)) * a.F;               \
+    const float* ar = a_base + static_cast<long long>(rl_) * a.F;                              \
     _Pragma("unroll") for (int k = 0; k < kMaxVecPerLane; ++k) {                               \
       const int q = lm.sub + lm.lph * k;                                                       \
       if (q < lm.vph) {                                                                        \
         float av[V];                                                                           \
-        RowVec<float, V>::load_cached(ar + q * V, av);                                         \
+        RowVec<float, V>::load_any(ar + q * V, av);                                            \
         _Pragma("unroll") for (int v = 0; v < V; ++v)                                          \
           acc[k][v] = fmaf(al, x_[k][v], fmaf(dzv, av[v], acc[k][v]));                         \
       }                                                                                        \
     }                                                                                          \
   }
 
-  while (true) {
-    int ty0, nd0, sl0, ds0, rl0, ty1, nd1, sl1, ds1, rl1;
-    RG_NEXT(ty0, nd0, sl0, ds0, rl0);
-    if (ty0 == IT_NONE) break;
-    RG_NEXT(ty1, nd1, sl1, ds1, rl1);
-    float x0[kMaxVecPerLane][V], x1[kMaxVecPerLane][V];
-    RG_ISSUE(ty0, nd0, ds0, x0);
-    RG_ISSUE(ty1, nd1, ds1, x1);
-    float z0 = 0.f, z1 = 0.f, t0 = 0.f, t1 = 0.f;
-    float2 mi0 = make_float2(0.f, 0.f), mi1 = make_float2(0.f, 0.f);
-    if (ty0 == IT_EDGE) {
-      z0 = __ldg(a.z + static_cast<long long>(sl0) * a.H + lm.hh);
-      t0 = __ldg(a.t + static_cast<long long>(ds0) * a.H + lm.hh);
-      mi0 = __ldg(reinterpret_cast<const float2*>(a.minv) + static_cast<long long>(ds0) * a.H + lm.hh);
+    while (true) {
+      int ty0, nd0, sl0, ds0, rl0, ty1, nd1, sl1, ds1, rl1;
+      RG_NEXT(ty0, nd0, sl0, ds0, rl0);
+      if (ty0 == IT_NONE) break;
+      RG_NEXT(ty1, nd1, sl1, ds1, rl1);
+      float x0[kMaxVecPerLane][V], x1[kMaxVecPerLane][V];
+      RG_ISSUE(ty0, nd0, ds0, x0);
+      RG_ISSUE(ty1, nd1, ds1, x1);
+      float z0 = 0.f, z1 = 0.f, t0 = 0.f, t1 = 0.f;
+      float2 mi0 = make_float2(0.f, 0.f), mi1 = make_float2(0.f, 0.f);
+      if (ty0 == IT_EDGE) {
+        z0 = __ldg(a.z + static_cast<long long>(sl0) * a.H + lm.hh);
+        t0 = __ldg(a.t + static_cast<long long>(ds0) * a.H + lm.hh);
+        mi0 = __ldg(reinterpret_cast<const float2*>(a.minv) + static_cast<long long>(ds0) * a.H + lm.hh);
+      }
+      if (ty1 == IT_EDGE) {
+        z1 = __ldg(a.z + static_cast<long long>(sl1) * a.H + lm.hh);
+        t1 = __ldg(a.t + static_cast<long long>(ds1) * a.H + lm.hh);
+        mi1 = __ldg(reinterpret_cast<const float2*>(a.minv) + static_cast<long long>(ds1) * a.H + lm.hh);
+      }
+      for (int u = 0; u < 2; ++u) {  // not unrolled: the row write below exists once in the code
+        const int ty = u ? ty1 : ty0;
+        if (ty == IT_NONE) break;
+        if (ty == IT_EDGE) {
+          if (u == 0) RG_EDGE_ITEM(sl0, rl0, x0, z0, mi0, t0) else RG_EDGE_ITEM(sl1, rl1, x1, z1, mi1, t1);
+          continue;
+        }
+        // OWN / ZERO / END: close the source being accumulated, then open the next one
+        if (cur >= 0) {
+#pragma unroll
+          for (int k = 0; k < kMaxVecPerLane; ++k) {
+            const int q = lm.sub + lm.lph * k;
+            if (q < lm.vph) {
+              const long long off = static_cast<long long>(n_lo + cur) * C + lm.head_off + q * V;
+              if (a.dP) RowVec<float, V>::store(a.dP + off, acc[k]);
+              if (a.dP_hi) store_split_bf16<V>(a.dP_hi + off, a.dP_lo ? a.dP_lo + off : nullptr, acc[k]);
+            }
+          }
+        }
+        cur = (ty == IT_END) ? -1 : (u ? nd1 : nd0);
+#pragma unroll
+        for (int k = 0; k < kMaxVecPerLane; ++k) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[k][v] = 0.f;
+        }
+        if (ty == IT_OWN) {
+#pragma unroll
+          for (int k = 0; k < kMaxVecPerLane; ++k) {
+            const int q = lm.sub + lm.lph * k;
+            if (q < lm.vph) {
+              if (u == 0) RowVec<float, V>::store(p_own + (k * 32 + lane) * V, x0[k]);
+              else RowVec<float, V>::store(p_own + (k * 32 + lane) * V, x1[k]);
+            }
+          }
+        }
+      }
     }
-    if (ty1 == IT_EDGE) {
-      z1 = __ldg(a.z + static_cast<long long>(sl1) * a.H + lm.hh);
-      t1 = __ldg(a.t + static_cast<long long>(ds1) * a.H + lm.hh);
-      mi1 = __ldg(reinterpret_cast<const float2*>(a.minv) + static_cast<long long>(ds1) * a.H + lm.hh);
-    }
-    RG_CONSUME(ty0, nd0, sl0, ds0, rl0, x0, z0, mi0, t0);
-    RG_CONSUME(ty1, nd1, sl1, ds1, rl1, x1, z1, mi1, t1);
-  }
-  if (cur >= 0) RG_WRITE_ROW(cur, false);
-#undef RG_CONSUME
+#undef RG_EDGE_ITEM
 #undef RG_ISSUE
 #undef RG_NEXT
-#undef RG_WRITE_ROW
 #undef RG_CP
+  }
 }
 
 // ------------------------------------------------------------------------------------
@@ -422,30 +448,50 @@ extern "C" int relgat_layer_bwd_prep(const float* dY, const float* out, const fl
   return launch_tasks(bwd_prep_kernel<1>, a, static_cast<long long>(N) * (H / hg), s);
 }
 
+template <int V>
+static int launch_src(SrcArgs<V> a, int sm_count, cudaStream_t s) {
+  if (a.n_chunks == 0) return RG_OK;
+  const int groups = a.H / a.hg;
+  if (sm_count <= 0) sm_count = 148;
+  int ctas = sm_count / groups;
+  if (ctas < 1) ctas = 1;
+  const int need = (a.n_chunks + kSrcWarps - 1) / kSrcWarps;
+  if (ctas > need) ctas = need;
+  const size_t own_bytes = static_cast<size_t>(kSrcWarps) * kMaxVecPerLane * 32 * V * sizeof(float);
+  const size_t a_bytes = static_cast<size_t>(a.hg) * a.R * a.F * sizeof(float);
+  a.a_in_smem = a_bytes <= kSmemBudgetA ? 1 : 0;
+  const size_t smem = own_bytes + (a.a_in_smem ? a_bytes : 0);
+  cudaError_t e = cudaFuncSetAttribute(bwd_src_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(own_bytes + kSmemBudgetA));
+  if (e != cudaSuccess) return cuda_status(e);
+  bwd_src_kernel<V><<<dim3(ctas, groups), kSrcWarps * 32, smem, s>>>(a);
+  return cuda_status(cudaGetLastError());
+}
+
 extern "C" int relgat_layer_bwd_src(const float* P, long long ldp, const float* G, const float* A,
                                     const float* z, const float* minv, const float* t,
                                     const int* colptr, const int* csc_slot, const int* csc_dst, const int* csc_rel,
                                     const int* chunk_node, int n_chunks,
                                     float* dP, void* dP_hi, void* dP_lo, float* dz,
-                                    int H, int F, int R, void* stream) {
+                                    int H, int F, int R, int sm_count, void* stream) {
   if (!P || !G || !A || !colptr || !chunk_node || n_chunks < 0 || H <= 0 || F <= 0 || R <= 0) return RG_ERR_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool planes_ok = (!dP_hi || reinterpret_cast<uintptr_t>(dP_hi) % 8 == 0) &&
                          (!dP_lo || reinterpret_cast<uintptr_t>(dP_lo) % 8 == 0);
   if (F % 4 == 0 && ldp % 4 == 0 && al16(P) && al16(G) && al16(A) && (!dP || al16(dP)) && planes_ok) {
-    const int hg = pick_heads_per_warp(H, F, 4);
+    const int hg = pick_heads_per_warp(H, F, 4, R);
     if (!hg) return RG_ERR_SHAPE;
     SrcArgs<4> a{P, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, chunk_node, dP,
                  static_cast<__nv_bfloat16*>(dP_hi), static_cast<__nv_bfloat16*>(dP_lo), dz,
-                 n_chunks, H, F, R, hg, ldp};
-    return launch_tasks(bwd_src_kernel<4>, a, static_cast<long long>(n_chunks) * (H / hg), s);
+                 n_chunks, H, F, R, hg, ldp, 0};
+    return launch_src(a, sm_count, s);
   }
-  const int hg = pick_heads_per_warp(H, F, 1);
+  const int hg = pick_heads_per_warp(H, F, 1, R);
   if (!hg) return RG_ERR_SHAPE;
   SrcArgs<1> a{P, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, chunk_node, dP,
                static_cast<__nv_bfloat16*>(dP_hi), static_cast<__nv_bfloat16*>(dP_lo), dz,
-               n_chunks, H, F, R, hg, ldp};
-  return launch_tasks(bwd_src_kernel<1>, a, static_cast<long long>(n_chunks) * (H / hg), s);
+               n_chunks, H, F, R, hg, ldp, 0};
+  return launch_src(a, sm_count, s);
 }
 
 extern "C" int relgat_layer_bwd_rel(const float* P, long long ldp, const float* dz, const float* hsum,
@@ -453,7 +499,8 @@ extern "C" int relgat_layer_bwd_rel(const float* P, long long ldp, const float* 
                                     const int* chunk_lo, const int* chunk_hi, const int* rel_chunk_ptr,
                                     int n_chunks, float* partA, float* partB, float* dA, float* dbeta,
                                     int H, int F, int R, void* stream) {
-  if (!P || !dz || !hsum || !rel_chunk_ptr || !dA || n_chunks < 0 || H <= 0 || F <= 0 || R <= 0) return RG_ERR_ARG;
+  if (!P || !hsum || !rel_chunk_ptr || !dA || n_chunks < 0 || H <= 0 || F <= 0 || R <= 0) return RG_ERR_ARG;
+  if (n_chunks > 0 && !dz) return RG_ERR_ARG;
   if (n_chunks > 0 && (!rel_slot || !csr_src || !csr_dst || !chunk_lo || !chunk_hi || !partA || !partB))
     return RG_ERR_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -3,7 +3,8 @@
 // weighted aggregation and relation bias in ONE pass over the CSR (by-destination) edges.
 //
 // Work decomposition: the CSR edge array is cut, at destination boundaries, into chunks of
-// ~64 edges (graph.py: fwd_chunk_node).  One warp streams one (chunk, head-group): the source
+// ~64 edges (graph.py: fwd_chunk_node).  Persistent CTAs (one per SM, 12 warps) own one head-group
+// and keep its attention vectors in shared memory; a warp streams one chunk at a time: the source
 // rows P[src] are gathered with 128-bit streaming loads, two rows in flight per warp, and the
 // pipeline does not drain at destination boundaries — a destination is "finalised" (normalise,
 // add bias, write the row, save the softmax statistics) when the stream crosses into the next
@@ -18,7 +19,7 @@
 
 namespace relgat {
 
-constexpr int kFwdWarps = 4;
+constexpr int kFwdWarps = 12;  // one persistent CTA per SM: 12 warps x <=170 registers
 
 template <typename T, int V>
 struct FwdArgs {
@@ -39,106 +40,75 @@ struct FwdArgs {
   int n_chunks, H, F, R, hg;
   long long ldp;         // row stride of P in elements
   int apply_elu;         // act = ELU (reference model.py:286-287) else identity
+  int a_in_smem;         // the head-group's slice of A (hg*R*F floats) is staged in shared memory
 };
 
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
 
+// grid = (CTAs per head-group, head-groups); every CTA is persistent and owns one head-group, so
+// it stages only that group's attention vectors (ncu on the first version showed the per-edge
+// A-row reads missing L1 ~40-70% of the time and doubling the L2->SM traffic).
 template <typename T, int V>
-__global__ void __launch_bounds__(kFwdWarps * 32, 3)
+__global__ void __launch_bounds__(kFwdWarps * 32, 1)
 edge_fwd_kernel(const FwdArgs<T, V> a) {
+  extern __shared__ __align__(16) float a_sm[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int groups = a.H / a.hg;
-  const long long task = static_cast<long long>(blockIdx.x) * kFwdWarps + warp;
-  if (task >= static_cast<long long>(a.n_chunks) * groups) return;
-  const int c = static_cast<int>(task / groups);
-  const int g = static_cast<int>(task - static_cast<long long>(c) * groups);
+  const int g = blockIdx.y;
   const LaneMap lm = make_lane_map<V>(lane, g, a.hg, a.F);
   const int C = a.H * a.F;
+  const int hl = lm.hh - g * a.hg;  // head index inside the group
 
-  const int n_lo = a.chunk_node[c];
-  const int nn = a.chunk_node[c + 1] - n_lo;  // 1..64 destinations
-  // rowptr window of the chunk, spread over the lanes (nn + 1 <= 65 entries)
-  int rp0 = 0, rp1 = 0, rp2 = 0;
-  if (lane <= nn) rp0 = __ldg(a.rowptr + n_lo + lane);
-  if (32 + lane <= nn) rp1 = __ldg(a.rowptr + n_lo + 32 + lane);
-  if (64 + lane <= nn) rp2 = __ldg(a.rowptr + n_lo + 64 + lane);
+  const float* a_base;  // rows of this lane's head: a_base + r * F
+  if (a.a_in_smem) {
+    const float* src = a.A + static_cast<long long>(g) * a.hg * a.R * a.F;
+    const int n = a.hg * a.R * a.F;
+    if ((n & 3) == 0) {
+      for (int i = threadIdx.x * 4; i < n; i += blockDim.x * 4)
+        *reinterpret_cast<float4*>(a_sm + i) = __ldg(reinterpret_cast<const float4*>(src + i));
+    } else {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) a_sm[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    a_base = a_sm + static_cast<long long>(hl) * a.R * a.F;
+  } else {
+    a_base = a.A + static_cast<long long>(lm.hh) * a.R * a.F;
+  }
+
+  for (int c = blockIdx.x * kFwdWarps + warp; c < a.n_chunks; c += gridDim.x * kFwdWarps) {
+    const int n_lo = a.chunk_node[c];
+    const int nn = a.chunk_node[c + 1] - n_lo;  // 1..64 destinations
+    // rowptr window of the chunk, spread over the lanes (nn + 1 <= 65 entries)
+    int rp0 = 0, rp1 = 0, rp2 = 0;
+    if (lane <= nn) rp0 = __ldg(a.rowptr + n_lo + lane);
+    if (32 + lane <= nn) rp1 = __ldg(a.rowptr + n_lo + 32 + lane);
+    if (64 + lane <= nn) rp2 = __ldg(a.rowptr + n_lo + 64 + lane);
 #define RG_RP(k_) ((k_) < 32 ? __shfl_sync(0xffffffffu, rp0, (k_) & 31)       \
                              : ((k_) < 64 ? __shfl_sync(0xffffffffu, rp1, (k_) & 31) \
                                           : __shfl_sync(0xffffffffu, rp2, (k_) & 31)))
-  const int e_lo = RG_RP(0);
-  const int e_hi = RG_RP(nn);
+    const int e_lo = RG_RP(0);
+    const int e_hi = RG_RP(nn);
 
-  float acc[kMaxVecPerLane][V];
+    float acc[kMaxVecPerLane][V];
 #pragma unroll
-  for (int k = 0; k < kMaxVecPerLane; ++k)
+    for (int k = 0; k < kMaxVecPerLane; ++k)
 #pragma unroll
-    for (int v = 0; v < V; ++v) acc[k][v] = 0.f;
-  float m = -INFINITY, l = 0.f, bsum = 0.f;
-  int kn = 0;               // destination cursor inside the chunk
-  int seg_start = e_lo;
-  int seg_end = RG_RP(1);
+      for (int v = 0; v < V; ++v) acc[k][v] = 0.f;
+    float m = -INFINITY, l = 0.f, bsum = 0.f;
+    int kn = 0;  // destination cursor inside the chunk
+    int seg_start = e_lo;
+    int seg_end = RG_RP(1);
+    int base = e_lo - 32;  // (src, rel) window [base, base + 32) held across the lanes
+    int my_src = 0, my_rel = 0;
 
-  // writes destination n_lo + kn and resets the running state
-#define RG_FINALIZE()                                                                              \
-  {                                                                                                \
-    const int j = n_lo + kn;                                                                       \
-    const bool empty = (seg_end == seg_start);                                                     \
-    const float inv = empty ? 0.f : 1.f / fmaxf(l, 1e-16f); /* reference layer.py:291 clamp */     \
-    _Pragma("unroll") for (int k = 0; k < kMaxVecPerLane; ++k) {                                   \
-      const int q = lm.sub + lm.lph * k;                                                           \
-      if (q < lm.vph) {                                                                            \
-        float o[V];                                                                                \
-        _Pragma("unroll") for (int v = 0; v < V; ++v) {                                            \
-          o[v] = empty ? 0.f : fmaf(acc[k][v], inv, bsum); /* bias on every head/channel :313-318 */ \
-          acc[k][v] = 0.f;                                                                         \
-        }                                                                                          \
-        const long long off = static_cast<long long>(j) * C + lm.head_off + q * V;                 \
-        if (a.out) RowVec<float, V>::store(a.out + off, o);                                        \
-        if (a.act_hi) {                                                                            \
-          if (a.apply_elu) {                                                                       \
-            _Pragma("unroll") for (int v = 0; v < V; ++v) o[v] = elu1(o[v]);                       \
-          }                                                                                        \
-          store_split_bf16<V>(a.act_hi + off, a.act_lo ? a.act_lo + off : nullptr, o);             \
-        }                                                                                          \
-      }                                                                                            \
-    }                                                                                              \
-    if (g == 0 && lane == 0 && a.bias_out) a.bias_out[j] = empty ? 0.f : bsum;                     \
-    if (lm.sub == 0 && a.minv) {                                                                   \
-      *reinterpret_cast<float2*>(a.minv + (static_cast<long long>(j) * a.H + lm.hh) * 2) =         \
-          make_float2(empty ? 0.f : m, inv);                                                       \
-    }                                                                                              \
-    if (a.alpha) { /* alpha = exp(eps - m) / den for every (edge, head of this group) */           \
-      __syncwarp();                                                                                \
-      const int items = (seg_end - seg_start) * a.hg;                                              \
-      for (int it = 0; it < items; it += 32) {                                                     \
-        const int idx = it + lane;                                                                 \
-        const int hgi = idx % a.hg;                                                                \
-        const float mh = __shfl_sync(0xffffffffu, m, hgi * lm.lph);                                \
-        const float ih = __shfl_sync(0xffffffffu, inv, hgi * lm.lph);                              \
-        if (idx < items) {                                                                         \
-          const long long o = static_cast<long long>(seg_start + idx / a.hg) * a.H + g * a.hg + hgi; \
-          const float zz = a.z[o];                                                                 \
-          const float ee = zz > 0.f ? zz : kLeakySlope * zz;                                       \
-          a.alpha[o] = expf(ee - mh) * ih;                                                         \
-        }                                                                                          \
-      }                                                                                            \
-    }                                                                                              \
-    m = -INFINITY; l = 0.f; bsum = 0.f;                                                            \
-    ++kn;                                                                                          \
-    seg_start = seg_end;                                                                           \
-    if (kn < nn) seg_end = RG_RP(kn + 1);                                                          \
-  }
-
-  // one edge: logit, online softmax update, weighted accumulate
+    // one edge: online softmax update + weighted accumulate (logit d_ already reduced)
 #define RG_EDGE(x_, d_, r_, e_)                                                                    \
   {                                                                                                \
-    while (kn < nn && (e_) == seg_end) RG_FINALIZE();                                              \
     if (lm.sub == 0) a.z[static_cast<long long>(e_) * a.H + lm.hh] = (d_);                         \
     const float ev = (d_) > 0.f ? (d_) : kLeakySlope * (d_);                                       \
     const float mn = fmaxf(m, ev);                                                                 \
-    const float sc = expf(m - mn);                                                                 \
-    const float w = expf(ev - mn);                                                                 \
+    const float sc = __expf(m - mn);                                                               \
+    const float w = __expf(ev - mn);                                                               \
     l = fmaf(l, sc, w);                                                                            \
     _Pragma("unroll") for (int k = 0; k < kMaxVecPerLane; ++k) {                                   \
       const int q = lm.sub + lm.lph * k;                                                           \
@@ -150,71 +120,147 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
     if (a.beta) bsum += __ldg(a.beta + (r_));                                                      \
   }
 
-  for (int base = e_lo; base < e_hi; base += 32) {
-    const int cnt = min(32, e_hi - base);
-    int my_src = 0, my_rel = 0;
-    if (lane < cnt) {
-      my_src = __ldg(a.csr_src + base + lane);
-      my_rel = __ldg(a.csr_rel + base + lane);
-    }
-    for (int t = 0; t < cnt; t += 2) {
-      const bool two = (t + 1 < cnt);
-      const int i0 = __shfl_sync(0xffffffffu, my_src, t);
-      const int r0 = __shfl_sync(0xffffffffu, my_rel, t);
-      const int i1 = __shfl_sync(0xffffffffu, my_src, two ? t + 1 : t);
-      const int r1 = __shfl_sync(0xffffffffu, my_rel, two ? t + 1 : t);
-      const T* p0 = a.P + static_cast<long long>(i0) * a.ldp + lm.head_off;
-      const T* p1 = a.P + static_cast<long long>(i1) * a.ldp + lm.head_off;
-      const float* a0 = a.A + (static_cast<long long>(lm.hh) * a.R + r0) * a.F;
-      const float* a1 = a.A + (static_cast<long long>(lm.hh) * a.R + r1) * a.F;
-      float x0[kMaxVecPerLane][V], x1[kMaxVecPerLane][V];
-      // issue both row gathers before any arithmetic (two rows in flight per warp)
-#pragma unroll
-      for (int k = 0; k < kMaxVecPerLane; ++k) {
-        const int q = lm.sub + lm.lph * k;
-        if (q < lm.vph) RowVec<T, V>::load_stream(p0 + q * V, x0[k]);
+    int e = e_lo;
+    while (true) {
+      if (e < e_hi && e >= base + 32) {
+        base = e;
+        const int idx = base + lane;
+        if (idx < e_hi) {
+          my_src = __ldg(a.csr_src + idx);
+          my_rel = __ldg(a.csr_rel + idx);
+        }
       }
-      if (two) {
+      const int npair = min(2, min(e_hi - e, base + 32 - e));  // 0 only when the chunk is exhausted
+      float x0[kMaxVecPerLane][V], x1[kMaxVecPerLane][V];
+      float d0 = 0.f, d1 = 0.f;
+      int r0 = 0, r1 = 0;
+      if (npair > 0) {
+        const bool two = npair == 2;
+        const int t = e - base;
+        const int i0 = __shfl_sync(0xffffffffu, my_src, t);
+        r0 = __shfl_sync(0xffffffffu, my_rel, t);
+        const int i1 = __shfl_sync(0xffffffffu, my_src, two ? t + 1 : t);
+        r1 = __shfl_sync(0xffffffffu, my_rel, two ? t + 1 : t);
+        const T* p0 = a.P + static_cast<long long>(i0) * a.ldp + lm.head_off;
+        const T* p1 = a.P + static_cast<long long>(i1) * a.ldp + lm.head_off;
+        // issue both row gathers before any arithmetic (two rows in flight per warp)
 #pragma unroll
         for (int k = 0; k < kMaxVecPerLane; ++k) {
           const int q = lm.sub + lm.lph * k;
-          if (q < lm.vph) RowVec<T, V>::load_stream(p1 + q * V, x1[k]);
+          if (q < lm.vph) RowVec<T, V>::load_stream(p0 + q * V, x0[k]);
         }
-      }
-      float d0 = 0.f, d1 = 0.f;
+        if (two) {
 #pragma unroll
-      for (int k = 0; k < kMaxVecPerLane; ++k) {
-        const int q = lm.sub + lm.lph * k;
-        if (q < lm.vph) {
-          float av[V];
-          RowVec<float, V>::load_cached(a0 + q * V, av);
-#pragma unroll
-          for (int v = 0; v < V; ++v) d0 = fmaf(x0[k][v], av[v], d0);
-          if (two) {
-            RowVec<float, V>::load_cached(a1 + q * V, av);
-#pragma unroll
-            for (int v = 0; v < V; ++v) d1 = fmaf(x1[k][v], av[v], d1);
+          for (int k = 0; k < kMaxVecPerLane; ++k) {
+            const int q = lm.sub + lm.lph * k;
+            if (q < lm.vph) RowVec<T, V>::load_stream(p1 + q * V, x1[k]);
           }
         }
+        const float* a0 = a_base + static_cast<long long>(r0) * a.F;
+        const float* a1 = a_base + static_cast<long long>(r1) * a.F;
+#pragma unroll
+        for (int k = 0; k < kMaxVecPerLane; ++k) {
+          const int q = lm.sub + lm.lph * k;
+          if (q < lm.vph) {
+            float av[V];
+            RowVec<float, V>::load_any(a0 + q * V, av);
+#pragma unroll
+            for (int v = 0; v < V; ++v) d0 = fmaf(x0[k][v], av[v], d0);
+            if (two) {
+              RowVec<float, V>::load_any(a1 + q * V, av);
+#pragma unroll
+              for (int v = 0; v < V; ++v) d1 = fmaf(x1[k][v], av[v], d1);
+            }
+          }
+        }
+        d0 = head_sum(d0, lm.lph);
+        d1 = head_sum(d1, lm.lph);
       }
-      d0 = head_sum(d0, lm.lph);
-      d1 = head_sum(d1, lm.lph);
-      RG_EDGE(x0, d0, r0, base + t);
-      if (two) RG_EDGE(x1, d1, r1, base + t + 1);
+      // consume the pair; destinations are finalised (ONE code site) whenever the edge cursor
+      // reaches the end of the current segment, including empty and trailing destinations
+      int u = 0;
+      while (true) {
+        const int cur = e + u;
+        if (kn < nn && cur == seg_end) {
+          const int j = n_lo + kn;
+          const bool empty = (seg_end == seg_start);
+          const float inv = empty ? 0.f : 1.f / fmaxf(l, 1e-16f);  // reference layer.py:291 clamp
+#pragma unroll
+          for (int k = 0; k < kMaxVecPerLane; ++k) {
+            const int q = lm.sub + lm.lph * k;
+            if (q < lm.vph) {
+              float o[V];
+#pragma unroll
+              for (int v = 0; v < V; ++v) {
+                o[v] = empty ? 0.f : fmaf(acc[k][v], inv, bsum);  // bias on every head/channel, :313-318
+                acc[k][v] = 0.f;
+              }
+              const long long off = static_cast<long long>(j) * C + lm.head_off + q * V;
+              if (a.out) RowVec<float, V>::store(a.out + off, o);
+              if (a.act_hi) {
+                if (a.apply_elu) {
+#pragma unroll
+                  for (int v = 0; v < V; ++v) o[v] = elu1(o[v]);
+                }
+                store_split_bf16<V>(a.act_hi + off, a.act_lo ? a.act_lo + off : nullptr, o);
+              }
+            }
+          }
+          if (g == 0 && lane == 0 && a.bias_out) a.bias_out[j] = empty ? 0.f : bsum;
+          if (lm.sub == 0 && a.minv) {
+            *reinterpret_cast<float2*>(a.minv + (static_cast<long long>(j) * a.H + lm.hh) * 2) =
+                make_float2(empty ? 0.f : m, inv);
+          }
+          if (a.alpha) {  // alpha = exp(eps - m) / den for every (edge, head of this group)
+            __syncwarp();
+            const int items = (seg_end - seg_start) * a.hg;
+            for (int it = 0; it < items; it += 32) {
+              const int idx = it + lane;
+              const int hgi = idx % a.hg;
+              const float mh = __shfl_sync(0xffffffffu, m, hgi * lm.lph);
+              const float ih = __shfl_sync(0xffffffffu, inv, hgi * lm.lph);
+              if (idx < items) {
+                const long long o = static_cast<long long>(seg_start + idx / a.hg) * a.H + g * a.hg + hgi;
+                const float zz = a.z[o];
+                const float ee = zz > 0.f ? zz : kLeakySlope * zz;
+                a.alpha[o] = __expf(ee - mh) * ih;
+              }
+            }
+          }
+          m = -INFINITY; l = 0.f; bsum = 0.f;
+          ++kn;
+          seg_start = seg_end;
+          if (kn < nn) seg_end = RG_RP(kn + 1);
+          continue;
+        }
+        if (u == npair) break;
+        if (u == 0) RG_EDGE(x0, d0, r0, cur) else RG_EDGE(x1, d1, r1, cur);
+        ++u;
+      }
+      e += npair;
+      if (e >= e_hi) break;
     }
-  }
-  while (kn < nn) RG_FINALIZE();  // last destination with edges + trailing empty ones
 #undef RG_EDGE
-#undef RG_FINALIZE
 #undef RG_RP
+  }
 }
 
 template <typename T, int V>
-static int launch_fwd(const FwdArgs<T, V>& a, cudaStream_t stream) {
-  const long long tasks = static_cast<long long>(a.n_chunks) * (a.H / a.hg);
-  if (tasks == 0) return RG_OK;
-  const long long blocks = (tasks + kFwdWarps - 1) / kFwdWarps;
-  edge_fwd_kernel<T, V><<<static_cast<unsigned>(blocks), kFwdWarps * 32, 0, stream>>>(a);
+static int launch_fwd(FwdArgs<T, V> a, int sm_count, cudaStream_t stream) {
+  if (a.n_chunks == 0) return RG_OK;
+  const int groups = a.H / a.hg;
+  if (sm_count <= 0) sm_count = 148;
+  int ctas = sm_count / groups;
+  if (ctas < 1) ctas = 1;
+  const int need = (a.n_chunks + kFwdWarps - 1) / kFwdWarps;
+  if (ctas > need) ctas = need;
+  const size_t a_bytes = static_cast<size_t>(a.hg) * a.R * a.F * sizeof(float);
+  a.a_in_smem = a_bytes <= kSmemBudgetA ? 1 : 0;
+  const size_t smem = a.a_in_smem ? a_bytes : 0;
+  cudaError_t e = cudaFuncSetAttribute(edge_fwd_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kSmemBudgetA));
+  if (e != cudaSuccess) return cuda_status(e);
+  edge_fwd_kernel<T, V><<<dim3(ctas, groups), kFwdWarps * 32, smem, stream>>>(a);
   return cuda_status(cudaGetLastError());
 }
 
@@ -227,7 +273,7 @@ extern "C" int relgat_layer_fwd(
     const int* rowptr, const int* csr_src, const int* csr_rel, const int* chunk_node, int n_chunks,
     float* out, void* act_hi, void* act_lo, int apply_elu,
     float* alpha, float* z, float* minv, float* bias_out,
-    int H, int F, int R, void* stream) {
+    int H, int F, int R, int sm_count, void* stream) {
   if (!P || !A || !rowptr || !chunk_node || n_chunks < 0 || H <= 0 || F <= 0 || R <= 0) return RG_ERR_ARG;
   if (p_is_bf16) return RG_ERR_DTYPE;  // bf16 feature storage: not built in this round
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -237,17 +283,17 @@ extern "C" int relgat_layer_fwd(
                       (!act_lo || reinterpret_cast<uintptr_t>(act_lo) % 8 == 0);
   const bool v4 = (F % 4 == 0) && (ldp % 4 == 0) && vec_ok;
   if (v4) {
-    const int hg = pick_heads_per_warp(H, F, 4);
+    const int hg = pick_heads_per_warp(H, F, 4, R);
     if (!hg) return RG_ERR_SHAPE;
     FwdArgs<float, 4> a{static_cast<const float*>(P), A, beta, rowptr, csr_src, csr_rel, chunk_node, out,
                         static_cast<__nv_bfloat16*>(act_hi), static_cast<__nv_bfloat16*>(act_lo),
-                        alpha, z, minv, bias_out, n_chunks, H, F, R, hg, ldp, apply_elu};
-    return launch_fwd(a, s);
+                        alpha, z, minv, bias_out, n_chunks, H, F, R, hg, ldp, apply_elu, 0};
+    return launch_fwd(a, sm_count, s);
   }
-  const int hg = pick_heads_per_warp(H, F, 1);
+  const int hg = pick_heads_per_warp(H, F, 1, R);
   if (!hg) return RG_ERR_SHAPE;
   FwdArgs<float, 1> a{static_cast<const float*>(P), A, beta, rowptr, csr_src, csr_rel, chunk_node, out,
                       static_cast<__nv_bfloat16*>(act_hi), static_cast<__nv_bfloat16*>(act_lo),
-                      alpha, z, minv, bias_out, n_chunks, H, F, R, hg, ldp, apply_elu};
-  return launch_fwd(a, s);
+                      alpha, z, minv, bias_out, n_chunks, H, F, R, hg, ldp, apply_elu, 0};
+  return launch_fwd(a, sm_count, s);
 }

@@ -140,7 +140,7 @@ def edge_fwd(P: torch.Tensor, A: torch.Tensor, beta: Optional[torch.Tensor], g: 
             _lib.ptr(P), 0, P.stride(0), _lib.ptr(A), _lib.ptr(beta),
             _lib.ptr(g.rowptr), _lib.ptr(g.csr_src), _lib.ptr(g.csr_rel), _lib.ptr(g.fwd_chunk_node), g.n_fwd_chunks,
             _lib.ptr(out), _lib.ptr(hi), _lib.ptr(lo), int(apply_elu),
-            _lib.ptr(alpha), _lib.ptr(z), _lib.ptr(minv), _lib.ptr(bias), H, F, R, _stream(P))
+            _lib.ptr(alpha), _lib.ptr(z), _lib.ptr(minv), _lib.ptr(bias), H, F, R, sm_count(dev), _stream(P))
     _lib.check(rc, "relgat_layer_fwd")
     _count(1)
     return out, ((hi, lo) if want_act else None), alpha, z, minv, bias
@@ -183,7 +183,7 @@ def edge_bwd_src(P, G, A, z, minv, t, g: GraphIndex, H: int, F: int, want_fp32: 
             _lib.ptr(P), P.stride(0), _lib.ptr(G), _lib.ptr(A), _lib.ptr(z), _lib.ptr(minv), _lib.ptr(t),
             _lib.ptr(g.colptr), _lib.ptr(g.csc_slot), _lib.ptr(g.csc_dst), _lib.ptr(g.csc_rel),
             _lib.ptr(g.src_chunk_node), g.n_src_chunks,
-            _lib.ptr(dP), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dz), H, F, g.R, _stream(P))
+            _lib.ptr(dP), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dz), H, F, g.R, sm_count(dev), _stream(P))
     _lib.check(rc, "relgat_layer_bwd_src")
     _count(1)
     return dP, ((hi, lo) if want_planes else None), dz
