@@ -181,4 +181,9 @@ inline int pick_heads_per_warp(int H, int F, int V, int R = 0) {
   return best;
 }
 
+inline int vectors_per_lane(int vph, int hg) {
+  const int lph = 32 / hg;
+  return (vph + lph - 1) / lph;
+}
+
 }  // namespace relgat

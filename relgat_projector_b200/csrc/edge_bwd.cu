@@ -104,10 +104,10 @@ struct SrcArgs {
   int a_in_smem;
 };
 
-template <int V>
+template <int V, int KV>
 __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArgs<V> a) {
   extern __shared__ __align__(16) float dyn_sm[];
-  constexpr int kOwnFloats = kMaxVecPerLane * 32 * V;  // lane-private slots of one warp's own row
+  constexpr int kOwnFloats = KV * 32 * V;  // lane-private slots of one warp's own row
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = blockIdx.y;
   const LaneMap lm = make_lane_map<V>(lane, g, a.hg, a.F);
@@ -147,9 +147,9 @@ __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArg
     const int e_lo = RG_CP(0);
     const int e_hi = RG_CP(nn);
 
-    float acc[kMaxVecPerLane][V];
+    float acc[KV][V];
 #pragma unroll
-    for (int k = 0; k < kMaxVecPerLane; ++k)
+    for (int k = 0; k < KV; ++k)
 #pragma unroll
       for (int v = 0; v < V; ++v) acc[k][v] = 0.f;
 
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArg
     const float* rowp = (ty_ == IT_OWN)                                                        \
         ? a.P + static_cast<long long>(n_lo + (nd_)) * a.ldp + lm.head_off                     \
         : a.G + static_cast<long long>(ds_) * C + lm.head_off;                                 \
-    _Pragma("unroll") for (int k = 0; k < kMaxVecPerLane; ++k) {                               \
+    _Pragma("unroll") for (int k = 0; k < KV; ++k) {                               \
       const int q = lm.sub + lm.lph * k;                                                       \
       if (q < lm.vph) RowVec<float, V>::load_stream(rowp + q * V, x_[k]);                      \
     }                                                                                          \
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArg
 #define RG_EDGE_ITEM(sl_, rl_, x_, zz_, mi_, tt_)                                              \
   {                                                                                            \
     float dd = 0.f;                                                                            \
-    _Pragma("unroll") for (int k = 0; k < kMaxVecPerLane; ++k) {                               \
+    _Pragma("unroll") for (int k = 0; k < KV; ++k) {                               \
       const int q = lm.sub + lm.lph * k;                                                       \
       if (q < lm.vph) {                                                                        \
         float pv[V];                                                                           \
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArg
     const float dzv = al * (dd - tt_) * (zz_ > 0.f ? 1.f : kLeakySlope);                       \
     if (lm.sub == 0) a.dz[static_cast<long long>(sl_) * a.H + lm.hh] = dzv;                    \
     const float* ar = a_base + static_cast<long long>(rl_) * a.F;                              \
-    _Pragma("unroll") for (int k = 0; k < kMaxVecPerLane; ++k) {                               \
+    _Pragma("unroll") for (int k = 0; k < KV; ++k) {                               \
       const int q = lm.sub + lm.lph * k;                                                       \
       if (q < lm.vph) {                                                                        \
         float av[V];                                                                           \
@@ -237,12 +237,36 @@ __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArg
     }                                                                                          \
   }
 
+    // EDGE: accumulate.  OWN / ZERO / END: close the source being accumulated (write its dP row),
+    // then open the next one (OWN parks the freshly loaded row in the lane-private smem slots).
+#define RG_CONSUME(ty_, nd_, sl_, rl_, x_, zz_, mi_, tt_)                                      \
+  if (ty_ == IT_EDGE) {                                                                        \
+    RG_EDGE_ITEM(sl_, rl_, x_, zz_, mi_, tt_)                                                  \
+  } else {                                                                                     \
+    if (cur >= 0) {                                                                            \
+      _Pragma("unroll") for (int k = 0; k < KV; ++k) {                             \
+        const int q = lm.sub + lm.lph * k;                                                     \
+        if (q < lm.vph) {                                                                      \
+          const long long off = static_cast<long long>(n_lo + cur) * C + lm.head_off + q * V;  \
+          if (a.dP) RowVec<float, V>::store(a.dP + off, acc[k]);                               \
+          if (a.dP_hi) store_split_bf16<V>(a.dP_hi + off, a.dP_lo ? a.dP_lo + off : nullptr, acc[k]); \
+        }                                                                                      \
+      }                                                                                        \
+    }                                                                                          \
+    cur = (ty_ == IT_END) ? -1 : (nd_);                                                        \
+    _Pragma("unroll") for (int k = 0; k < KV; ++k) {                               \
+      _Pragma("unroll") for (int v = 0; v < V; ++v) acc[k][v] = 0.f;                           \
+      const int q = lm.sub + lm.lph * k;                                                       \
+      if (ty_ == IT_OWN && q < lm.vph) RowVec<float, V>::store(p_own + (k * 32 + lane) * V, x_[k]); \
+    }                                                                                          \
+  }
+
     while (true) {
       int ty0, nd0, sl0, ds0, rl0, ty1, nd1, sl1, ds1, rl1;
       RG_NEXT(ty0, nd0, sl0, ds0, rl0);
       if (ty0 == IT_NONE) break;
       RG_NEXT(ty1, nd1, sl1, ds1, rl1);
-      float x0[kMaxVecPerLane][V], x1[kMaxVecPerLane][V];
+      float x0[KV][V], x1[KV][V];
       RG_ISSUE(ty0, nd0, ds0, x0);
       RG_ISSUE(ty1, nd1, ds1, x1);
       float z0 = 0.f, z1 = 0.f, t0 = 0.f, t1 = 0.f;
@@ -257,43 +281,10 @@ __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArg
         t1 = __ldg(a.t + static_cast<long long>(ds1) * a.H + lm.hh);
         mi1 = __ldg(reinterpret_cast<const float2*>(a.minv) + static_cast<long long>(ds1) * a.H + lm.hh);
       }
-      for (int u = 0; u < 2; ++u) {  // not unrolled: the row write below exists once in the code
-        const int ty = u ? ty1 : ty0;
-        if (ty == IT_NONE) break;
-        if (ty == IT_EDGE) {
-          if (u == 0) RG_EDGE_ITEM(sl0, rl0, x0, z0, mi0, t0) else RG_EDGE_ITEM(sl1, rl1, x1, z1, mi1, t1);
-          continue;
-        }
-        // OWN / ZERO / END: close the source being accumulated, then open the next one
-        if (cur >= 0) {
-#pragma unroll
-          for (int k = 0; k < kMaxVecPerLane; ++k) {
-            const int q = lm.sub + lm.lph * k;
-            if (q < lm.vph) {
-              const long long off = static_cast<long long>(n_lo + cur) * C + lm.head_off + q * V;
-              if (a.dP) RowVec<float, V>::store(a.dP + off, acc[k]);
-              if (a.dP_hi) store_split_bf16<V>(a.dP_hi + off, a.dP_lo ? a.dP_lo + off : nullptr, acc[k]);
-            }
-          }
-        }
-        cur = (ty == IT_END) ? -1 : (u ? nd1 : nd0);
-#pragma unroll
-        for (int k = 0; k < kMaxVecPerLane; ++k) {
-#pragma unroll
-          for (int v = 0; v < V; ++v) acc[k][v] = 0.f;
-        }
-        if (ty == IT_OWN) {
-#pragma unroll
-          for (int k = 0; k < kMaxVecPerLane; ++k) {
-            const int q = lm.sub + lm.lph * k;
-            if (q < lm.vph) {
-              if (u == 0) RowVec<float, V>::store(p_own + (k * 32 + lane) * V, x0[k]);
-              else RowVec<float, V>::store(p_own + (k * 32 + lane) * V, x1[k]);
-            }
-          }
-        }
-      }
+      RG_CONSUME(ty0, nd0, sl0, rl0, x0, z0, mi0, t0);
+      if (ty1 != IT_NONE) RG_CONSUME(ty1, nd1, sl1, rl1, x1, z1, mi1, t1);
     }
+#undef RG_CONSUME
 #undef RG_EDGE_ITEM
 #undef RG_ISSUE
 #undef RG_NEXT
@@ -448,24 +439,34 @@ extern "C" int relgat_layer_bwd_prep(const float* dY, const float* out, const fl
   return launch_tasks(bwd_prep_kernel<1>, a, static_cast<long long>(N) * (H / hg), s);
 }
 
-template <int V>
-static int launch_src(SrcArgs<V> a, int sm_count, cudaStream_t s) {
-  if (a.n_chunks == 0) return RG_OK;
+template <int V, int KV>
+static int launch_src_kv(SrcArgs<V> a, int sm_count, cudaStream_t s) {
   const int groups = a.H / a.hg;
   if (sm_count <= 0) sm_count = 148;
   int ctas = sm_count / groups;
   if (ctas < 1) ctas = 1;
   const int need = (a.n_chunks + kSrcWarps - 1) / kSrcWarps;
   if (ctas > need) ctas = need;
-  const size_t own_bytes = static_cast<size_t>(kSrcWarps) * kMaxVecPerLane * 32 * V * sizeof(float);
+  const size_t own_bytes = static_cast<size_t>(kSrcWarps) * KV * 32 * V * sizeof(float);
   const size_t a_bytes = static_cast<size_t>(a.hg) * a.R * a.F * sizeof(float);
   a.a_in_smem = a_bytes <= kSmemBudgetA ? 1 : 0;
   const size_t smem = own_bytes + (a.a_in_smem ? a_bytes : 0);
-  cudaError_t e = cudaFuncSetAttribute(bwd_src_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(bwd_src_kernel<V, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(own_bytes + kSmemBudgetA));
   if (e != cudaSuccess) return cuda_status(e);
-  bwd_src_kernel<V><<<dim3(ctas, groups), kSrcWarps * 32, smem, s>>>(a);
+  bwd_src_kernel<V, KV><<<dim3(ctas, groups), kSrcWarps * 32, smem, s>>>(a);
   return cuda_status(cudaGetLastError());
+}
+
+template <int V>
+static int launch_src(const SrcArgs<V>& a, int sm_count, cudaStream_t s) {
+  if (a.n_chunks == 0) return RG_OK;
+  const int kv = vectors_per_lane(a.F / V, a.hg);
+  if (kv <= 1) return launch_src_kv<V, 1>(a, sm_count, s);
+  if (kv <= 2) return launch_src_kv<V, 2>(a, sm_count, s);
+  if (kv <= 4) return launch_src_kv<V, 4>(a, sm_count, s);
+  if (kv <= 7) return launch_src_kv<V, 7>(a, sm_count, s);
+  return launch_src_kv<V, 8>(a, sm_count, s);
 }
 
 extern "C" int relgat_layer_bwd_src(const float* P, long long ldp, const float* G, const float* A,
