@@ -180,3 +180,23 @@ def test_partitioned_destination_ranges_reproduce_whole_graph(dev):
             part, _, _, _, _, _ = ops.edge_fwd(P, A, beta, g, H, F)
             rows.append(part)
         assert torch.equal(torch.cat(rows), whole)
+
+
+def test_partitioned_stack_world1_equals_plain_stack(dev):
+    """The partitioned autograd path with one rank must reproduce the plain stack (same kernels,
+    padded layout with a single owner)."""
+    from relgat_projector_b200 import dist as RD
+    c = Case("tiny_fp64")
+    m = _load_model(c, dev)
+    part = RD.DstPartition(m.edge_index, m.edge_type, c.n, c.r, 0, 1)
+    prg = RD.PartitionedRelGAT(m, part)
+    src_ids, rel_ids, dst_ids = c.t("src_ids").to(dev), c.t("rel_ids").to(dev), c.t("dst_ids").to(dev)
+    s1 = prg.scores(src_ids, rel_ids, dst_ids)
+    s1.sum().backward()
+    g1 = {n_: p.grad.clone() for n_, p in m.named_parameters()}
+    m.zero_grad(set_to_none=True)
+    s2, _, _ = m(src_ids, rel_ids, dst_ids, transform_to_input_if_possible=False)
+    s2.sum().backward()
+    assert rel_err(s1.detach().cpu().numpy(), s2.detach().cpu().numpy()) < 1e-6
+    for n_, p in m.named_parameters():
+        assert rel_err(g1[n_].cpu().numpy(), p.grad.cpu().numpy()) < 1e-5, n_
