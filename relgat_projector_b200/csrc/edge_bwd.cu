@@ -104,7 +104,7 @@ struct SrcArgs {
   int a_in_smem;
 };
 
-template <int V, int KV>
+template <int V, int KV, bool ASM>
 __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArgs<V> a) {
   extern __shared__ __align__(16) float dyn_sm[];
   constexpr int kOwnFloats = KV * 32 * V;  // lane-private slots of one warp's own row
@@ -116,8 +116,13 @@ __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArg
   float* p_own = dyn_sm + warp * kOwnFloats;
   float* a_sm = dyn_sm + kSrcWarps * kOwnFloats;
 
+  const int kstride = lm.lph * V;
+  const int lane_off = lm.head_off + lm.sub * V;
+  const bool last_ok = lm.sub + lm.lph * (KV - 1) < lm.vph;
+#define RG_VALID(k_) ((k_) < KV - 1 || last_ok)
+
   const float* a_base;
-  if (a.a_in_smem) {
+  if (ASM) {
     const float* src = a.A + static_cast<long long>(g) * a.hg * a.R * a.F;
     const int n = a.hg * a.R * a.F;
     if ((n & 3) == 0) {
@@ -127,9 +132,9 @@ __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArg
       for (int i = threadIdx.x; i < n; i += blockDim.x) a_sm[i] = __ldg(src + i);
     }
     __syncthreads();
-    a_base = a_sm + static_cast<long long>(hl) * a.R * a.F;
+    a_base = a_sm + hl * a.R * a.F + lm.sub * V;
   } else {
-    a_base = a.A + static_cast<long long>(lm.hh) * a.R * a.F;
+    a_base = a.A + static_cast<long long>(lm.hh) * a.R * a.F + lm.sub * V;
   }
 
   enum { IT_NONE = 0, IT_OWN = 1, IT_EDGE = 2, IT_ZERO = 3, IT_END = 4 };
@@ -199,38 +204,34 @@ __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArg
   }
 
 #define RG_ISSUE(ty_, nd_, ds_, x_)                                                            \
+  _Pragma("unroll") for (int v = 0; v < V; ++v) x_[KV - 1][v] = 0.f;                           \
   if (ty_ == IT_OWN || ty_ == IT_EDGE) {                                                       \
     const float* rowp = (ty_ == IT_OWN)                                                        \
-        ? a.P + static_cast<long long>(n_lo + (nd_)) * a.ldp + lm.head_off                     \
-        : a.G + static_cast<long long>(ds_) * C + lm.head_off;                                 \
-    _Pragma("unroll") for (int k = 0; k < KV; ++k) {                               \
-      const int q = lm.sub + lm.lph * k;                                                       \
-      if (q < lm.vph) RowVec<float, V>::load_stream(rowp + q * V, x_[k]);                      \
-    }                                                                                          \
+        ? a.P + static_cast<long long>(n_lo + (nd_)) * a.ldp + lane_off                        \
+        : a.G + static_cast<long long>(ds_) * C + lane_off;                                    \
+    _Pragma("unroll") for (int k = 0; k < KV; ++k)                                             \
+      if (RG_VALID(k)) RowVec<float, V>::load_stream(rowp + k * kstride, x_[k]);               \
   }
 
 #define RG_EDGE_ITEM(sl_, rl_, x_, zz_, mi_, tt_)                                              \
   {                                                                                            \
     float dd = 0.f;                                                                            \
-    _Pragma("unroll") for (int k = 0; k < KV; ++k) {                               \
-      const int q = lm.sub + lm.lph * k;                                                       \
-      if (q < lm.vph) {                                                                        \
-        float pv[V];                                                                           \
-        RowVec<float, V>::load_shared(p_own + (k * 32 + lane) * V, pv);                        \
-        _Pragma("unroll") for (int v = 0; v < V; ++v) dd = fmaf(x_[k][v], pv[v], dd);          \
-      }                                                                                        \
+    _Pragma("unroll") for (int k = 0; k < KV; ++k) {                                           \
+      float pv[V];                                                                             \
+      RowVec<float, V>::load_shared(p_own + (k * 32 + lane) * V, pv);                          \
+      _Pragma("unroll") for (int v = 0; v < V; ++v) dd = fmaf(x_[k][v], pv[v], dd);            \
     }                                                                                          \
     dd = head_sum(dd, lm.lph); /* dalpha */                                                    \
     const float ee = zz_ > 0.f ? zz_ : kLeakySlope * zz_;                                      \
     const float al = __expf(ee - mi_.x) * mi_.y;                                               \
     const float dzv = al * (dd - tt_) * (zz_ > 0.f ? 1.f : kLeakySlope);                       \
     if (lm.sub == 0) a.dz[static_cast<long long>(sl_) * a.H + lm.hh] = dzv;                    \
-    const float* ar = a_base + static_cast<long long>(rl_) * a.F;                              \
-    _Pragma("unroll") for (int k = 0; k < KV; ++k) {                               \
-      const int q = lm.sub + lm.lph * k;                                                       \
-      if (q < lm.vph) {                                                                        \
+    const float* ar = a_base + (rl_) * a.F;                                                    \
+    _Pragma("unroll") for (int k = 0; k < KV; ++k) {                                           \
+      if (RG_VALID(k)) {                                                                       \
         float av[V];                                                                           \
-        RowVec<float, V>::load_any(ar + q * V, av);                                            \
+        if (ASM) RowVec<float, V>::load_shared(ar + k * kstride, av);                          \
+        else RowVec<float, V>::load_cached(ar + k * kstride, av);                              \
         _Pragma("unroll") for (int v = 0; v < V; ++v)                                          \
           acc[k][v] = fmaf(al, x_[k][v], fmaf(dzv, av[v], acc[k][v]));                         \
       }                                                                                        \
@@ -244,20 +245,19 @@ __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArg
     RG_EDGE_ITEM(sl_, rl_, x_, zz_, mi_, tt_)                                                  \
   } else {                                                                                     \
     if (cur >= 0) {                                                                            \
-      _Pragma("unroll") for (int k = 0; k < KV; ++k) {                             \
-        const int q = lm.sub + lm.lph * k;                                                     \
-        if (q < lm.vph) {                                                                      \
-          const long long off = static_cast<long long>(n_lo + cur) * C + lm.head_off + q * V;  \
+      const long long row_off = static_cast<long long>(n_lo + cur) * C + lane_off;             \
+      _Pragma("unroll") for (int k = 0; k < KV; ++k) {                                         \
+        if (RG_VALID(k)) {                                                                     \
+          const long long off = row_off + k * kstride;                                         \
           if (a.dP) RowVec<float, V>::store(a.dP + off, acc[k]);                               \
           if (a.dP_hi) store_split_bf16<V>(a.dP_hi + off, a.dP_lo ? a.dP_lo + off : nullptr, acc[k]); \
         }                                                                                      \
       }                                                                                        \
     }                                                                                          \
     cur = (ty_ == IT_END) ? -1 : (nd_);                                                        \
-    _Pragma("unroll") for (int k = 0; k < KV; ++k) {                               \
+    _Pragma("unroll") for (int k = 0; k < KV; ++k) {                                           \
       _Pragma("unroll") for (int v = 0; v < V; ++v) acc[k][v] = 0.f;                           \
-      const int q = lm.sub + lm.lph * k;                                                       \
-      if (ty_ == IT_OWN && q < lm.vph) RowVec<float, V>::store(p_own + (k * 32 + lane) * V, x_[k]); \
+      if (ty_ == IT_OWN) RowVec<float, V>::store(p_own + (k * 32 + lane) * V, x_[k]);          \
     }                                                                                          \
   }
 
@@ -290,6 +290,7 @@ __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArg
 #undef RG_NEXT
 #undef RG_CP
   }
+#undef RG_VALID
 }
 
 // ------------------------------------------------------------------------------------
@@ -450,11 +451,14 @@ static int launch_src_kv(SrcArgs<V> a, int sm_count, cudaStream_t s) {
   const size_t own_bytes = static_cast<size_t>(kSrcWarps) * KV * 32 * V * sizeof(float);
   const size_t a_bytes = static_cast<size_t>(a.hg) * a.R * a.F * sizeof(float);
   a.a_in_smem = a_bytes <= kSmemBudgetA ? 1 : 0;
-  const size_t smem = own_bytes + (a.a_in_smem ? a_bytes : 0);
-  cudaError_t e = cudaFuncSetAttribute(bwd_src_kernel<V, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(own_bytes + kSmemBudgetA));
-  if (e != cudaSuccess) return cuda_status(e);
-  bwd_src_kernel<V, KV><<<dim3(ctas, groups), kSrcWarps * 32, smem, s>>>(a);
+  if (a.a_in_smem) {
+    cudaError_t e = cudaFuncSetAttribute(bwd_src_kernel<V, KV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(own_bytes + kSmemBudgetA));
+    if (e != cudaSuccess) return cuda_status(e);
+    bwd_src_kernel<V, KV, true><<<dim3(ctas, groups), kSrcWarps * 32, own_bytes + a_bytes, s>>>(a);
+  } else {
+    bwd_src_kernel<V, KV, false><<<dim3(ctas, groups), kSrcWarps * 32, own_bytes, s>>>(a);
+  }
   return cuda_status(cudaGetLastError());
 }
 
@@ -462,11 +466,16 @@ template <int V>
 static int launch_src(const SrcArgs<V>& a, int sm_count, cudaStream_t s) {
   if (a.n_chunks == 0) return RG_OK;
   const int kv = vectors_per_lane(a.F / V, a.hg);
-  if (kv <= 1) return launch_src_kv<V, 1>(a, sm_count, s);
-  if (kv <= 2) return launch_src_kv<V, 2>(a, sm_count, s);
-  if (kv <= 4) return launch_src_kv<V, 4>(a, sm_count, s);
-  if (kv <= 7) return launch_src_kv<V, 7>(a, sm_count, s);
-  return launch_src_kv<V, 8>(a, sm_count, s);
+  switch (kv) {
+    case 1: return launch_src_kv<V, 1>(a, sm_count, s);
+    case 2: return launch_src_kv<V, 2>(a, sm_count, s);
+    case 3: return launch_src_kv<V, 3>(a, sm_count, s);
+    case 4: return launch_src_kv<V, 4>(a, sm_count, s);
+    case 5: return launch_src_kv<V, 5>(a, sm_count, s);
+    case 6: return launch_src_kv<V, 6>(a, sm_count, s);
+    case 7: return launch_src_kv<V, 7>(a, sm_count, s);
+    default: return launch_src_kv<V, 8>(a, sm_count, s);
+  }
 }
 
 extern "C" int relgat_layer_bwd_src(const float* P, long long ldp, const float* G, const float* A,

@@ -51,7 +51,7 @@ __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : __expf(x) 
 // grid = (CTAs per head-group, head-groups); every CTA is persistent and owns one head-group, so
 // it stages only that group's attention vectors (ncu on the first version showed the per-edge
 // A-row reads missing L1 ~40-70% of the time and doubling the L2->SM traffic).
-template <typename T, int V, int KV>
+template <typename T, int V, int KV, bool ASM>
 __global__ void __launch_bounds__(kFwdWarps * 32, 1)
 edge_fwd_kernel(const FwdArgs<T, V> a) {
   extern __shared__ __align__(16) float a_sm[];
@@ -62,8 +62,14 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
   const int C = a.H * a.F;
   const int hl = lm.hh - g * a.hg;  // head index inside the group
 
+  // lane geometry: vectors k < KV-1 are always inside the head, only the last one needs a guard
+  const int kstride = lm.lph * V;                      // elements between a lane's consecutive vectors
+  const int lane_off = lm.head_off + lm.sub * V;       // first element of this lane inside a node row
+  const bool last_ok = lm.sub + lm.lph * (KV - 1) < lm.vph;
+#define RG_VALID(k_) ((k_) < KV - 1 || last_ok)
+
   const float* a_base;  // rows of this lane's head: a_base + r * F
-  if (a.a_in_smem) {
+  if (ASM) {
     const float* src = a.A + static_cast<long long>(g) * a.hg * a.R * a.F;
     const int n = a.hg * a.R * a.F;
     if ((n & 3) == 0) {
@@ -73,9 +79,9 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
       for (int i = threadIdx.x; i < n; i += blockDim.x) a_sm[i] = __ldg(src + i);
     }
     __syncthreads();
-    a_base = a_sm + static_cast<long long>(hl) * a.R * a.F;
+    a_base = a_sm + hl * a.R * a.F + lm.sub * V;
   } else {
-    a_base = a.A + static_cast<long long>(lm.hh) * a.R * a.F;
+    a_base = a.A + static_cast<long long>(lm.hh) * a.R * a.F + lm.sub * V;
   }
 
   for (int c = blockIdx.x * kFwdWarps + warp; c < a.n_chunks; c += gridDim.x * kFwdWarps) {
@@ -103,9 +109,10 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
     int seg_end = RG_RP(1);
     int base = e_lo - 32;  // (src, rel) window [base, base + 32) held across the lanes
     int my_src = 0, my_rel = 0;
+    float my_beta = 0.f;
 
     // one edge: online softmax update + weighted accumulate (logit d_ already reduced)
-#define RG_EDGE(x_, d_, r_, e_)                                                                    \
+#define RG_EDGE(x_, d_, b_, e_)                                                                    \
   {                                                                                                \
     if (lm.sub == 0) a.z[static_cast<long long>(e_) * a.H + lm.hh] = (d_);                         \
     const float ev = (d_) > 0.f ? (d_) : kLeakySlope * (d_);                                       \
@@ -113,14 +120,11 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
     const float sc = __expf(m - mn);                                                               \
     const float w = __expf(ev - mn);                                                               \
     l = fmaf(l, sc, w);                                                                            \
-    _Pragma("unroll") for (int k = 0; k < KV; ++k) {                                   \
-      const int q = lm.sub + lm.lph * k;                                                           \
-      if (q < lm.vph) {                                                                            \
-        _Pragma("unroll") for (int v = 0; v < V; ++v) acc[k][v] = fmaf(acc[k][v], sc, w * x_[k][v]); \
-      }                                                                                            \
+    _Pragma("unroll") for (int k = 0; k < KV; ++k) {                                               \
+      _Pragma("unroll") for (int v = 0; v < V; ++v) acc[k][v] = fmaf(acc[k][v], sc, w * x_[k][v]); \
     }                                                                                              \
     m = (ev != ev) ? ev : mn; /* NaN logits poison the row like the reference does */              \
-    if (a.beta) bsum += __ldg(a.beta + (r_));                                                      \
+    bsum += (b_);                                                                                  \
   }
 
     int e = e_lo;
@@ -131,46 +135,45 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
         if (idx < e_hi) {
           my_src = __ldg(a.csr_src + idx);
           my_rel = __ldg(a.csr_rel + idx);
+          my_beta = a.beta ? __ldg(a.beta + my_rel) : 0.f;
         }
       }
       const int npair = min(2, min(e_hi - e, base + 32 - e));  // 0 only when the chunk is exhausted
       float x0[KV][V], x1[KV][V];
-      float d0 = 0.f, d1 = 0.f;
-      int r0 = 0, r1 = 0;
+      float d0 = 0.f, d1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+      for (int v = 0; v < V; ++v) { x0[KV - 1][v] = 0.f; x1[KV - 1][v] = 0.f; }  // the only guarded vector
       if (npair > 0) {
         const bool two = npair == 2;
         const int t = e - base;
         const int i0 = __shfl_sync(0xffffffffu, my_src, t);
-        r0 = __shfl_sync(0xffffffffu, my_rel, t);
+        const int r0 = __shfl_sync(0xffffffffu, my_rel, t);
+        b0 = __shfl_sync(0xffffffffu, my_beta, t);
         const int i1 = __shfl_sync(0xffffffffu, my_src, two ? t + 1 : t);
-        r1 = __shfl_sync(0xffffffffu, my_rel, two ? t + 1 : t);
-        const T* p0 = a.P + static_cast<long long>(i0) * a.ldp + lm.head_off;
-        const T* p1 = a.P + static_cast<long long>(i1) * a.ldp + lm.head_off;
+        const int r1 = __shfl_sync(0xffffffffu, my_rel, two ? t + 1 : t);
+        b1 = __shfl_sync(0xffffffffu, my_beta, two ? t + 1 : t);
+        const T* p0 = a.P + static_cast<long long>(i0) * a.ldp + lane_off;
+        const T* p1 = a.P + static_cast<long long>(i1) * a.ldp + lane_off;
         // issue both row gathers before any arithmetic (two rows in flight per warp)
 #pragma unroll
-        for (int k = 0; k < KV; ++k) {
-          const int q = lm.sub + lm.lph * k;
-          if (q < lm.vph) RowVec<T, V>::load_stream(p0 + q * V, x0[k]);
-        }
+        for (int k = 0; k < KV; ++k)
+          if (RG_VALID(k)) RowVec<T, V>::load_stream(p0 + k * kstride, x0[k]);
         if (two) {
 #pragma unroll
-          for (int k = 0; k < KV; ++k) {
-            const int q = lm.sub + lm.lph * k;
-            if (q < lm.vph) RowVec<T, V>::load_stream(p1 + q * V, x1[k]);
-          }
+          for (int k = 0; k < KV; ++k)
+            if (RG_VALID(k)) RowVec<T, V>::load_stream(p1 + k * kstride, x1[k]);
         }
-        const float* a0 = a_base + static_cast<long long>(r0) * a.F;
-        const float* a1 = a_base + static_cast<long long>(r1) * a.F;
+        const float* a0 = a_base + r0 * a.F;
+        const float* a1 = a_base + r1 * a.F;
 #pragma unroll
         for (int k = 0; k < KV; ++k) {
-          const int q = lm.sub + lm.lph * k;
-          if (q < lm.vph) {
+          if (RG_VALID(k)) {
             float av[V];
-            RowVec<float, V>::load_any(a0 + q * V, av);
+            if (ASM) RowVec<float, V>::load_shared(a0 + k * kstride, av); else RowVec<float, V>::load_cached(a0 + k * kstride, av);
 #pragma unroll
             for (int v = 0; v < V; ++v) d0 = fmaf(x0[k][v], av[v], d0);
             if (two) {
-              RowVec<float, V>::load_any(a1 + q * V, av);
+              if (ASM) RowVec<float, V>::load_shared(a1 + k * kstride, av); else RowVec<float, V>::load_cached(a1 + k * kstride, av);
 #pragma unroll
               for (int v = 0; v < V; ++v) d1 = fmaf(x1[k][v], av[v], d1);
             }
@@ -188,17 +191,17 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
           const int j = n_lo + kn;
           const bool empty = (seg_end == seg_start);
           const float inv = empty ? 0.f : 1.f / fmaxf(l, 1e-16f);  // reference layer.py:291 clamp
+          const long long row_off = static_cast<long long>(j) * C + lane_off;
 #pragma unroll
           for (int k = 0; k < KV; ++k) {
-            const int q = lm.sub + lm.lph * k;
-            if (q < lm.vph) {
+            if (RG_VALID(k)) {
               float o[V];
 #pragma unroll
               for (int v = 0; v < V; ++v) {
                 o[v] = empty ? 0.f : fmaf(acc[k][v], inv, bsum);  // bias on every head/channel, :313-318
                 acc[k][v] = 0.f;
               }
-              const long long off = static_cast<long long>(j) * C + lm.head_off + q * V;
+              const long long off = row_off + k * kstride;
               if (a.out) RowVec<float, V>::store(a.out + off, o);
               if (a.act_hi) {
                 if (a.apply_elu) {
@@ -237,7 +240,7 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
           continue;
         }
         if (u == npair) break;
-        if (u == 0) RG_EDGE(x0, d0, r0, cur) else RG_EDGE(x1, d1, r1, cur);
+        if (u == 0) RG_EDGE(x0, d0, b0, cur) else RG_EDGE(x1, d1, b1, cur);
         ++u;
       }
       e += npair;
@@ -246,6 +249,7 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
 #undef RG_EDGE
 #undef RG_RP
   }
+#undef RG_VALID
 }
 
 template <typename T, int V, int KV>
@@ -258,11 +262,14 @@ static int launch_fwd_kv(FwdArgs<T, V> a, int sm_count, cudaStream_t stream) {
   if (ctas > need) ctas = need;
   const size_t a_bytes = static_cast<size_t>(a.hg) * a.R * a.F * sizeof(float);
   a.a_in_smem = a_bytes <= kSmemBudgetA ? 1 : 0;
-  const size_t smem = a.a_in_smem ? a_bytes : 0;
-  cudaError_t e = cudaFuncSetAttribute(edge_fwd_kernel<T, V, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(kSmemBudgetA));
-  if (e != cudaSuccess) return cuda_status(e);
-  edge_fwd_kernel<T, V, KV><<<dim3(ctas, groups), kFwdWarps * 32, smem, stream>>>(a);
+  if (a.a_in_smem) {
+    cudaError_t e = cudaFuncSetAttribute(edge_fwd_kernel<T, V, KV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(kSmemBudgetA));
+    if (e != cudaSuccess) return cuda_status(e);
+    edge_fwd_kernel<T, V, KV, true><<<dim3(ctas, groups), kFwdWarps * 32, a_bytes, stream>>>(a);
+  } else {
+    edge_fwd_kernel<T, V, KV, false><<<dim3(ctas, groups), kFwdWarps * 32, 0, stream>>>(a);
+  }
   return cuda_status(cudaGetLastError());
 }
 
@@ -271,11 +278,16 @@ template <typename T, int V>
 static int launch_fwd(const FwdArgs<T, V>& a, int sm_count, cudaStream_t stream) {
   if (a.n_chunks == 0) return RG_OK;
   const int kv = vectors_per_lane(a.F / V, a.hg);
-  if (kv <= 1) return launch_fwd_kv<T, V, 1>(a, sm_count, stream);
-  if (kv <= 2) return launch_fwd_kv<T, V, 2>(a, sm_count, stream);
-  if (kv <= 4) return launch_fwd_kv<T, V, 4>(a, sm_count, stream);
-  if (kv <= 7) return launch_fwd_kv<T, V, 7>(a, sm_count, stream);
-  return launch_fwd_kv<T, V, 8>(a, sm_count, stream);
+  switch (kv) {  // exact count: only the last vector of a lane needs a bounds guard
+    case 1: return launch_fwd_kv<T, V, 1>(a, sm_count, stream);
+    case 2: return launch_fwd_kv<T, V, 2>(a, sm_count, stream);
+    case 3: return launch_fwd_kv<T, V, 3>(a, sm_count, stream);
+    case 4: return launch_fwd_kv<T, V, 4>(a, sm_count, stream);
+    case 5: return launch_fwd_kv<T, V, 5>(a, sm_count, stream);
+    case 6: return launch_fwd_kv<T, V, 6>(a, sm_count, stream);
+    case 7: return launch_fwd_kv<T, V, 7>(a, sm_count, stream);
+    default: return launch_fwd_kv<T, V, 8>(a, sm_count, stream);
+  }
 }
 
 }  // namespace relgat

@@ -212,20 +212,22 @@ index_add_sorted_kernel(const float* __restrict__ rows, const long long* __restr
   if (p0 > 0 && sorted_keys[p0 - 1] == key) return;
   int p1 = p0 + 1;
   while (p1 < M && sorted_keys[p1] == key) ++p1;
+  // blockIdx.y selects a 32*V-column slab, so a long key run (few relations, many triples) is
+  // spread over D / (32*V) warps instead of one
+  const int c = (blockIdx.y * 32 + lane) * V;
+  if (c >= D) return;
   float* o = out + key * D;
-  for (int c = lane * V; c < D; c += 32 * V) {
-    float acc[V];
+  float acc[V];
 #pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = 0.f;
-    if (accumulate) ldv<V>(o + c, acc);
-    for (int p = p0; p < p1; ++p) {
-      float x[V];
-      ldv<V>(rows + perm[p] * D + c, x);
+  for (int v = 0; v < V; ++v) acc[v] = 0.f;
+  if (accumulate) ldv<V>(o + c, acc);
+  for (int p = p0; p < p1; ++p) {
+    float x[V];
+    ldv<V>(rows + perm[p] * D + c, x);
 #pragma unroll
-      for (int v = 0; v < V; ++v) acc[v] += x[v];
-    }
-    RowVec<float, V>::store(o + c, acc);
+    for (int v = 0; v < V; ++v) acc[v] += x[v];
   }
+  RowVec<float, V>::store(o + c, acc);
 }
 
 static inline bool al16(const void* p) { return !p || reinterpret_cast<uintptr_t>(p) % 16 == 0; }
@@ -282,8 +284,8 @@ extern "C" int relgat_index_add_sorted(const float* rows, const long long* perm,
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const unsigned blocks = (M + kScoreWarps - 1) / kScoreWarps;
   if (D % 4 == 0 && al16(rows) && al16(out))
-    index_add_sorted_kernel<4><<<blocks, kScoreWarps * 32, 0, s>>>(rows, perm, sorted_keys, out, M, D, accumulate);
+    index_add_sorted_kernel<4><<<dim3(blocks, (D + 127) / 128), kScoreWarps * 32, 0, s>>>(rows, perm, sorted_keys, out, M, D, accumulate);
   else
-    index_add_sorted_kernel<1><<<blocks, kScoreWarps * 32, 0, s>>>(rows, perm, sorted_keys, out, M, D, accumulate);
+    index_add_sorted_kernel<1><<<dim3(blocks, (D + 31) / 32), kScoreWarps * 32, 0, s>>>(rows, perm, sorted_keys, out, M, D, accumulate);
   return cuda_status(cudaGetLastError());
 }

@@ -17,6 +17,17 @@ from .graph import GraphIndex
 
 PRECISIONS = ("fp32", "bf16")
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    """One extra stream per device: the HBM-bound by-relation pass runs beside the tensor-bound
+    dW / dX GEMMs (they only share read-only inputs)."""
+    key = torch.device(device).index
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
 
 class RelGATStackFunction(torch.autograd.Function):
     """out = RelGAT_L(... ELU(RelGAT_1(x0)) ...) for layers sharing one graph.
@@ -76,7 +87,11 @@ class RelGATStackFunction(torch.autograd.Function):
             G, t, hsum = ops.edge_bwd_prep(dY, s["out"], s["bias"], H, F, apply_elu=(l < L - 1), inplace=owned)
             _, dPp, dz = ops.edge_bwd_src(s["P"], G, s["A"], s["z"], s["minv"], t, g, H, F,
                                           want_fp32=False, want_planes=True, planes_lo=with_lo)
-            dA, dbeta = ops.edge_bwd_rel(s["P"], dz, hsum, g, H, F, want_dbeta=s["has_beta"])
+            main = torch.cuda.current_stream(dY.device)
+            side = _side_stream(dY.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):  # dA / dbeta: gather-bound, overlaps the GEMMs below
+                dA, dbeta = ops.edge_bwd_rel(s["P"], dz, hsum, g, H, F, want_dbeta=s["has_beta"])
             d_in = s["d_in"]
             splits = ops.pick_splits_k(C, d_in, N, dY.device)
             dW = ops.gemm(dPp, True, s["xp"], True, C, d_in, N, splits_k=splits)
@@ -84,6 +99,10 @@ class RelGATStackFunction(torch.autograd.Function):
             if l > 0 or ctx.x0_needs_grad:
                 dX = ops.gemm(dPp, False, s["Wp"], True, N, d_in, C)
                 dY, owned = dX, True
+            main.wait_stream(side)  # join before any buffer of this layer is released or reused
+            for tns in (dA, dbeta):
+                if tns is not None:
+                    tns.record_stream(main)
             del G, dPp, dz
         ctx.saved = None
         return (dX if ctx.x0_needs_grad else None, None, None, None, None, None, *grads)
