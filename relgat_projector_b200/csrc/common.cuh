@@ -10,6 +10,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace relgat {
 
@@ -167,7 +168,7 @@ __device__ __forceinline__ float warp_sum(float x) {
 // (hg*R*F fp32) fit the shared-memory budget; if no group fits the budget the largest
 // register-feasible group is used and the kernels read A through L1/L2 instead.
 // Returns 0 when no mapping exists.
-inline int pick_heads_per_warp(int H, int F, int V, int R = 0) {
+inline int pick_heads_per_warp(int H, int F, int V, int R = 0, size_t budget = kSmemBudgetA) {
   if (H <= 0 || F <= 0 || F % V != 0) return 0;
   const int vph = F / V;
   int best = 0;
@@ -176,9 +177,17 @@ inline int pick_heads_per_warp(int H, int F, int V, int R = 0) {
     const int lph = 32 / hg;
     if ((vph + lph - 1) / lph > kMaxVecPerLane) continue;
     if (!best) best = hg;
-    if (R <= 0 || static_cast<size_t>(hg) * R * F * sizeof(float) <= kSmemBudgetA) return hg;
+    if (R <= 0 || static_cast<size_t>(hg) * R * F * sizeof(float) <= budget) return hg;
   }
   return best;
+}
+
+// experiment knob (host side): RELGAT_<name>_BUDGET_KB overrides the attention-vector smem budget
+inline size_t smem_budget_override(const char* name, size_t dflt) {
+  const char* v = getenv(name);
+  if (!v) return dflt;
+  const long kb = atol(v);
+  return kb > 0 ? static_cast<size_t>(kb) * 1024 : dflt;
 }
 
 inline int vectors_per_lane(int vph, int hg) {

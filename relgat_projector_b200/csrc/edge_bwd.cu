@@ -489,7 +489,7 @@ extern "C" int relgat_layer_bwd_src(const float* P, long long ldp, const float* 
   const bool planes_ok = (!dP_hi || reinterpret_cast<uintptr_t>(dP_hi) % 8 == 0) &&
                          (!dP_lo || reinterpret_cast<uintptr_t>(dP_lo) % 8 == 0);
   if (F % 4 == 0 && ldp % 4 == 0 && al16(P) && al16(G) && al16(A) && (!dP || al16(dP)) && planes_ok) {
-    const int hg = pick_heads_per_warp(H, F, 4, R);
+    const int hg = pick_heads_per_warp(H, F, 4, R, smem_budget_override("RELGAT_SRC_BUDGET_KB", kSmemBudgetA));
     if (!hg) return RG_ERR_SHAPE;
     SrcArgs<4> a{P, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, chunk_node, dP,
                  static_cast<__nv_bfloat16*>(dP_hi), static_cast<__nv_bfloat16*>(dP_lo), dz,

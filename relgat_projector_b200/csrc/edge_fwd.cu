@@ -309,7 +309,7 @@ extern "C" int relgat_layer_fwd(
                       (!act_lo || reinterpret_cast<uintptr_t>(act_lo) % 8 == 0);
   const bool v4 = (F % 4 == 0) && (ldp % 4 == 0) && vec_ok;
   if (v4) {
-    const int hg = pick_heads_per_warp(H, F, 4, R);
+    const int hg = pick_heads_per_warp(H, F, 4, R, smem_budget_override("RELGAT_FWD_BUDGET_KB", kSmemBudgetA));
     if (!hg) return RG_ERR_SHAPE;
     FwdArgs<float, 4> a{static_cast<const float*>(P), A, beta, rowptr, csr_src, csr_rel, chunk_node, out,
                         static_cast<__nv_bfloat16*>(act_hi), static_cast<__nv_bfloat16*>(act_lo),
