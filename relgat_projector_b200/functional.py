@@ -82,34 +82,28 @@ class RelGATStackFunction(torch.autograd.Function):
         dY = grad_out.contiguous()
         owned = False
         dX = None
-        keep = []
         for l in reversed(range(L)):
             s = ctx.saved[l]
             G, t, hsum = ops.edge_bwd_prep(dY, s["out"], s["bias"], H, F, apply_elu=(l < L - 1), inplace=owned)
             _, dPp, dz = ops.edge_bwd_src(s["P"], G, s["A"], s["z"], s["minv"], t, g, H, F,
                                           want_fp32=False, want_planes=True, planes_lo=with_lo)
-            # dA / dbeta (gather-bound) and dW (tensor-bound) only feed the optimizer: they run on a
-            # side stream beside the critical chain dX -> next layer's prep / by-source pass, so
-            # tensor-core and HBM work overlap.  Joined once, after the last layer.
             main = torch.cuda.current_stream(dY.device)
             side = _side_stream(dY.device)
             side.wait_stream(main)
-            d_in = s["d_in"]
-            with torch.cuda.stream(side):
+            with torch.cuda.stream(side):  # dA / dbeta: gather-bound, overlaps the GEMMs below
                 dA, dbeta = ops.edge_bwd_rel(s["P"], dz, hsum, g, H, F, want_dbeta=s["has_beta"])
-                dW = ops.gemm(dPp, True, s["xp"], True, C, d_in, N,
-                              splits_k=ops.pick_splits_k(C, d_in, N, dY.device))
+            d_in = s["d_in"]
+            splits = ops.pick_splits_k(C, d_in, N, dY.device)
+            dW = ops.gemm(dPp, True, s["xp"], True, C, d_in, N, splits_k=splits)
             grads[3 * l], grads[3 * l + 1], grads[3 * l + 2] = dW, dA, dbeta
-            keep.append((G, dPp, dz, hsum, t))  # read by the side stream: released after the join
             if l > 0 or ctx.x0_needs_grad:
                 dX = ops.gemm(dPp, False, s["Wp"], True, N, d_in, C)
                 dY, owned = dX, True
-        main = torch.cuda.current_stream(grad_out.device)
-        main.wait_stream(_side_stream(grad_out.device))
-        for tns in grads:
-            if tns is not None:
-                tns.record_stream(main)
-        keep.clear()
+            main.wait_stream(side)  # join before any buffer of this layer is released or reused
+            for tns in (dA, dbeta):
+                if tns is not None:
+                    tns.record_stream(main)
+            del G, dPp, dz
         ctx.saved = None
         return (dX if ctx.x0_needs_grad else None, None, None, None, None, None, *grads)
 
