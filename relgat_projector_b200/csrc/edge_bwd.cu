@@ -81,6 +81,12 @@ __global__ void __launch_bounds__(kBwdWarps * 32) bwd_prep_kernel(const PrepArgs
 // row).  Two items are in flight per warp and the pipeline does not drain at source boundaries.
 // ------------------------------------------------------------------------------------
 constexpr int kSrcWarps = 12;
+constexpr int kSrcPrefetchDist = 2;  // default: edges ahead whose G[dst] rows are pulled into L2
+
+__device__ __forceinline__ void prefetch_row_l2(const void* ptr, int bytes, int lane) {
+  const char* p = static_cast<const char*>(ptr) + lane * 128;
+  if (lane * 128 < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 template <int V>
 struct SrcArgs {
@@ -102,6 +108,7 @@ struct SrcArgs {
   int n_chunks, H, F, R, hg;
   long long ldp;
   int a_in_smem;
+  int pf_dist;  // L2 prefetch distance in edges (0 = off)
 };
 
 template <int V, int KV, bool ASM>
@@ -119,6 +126,8 @@ __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArg
   const int kstride = lm.lph * V;
   const int lane_off = lm.head_off + lm.sub * V;
   const bool last_ok = lm.sub + lm.lph * (KV - 1) < lm.vph;
+  const int row_bytes = a.hg * a.F * static_cast<int>(sizeof(float));
+  const int grp_off = g * a.hg * a.F;
 #define RG_VALID(k_) ((k_) < KV - 1 || last_ok)
 
   const float* a_base;
@@ -180,6 +189,8 @@ __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArg
       if (!own_done) {                                                                         \
         own_done = true; nd_ = fk;                                                             \
         ty_ = (f_end == fe) ? IT_ZERO : IT_OWN;                                                \
+        if (a.pf_dist > 0 && fk + 2 < nn) /* own rows are consecutive: keep two ahead in L2 */  \
+          prefetch_row_l2(a.P + static_cast<long long>(n_lo + fk + 2) * a.ldp + grp_off, row_bytes, lane); \
         break;                                                                                 \
       }                                                                                        \
       if (fe < f_end) {                                                                        \
@@ -191,6 +202,17 @@ __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArg
             my_dst = __ldg(a.csc_dst + idx);                                                   \
             my_rel = __ldg(a.csc_rel + idx);                                                   \
           }                                                                                    \
+          for (int pf = 0; pf < a.pf_dist; ++pf) { /* warm L2 with the window's first rows */  \
+            const int jp = __shfl_sync(0xffffffffu, my_dst, pf);                               \
+            if (base + pf < e_hi)                                                              \
+              prefetch_row_l2(a.G + static_cast<long long>(jp) * C + grp_off, row_bytes, lane); \
+          }                                                                                    \
+        }                                                                                      \
+        if (a.pf_dist > 0) { /* rolling prefetch, pf_dist edges ahead inside the window */      \
+          const int tp = fe - base + a.pf_dist;                                                \
+          const int jp = __shfl_sync(0xffffffffu, my_dst, tp & 31);                            \
+          if (tp < 32 && base + tp < e_hi)                                                     \
+            prefetch_row_l2(a.G + static_cast<long long>(jp) * C + grp_off, row_bytes, lane);  \
         }                                                                                      \
         sl_ = __shfl_sync(0xffffffffu, my_slot, fe - base);                                    \
         ds_ = __shfl_sync(0xffffffffu, my_dst, fe - base);                                     \
@@ -451,6 +473,12 @@ static int launch_src_kv(SrcArgs<V> a, int sm_count, cudaStream_t s) {
   const size_t own_bytes = static_cast<size_t>(kSrcWarps) * KV * 32 * V * sizeof(float);
   const size_t a_bytes = static_cast<size_t>(a.hg) * a.R * a.F * sizeof(float);
   a.a_in_smem = a_bytes <= kSmemBudgetA ? 1 : 0;
+  {
+    const char* pv = getenv("RELGAT_SRC_PF_DIST");
+    a.pf_dist = pv ? atoi(pv) : kSrcPrefetchDist;
+    if (a.pf_dist < 0) a.pf_dist = 0;
+    if (a.pf_dist > 30) a.pf_dist = 30;
+  }
   if (a.a_in_smem) {
     cudaError_t e = cudaFuncSetAttribute(bwd_src_kernel<V, KV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(own_bytes + kSmemBudgetA));
@@ -493,14 +521,14 @@ extern "C" int relgat_layer_bwd_src(const float* P, long long ldp, const float* 
     if (!hg) return RG_ERR_SHAPE;
     SrcArgs<4> a{P, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, chunk_node, dP,
                  static_cast<__nv_bfloat16*>(dP_hi), static_cast<__nv_bfloat16*>(dP_lo), dz,
-                 n_chunks, H, F, R, hg, ldp, 0};
+                 n_chunks, H, F, R, hg, ldp, 0, 0};
     return launch_src(a, sm_count, s);
   }
   const int hg = pick_heads_per_warp(H, F, 1, R);
   if (!hg) return RG_ERR_SHAPE;
   SrcArgs<1> a{P, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, chunk_node, dP,
                static_cast<__nv_bfloat16*>(dP_hi), static_cast<__nv_bfloat16*>(dP_lo), dz,
-               n_chunks, H, F, R, hg, ldp, 0};
+               n_chunks, H, F, R, hg, ldp, 0, 0};
   return launch_src(a, sm_count, s);
 }
 

@@ -21,6 +21,14 @@ namespace relgat {
 
 constexpr int kFwdWarps = 12;  // one persistent CTA per SM: 12 warps x <=170 registers
 
+constexpr int kPrefetchDist = 2;  // default number of edges ahead whose source rows are pulled into L2
+
+// warp-cooperative L2 prefetch of one row slice [ptr, ptr + bytes): lane l touches line l
+__device__ __forceinline__ void prefetch_row_l2_fwd(const void* ptr, int bytes, int lane) {
+  const char* p = static_cast<const char*>(ptr) + lane * 128;
+  if (lane * 128 < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 template <typename T, int V>
 struct FwdArgs {
   const T* P;            // [N_src, H*F] projected features (row stride = ldp elements)
@@ -41,6 +49,7 @@ struct FwdArgs {
   long long ldp;         // row stride of P in elements
   int apply_elu;         // act = ELU (reference model.py:286-287) else identity
   int a_in_smem;         // the head-group's slice of A (hg*R*F floats) is staged in shared memory
+  int pf_dist;           // L2 prefetch distance in edges (0 = off)
 };
 
 // ELU(x) = x (x > 0) else exp(x) - 1.  __expf keeps the absolute error at ~1e-7 (the inputs are
@@ -66,6 +75,7 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
   const int kstride = lm.lph * V;                      // elements between a lane's consecutive vectors
   const int lane_off = lm.head_off + lm.sub * V;       // first element of this lane inside a node row
   const bool last_ok = lm.sub + lm.lph * (KV - 1) < lm.vph;
+  const int row_bytes = a.hg * a.F * static_cast<int>(sizeof(T));  // this head-group's slice of a row
 #define RG_VALID(k_) ((k_) < KV - 1 || last_ok)
 
   const float* a_base;  // rows of this lane's head: a_base + r * F
@@ -137,6 +147,12 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
           my_rel = __ldg(a.csr_rel + idx);
           my_beta = a.beta ? __ldg(a.beta + my_rel) : 0.f;
         }
+        // warm L2 with the first rows of the new window; the rolling prefetch below keeps
+        // kPrefetchDist rows ahead, so the gathers mostly pay L2 instead of HBM latency
+        for (int pf = 0; pf < a.pf_dist; ++pf) {
+          const int ip = __shfl_sync(0xffffffffu, my_src, pf);
+          if (base + pf < e_hi) prefetch_row_l2_fwd(a.P + static_cast<long long>(ip) * a.ldp + g * a.hg * a.F, row_bytes, lane);
+        }
       }
       const int npair = min(2, min(e_hi - e, base + 32 - e));  // 0 only when the chunk is exhausted
       float x0[KV][V], x1[KV][V];
@@ -154,6 +170,13 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
         b1 = __shfl_sync(0xffffffffu, my_beta, two ? t + 1 : t);
         const T* p0 = a.P + static_cast<long long>(i0) * a.ldp + lane_off;
         const T* p1 = a.P + static_cast<long long>(i1) * a.ldp + lane_off;
+#pragma unroll
+        for (int pf = 0; pf < 2; ++pf) {  // rolling L2 prefetch, kPrefetchDist edges ahead (same window)
+          const int tp = t + a.pf_dist + pf;
+          const int ip = __shfl_sync(0xffffffffu, my_src, tp & 31);
+          if (a.pf_dist > 0 && tp < 32 && base + tp < e_hi)
+            prefetch_row_l2_fwd(a.P + static_cast<long long>(ip) * a.ldp + g * a.hg * a.F, row_bytes, lane);
+        }
         // issue both row gathers before any arithmetic (two rows in flight per warp)
 #pragma unroll
         for (int k = 0; k < KV; ++k)
@@ -262,6 +285,12 @@ static int launch_fwd_kv(FwdArgs<T, V> a, int sm_count, cudaStream_t stream) {
   if (ctas > need) ctas = need;
   const size_t a_bytes = static_cast<size_t>(a.hg) * a.R * a.F * sizeof(float);
   a.a_in_smem = a_bytes <= kSmemBudgetA ? 1 : 0;
+  {
+    const char* pv = getenv("RELGAT_PF_DIST");
+    a.pf_dist = pv ? atoi(pv) : kPrefetchDist;
+    if (a.pf_dist < 0) a.pf_dist = 0;
+    if (a.pf_dist > 30) a.pf_dist = 30;
+  }
   if (a.a_in_smem) {
     cudaError_t e = cudaFuncSetAttribute(edge_fwd_kernel<T, V, KV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(kSmemBudgetA));
@@ -313,13 +342,13 @@ extern "C" int relgat_layer_fwd(
     if (!hg) return RG_ERR_SHAPE;
     FwdArgs<float, 4> a{static_cast<const float*>(P), A, beta, rowptr, csr_src, csr_rel, chunk_node, out,
                         static_cast<__nv_bfloat16*>(act_hi), static_cast<__nv_bfloat16*>(act_lo),
-                        alpha, z, minv, bias_out, n_chunks, H, F, R, hg, ldp, apply_elu, 0};
+                        alpha, z, minv, bias_out, n_chunks, H, F, R, hg, ldp, apply_elu, 0, 0};
     return launch_fwd(a, sm_count, s);
   }
   const int hg = pick_heads_per_warp(H, F, 1, R);
   if (!hg) return RG_ERR_SHAPE;
   FwdArgs<float, 1> a{static_cast<const float*>(P), A, beta, rowptr, csr_src, csr_rel, chunk_node, out,
                       static_cast<__nv_bfloat16*>(act_hi), static_cast<__nv_bfloat16*>(act_lo),
-                      alpha, z, minv, bias_out, n_chunks, H, F, R, hg, ldp, apply_elu, 0};
+                      alpha, z, minv, bias_out, n_chunks, H, F, R, hg, ldp, apply_elu, 0, 0};
   return launch_fwd(a, sm_count, s);
 }
