@@ -71,24 +71,33 @@ int relgat_gemm_bf16(const void* a_hi, const void* a_lo, long long lda, int a_mn
  * per-destination stable softmax (torch_scatter.scatter_max / scatter_add), weighted
  * aggregation and the relation bias.  P: projected features [N_src, H*F] (row stride ldp),
  * A: [H, R, F] (stacked attn_vec), beta: [R] or NULL.
- * chunk_node [n_chunks+1]: the CSR edge array cut at destination boundaries into chunks of ~64
- * edges and <= 64 destinations (chunk c owns destinations [chunk_node[c], chunk_node[c+1])); one
- * warp streams one chunk, so short segments do not drain the load pipeline.  The kernels are
- * persistent (sm_count CTAs; <= 0 means 148) and stage the attention vectors in shared memory.
+ * Work tables (built once per graph, see relgat_projector_b200/graph.py StreamChunks):
+ *   chunks int32[n_chunks][4] = (first destination, count <= 64, part slot or -1, 0): the CSR edge
+ *     array cut at destination boundaries into ~64-edge chunks; one warp streams one chunk, so
+ *     short segments do not drain the load pipeline;
+ *   parts int32[n_parts][2] = (first edge, end edge): a destination with more than 512 in-edges is
+ *     split into 256-edge parts (one chunk each) whose partial softmax states (part_ml [n_parts,H,2],
+ *     part_b [n_parts], part_acc [n_parts,H*F], caller-allocated) are merged in part order;
+ *   long_node int32[n_long], long_part_ptr int32[n_long+1]: the split destinations.
+ * The kernels are persistent (sm_count CTAs; <= 0 means 148) and stage the attention vectors in
+ * shared memory.
  * Outputs: out [N, H*F] fp32 pre-activation (may be NULL), optional bf16 (hi, lo) planes of
  * act(out) for the next layer's GEMM (act = ELU if apply_elu, reference model.py:286-287),
  * z [E, H] raw logits and minv [N, H, 2] = (segment max, 1/denominator) saved for backward,
  * alpha [E, H] attention weights (optional, NULL to skip), bias_out [N]. */
 int relgat_layer_fwd(const void* P, int p_is_bf16, long long ldp, const float* A, const float* beta,
                      const int* rowptr, const int* csr_src, const int* csr_rel,
-                     const int* chunk_node, int n_chunks,
+                     const int* chunks, int n_chunks, const int* parts, int n_parts,
+                     const int* long_node, const int* long_part_ptr, int n_long,
+                     float* part_ml, float* part_b, float* part_acc,
                      float* out, void* act_hi, void* act_lo, int apply_elu,
                      float* alpha, float* z, float* minv, float* bias_out,
                      int H, int F, int R, int sm_count, void* stream);
 
 /* ---- RelGAT layer, edge part, backward (replaces the autograd replay of layer.py:220-318) ---
  * bwd_prep: G = dY * act'(out) (in place allowed), t[N,H] = <G, out - bias>, hsum[N,H] = sum_f G.
- * bwd_src : by-source pass over chunks of the CSC order (chunk_node as in fwd, over sources):
+ * bwd_src : by-source pass over chunks of the CSC order (work tables as in fwd, over sources;
+ *           part_acc [n_parts, H*F] holds the partial rows of split sources):
  *           dP [N_src, H*F] (fp32 and/or bf16 hi/lo planes) and dz [E, H]; the attention weights
  *           are recomputed from z and minv.
  * bwd_rel : by-relation pass over chunks [chunk_lo, chunk_hi) of rel_slot (a chunk never spans
@@ -100,7 +109,8 @@ int relgat_layer_bwd_prep(const float* dY, const float* out, const float* bias, 
 int relgat_layer_bwd_src(const float* P, long long ldp, const float* G, const float* A,
                          const float* z, const float* minv, const float* t,
                          const int* colptr, const int* csc_slot, const int* csc_dst, const int* csc_rel,
-                         const int* chunk_node, int n_chunks,
+                         const int* chunks, int n_chunks, const int* parts, int n_parts,
+                         const int* long_node, const int* long_part_ptr, int n_long, float* part_acc,
                          float* dP, void* dP_hi, void* dP_lo, float* dz,
                          int H, int F, int R, int sm_count, void* stream);
 int relgat_layer_bwd_rel(const float* P, long long ldp, const float* dz, const float* hsum,

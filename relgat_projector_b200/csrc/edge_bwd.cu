@@ -100,7 +100,9 @@ struct SrcArgs {
   const int* csc_slot;  // [E] CSR slot of each by-source edge
   const int* csc_dst;   // [E]
   const int* csc_rel;   // [E]
-  const int* chunk_node;  // [n_chunks+1] first source of every chunk (<= 64 sources each)
+  const int4* chunks;   // [n_chunks] (first source, count <= 64, part slot or -1, 0)
+  const int2* parts;    // [n_parts] (first edge, end edge) of the parts of split (high out-degree) sources
+  float* part_acc;      // [n_parts, C] partial dP rows of split sources
   float* dP;            // [N_src, C] fp32 (may be nullptr when only the bf16 split is wanted)
   __nv_bfloat16* dP_hi; // optional bf16 split of dP for the tensor-core GEMMs
   __nv_bfloat16* dP_lo;
@@ -149,8 +151,10 @@ __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArg
   enum { IT_NONE = 0, IT_OWN = 1, IT_EDGE = 2, IT_ZERO = 3, IT_END = 4 };
 
   for (int c = blockIdx.x * kSrcWarps + warp; c < a.n_chunks; c += gridDim.x * kSrcWarps) {
-    const int n_lo = a.chunk_node[c];
-    const int nn = a.chunk_node[c + 1] - n_lo;  // 1..64 sources
+    const int4 ch = __ldg(a.chunks + c);
+    const int n_lo = ch.x;
+    const int nn = ch.y;     // 1..64 sources
+    const int part = ch.z;   // >= 0: one part of a split (high out-degree) source
     int cp0 = 0, cp1 = 0, cp2 = 0;
     if (lane <= nn) cp0 = __ldg(a.colptr + n_lo + lane);
     if (32 + lane <= nn) cp1 = __ldg(a.colptr + n_lo + 32 + lane);
@@ -158,8 +162,13 @@ __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArg
 #define RG_CP(k_) ((k_) < 32 ? __shfl_sync(0xffffffffu, cp0, (k_) & 31)       \
                              : ((k_) < 64 ? __shfl_sync(0xffffffffu, cp1, (k_) & 31) \
                                           : __shfl_sync(0xffffffffu, cp2, (k_) & 31)))
-    const int e_lo = RG_CP(0);
-    const int e_hi = RG_CP(nn);
+    int e_lo = RG_CP(0);
+    int e_hi = RG_CP(nn);
+    if (part >= 0) {
+      const int2 pe = __ldg(a.parts + part);
+      e_lo = pe.x;
+      e_hi = pe.y;
+    }
 
     float acc[KV][V];
 #pragma unroll
@@ -170,7 +179,7 @@ __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArg
     // fetch cursor (item generation)
     int fk = 0;             // source whose items are being generated
     int fe = e_lo;          // next edge to hand out
-    int f_end = RG_CP(1);   // end of source fk's edges
+    int f_end = part >= 0 ? e_hi : RG_CP(1);   // end of source fk's edges
     bool own_done = false;  // OWN(fk) already handed out
     bool end_done = false;  // the closing IT_END item already handed out
     int base = e_lo - 32;   // edge-metadata window [base, base + 32) held across the lanes
@@ -266,7 +275,11 @@ __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArg
   if (ty_ == IT_EDGE) {                                                                        \
     RG_EDGE_ITEM(sl_, rl_, x_, zz_, mi_, tt_)                                                  \
   } else {                                                                                     \
-    if (cur >= 0) {                                                                            \
+    if (cur >= 0 && part >= 0) { /* split source: park the partial row for the merge kernel */  \
+      const long long row_off = static_cast<long long>(part) * C + lane_off;                   \
+      _Pragma("unroll") for (int k = 0; k < KV; ++k)                                           \
+        if (RG_VALID(k)) RowVec<float, V>::store(a.part_acc + row_off + k * kstride, acc[k]);  \
+    } else if (cur >= 0) {                                                                     \
       const long long row_off = static_cast<long long>(n_lo + cur) * C + lane_off;             \
       _Pragma("unroll") for (int k = 0; k < KV; ++k) {                                         \
         if (RG_VALID(k)) {                                                                     \
@@ -462,6 +475,32 @@ extern "C" int relgat_layer_bwd_prep(const float* dY, const float* out, const fl
   return launch_tasks(bwd_prep_kernel<1>, a, static_cast<long long>(N) * (H / hg), s);
 }
 
+// dP rows of split sources: ordered sum of their parts.
+template <int V>
+__global__ void __launch_bounds__(128)
+bwd_src_merge_kernel(const SrcArgs<V> a, const int* __restrict__ long_node, const int* __restrict__ long_part_ptr,
+                     int n_long) {
+  const int C = a.H * a.F;
+  const int li = blockIdx.x;
+  if (li >= n_long) return;
+  const int i = long_node[li];
+  const int p_lo = long_part_ptr[li], p_hi = long_part_ptr[li + 1];
+  for (int c = threadIdx.x * V; c < C; c += blockDim.x * V) {
+    float acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = 0.f;
+    for (int p = p_lo; p < p_hi; ++p) {
+      float x[V];
+      RowVec<float, V>::load_cached(a.part_acc + static_cast<long long>(p) * C + c, x);
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[v] += x[v];
+    }
+    const long long off = static_cast<long long>(i) * C + c;
+    if (a.dP) RowVec<float, V>::store(a.dP + off, acc);
+    if (a.dP_hi) store_split_bf16<V>(a.dP_hi + off, a.dP_lo ? a.dP_lo + off : nullptr, acc);
+  }
+}
+
 template <int V, int KV>
 static int launch_src_kv(SrcArgs<V> a, int sm_count, cudaStream_t s) {
   const int groups = a.H / a.hg;
@@ -509,27 +548,41 @@ static int launch_src(const SrcArgs<V>& a, int sm_count, cudaStream_t s) {
 extern "C" int relgat_layer_bwd_src(const float* P, long long ldp, const float* G, const float* A,
                                     const float* z, const float* minv, const float* t,
                                     const int* colptr, const int* csc_slot, const int* csc_dst, const int* csc_rel,
-                                    const int* chunk_node, int n_chunks,
+                                    const int* chunks, int n_chunks, const int* parts, int n_parts,
+                                    const int* long_node, const int* long_part_ptr, int n_long, float* part_acc,
                                     float* dP, void* dP_hi, void* dP_lo, float* dz,
                                     int H, int F, int R, int sm_count, void* stream) {
-  if (!P || !G || !A || !colptr || !chunk_node || n_chunks < 0 || H <= 0 || F <= 0 || R <= 0) return RG_ERR_ARG;
+  if (!P || !G || !A || !colptr || n_chunks < 0 || n_parts < 0 || n_long < 0 || H <= 0 || F <= 0 || R <= 0)
+    return RG_ERR_ARG;
+  if (n_chunks > 0 && !chunks) return RG_ERR_ARG;
+  if (n_parts > 0 && (!parts || !long_node || !long_part_ptr || !part_acc)) return RG_ERR_ARG;
+  if (n_chunks == 0) return RG_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool planes_ok = (!dP_hi || reinterpret_cast<uintptr_t>(dP_hi) % 8 == 0) &&
                          (!dP_lo || reinterpret_cast<uintptr_t>(dP_lo) % 8 == 0);
-  if (F % 4 == 0 && ldp % 4 == 0 && al16(P) && al16(G) && al16(A) && (!dP || al16(dP)) && planes_ok) {
+  const int4* ch = reinterpret_cast<const int4*>(chunks);
+  const int2* pt = reinterpret_cast<const int2*>(parts);
+  if (F % 4 == 0 && ldp % 4 == 0 && al16(P) && al16(G) && al16(A) && (!dP || al16(dP)) && planes_ok &&
+      (!part_acc || al16(part_acc))) {
     const int hg = pick_heads_per_warp(H, F, 4, R, smem_budget_override("RELGAT_SRC_BUDGET_KB", kSmemBudgetA));
     if (!hg) return RG_ERR_SHAPE;
-    SrcArgs<4> a{P, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, chunk_node, dP,
+    SrcArgs<4> a{P, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, ch, pt, part_acc, dP,
                  static_cast<__nv_bfloat16*>(dP_hi), static_cast<__nv_bfloat16*>(dP_lo), dz,
                  n_chunks, H, F, R, hg, ldp, 0, 0};
-    return launch_src(a, sm_count, s);
+    int rc = launch_src(a, sm_count, s);
+    if (rc != RG_OK || n_long == 0) return rc;
+    bwd_src_merge_kernel<4><<<n_long, 128, 0, s>>>(a, long_node, long_part_ptr, n_long);
+    return cuda_status(cudaGetLastError());
   }
   const int hg = pick_heads_per_warp(H, F, 1, R);
   if (!hg) return RG_ERR_SHAPE;
-  SrcArgs<1> a{P, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, chunk_node, dP,
+  SrcArgs<1> a{P, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, ch, pt, part_acc, dP,
                static_cast<__nv_bfloat16*>(dP_hi), static_cast<__nv_bfloat16*>(dP_lo), dz,
                n_chunks, H, F, R, hg, ldp, 0, 0};
-  return launch_src(a, sm_count, s);
+  int rc = launch_src(a, sm_count, s);
+  if (rc != RG_OK || n_long == 0) return rc;
+  bwd_src_merge_kernel<1><<<n_long, 128, 0, s>>>(a, long_node, long_part_ptr, n_long);
+  return cuda_status(cudaGetLastError());
 }
 
 extern "C" int relgat_layer_bwd_rel(const float* P, long long ldp, const float* dz, const float* hsum,

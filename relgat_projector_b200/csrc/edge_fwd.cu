@@ -37,7 +37,11 @@ struct FwdArgs {
   const int* rowptr;     // [N+1]
   const int* csr_src;    // [E]
   const int* csr_rel;    // [E]
-  const int* chunk_node; // [n_chunks+1] first destination of every chunk (<= 64 destinations each)
+  const int4* chunks;    // [n_chunks] (first destination, count <= 64, part slot or -1, 0)
+  const int2* parts;     // [n_parts] (first edge, end edge) of the parts of split (long) destinations
+  float* part_ml;        // [n_parts, H, 2] partial (max, sum)
+  float* part_b;         // [n_parts] partial bias sums
+  float* part_acc;       // [n_parts, H*F] partial un-normalised accumulators
   float* out;            // [N, H*F] fp32 layer output (pre-activation), may be nullptr
   __nv_bfloat16* act_hi; // [N, H*F] optional bf16 copy of act(out) (hi part)
   __nv_bfloat16* act_lo; // [N, H*F] optional residual (lo part); nullptr = hi only
@@ -95,8 +99,10 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
   }
 
   for (int c = blockIdx.x * kFwdWarps + warp; c < a.n_chunks; c += gridDim.x * kFwdWarps) {
-    const int n_lo = a.chunk_node[c];
-    const int nn = a.chunk_node[c + 1] - n_lo;  // 1..64 destinations
+    const int4 ch = __ldg(a.chunks + c);
+    const int n_lo = ch.x;
+    const int nn = ch.y;     // 1..64 destinations
+    const int part = ch.z;   // >= 0: this chunk is one part of a split (long) destination
     // rowptr window of the chunk, spread over the lanes (nn + 1 <= 65 entries)
     int rp0 = 0, rp1 = 0, rp2 = 0;
     if (lane <= nn) rp0 = __ldg(a.rowptr + n_lo + lane);
@@ -105,8 +111,13 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
 #define RG_RP(k_) ((k_) < 32 ? __shfl_sync(0xffffffffu, rp0, (k_) & 31)       \
                              : ((k_) < 64 ? __shfl_sync(0xffffffffu, rp1, (k_) & 31) \
                                           : __shfl_sync(0xffffffffu, rp2, (k_) & 31)))
-    const int e_lo = RG_RP(0);
-    const int e_hi = RG_RP(nn);
+    int e_lo = RG_RP(0);
+    int e_hi = RG_RP(nn);
+    if (part >= 0) {  // sub-range of the destination's segment
+      const int2 pe = __ldg(a.parts + part);
+      e_lo = pe.x;
+      e_hi = pe.y;
+    }
 
     float acc[KV][V];
 #pragma unroll
@@ -116,7 +127,7 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
     float m = -INFINITY, l = 0.f, bsum = 0.f;
     int kn = 0;  // destination cursor inside the chunk
     int seg_start = e_lo;
-    int seg_end = RG_RP(1);
+    int seg_end = part >= 0 ? e_hi : RG_RP(1);
     int base = e_lo - 32;  // (src, rel) window [base, base + 32) held across the lanes
     int my_src = 0, my_rel = 0;
     float my_beta = 0.f;
@@ -210,6 +221,18 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
       int u = 0;
       while (true) {
         const int cur = e + u;
+        if (kn < nn && cur == seg_end && part >= 0) {
+          // split destination: park the running (max, sum, bias, accumulator) for the merge kernel
+          const long long prow = static_cast<long long>(part) * C + lane_off;
+#pragma unroll
+          for (int k = 0; k < KV; ++k)
+            if (RG_VALID(k)) RowVec<float, V>::store(a.part_acc + prow + k * kstride, acc[k]);
+          if (lm.sub == 0)
+            *reinterpret_cast<float2*>(a.part_ml + (static_cast<long long>(part) * a.H + lm.hh) * 2) = make_float2(m, l);
+          if (g == 0 && lane == 0) a.part_b[part] = bsum;
+          ++kn;
+          continue;
+        }
         if (kn < nn && cur == seg_end) {
           const int j = n_lo + kn;
           const bool empty = (seg_end == seg_start);
@@ -275,6 +298,91 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
 #undef RG_VALID
 }
 
+// Combines the parts of split destinations in part order (flash-decoding style) and writes the
+// same outputs as the main kernel's epilogue.  One warp per (split destination, head-group).
+template <int V>
+__global__ void __launch_bounds__(128)
+edge_fwd_merge_kernel(const FwdArgs<float, V> a, const int* __restrict__ long_node,
+                      const int* __restrict__ long_part_ptr, int n_long) {
+  const int lane = threadIdx.x & 31;
+  const int groups = a.H / a.hg;
+  const int task = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (task >= n_long * groups) return;
+  const int li = task / groups, g = task - li * groups;
+  const LaneMap lm = make_lane_map<V>(lane, g, a.hg, a.F);
+  const int C = a.H * a.F;
+  const int j = long_node[li];
+  const int p_lo = long_part_ptr[li], p_hi = long_part_ptr[li + 1];
+  float M = -INFINITY;
+  bool nan = false;
+  for (int p = p_lo; p < p_hi; ++p) {
+    const float mp = a.part_ml[(static_cast<long long>(p) * a.H + lm.hh) * 2];
+    nan |= (mp != mp);
+    M = fmaxf(M, mp);
+  }
+  if (nan) M = NAN;
+  float L = 0.f, bsum = 0.f;
+  float acc[kMaxVecPerLane][V];
+#pragma unroll
+  for (int k = 0; k < kMaxVecPerLane; ++k)
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[k][v] = 0.f;
+  for (int p = p_lo; p < p_hi; ++p) {
+    const float2 ml = *reinterpret_cast<const float2*>(a.part_ml + (static_cast<long long>(p) * a.H + lm.hh) * 2);
+    const float sc = __expf(ml.x - M);
+    L = fmaf(ml.y, sc, L);
+    bsum += a.part_b[p];
+#pragma unroll
+    for (int k = 0; k < kMaxVecPerLane; ++k) {
+      const int q = lm.sub + lm.lph * k;
+      if (q < lm.vph) {
+        float x[V];
+        RowVec<float, V>::load_cached(a.part_acc + static_cast<long long>(p) * C + lm.head_off + q * V, x);
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[k][v] = fmaf(x[v], sc, acc[k][v]);
+      }
+    }
+  }
+  const float inv = 1.f / fmaxf(L, 1e-16f);
+#pragma unroll
+  for (int k = 0; k < kMaxVecPerLane; ++k) {
+    const int q = lm.sub + lm.lph * k;
+    if (q < lm.vph) {
+      float o[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) o[v] = fmaf(acc[k][v], inv, bsum);
+      const long long off = static_cast<long long>(j) * C + lm.head_off + q * V;
+      if (a.out) RowVec<float, V>::store(a.out + off, o);
+      if (a.act_hi) {
+        if (a.apply_elu) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) o[v] = elu1(o[v]);
+        }
+        store_split_bf16<V>(a.act_hi + off, a.act_lo ? a.act_lo + off : nullptr, o);
+      }
+    }
+  }
+  if (g == 0 && lane == 0 && a.bias_out) a.bias_out[j] = bsum;
+  if (lm.sub == 0 && a.minv)
+    *reinterpret_cast<float2*>(a.minv + (static_cast<long long>(j) * a.H + lm.hh) * 2) = make_float2(M, inv);
+  if (a.alpha) {
+    const int e0 = a.rowptr[j], e1 = a.rowptr[j + 1];
+    const int items = (e1 - e0) * a.hg;
+    for (int it = 0; it < items; it += 32) {
+      const int idx = it + lane;
+      const int hgi = idx % a.hg;
+      const float mh = __shfl_sync(0xffffffffu, M, hgi * lm.lph);
+      const float ih = __shfl_sync(0xffffffffu, inv, hgi * lm.lph);
+      if (idx < items) {
+        const long long o = static_cast<long long>(e0 + idx / a.hg) * a.H + g * a.hg + hgi;
+        const float zz = a.z[o];
+        const float ee = zz > 0.f ? zz : kLeakySlope * zz;
+        a.alpha[o] = __expf(ee - mh) * ih;
+      }
+    }
+  }
+}
+
 template <typename T, int V, int KV>
 static int launch_fwd_kv(FwdArgs<T, V> a, int sm_count, cudaStream_t stream) {
   const int groups = a.H / a.hg;
@@ -325,30 +433,48 @@ using namespace relgat;
 
 extern "C" int relgat_layer_fwd(
     const void* P, int p_is_bf16, long long ldp, const float* A, const float* beta,
-    const int* rowptr, const int* csr_src, const int* csr_rel, const int* chunk_node, int n_chunks,
+    const int* rowptr, const int* csr_src, const int* csr_rel,
+    const int* chunks, int n_chunks, const int* parts, int n_parts,
+    const int* long_node, const int* long_part_ptr, int n_long,
+    float* part_ml, float* part_b, float* part_acc,
     float* out, void* act_hi, void* act_lo, int apply_elu,
     float* alpha, float* z, float* minv, float* bias_out,
     int H, int F, int R, int sm_count, void* stream) {
-  if (!P || !A || !rowptr || !chunk_node || n_chunks < 0 || H <= 0 || F <= 0 || R <= 0) return RG_ERR_ARG;
+  if (!P || !A || !rowptr || n_chunks < 0 || n_parts < 0 || n_long < 0 || H <= 0 || F <= 0 || R <= 0) return RG_ERR_ARG;
+  if (n_chunks > 0 && !chunks) return RG_ERR_ARG;
+  if (n_parts > 0 && (!parts || !long_node || !long_part_ptr || !part_ml || !part_b || !part_acc)) return RG_ERR_ARG;
   if (p_is_bf16) return RG_ERR_DTYPE;  // bf16 feature storage: not built in this round
+  if (n_chunks == 0) return RG_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool vec_ok = (reinterpret_cast<uintptr_t>(P) % 16 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0) &&
                       (!out || reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
                       (!act_hi || reinterpret_cast<uintptr_t>(act_hi) % 8 == 0) &&
-                      (!act_lo || reinterpret_cast<uintptr_t>(act_lo) % 8 == 0);
+                      (!act_lo || reinterpret_cast<uintptr_t>(act_lo) % 8 == 0) &&
+                      (!part_acc || reinterpret_cast<uintptr_t>(part_acc) % 16 == 0);
   const bool v4 = (F % 4 == 0) && (ldp % 4 == 0) && vec_ok;
+  const int4* ch = reinterpret_cast<const int4*>(chunks);
+  const int2* pt = reinterpret_cast<const int2*>(parts);
+  const int groups_blocks = 4;
   if (v4) {
     const int hg = pick_heads_per_warp(H, F, 4, R, smem_budget_override("RELGAT_FWD_BUDGET_KB", kSmemBudgetA));
     if (!hg) return RG_ERR_SHAPE;
-    FwdArgs<float, 4> a{static_cast<const float*>(P), A, beta, rowptr, csr_src, csr_rel, chunk_node, out,
-                        static_cast<__nv_bfloat16*>(act_hi), static_cast<__nv_bfloat16*>(act_lo),
+    FwdArgs<float, 4> a{static_cast<const float*>(P), A, beta, rowptr, csr_src, csr_rel, ch, pt, part_ml, part_b,
+                        part_acc, out, static_cast<__nv_bfloat16*>(act_hi), static_cast<__nv_bfloat16*>(act_lo),
                         alpha, z, minv, bias_out, n_chunks, H, F, R, hg, ldp, apply_elu, 0, 0};
-    return launch_fwd(a, sm_count, s);
+    int rc = launch_fwd(a, sm_count, s);
+    if (rc != RG_OK || n_long == 0) return rc;
+    const int tasks = n_long * (H / hg);
+    edge_fwd_merge_kernel<4><<<(tasks + groups_blocks - 1) / groups_blocks, 128, 0, s>>>(a, long_node, long_part_ptr, n_long);
+    return cuda_status(cudaGetLastError());
   }
   const int hg = pick_heads_per_warp(H, F, 1, R);
   if (!hg) return RG_ERR_SHAPE;
-  FwdArgs<float, 1> a{static_cast<const float*>(P), A, beta, rowptr, csr_src, csr_rel, chunk_node, out,
-                      static_cast<__nv_bfloat16*>(act_hi), static_cast<__nv_bfloat16*>(act_lo),
+  FwdArgs<float, 1> a{static_cast<const float*>(P), A, beta, rowptr, csr_src, csr_rel, ch, pt, part_ml, part_b,
+                      part_acc, out, static_cast<__nv_bfloat16*>(act_hi), static_cast<__nv_bfloat16*>(act_lo),
                       alpha, z, minv, bias_out, n_chunks, H, F, R, hg, ldp, apply_elu, 0, 0};
-  return launch_fwd(a, sm_count, s);
+  int rc = launch_fwd(a, sm_count, s);
+  if (rc != RG_OK || n_long == 0) return rc;
+  const int tasks = n_long * (H / hg);
+  edge_fwd_merge_kernel<1><<<(tasks + groups_blocks - 1) / groups_blocks, 128, 0, s>>>(a, long_node, long_part_ptr, n_long);
+  return cuda_status(cudaGetLastError());
 }

@@ -19,21 +19,72 @@ STREAM_CHUNK_EDGES = 64  # target edges per warp-chunk of the forward / by-sourc
 STREAM_CHUNK_NODES = 64  # hard cap on segments per chunk (the kernels hold the pointer window in 3 registers)
 
 
-def stream_chunks(ptr: torch.Tensor, chunk_edges: int = STREAM_CHUNK_EDGES,
-                  chunk_nodes: int = STREAM_CHUNK_NODES) -> torch.Tensor:
-    """Cut a CSR pointer array [n+1] into chunks at segment boundaries: a new chunk starts at
-    segment j when its first edge crosses a multiple of ``chunk_edges`` or j is a multiple of
-    ``chunk_nodes``.  Returns chunk_node [n_chunks+1] (int32).  Deterministic, one-off per graph."""
-    n = ptr.numel() - 1
-    if n <= 0:
-        return torch.zeros(1, dtype=torch.int32, device=ptr.device)
-    start = ptr[:-1].to(torch.int64)
-    idx = torch.arange(n, device=ptr.device, dtype=torch.int64)
-    key = (start // chunk_edges) * (n // chunk_nodes + 2) + idx // chunk_nodes
-    new = torch.ones(n, dtype=torch.bool, device=ptr.device)
-    new[1:] = key[1:] != key[:-1]
-    heads = torch.nonzero(new).flatten()
-    return torch.cat([heads, torch.tensor([n], device=ptr.device)]).to(torch.int32)
+LONG_SEGMENT = 512   # segments with more edges are split across warps (heavy-tailed graphs)
+PART_EDGES = 256     # edges per part of a split segment
+
+
+class StreamChunks:
+    """Work decomposition of a CSR pointer array for the streaming edge kernels.
+
+    ``chunks`` int32 [n_chunks, 4] = (first segment, number of segments (1..64), part slot or -1, 0):
+    ordinary chunks cover whole segments, ~``chunk_edges`` edges; a segment longer than
+    ``long_segment`` is isolated and cut into parts of ``part_edges`` edges, one chunk per part,
+    whose partial results a merge kernel combines in part order (deterministic).
+    ``parts`` int32 [n_parts, 2] = (first edge, end edge); ``long_node`` [n_long] and
+    ``long_part_ptr`` [n_long+1] list the split segments and their part ranges.
+    """
+
+    def __init__(self, ptr: torch.Tensor, chunk_edges: int = STREAM_CHUNK_EDGES,
+                 chunk_nodes: int = STREAM_CHUNK_NODES, long_segment: int = LONG_SEGMENT,
+                 part_edges: int = PART_EDGES):
+        dev = ptr.device
+        n = ptr.numel() - 1
+        i32 = dict(dtype=torch.int32, device=dev)
+        if n <= 0:
+            self.chunks = torch.zeros((0, 4), **i32)
+            self.parts = torch.zeros((0, 2), **i32)
+            self.long_node = torch.zeros((0,), **i32)
+            self.long_part_ptr = torch.zeros((1,), **i32)
+            self.n_chunks = self.n_parts = self.n_long = 0
+            return
+        p64 = ptr.to(torch.int64)
+        start, deg = p64[:-1], p64[1:] - p64[:-1]
+        is_long = deg > long_segment
+        idx = torch.arange(n, device=dev, dtype=torch.int64)
+        # a long segment is alone in its chunk: the island id changes at it and right after it
+        bump = is_long.clone()
+        bump[1:] |= is_long[:-1]
+        island = torch.cumsum(bump.to(torch.int64), 0)
+        new = torch.ones(n, dtype=torch.bool, device=dev)
+        new[1:] = ((island[1:] != island[:-1]) | ((start[1:] // chunk_edges) != (start[:-1] // chunk_edges))
+                   | ((idx[1:] // chunk_nodes) != (idx[:-1] // chunk_nodes)))
+        heads = torch.nonzero(new).flatten()
+        ends = torch.cat([heads[1:], torch.tensor([n], device=dev)])
+        head_long = is_long[heads]
+        # ordinary chunks
+        o_lo, o_nn = heads[~head_long], (ends - heads)[~head_long]
+        # split segments -> parts
+        ln = heads[head_long]
+        n_parts_per = (deg[ln] + part_edges - 1) // part_edges
+        self.n_long = int(ln.numel())
+        part_ptr = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(n_parts_per, 0)])
+        self.n_parts = int(part_ptr[-1].item())
+        owner = torch.repeat_interleave(torch.arange(self.n_long, device=dev), n_parts_per)
+        within = torch.arange(self.n_parts, device=dev) - part_ptr[:-1][owner]
+        pe_lo = start[ln][owner] + within * part_edges
+        pe_hi = torch.minimum(pe_lo + part_edges, p64[1:][ln][owner])
+        slots = torch.arange(self.n_parts, device=dev)
+        c_lo = torch.cat([o_lo, ln[owner]])
+        c_nn = torch.cat([o_nn, torch.ones(self.n_parts, dtype=torch.int64, device=dev)])
+        c_part = torch.cat([torch.full_like(o_lo, -1), slots])
+        # long parts first: they are the longest tasks of the launch
+        order = torch.argsort(c_part >= 0, descending=True, stable=True)
+        self.chunks = torch.stack([c_lo, c_nn, c_part, torch.zeros_like(c_lo)], 1)[order].to(torch.int32).contiguous()
+        self.parts = torch.stack([pe_lo, pe_hi], 1).to(torch.int32).contiguous() if self.n_parts else \
+            torch.zeros((0, 2), **i32)
+        self.long_node = ln.to(torch.int32)
+        self.long_part_ptr = part_ptr.to(torch.int32)
+        self.n_chunks = int(self.chunks.size(0))
 
 
 class GraphIndex:
@@ -83,10 +134,8 @@ class GraphIndex:
                 _lib.ptr(ws), ws_bytes, stream)
         _lib.check(rc, "relgat_graph_index_build")
         self._build_rel_chunks()
-        self.fwd_chunk_node = stream_chunks(self.rowptr)
-        self.src_chunk_node = stream_chunks(self.colptr)
-        self.n_fwd_chunks = int(self.fwd_chunk_node.numel()) - 1
-        self.n_src_chunks = int(self.src_chunk_node.numel()) - 1
+        self.fwd_chunks = StreamChunks(self.rowptr)
+        self.src_chunks = StreamChunks(self.colptr)
         self.max_in_degree = int((self.rowptr[1:] - self.rowptr[:-1]).max().item()) if N > 0 else 0
         self.max_out_degree = int((self.colptr[1:] - self.colptr[:-1]).max().item()) if NS > 0 else 0
         del ws

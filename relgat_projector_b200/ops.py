@@ -135,14 +135,21 @@ def edge_fwd(P: torch.Tensor, A: torch.Tensor, beta: Optional[torch.Tensor], g: 
     z = torch.empty((E, H), dtype=torch.float32, device=dev)
     minv = torch.empty((N, H, 2), dtype=torch.float32, device=dev)
     bias = torch.empty((N,), dtype=torch.float32, device=dev)
+    ck = g.fwd_chunks
+    part_ml = torch.empty((ck.n_parts, H, 2), dtype=torch.float32, device=dev) if ck.n_parts else None
+    part_b = torch.empty((ck.n_parts,), dtype=torch.float32, device=dev) if ck.n_parts else None
+    part_acc = torch.empty((ck.n_parts, C), dtype=torch.float32, device=dev) if ck.n_parts else None
     with torch.cuda.device(dev):
         rc = _lib.load().relgat_layer_fwd(
             _lib.ptr(P), 0, P.stride(0), _lib.ptr(A), _lib.ptr(beta),
-            _lib.ptr(g.rowptr), _lib.ptr(g.csr_src), _lib.ptr(g.csr_rel), _lib.ptr(g.fwd_chunk_node), g.n_fwd_chunks,
+            _lib.ptr(g.rowptr), _lib.ptr(g.csr_src), _lib.ptr(g.csr_rel),
+            _lib.ptr(ck.chunks), ck.n_chunks, _lib.ptr(ck.parts), ck.n_parts,
+            _lib.ptr(ck.long_node), _lib.ptr(ck.long_part_ptr), ck.n_long,
+            _lib.ptr(part_ml), _lib.ptr(part_b), _lib.ptr(part_acc),
             _lib.ptr(out), _lib.ptr(hi), _lib.ptr(lo), int(apply_elu),
             _lib.ptr(alpha), _lib.ptr(z), _lib.ptr(minv), _lib.ptr(bias), H, F, R, sm_count(dev), _stream(P))
     _lib.check(rc, "relgat_layer_fwd")
-    _count(1)
+    _count(2 if ck.n_long else 1)
     return out, ((hi, lo) if want_act else None), alpha, z, minv, bias
 
 
@@ -178,14 +185,17 @@ def edge_bwd_src(P, G, A, z, minv, t, g: GraphIndex, H: int, F: int, want_fp32: 
     hi = torch.empty((n_src, C), dtype=torch.bfloat16, device=dev) if want_planes else None
     lo = torch.empty((n_src, C), dtype=torch.bfloat16, device=dev) if (want_planes and planes_lo) else None
     dz = torch.empty((g.E, H), dtype=torch.float32, device=dev)
+    ck = g.src_chunks
+    part_acc = torch.empty((ck.n_parts, C), dtype=torch.float32, device=dev) if ck.n_parts else None
     with torch.cuda.device(dev):
         rc = _lib.load().relgat_layer_bwd_src(
             _lib.ptr(P), P.stride(0), _lib.ptr(G), _lib.ptr(A), _lib.ptr(z), _lib.ptr(minv), _lib.ptr(t),
             _lib.ptr(g.colptr), _lib.ptr(g.csc_slot), _lib.ptr(g.csc_dst), _lib.ptr(g.csc_rel),
-            _lib.ptr(g.src_chunk_node), g.n_src_chunks,
+            _lib.ptr(ck.chunks), ck.n_chunks, _lib.ptr(ck.parts), ck.n_parts,
+            _lib.ptr(ck.long_node), _lib.ptr(ck.long_part_ptr), ck.n_long, _lib.ptr(part_acc),
             _lib.ptr(dP), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dz), H, F, g.R, sm_count(dev), _stream(P))
     _lib.check(rc, "relgat_layer_bwd_src")
-    _count(1)
+    _count(2 if ck.n_long else 1)
     return dP, ((hi, lo) if want_planes else None), dz
 
 
