@@ -298,39 +298,40 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
 #undef RG_VALID
 }
 
-// Combines the parts of split destinations in part order (flash-decoding style) and writes the
-// same outputs as the main kernel's epilogue.  One warp per (split destination, head-group).
+// Combines the parts of split destinations (flash-decoding style) and writes the same outputs as
+// the main kernel's epilogue.  One CTA of kMergeWarps warps per (split destination, head-group):
+// warp w folds parts p_lo+w, p_lo+w+kMergeWarps, ... in ascending order, the per-warp states are
+// then folded in warp order — a fixed reduction tree, so results are reproducible.
+constexpr int kMergeWarps = 8;
+
 template <int V>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kMergeWarps * 32)
 edge_fwd_merge_kernel(const FwdArgs<float, V> a, const int* __restrict__ long_node,
                       const int* __restrict__ long_part_ptr, int n_long) {
-  const int lane = threadIdx.x & 31;
+  __shared__ __align__(16) float sm_acc[kMergeWarps][kMaxVecPerLane * 32 * V];
+  __shared__ float sm_m[kMergeWarps][32], sm_l[kMergeWarps][32], sm_b[kMergeWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int groups = a.H / a.hg;
-  const int task = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int task = blockIdx.x;
   if (task >= n_long * groups) return;
   const int li = task / groups, g = task - li * groups;
   const LaneMap lm = make_lane_map<V>(lane, g, a.hg, a.F);
   const int C = a.H * a.F;
   const int j = long_node[li];
   const int p_lo = long_part_ptr[li], p_hi = long_part_ptr[li + 1];
-  float M = -INFINITY;
-  bool nan = false;
-  for (int p = p_lo; p < p_hi; ++p) {
-    const float mp = a.part_ml[(static_cast<long long>(p) * a.H + lm.hh) * 2];
-    nan |= (mp != mp);
-    M = fmaxf(M, mp);
-  }
-  if (nan) M = NAN;
-  float L = 0.f, bsum = 0.f;
+
+  // pass 1 (per warp): online merge of this warp's parts
+  float M = -INFINITY, L = 0.f, bsum = 0.f;
   float acc[kMaxVecPerLane][V];
 #pragma unroll
   for (int k = 0; k < kMaxVecPerLane; ++k)
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[k][v] = 0.f;
-  for (int p = p_lo; p < p_hi; ++p) {
+  for (int p = p_lo + warp; p < p_hi; p += kMergeWarps) {
     const float2 ml = *reinterpret_cast<const float2*>(a.part_ml + (static_cast<long long>(p) * a.H + lm.hh) * 2);
-    const float sc = __expf(ml.x - M);
-    L = fmaf(ml.y, sc, L);
+    const float mn = (ml.x != ml.x) ? ml.x : fmaxf(M, ml.x);
+    const float s_old = __expf(M - mn), s_new = __expf(ml.x - mn);
+    L = fmaf(L, s_old, ml.y * s_new);
     bsum += a.part_b[p];
 #pragma unroll
     for (int k = 0; k < kMaxVecPerLane; ++k) {
@@ -339,9 +340,35 @@ edge_fwd_merge_kernel(const FwdArgs<float, V> a, const int* __restrict__ long_no
         float x[V];
         RowVec<float, V>::load_cached(a.part_acc + static_cast<long long>(p) * C + lm.head_off + q * V, x);
 #pragma unroll
-        for (int v = 0; v < V; ++v) acc[k][v] = fmaf(x[v], sc, acc[k][v]);
+        for (int v = 0; v < V; ++v) acc[k][v] = fmaf(acc[k][v], s_old, x[v] * s_new);
       }
     }
+    M = mn;
+  }
+#pragma unroll
+  for (int k = 0; k < kMaxVecPerLane; ++k) RowVec<float, V>::store(&sm_acc[warp][(k * 32 + lane) * V], acc[k]);
+  sm_m[warp][lane] = M;
+  sm_l[warp][lane] = L;
+  if (lane == 0) sm_b[warp] = bsum;
+  __syncthreads();
+  if (warp != 0) return;
+
+  // pass 2 (warp 0): fold the per-warp states in warp order
+  const int nw = min(kMergeWarps, p_hi - p_lo);
+  for (int w = 1; w < nw; ++w) {
+    const float mw = sm_m[w][lane], lw = sm_l[w][lane];
+    const float mn = (mw != mw) ? mw : fmaxf(M, mw);
+    const float s_old = __expf(M - mn), s_new = __expf(mw - mn);
+    L = fmaf(L, s_old, lw * s_new);
+    bsum += sm_b[w];
+#pragma unroll
+    for (int k = 0; k < kMaxVecPerLane; ++k) {
+      float x[V];
+      RowVec<float, V>::load_shared(&sm_acc[w][(k * 32 + lane) * V], x);
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[k][v] = fmaf(acc[k][v], s_old, x[v] * s_new);
+    }
+    M = mn;
   }
   const float inv = 1.f / fmaxf(L, 1e-16f);
 #pragma unroll
@@ -454,7 +481,6 @@ extern "C" int relgat_layer_fwd(
   const bool v4 = (F % 4 == 0) && (ldp % 4 == 0) && vec_ok;
   const int4* ch = reinterpret_cast<const int4*>(chunks);
   const int2* pt = reinterpret_cast<const int2*>(parts);
-  const int groups_blocks = 4;
   if (v4) {
     const int hg = pick_heads_per_warp(H, F, 4, R, smem_budget_override("RELGAT_FWD_BUDGET_KB", kSmemBudgetA));
     if (!hg) return RG_ERR_SHAPE;
@@ -464,7 +490,7 @@ extern "C" int relgat_layer_fwd(
     int rc = launch_fwd(a, sm_count, s);
     if (rc != RG_OK || n_long == 0) return rc;
     const int tasks = n_long * (H / hg);
-    edge_fwd_merge_kernel<4><<<(tasks + groups_blocks - 1) / groups_blocks, 128, 0, s>>>(a, long_node, long_part_ptr, n_long);
+    edge_fwd_merge_kernel<4><<<tasks, kMergeWarps * 32, 0, s>>>(a, long_node, long_part_ptr, n_long);
     return cuda_status(cudaGetLastError());
   }
   const int hg = pick_heads_per_warp(H, F, 1, R);
@@ -475,6 +501,6 @@ extern "C" int relgat_layer_fwd(
   int rc = launch_fwd(a, sm_count, s);
   if (rc != RG_OK || n_long == 0) return rc;
   const int tasks = n_long * (H / hg);
-  edge_fwd_merge_kernel<1><<<(tasks + groups_blocks - 1) / groups_blocks, 128, 0, s>>>(a, long_node, long_part_ptr, n_long);
+  edge_fwd_merge_kernel<1><<<tasks, kMergeWarps * 32, 0, s>>>(a, long_node, long_part_ptr, n_long);
   return cuda_status(cudaGetLastError());
 }
