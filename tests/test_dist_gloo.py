@@ -38,7 +38,7 @@ def _worker(rank, world, port, ret):
     try:
         n, r, h, f, src, dst, rel, P, A, beta = _graph()
         ei = torch.from_numpy(np.stack([src, dst])); et = torch.from_numpy(rel)
-        part = RD.DstPartition(ei, et, n, r, rank, world, balance="edges", build_index=False)
+        part = RD.DstPartition(ei, et, n, r, rank, world, balance="edges", build_index=False, mode="allgather")
         # bounds agree with the oracle rule; bucketing is stable and complete
         ref_b = O.partition_bounds_np(dst, n, world, "edges")
         assert part.bounds == [int(v) for v in ref_b]
@@ -60,6 +60,19 @@ def _worker(rank, world, port, ret):
         gathered = RD.all_gather_rows(part.pad_rows(out_loc), world)[padded]
         whole, _, _, _ = O.layer_forward_closed(P, A, beta, O.graph_index_np(src, dst, rel, n, r))
         assert np.allclose(gathered.numpy(), whole.reshape(n, -1), rtol=0, atol=1e-12)
+        # halo mode: only referenced rows travel; extended layout [own | halo] reproduces the same output
+        hp = RD.DstPartition(ei, et, n, r, rank, world, balance="edges", build_index=False, mode="halo")
+        assert hp.n_src == hp.n_local + hp.n_halo and hp.n_halo <= n - hp.n_local
+        P_own = part.local_rows(P_all_true).contiguous()
+        recv = RD._all_to_all_rows(P_own[hp.send_idx], hp.send_counts, hp.recv_counts)
+        assert torch.equal(recv, P_all_true[hp.halo_ids])
+        P_ext = torch.cat([P_own, recv])
+        gh = O.graph_index_np(hp.local_src.numpy(), hp.local_dst.numpy(), hp.local_rel.numpy(), max(hp.n_src, 1), r)
+        out_h, _, _, _ = O.layer_forward_closed(P_ext.numpy().reshape(hp.n_src, h, f), A, beta, gh)
+        assert np.allclose(out_h[:hp.n_local].reshape(hp.n_local, -1), whole.reshape(n, -1)[hp.lo:hp.hi], rtol=0, atol=1e-12)
+        # reverse exchange: halo gradient rows return to their owners
+        back = RD._all_to_all_rows(recv * 0 + float(rank + 1), hp.recv_counts, hp.send_counts)
+        assert back.shape[0] == hp.n_send
         # reduce-scatter of per-rank partial rows == slice of the global sum
         part_rows = torch.full((part.n_padded, 3), float(rank + 1), dtype=torch.float64)
         mine = RD.reduce_scatter_rows(part_rows, world)
