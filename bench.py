@@ -250,6 +250,7 @@ def main():
     ap.add_argument("--config", default=None, help="c1|c2|c3|c4|tiny (default: c2 on 1 GPU, c4 sharded on >1)")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-alt-precision", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=3)
     args = ap.parse_args()
 
@@ -387,6 +388,23 @@ def main():
                  "frac_of_hbm_peak": round(sbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
                  "formula": "SURVEY.md §8(d) bytes_step, fp32"}
 
+    # secondary record: single-pass bf16 tensor-core operands (stated tolerance 2e-2, tests/test_gpu_model.py)
+    alt = None
+    if args.precision == "fp32" and not args.no_alt_precision:
+        model = opt = None
+        torch.cuda.empty_cache()
+        torch.manual_seed(42)
+        model = R.RelGATModel(kg.node_emb, kg.edge_index, kg.edge_type, num_rel=cfg["R"], scorer_type=cfg["scorer"],
+                              gat_out_dim=cfg["F"], gat_heads=cfg["H"], dropout=0.0, gat_num_layers=cfg["L"],
+                              project_to_input_size=cfg["proj"], projection_layers=2, precision="bf16").to(dev)
+        model.train()
+        opt = torch.optim.Adam(model.parameters(), lr=2e-4)
+        for i in range(3):
+            train_step(*dev_batches[i % n_pool])
+        ms_alt = timed(lambda i: train_step(*dev_batches[i % n_pool]), max(args.steps // 2, 5))
+        alt = {"dtype": "bf16 tensor-core operands, fp32 accumulate and storage", "value": E / (ms_alt * 1e-3),
+               "unit": UNIT, "ms_per_step": ms_alt, "tolerance": "2e-2 relative (stated, tested)"}
+
     cpu = None
     if not args.no_cpu_baseline:
         scale = CPU_SAMPLE_SCALE if cfg["N"] >= 100_000 else 1
@@ -409,6 +427,7 @@ def main():
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
         "roofline": roofline, "step_roofline": step_roof, "kernels": kernels, "cpu_baseline": cpu,
+        "alt_precision": alt,
     }
     print(json.dumps(line))
     return 0

@@ -59,11 +59,13 @@ class RelGATStackFunction(torch.autograd.Function):
             if W.size(0) != C:
                 raise ValueError(f"layer {l}: W must be [{C}, D_in]")
             Wp = ops.split_bf16(W.detach(), with_lo)
+            # K-major copy of Wᵀ for dX = dP·W (3 MB transpose; the K-major B path is ~12% faster than MN-major)
+            WTp = ops.split_bf16(W.detach().t().contiguous(), with_lo) if (l > 0 or x0.requires_grad) else None
             P = ops.gemm(planes, False, Wp, False, N, C, d_in)
             last = l == L - 1
             out, act, _, z, minv, bias = ops.edge_fwd(P, A.detach(), None if beta is None else beta.detach(), graph,
                                                       H, F, want_act=not last, apply_elu=True, act_lo=with_lo)
-            saved.append(dict(xp=planes, Wp=Wp, P=P, out=out, minv=minv, z=z, bias=bias, A=A.detach(),
+            saved.append(dict(xp=planes, Wp=Wp, WTp=WTp, P=P, out=out, minv=minv, z=z, bias=bias, A=A.detach(),
                               d_in=d_in, has_beta=beta is not None))
             planes = act
         ctx.saved = saved
@@ -97,7 +99,7 @@ class RelGATStackFunction(torch.autograd.Function):
             dW = ops.gemm(dPp, True, s["xp"], True, C, d_in, N, splits_k=splits)
             grads[3 * l], grads[3 * l + 1], grads[3 * l + 2] = dW, dA, dbeta
             if l > 0 or ctx.x0_needs_grad:
-                dX = ops.gemm(dPp, False, s["Wp"], True, N, d_in, C)
+                dX = ops.gemm(dPp, False, s["WTp"], False, N, d_in, C)
                 dY, owned = dX, True
             main.wait_stream(side)  # join before any buffer of this layer is released or reused
             for tns in (dA, dbeta):
