@@ -174,3 +174,41 @@ class ScoreRowsFunction(torch.autograd.Function):
                                             want_rel=ctx.needs_input_grad[4])
         drel = ops.index_add_sorted(d_rel, rel_ids, rel_emb.size(0)) if d_rel is not None else None
         return None, None, d_src, d_dst, drel, None, None, None
+
+
+class SplitLinearFunction(torch.autograd.Function):
+    """y = x · Wᵀ for a bias-free ``nn.Linear`` on the tcgen05 GEMM (fp32 operands carried as bf16
+    hi/lo planes in "fp32" mode).  Used for the ProjectionHead's linears over all N rows (reference
+    core/model/projection.py:48-72, called from model.py:289-290), where torch's fp32 SGEMM would cost
+    more than the whole GAT stack."""
+
+    @staticmethod
+    def forward(ctx, x, W, precision):
+        with_lo = precision == "fp32"
+        x2 = x.reshape(-1, x.size(-1))
+        xp = ops.split_bf16(x2.detach(), with_lo)
+        Wp = ops.split_bf16(W.detach(), with_lo)
+        y = ops.gemm(xp, False, Wp, False, x2.size(0), W.size(0), W.size(1))
+        ctx.save_for_backward(W)
+        ctx.xp, ctx.with_lo, ctx.x_shape = xp, with_lo, x.shape
+        return y.view(*x.shape[:-1], W.size(0))
+
+    @staticmethod
+    def backward(ctx, gy):
+        (W,) = ctx.saved_tensors
+        with_lo = ctx.with_lo
+        g2 = gy.reshape(-1, gy.size(-1)).contiguous()
+        M, N_out, K_in = g2.size(0), W.size(0), W.size(1)
+        gp = ops.split_bf16(g2, with_lo)
+        dW = dx = None
+        if ctx.needs_input_grad[1]:  # dW[N_out, K_in] = gyᵀ · x  (both operands MN-major, split-K over rows)
+            dW = ops.gemm(gp, True, ctx.xp, True, N_out, K_in, M, splits_k=ops.pick_splits_k(N_out, K_in, M, gy.device))
+        if ctx.needs_input_grad[0]:  # dx[M, K_in] = gy · W  (B = Wᵀ stored K-major)
+            WTp = ops.split_bf16(W.detach().t().contiguous(), with_lo)
+            dx = ops.gemm(gp, False, WTp, False, M, K_in, N_out).view(ctx.x_shape)
+        ctx.xp = None
+        return dx, dW, None
+
+
+def split_linear(x, weight, precision="fp32"):
+    return SplitLinearFunction.apply(x, weight, precision)

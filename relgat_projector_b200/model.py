@@ -76,7 +76,7 @@ class RelGATModel(nn.Module):
         if self.project_to_input_size:
             self.projection = ProjectionHead(in_dim=scorer_dim, out_dim=node_emb.size(1),
                                              hidden_dim=projection_hidden_dim, num_layers=self.projection_layers,
-                                             dropout=projection_dropout)
+                                             dropout=projection_dropout, precision=precision)
             scorer_dim = node_emb.size(1)
         else:
             self.projection = None

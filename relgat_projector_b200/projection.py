@@ -1,6 +1,8 @@
 """``ProjectionHead`` with the reference's structure and state-dict keys (reference
-relgat_projector/core/model/projection.py:7-72).  A plain dense MLP: left to cuBLAS/ATen
-(SURVEY.md §2 row 4 — out of scope for hand kernels; "next" row §8(f)-1)."""
+relgat_projector/core/model/projection.py:7-72).  "Next" row §8(f)-1: on CUDA its bias-free linears
+run on the tcgen05 GEMM of the hot path (fp32-accurate bf16 hi/lo split, or single-pass bf16),
+because torch's fp32 SGEMM over all N rows would cost more than the whole GAT stack; GELU and
+LayerNorm stay ATen element-wise ops."""
 from __future__ import annotations
 
 from typing import Optional
@@ -11,8 +13,9 @@ import torch.nn as nn
 
 class ProjectionHead(nn.Module):
     def __init__(self, in_dim: int, out_dim: int, num_layers: int = 1, dropout: float = 0.0,
-                 hidden_dim: Optional[int] = None):
+                 hidden_dim: Optional[int] = None, precision: str = "fp32"):
         super().__init__()
+        self.precision = precision
         self.in_dim = in_dim
         self.out_dim = out_dim
         self.hidden_dim = hidden_dim if hidden_dim is not None and hidden_dim > 0 else in_dim
@@ -31,5 +34,16 @@ class ProjectionHead(nn.Module):
             blocks.append(nn.Linear(self.hidden_dim, out_dim, bias=False))
             self.net = nn.Sequential(*blocks)
 
+    def _run(self, mod: nn.Module, x: torch.Tensor) -> torch.Tensor:
+        if isinstance(mod, nn.Linear) and mod.bias is None and x.is_cuda and x.dtype == torch.float32:
+            from .functional import split_linear
+            return split_linear(x, mod.weight, self.precision)
+        return mod(x)
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return self.dropout(self.net(x))
+        if isinstance(self.net, nn.Sequential):
+            for mod in self.net:
+                x = self._run(mod, x)
+        else:
+            x = self._run(self.net, x)
+        return self.dropout(x)
