@@ -54,7 +54,8 @@ int relgat_graph_index_build(const long long* src, const long long* dst, const l
 
 /* ---- dense feature transform (tcgen05 + TMA) ---------------------------------------------
  * Replaces `lin(node_emb)` of core/model/layer.py:220 (all heads in one GEMM) and its autograd
- * GEMMs.  D[M,N] fp32 = A·Bᵀ, bf16 operands, fp32 accumulation in tensor memory.
+ * GEMMs.  D[M,N] = A·Bᵀ, bf16 operands, fp32 accumulation in tensor memory; D is written as fp32,
+ * or as bf16 when d_is_bf16 (bf16 feature-storage mode; not with split-K).
  *   a_mn/b_mn = 0: operand stored [rows = M|N, K] (K contiguous); 1: stored [K, M|N].
  *   a_lo/b_lo != NULL selects the fp32-parity mode: operands are (hi, lo) bf16 planes of an
  *   fp32 matrix (relgat_split_bf16) and hi·hi + hi·lo + lo·hi is accumulated.
@@ -63,7 +64,7 @@ int relgat_split_bf16(const float* x, void* hi, void* lo, long long n, void* str
 long long relgat_gemm_workspace_bytes(int M, int N, int K, int a_mn, int b_mn, int splits_k);
 int relgat_gemm_bf16(const void* a_hi, const void* a_lo, long long lda, int a_mn,
                      const void* b_hi, const void* b_lo, long long ldb, int b_mn,
-                     float* d, long long ldd, int M, int N, int K, int splits_k,
+                     void* d, int d_is_bf16, long long ldd, int M, int N, int K, int splits_k,
                      void* workspace, long long workspace_bytes, int sm_count, void* stream);
 
 /* ---- RelGAT layer, edge part, forward ------------------------------------------------------
@@ -95,7 +96,9 @@ int relgat_layer_fwd(const void* P, int p_is_bf16, long long ldp, const float* A
                      int H, int F, int R, int sm_count, void* stream);
 
 /* ---- RelGAT layer, edge part, backward (replaces the autograd replay of layer.py:220-318) ---
- * bwd_prep: G = dY * act'(out) (in place allowed), t[N,H] = <G, out - bias>, hsum[N,H] = sum_f G.
+ * Feature storage: P and G are fp32, or both bf16 when the *_is_bf16 flags are set (F % 8 == 0).
+ * bwd_prep: G = dY * act'(out) (fp32: in place allowed; or written as bf16), t[N,H] = <G, out - bias>,
+ *           hsum[N,H] = sum_f G.
  * bwd_src : by-source pass over chunks of the CSC order (work tables as in fwd, over sources;
  *           part_acc [n_parts, H*F] holds the partial rows of split sources):
  *           dP [N_src, H*F] (fp32 and/or bf16 hi/lo planes) and dz [E, H]; the attention weights
@@ -104,16 +107,16 @@ int relgat_layer_fwd(const void* P, int p_is_bf16, long long ldp, const float* A
  *           two relations; rel_chunk_ptr[R+1] gives each relation's chunk range):
  *           dA [H, R, F] and dbeta [R] (NULL to skip) with an ordered reduction of the partials
  *           partA [n_chunks, H*F], partB [n_chunks]. */
-int relgat_layer_bwd_prep(const float* dY, const float* out, const float* bias, float* G, float* t,
-                          float* hsum, int N, int H, int F, int apply_elu, void* stream);
-int relgat_layer_bwd_src(const float* P, long long ldp, const float* G, const float* A,
+int relgat_layer_bwd_prep(const float* dY, const float* out, const float* bias, void* G, int g_is_bf16,
+                          float* t, float* hsum, int N, int H, int F, int apply_elu, void* stream);
+int relgat_layer_bwd_src(const void* P, long long ldp, const void* G, int feat_is_bf16, const float* A,
                          const float* z, const float* minv, const float* t,
                          const int* colptr, const int* csc_slot, const int* csc_dst, const int* csc_rel,
                          const int* chunks, int n_chunks, const int* parts, int n_parts,
                          const int* long_node, const int* long_part_ptr, int n_long, float* part_acc,
                          float* dP, void* dP_hi, void* dP_lo, float* dz,
                          int H, int F, int R, int sm_count, void* stream);
-int relgat_layer_bwd_rel(const float* P, long long ldp, const float* dz, const float* hsum,
+int relgat_layer_bwd_rel(const void* P, int p_is_bf16, long long ldp, const float* dz, const float* hsum,
                          const int* rel_slot, const int* csr_src, const int* csr_dst,
                          const int* chunk_lo, const int* chunk_hi, const int* rel_chunk_ptr,
                          int n_chunks, float* partA, float* partB, float* dA, float* dbeta,

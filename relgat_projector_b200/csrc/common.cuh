@@ -14,7 +14,11 @@
 
 namespace relgat {
 
-constexpr int kMaxVecPerLane = 8;  // KMAX: 128-bit vectors a lane may own per row
+constexpr int kMaxVecPerLane = 8;  // KMAX: 128-bit vectors a lane may own per row (fp32 layout)
+// a lane owns at most 32 feature elements: 8 vectors of 4 fp32, or 4 vectors of 8 bf16
+template <int V>
+__host__ __device__ constexpr int max_vec() { return V == 8 ? 4 : 8; }
+inline int max_vec_rt(int V) { return V == 8 ? 4 : 8; }
 constexpr float kLeakySlope = 0.2f;  // reference layer.py:233
 // shared-memory budget for a head-group's attention vectors (hg*R*F fp32) in the edge kernels;
 // leaves room for the by-source kernel's per-warp own-row slots (12 x 4 KB) inside 227 KB
@@ -60,6 +64,31 @@ struct RowVec<float, 4> {
     const float4 t = *reinterpret_cast<const float4*>(p);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
+};
+
+template <>
+struct RowVec<float, 8> {  // fp32 data addressed with the 8-element vectors of the bf16 feature layout
+  static __device__ __forceinline__ void load_stream(const float* p, float (&v)[8]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p + 4));
+  }
+  static __device__ __forceinline__ void load_cached(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  static __device__ __forceinline__ void load_shared(const float* p, float (&v)[8]) {
+    const float4 a = reinterpret_cast<const float4*>(p)[0];
+    const float4 b = reinterpret_cast<const float4*>(p)[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void load_any(const float* p, float (&v)[8]) { load_shared(p, v); }
 };
 
 template <>
@@ -112,7 +141,16 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 
 template <int V>
 __device__ __forceinline__ void store_split_bf16(__nv_bfloat16* hi, __nv_bfloat16* lo, const float (&v)[V]) {
-  if constexpr (V == 4) {
+  if constexpr (V == 8) {
+    float h[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = bf16_round(v[i]);
+    *reinterpret_cast<uint4*>(hi) = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]),
+                                               pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+    if (lo)
+      *reinterpret_cast<uint4*>(lo) = make_uint4(pack_bf16x2(v[0] - h[0], v[1] - h[1]), pack_bf16x2(v[2] - h[2], v[3] - h[3]),
+                                                 pack_bf16x2(v[4] - h[4], v[5] - h[5]), pack_bf16x2(v[6] - h[6], v[7] - h[7]));
+  } else if constexpr (V == 4) {
     const float h0 = bf16_round(v[0]), h1 = bf16_round(v[1]), h2 = bf16_round(v[2]), h3 = bf16_round(v[3]);
     *reinterpret_cast<uint2*>(hi) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
     if (lo) *reinterpret_cast<uint2*>(lo) = make_uint2(pack_bf16x2(v[0] - h0, v[1] - h1), pack_bf16x2(v[2] - h2, v[3] - h3));
@@ -175,7 +213,7 @@ inline int pick_heads_per_warp(int H, int F, int V, int R = 0, size_t budget = k
   for (int hg = 32; hg >= 1; hg >>= 1) {
     if (H % hg != 0) continue;
     const int lph = 32 / hg;
-    if ((vph + lph - 1) / lph > kMaxVecPerLane) continue;
+    if ((vph + lph - 1) / lph > max_vec_rt(V)) continue;
     if (!best) best = hg;
     if (R <= 0 || static_cast<size_t>(hg) * R * F * sizeof(float) <= budget) return hg;
   }

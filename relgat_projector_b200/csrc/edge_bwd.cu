@@ -22,19 +22,19 @@ constexpr int kBwdWarps = 4;
 // ------------------------------------------------------------------------------------
 // bwd_prep
 // ------------------------------------------------------------------------------------
-template <int V>
+template <typename TG, int V>
 struct PrepArgs {
   const float* dY;     // [N, C] gradient w.r.t. the layer's (activated) output
   const float* out;    // [N, C] forward pre-activation output
   const float* bias;   // [N] forward bias_out
-  float* G;            // [N, C] gradient w.r.t. out (may alias dY when apply_elu == 0)
+  TG* G;               // [N, C] gradient w.r.t. out, fp32 (may alias dY when apply_elu == 0) or bf16
   float* t;            // [N, H]
   float* hsum;         // [N, H]
   int N, H, F, hg, apply_elu;
 };
 
-template <int V>
-__global__ void __launch_bounds__(kBwdWarps * 32) bwd_prep_kernel(const PrepArgs<V> a) {
+template <typename TG, int V>
+__global__ void __launch_bounds__(kBwdWarps * 32) bwd_prep_kernel(const PrepArgs<TG, V> a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int groups = a.H / a.hg;
   const long long task = static_cast<long long>(blockIdx.x) * kBwdWarps + warp;
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32) bwd_prep_kernel(const PrepArgs
   const float b = a.bias ? __ldg(a.bias + j) : 0.f;
   float tt = 0.f, hs = 0.f;
 #pragma unroll
-  for (int k = 0; k < kMaxVecPerLane; ++k) {
+  for (int k = 0; k < max_vec<V>(); ++k) {
     const int q = lm.sub + lm.lph * k;
     if (q < lm.vph) {
       float dy[V], o[V];
@@ -55,12 +55,14 @@ __global__ void __launch_bounds__(kBwdWarps * 32) bwd_prep_kernel(const PrepArgs
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         // ELU'(x) = 1 (x > 0) else exp(x)  (reference model.py:286-287, torch ELU alpha = 1)
-        const float gg = a.apply_elu ? (o[v] > 0.f ? dy[v] : dy[v] * expf(o[v])) : dy[v];
+        float gg = a.apply_elu ? (o[v] > 0.f ? dy[v] : dy[v] * expf(o[v])) : dy[v];
+        if (sizeof(TG) == 2) gg = bf16_round(gg);  // t / hsum consistent with the stored (rounded) G
         dy[v] = gg;
         tt = fmaf(gg, o[v] - b, tt);
         hs += gg;
       }
-      if (a.G != a.dY || a.apply_elu) RowVec<float, V>::store(a.G + row + q * V, dy);
+      if (static_cast<const void*>(a.G) != static_cast<const void*>(a.dY) || a.apply_elu)
+        RowVec<TG, V>::store(a.G + row + q * V, dy);
     }
   }
   tt = head_sum(tt, lm.lph);
@@ -88,10 +90,10 @@ __device__ __forceinline__ void prefetch_row_l2(const void* ptr, int bytes, int 
   if (lane * 128 < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
-template <int V>
+template <typename T, int V>
 struct SrcArgs {
-  const float* P;       // [N_src, C]   (row stride ldp)
-  const float* G;       // [N_dst, C]
+  const T* P;           // [N_src, C]   (row stride ldp), fp32 or bf16
+  const T* G;           // [N_dst, C]   same storage type as P
   const float* A;       // [H, R, F]
   const float* z;       // [E, H] CSR order
   const float* minv;    // [N_dst, H, 2] forward softmax statistics (max, 1/den)
@@ -113,8 +115,8 @@ struct SrcArgs {
   int pf_dist;  // L2 prefetch distance in edges (0 = off)
 };
 
-template <int V, int KV, bool ASM>
-__global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArgs<V> a) {
+template <typename T, int V, int KV, bool ASM>
+__global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArgs<T, V> a) {
   extern __shared__ __align__(16) float dyn_sm[];
   constexpr int kOwnFloats = KV * 32 * V;  // lane-private slots of one warp's own row
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArg
   const int kstride = lm.lph * V;
   const int lane_off = lm.head_off + lm.sub * V;
   const bool last_ok = lm.sub + lm.lph * (KV - 1) < lm.vph;
-  const int row_bytes = a.hg * a.F * static_cast<int>(sizeof(float));
+  const int row_bytes = a.hg * a.F * static_cast<int>(sizeof(T));
   const int grp_off = g * a.hg * a.F;
 #define RG_VALID(k_) ((k_) < KV - 1 || last_ok)
 
@@ -237,11 +239,11 @@ __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArg
 #define RG_ISSUE(ty_, nd_, ds_, x_)                                                            \
   _Pragma("unroll") for (int v = 0; v < V; ++v) x_[KV - 1][v] = 0.f;                           \
   if (ty_ == IT_OWN || ty_ == IT_EDGE) {                                                       \
-    const float* rowp = (ty_ == IT_OWN)                                                        \
+    const T* rowp = (ty_ == IT_OWN)                                                            \
         ? a.P + static_cast<long long>(n_lo + (nd_)) * a.ldp + lane_off                        \
         : a.G + static_cast<long long>(ds_) * C + lane_off;                                    \
     _Pragma("unroll") for (int k = 0; k < KV; ++k)                                             \
-      if (RG_VALID(k)) RowVec<float, V>::load_stream(rowp + k * kstride, x_[k]);               \
+      if (RG_VALID(k)) RowVec<T, V>::load_stream(rowp + k * kstride, x_[k]);                   \
   }
 
 #define RG_EDGE_ITEM(sl_, rl_, x_, zz_, mi_, tt_)                                              \
@@ -331,9 +333,9 @@ __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArg
 // ------------------------------------------------------------------------------------
 // bwd_rel: chunk partials of dA and dbeta, then ordered reduce
 // ------------------------------------------------------------------------------------
-template <int V>
+template <typename T, int V>
 struct RelArgs {
-  const float* P;        // [N_src, C]
+  const T* P;            // [N_src, C] fp32 or bf16
   const float* dz;       // [E, H] CSR order
   const float* hsum;     // [N_dst, H]
   const int* rel_slot;   // [E] CSR slots in by-relation order
@@ -347,8 +349,8 @@ struct RelArgs {
   long long ldp;
 };
 
-template <int V>
-__global__ void __launch_bounds__(kBwdWarps * 32, 3) bwd_rel_kernel(const RelArgs<V> a) {
+template <typename T, int V>
+__global__ void __launch_bounds__(kBwdWarps * 32, 3) bwd_rel_kernel(const RelArgs<T, V> a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int groups = a.H / a.hg;
   const long long task = static_cast<long long>(blockIdx.x) * kBwdWarps + warp;
@@ -359,9 +361,9 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 3) bwd_rel_kernel(const RelArg
   const int C = a.H * a.F;
   const int lo = a.chunk_lo[c], hi = a.chunk_hi[c];
 
-  float acc[kMaxVecPerLane][V];
+  float acc[max_vec<V>()][V];
 #pragma unroll
-  for (int k = 0; k < kMaxVecPerLane; ++k)
+  for (int k = 0; k < max_vec<V>(); ++k)
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[k][v] = 0.f;
   float bacc = 0.f;
@@ -384,25 +386,25 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 3) bwd_rel_kernel(const RelArg
       const int u1 = two ? tix + 1 : tix;
       const int s0 = __shfl_sync(0xffffffffu, my_slot, tix), s1 = __shfl_sync(0xffffffffu, my_slot, u1);
       const int i0 = __shfl_sync(0xffffffffu, my_src, tix), i1 = __shfl_sync(0xffffffffu, my_src, u1);
-      const float* p0 = a.P + static_cast<long long>(i0) * a.ldp + lm.head_off;
-      const float* p1 = a.P + static_cast<long long>(i1) * a.ldp + lm.head_off;
-      float x0[kMaxVecPerLane][V], x1[kMaxVecPerLane][V];
+      const T* p0 = a.P + static_cast<long long>(i0) * a.ldp + lm.head_off;
+      const T* p1 = a.P + static_cast<long long>(i1) * a.ldp + lm.head_off;
+      float x0[max_vec<V>()][V], x1[max_vec<V>()][V];
 #pragma unroll
-      for (int k = 0; k < kMaxVecPerLane; ++k) {
+      for (int k = 0; k < max_vec<V>(); ++k) {
         const int q = lm.sub + lm.lph * k;
-        if (q < lm.vph) RowVec<float, V>::load_stream(p0 + q * V, x0[k]);
+        if (q < lm.vph) RowVec<T, V>::load_stream(p0 + q * V, x0[k]);
       }
       if (two) {
 #pragma unroll
-        for (int k = 0; k < kMaxVecPerLane; ++k) {
+        for (int k = 0; k < max_vec<V>(); ++k) {
           const int q = lm.sub + lm.lph * k;
-          if (q < lm.vph) RowVec<float, V>::load_stream(p1 + q * V, x1[k]);
+          if (q < lm.vph) RowVec<T, V>::load_stream(p1 + q * V, x1[k]);
         }
       }
       const float dz0 = __ldg(a.dz + static_cast<long long>(s0) * a.H + lm.hh);
       const float dz1 = two ? __ldg(a.dz + static_cast<long long>(s1) * a.H + lm.hh) : 0.f;
 #pragma unroll
-      for (int k = 0; k < kMaxVecPerLane; ++k) {
+      for (int k = 0; k < max_vec<V>(); ++k) {
         const int q = lm.sub + lm.lph * k;
         if (q < lm.vph) {
 #pragma unroll
@@ -415,7 +417,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 3) bwd_rel_kernel(const RelArg
     }
   }
 #pragma unroll
-  for (int k = 0; k < kMaxVecPerLane; ++k) {
+  for (int k = 0; k < max_vec<V>(); ++k) {
     const int q = lm.sub + lm.lph * k;
     if (q < lm.vph) RowVec<float, V>::store(a.partA + static_cast<long long>(c) * C + lm.head_off + q * V, acc[k]);
   }
@@ -459,26 +461,35 @@ static inline bool al16(const void* p) { return reinterpret_cast<uintptr_t>(p) %
 
 using namespace relgat;
 
-extern "C" int relgat_layer_bwd_prep(const float* dY, const float* out, const float* bias, float* G, float* t,
-                                     float* hsum, int N, int H, int F, int apply_elu, void* stream) {
+extern "C" int relgat_layer_bwd_prep(const float* dY, const float* out, const float* bias, void* G, int g_is_bf16,
+                                     float* t, float* hsum, int N, int H, int F, int apply_elu, void* stream) {
   if (!dY || !out || !G || !t || !hsum || N < 0 || H <= 0 || F <= 0) return RG_ERR_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (g_is_bf16) {
+    if (F % 8 != 0) return RG_ERR_SHAPE;
+    if (!al16(dY) || !al16(out) || !al16(G)) return RG_ERR_ALIGN;
+    const int hg = pick_heads_per_warp(H, F, 8);
+    if (!hg) return RG_ERR_SHAPE;
+    PrepArgs<__nv_bfloat16, 8> a{dY, out, bias, static_cast<__nv_bfloat16*>(G), t, hsum, N, H, F, hg, apply_elu};
+    return launch_tasks(bwd_prep_kernel<__nv_bfloat16, 8>, a, static_cast<long long>(N) * (H / hg), s);
+  }
+  float* Gf = static_cast<float*>(G);
   if (F % 4 == 0 && al16(dY) && al16(out) && al16(G)) {
     const int hg = pick_heads_per_warp(H, F, 4);
     if (!hg) return RG_ERR_SHAPE;
-    PrepArgs<4> a{dY, out, bias, G, t, hsum, N, H, F, hg, apply_elu};
-    return launch_tasks(bwd_prep_kernel<4>, a, static_cast<long long>(N) * (H / hg), s);
+    PrepArgs<float, 4> a{dY, out, bias, Gf, t, hsum, N, H, F, hg, apply_elu};
+    return launch_tasks(bwd_prep_kernel<float, 4>, a, static_cast<long long>(N) * (H / hg), s);
   }
   const int hg = pick_heads_per_warp(H, F, 1);
   if (!hg) return RG_ERR_SHAPE;
-  PrepArgs<1> a{dY, out, bias, G, t, hsum, N, H, F, hg, apply_elu};
-  return launch_tasks(bwd_prep_kernel<1>, a, static_cast<long long>(N) * (H / hg), s);
+  PrepArgs<float, 1> a{dY, out, bias, Gf, t, hsum, N, H, F, hg, apply_elu};
+  return launch_tasks(bwd_prep_kernel<float, 1>, a, static_cast<long long>(N) * (H / hg), s);
 }
 
 // dP rows of split sources: ordered sum of their parts.
-template <int V>
+template <typename T, int V>
 __global__ void __launch_bounds__(128)
-bwd_src_merge_kernel(const SrcArgs<V> a, const int* __restrict__ long_node, const int* __restrict__ long_part_ptr,
+bwd_src_merge_kernel(const SrcArgs<T, V> a, const int* __restrict__ long_node, const int* __restrict__ long_part_ptr,
                      int n_long) {
   const int C = a.H * a.F;
   const int li = blockIdx.x;
@@ -501,8 +512,8 @@ bwd_src_merge_kernel(const SrcArgs<V> a, const int* __restrict__ long_node, cons
   }
 }
 
-template <int V, int KV>
-static int launch_src_kv(SrcArgs<V> a, int sm_count, cudaStream_t s) {
+template <typename T, int V, int KV>
+static int launch_src_kv(SrcArgs<T, V> a, int sm_count, cudaStream_t s) {
   const int groups = a.H / a.hg;
   if (sm_count <= 0) sm_count = 148;
   int ctas = sm_count / groups;
@@ -519,33 +530,56 @@ static int launch_src_kv(SrcArgs<V> a, int sm_count, cudaStream_t s) {
     if (a.pf_dist > 30) a.pf_dist = 30;
   }
   if (a.a_in_smem) {
-    cudaError_t e = cudaFuncSetAttribute(bwd_src_kernel<V, KV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(bwd_src_kernel<T, V, KV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(own_bytes + kSmemBudgetA));
     if (e != cudaSuccess) return cuda_status(e);
-    bwd_src_kernel<V, KV, true><<<dim3(ctas, groups), kSrcWarps * 32, own_bytes + a_bytes, s>>>(a);
+    bwd_src_kernel<T, V, KV, true><<<dim3(ctas, groups), kSrcWarps * 32, own_bytes + a_bytes, s>>>(a);
   } else {
-    bwd_src_kernel<V, KV, false><<<dim3(ctas, groups), kSrcWarps * 32, own_bytes, s>>>(a);
+    bwd_src_kernel<T, V, KV, false><<<dim3(ctas, groups), kSrcWarps * 32, own_bytes, s>>>(a);
   }
   return cuda_status(cudaGetLastError());
 }
 
-template <int V>
-static int launch_src(const SrcArgs<V>& a, int sm_count, cudaStream_t s) {
+template <typename T, int V>
+static int launch_src(const SrcArgs<T, V>& a, int sm_count, cudaStream_t s) {
   if (a.n_chunks == 0) return RG_OK;
   const int kv = vectors_per_lane(a.F / V, a.hg);
   switch (kv) {
-    case 1: return launch_src_kv<V, 1>(a, sm_count, s);
-    case 2: return launch_src_kv<V, 2>(a, sm_count, s);
-    case 3: return launch_src_kv<V, 3>(a, sm_count, s);
-    case 4: return launch_src_kv<V, 4>(a, sm_count, s);
-    case 5: return launch_src_kv<V, 5>(a, sm_count, s);
-    case 6: return launch_src_kv<V, 6>(a, sm_count, s);
-    case 7: return launch_src_kv<V, 7>(a, sm_count, s);
-    default: return launch_src_kv<V, 8>(a, sm_count, s);
+    case 1: return launch_src_kv<T, V, 1>(a, sm_count, s);
+    case 2: return launch_src_kv<T, V, 2>(a, sm_count, s);
+    case 3: return launch_src_kv<T, V, 3>(a, sm_count, s);
+    case 4: return launch_src_kv<T, V, 4>(a, sm_count, s);
+    default: break;
   }
+  if constexpr (V != 8) {
+    switch (kv) {
+      case 5: return launch_src_kv<T, V, 5>(a, sm_count, s);
+      case 6: return launch_src_kv<T, V, 6>(a, sm_count, s);
+      case 7: return launch_src_kv<T, V, 7>(a, sm_count, s);
+      default: return launch_src_kv<T, V, 8>(a, sm_count, s);
+    }
+  }
+  return RG_ERR_SHAPE;
 }
 
-extern "C" int relgat_layer_bwd_src(const float* P, long long ldp, const float* G, const float* A,
+template <typename T, int V>
+static int run_src(const void* P, long long ldp, const void* G, const float* A, const float* z, const float* minv,
+                   const float* t, const int* colptr, const int* csc_slot, const int* csc_dst, const int* csc_rel,
+                   const int4* ch, int n_chunks, const int2* pt, const int* long_node, const int* long_part_ptr,
+                   int n_long, float* part_acc, float* dP, void* dP_hi, void* dP_lo, float* dz, int H, int F, int R,
+                   int sm_count, cudaStream_t s) {
+  const int hg = pick_heads_per_warp(H, F, V, R, smem_budget_override("RELGAT_SRC_BUDGET_KB", kSmemBudgetA));
+  if (!hg) return RG_ERR_SHAPE;
+  SrcArgs<T, V> a{static_cast<const T*>(P), static_cast<const T*>(G), A, z, minv, t, colptr, csc_slot, csc_dst,
+                  csc_rel, ch, pt, part_acc, dP, static_cast<__nv_bfloat16*>(dP_hi),
+                  static_cast<__nv_bfloat16*>(dP_lo), dz, n_chunks, H, F, R, hg, ldp, 0, 0};
+  int rc = launch_src(a, sm_count, s);
+  if (rc != RG_OK || n_long == 0) return rc;
+  bwd_src_merge_kernel<T, V><<<n_long, 128, 0, s>>>(a, long_node, long_part_ptr, n_long);
+  return cuda_status(cudaGetLastError());
+}
+
+extern "C" int relgat_layer_bwd_src(const void* P, long long ldp, const void* G, int feat_is_bf16, const float* A,
                                     const float* z, const float* minv, const float* t,
                                     const int* colptr, const int* csc_slot, const int* csc_dst, const int* csc_rel,
                                     const int* chunks, int n_chunks, const int* parts, int n_parts,
@@ -558,34 +592,36 @@ extern "C" int relgat_layer_bwd_src(const float* P, long long ldp, const float* 
   if (n_parts > 0 && (!parts || !long_node || !long_part_ptr || !part_acc)) return RG_ERR_ARG;
   if (n_chunks == 0) return RG_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const bool planes_ok = (!dP_hi || reinterpret_cast<uintptr_t>(dP_hi) % 8 == 0) &&
-                         (!dP_lo || reinterpret_cast<uintptr_t>(dP_lo) % 8 == 0);
+  const bool ok16 = al16(P) && al16(G) && al16(A) && (!dP || al16(dP)) && (!dP_hi || al16(dP_hi)) &&
+                    (!dP_lo || al16(dP_lo)) && (!part_acc || al16(part_acc));
   const int4* ch = reinterpret_cast<const int4*>(chunks);
   const int2* pt = reinterpret_cast<const int2*>(parts);
-  if (F % 4 == 0 && ldp % 4 == 0 && al16(P) && al16(G) && al16(A) && (!dP || al16(dP)) && planes_ok &&
-      (!part_acc || al16(part_acc))) {
-    const int hg = pick_heads_per_warp(H, F, 4, R, smem_budget_override("RELGAT_SRC_BUDGET_KB", kSmemBudgetA));
-    if (!hg) return RG_ERR_SHAPE;
-    SrcArgs<4> a{P, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, ch, pt, part_acc, dP,
-                 static_cast<__nv_bfloat16*>(dP_hi), static_cast<__nv_bfloat16*>(dP_lo), dz,
-                 n_chunks, H, F, R, hg, ldp, 0, 0};
-    int rc = launch_src(a, sm_count, s);
-    if (rc != RG_OK || n_long == 0) return rc;
-    bwd_src_merge_kernel<4><<<n_long, 128, 0, s>>>(a, long_node, long_part_ptr, n_long);
-    return cuda_status(cudaGetLastError());
+  if (feat_is_bf16) {
+    if (F % 8 != 0 || ldp % 8 != 0) return RG_ERR_SHAPE;
+    if (!ok16) return RG_ERR_ALIGN;
+    return run_src<__nv_bfloat16, 8>(P, ldp, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, ch, n_chunks, pt,
+                                     long_node, long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, H, F, R,
+                                     sm_count, s);
   }
-  const int hg = pick_heads_per_warp(H, F, 1, R);
-  if (!hg) return RG_ERR_SHAPE;
-  SrcArgs<1> a{P, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, ch, pt, part_acc, dP,
-               static_cast<__nv_bfloat16*>(dP_hi), static_cast<__nv_bfloat16*>(dP_lo), dz,
-               n_chunks, H, F, R, hg, ldp, 0, 0};
-  int rc = launch_src(a, sm_count, s);
-  if (rc != RG_OK || n_long == 0) return rc;
-  bwd_src_merge_kernel<1><<<n_long, 128, 0, s>>>(a, long_node, long_part_ptr, n_long);
-  return cuda_status(cudaGetLastError());
+  if (F % 4 == 0 && ldp % 4 == 0 && ok16)
+    return run_src<float, 4>(P, ldp, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, ch, n_chunks, pt, long_node,
+                             long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, H, F, R, sm_count, s);
+  return run_src<float, 1>(P, ldp, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, ch, n_chunks, pt, long_node,
+                           long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, H, F, R, sm_count, s);
 }
 
-extern "C" int relgat_layer_bwd_rel(const float* P, long long ldp, const float* dz, const float* hsum,
+template <typename T, int V>
+static int run_rel(const void* P, long long ldp, const float* dz, const float* hsum, const int* rel_slot,
+                   const int* csr_src, const int* csr_dst, const int* chunk_lo, const int* chunk_hi, int n_chunks,
+                   float* partA, float* partB, int H, int F, cudaStream_t s) {
+  const int hg = pick_heads_per_warp(H, F, V);
+  if (!hg) return RG_ERR_SHAPE;
+  RelArgs<T, V> a{static_cast<const T*>(P), dz, hsum, rel_slot, csr_src, csr_dst, chunk_lo, chunk_hi, partA, partB,
+                  n_chunks, H, F, hg, ldp};
+  return launch_tasks(bwd_rel_kernel<T, V>, a, static_cast<long long>(n_chunks) * (H / hg), s);
+}
+
+extern "C" int relgat_layer_bwd_rel(const void* P, int p_is_bf16, long long ldp, const float* dz, const float* hsum,
                                     const int* rel_slot, const int* csr_src, const int* csr_dst,
                                     const int* chunk_lo, const int* chunk_hi, const int* rel_chunk_ptr,
                                     int n_chunks, float* partA, float* partB, float* dA, float* dbeta,
@@ -596,16 +632,17 @@ extern "C" int relgat_layer_bwd_rel(const float* P, long long ldp, const float* 
     return RG_ERR_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int rc;
-  if (F % 4 == 0 && ldp % 4 == 0 && al16(P) && al16(partA)) {
-    const int hg = pick_heads_per_warp(H, F, 4);
-    if (!hg) return RG_ERR_SHAPE;
-    RelArgs<4> a{P, dz, hsum, rel_slot, csr_src, csr_dst, chunk_lo, chunk_hi, partA, partB, n_chunks, H, F, hg, ldp};
-    rc = launch_tasks(bwd_rel_kernel<4>, a, static_cast<long long>(n_chunks) * (H / hg), s);
+  if (p_is_bf16) {
+    if (F % 8 != 0 || ldp % 8 != 0) return RG_ERR_SHAPE;
+    if (!al16(P) || !al16(partA)) return RG_ERR_ALIGN;
+    rc = run_rel<__nv_bfloat16, 8>(P, ldp, dz, hsum, rel_slot, csr_src, csr_dst, chunk_lo, chunk_hi, n_chunks, partA,
+                                   partB, H, F, s);
+  } else if (F % 4 == 0 && ldp % 4 == 0 && al16(P) && al16(partA)) {
+    rc = run_rel<float, 4>(P, ldp, dz, hsum, rel_slot, csr_src, csr_dst, chunk_lo, chunk_hi, n_chunks, partA, partB,
+                           H, F, s);
   } else {
-    const int hg = pick_heads_per_warp(H, F, 1);
-    if (!hg) return RG_ERR_SHAPE;
-    RelArgs<1> a{P, dz, hsum, rel_slot, csr_src, csr_dst, chunk_lo, chunk_hi, partA, partB, n_chunks, H, F, hg, ldp};
-    rc = launch_tasks(bwd_rel_kernel<1>, a, static_cast<long long>(n_chunks) * (H / hg), s);
+    rc = run_rel<float, 1>(P, ldp, dz, hsum, rel_slot, csr_src, csr_dst, chunk_lo, chunk_hi, n_chunks, partA, partB,
+                           H, F, s);
   }
   if (rc != RG_OK) return rc;
   const long long total = static_cast<long long>(R) * H * F;

@@ -304,11 +304,11 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
 // then folded in warp order — a fixed reduction tree, so results are reproducible.
 constexpr int kMergeWarps = 8;
 
-template <int V>
+template <typename T, int V>
 __global__ void __launch_bounds__(kMergeWarps * 32)
-edge_fwd_merge_kernel(const FwdArgs<float, V> a, const int* __restrict__ long_node,
+edge_fwd_merge_kernel(const FwdArgs<T, V> a, const int* __restrict__ long_node,
                       const int* __restrict__ long_part_ptr, int n_long) {
-  __shared__ __align__(16) float sm_acc[kMergeWarps][kMaxVecPerLane * 32 * V];
+  __shared__ __align__(16) float sm_acc[kMergeWarps][max_vec<V>() * 32 * V];
   __shared__ float sm_m[kMergeWarps][32], sm_l[kMergeWarps][32], sm_b[kMergeWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int groups = a.H / a.hg;
@@ -322,9 +322,9 @@ edge_fwd_merge_kernel(const FwdArgs<float, V> a, const int* __restrict__ long_no
 
   // pass 1 (per warp): online merge of this warp's parts
   float M = -INFINITY, L = 0.f, bsum = 0.f;
-  float acc[kMaxVecPerLane][V];
+  float acc[max_vec<V>()][V];
 #pragma unroll
-  for (int k = 0; k < kMaxVecPerLane; ++k)
+  for (int k = 0; k < max_vec<V>(); ++k)
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[k][v] = 0.f;
   for (int p = p_lo + warp; p < p_hi; p += kMergeWarps) {
@@ -334,7 +334,7 @@ edge_fwd_merge_kernel(const FwdArgs<float, V> a, const int* __restrict__ long_no
     L = fmaf(L, s_old, ml.y * s_new);
     bsum += a.part_b[p];
 #pragma unroll
-    for (int k = 0; k < kMaxVecPerLane; ++k) {
+    for (int k = 0; k < max_vec<V>(); ++k) {
       const int q = lm.sub + lm.lph * k;
       if (q < lm.vph) {
         float x[V];
@@ -346,7 +346,7 @@ edge_fwd_merge_kernel(const FwdArgs<float, V> a, const int* __restrict__ long_no
     M = mn;
   }
 #pragma unroll
-  for (int k = 0; k < kMaxVecPerLane; ++k) RowVec<float, V>::store(&sm_acc[warp][(k * 32 + lane) * V], acc[k]);
+  for (int k = 0; k < max_vec<V>(); ++k) RowVec<float, V>::store(&sm_acc[warp][(k * 32 + lane) * V], acc[k]);
   sm_m[warp][lane] = M;
   sm_l[warp][lane] = L;
   if (lane == 0) sm_b[warp] = bsum;
@@ -362,7 +362,7 @@ edge_fwd_merge_kernel(const FwdArgs<float, V> a, const int* __restrict__ long_no
     L = fmaf(L, s_old, lw * s_new);
     bsum += sm_b[w];
 #pragma unroll
-    for (int k = 0; k < kMaxVecPerLane; ++k) {
+    for (int k = 0; k < max_vec<V>(); ++k) {
       float x[V];
       RowVec<float, V>::load_shared(&sm_acc[w][(k * 32 + lane) * V], x);
 #pragma unroll
@@ -372,7 +372,7 @@ edge_fwd_merge_kernel(const FwdArgs<float, V> a, const int* __restrict__ long_no
   }
   const float inv = 1.f / fmaxf(L, 1e-16f);
 #pragma unroll
-  for (int k = 0; k < kMaxVecPerLane; ++k) {
+  for (int k = 0; k < max_vec<V>(); ++k) {
     const int q = lm.sub + lm.lph * k;
     if (q < lm.vph) {
       float o[V];
@@ -447,16 +447,40 @@ static int launch_fwd(const FwdArgs<T, V>& a, int sm_count, cudaStream_t stream)
     case 2: return launch_fwd_kv<T, V, 2>(a, sm_count, stream);
     case 3: return launch_fwd_kv<T, V, 3>(a, sm_count, stream);
     case 4: return launch_fwd_kv<T, V, 4>(a, sm_count, stream);
-    case 5: return launch_fwd_kv<T, V, 5>(a, sm_count, stream);
-    case 6: return launch_fwd_kv<T, V, 6>(a, sm_count, stream);
-    case 7: return launch_fwd_kv<T, V, 7>(a, sm_count, stream);
-    default: return launch_fwd_kv<T, V, 8>(a, sm_count, stream);
+    default: break;
   }
+  if constexpr (V != 8) {
+    switch (kv) {
+      case 5: return launch_fwd_kv<T, V, 5>(a, sm_count, stream);
+      case 6: return launch_fwd_kv<T, V, 6>(a, sm_count, stream);
+      case 7: return launch_fwd_kv<T, V, 7>(a, sm_count, stream);
+      default: return launch_fwd_kv<T, V, 8>(a, sm_count, stream);
+    }
+  }
+  return RG_ERR_SHAPE;
 }
 
 }  // namespace relgat
 
 using namespace relgat;
+
+template <typename T, int V>
+static int run_fwd(const void* P, long long ldp, const float* A, const float* beta, const int* rowptr,
+                   const int* csr_src, const int* csr_rel, const int4* ch, int n_chunks, const int2* pt,
+                   const int* long_node, const int* long_part_ptr, int n_long, float* part_ml, float* part_b,
+                   float* part_acc, float* out, void* act_hi, void* act_lo, int apply_elu, float* alpha, float* z,
+                   float* minv, float* bias_out, int H, int F, int R, int sm_count, cudaStream_t s) {
+  const int hg = pick_heads_per_warp(H, F, V, R, smem_budget_override("RELGAT_FWD_BUDGET_KB", kSmemBudgetA));
+  if (!hg) return RG_ERR_SHAPE;
+  FwdArgs<T, V> a{static_cast<const T*>(P), A, beta, rowptr, csr_src, csr_rel, ch, pt, part_ml, part_b,
+                  part_acc, out, static_cast<__nv_bfloat16*>(act_hi), static_cast<__nv_bfloat16*>(act_lo),
+                  alpha, z, minv, bias_out, n_chunks, H, F, R, hg, ldp, apply_elu, 0, 0};
+  int rc = launch_fwd(a, sm_count, s);
+  if (rc != RG_OK || n_long == 0) return rc;
+  const int tasks = n_long * (H / hg);
+  edge_fwd_merge_kernel<T, V><<<tasks, kMergeWarps * 32, 0, s>>>(a, long_node, long_part_ptr, n_long);
+  return cuda_status(cudaGetLastError());
+}
 
 extern "C" int relgat_layer_fwd(
     const void* P, int p_is_bf16, long long ldp, const float* A, const float* beta,
@@ -470,37 +494,24 @@ extern "C" int relgat_layer_fwd(
   if (!P || !A || !rowptr || n_chunks < 0 || n_parts < 0 || n_long < 0 || H <= 0 || F <= 0 || R <= 0) return RG_ERR_ARG;
   if (n_chunks > 0 && !chunks) return RG_ERR_ARG;
   if (n_parts > 0 && (!parts || !long_node || !long_part_ptr || !part_ml || !part_b || !part_acc)) return RG_ERR_ARG;
-  if (p_is_bf16) return RG_ERR_DTYPE;  // bf16 feature storage: not built in this round
   if (n_chunks == 0) return RG_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const bool vec_ok = (reinterpret_cast<uintptr_t>(P) % 16 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0) &&
-                      (!out || reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
-                      (!act_hi || reinterpret_cast<uintptr_t>(act_hi) % 8 == 0) &&
-                      (!act_lo || reinterpret_cast<uintptr_t>(act_lo) % 8 == 0) &&
-                      (!part_acc || reinterpret_cast<uintptr_t>(part_acc) % 16 == 0);
-  const bool v4 = (F % 4 == 0) && (ldp % 4 == 0) && vec_ok;
+  auto al = [](const void* p, int n) { return !p || reinterpret_cast<uintptr_t>(p) % n == 0; };
+  const bool vec_ok = al(P, 16) && al(A, 16) && al(out, 16) && al(act_hi, 16) && al(act_lo, 16) && al(part_acc, 16);
   const int4* ch = reinterpret_cast<const int4*>(chunks);
   const int2* pt = reinterpret_cast<const int2*>(parts);
-  if (v4) {
-    const int hg = pick_heads_per_warp(H, F, 4, R, smem_budget_override("RELGAT_FWD_BUDGET_KB", kSmemBudgetA));
-    if (!hg) return RG_ERR_SHAPE;
-    FwdArgs<float, 4> a{static_cast<const float*>(P), A, beta, rowptr, csr_src, csr_rel, ch, pt, part_ml, part_b,
-                        part_acc, out, static_cast<__nv_bfloat16*>(act_hi), static_cast<__nv_bfloat16*>(act_lo),
-                        alpha, z, minv, bias_out, n_chunks, H, F, R, hg, ldp, apply_elu, 0, 0};
-    int rc = launch_fwd(a, sm_count, s);
-    if (rc != RG_OK || n_long == 0) return rc;
-    const int tasks = n_long * (H / hg);
-    edge_fwd_merge_kernel<4><<<tasks, kMergeWarps * 32, 0, s>>>(a, long_node, long_part_ptr, n_long);
-    return cuda_status(cudaGetLastError());
+  if (p_is_bf16) {  // bf16 feature storage: 8-element vectors
+    if (F % 8 != 0 || ldp % 8 != 0) return RG_ERR_SHAPE;
+    if (!vec_ok) return RG_ERR_ALIGN;
+    return run_fwd<__nv_bfloat16, 8>(P, ldp, A, beta, rowptr, csr_src, csr_rel, ch, n_chunks, pt, long_node,
+                                     long_part_ptr, n_long, part_ml, part_b, part_acc, out, act_hi, act_lo, apply_elu,
+                                     alpha, z, minv, bias_out, H, F, R, sm_count, s);
   }
-  const int hg = pick_heads_per_warp(H, F, 1, R);
-  if (!hg) return RG_ERR_SHAPE;
-  FwdArgs<float, 1> a{static_cast<const float*>(P), A, beta, rowptr, csr_src, csr_rel, ch, pt, part_ml, part_b,
-                      part_acc, out, static_cast<__nv_bfloat16*>(act_hi), static_cast<__nv_bfloat16*>(act_lo),
-                      alpha, z, minv, bias_out, n_chunks, H, F, R, hg, ldp, apply_elu, 0, 0};
-  int rc = launch_fwd(a, sm_count, s);
-  if (rc != RG_OK || n_long == 0) return rc;
-  const int tasks = n_long * (H / hg);
-  edge_fwd_merge_kernel<1><<<tasks, kMergeWarps * 32, 0, s>>>(a, long_node, long_part_ptr, n_long);
-  return cuda_status(cudaGetLastError());
+  if ((F % 4 == 0) && (ldp % 4 == 0) && vec_ok)
+    return run_fwd<float, 4>(P, ldp, A, beta, rowptr, csr_src, csr_rel, ch, n_chunks, pt, long_node, long_part_ptr,
+                             n_long, part_ml, part_b, part_acc, out, act_hi, act_lo, apply_elu, alpha, z, minv,
+                             bias_out, H, F, R, sm_count, s);
+  return run_fwd<float, 1>(P, ldp, A, beta, rowptr, csr_src, csr_rel, ch, n_chunks, pt, long_node, long_part_ptr,
+                           n_long, part_ml, part_b, part_acc, out, act_hi, act_lo, apply_elu, alpha, z, minv,
+                           bias_out, H, F, R, sm_count, s);
 }

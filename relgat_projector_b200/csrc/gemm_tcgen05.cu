@@ -34,7 +34,8 @@ struct GemmParams {
   int stages;
   int splits_k;          // split-K factor (partials written at d + s * d_split_stride)
   int kb_per_split;      // k-blocks per split
-  float* d;
+  float* d;              // fp32 output (or split-K partials)
+  __nv_bfloat16* d_bf16; // bf16 output instead of d (no split-K)
   long long ldd;
   long long d_split_stride;
   int a_tile_bytes, b_tile_bytes;   // per plane
@@ -251,7 +252,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
       mbar_wait(&tmem_full[acc], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int row = m_tile * kBM + ew * 32 + lane;
-      float* drow = p.d + static_cast<long long>(ks) * p.d_split_stride + static_cast<long long>(row) * p.ldd;
+      float* drow = p.d ? p.d + static_cast<long long>(ks) * p.d_split_stride + static_cast<long long>(row) * p.ldd
+                        : nullptr;
+      __nv_bfloat16* hrow = p.d_bf16 ? p.d_bf16 + static_cast<long long>(row) * p.ldd : nullptr;
       const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(ew * 32) << 16);
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t r[32];
@@ -259,7 +262,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
         if (width == 32) tmem_ld32(taddr + c0, r); else tmem_ld16(taddr + c0, r);
         const int col = n_tile * p.BN + c0;
         if (row < p.M) {
-          if (col + width <= p.N && (p.ldd & 3) == 0) {
+          if (hrow) {  // bf16 output: 8 elements per 128-bit store
+            if (col + width <= p.N && (p.ldd & 7) == 0) {
+#pragma unroll
+              for (int v = 0; v < 4; ++v) {
+                if (v * 8 < width) {
+                  uint4 o;
+                  o.x = empty_k ? 0u : pack_bf16x2(__uint_as_float(r[8 * v]), __uint_as_float(r[8 * v + 1]));
+                  o.y = empty_k ? 0u : pack_bf16x2(__uint_as_float(r[8 * v + 2]), __uint_as_float(r[8 * v + 3]));
+                  o.z = empty_k ? 0u : pack_bf16x2(__uint_as_float(r[8 * v + 4]), __uint_as_float(r[8 * v + 5]));
+                  o.w = empty_k ? 0u : pack_bf16x2(__uint_as_float(r[8 * v + 6]), __uint_as_float(r[8 * v + 7]));
+                  *reinterpret_cast<uint4*>(hrow + col + 8 * v) = o;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int v = 0; v < 32; ++v)
+                if (v < width && col + v < p.N) hrow[col + v] = __float2bfloat16_rn(empty_k ? 0.f : __uint_as_float(r[v]));
+            }
+          } else if (col + width <= p.N && (p.ldd & 3) == 0) {
 #pragma unroll
             for (int v = 0; v < 8; ++v) {
               if (v * 4 < width) {
@@ -381,9 +402,11 @@ extern "C" long long relgat_gemm_workspace_bytes(int M, int N, int K, int a_mn, 
 //   a_lo / b_lo: residual planes of the fp32 split (both or neither); nullptr = plain bf16 GEMM
 extern "C" int relgat_gemm_bf16(const void* a_hi, const void* a_lo, long long lda, int a_mn,
                                 const void* b_hi, const void* b_lo, long long ldb, int b_mn,
-                                float* d, long long ldd, int M, int N, int K, int splits_k,
+                                void* d_out, int d_is_bf16, long long ldd, int M, int N, int K, int splits_k,
                                 void* workspace, long long workspace_bytes, int sm_count, void* stream) {
-  if (!a_hi || !b_hi || !d || M <= 0 || N <= 0 || K <= 0 || splits_k < 1) return RG_ERR_ARG;
+  if (!a_hi || !b_hi || !d_out || M <= 0 || N <= 0 || K <= 0 || splits_k < 1) return RG_ERR_ARG;
+  if (d_is_bf16 && splits_k > 1) return RG_ERR_ARG;  // split-K partials are fp32
+  float* d = d_is_bf16 ? nullptr : static_cast<float*>(d_out);
   if ((a_lo == nullptr) != (b_lo == nullptr)) return RG_ERR_ARG;
   if (lda % 8 || ldb % 8) return RG_ERR_ALIGN;  // TMA: 16-byte global strides
   if (reinterpret_cast<uintptr_t>(a_hi) % 16 || reinterpret_cast<uintptr_t>(b_hi) % 16 ||
@@ -415,7 +438,7 @@ extern "C" int relgat_gemm_bf16(const void* a_hi, const void* a_lo, long long ld
     p.ldd = N;
     p.d_split_stride = static_cast<long long>(M) * N;
   } else {
-    p.d = d; p.ldd = ldd; p.d_split_stride = 0;
+    p.d = d; p.d_bf16 = d_is_bf16 ? static_cast<__nv_bfloat16*>(d_out) : nullptr; p.ldd = ldd; p.d_split_stride = 0;
   }
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;

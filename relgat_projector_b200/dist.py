@@ -264,7 +264,7 @@ class PartitionedStackFunction(torch.autograd.Function):
         dY, owned, dX = grad_out.contiguous(), False, None
         for l in reversed(range(L)):
             s = ctx.saved[l]
-            G, t, hsum = ops.edge_bwd_prep(dY, s["out"], s["bias"], H, F, apply_elu=(l < L - 1), inplace=owned)
+            G, t, hsum = ops.edge_bwd_prep(dY, s["out"], s["bias"], H, F, apply_elu=(l < L - 1), inplace=owned)  # fp32 storage
             dP_part, _, dz = ops.edge_bwd_src(s["P"], G, s["A"], s["z"], s["minv"], t, g, H, F,
                                               want_fp32=True, want_planes=False)
             dA, dbeta = ops.edge_bwd_rel(s["P"], dz, hsum, g, H, F, want_dbeta=s["has_beta"])

@@ -61,7 +61,9 @@ class RelGATStackFunction(torch.autograd.Function):
             Wp = ops.split_bf16(W.detach(), with_lo)
             # K-major copy of Wᵀ for dX = dP·W (3 MB transpose; the K-major B path is ~12% faster than MN-major)
             WTp = ops.split_bf16(W.detach().t().contiguous(), with_lo) if (l > 0 or x0.requires_grad) else None
-            P = ops.gemm(planes, False, Wp, False, N, C, d_in)
+            # "bf16": projected features are stored in bf16 (halves every gather of the edge kernels)
+            P = ops.gemm(planes, False, Wp, False, N, C, d_in,
+                         out_dtype=torch.float32 if with_lo else torch.bfloat16)
             last = l == L - 1
             out, act, _, z, minv, bias = ops.edge_fwd(P, A.detach(), None if beta is None else beta.detach(), graph,
                                                       H, F, want_act=not last, apply_elu=True, act_lo=with_lo)
@@ -86,7 +88,8 @@ class RelGATStackFunction(torch.autograd.Function):
         dX = None
         for l in reversed(range(L)):
             s = ctx.saved[l]
-            G, t, hsum = ops.edge_bwd_prep(dY, s["out"], s["bias"], H, F, apply_elu=(l < L - 1), inplace=owned)
+            G, t, hsum = ops.edge_bwd_prep(dY, s["out"], s["bias"], H, F, apply_elu=(l < L - 1), inplace=owned,
+                                           g_bf16=not with_lo)
             _, dPp, dz = ops.edge_bwd_src(s["P"], G, s["A"], s["z"], s["minv"], t, g, H, F,
                                           want_fp32=False, want_planes=True, planes_lo=with_lo)
             main = torch.cuda.current_stream(dY.device)

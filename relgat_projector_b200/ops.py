@@ -36,6 +36,14 @@ def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
     return t.contiguous()
 
 
+def _feat(t: torch.Tensor, name: str) -> torch.Tensor:
+    """Feature matrices are fp32 or bf16 (bf16 feature-storage mode)."""
+    _lib.require_cuda(t)
+    if t.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError(f"{name} must be float32 or bfloat16, got {t.dtype}")
+    return t.contiguous()
+
+
 def sm_count(device) -> int:
     return torch.cuda.get_device_properties(device).multi_processor_count
 
@@ -67,8 +75,8 @@ def _tma_ready(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 
 
 def gemm(a: Planes, a_mn: bool, b: Planes, b_mn: bool, M: int, N: int, K: int,
-         splits_k: int = 1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """D[M, N] fp32 = A · Bᵀ on tcgen05.  Operands are 2-D bf16 planes:
+         splits_k: int = 1, out: Optional[torch.Tensor] = None, out_dtype=torch.float32) -> torch.Tensor:
+    """D[M, N] = A · Bᵀ on tcgen05 (fp32 accumulation; D fp32 or bf16).  Operands are 2-D bf16 planes:
     a_mn False: A stored [M, K]; True: stored [K, M].  Same for B with N."""
     a_hi, a_lo = a
     b_hi, b_lo = b
@@ -85,7 +93,9 @@ def gemm(a: Planes, a_mn: bool, b: Planes, b_mn: bool, M: int, N: int, K: int,
     a_hi, a_lo, b_hi, b_lo = _tma_ready(a_hi), _tma_ready(a_lo), _tma_ready(b_hi), _tma_ready(b_lo)
     dev = a_hi.device
     if out is None:
-        out = torch.empty((M, N), dtype=torch.float32, device=dev)
+        out = torch.empty((M, N), dtype=out_dtype, device=dev)
+    if out.dtype not in (torch.float32, torch.bfloat16) or out.stride(1) != 1:
+        raise TypeError("gemm output must be fp32 or bf16 with unit inner stride")
     lib = _lib.load()
     ws = None
     ws_bytes = 0
@@ -96,18 +106,31 @@ def gemm(a: Planes, a_mn: bool, b: Planes, b_mn: bool, M: int, N: int, K: int,
         rc = lib.relgat_gemm_bf16(
             _lib.ptr(a_hi), _lib.ptr(a_lo), a_hi.stride(0), int(a_mn),
             _lib.ptr(b_hi), _lib.ptr(b_lo), b_hi.stride(0), int(b_mn),
-            _lib.ptr(out), out.stride(0), M, N, K, splits_k, _lib.ptr(ws), ws_bytes, sm_count(dev), _stream(out))
+            _lib.ptr(out), int(out.dtype == torch.bfloat16), out.stride(0), M, N, K, splits_k, _lib.ptr(ws), ws_bytes,
+            sm_count(dev), _stream(out))
     _lib.check(rc, "relgat_gemm_bf16")
     _count(2 if splits_k > 1 else 1)
     return out
 
 
 def pick_splits_k(M: int, N: int, K: int, device) -> int:
-    """Split-K factor that fills the SMs when the output has few tiles (the dW GEMM)."""
+    """Split-K factor for GEMMs with few output tiles and a long reduction (the dW GEMMs): the one
+    (<= 16) that fills the persistent grid's waves best, smaller factors winning ties."""
     bn = (N + 15) // 16 * 16 if N <= 256 else next((b for b in range(256, 127, -16) if N % b == 0), 256)
     tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
     kb = (K + 63) // 64
-    return max(1, min(kb, sm_count(device) // max(tiles, 1)))
+    sms = sm_count(device)
+    if tiles >= 4 * sms or kb < 16:
+        return 1
+    best, best_eff = 1, 0.0
+    for sk in range(1, 17):
+        if kb // sk < 8:
+            break
+        units = tiles * sk
+        eff = units / (-(-units // sms) * sms)
+        if eff > best_eff + 0.02:
+            best, best_eff = sk, eff
+    return best
 
 
 # ------------------------------------------------------------------------------------------
@@ -118,7 +141,7 @@ def edge_fwd(P: torch.Tensor, A: torch.Tensor, beta: Optional[torch.Tensor], g: 
              want_alpha: bool = False):
     """Returns (out [N, H*F] fp32 or None, act planes or None, alpha [E,H] or None, z [E,H],
     minv [N,H,2], bias [N])."""
-    P = _f32c(P, "P")
+    P = _feat(P, "P")
     A = _f32c(A, "A")
     if beta is not None:
         beta = _f32c(beta, "beta")
@@ -141,7 +164,7 @@ def edge_fwd(P: torch.Tensor, A: torch.Tensor, beta: Optional[torch.Tensor], g: 
     part_acc = torch.empty((ck.n_parts, C), dtype=torch.float32, device=dev) if ck.n_parts else None
     with torch.cuda.device(dev):
         rc = _lib.load().relgat_layer_fwd(
-            _lib.ptr(P), 0, P.stride(0), _lib.ptr(A), _lib.ptr(beta),
+            _lib.ptr(P), int(P.dtype == torch.bfloat16), P.stride(0), _lib.ptr(A), _lib.ptr(beta),
             _lib.ptr(g.rowptr), _lib.ptr(g.csr_src), _lib.ptr(g.csr_rel),
             _lib.ptr(ck.chunks), ck.n_chunks, _lib.ptr(ck.parts), ck.n_parts,
             _lib.ptr(ck.long_node), _lib.ptr(ck.long_part_ptr), ck.n_long,
@@ -154,18 +177,21 @@ def edge_fwd(P: torch.Tensor, A: torch.Tensor, beta: Optional[torch.Tensor], g: 
 
 
 def edge_bwd_prep(dY: torch.Tensor, out: torch.Tensor, bias: torch.Tensor, H: int, F: int,
-                  apply_elu: bool, inplace: bool = False):
-    """Returns (G [N,C], t [N,H], hsum [N,H])."""
+                  apply_elu: bool, inplace: bool = False, g_bf16: bool = False):
+    """Returns (G [N,C] fp32 or bf16, t [N,H], hsum [N,H])."""
     dY = _f32c(dY, "dY")
     out = _f32c(out, "out")
     N = out.size(0)
-    # without an activation G == dY: nothing to write, alias it (saves a full [N, C] copy)
-    G = dY if (inplace or not apply_elu) else torch.empty_like(dY)
+    if g_bf16:
+        G = torch.empty(dY.shape, dtype=torch.bfloat16, device=dY.device)
+    else:
+        # without an activation G == dY: nothing to write, alias it (saves a full [N, C] copy)
+        G = dY if (inplace or not apply_elu) else torch.empty_like(dY)
     t = torch.empty((N, H), dtype=torch.float32, device=dY.device)
     hsum = torch.empty((N, H), dtype=torch.float32, device=dY.device)
     with torch.cuda.device(dY.device):
-        rc = _lib.load().relgat_layer_bwd_prep(_lib.ptr(dY), _lib.ptr(out), _lib.ptr(bias), _lib.ptr(G), _lib.ptr(t),
-                                               _lib.ptr(hsum), N, H, F, int(apply_elu), _stream(dY))
+        rc = _lib.load().relgat_layer_bwd_prep(_lib.ptr(dY), _lib.ptr(out), _lib.ptr(bias), _lib.ptr(G), int(g_bf16),
+                                               _lib.ptr(t), _lib.ptr(hsum), N, H, F, int(apply_elu), _stream(dY))
     _lib.check(rc, "relgat_layer_bwd_prep")
     _count(1)
     return G, t, hsum
@@ -174,8 +200,10 @@ def edge_bwd_prep(dY: torch.Tensor, out: torch.Tensor, bias: torch.Tensor, H: in
 def edge_bwd_src(P, G, A, z, minv, t, g: GraphIndex, H: int, F: int, want_fp32: bool = True,
                  want_planes: bool = False, planes_lo: bool = True):
     """Returns (dP fp32 or None, dP planes or None, dz [E,H])."""
-    P = _f32c(P, "P")
-    G = _f32c(G, "G")
+    P = _feat(P, "P")
+    G = _feat(G, "G")
+    if P.dtype != G.dtype:
+        raise TypeError("P and G must share one storage type (both fp32 or both bf16)")
     A = _f32c(A, "A")
     dev = P.device
     n_src, C = P.size(0), H * F
@@ -189,8 +217,8 @@ def edge_bwd_src(P, G, A, z, minv, t, g: GraphIndex, H: int, F: int, want_fp32: 
     part_acc = torch.empty((ck.n_parts, C), dtype=torch.float32, device=dev) if ck.n_parts else None
     with torch.cuda.device(dev):
         rc = _lib.load().relgat_layer_bwd_src(
-            _lib.ptr(P), P.stride(0), _lib.ptr(G), _lib.ptr(A), _lib.ptr(z), _lib.ptr(minv), _lib.ptr(t),
-            _lib.ptr(g.colptr), _lib.ptr(g.csc_slot), _lib.ptr(g.csc_dst), _lib.ptr(g.csc_rel),
+            _lib.ptr(P), P.stride(0), _lib.ptr(G), int(P.dtype == torch.bfloat16), _lib.ptr(A), _lib.ptr(z),
+            _lib.ptr(minv), _lib.ptr(t), _lib.ptr(g.colptr), _lib.ptr(g.csc_slot), _lib.ptr(g.csc_dst), _lib.ptr(g.csc_rel),
             _lib.ptr(ck.chunks), ck.n_chunks, _lib.ptr(ck.parts), ck.n_parts,
             _lib.ptr(ck.long_node), _lib.ptr(ck.long_part_ptr), ck.n_long, _lib.ptr(part_acc),
             _lib.ptr(dP), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dz), H, F, g.R, sm_count(dev), _stream(P))
@@ -201,7 +229,7 @@ def edge_bwd_src(P, G, A, z, minv, t, g: GraphIndex, H: int, F: int, want_fp32: 
 
 def edge_bwd_rel(P, dz, hsum, g: GraphIndex, H: int, F: int, want_dbeta: bool = True):
     """Returns (dA [H,R,F], dbeta [R] or None)."""
-    P = _f32c(P, "P")
+    P = _feat(P, "P")
     dev = P.device
     C = H * F
     partA = torch.empty((max(g.n_chunks, 1), C), dtype=torch.float32, device=dev)
@@ -210,7 +238,8 @@ def edge_bwd_rel(P, dz, hsum, g: GraphIndex, H: int, F: int, want_dbeta: bool = 
     dbeta = torch.empty((g.R,), dtype=torch.float32, device=dev) if want_dbeta else None
     with torch.cuda.device(dev):
         rc = _lib.load().relgat_layer_bwd_rel(
-            _lib.ptr(P), P.stride(0), _lib.ptr(dz), _lib.ptr(hsum), _lib.ptr(g.rel_slot), _lib.ptr(g.csr_src),
+            _lib.ptr(P), int(P.dtype == torch.bfloat16), P.stride(0), _lib.ptr(dz), _lib.ptr(hsum), _lib.ptr(g.rel_slot),
+            _lib.ptr(g.csr_src),
             _lib.ptr(g.csr_dst), _lib.ptr(g.chunk_lo), _lib.ptr(g.chunk_hi), _lib.ptr(g.rel_chunk_ptr),
             g.n_chunks, _lib.ptr(partA), _lib.ptr(partB), _lib.ptr(dA), _lib.ptr(dbeta), H, F, g.R, _stream(P))
     _lib.check(rc, "relgat_layer_bwd_rel")

@@ -142,16 +142,28 @@ def test_training_mode_dropout_path_runs_and_eval_is_deterministic(dev):
             torch.zeros(3, dtype=torch.long, device=dev))
 
 
-def test_bf16_operand_mode_stated_tolerance(dev):
-    """precision='bf16': single-pass bf16 tensor-core operands, fp32 accumulate/storage.
-    Stated tolerance: 2e-2 relative on embeddings and loss-level quantities."""
-    c = Case("f200_fp32")
+BF16_TOL = 2e-2       # stated tolerance of the bf16 mode: embeddings, scores, loss
+BF16_GRAD_TOL = 6e-2  # ... and parameter gradients (relative to the largest entry of each tensor)
+
+
+@pytest.mark.parametrize("name", ["f200_fp32", "adversarial_fp32"])
+def test_bf16_storage_mode_stated_tolerance(dev, name):
+    """precision='bf16': P / G / dP rows stored in bf16, single-pass bf16 tensor-core operands, fp32
+    accumulation everywhere.  Stated tolerance vs the reference's fp32 results: 2e-2 relative on
+    embeddings / scores / loss, 6e-2 on gradients."""
+    c = Case(name)
     m = _load_model(c, dev, precision="bf16")
     with torch.no_grad():
         xf = m.single_gat_step()
-    assert rel_err(xf.cpu().numpy(), c.z["x_final"]) < 2e-2
+    assert rel_err(xf.cpu().numpy(), c.z["x_final"]) < BF16_TOL
     loss, pos, neg = _step(m, c, dev)
-    assert abs(float(loss.detach()) - float(c.z["loss"])) < 2e-2
+    assert rel_err(pos.detach().cpu().numpy(), c.z["pos"]) < BF16_TOL
+    assert abs(float(loss.detach()) - float(c.z["loss"])) < BF16_TOL * max(1.0, abs(float(c.z["loss"])))
+    loss.backward()
+    for pname, p in m.named_parameters():
+        ref = c.z["grad/" + pname]
+        if ref.size and np.abs(ref).max() > 1e-6:
+            assert rel_err(p.grad.cpu().numpy(), ref) < BF16_GRAD_TOL, pname
 
 
 def test_partitioned_destination_ranges_reproduce_whole_graph(dev):
