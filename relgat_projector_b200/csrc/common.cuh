@@ -139,21 +139,40 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+// (a, b) -> packed bf16x2 with one cvt; also returns the rounded values widened back to fp32
+__device__ __forceinline__ uint32_t cvt_bf16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));  // low half = a, high half = b
+  return r;
+}
+__device__ __forceinline__ float bf16_lo_as_f32(uint32_t p) { return __uint_as_float(p << 16); }
+__device__ __forceinline__ float bf16_hi_as_f32(uint32_t p) { return __uint_as_float(p & 0xffff0000u); }
+
+// Lean split store: per PAIR of elements one cvt for hi, two integer ops to widen it back, two
+// subtractions and one cvt for lo (ncu: the scalar conversion helpers made the per-destination
+// epilogue 35% of the forward kernel's instructions).
 template <int V>
 __device__ __forceinline__ void store_split_bf16(__nv_bfloat16* hi, __nv_bfloat16* lo, const float (&v)[V]) {
-  if constexpr (V == 8) {
-    float h[8];
+  if constexpr (V % 2 == 0) {
+    uint32_t h[V / 2], l[V / 2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) h[i] = bf16_round(v[i]);
-    *reinterpret_cast<uint4*>(hi) = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]),
-                                               pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
-    if (lo)
-      *reinterpret_cast<uint4*>(lo) = make_uint4(pack_bf16x2(v[0] - h[0], v[1] - h[1]), pack_bf16x2(v[2] - h[2], v[3] - h[3]),
-                                                 pack_bf16x2(v[4] - h[4], v[5] - h[5]), pack_bf16x2(v[6] - h[6], v[7] - h[7]));
-  } else if constexpr (V == 4) {
-    const float h0 = bf16_round(v[0]), h1 = bf16_round(v[1]), h2 = bf16_round(v[2]), h3 = bf16_round(v[3]);
-    *reinterpret_cast<uint2*>(hi) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
-    if (lo) *reinterpret_cast<uint2*>(lo) = make_uint2(pack_bf16x2(v[0] - h0, v[1] - h1), pack_bf16x2(v[2] - h2, v[3] - h3));
+    for (int i = 0; i < V / 2; ++i) {
+      h[i] = cvt_bf16x2(v[2 * i], v[2 * i + 1]);
+      l[i] = cvt_bf16x2(v[2 * i] - bf16_lo_as_f32(h[i]), v[2 * i + 1] - bf16_hi_as_f32(h[i]));
+    }
+    if constexpr (V == 8) {
+      *reinterpret_cast<uint4*>(hi) = make_uint4(h[0], h[1], h[2], h[3]);
+      if (lo) *reinterpret_cast<uint4*>(lo) = make_uint4(l[0], l[1], l[2], l[3]);
+    } else if constexpr (V == 4) {
+      *reinterpret_cast<uint2*>(hi) = make_uint2(h[0], h[1]);
+      if (lo) *reinterpret_cast<uint2*>(lo) = make_uint2(l[0], l[1]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < V / 2; ++i) {
+        reinterpret_cast<uint32_t*>(hi)[i] = h[i];
+        if (lo) reinterpret_cast<uint32_t*>(lo)[i] = l[i];
+      }
+    }
   } else {
 #pragma unroll
     for (int i = 0; i < V; ++i) {
@@ -162,6 +181,13 @@ __device__ __forceinline__ void store_split_bf16(__nv_bfloat16* hi, __nv_bfloat1
       if (lo) lo[i] = __float2bfloat16_rn(v[i] - h);
     }
   }
+}
+
+// exp(x) for x <= 0-ish activations: one multiply + MUFU.EX2 (flush-to-zero, no range fix-up)
+__device__ __forceinline__ float fast_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
 }
 
 // ---- lane mapping ------------------------------------------------------------------

@@ -249,11 +249,14 @@ __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArg
 #define RG_EDGE_ITEM(sl_, rl_, x_, zz_, mi_, tt_)                                              \
   {                                                                                            \
     float dd = 0.f;                                                                            \
+    float sd[V];  /* V independent partial sums: short FMA dependency chains */                 \
+    _Pragma("unroll") for (int v = 0; v < V; ++v) sd[v] = 0.f;                                 \
     _Pragma("unroll") for (int k = 0; k < KV; ++k) {                                           \
       float pv[V];                                                                             \
       RowVec<float, V>::load_shared(p_own + (k * 32 + lane) * V, pv);                          \
-      _Pragma("unroll") for (int v = 0; v < V; ++v) dd = fmaf(x_[k][v], pv[v], dd);            \
+      _Pragma("unroll") for (int v = 0; v < V; ++v) sd[v] = fmaf(x_[k][v], pv[v], sd[v]);      \
     }                                                                                          \
+    _Pragma("unroll") for (int v = 0; v < V; ++v) dd += sd[v];                                 \
     dd = head_sum(dd, lm.lph); /* dalpha */                                                    \
     const float ee = zz_ > 0.f ? zz_ : kLeakySlope * zz_;                                      \
     const float al = __expf(ee - mi_.x) * mi_.y;                                               \

@@ -19,9 +19,12 @@
 
 namespace relgat {
 
-constexpr int kFwdWarps = 12;  // one persistent CTA per SM: 12 warps x <=170 registers
+constexpr int kFwdWarps = 12;  // paired variant: 12 warps x <=170 registers, two rows in flight per warp
+constexpr int kFwdWarpsSingle = 16;  // single-row variant: 16 warps x <=128 registers (latency hidden by the L2 prefetch)
 
-constexpr int kPrefetchDist = 2;  // default number of edges ahead whose source rows are pulled into L2
+constexpr int kPrefetchDist = 2;
+constexpr int kPrefetchDistSingle = 3;
+constexpr int kFwdRowsDefault = 2;  // default number of edges ahead whose source rows are pulled into L2
 
 // warp-cooperative L2 prefetch of one row slice [ptr, ptr + bytes): lane l touches line l
 __device__ __forceinline__ void prefetch_row_l2_fwd(const void* ptr, int bytes, int lane) {
@@ -59,14 +62,15 @@ struct FwdArgs {
 // ELU(x) = x (x > 0) else exp(x) - 1.  __expf keeps the absolute error at ~1e-7 (the inputs are
 // O(1) activations and the parity budget is 1e-4 of the tensor's max); expm1f costs ~20 instructions
 // per element and made the epilogue the largest instruction consumer of the kernel (ncu, round 1).
-__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : fast_exp(x) - 1.f; }  // NaN stays NaN
 
 // grid = (CTAs per head-group, head-groups); every CTA is persistent and owns one head-group, so
 // it stages only that group's attention vectors (ncu on the first version showed the per-edge
 // A-row reads missing L1 ~40-70% of the time and doubling the L2->SM traffic).
-template <typename T, int V, int KV, bool ASM>
-__global__ void __launch_bounds__(kFwdWarps * 32, 1)
+template <typename T, int V, int KV, bool ASM, int NP>
+__global__ void __launch_bounds__((NP == 2 ? kFwdWarps : kFwdWarpsSingle) * 32, 1)
 edge_fwd_kernel(const FwdArgs<T, V> a) {
+  constexpr int kWarps = NP == 2 ? kFwdWarps : kFwdWarpsSingle;
   extern __shared__ __align__(16) float a_sm[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -98,7 +102,7 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
     a_base = a.A + static_cast<long long>(lm.hh) * a.R * a.F + lm.sub * V;
   }
 
-  for (int c = blockIdx.x * kFwdWarps + warp; c < a.n_chunks; c += gridDim.x * kFwdWarps) {
+  for (int c = blockIdx.x * kWarps + warp; c < a.n_chunks; c += gridDim.x * kWarps) {
     const int4 ch = __ldg(a.chunks + c);
     const int n_lo = ch.x;
     const int nn = ch.y;     // 1..64 destinations
@@ -165,13 +169,13 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
           if (base + pf < e_hi) prefetch_row_l2_fwd(a.P + static_cast<long long>(ip) * a.ldp + g * a.hg * a.F, row_bytes, lane);
         }
       }
-      const int npair = min(2, min(e_hi - e, base + 32 - e));  // 0 only when the chunk is exhausted
+      const int npair = min(NP, min(e_hi - e, base + 32 - e));  // 0 only when the chunk is exhausted
       float x0[KV][V], x1[KV][V];
       float d0 = 0.f, d1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll
       for (int v = 0; v < V; ++v) { x0[KV - 1][v] = 0.f; x1[KV - 1][v] = 0.f; }  // the only guarded vector
       if (npair > 0) {
-        const bool two = npair == 2;
+        const bool two = NP == 2 && npair == 2;
         const int t = e - base;
         const int i0 = __shfl_sync(0xffffffffu, my_src, t);
         const int r0 = __shfl_sync(0xffffffffu, my_rel, t);
@@ -182,7 +186,7 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
         const T* p0 = a.P + static_cast<long long>(i0) * a.ldp + lane_off;
         const T* p1 = a.P + static_cast<long long>(i1) * a.ldp + lane_off;
 #pragma unroll
-        for (int pf = 0; pf < 2; ++pf) {  // rolling L2 prefetch, kPrefetchDist edges ahead (same window)
+        for (int pf = 0; pf < NP; ++pf) {  // rolling L2 prefetch, pf_dist edges ahead (same window)
           const int tp = t + a.pf_dist + pf;
           const int ip = __shfl_sync(0xffffffffu, my_src, tp & 31);
           if (a.pf_dist > 0 && tp < 32 && base + tp < e_hi)
@@ -199,20 +203,26 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
         }
         const float* a0 = a_base + r0 * a.F;
         const float* a1 = a_base + r1 * a.F;
+        // V independent partial sums per edge: the logit's FMA chain is KV long instead of KV*V
+        float s0[V], s1[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) { s0[v] = 0.f; s1[v] = 0.f; }
 #pragma unroll
         for (int k = 0; k < KV; ++k) {
           if (RG_VALID(k)) {
             float av[V];
             if (ASM) RowVec<float, V>::load_shared(a0 + k * kstride, av); else RowVec<float, V>::load_cached(a0 + k * kstride, av);
 #pragma unroll
-            for (int v = 0; v < V; ++v) d0 = fmaf(x0[k][v], av[v], d0);
+            for (int v = 0; v < V; ++v) s0[v] = fmaf(x0[k][v], av[v], s0[v]);
             if (two) {
               if (ASM) RowVec<float, V>::load_shared(a1 + k * kstride, av); else RowVec<float, V>::load_cached(a1 + k * kstride, av);
 #pragma unroll
-              for (int v = 0; v < V; ++v) d1 = fmaf(x1[k][v], av[v], d1);
+              for (int v = 0; v < V; ++v) s1[v] = fmaf(x1[k][v], av[v], s1[v]);
             }
           }
         }
+#pragma unroll
+        for (int v = 0; v < V; ++v) { d0 += s0[v]; d1 += s1[v]; }
         d0 = head_sum(d0, lm.lph);
         d1 = head_sum(d1, lm.lph);
       }
@@ -237,6 +247,7 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
           const int j = n_lo + kn;
           const bool empty = (seg_end == seg_start);
           const float inv = empty ? 0.f : 1.f / fmaxf(l, 1e-16f);  // reference layer.py:291 clamp
+          if (empty) bsum = 0.f;  // acc is 0 too, so the row below comes out exactly 0
           const long long row_off = static_cast<long long>(j) * C + lane_off;
 #pragma unroll
           for (int k = 0; k < KV; ++k) {
@@ -244,7 +255,7 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
               float o[V];
 #pragma unroll
               for (int v = 0; v < V; ++v) {
-                o[v] = empty ? 0.f : fmaf(acc[k][v], inv, bsum);  // bias on every head/channel, :313-318
+                o[v] = fmaf(acc[k][v], inv, bsum);  // bias on every head/channel, :313-318
                 acc[k][v] = 0.f;
               }
               const long long off = row_off + k * kstride;
@@ -258,7 +269,7 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
               }
             }
           }
-          if (g == 0 && lane == 0 && a.bias_out) a.bias_out[j] = empty ? 0.f : bsum;
+          if (g == 0 && lane == 0 && a.bias_out) a.bias_out[j] = bsum;
           if (lm.sub == 0 && a.minv) {
             *reinterpret_cast<float2*>(a.minv + (static_cast<long long>(j) * a.H + lm.hh) * 2) =
                 make_float2(empty ? 0.f : m, inv);
@@ -410,31 +421,40 @@ edge_fwd_merge_kernel(const FwdArgs<T, V> a, const int* __restrict__ long_node,
   }
 }
 
-template <typename T, int V, int KV>
-static int launch_fwd_kv(FwdArgs<T, V> a, int sm_count, cudaStream_t stream) {
+template <typename T, int V, int KV, int NP>
+static int launch_fwd_np(FwdArgs<T, V> a, int sm_count, cudaStream_t stream) {
+  constexpr int kWarps = NP == 2 ? kFwdWarps : kFwdWarpsSingle;
   const int groups = a.H / a.hg;
   if (sm_count <= 0) sm_count = 148;
   int ctas = sm_count / groups;
   if (ctas < 1) ctas = 1;
-  const int need = (a.n_chunks + kFwdWarps - 1) / kFwdWarps;
+  const int need = (a.n_chunks + kWarps - 1) / kWarps;
   if (ctas > need) ctas = need;
   const size_t a_bytes = static_cast<size_t>(a.hg) * a.R * a.F * sizeof(float);
   a.a_in_smem = a_bytes <= kSmemBudgetA ? 1 : 0;
   {
     const char* pv = getenv("RELGAT_PF_DIST");
-    a.pf_dist = pv ? atoi(pv) : kPrefetchDist;
+    a.pf_dist = pv ? atoi(pv) : (NP == 2 ? kPrefetchDist : kPrefetchDistSingle);
     if (a.pf_dist < 0) a.pf_dist = 0;
     if (a.pf_dist > 30) a.pf_dist = 30;
   }
   if (a.a_in_smem) {
-    cudaError_t e = cudaFuncSetAttribute(edge_fwd_kernel<T, V, KV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(kSmemBudgetA));
+    cudaError_t e = cudaFuncSetAttribute(edge_fwd_kernel<T, V, KV, true, NP>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudgetA));
     if (e != cudaSuccess) return cuda_status(e);
-    edge_fwd_kernel<T, V, KV, true><<<dim3(ctas, groups), kFwdWarps * 32, a_bytes, stream>>>(a);
+    edge_fwd_kernel<T, V, KV, true, NP><<<dim3(ctas, groups), kWarps * 32, a_bytes, stream>>>(a);
   } else {
-    edge_fwd_kernel<T, V, KV, false><<<dim3(ctas, groups), kFwdWarps * 32, 0, stream>>>(a);
+    edge_fwd_kernel<T, V, KV, false, NP><<<dim3(ctas, groups), kWarps * 32, 0, stream>>>(a);
   }
   return cuda_status(cudaGetLastError());
+}
+
+template <typename T, int V, int KV>
+static int launch_fwd_kv(const FwdArgs<T, V>& a, int sm_count, cudaStream_t stream) {
+  const char* v = getenv("RELGAT_FWD_ROWS");  // experiment knob: rows in flight per warp (1 or 2)
+  const int np = v ? atoi(v) : kFwdRowsDefault;
+  if (np == 1) return launch_fwd_np<T, V, KV, 1>(a, sm_count, stream);
+  return launch_fwd_np<T, V, KV, 2>(a, sm_count, stream);
 }
 
 // KV = 128-bit vectors per lane: specialised so unused accumulator registers are not allocated

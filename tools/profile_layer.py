@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--config", default="c2")
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--skew", type=float, default=0.0)
+    ap.add_argument("--bf16", action="store_true", help="bf16 feature storage (P, G)")
     args = ap.parse_args()
     cfg = S.CONFIGS[args.config]
     dev = torch.device("cuda:0")
@@ -26,17 +27,20 @@ def main():
     H, F, N = cfg["H"], cfg["F"], cfg["N"]
     gen = torch.Generator(device=dev).manual_seed(0)
     P = torch.randn((N, H * F), generator=gen, device=dev)
+    if args.bf16:
+        P = P.bfloat16()
     A = torch.randn((H, cfg["R"], F), generator=gen, device=dev) / F ** 0.5
     beta = torch.randn((cfg["R"],), generator=gen, device=dev) * 0.1
     dY = torch.randn((N, H * F), generator=gen, device=dev)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     for it in range(args.iters):
         ev[0].record()
-        out, act, _, z, minv, bias = ops.edge_fwd(P, A, beta, g, H, F, want_act=True, apply_elu=True)
+        out, act, _, z, minv, bias = ops.edge_fwd(P, A, beta, g, H, F, want_act=True, apply_elu=True, act_lo=not args.bf16)
         ev[1].record()
-        G, t, hsum = ops.edge_bwd_prep(dY, out, bias, H, F, apply_elu=True)
+        G, t, hsum = ops.edge_bwd_prep(dY, out, bias, H, F, apply_elu=True, g_bf16=args.bf16)
         ev[2].record()
-        _, planes, dz = ops.edge_bwd_src(P, G, A, z, minv, t, g, H, F, want_fp32=False, want_planes=True)
+        _, planes, dz = ops.edge_bwd_src(P, G, A, z, minv, t, g, H, F, want_fp32=False, want_planes=True,
+                                         planes_lo=not args.bf16)
         ev[3].record()
         dA, dbeta = ops.edge_bwd_rel(P, dz, hsum, g, H, F)
         ev[4].record()
