@@ -142,6 +142,18 @@ int relgat_score_bwd(int kind, int normalize, const float* xs, const long long* 
 int relgat_index_add_sorted(const float* rows, const long long* perm, const long long* sorted_keys,
                             float* out, int M, int D, int accumulate, void* stream);
 
+/* ---- host-side batch construction (HOST pointers; no GPU involved) --------------------------
+ * Replaces the per-sample Python loop of dataset/edge.py:71-115 + trainer/components/
+ * relgat_batching.py:5-19 bit for bit: `state` is CPython's MT19937 state (624 words + position, i.e.
+ * random.getstate()[1]) and is advanced exactly as B*K random.choice calls (with the reference's
+ * redraw-while-equal-to-tail loop) would advance it.  edges int64[n_edges][3] = (src, dst, rel);
+ * idxs int64[B]; outputs int64[B*(1+K)], positives then K-major negative blocks.
+ * relgat_host_shuffle: random.shuffle of a permutation (dataset/relgat_dataset.py:72). */
+int relgat_host_sample_batch(unsigned int* state, const long long* edges, long long n_edges,
+                             const long long* idxs, int B, int K, long long n_nodes,
+                             long long* src_out, long long* rel_out, long long* dst_out);
+int relgat_host_shuffle(unsigned int* state, long long* perm, long long n);
+
 #ifdef __cplusplus
 }
 #endif

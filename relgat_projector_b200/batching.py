@@ -60,3 +60,43 @@ class ReferenceStreamSampler:
     def __iter__(self) -> Iterator:
         for idxs in self._loader:
             yield self.build(idxs)
+
+
+class NativeStreamSampler(ReferenceStreamSampler):
+    """Same stream, same outputs as ``ReferenceStreamSampler``, but the B*K ``random.choice`` draws run in
+    C (``relgat_host_sample_batch``): CPython's MT19937 state is handed over with ``random.getstate()``
+    and handed back with ``random.setstate()``, so any other user of ``random`` is unaffected."""
+
+    def __init__(self, edges, num_nodes: int, num_neg: int, batch_size: int, shuffle: bool = True):
+        super().__init__(edges, num_nodes, num_neg, batch_size, shuffle)
+        self._edges_np = np.ascontiguousarray(np.asarray(edges, dtype=np.int64).reshape(-1, 3))
+
+    def build(self, idxs):
+        from . import _lib
+        lib = _lib.load()
+        version, internal, gauss = random.getstate()
+        state = np.array(internal, dtype=np.uint32)
+        idx = np.ascontiguousarray(np.asarray(idxs, dtype=np.int64))
+        b, k = int(idx.size), self.num_neg
+        out = np.empty((3, b * (1 + k)), dtype=np.int64)
+        rc = lib.relgat_host_sample_batch(
+            state.ctypes.data, self._edges_np.ctypes.data, self._edges_np.shape[0], idx.ctypes.data, b, k,
+            self.num_nodes, out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data)
+        _lib.check(rc, "relgat_host_sample_batch")
+        random.setstate((version, tuple(int(v) for v in state), gauss))
+        return torch.from_numpy(out[0]), torch.from_numpy(out[1]), torch.from_numpy(out[2])
+
+
+def native_shuffle_and_split(edge_index_raw, train_ratio: float):
+    """``shuffle_and_split`` with the permutation drawn in C from CPython's own generator state."""
+    from . import _lib
+    lib = _lib.load()
+    version, internal, gauss = random.getstate()
+    state = np.array(internal, dtype=np.uint32)
+    perm = np.arange(len(edge_index_raw), dtype=np.int64)
+    _lib.check(lib.relgat_host_shuffle(state.ctypes.data, perm.ctypes.data, perm.size), "relgat_host_shuffle")
+    random.setstate((version, tuple(int(v) for v in state), gauss))
+    shuffled = [edge_index_raw[i] for i in perm]
+    edge_index_raw[:] = shuffled  # in place, like random.shuffle
+    n_train = int(train_ratio * len(edge_index_raw))
+    return edge_index_raw[:n_train], edge_index_raw[n_train:]

@@ -18,7 +18,7 @@ from tests.helpers import GOLDEN_DIR, Case, MODEL_CASES
 def test_library_loads_and_exports_header_symbols():
     lib = _lib.load()
     names = _lib.header_symbols()
-    assert len(names) >= 13
+    assert len(names) >= 15
     assert set(names) == set(_lib.SIGNATURES.keys())
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/relgat_b200.h but not exported"
@@ -153,3 +153,34 @@ def test_synthetic_graph_is_seeded_and_well_formed():
     assert int((d[16:].view(3, 16) == d[:16].unsqueeze(0)).sum()) == 0
     n2e, r2i, raw = S.reference_inputs(50, 200, 4, 6, seed=1)
     assert len(n2e) == 50 and len(raw) == 200 and raw[0][2].startswith("rel_")
+
+
+def test_native_sampler_is_bit_exact_with_cpython_stream():
+    """C restatement of random.choice / random.shuffle: same ids, same generator state afterwards,
+    for node counts around powers of two (rejection paths) and against the reference fixture."""
+    from relgat_projector_b200.batching import NativeStreamSampler, native_shuffle_and_split
+    for n_nodes in (2, 3, 200, 255, 256, 257, 65536, 300_000, 5_000_000):
+        edges = [(i % n_nodes, (7 * i + 1) % n_nodes, i % 5) for i in range(300)]
+        random.seed(99); torch.manual_seed(99)
+        py = ReferenceStreamSampler(edges, n_nodes, 6, 64, shuffle=False)
+        want = [py.build(list(range(b * 64, b * 64 + 64))) for b in range(4)]
+        tail_py = random.random()
+        random.seed(99)
+        nat = NativeStreamSampler(edges, n_nodes, 6, 64, shuffle=False)
+        got = [nat.build(list(range(b * 64, b * 64 + 64))) for b in range(4)]
+        assert random.random() == tail_py  # generator left in the identical state
+        for w, g in zip(want, got):
+            for a, b_ in zip(w, g):
+                assert torch.equal(a, b_)
+    z = np.load(os.path.join(GOLDEN_DIR, "sampling.npz"))
+    n, t, r, d, k, bs, seed = [int(v) for v in z["meta"]]
+    raw = list(zip(z["raw_src"].tolist(), z["raw_dst"].tolist(), z["raw_rel"].tolist()))
+    random.seed(seed); np.random.seed(seed); torch.manual_seed(seed)
+    train, ev = native_shuffle_and_split(raw, 0.9)
+    assert np.array_equal(np.array([e[0] for e in train]), z["edge_index"][0])
+    assert np.array_equal(np.array(ev), z["eval_edges"])
+    for bi, (s_, rr, dd) in enumerate(NativeStreamSampler(train, n, k, bs)):
+        if bi >= 3:
+            break
+        assert np.array_equal(s_.numpy(), z[f"batch{bi}_src"])
+        assert np.array_equal(dd.numpy(), z[f"batch{bi}_dst"])
