@@ -352,8 +352,10 @@ def bench_main(args, cfg, rank, world, local_rank, metric, unit, load_peaks, Clo
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=dev)
-    # weak scaling: the graph grows with the number of GPUs (per-GPU work fixed at the 1-GPU config)
-    n_nodes, n_trip = cfg["N"] * world, cfg["T"] * world
+    # default: weak scaling — the graph grows with the number of GPUs (per-GPU work fixed at the 1-GPU
+    # config); `--config c4` (an explicitly named config): strong scaling on that fixed graph
+    strong = bool(getattr(args, "config", None))
+    n_nodes, n_trip = (cfg["N"], cfg["T"]) if strong else (cfg["N"] * world, cfg["T"] * world)
     kg = S.tensor_kg(n_nodes, n_trip, cfg["R"], cfg["D_in"], seed=42, device=str(dev))
     E = int(kg.edge_index.size(1))
     part = DstPartition(kg.edge_index, kg.edge_type, n_nodes, cfg["R"], rank, world)
@@ -418,9 +420,10 @@ def bench_main(args, cfg, rank, world, local_rank, metric, unit, load_peaks, Clo
         C = cfg["H"] * cfg["F"]
         line = {
             "metric": metric, "value": E / (ms * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps,
-            "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+            "vs_baseline": None,
             "dtype": "fp32" if args.precision == "fp32" else "bf16", "data": "synthetic",
-            "config": {"workload": f"{cfg['name']} x{world}: synthetic KG {n_nodes} nodes / {n_trip} triplets ({E} "
+            "config": {"workload": f"{cfg['name']}{'' if strong else ' x' + str(world)}: synthetic KG {n_nodes} nodes / {n_trip} triplets ({E} "
                                    f"message-passing edges) / {cfg['R']} relations, {cfg['D_in']}-d, {cfg['L']} layers, "
                                    f"{cfg['H']} heads, gat-out-dim {cfg['F']}, {cfg['scorer']}, batch {b}, num-neg {k}",
                        "parallelism": f"dst-range partition x{world}, NCCL all-to-all of halo rows of P fwd / of dP bwd, "
