@@ -107,7 +107,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 class KernelProfiler:
     NAMES = ["split_bf16", "gemm", "edge_fwd", "edge_bwd_prep", "edge_bwd_src", "edge_bwd_rel", "score_fwd",
-             "score_bwd", "index_add_sorted"]
+             "score_bwd", "index_add_sorted", "margin_loss"]
 
     def __init__(self):
         from relgat_projector_b200 import ops
@@ -312,8 +312,7 @@ def main():
         opt.zero_grad(set_to_none=True)
         if not cfg["proj"]:
             scores, _, _ = model(src, rel, dst, transform_to_input_if_possible=False)
-            pos, neg = L.split_scores(scores, b, k)
-            loss = rank_loss.prepare_scores_and_compute_loss(pos, neg)
+            loss = L.fused_margin_ranking_loss(scores, b, k, rank_loss.margin)  # == RelGATLoss on split_scores
         else:
             scores, tr, dst_vec = model(src, rel, dst)
             pos, neg = L.split_scores(scores, b, k, projection_path=True)

@@ -142,6 +142,12 @@ int relgat_score_bwd(int kind, int normalize, const float* xs, const long long* 
 int relgat_index_add_sorted(const float* rows, const long long* perm, const long long* sorted_keys,
                             float* out, int M, int D, int accumulate, void* stream);
 
+/* Margin-ranking loss fused on the flat scores (core/loss/relgat_loss.py:51-54 applied to the split of
+ * trainer/relgat_projector.py:657-676, or :628-630 when bk_layout != 0): score float[B*(1+K)] ->
+ * loss float[1] = mean relu(margin + neg - pos) and dscore float[B*(1+K)] = d loss / d score. */
+int relgat_margin_loss(const float* score, int B, int K, float margin, int bk_layout, float* loss,
+                       float* dscore, void* stream);
+
 /* ---- host-side batch construction (HOST pointers; no GPU involved) --------------------------
  * Replaces the per-sample Python loop of dataset/edge.py:71-115 + trainer/components/
  * relgat_batching.py:5-19 bit for bit: `state` is CPython's MT19937 state (624 words + position, i.e.

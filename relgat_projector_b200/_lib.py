@@ -42,6 +42,7 @@ SIGNATURES = {
     "relgat_score_fwd": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _P, _P, _P]),
     "relgat_score_bwd": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P]),
     "relgat_index_add_sorted": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "relgat_margin_loss": (_I, [_P, _I, _I, ctypes.c_float, _I, _P, _P, _P]),
     "relgat_host_sample_batch": (_I, [_P, _P, _L, _P, _I, _I, _L, _P, _P, _P]),
     "relgat_host_shuffle": (_I, [_P, _P, _L]),
 }

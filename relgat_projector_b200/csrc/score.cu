@@ -230,6 +230,41 @@ index_add_sorted_kernel(const float* __restrict__ rows, const long long* __restr
   RowVec<float, V>::store(o + c, acc);
 }
 
+// Margin-ranking loss fused on the scores (reference core/loss/relgat_loss.py:51-54 on the split of
+// trainer/relgat_projector.py:657-676 / :628-630):  loss = mean_{b,k} relu(margin + neg[b,k] - pos[b]).
+// score layout: positives [0, B), then B*K negatives; neg[b,k] = score[B + k*B + b] (K-major blocks,
+// no-projection path) or score[B + b*K + k] (the projection path's view(B, K)).
+// Also writes dloss/dscore so the backward of the scorer needs no further loss arithmetic.
+// Single block, fixed summation order => reproducible.
+__global__ void __launch_bounds__(256)
+margin_loss_kernel(const float* __restrict__ score, int B, int K, float margin, int bk_layout,
+                   float* __restrict__ loss, float* __restrict__ dscore) {
+  __shared__ float red[256];
+  const int tid = threadIdx.x;
+  const float inv = (B > 0 && K > 0) ? 1.f / (static_cast<float>(B) * K) : 0.f;
+  float acc = 0.f;
+  for (int b = tid; b < B; b += blockDim.x) {
+    const float pos = score[b];
+    float dpos = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const int o = bk_layout ? B + b * K + k : B + k * B + b;
+      const float v = margin + score[o] - pos;
+      const bool on = v > 0.f;
+      acc += on ? v : 0.f;
+      dscore[o] = on ? inv : 0.f;
+      dpos -= on ? inv : 0.f;
+    }
+    dscore[b] = dpos;
+  }
+  red[tid] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s) red[tid] += red[tid + s];
+    __syncthreads();
+  }
+  if (tid == 0) loss[0] = red[0] * inv;
+}
+
 static inline bool al16(const void* p) { return !p || reinterpret_cast<uintptr_t>(p) % 16 == 0; }
 
 static bool score_vec4(const ScoreArgs& a) {
@@ -287,5 +322,12 @@ extern "C" int relgat_index_add_sorted(const float* rows, const long long* perm,
     index_add_sorted_kernel<4><<<dim3(blocks, (D + 127) / 128), kScoreWarps * 32, 0, s>>>(rows, perm, sorted_keys, out, M, D, accumulate);
   else
     index_add_sorted_kernel<1><<<dim3(blocks, (D + 31) / 32), kScoreWarps * 32, 0, s>>>(rows, perm, sorted_keys, out, M, D, accumulate);
+  return cuda_status(cudaGetLastError());
+}
+
+extern "C" int relgat_margin_loss(const float* score, int B, int K, float margin, int bk_layout, float* loss,
+                                  float* dscore, void* stream) {
+  if (!score || !loss || !dscore || B < 0 || K < 0) return RG_ERR_ARG;
+  margin_loss_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(score, B, K, margin, bk_layout, loss, dscore);
   return cuda_status(cudaGetLastError());
 }

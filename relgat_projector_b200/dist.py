@@ -100,6 +100,7 @@ class DstPartition:
         self.send_counts = [int(t.numel()) for t in send_lists]
         self.send_idx = (torch.cat(send_lists) - self.lo) if send_lists else remote.new_zeros(0)
         self.n_send = int(self.send_idx.numel())
+        self.send_sorted = torch.sort(self.send_idx, stable=True) if self.n_send else None  # static per graph
 
     def owner_of(self, ids: torch.Tensor) -> torch.Tensor:
         edges = torch.tensor(self.bounds[1:-1], device=ids.device, dtype=ids.dtype)
@@ -272,7 +273,8 @@ class PartitionedStackFunction(torch.autograd.Function):
                 dP_loc = dP_part[:n_loc]
                 if part.n_send or part.n_halo:  # halo rows go back to their owners, folded in a fixed order
                     back = _all_to_all_rows(dP_part[n_loc:].contiguous(), part.recv_counts, part.send_counts)
-                    dP_loc = ops.index_add_sorted(back, part.send_idx, n_loc, out=dP_loc.contiguous())
+                    dP_loc = ops.index_add_sorted(back, part.send_idx, n_loc, out=dP_loc.contiguous(),
+                                                  presorted=part.send_sorted)
             else:
                 dP_loc = reduce_scatter_rows(dP_part, world)[:n_loc]  # sum over ranks of my sources' rows
             del dP_part
@@ -379,8 +381,7 @@ def bench_main(args, cfg, rank, world, local_rank, metric, unit, load_peaks, Clo
     def step(src, rel, dst):
         opt.zero_grad(set_to_none=True)
         scores = prg.scores(src, rel, dst)
-        pos, neg = L.split_scores(scores, b, k)
-        loss = rank_loss.prepare_scores_and_compute_loss(pos, neg)
+        loss = L.fused_margin_ranking_loss(scores, b, k, 1.0)
         loss.backward()
         prg.finish_backward()
         opt.step()

@@ -215,3 +215,23 @@ class SplitLinearFunction(torch.autograd.Function):
 
 def split_linear(x, weight, precision="fp32"):
     return SplitLinearFunction.apply(x, weight, precision)
+
+
+class MarginLossFunction(torch.autograd.Function):
+    """loss = mean_{b,k} relu(margin + neg[b,k] - pos[b]) on the flat score vector (one kernel that also
+    produces d loss / d score; reference relgat_loss.py:51-54 + trainer score split)."""
+
+    @staticmethod
+    def forward(ctx, score, B, K, margin, projection_layout):
+        loss, dscore = ops.margin_loss(score.detach(), B, K, margin, projection_layout)
+        ctx.save_for_backward(dscore)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (dscore,) = ctx.saved_tensors
+        return dscore * g, None, None, None, None
+
+
+def fused_margin_loss(score, num_pos: int, num_neg: int, margin: float, projection_path: bool = False):
+    return MarginLossFunction.apply(score, int(num_pos), int(num_neg), float(margin), bool(projection_path))

@@ -86,6 +86,14 @@ class MultiObjectiveRelLoss:
         return torch.stack([w * fn() for w, fn in active]).sum() / sum(w for w, _ in active)
 
 
+def fused_margin_ranking_loss(scores: torch.Tensor, num_pos: int, num_neg: int, margin: float,
+                              projection_path: bool = False) -> torch.Tensor:
+    """``RelGATLoss("margin")`` applied to ``split_scores(scores, ...)`` as ONE kernel on the flat CUDA
+    score vector (same value; also yields d loss / d score for the scorer's backward)."""
+    from .functional import fused_margin_loss
+    return fused_margin_loss(scores, num_pos, num_neg, margin, projection_path)
+
+
 def split_scores(scores: torch.Tensor, num_pos: int, num_neg: int, projection_path: bool = False):
     """Flat scores [B*(1+K)] (positives, then K-major negative blocks — reference
     trainer/components/relgat_batching.py:5-19) -> (pos [B], neg [B, K]).

@@ -302,8 +302,10 @@ def score_bwd(kind: str, normalize: bool, xs, src_idx, xd, dst_idx, rel_emb, rel
     return d_src, d_dst, d_rel
 
 
-def index_add_sorted(rows: torch.Tensor, keys: torch.Tensor, n_out: int, out: Optional[torch.Tensor] = None):
-    """out[k] (+)= ordered sum of rows whose key == k.  ``keys`` int64 [M]; rows [M, D]."""
+def index_add_sorted(rows: torch.Tensor, keys: torch.Tensor, n_out: int, out: Optional[torch.Tensor] = None,
+                     presorted=None):
+    """out[k] (+)= ordered sum of rows whose key == k.  ``keys`` int64 [M]; rows [M, D].
+    ``presorted`` = (sorted_keys, perm) of a stable sort of ``keys`` when the caller cached it."""
     rows = _f32c(rows, "rows")
     M, D = rows.shape
     accumulate = out is not None
@@ -311,10 +313,26 @@ def index_add_sorted(rows: torch.Tensor, keys: torch.Tensor, n_out: int, out: Op
         out = torch.zeros((n_out, D), dtype=torch.float32, device=rows.device)
     if M == 0:
         return out
-    sorted_keys, perm = torch.sort(keys, stable=True)  # plumbing: stable order = deterministic sum order
+    # plumbing: stable order = deterministic sum order
+    sorted_keys, perm = presorted if presorted is not None else torch.sort(keys, stable=True)
     with torch.cuda.device(rows.device):
         rc = _lib.load().relgat_index_add_sorted(_lib.ptr(rows), _lib.ptr(perm), _lib.ptr(sorted_keys), _lib.ptr(out),
                                                  M, D, int(accumulate), _stream(rows))
     _lib.check(rc, "relgat_index_add_sorted")
     _count(1)
     return out
+
+
+def margin_loss(score: torch.Tensor, B: int, K: int, margin: float, projection_layout: bool = False):
+    """Returns (loss [1], dscore [B*(1+K)])."""
+    score = _f32c(score, "score")
+    if score.numel() != B * (1 + K):
+        raise ValueError("score must have B*(1+K) entries")
+    loss = torch.empty((1,), dtype=torch.float32, device=score.device)
+    dscore = torch.empty_like(score)
+    with torch.cuda.device(score.device):
+        rc = _lib.load().relgat_margin_loss(_lib.ptr(score), B, K, float(margin), int(projection_layout),
+                                            _lib.ptr(loss), _lib.ptr(dscore), _stream(score))
+    _lib.check(rc, "relgat_margin_loss")
+    _count(1)
+    return loss, dscore

@@ -18,7 +18,7 @@ from tests.helpers import GOLDEN_DIR, Case, MODEL_CASES
 def test_library_loads_and_exports_header_symbols():
     lib = _lib.load()
     names = _lib.header_symbols()
-    assert len(names) >= 15
+    assert len(names) >= 16
     assert set(names) == set(_lib.SIGNATURES.keys())
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/relgat_b200.h but not exported"

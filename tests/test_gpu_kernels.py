@@ -258,3 +258,22 @@ def test_scorer_forward_backward_vs_oracle(dev, kind, normalize, D):
     # rows variant (module-level seam): same numbers without index vectors
     score2, _, _, _ = ops.score_fwd(kind, normalize, sv, None, dv, None, rd, ri)
     assert torch.equal(score2, score)
+
+
+@pytest.mark.parametrize("B,K,proj", [(64, 4, False), (1024, 4, False), (37, 10, True), (5, 0, False), (300, 1, True)])
+def test_fused_margin_loss_matches_oracle(dev, B, K, proj):
+    from relgat_projector_b200 import loss as L
+    g = torch.Generator().manual_seed(B + K)
+    s = torch.randn(B * (1 + K), generator=g)
+    s64 = s.double().requires_grad_(True)
+    pos, neg = (O.split_scores_projection_path if proj else O.split_scores_kmajor)(s64, B, K)
+    sd = s.to(dev).requires_grad_(True)
+    got = L.fused_margin_ranking_loss(sd, B, K, 0.7, projection_path=proj)
+    if K == 0:
+        assert float(got) == 0.0
+        return
+    ref = O.margin_ranking_loss_port(pos, neg, 0.7)
+    ref.backward()
+    got.backward()
+    assert abs(float(got) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+    assert rel_err(sd.grad.cpu().numpy(), s64.grad.numpy()) < 1e-5
