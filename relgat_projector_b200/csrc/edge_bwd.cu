@@ -82,8 +82,10 @@ __global__ void __launch_bounds__(kBwdWarps * 32) bwd_prep_kernel(const PrepArgs
 // lane-private shared-memory slot), followed by one EDGE item per out-edge (the gathered G[dst]
 // row).  Two items are in flight per warp and the pipeline does not drain at source boundaries.
 // ------------------------------------------------------------------------------------
-constexpr int kSrcWarps = 12;
-constexpr int kSrcPrefetchDist = 2;  // default: edges ahead whose G[dst] rows are pulled into L2
+constexpr int kSrcWarps = 12;      // plain variant
+constexpr int kSrcWarpsPipe = 8;   // register double-buffered variant (needs ~230 registers)
+constexpr int kSrcPrefetchDist = 2;
+constexpr int kSrcPipeDefault = 0;  // default: edges ahead whose G[dst] rows are pulled into L2
 
 __device__ __forceinline__ void prefetch_row_l2(const void* ptr, int bytes, int lane) {
   const char* p = static_cast<const char*>(ptr) + lane * 128;
@@ -115,8 +117,9 @@ struct SrcArgs {
   int pf_dist;  // L2 prefetch distance in edges (0 = off)
 };
 
-template <typename T, int V, int KV, bool ASM>
-__global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArgs<T, V> a) {
+template <typename T, int V, int KV, bool ASM, int PIPE>
+__global__ void __launch_bounds__((PIPE ? kSrcWarpsPipe : kSrcWarps) * 32, 1) bwd_src_kernel(const SrcArgs<T, V> a) {
+  constexpr int kWarps = PIPE ? kSrcWarpsPipe : kSrcWarps;
   extern __shared__ __align__(16) float dyn_sm[];
   constexpr int kOwnFloats = KV * 32 * V;  // lane-private slots of one warp's own row
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArg
   const int C = a.H * a.F;
   const int hl = lm.hh - g * a.hg;
   float* p_own = dyn_sm + warp * kOwnFloats;
-  float* a_sm = dyn_sm + kSrcWarps * kOwnFloats;
+  float* a_sm = dyn_sm + kWarps * kOwnFloats;
 
   const int kstride = lm.lph * V;
   const int lane_off = lm.head_off + lm.sub * V;
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArg
 
   enum { IT_NONE = 0, IT_OWN = 1, IT_EDGE = 2, IT_ZERO = 3, IT_END = 4 };
 
-  for (int c = blockIdx.x * kSrcWarps + warp; c < a.n_chunks; c += gridDim.x * kSrcWarps) {
+  for (int c = blockIdx.x * kWarps + warp; c < a.n_chunks; c += gridDim.x * kWarps) {
     const int4 ch = __ldg(a.chunks + c);
     const int n_lo = ch.x;
     const int nn = ch.y;     // 1..64 sources
@@ -301,29 +304,59 @@ __global__ void __launch_bounds__(kSrcWarps * 32, 1) bwd_src_kernel(const SrcArg
     }                                                                                          \
   }
 
-    while (true) {
-      int ty0, nd0, sl0, ds0, rl0, ty1, nd1, sl1, ds1, rl1;
-      RG_NEXT(ty0, nd0, sl0, ds0, rl0);
-      if (ty0 == IT_NONE) break;
-      RG_NEXT(ty1, nd1, sl1, ds1, rl1);
-      float x0[KV][V], x1[KV][V];
-      RG_ISSUE(ty0, nd0, ds0, x0);
-      RG_ISSUE(ty1, nd1, ds1, x1);
-      float z0 = 0.f, z1 = 0.f, t0 = 0.f, t1 = 0.f;
-      float2 mi0 = make_float2(0.f, 0.f), mi1 = make_float2(0.f, 0.f);
-      if (ty0 == IT_EDGE) {
-        z0 = __ldg(a.z + static_cast<long long>(sl0) * a.H + lm.hh);
-        t0 = __ldg(a.t + static_cast<long long>(ds0) * a.H + lm.hh);
-        mi0 = __ldg(reinterpret_cast<const float2*>(a.minv) + static_cast<long long>(ds0) * a.H + lm.hh);
-      }
-      if (ty1 == IT_EDGE) {
-        z1 = __ldg(a.z + static_cast<long long>(sl1) * a.H + lm.hh);
-        t1 = __ldg(a.t + static_cast<long long>(ds1) * a.H + lm.hh);
-        mi1 = __ldg(reinterpret_cast<const float2*>(a.minv) + static_cast<long long>(ds1) * a.H + lm.hh);
-      }
-      RG_CONSUME(ty0, nd0, sl0, rl0, x0, z0, mi0, t0);
-      if (ty1 != IT_NONE) RG_CONSUME(ty1, nd1, sl1, rl1, x1, z1, mi1, t1);
+    // FETCH: hand out the next two items, issue their row loads and per-edge scalars
+#define RG_DECL(S_)                                                                            \
+    int ty##S_##0 = IT_NONE, nd##S_##0 = 0, sl##S_##0 = 0, ds##S_##0 = 0, rl##S_##0 = 0;       \
+    int ty##S_##1 = IT_NONE, nd##S_##1 = 0, sl##S_##1 = 0, ds##S_##1 = 0, rl##S_##1 = 0;       \
+    float x##S_##0[KV][V], x##S_##1[KV][V];                                                    \
+    float z##S_##0 = 0.f, z##S_##1 = 0.f, t##S_##0 = 0.f, t##S_##1 = 0.f;                      \
+    float2 mi##S_##0 = make_float2(0.f, 0.f), mi##S_##1 = make_float2(0.f, 0.f);
+#define RG_FETCH(S_)                                                                           \
+    RG_NEXT(ty##S_##0, nd##S_##0, sl##S_##0, ds##S_##0, rl##S_##0);                            \
+    if (ty##S_##0 != IT_NONE) { RG_NEXT(ty##S_##1, nd##S_##1, sl##S_##1, ds##S_##1, rl##S_##1); } \
+    else { ty##S_##1 = IT_NONE; }                                                              \
+    RG_ISSUE(ty##S_##0, nd##S_##0, ds##S_##0, x##S_##0);                                       \
+    RG_ISSUE(ty##S_##1, nd##S_##1, ds##S_##1, x##S_##1);                                       \
+    if (ty##S_##0 == IT_EDGE) {                                                                \
+      z##S_##0 = __ldg(a.z + static_cast<long long>(sl##S_##0) * a.H + lm.hh);                 \
+      t##S_##0 = __ldg(a.t + static_cast<long long>(ds##S_##0) * a.H + lm.hh);                 \
+      mi##S_##0 = __ldg(reinterpret_cast<const float2*>(a.minv) + static_cast<long long>(ds##S_##0) * a.H + lm.hh); \
+    }                                                                                          \
+    if (ty##S_##1 == IT_EDGE) {                                                                \
+      z##S_##1 = __ldg(a.z + static_cast<long long>(sl##S_##1) * a.H + lm.hh);                 \
+      t##S_##1 = __ldg(a.t + static_cast<long long>(ds##S_##1) * a.H + lm.hh);                 \
+      mi##S_##1 = __ldg(reinterpret_cast<const float2*>(a.minv) + static_cast<long long>(ds##S_##1) * a.H + lm.hh); \
     }
+#define RG_DRAIN(S_)                                                                           \
+    RG_CONSUME(ty##S_##0, nd##S_##0, sl##S_##0, rl##S_##0, x##S_##0, z##S_##0, mi##S_##0, t##S_##0); \
+    if (ty##S_##1 != IT_NONE)                                                                  \
+      RG_CONSUME(ty##S_##1, nd##S_##1, sl##S_##1, rl##S_##1, x##S_##1, z##S_##1, mi##S_##1, t##S_##1);
+
+    if (PIPE) {
+      // register double buffering: the loads of the next two items are in flight while the
+      // current two are consumed
+      RG_DECL(A)
+      RG_DECL(B)
+      RG_FETCH(A)
+      while (true) {
+        if (tyA0 == IT_NONE) break;
+        RG_FETCH(B)
+        RG_DRAIN(A)
+        if (tyB0 == IT_NONE) break;
+        RG_FETCH(A)
+        RG_DRAIN(B)
+      }
+    } else {
+      while (true) {
+        RG_DECL(A)
+        RG_FETCH(A)
+        if (tyA0 == IT_NONE) break;
+        RG_DRAIN(A)
+      }
+    }
+#undef RG_DRAIN
+#undef RG_FETCH
+#undef RG_DECL
 #undef RG_CONSUME
 #undef RG_EDGE_ITEM
 #undef RG_ISSUE
@@ -515,15 +548,16 @@ bwd_src_merge_kernel(const SrcArgs<T, V> a, const int* __restrict__ long_node, c
   }
 }
 
-template <typename T, int V, int KV>
-static int launch_src_kv(SrcArgs<T, V> a, int sm_count, cudaStream_t s) {
+template <typename T, int V, int KV, int PIPE>
+static int launch_src_pipe(SrcArgs<T, V> a, int sm_count, cudaStream_t s) {
+  constexpr int kWarps = PIPE ? kSrcWarpsPipe : kSrcWarps;
   const int groups = a.H / a.hg;
   if (sm_count <= 0) sm_count = 148;
   int ctas = sm_count / groups;
   if (ctas < 1) ctas = 1;
-  const int need = (a.n_chunks + kSrcWarps - 1) / kSrcWarps;
+  const int need = (a.n_chunks + kWarps - 1) / kWarps;
   if (ctas > need) ctas = need;
-  const size_t own_bytes = static_cast<size_t>(kSrcWarps) * KV * 32 * V * sizeof(float);
+  const size_t own_bytes = static_cast<size_t>(kWarps) * KV * 32 * V * sizeof(float);
   const size_t a_bytes = static_cast<size_t>(a.hg) * a.R * a.F * sizeof(float);
   a.a_in_smem = a_bytes <= kSmemBudgetA ? 1 : 0;
   {
@@ -533,14 +567,23 @@ static int launch_src_kv(SrcArgs<T, V> a, int sm_count, cudaStream_t s) {
     if (a.pf_dist > 30) a.pf_dist = 30;
   }
   if (a.a_in_smem) {
-    cudaError_t e = cudaFuncSetAttribute(bwd_src_kernel<T, V, KV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(bwd_src_kernel<T, V, KV, true, PIPE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(own_bytes + kSmemBudgetA));
     if (e != cudaSuccess) return cuda_status(e);
-    bwd_src_kernel<T, V, KV, true><<<dim3(ctas, groups), kSrcWarps * 32, own_bytes + a_bytes, s>>>(a);
+    bwd_src_kernel<T, V, KV, true, PIPE><<<dim3(ctas, groups), kWarps * 32, own_bytes + a_bytes, s>>>(a);
   } else {
-    bwd_src_kernel<T, V, KV, false><<<dim3(ctas, groups), kSrcWarps * 32, own_bytes, s>>>(a);
+    bwd_src_kernel<T, V, KV, false, PIPE><<<dim3(ctas, groups), kWarps * 32, own_bytes, s>>>(a);
   }
   return cuda_status(cudaGetLastError());
+}
+
+template <typename T, int V, int KV>
+static int launch_src_kv(const SrcArgs<T, V>& a, int sm_count, cudaStream_t s) {
+  const char* v = getenv("RELGAT_SRC_PIPE");  // experiment knob
+  const int pipe = v ? atoi(v) : kSrcPipeDefault;
+  if (pipe) return launch_src_pipe<T, V, KV, 1>(a, sm_count, s);
+  return launch_src_pipe<T, V, KV, 0>(a, sm_count, s);
 }
 
 template <typename T, int V>
