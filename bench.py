@@ -41,7 +41,7 @@ def load_peaks():
         with open(path) as f:
             p = json.load(f)
         return dict(hbm_gbs=float(p["hbm_gbs"]), tflops=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
-                    source="measured (MEASURED_PEAKS.json; sustained bf16 figure: kernel timed inside a long step)")
+                    source="measured (MEASURED_PEAKS.json: copy bandwidth for HBM, sustained bf16 GEMM figure for tensor)")
     return dict(hbm_gbs=6650.0, tflops=1400.0, source="fallback (B200_PROFILING.md)")
 
 
