@@ -87,10 +87,7 @@ constexpr int kSrcWarpsPipe = 8;   // register double-buffered variant (needs ~2
 constexpr int kSrcPrefetchDist = 2;
 constexpr int kSrcPipeDefault = 0;  // default: edges ahead whose G[dst] rows are pulled into L2
 
-__device__ __forceinline__ void prefetch_row_l2(const void* ptr, int bytes, int lane) {
-  const char* p = static_cast<const char*>(ptr) + lane * 128;
-  if (lane * 128 < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
+__device__ __forceinline__ void prefetch_l2(const char* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <typename T, int V>
 struct SrcArgs {
@@ -117,7 +114,7 @@ struct SrcArgs {
   int pf_dist;  // L2 prefetch distance in edges (0 = off)
 };
 
-template <typename T, int V, int KV, bool ASM, int PIPE>
+template <typename T, int V, int KV, bool ASM, int PIPE, int LPHC>
 __global__ void __launch_bounds__((PIPE ? kSrcWarpsPipe : kSrcWarps) * 32, 1) bwd_src_kernel(const SrcArgs<T, V> a) {
   constexpr int kWarps = PIPE ? kSrcWarpsPipe : kSrcWarps;
   extern __shared__ __align__(16) float dyn_sm[];
@@ -130,11 +127,18 @@ __global__ void __launch_bounds__((PIPE ? kSrcWarpsPipe : kSrcWarps) * 32, 1) bw
   float* p_own = dyn_sm + warp * kOwnFloats;
   float* a_sm = dyn_sm + kWarps * kOwnFloats;
 
-  const int kstride = lm.lph * V;
+  const int kstride = (LPHC > 0 ? LPHC : lm.lph) * V;  // compile-time on the specialised paths
   const int lane_off = lm.head_off + lm.sub * V;
   const bool last_ok = lm.sub + lm.lph * (KV - 1) < lm.vph;
   const int row_bytes = a.hg * a.F * static_cast<int>(sizeof(T));
   const int grp_off = g * a.hg * a.F;
+  const unsigned long long p_stride_b = static_cast<unsigned long long>(a.ldp) * sizeof(T);
+  const unsigned long long g_stride_b = static_cast<unsigned long long>(C) * sizeof(T);
+  const char* p_lane = reinterpret_cast<const char*>(a.P + lane_off);
+  const char* g_lane = reinterpret_cast<const char*>(a.G + lane_off);
+  const char* p_pf = reinterpret_cast<const char*>(a.P + grp_off) + lane * 128;
+  const char* g_pf = reinterpret_cast<const char*>(a.G + grp_off) + lane * 128;
+  const bool pf_lane_ok = lane * 128 < row_bytes;
 #define RG_VALID(k_) ((k_) < KV - 1 || last_ok)
 
   const float* a_base;
@@ -203,8 +207,8 @@ __global__ void __launch_bounds__((PIPE ? kSrcWarpsPipe : kSrcWarps) * 32, 1) bw
       if (!own_done) {                                                                         \
         own_done = true; nd_ = fk;                                                             \
         ty_ = (f_end == fe) ? IT_ZERO : IT_OWN;                                                \
-        if (a.pf_dist > 0 && fk + 2 < nn) /* own rows are consecutive: keep two ahead in L2 */  \
-          prefetch_row_l2(a.P + static_cast<long long>(n_lo + fk + 2) * a.ldp + grp_off, row_bytes, lane); \
+        if (pf_lane_ok && a.pf_dist > 0 && fk + 2 < nn) /* own rows: keep two ahead in L2 */     \
+          prefetch_l2(p_pf + static_cast<unsigned long long>(n_lo + fk + 2) * p_stride_b);     \
         break;                                                                                 \
       }                                                                                        \
       if (fe < f_end) {                                                                        \
@@ -218,15 +222,15 @@ __global__ void __launch_bounds__((PIPE ? kSrcWarpsPipe : kSrcWarps) * 32, 1) bw
           }                                                                                    \
           for (int pf = 0; pf < a.pf_dist; ++pf) { /* warm L2 with the window's first rows */  \
             const int jp = __shfl_sync(0xffffffffu, my_dst, pf);                               \
-            if (base + pf < e_hi)                                                              \
-              prefetch_row_l2(a.G + static_cast<long long>(jp) * C + grp_off, row_bytes, lane); \
+            if (pf_lane_ok && base + pf < e_hi)                                                \
+              prefetch_l2(g_pf + static_cast<unsigned long long>(jp) * g_stride_b);            \
           }                                                                                    \
         }                                                                                      \
         if (a.pf_dist > 0) { /* rolling prefetch, pf_dist edges ahead inside the window */      \
           const int tp = fe - base + a.pf_dist;                                                \
           const int jp = __shfl_sync(0xffffffffu, my_dst, tp & 31);                            \
-          if (tp < 32 && base + tp < e_hi)                                                     \
-            prefetch_row_l2(a.G + static_cast<long long>(jp) * C + grp_off, row_bytes, lane);  \
+          if (pf_lane_ok && tp < 32 && base + tp < e_hi)                                       \
+            prefetch_l2(g_pf + static_cast<unsigned long long>(jp) * g_stride_b);              \
         }                                                                                      \
         sl_ = __shfl_sync(0xffffffffu, my_slot, fe - base);                                    \
         ds_ = __shfl_sync(0xffffffffu, my_dst, fe - base);                                     \
@@ -242,9 +246,9 @@ __global__ void __launch_bounds__((PIPE ? kSrcWarpsPipe : kSrcWarps) * 32, 1) bw
 #define RG_ISSUE(ty_, nd_, ds_, x_)                                                            \
   _Pragma("unroll") for (int v = 0; v < V; ++v) x_[KV - 1][v] = 0.f;                           \
   if (ty_ == IT_OWN || ty_ == IT_EDGE) {                                                       \
-    const T* rowp = (ty_ == IT_OWN)                                                            \
-        ? a.P + static_cast<long long>(n_lo + (nd_)) * a.ldp + lane_off                        \
-        : a.G + static_cast<long long>(ds_) * C + lane_off;                                    \
+    const T* rowp = reinterpret_cast<const T*>((ty_ == IT_OWN)                                 \
+        ? p_lane + static_cast<unsigned long long>(n_lo + (nd_)) * p_stride_b                  \
+        : g_lane + static_cast<unsigned long long>(ds_) * g_stride_b);                         \
     _Pragma("unroll") for (int k = 0; k < KV; ++k)                                             \
       if (RG_VALID(k)) RowVec<T, V>::load_stream(rowp + k * kstride, x_[k]);                   \
   }
@@ -548,7 +552,7 @@ bwd_src_merge_kernel(const SrcArgs<T, V> a, const int* __restrict__ long_node, c
   }
 }
 
-template <typename T, int V, int KV, int PIPE>
+template <typename T, int V, int KV, int PIPE, int LPHC>
 static int launch_src_pipe(SrcArgs<T, V> a, int sm_count, cudaStream_t s) {
   constexpr int kWarps = PIPE ? kSrcWarpsPipe : kSrcWarps;
   const int groups = a.H / a.hg;
@@ -567,13 +571,13 @@ static int launch_src_pipe(SrcArgs<T, V> a, int sm_count, cudaStream_t s) {
     if (a.pf_dist > 30) a.pf_dist = 30;
   }
   if (a.a_in_smem) {
-    cudaError_t e = cudaFuncSetAttribute(bwd_src_kernel<T, V, KV, true, PIPE>,
+    cudaError_t e = cudaFuncSetAttribute(bwd_src_kernel<T, V, KV, true, PIPE, LPHC>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(own_bytes + kSmemBudgetA));
     if (e != cudaSuccess) return cuda_status(e);
-    bwd_src_kernel<T, V, KV, true, PIPE><<<dim3(ctas, groups), kWarps * 32, own_bytes + a_bytes, s>>>(a);
+    bwd_src_kernel<T, V, KV, true, PIPE, LPHC><<<dim3(ctas, groups), kWarps * 32, own_bytes + a_bytes, s>>>(a);
   } else {
-    bwd_src_kernel<T, V, KV, false, PIPE><<<dim3(ctas, groups), kWarps * 32, own_bytes, s>>>(a);
+    bwd_src_kernel<T, V, KV, false, PIPE, LPHC><<<dim3(ctas, groups), kWarps * 32, own_bytes, s>>>(a);
   }
   return cuda_status(cudaGetLastError());
 }
@@ -582,8 +586,13 @@ template <typename T, int V, int KV>
 static int launch_src_kv(const SrcArgs<T, V>& a, int sm_count, cudaStream_t s) {
   const char* v = getenv("RELGAT_SRC_PIPE");  // experiment knob
   const int pipe = v ? atoi(v) : kSrcPipeDefault;
-  if (pipe) return launch_src_pipe<T, V, KV, 1>(a, sm_count, s);
-  return launch_src_pipe<T, V, KV, 0>(a, sm_count, s);
+  const int lph = 32 / a.hg;
+  constexpr bool kSpec8 = (V == 4 && KV == 7) || (V == 8 && KV == 4);  // F = 200, 4 heads per warp
+  constexpr bool kSpec32 = (V == 4 && KV == 2);                        // F = 200, one head per warp
+  if (pipe) return launch_src_pipe<T, V, KV, 1, 0>(a, sm_count, s);
+  if (kSpec8 && lph == 8) return launch_src_pipe<T, V, KV, 0, kSpec8 ? 8 : 0>(a, sm_count, s);
+  if (kSpec32 && lph == 32) return launch_src_pipe<T, V, KV, 0, kSpec32 ? 32 : 0>(a, sm_count, s);
+  return launch_src_pipe<T, V, KV, 0, 0>(a, sm_count, s);
 }
 
 template <typename T, int V>

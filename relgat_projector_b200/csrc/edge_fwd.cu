@@ -27,10 +27,7 @@ constexpr int kPrefetchDistSingle = 3;
 constexpr int kFwdRowsDefault = 2;  // default number of edges ahead whose source rows are pulled into L2
 
 // warp-cooperative L2 prefetch of one row slice [ptr, ptr + bytes): lane l touches line l
-__device__ __forceinline__ void prefetch_row_l2_fwd(const void* ptr, int bytes, int lane) {
-  const char* p = static_cast<const char*>(ptr) + lane * 128;
-  if (lane * 128 < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
+__device__ __forceinline__ void prefetch_l2(const char* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <typename T, int V>
 struct FwdArgs {
@@ -67,7 +64,7 @@ __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : fast_exp(x
 // grid = (CTAs per head-group, head-groups); every CTA is persistent and owns one head-group, so
 // it stages only that group's attention vectors (ncu on the first version showed the per-edge
 // A-row reads missing L1 ~40-70% of the time and doubling the L2->SM traffic).
-template <typename T, int V, int KV, bool ASM, int NP>
+template <typename T, int V, int KV, bool ASM, int NP, int LPHC>
 __global__ void __launch_bounds__((NP == 2 ? kFwdWarps : kFwdWarpsSingle) * 32, 1)
 edge_fwd_kernel(const FwdArgs<T, V> a) {
   constexpr int kWarps = NP == 2 ? kFwdWarps : kFwdWarpsSingle;
@@ -80,10 +77,16 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
   const int hl = lm.hh - g * a.hg;  // head index inside the group
 
   // lane geometry: vectors k < KV-1 are always inside the head, only the last one needs a guard
-  const int kstride = lm.lph * V;                      // elements between a lane's consecutive vectors
+  // elements between a lane's consecutive vectors; a compile-time constant on the specialised paths
+  // (LPHC > 0), which turns every per-vector address into base + immediate
+  const int kstride = (LPHC > 0 ? LPHC : lm.lph) * V;
   const int lane_off = lm.head_off + lm.sub * V;       // first element of this lane inside a node row
   const bool last_ok = lm.sub + lm.lph * (KV - 1) < lm.vph;
   const int row_bytes = a.hg * a.F * static_cast<int>(sizeof(T));  // this head-group's slice of a row
+  const unsigned long long row_stride_b = static_cast<unsigned long long>(a.ldp) * sizeof(T);
+  const char* p_lane = reinterpret_cast<const char*>(a.P + lane_off);              // lane's first vector of row 0
+  const char* p_pf = reinterpret_cast<const char*>(a.P + g * a.hg * a.F) + lane * 128;  // lane's prefetch line
+  const bool pf_lane_ok = lane * 128 < row_bytes;
 #define RG_VALID(k_) ((k_) < KV - 1 || last_ok)
 
   const float* a_base;  // rows of this lane's head: a_base + r * F
@@ -166,7 +169,7 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
         // kPrefetchDist rows ahead, so the gathers mostly pay L2 instead of HBM latency
         for (int pf = 0; pf < a.pf_dist; ++pf) {
           const int ip = __shfl_sync(0xffffffffu, my_src, pf);
-          if (base + pf < e_hi) prefetch_row_l2_fwd(a.P + static_cast<long long>(ip) * a.ldp + g * a.hg * a.F, row_bytes, lane);
+          if (base + pf < e_hi && pf_lane_ok) prefetch_l2(p_pf + static_cast<unsigned long long>(ip) * row_stride_b);
         }
       }
       const int npair = min(NP, min(e_hi - e, base + 32 - e));  // 0 only when the chunk is exhausted
@@ -183,14 +186,14 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
         const int i1 = __shfl_sync(0xffffffffu, my_src, two ? t + 1 : t);
         const int r1 = __shfl_sync(0xffffffffu, my_rel, two ? t + 1 : t);
         b1 = __shfl_sync(0xffffffffu, my_beta, two ? t + 1 : t);
-        const T* p0 = a.P + static_cast<long long>(i0) * a.ldp + lane_off;
-        const T* p1 = a.P + static_cast<long long>(i1) * a.ldp + lane_off;
+        const T* p0 = reinterpret_cast<const T*>(p_lane + static_cast<unsigned long long>(i0) * row_stride_b);
+        const T* p1 = reinterpret_cast<const T*>(p_lane + static_cast<unsigned long long>(i1) * row_stride_b);
 #pragma unroll
         for (int pf = 0; pf < NP; ++pf) {  // rolling L2 prefetch, pf_dist edges ahead (same window)
           const int tp = t + a.pf_dist + pf;
           const int ip = __shfl_sync(0xffffffffu, my_src, tp & 31);
-          if (a.pf_dist > 0 && tp < 32 && base + tp < e_hi)
-            prefetch_row_l2_fwd(a.P + static_cast<long long>(ip) * a.ldp + g * a.hg * a.F, row_bytes, lane);
+          if (pf_lane_ok && a.pf_dist > 0 && tp < 32 && base + tp < e_hi)
+            prefetch_l2(p_pf + static_cast<unsigned long long>(ip) * row_stride_b);
         }
         // issue both row gathers before any arithmetic (two rows in flight per warp)
 #pragma unroll
@@ -421,7 +424,7 @@ edge_fwd_merge_kernel(const FwdArgs<T, V> a, const int* __restrict__ long_node,
   }
 }
 
-template <typename T, int V, int KV, int NP>
+template <typename T, int V, int KV, int NP, int LPHC>
 static int launch_fwd_np(FwdArgs<T, V> a, int sm_count, cudaStream_t stream) {
   constexpr int kWarps = NP == 2 ? kFwdWarps : kFwdWarpsSingle;
   const int groups = a.H / a.hg;
@@ -439,12 +442,12 @@ static int launch_fwd_np(FwdArgs<T, V> a, int sm_count, cudaStream_t stream) {
     if (a.pf_dist > 30) a.pf_dist = 30;
   }
   if (a.a_in_smem) {
-    cudaError_t e = cudaFuncSetAttribute(edge_fwd_kernel<T, V, KV, true, NP>,
+    cudaError_t e = cudaFuncSetAttribute(edge_fwd_kernel<T, V, KV, true, NP, LPHC>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudgetA));
     if (e != cudaSuccess) return cuda_status(e);
-    edge_fwd_kernel<T, V, KV, true, NP><<<dim3(ctas, groups), kWarps * 32, a_bytes, stream>>>(a);
+    edge_fwd_kernel<T, V, KV, true, NP, LPHC><<<dim3(ctas, groups), kWarps * 32, a_bytes, stream>>>(a);
   } else {
-    edge_fwd_kernel<T, V, KV, false, NP><<<dim3(ctas, groups), kWarps * 32, 0, stream>>>(a);
+    edge_fwd_kernel<T, V, KV, false, NP, LPHC><<<dim3(ctas, groups), kWarps * 32, 0, stream>>>(a);
   }
   return cuda_status(cudaGetLastError());
 }
@@ -453,8 +456,15 @@ template <typename T, int V, int KV>
 static int launch_fwd_kv(const FwdArgs<T, V>& a, int sm_count, cudaStream_t stream) {
   const char* v = getenv("RELGAT_FWD_ROWS");  // experiment knob: rows in flight per warp (1 or 2)
   const int np = v ? atoi(v) : kFwdRowsDefault;
-  if (np == 1) return launch_fwd_np<T, V, KV, 1>(a, sm_count, stream);
-  return launch_fwd_np<T, V, KV, 2>(a, sm_count, stream);
+  const int lph = 32 / a.hg;
+  // compile-time lane stride for the shapes of the named configs (F = 200: 4 heads per warp in fp32
+  // and bf16, or one head per warp when R is large); everything else takes the generic path
+  constexpr bool kSpec8 = (V == 4 && KV == 7) || (V == 8 && KV == 4);
+  constexpr bool kSpec32 = (V == 4 && KV == 2);
+  if (np == 1) return launch_fwd_np<T, V, KV, 1, 0>(a, sm_count, stream);
+  if (kSpec8 && lph == 8) return launch_fwd_np<T, V, KV, 2, kSpec8 ? 8 : 0>(a, sm_count, stream);
+  if (kSpec32 && lph == 32) return launch_fwd_np<T, V, KV, 2, kSpec32 ? 32 : 0>(a, sm_count, stream);
+  return launch_fwd_np<T, V, KV, 2, 0>(a, sm_count, stream);
 }
 
 // KV = 128-bit vectors per lane: specialised so unused accumulator registers are not allocated
