@@ -81,7 +81,8 @@ int relgat_gemm_bf16(const void* a_hi, const void* a_lo, long long lda, int a_mn
  *     part_b [n_parts], part_acc [n_parts,H*F], caller-allocated) are merged in part order;
  *   long_node int32[n_long], long_part_ptr int32[n_long+1]: the split destinations.
  * The kernels are persistent (sm_count CTAs; <= 0 means 148) and stage the attention vectors in
- * shared memory.
+ * shared memory.  work_counter: >= 32 device ints of scratch (zeroed by the call) from which warps
+ * claim chunks dynamically; NULL = static round-robin assignment.
  * Outputs: out [N, H*F] fp32 pre-activation (may be NULL), optional bf16 (hi, lo) planes of
  * act(out) for the next layer's GEMM (act = ELU if apply_elu, reference model.py:286-287),
  * z [E, H] raw logits and minv [N, H, 2] = (segment max, 1/denominator) saved for backward,
@@ -93,7 +94,7 @@ int relgat_layer_fwd(const void* P, int p_is_bf16, long long ldp, const float* A
                      float* part_ml, float* part_b, float* part_acc,
                      float* out, void* act_hi, void* act_lo, int apply_elu,
                      float* alpha, float* z, float* minv, float* bias_out,
-                     int H, int F, int R, int sm_count, void* stream);
+                     int H, int F, int R, int sm_count, int* work_counter, void* stream);
 
 /* ---- RelGAT layer, edge part, backward (replaces the autograd replay of layer.py:220-318) ---
  * Feature storage: P and G are fp32, or both bf16 when the *_is_bf16 flags are set (F % 8 == 0).
@@ -115,7 +116,7 @@ int relgat_layer_bwd_src(const void* P, long long ldp, const void* G, int feat_i
                          const int* chunks, int n_chunks, const int* parts, int n_parts,
                          const int* long_node, const int* long_part_ptr, int n_long, float* part_acc,
                          float* dP, void* dP_hi, void* dP_lo, float* dz,
-                         int H, int F, int R, int sm_count, void* stream);
+                         int H, int F, int R, int sm_count, int* work_counter, void* stream);
 int relgat_layer_bwd_rel(const void* P, int p_is_bf16, long long ldp, const float* dz, const float* hsum,
                          const int* rel_slot, const int* csr_src, const int* csr_dst,
                          const int* chunk_lo, const int* chunk_hi, const int* rel_chunk_ptr,

@@ -211,6 +211,15 @@ __device__ __forceinline__ LaneMap make_lane_map(int lane, int group, int hg, in
   return m;
 }
 
+// Next chunk for this warp: dynamic claim from a device counter (lane 0 does the atomic, the warp gets the
+// value), or the static start index when no counter is given.
+__device__ __forceinline__ int claim_chunk(int* counter, int lane, int static_index) {
+  if (!counter) return static_index;
+  int c = 0;
+  if (lane == 0) c = atomicAdd(counter, 1);
+  return __shfl_sync(0xffffffffu, c, 0);
+}
+
 // Sum over the lanes that own the same head (lph is a power of two <= 32).
 __device__ __forceinline__ float head_sum(float x, int lph) {
 #pragma unroll

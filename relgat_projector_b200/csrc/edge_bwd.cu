@@ -112,6 +112,7 @@ struct SrcArgs {
   long long ldp;
   int a_in_smem;
   int pf_dist;  // L2 prefetch distance in edges (0 = off)
+  int* work_counter;  // zeroed device ints (one per head-group): dynamic chunk claim; nullptr = static
 };
 
 template <typename T, int V, int KV, bool ASM, int PIPE, int LPHC>
@@ -159,7 +160,9 @@ __global__ void __launch_bounds__((PIPE ? kSrcWarpsPipe : kSrcWarps) * 32, 1) bw
 
   enum { IT_NONE = 0, IT_OWN = 1, IT_EDGE = 2, IT_ZERO = 3, IT_END = 4 };
 
-  for (int c = blockIdx.x * kWarps + warp; c < a.n_chunks; c += gridDim.x * kWarps) {
+  int* counter = a.work_counter ? a.work_counter + g : nullptr;
+  for (int c = claim_chunk(counter, lane, blockIdx.x * kWarps + warp); c < a.n_chunks;
+       c = counter ? claim_chunk(counter, lane, 0) : c + gridDim.x * kWarps) {
     const int4 ch = __ldg(a.chunks + c);
     const int n_lo = ch.x;
     const int nn = ch.y;     // 1..64 sources
@@ -622,12 +625,16 @@ static int run_src(const void* P, long long ldp, const void* G, const float* A, 
                    const float* t, const int* colptr, const int* csc_slot, const int* csc_dst, const int* csc_rel,
                    const int4* ch, int n_chunks, const int2* pt, const int* long_node, const int* long_part_ptr,
                    int n_long, float* part_acc, float* dP, void* dP_hi, void* dP_lo, float* dz, int H, int F, int R,
-                   int sm_count, cudaStream_t s) {
+                   int sm_count, int* work_counter, cudaStream_t s) {
   const int hg = pick_heads_per_warp(H, F, V, R, smem_budget_override("RELGAT_SRC_BUDGET_KB", kSmemBudgetA));
   if (!hg) return RG_ERR_SHAPE;
+  if (work_counter) {
+    cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int) * (H / hg), s);
+    if (e != cudaSuccess) return cuda_status(e);
+  }
   SrcArgs<T, V> a{static_cast<const T*>(P), static_cast<const T*>(G), A, z, minv, t, colptr, csc_slot, csc_dst,
                   csc_rel, ch, pt, part_acc, dP, static_cast<__nv_bfloat16*>(dP_hi),
-                  static_cast<__nv_bfloat16*>(dP_lo), dz, n_chunks, H, F, R, hg, ldp, 0, 0};
+                  static_cast<__nv_bfloat16*>(dP_lo), dz, n_chunks, H, F, R, hg, ldp, 0, 0, work_counter};
   int rc = launch_src(a, sm_count, s);
   if (rc != RG_OK || n_long == 0) return rc;
   bwd_src_merge_kernel<T, V><<<n_long, 128, 0, s>>>(a, long_node, long_part_ptr, n_long);
@@ -640,7 +647,7 @@ extern "C" int relgat_layer_bwd_src(const void* P, long long ldp, const void* G,
                                     const int* chunks, int n_chunks, const int* parts, int n_parts,
                                     const int* long_node, const int* long_part_ptr, int n_long, float* part_acc,
                                     float* dP, void* dP_hi, void* dP_lo, float* dz,
-                                    int H, int F, int R, int sm_count, void* stream) {
+                                    int H, int F, int R, int sm_count, int* work_counter, void* stream) {
   if (!P || !G || !A || !colptr || n_chunks < 0 || n_parts < 0 || n_long < 0 || H <= 0 || F <= 0 || R <= 0)
     return RG_ERR_ARG;
   if (n_chunks > 0 && !chunks) return RG_ERR_ARG;
@@ -656,13 +663,13 @@ extern "C" int relgat_layer_bwd_src(const void* P, long long ldp, const void* G,
     if (!ok16) return RG_ERR_ALIGN;
     return run_src<__nv_bfloat16, 8>(P, ldp, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, ch, n_chunks, pt,
                                      long_node, long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, H, F, R,
-                                     sm_count, s);
+                                     sm_count, work_counter, s);
   }
   if (F % 4 == 0 && ldp % 4 == 0 && ok16)
     return run_src<float, 4>(P, ldp, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, ch, n_chunks, pt, long_node,
-                             long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, H, F, R, sm_count, s);
+                             long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, H, F, R, sm_count, work_counter, s);
   return run_src<float, 1>(P, ldp, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, ch, n_chunks, pt, long_node,
-                           long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, H, F, R, sm_count, s);
+                           long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, H, F, R, sm_count, work_counter, s);
 }
 
 template <typename T, int V>

@@ -54,6 +54,7 @@ struct FwdArgs {
   int apply_elu;         // act = ELU (reference model.py:286-287) else identity
   int a_in_smem;         // the head-group's slice of A (hg*R*F floats) is staged in shared memory
   int pf_dist;           // L2 prefetch distance in edges (0 = off)
+  int* work_counter;     // zeroed device int: warps claim chunks dynamically (nullptr = static round-robin)
 };
 
 // ELU(x) = x (x > 0) else exp(x) - 1.  __expf keeps the absolute error at ~1e-7 (the inputs are
@@ -105,7 +106,11 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
     a_base = a.A + static_cast<long long>(lm.hh) * a.R * a.F + lm.sub * V;
   }
 
-  for (int c = blockIdx.x * kWarps + warp; c < a.n_chunks; c += gridDim.x * kWarps) {
+  // chunk claim: dynamic (one atomic per chunk, per head-group counter) keeps all warps busy until the
+  // last chunk; static round-robin left a tail of up to one chunk per warp (CE sweep in DESIGN.md)
+  int* counter = a.work_counter ? a.work_counter + g : nullptr;
+  for (int c = claim_chunk(counter, lane, blockIdx.x * kWarps + warp); c < a.n_chunks;
+       c = counter ? claim_chunk(counter, lane, 0) : c + gridDim.x * kWarps) {
     const int4 ch = __ldg(a.chunks + c);
     const int n_lo = ch.x;
     const int nn = ch.y;     // 1..64 destinations
@@ -499,12 +504,17 @@ static int run_fwd(const void* P, long long ldp, const float* A, const float* be
                    const int* csr_src, const int* csr_rel, const int4* ch, int n_chunks, const int2* pt,
                    const int* long_node, const int* long_part_ptr, int n_long, float* part_ml, float* part_b,
                    float* part_acc, float* out, void* act_hi, void* act_lo, int apply_elu, float* alpha, float* z,
-                   float* minv, float* bias_out, int H, int F, int R, int sm_count, cudaStream_t s) {
+                   float* minv, float* bias_out, int H, int F, int R, int sm_count, int* work_counter,
+                   cudaStream_t s) {
   const int hg = pick_heads_per_warp(H, F, V, R, smem_budget_override("RELGAT_FWD_BUDGET_KB", kSmemBudgetA));
   if (!hg) return RG_ERR_SHAPE;
+  if (work_counter) {
+    cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int) * (H / hg), s);
+    if (e != cudaSuccess) return cuda_status(e);
+  }
   FwdArgs<T, V> a{static_cast<const T*>(P), A, beta, rowptr, csr_src, csr_rel, ch, pt, part_ml, part_b,
                   part_acc, out, static_cast<__nv_bfloat16*>(act_hi), static_cast<__nv_bfloat16*>(act_lo),
-                  alpha, z, minv, bias_out, n_chunks, H, F, R, hg, ldp, apply_elu, 0, 0};
+                  alpha, z, minv, bias_out, n_chunks, H, F, R, hg, ldp, apply_elu, 0, 0, work_counter};
   int rc = launch_fwd(a, sm_count, s);
   if (rc != RG_OK || n_long == 0) return rc;
   const int tasks = n_long * (H / hg);
@@ -520,7 +530,7 @@ extern "C" int relgat_layer_fwd(
     float* part_ml, float* part_b, float* part_acc,
     float* out, void* act_hi, void* act_lo, int apply_elu,
     float* alpha, float* z, float* minv, float* bias_out,
-    int H, int F, int R, int sm_count, void* stream) {
+    int H, int F, int R, int sm_count, int* work_counter, void* stream) {
   if (!P || !A || !rowptr || n_chunks < 0 || n_parts < 0 || n_long < 0 || H <= 0 || F <= 0 || R <= 0) return RG_ERR_ARG;
   if (n_chunks > 0 && !chunks) return RG_ERR_ARG;
   if (n_parts > 0 && (!parts || !long_node || !long_part_ptr || !part_ml || !part_b || !part_acc)) return RG_ERR_ARG;
@@ -535,13 +545,13 @@ extern "C" int relgat_layer_fwd(
     if (!vec_ok) return RG_ERR_ALIGN;
     return run_fwd<__nv_bfloat16, 8>(P, ldp, A, beta, rowptr, csr_src, csr_rel, ch, n_chunks, pt, long_node,
                                      long_part_ptr, n_long, part_ml, part_b, part_acc, out, act_hi, act_lo, apply_elu,
-                                     alpha, z, minv, bias_out, H, F, R, sm_count, s);
+                                     alpha, z, minv, bias_out, H, F, R, sm_count, work_counter, s);
   }
   if ((F % 4 == 0) && (ldp % 4 == 0) && vec_ok)
     return run_fwd<float, 4>(P, ldp, A, beta, rowptr, csr_src, csr_rel, ch, n_chunks, pt, long_node, long_part_ptr,
                              n_long, part_ml, part_b, part_acc, out, act_hi, act_lo, apply_elu, alpha, z, minv,
-                             bias_out, H, F, R, sm_count, s);
+                             bias_out, H, F, R, sm_count, work_counter, s);
   return run_fwd<float, 1>(P, ldp, A, beta, rowptr, csr_src, csr_rel, ch, n_chunks, pt, long_node, long_part_ptr,
                            n_long, part_ml, part_b, part_acc, out, act_hi, act_lo, apply_elu, alpha, z, minv,
-                           bias_out, H, F, R, sm_count, s);
+                           bias_out, H, F, R, sm_count, work_counter, s);
 }

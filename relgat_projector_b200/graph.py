@@ -15,7 +15,10 @@ import torch
 from . import _lib
 
 REL_CHUNK = 256  # edges per by-relation chunk of the dA / dbeta pass
-STREAM_CHUNK_EDGES = 64  # target edges per warp-chunk of the forward / by-source streaming kernels
+import os as _os
+
+# target edges per warp-chunk of the forward / by-source streaming kernels (env override: experiments)
+STREAM_CHUNK_EDGES = int(_os.environ.get("RELGAT_CHUNK_EDGES", "32"))
 STREAM_CHUNK_NODES = 64  # hard cap on segments per chunk (the kernels hold the pointer window in 3 registers)
 
 

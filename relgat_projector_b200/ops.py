@@ -6,6 +6,7 @@ torch.  CPU tensors are rejected (no fallback).
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -42,6 +43,13 @@ def _feat(t: torch.Tensor, name: str) -> torch.Tensor:
     if t.dtype not in (torch.float32, torch.bfloat16):
         raise TypeError(f"{name} must be float32 or bfloat16, got {t.dtype}")
     return t.contiguous()
+
+
+def _work_counter(device):
+    """32 ints of scratch for the dynamic chunk claim (zeroed by the C entry point on the launch stream)."""
+    if os.environ.get("RELGAT_STATIC_CHUNKS"):
+        return None
+    return torch.empty(32, dtype=torch.int32, device=device)
 
 
 def sm_count(device) -> int:
@@ -170,7 +178,8 @@ def edge_fwd(P: torch.Tensor, A: torch.Tensor, beta: Optional[torch.Tensor], g: 
             _lib.ptr(ck.long_node), _lib.ptr(ck.long_part_ptr), ck.n_long,
             _lib.ptr(part_ml), _lib.ptr(part_b), _lib.ptr(part_acc),
             _lib.ptr(out), _lib.ptr(hi), _lib.ptr(lo), int(apply_elu),
-            _lib.ptr(alpha), _lib.ptr(z), _lib.ptr(minv), _lib.ptr(bias), H, F, R, sm_count(dev), _stream(P))
+            _lib.ptr(alpha), _lib.ptr(z), _lib.ptr(minv), _lib.ptr(bias), H, F, R, sm_count(dev),
+            _lib.ptr(_work_counter(dev)), _stream(P))
     _lib.check(rc, "relgat_layer_fwd")
     _count(2 if ck.n_long else 1)
     return out, ((hi, lo) if want_act else None), alpha, z, minv, bias
@@ -221,7 +230,8 @@ def edge_bwd_src(P, G, A, z, minv, t, g: GraphIndex, H: int, F: int, want_fp32: 
             _lib.ptr(minv), _lib.ptr(t), _lib.ptr(g.colptr), _lib.ptr(g.csc_slot), _lib.ptr(g.csc_dst), _lib.ptr(g.csc_rel),
             _lib.ptr(ck.chunks), ck.n_chunks, _lib.ptr(ck.parts), ck.n_parts,
             _lib.ptr(ck.long_node), _lib.ptr(ck.long_part_ptr), ck.n_long, _lib.ptr(part_acc),
-            _lib.ptr(dP), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dz), H, F, g.R, sm_count(dev), _stream(P))
+            _lib.ptr(dP), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dz), H, F, g.R, sm_count(dev),
+            _lib.ptr(_work_counter(dev)), _stream(P))
     _lib.check(rc, "relgat_layer_bwd_src")
     _count(2 if ck.n_long else 1)
     return dP, ((hi, lo) if want_planes else None), dz

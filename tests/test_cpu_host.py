@@ -28,7 +28,7 @@ def test_library_loads_and_exports_header_symbols():
     assert lib.relgat_gemm_workspace_bytes(128, 128, 64, 0, 0, 1) == 0
     assert lib.relgat_gemm_workspace_bytes(128, 64, 640, 1, 1, 4) == 4 * 128 * 64 * 4
     assert lib.relgat_layer_fwd(None, 0, 0, None, None, None, None, None, None, 0, None, 0, None, None, 0, None, None,
-                                None, None, None, None, 0, None, None, None, None, 1, 4, 1, 148, None) == -1
+                                None, None, None, None, 0, None, None, None, None, 1, 4, 1, 148, None, None) == -1
     assert lib.relgat_score_fwd(7, 0, None, None, None, None, None, None, 1, 4, None, None, 0, None, None, None) == -1
 
 
