@@ -374,8 +374,12 @@ def main():
             ent["tensor_flops"] = flops
             ent["tflops"] = round(flops / (d["avg_ms"] * 1e-3) / 1e12, 1)
             ent["frac_tensor"] = round(ent["tflops"] / peaks["tflops"], 4)
+        if d["kernel"] == "edge_bwd_rel" or (d["kernel"] == "gemm" and tag.endswith("mnmn]")):
+            # the by-relation pass runs on a side stream beside the dW GEMM: both elapsed times include
+            # the other's interference (isolated: 0.69 ms at 96 % of HBM peak; 1.14 ms) — not "dominant"
+            ent["overlapped"] = True
         kernels[tag] = ent
-    top_tag = next(iter(kernels))
+    top_tag = next(t for t, e in kernels.items() if not e.get("overlapped"))
     top = kernels[top_tag]
     if "tflops" in top:
         roofline = {"kernel": top_tag, "bound": "tensor", "achieved": top["tflops"], "peak": peaks["tflops"],
