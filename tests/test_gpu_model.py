@@ -270,3 +270,30 @@ def test_training_trajectory_and_mrr_parity_with_oracle(dev):
     ranks = 1 + (neg >= pos.unsqueeze(1)).sum(1)
     rranks = 1 + (rneg.detach() >= rpos.detach().unsqueeze(1)).sum(1)
     assert int((ranks != rranks).sum()) <= 1
+
+
+def test_config5_imputation_and_relation_path_expansion(dev):
+    """BASELINE config 5: 20 % of the nodes masked (input row zeroed), full-graph forward + projection head,
+    then relation operators composed along paths of length 1-3 — against the oracle port."""
+    from relgat_projector_b200.inference import expand_relation_path, impute_masked_nodes
+    c = Case("transe_proj_fp32")
+    m = _load_model(c, dev).eval()
+    g = torch.Generator().manual_seed(0)
+    masked = torch.randperm(c.n, generator=g)[: c.n // 5]
+    rows = impute_masked_nodes(m, masked.to(dev))
+    x0 = c.t("x0").clone()
+    x0[masked] = 0
+    with torch.no_grad():
+        ref = O.projection_port(O.gat_stack_port(x0, c.layer_params(), c.edge_index(), c.t("rel")), c.proj_params())
+    assert rel_err(rows.cpu().numpy(), ref[masked].numpy()) < FP32_TOL
+    assert torch.equal(m.node_emb_fixed.cpu(), c.t("x0"))  # buffer restored
+    rel_emb = c.rel_emb()
+    for path in ([2], [0, 3], [1, 1, 4]):
+        got = expand_relation_path(m, rows, path)
+        want = ref[masked]
+        for r in path:
+            want = O.transform_port(c.scorer, want, rel_emb, torch.full((want.size(0),), r, dtype=torch.long))
+        assert rel_err(got.cpu().numpy(), want.numpy()) < FP32_TOL
+    # the unmasked forward is unchanged afterwards (input-plane cache was invalidated and rebuilt)
+    with torch.no_grad():
+        assert rel_err(m.get_node_repr().cpu().numpy(), c.z["x_final"]) < FP32_TOL
