@@ -161,6 +161,33 @@ int relgat_host_sample_batch(unsigned int* state, const long long* edges, long l
                              long long* src_out, long long* rel_out, long long* dst_out);
 int relgat_host_shuffle(unsigned int* state, long long* perm, long long n);
 
+/* ---- peer tables (host side; multi-GPU, one process per GPU) ----------------------------------
+ * The destination-range partition of BASELINE.json's north_star needs the transformed source rows
+ * of other ranks ("exchanged ... over NVLink"; the reference is single-device, its gather is
+ * core/model/layer.py:238-239 `Wh[src_ids]`).  Instead of a pack / all-gather / unpack step every rank
+ * keeps its rows in a peer table: one physical allocation per rank (cuMemCreate, exported as a POSIX
+ * file descriptor) and, in every process, ONE contiguous virtual range that maps all ranks' allocations
+ * back to back.  relgat_layer_fwd / relgat_layer_bwd_src / relgat_layer_bwd_rel then read that range
+ * through their ordinary row pointer: rows of a peer arrive by plain loads over NVLink / NVSwitch.
+ *   granularity: allocation sizes must be multiples of it.
+ *   create     : this rank's allocation of `bytes`; *fd is to be passed to the peers (SCM_RIGHTS).
+ *   map        : peer_fds[world] (entry `rank` ignored) -> *base, a range of world*bytes in which
+ *                slot s holds the table of rank (rank + s) % world (own table first), read/write.
+ *   unmap      : unmaps the range and releases this rank's allocation.
+ * The caller orders accesses across ranks (a stream-ordered NCCL collective between the writer's and
+ * the readers' kernels is enough).  last_driver_error: CUresult of the last failed driver call. */
+int relgat_peer_table_granularity(int device, unsigned long long* granularity);
+int relgat_peer_table_create(int device, unsigned long long bytes, unsigned long long* handle, int* fd);
+int relgat_peer_table_map(int device, int world, int rank, unsigned long long own_handle, const int* peer_fds,
+                          unsigned long long bytes, void** base);
+int relgat_peer_table_unmap(void* base, int world, unsigned long long bytes, unsigned long long own_handle);
+int relgat_peer_table_last_driver_error(void);
+/* halo pull (device): out[i, :] = table[ids[i], :] for i < n; ids int64 row numbers of the mapped range
+ * (a peer's rows arrive over NVLink), D floats per row, ld / ldo row strides in floats.  Run between the
+ * writers' rendezvous and the edge kernel that consumes [own rows | pulled rows]. */
+int relgat_pull_rows(const float* table, long long ld, const long long* ids, long long n, int D,
+                     float* out, long long ldo, int sm_count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

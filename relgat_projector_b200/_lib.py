@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes
 import os
 import re
-from ctypes import c_int, c_longlong, c_void_p
+from ctypes import c_int, c_longlong, c_ulonglong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librelgat_b200.so")
@@ -45,6 +45,12 @@ SIGNATURES = {
     "relgat_margin_loss": (_I, [_P, _I, _I, ctypes.c_float, _I, _P, _P, _P]),
     "relgat_host_sample_batch": (_I, [_P, _P, _L, _P, _I, _I, _L, _P, _P, _P]),
     "relgat_host_shuffle": (_I, [_P, _P, _L]),
+    "relgat_peer_table_granularity": (_I, [_I, _P]),
+    "relgat_peer_table_create": (_I, [_I, c_ulonglong, _P, _P]),
+    "relgat_peer_table_map": (_I, [_I, _I, _I, c_ulonglong, _P, c_ulonglong, _P]),
+    "relgat_peer_table_unmap": (_I, [_P, _I, c_ulonglong, c_ulonglong]),
+    "relgat_peer_table_last_driver_error": (_I, []),
+    "relgat_pull_rows": (_I, [_P, _L, _P, _L, _I, _P, _L, _I, _P]),
 }
 
 _lib = None

@@ -1,0 +1,196 @@
+// Peer tables: one row table per GPU, all of them mapped back to back into every process's address
+// space (CUDA virtual memory management), so an edge kernel on GPU a gathers rows owned by GPU b with
+// plain loads over NVLink/NVSwitch — no pack / exchange / unpack step and no staging copy.
+//
+// Replaces the feature all-gather of the destination-range partition (BASELINE.json north_star,
+// "transformed source features are exchanged ... over NVLink"; the reference itself is single-device,
+// SURVEY.md §2.5).  Host-side entry points; the device work is the unchanged edge kernels reading the
+// mapped range.  The driver API is reached through cudaGetDriverEntryPoint (no link-time libcuda).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "common.cuh"
+
+namespace {
+
+template <typename Fn>
+Fn driver_fn(const char* name) {
+  void* f = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &f, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+  if (q != cudaDriverEntryPointSuccess) return nullptr;
+  return reinterpret_cast<Fn>(f);
+}
+
+using GranFn = CUresult (*)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags);
+using CreateFn = CUresult (*)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long);
+using ExportFn = CUresult (*)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long);
+using ImportFn = CUresult (*)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType);
+using ReserveFn = CUresult (*)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long);
+using MapFn = CUresult (*)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long);
+using AccessFn = CUresult (*)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t);
+using UnmapFn = CUresult (*)(CUdeviceptr, size_t);
+using ReleaseFn = CUresult (*)(CUmemGenericAllocationHandle);
+using FreeVaFn = CUresult (*)(CUdeviceptr, size_t);
+
+CUmemAllocationProp table_prop(int device) {
+  CUmemAllocationProp prop = {};
+  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  prop.location.id = device;
+  prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  return prop;
+}
+
+int g_last_driver_error = 0;  // CUresult of the last failed driver call (diagnostics only)
+int drv(CUresult r) {
+  if (r == CUDA_SUCCESS) return 0;
+  g_last_driver_error = static_cast<int>(r);
+  return relgat::RG_ERR_DRIVER;
+}
+
+}  // namespace
+
+extern "C" int relgat_peer_table_last_driver_error(void) { return g_last_driver_error; }
+
+extern "C" int relgat_peer_table_granularity(int device, unsigned long long* granularity) {
+  if (!granularity) return relgat::RG_ERR_ARG;
+  auto fn = driver_fn<GranFn>("cuMemGetAllocationGranularity");
+  if (!fn) return relgat::RG_ERR_DRIVER;
+  if (cudaSetDevice(device) != cudaSuccess || cudaFree(nullptr) != cudaSuccess) return relgat::RG_ERR_DRIVER;
+  const CUmemAllocationProp prop = table_prop(device);
+  size_t g = 0;
+  if (int rc = drv(fn(&g, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED))) return rc;
+  *granularity = g;
+  return 0;
+}
+
+extern "C" int relgat_peer_table_create(int device, unsigned long long bytes, unsigned long long* handle, int* fd) {
+  if (!handle || !fd || bytes == 0) return relgat::RG_ERR_ARG;
+  auto create = driver_fn<CreateFn>("cuMemCreate");
+  auto exportfn = driver_fn<ExportFn>("cuMemExportToShareableHandle");
+  if (!create || !exportfn) return relgat::RG_ERR_DRIVER;
+  if (cudaSetDevice(device) != cudaSuccess || cudaFree(nullptr) != cudaSuccess) return relgat::RG_ERR_DRIVER;
+  const CUmemAllocationProp prop = table_prop(device);
+  CUmemGenericAllocationHandle h = 0;
+  if (int rc = drv(create(&h, bytes, &prop, 0))) return rc;
+  int out_fd = -1;
+  if (int rc = drv(exportfn(&out_fd, h, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0))) return rc;
+  *handle = h;
+  *fd = out_fd;
+  return 0;
+}
+
+// slot s of the mapped range holds the table of rank (rank + s) % world: every process sees its own table first
+extern "C" int relgat_peer_table_map(int device, int world, int rank, unsigned long long own_handle,
+                                     const int* peer_fds, unsigned long long bytes, void** base) {
+  if (!base || world < 1 || rank < 0 || rank >= world || bytes == 0 || (world > 1 && !peer_fds)) return relgat::RG_ERR_ARG;
+  auto importfn = driver_fn<ImportFn>("cuMemImportFromShareableHandle");
+  auto reserve = driver_fn<ReserveFn>("cuMemAddressReserve");
+  auto map = driver_fn<MapFn>("cuMemMap");
+  auto access = driver_fn<AccessFn>("cuMemSetAccess");
+  auto release = driver_fn<ReleaseFn>("cuMemRelease");
+  if (!importfn || !reserve || !map || !access || !release) return relgat::RG_ERR_DRIVER;
+  if (cudaSetDevice(device) != cudaSuccess || cudaFree(nullptr) != cudaSuccess) return relgat::RG_ERR_DRIVER;
+  CUdeviceptr va = 0;
+  if (int rc = drv(reserve(&va, bytes * world, 0, 0, 0))) return rc;
+  for (int s = 0; s < world; ++s) {
+    const int owner = (rank + s) % world;
+    CUmemGenericAllocationHandle h = own_handle;
+    if (owner != rank) {
+      if (int rc = drv(importfn(&h, reinterpret_cast<void*>(static_cast<uintptr_t>(peer_fds[owner])),
+                                CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR)))
+        return rc;
+    }
+    const int rc = drv(map(va + static_cast<CUdeviceptr>(s) * bytes, bytes, 0, h, 0));
+    if (owner != rank) release(h);  // the mapping keeps the peer's allocation alive
+    if (rc) return rc;
+  }
+  CUmemAccessDesc desc = {};
+  desc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  desc.location.id = device;
+  desc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  if (int rc = drv(access(va, bytes * world, &desc, 1))) return rc;
+  *base = reinterpret_cast<void*>(va);
+  return 0;
+}
+
+extern "C" int relgat_peer_table_unmap(void* base, int world, unsigned long long bytes, unsigned long long own_handle) {
+  auto unmap = driver_fn<UnmapFn>("cuMemUnmap");
+  auto release = driver_fn<ReleaseFn>("cuMemRelease");
+  auto freeva = driver_fn<FreeVaFn>("cuMemAddressFree");
+  if (!unmap || !release || !freeva) return relgat::RG_ERR_DRIVER;
+  int rc = 0;
+  if (base) {
+    const CUdeviceptr va = reinterpret_cast<CUdeviceptr>(base);
+    rc |= drv(unmap(va, bytes * world));
+    rc |= drv(freeva(va, bytes * world));
+  }
+  if (own_handle) rc |= drv(release(own_handle));
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------
+// halo pull: out[i, :] = table[ids[i], :] — the rows of other ranks that this rank's edges reference,
+// read from the mapped peer tables (NVLink) into local memory ahead of the edge kernel.  Each thread
+// keeps kPullUnroll independent 16-byte loads in flight: the link is latency-bound (~3 us), the
+// kernel needs megabytes in flight to fill it.  (`prefetch.global.L2` on a peer address is NOT an
+// option: measured 70x slower than plain loads — profiles/r01_summary.md.)
+// ------------------------------------------------------------------------------------
+namespace relgat {
+
+static inline bool al16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; }
+
+constexpr int kPullUnroll = 4;
+constexpr int kPullThreads = 256;
+
+template <int V>
+__global__ void __launch_bounds__(kPullThreads)
+pull_rows_kernel(const float* __restrict__ table, long long ld, const long long* __restrict__ ids, long long n, int D,
+                 float* __restrict__ out, long long ldo) {
+  const int dv = D / V;  // vectors per row
+  const long long total = n * dv;
+  const long long stride = static_cast<long long>(gridDim.x) * kPullThreads;
+  for (long long base = static_cast<long long>(blockIdx.x) * kPullThreads + threadIdx.x; base < total;
+       base += stride * kPullUnroll) {
+    float v[kPullUnroll][V];
+    long long row[kPullUnroll];
+    int q[kPullUnroll];
+#pragma unroll
+    for (int u = 0; u < kPullUnroll; ++u) {
+      const long long idx = base + u * stride;
+      row[u] = -1;
+      if (idx < total) {
+        row[u] = idx / dv;
+        q[u] = static_cast<int>(idx - row[u] * dv);
+        RowVec<float, V>::load_stream(table + __ldg(ids + row[u]) * ld + q[u] * V, v[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kPullUnroll; ++u)
+      if (row[u] >= 0) RowVec<float, V>::store(out + row[u] * ldo + q[u] * V, v[u]);
+  }
+}
+
+}  // namespace relgat
+
+extern "C" int relgat_pull_rows(const float* table, long long ld, const long long* ids, long long n, int D,
+                                float* out, long long ldo, int sm_count, void* stream) {
+  using namespace relgat;
+  if (n < 0 || D <= 0 || ld < D || ldo < D) return RG_ERR_ARG;
+  if (n == 0) return RG_OK;
+  if (!table || !ids || !out) return RG_ERR_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool vec = D % 4 == 0 && ld % 4 == 0 && ldo % 4 == 0 && al16(table) && al16(out);
+  const long long total = n * (vec ? D / 4 : D);
+  const long long want = (total + static_cast<long long>(kPullThreads) * kPullUnroll - 1) / (kPullThreads * kPullUnroll);
+  const long long cap = static_cast<long long>(sm_count > 0 ? sm_count : 148) * 8;  // 8 resident CTAs of 256 threads per SM
+  const unsigned blocks = static_cast<unsigned>(want < cap ? (want > 0 ? want : 1) : cap);
+  if (vec)
+    pull_rows_kernel<4><<<blocks, kPullThreads, 0, s>>>(table, ld, ids, n, D, out, ldo);
+  else
+    pull_rows_kernel<1><<<blocks, kPullThreads, 0, s>>>(table, ld, ids, n, D, out, ldo);
+  return cuda_status(cudaGetLastError());
+}

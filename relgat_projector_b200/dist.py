@@ -360,7 +360,16 @@ def bench_main(args, cfg, rank, world, local_rank, metric, unit, load_peaks, Clo
     n_nodes, n_trip = (cfg["N"], cfg["T"]) if strong else (cfg["N"] * world, cfg["T"] * world)
     kg = S.tensor_kg(n_nodes, n_trip, cfg["R"], cfg["D_in"], seed=42, device=str(dev))
     E = int(kg.edge_index.size(1))
-    part = DstPartition(kg.edge_index, kg.edge_type, n_nodes, cfg["R"], rank, world)
+    exchange = getattr(args, "exchange", "peer")
+    if args.precision != "fp32" and exchange == "peer":
+        exchange = "halo"
+    if exchange == "peer":  # rows of other ranks are read in place over NVLink (peer.py); no exchange step
+        from . import peer as RP
+        part = RP.PeerPartition(kg.edge_index, kg.edge_type, n_nodes, cfg["R"], rank, world,
+                                RP.PeerTables(world, rank, dev), cfg["H"], cfg["F"], cfg["L"])
+        part.E_local = part.E_fwd
+    else:
+        part = DstPartition(kg.edge_index, kg.edge_type, n_nodes, cfg["R"], rank, world, mode=exchange)
     x0_local = kg.node_emb[part.lo:part.hi].clone()  # this rank's rows of the frozen embeddings
     kg.node_emb = None
     torch.cuda.empty_cache()
@@ -368,7 +377,10 @@ def bench_main(args, cfg, rank, world, local_rank, metric, unit, load_peaks, Clo
     model = R.RelGATModel(x0_local, kg.edge_index[:, :1], kg.edge_type[:1], num_rel=cfg["R"],
                           scorer_type=cfg["scorer"], gat_out_dim=cfg["F"], gat_heads=cfg["H"], dropout=0.0,
                           gat_num_layers=cfg["L"], precision=args.precision).to(dev)
-    prg = PartitionedRelGAT(model, part, x0_local=model.node_emb_fixed)
+    if exchange == "peer":
+        prg = RP.PeerRelGAT(model, part, model.node_emb_fixed)
+    else:
+        prg = PartitionedRelGAT(model, part, x0_local=model.node_emb_fixed)
     model.train()
     opt = torch.optim.Adam(model.parameters(), lr=2e-4)
     rank_loss = L.RelGATLoss("margin", None, 1.0, None, {})
@@ -419,6 +431,19 @@ def bench_main(args, cfg, rank, world, local_rank, metric, unit, load_peaks, Clo
     dist.all_gather(e_all, e_local)
     if rank == 0:
         C = cfg["H"] * cfg["F"]
+        if exchange == "peer":
+            par = (f"dst-range partition x{world}; halo rows pulled by one gather kernel from peer tables mapped over "
+                   f"NVLink (no pack / collective / unpack); fwd by destination owner, bwd by source owner (no "
+                   f"cross-rank sum of dP); all-reduce of parameter grads")
+            extra = {"halo_rows_fwd_rank0": part.n_halo_f, "halo_rows_bwd_rank0": part.n_halo_b,
+                     "local_rows_rank0": part.n_local,
+                     "nvlink_bytes_per_layer_pass_rank0": max(part.n_halo_f, part.n_halo_b) * C * 4}
+        else:
+            par = (f"dst-range partition x{world}, NCCL {'all-to-all of halo rows' if exchange == 'halo' else 'all-gather'} "
+                   f"of P fwd / of dP bwd, all-reduce of parameter grads")
+            extra = {"halo_rows_rank0": getattr(part, "n_halo", None), "local_rows_rank0": part.n_local,
+                     "exchange_bytes_per_layer_per_rank": getattr(part, "n_halo", 0) * C * 4,
+                     "allgather_equivalent_bytes": (world - 1) * part.max_rows * C * 4}
         line = {
             "metric": metric, "value": E / (ms * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if strong else "weak",
@@ -427,12 +452,8 @@ def bench_main(args, cfg, rank, world, local_rank, metric, unit, load_peaks, Clo
             "config": {"workload": f"{cfg['name']}{'' if strong else ' x' + str(world)}: synthetic KG {n_nodes} nodes / {n_trip} triplets ({E} "
                                    f"message-passing edges) / {cfg['R']} relations, {cfg['D_in']}-d, {cfg['L']} layers, "
                                    f"{cfg['H']} heads, gat-out-dim {cfg['F']}, {cfg['scorer']}, batch {b}, num-neg {k}",
-                       "parallelism": f"dst-range partition x{world}, NCCL all-to-all of halo rows of P fwd / of dP bwd, "
-                                      f"all-reduce of parameter grads",
-                       "edges_per_rank": [int(t.item()) for t in e_all],
-                       "halo_rows_rank0": part.n_halo, "local_rows_rank0": part.n_local,
-                       "exchange_bytes_per_layer_per_rank": part.n_halo * C * 4,
-                       "allgather_equivalent_bytes": (world - 1) * part.max_rows * C * 4,
+                       "parallelism": par, "exchange": exchange,
+                       "edges_per_rank": [int(t.item()) for t in e_all], **extra,
                        "l2": "inputs_exceed_L2"},
             "clocks": clocks.summary(),
             "e2e": {"value": E / (ms_e2e * 1e-3), "unit": unit, "ms_per_step": ms_e2e,

@@ -94,9 +94,12 @@ class GraphIndex:
     """All integer structures of one message-passing graph, as int32 CUDA tensors."""
 
     def __init__(self, edge_index: torch.Tensor, edge_type: torch.Tensor, num_nodes: int, num_rel: int,
-                 validate: bool = True, num_src_nodes: Optional[int] = None):
+                 validate: bool = True, num_src_nodes: Optional[int] = None,
+                 fwd_chunks: bool = True, src_chunks: bool = True):
         """``num_nodes`` = destination rows (segments); ``num_src_nodes`` = rows of the feature matrix
-        the sources index (defaults to ``num_nodes``; larger on a destination-range partition)."""
+        the sources index (defaults to ``num_nodes``; larger on a destination-range partition).
+        ``fwd_chunks`` / ``src_chunks``: build the work tables of the forward / by-source kernel (a
+        partitioned graph that only ever runs one of the two skips the other)."""
         _lib.require_cuda(edge_index, edge_type)
         if edge_index.dim() != 2 or edge_index.size(0) != 2:
             raise ValueError("edge_index must have shape [2, E]")
@@ -137,8 +140,8 @@ class GraphIndex:
                 _lib.ptr(ws), ws_bytes, stream)
         _lib.check(rc, "relgat_graph_index_build")
         self._build_rel_chunks()
-        self.fwd_chunks = StreamChunks(self.rowptr)
-        self.src_chunks = StreamChunks(self.colptr)
+        self.fwd_chunks = StreamChunks(self.rowptr) if fwd_chunks else None
+        self.src_chunks = StreamChunks(self.colptr) if src_chunks else None
         self.max_in_degree = int((self.rowptr[1:] - self.rowptr[:-1]).max().item()) if N > 0 else 0
         self.max_out_degree = int((self.colptr[1:] - self.colptr[:-1]).max().item()) if NS > 0 else 0
         del ws

@@ -52,6 +52,16 @@ def _work_counter(device):
     return torch.empty(32, dtype=torch.int32, device=device)
 
 
+def _out_buf(buf: Optional[torch.Tensor], shape, device, name: str) -> torch.Tensor:
+    """A fresh fp32 output, or the caller's buffer after checking it can be written in place."""
+    if buf is None:
+        return torch.empty(shape, dtype=torch.float32, device=device)
+    _lib.require_cuda(buf)
+    if buf.dtype != torch.float32 or tuple(buf.shape) != tuple(shape) or not buf.is_contiguous():
+        raise ValueError(f"{name} must be a contiguous float32 tensor of shape {tuple(shape)}, got {tuple(buf.shape)}")
+    return buf
+
+
 def sm_count(device) -> int:
     return torch.cuda.get_device_properties(device).multi_processor_count
 
@@ -146,9 +156,11 @@ def pick_splits_k(M: int, N: int, K: int, device) -> int:
 # ------------------------------------------------------------------------------------------
 def edge_fwd(P: torch.Tensor, A: torch.Tensor, beta: Optional[torch.Tensor], g: GraphIndex, H: int, F: int,
              want_act: bool = False, apply_elu: bool = False, act_lo: bool = True, want_out: bool = True,
-             want_alpha: bool = False):
+             want_alpha: bool = False, z_out: Optional[torch.Tensor] = None,
+             minv_out: Optional[torch.Tensor] = None, out_buf: Optional[torch.Tensor] = None):
     """Returns (out [N, H*F] fp32 or None, act planes or None, alpha [E,H] or None, z [E,H],
-    minv [N,H,2], bias [N])."""
+    minv [N,H,2], bias [N]).  ``z_out`` / ``minv_out`` / ``out_buf``: caller-owned buffers for the saved
+    statistics and the output rows (rows of a peer table on the partitioned path)."""
     P = _feat(P, "P")
     A = _f32c(A, "A")
     if beta is not None:
@@ -159,12 +171,12 @@ def edge_fwd(P: torch.Tensor, A: torch.Tensor, beta: Optional[torch.Tensor], g: 
         raise ValueError(f"P must be [{g.N_src}, {C}], got {tuple(P.shape)}")
     if tuple(A.shape) != (H, R, F):
         raise ValueError(f"A must be [{H}, {R}, {F}], got {tuple(A.shape)}")
-    out = torch.empty((N, C), dtype=torch.float32, device=dev) if want_out else None
+    out = _out_buf(out_buf, (N, C), dev, "out_buf") if want_out else None
     hi = torch.empty((N, C), dtype=torch.bfloat16, device=dev) if want_act else None
     lo = torch.empty((N, C), dtype=torch.bfloat16, device=dev) if (want_act and act_lo) else None
     alpha = torch.empty((E, H), dtype=torch.float32, device=dev) if want_alpha else None
-    z = torch.empty((E, H), dtype=torch.float32, device=dev)
-    minv = torch.empty((N, H, 2), dtype=torch.float32, device=dev)
+    z = _out_buf(z_out, (E, H), dev, "z_out")
+    minv = _out_buf(minv_out, (N, H, 2), dev, "minv_out")
     bias = torch.empty((N,), dtype=torch.float32, device=dev)
     ck = g.fwd_chunks
     part_ml = torch.empty((ck.n_parts, H, 2), dtype=torch.float32, device=dev) if ck.n_parts else None
@@ -186,18 +198,24 @@ def edge_fwd(P: torch.Tensor, A: torch.Tensor, beta: Optional[torch.Tensor], g: 
 
 
 def edge_bwd_prep(dY: torch.Tensor, out: torch.Tensor, bias: torch.Tensor, H: int, F: int,
-                  apply_elu: bool, inplace: bool = False, g_bf16: bool = False):
-    """Returns (G [N,C] fp32 or bf16, t [N,H], hsum [N,H])."""
+                  apply_elu: bool, inplace: bool = False, g_bf16: bool = False,
+                  G_out: Optional[torch.Tensor] = None, t_out: Optional[torch.Tensor] = None,
+                  hsum_out: Optional[torch.Tensor] = None):
+    """Returns (G [N,C] fp32 or bf16, t [N,H], hsum [N,H]).  ``G_out`` / ``t_out`` / ``hsum_out``:
+    caller-owned fp32 buffers (rows of a peer table on the partitioned path)."""
     dY = _f32c(dY, "dY")
     out = _f32c(out, "out")
     N = out.size(0)
-    if g_bf16:
+    if G_out is not None:
+        G = _out_buf(G_out, tuple(dY.shape), dY.device, "G_out")
+        g_bf16 = False
+    elif g_bf16:
         G = torch.empty(dY.shape, dtype=torch.bfloat16, device=dY.device)
     else:
         # without an activation G == dY: nothing to write, alias it (saves a full [N, C] copy)
         G = dY if (inplace or not apply_elu) else torch.empty_like(dY)
-    t = torch.empty((N, H), dtype=torch.float32, device=dY.device)
-    hsum = torch.empty((N, H), dtype=torch.float32, device=dY.device)
+    t = _out_buf(t_out, (N, H), dY.device, "t_out")
+    hsum = _out_buf(hsum_out, (N, H), dY.device, "hsum_out")
     with torch.cuda.device(dY.device):
         rc = _lib.load().relgat_layer_bwd_prep(_lib.ptr(dY), _lib.ptr(out), _lib.ptr(bias), _lib.ptr(G), int(g_bf16),
                                                _lib.ptr(t), _lib.ptr(hsum), N, H, F, int(apply_elu), _stream(dY))
@@ -346,3 +364,23 @@ def margin_loss(score: torch.Tensor, B: int, K: int, margin: float, projection_l
     _lib.check(rc, "relgat_margin_loss")
     _count(1)
     return loss, dscore
+
+
+def pull_rows(table: torch.Tensor, ids: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[i] = table[ids[i]] (rows of a mapped peer table -> local rows).  ``table`` / ``out``: fp32 with
+    unit inner stride, any number of trailing dims (flattened); ``ids`` int64."""
+    _lib.require_cuda(table, ids, out)
+    if table.dtype != torch.float32 or out.dtype != torch.float32 or ids.dtype != torch.int64:
+        raise TypeError("pull_rows: table / out must be float32 and ids int64")
+    n = int(ids.numel())
+    D = int(table[0].numel()) if table.size(0) else int(out[0].numel())
+    if out.size(0) != n or (n and int(out[0].numel()) != D) or not table.is_contiguous() or not out.is_contiguous():
+        raise ValueError("pull_rows: out must be a contiguous [len(ids), ...] tensor with the table's row shape")
+    if n == 0:
+        return out
+    with torch.cuda.device(out.device):
+        rc = _lib.load().relgat_pull_rows(_lib.ptr(table), D, _lib.ptr(ids.contiguous()), n, D, _lib.ptr(out), D,
+                                          sm_count(out.device), _stream(out))
+    _lib.check(rc, "relgat_pull_rows")
+    _count(1)
+    return out

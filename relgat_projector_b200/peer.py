@@ -1,0 +1,474 @@
+"""Destination-range partition over peer tables: the multi-GPU path without an exchange step.
+
+BASELINE.json's north_star partitions the graph by destination range and moves the transformed source
+rows between GPUs over NVLink.  Here every rank keeps the rows other ranks need (projected features P,
+output gradients G, per-node softmax statistics, raw logits) in *peer tables*
+(``csrc/peer_table.cu``): one allocation per rank, all of them mapped back to back into every process.
+The unchanged edge kernels gather a peer's rows with plain loads over NVLink / NVSwitch while they
+compute — there is no pack / all-gather / unpack and no reduction of partial results.  One gather
+kernel per edge pass pulls the distinct rows a rank's edges reference into its own table ahead of the
+edge kernel ([own rows | pulled rows]): reading them in place from inside the edge kernel moves every
+row once per EDGE instead of once per distinct row and cannot use the kernels' L2 prefetch
+(`prefetch.global.L2` on a peer address measured 70x slower than a plain load):
+
+* forward:  a rank owns a destination range and the in-edges of those destinations; sources are
+  read from the mapped P table (global row ids).
+* backward: a rank owns the SAME node range as sources and processes their out-edges (by-source pass
+  and by-relation pass), reading G / t / hsum / softmax statistics of the destinations and the saved
+  logits from the mapped tables.  Every dP row is complete on its owner: no cross-rank sum.  Forward node
+  rows are bit-identical to one GPU; gradients agree to rounding (a source's out-edges are summed in the
+  order of the renumbered destinations).
+
+Ordering across ranks is a stream-ordered NCCL all-reduce of one integer after each writer kernel
+(``sync``): a reader kernel enqueued behind it cannot start before every rank's writer has finished.
+Parameter gradients are per-rank partial sums, all-reduced once per step (``dist.allreduce_grads``).
+
+``mode="sim"`` keeps all ranks' tables in one ordinary tensor of one process: the index logic and the
+numerics of a W-rank run are then testable on a single GPU by stepping the W rank programs in
+lock-step (``tests/test_gpu_model.py``)."""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+import socket
+import threading
+import time
+from typing import Dict, Generator, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+from .dist import allreduce_grads, partition_bounds
+from .functional import _side_stream
+from .graph import GraphIndex
+
+
+# ---------------------------------------------------------------------------------------------
+# peer tables
+# ---------------------------------------------------------------------------------------------
+class PeerTable:
+    """``whole`` [world * stride_rows, *row_shape]: every rank's table, this rank's rows in
+    ``local`` (a view).  ``slot_of[g]`` = position of rank g's table inside ``whole``."""
+
+    def __init__(self, whole: torch.Tensor, stride_rows: int, slot_of: List[int], rank: int):
+        self.whole, self.stride_rows, self.slot_of = whole, stride_rows, slot_of
+        s = slot_of[rank]
+        self.local = whole[s * stride_rows:(s + 1) * stride_rows]
+
+
+class _DevicePointer:
+    """Minimal __cuda_array_interface__ carrier: lets torch wrap a mapped range without copying."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+def _exchange_fds(my_fds: List[int], world: int, rank: int, tag: str) -> List[List[int]]:
+    """Every rank hands its file descriptors to every peer over AF_UNIX sockets (SCM_RIGHTS)."""
+    base = f"/tmp/relgat_peer_{os.environ.get('MASTER_PORT', '0')}_{tag}"
+    path = f"{base}_{rank}.sock"
+    if os.path.exists(path):
+        os.unlink(path)
+    srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    srv.bind(path)
+    srv.listen(world)
+
+    def serve():
+        for _ in range(world - 1):
+            conn, _addr = srv.accept()
+            with conn:
+                socket.send_fds(conn, [b"f"], my_fds)
+                conn.recv(1)  # the peer confirms it holds the descriptors before we move on
+
+    th = threading.Thread(target=serve, daemon=True)
+    th.start()
+    got: List[List[int]] = [[] for _ in range(world)]
+    for g in range(world):
+        if g == rank:
+            continue
+        peer_path = f"{base}_{g}.sock"
+        deadline = time.time() + 120
+        while True:
+            try:
+                c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+                c.connect(peer_path)
+                break
+            except (FileNotFoundError, ConnectionRefusedError):
+                c.close()
+                if time.time() > deadline:
+                    raise RuntimeError(f"peer table exchange: rank {g} never opened {peer_path}")
+                time.sleep(0.05)
+        with c:
+            _msg, fds, _flags, _addr = socket.recv_fds(c, 16, len(my_fds))
+            if len(fds) != len(my_fds):
+                raise RuntimeError("peer table exchange: short descriptor list")
+            got[g] = list(fds)
+            c.send(b"k")
+    th.join()
+    srv.close()
+    os.unlink(path)
+    return got
+
+
+class PeerTables:
+    """Allocator of peer tables.  mode "vmm": real peer mapping (one process per GPU);
+    mode "sim": all ranks' tables inside one tensor shared through ``sim_store`` (tests)."""
+
+    def __init__(self, world: int, rank: int, device, mode: str = "vmm", sim_store: Optional[dict] = None):
+        if mode not in ("vmm", "sim"):
+            raise ValueError("mode must be 'vmm' or 'sim'")
+        self.world, self.rank, self.device, self.mode = world, rank, torch.device(device), mode
+        self.sim_store = sim_store if sim_store is not None else {}
+        self._mapped: List[Tuple[int, int, int]] = []  # (base, bytes, handle)
+        self._keep: List[object] = []
+        if mode == "vmm":
+            g = ctypes.c_ulonglong(0)
+            _lib.check(_lib.load().relgat_peer_table_granularity(self._dev_index(), ctypes.byref(g)),
+                       "relgat_peer_table_granularity")
+            self.granularity = int(g.value)
+            self.slot_of = [(o - rank) % world for o in range(world)]  # own table first
+        else:
+            self.granularity = 1
+            self.slot_of = list(range(world))
+
+    def _dev_index(self) -> int:
+        return self.device.index if self.device.index is not None else torch.cuda.current_device()
+
+    def stride_rows(self, min_rows: int, row_bytes: Sequence[int]) -> int:
+        """Smallest row count >= min_rows whose byte size is a granularity multiple for every row size."""
+        m = 1
+        for b in row_bytes:
+            m = math.lcm(m, self.granularity // math.gcd(self.granularity, b))
+        return max(1, -(-max(min_rows, 1) // m)) * m
+
+    def allocate(self, specs: Sequence[Tuple[str, int, Tuple[int, ...], torch.dtype]], tag: str = "t") -> Dict[str, PeerTable]:
+        """specs: (name, stride_rows, row_shape, dtype).  Collective over all ranks in mode "vmm"."""
+        out: Dict[str, PeerTable] = {}
+        if self.mode == "sim":
+            for name, stride, row_shape, dtype in specs:
+                key = (tag, name)
+                if key not in self.sim_store:
+                    self.sim_store[key] = torch.zeros((self.world * stride, *row_shape), dtype=dtype, device=self.device)
+                out[name] = PeerTable(self.sim_store[key], stride, self.slot_of, self.rank)
+            return out
+        lib = _lib.load()
+        dev = self._dev_index()
+        handles, fds, sizes = [], [], []
+        for name, stride, row_shape, dtype in specs:
+            nbytes = stride * int(torch.tensor([], dtype=dtype).element_size()) * int(math.prod(row_shape))
+            if nbytes % self.granularity:
+                raise ValueError(f"peer table {name}: {nbytes} bytes is not a multiple of {self.granularity}")
+            h, fd = ctypes.c_ulonglong(0), ctypes.c_int(-1)
+            rc = lib.relgat_peer_table_create(dev, nbytes, ctypes.byref(h), ctypes.byref(fd))
+            self._check(rc, f"relgat_peer_table_create({name})")
+            handles.append(int(h.value))
+            fds.append(int(fd.value))
+            sizes.append(nbytes)
+        peer_fds = _exchange_fds(fds, self.world, self.rank, tag) if self.world > 1 else [[]]
+        for i, (name, stride, row_shape, dtype) in enumerate(specs):
+            arr = (ctypes.c_int * self.world)(*[(peer_fds[g][i] if g != self.rank else -1) for g in range(self.world)])
+            base = ctypes.c_void_p(0)
+            rc = lib.relgat_peer_table_map(dev, self.world, self.rank, handles[i], arr, sizes[i], ctypes.byref(base))
+            self._check(rc, f"relgat_peer_table_map({name})")
+            self._mapped.append((int(base.value), sizes[i], handles[i]))
+            carrier = _DevicePointer(int(base.value), self.world * sizes[i])
+            self._keep.append(carrier)
+            raw = torch.as_tensor(carrier, device=self.device)
+            whole = raw.view(dtype).view(self.world * stride, *row_shape)
+            out[name] = PeerTable(whole, stride, self.slot_of, self.rank)
+        for lst in peer_fds:
+            for fd in lst:
+                os.close(fd)
+        for fd in fds:
+            os.close(fd)
+        return out
+
+    @staticmethod
+    def _check(rc: int, what: str) -> None:
+        if rc != 0:
+            drv = _lib.load().relgat_peer_table_last_driver_error()
+            raise RuntimeError(f"{what} failed: rc={rc}, CUresult={drv} (peer tables need CUDA VMM with "
+                               "POSIX file-descriptor handles and peer access between the GPUs)")
+
+    def close(self) -> None:
+        lib = _lib.load()
+        for base, nbytes, handle in self._mapped:
+            lib.relgat_peer_table_unmap(ctypes.c_void_p(base), self.world, nbytes, handle)
+        self._mapped.clear()
+
+
+# ---------------------------------------------------------------------------------------------
+# the partition: forward graph (in-edges of my destinations), backward graph (out-edges of my sources)
+# ---------------------------------------------------------------------------------------------
+class PeerPartition:
+    """Index structures of one rank.  A node table of rank g holds [own rows | pulled rows]; row v of the
+    mapped range = slot_of[owner(v)] * stride_rows + (v - lo_owner).
+
+    forward graph : in-edges of my destinations; sources renumbered into [own | forward halo]
+    backward graph: out-edges of my sources;     destinations renumbered into [own | backward halo]"""
+
+    def __init__(self, edge_index: torch.Tensor, edge_type: torch.Tensor, num_nodes: int, num_rel: int,
+                 rank: int, world: int, tables: PeerTables, heads: int, out_dim: int, num_layers: int,
+                 balance: str = "edges", tag: str = "p"):
+        self.rank, self.world, self.N, self.R = rank, world, int(num_nodes), int(num_rel)
+        self.H, self.F, self.L = heads, out_dim, num_layers
+        self.tables = tables
+        dev = edge_index.device
+        src, dst = edge_index[0], edge_index[1]
+        E = int(src.numel())
+        self.bounds = partition_bounds(dst, self.N, world, balance)
+        self.lo, self.hi = self.bounds[rank], self.bounds[rank + 1]
+        self.n_local = n = self.hi - self.lo
+        C = heads * out_dim
+        starts = torch.tensor(self.bounds[:-1], device=dev, dtype=torch.int64)
+        inner = torch.tensor(self.bounds[1:-1], device=dev, dtype=torch.int64)
+        slot_of = torch.tensor(tables.slot_of, device=dev, dtype=torch.int64)
+
+        def owner_of(ids):
+            return torch.bucketize(ids, inner, right=True) if world > 1 else torch.zeros_like(ids)
+
+        def halo_of(g: int):
+            """(edges into g's range, their remote sources, edges out of g's range, their remote destinations)"""
+            lo_g, hi_g = self.bounds[g], self.bounds[g + 1]
+            in_f = (dst >= lo_g) & (dst < hi_g)
+            in_b = (src >= lo_g) & (src < hi_g)
+            hf = torch.unique(src[in_f & ~in_b])  # sorted ascending = grouped by owner
+            hb = torch.unique(dst[in_b & ~in_f])
+            return in_f, hf, in_b, hb
+
+        in_f, halo_f, in_b, halo_b = halo_of(rank)
+        self.n_halo_f, self.n_halo_b = int(halo_f.numel()), int(halo_b.numel())
+        need = n + max(self.n_halo_f, self.n_halo_b)
+        if world > 1 and tables.mode == "vmm":  # all ranks must agree on the table stride
+            t = torch.tensor([need], device=dev, dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            need = int(t.item())
+        elif world > 1:  # single-process simulation: look at every rank's halo
+            for g in range(world):
+                if g != rank:
+                    _, hf, _, hb = halo_of(g)
+                    need = max(need, self.bounds[g + 1] - self.bounds[g] + max(int(hf.numel()), int(hb.numel())))
+        self.stride_rows = tables.stride_rows(need, [4 * C, 4 * heads, 8 * heads])
+
+        def row_id(ids):
+            own = owner_of(ids)
+            return slot_of[own] * self.stride_rows + (ids - starts[own])
+
+        def renumber(ids, halo):
+            mine = (ids >= self.lo) & (ids < self.hi)
+            return torch.where(mine, ids - self.lo, n + torch.searchsorted(halo, ids))
+
+        self.owner_of, self.row_id = owner_of, row_id
+        self.pull_f, self.pull_b = row_id(halo_f), row_id(halo_b)  # rows of the mapped range to pull
+        # forward: in-edges of my destinations, original order (stable bucketing)
+        sel_f = torch.nonzero(in_f).flatten()
+        self.E_fwd = int(sel_f.numel())
+        self.fwd_graph = GraphIndex(torch.stack([renumber(src[sel_f], halo_f), dst[sel_f] - self.lo]), edge_type[sel_f],
+                                    max(n, 1), self.R, num_src_nodes=max(n + self.n_halo_f, 1), src_chunks=False)
+        # backward: out-edges of my sources
+        sel_b = torch.nonzero(in_b).flatten()
+        self.E_bwd = int(sel_b.numel())
+        self.bwd_graph = GraphIndex(torch.stack([src[sel_b] - self.lo, renumber(dst[sel_b], halo_b)]), edge_type[sel_b],
+                                    max(n + self.n_halo_b, 1), self.R, num_src_nodes=max(n, 1), fwd_chunks=False)
+        # where the forward pass of the destination's owner stored the logit of each of my out-edges:
+        # the owner's CSR order is the global stable by-destination order restricted to its range
+        own_dst = owner_of(dst)
+        per_owner = torch.bincount(own_dst, minlength=world)
+        first = torch.cumsum(per_owner, 0) - per_owner
+        order = torch.argsort(dst, stable=True)
+        pos = torch.empty(E, dtype=torch.int64, device=dev)
+        pos[order] = torch.arange(E, device=dev)
+        self.stride_slots = tables.stride_rows(int(per_owner.max().item()) if E else 1, [4 * heads])
+        z_row = slot_of[own_dst] * self.stride_slots + (pos - first[own_dst])
+        self.z_index = z_row[sel_b][self.bwd_graph.csr_perm.long()].contiguous()  # by slot of the backward graph
+        specs = []
+        for l in range(num_layers):
+            specs += [(f"P{l}", self.stride_rows, (C,), torch.float32), (f"G{l}", self.stride_rows, (C,), torch.float32),
+                      (f"minv{l}", self.stride_rows, (heads, 2), torch.float32),
+                      (f"t{l}", self.stride_rows, (heads,), torch.float32),
+                      (f"hsum{l}", self.stride_rows, (heads,), torch.float32),
+                      (f"z{l}", self.stride_slots, (heads,), torch.float32)]
+        specs.append(("out", self.stride_rows, (C,), torch.float32))
+        self.t = tables.allocate(specs, tag=tag)
+        self._token = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def sync(self) -> None:
+        """Stream-ordered rendezvous of all ranks (see module docstring)."""
+        if self.tables.mode == "vmm" and self.world > 1:
+            dist.all_reduce(self._token)
+
+    def pull(self, name: str, ids: torch.Tensor) -> torch.Tensor:
+        """Fills the halo rows of table ``name`` from their owners; returns the [own | halo] view."""
+        tb, n = self.t[name], self.n_local
+        k = int(ids.numel())
+        ops.pull_rows(tb.whole, ids, tb.local[n:n + k])
+        return tb.local[:n + k]
+
+
+# ---------------------------------------------------------------------------------------------
+# the rank program: generators that yield where all ranks must have finished the previous phase
+# ---------------------------------------------------------------------------------------------
+def forward_steps(part: PeerPartition, planes, params: Sequence[torch.Tensor], with_lo: bool, saved: list,
+                  x0_needs_grad: bool = False) -> Generator[None, None, torch.Tensor]:
+    H, F, L = part.H, part.F, part.L
+    C, n = H * F, part.n_local
+    T = part.t
+    out = None
+    for l in range(L):
+        W, A, beta = params[3 * l], params[3 * l + 1], params[3 * l + 2]
+        d_in = W.size(1)
+        Wp = ops.split_bf16(W.detach(), with_lo)
+        WTp = ops.split_bf16(W.detach().t().contiguous(), with_lo) if (l > 0 or x0_needs_grad) else None
+        ops.gemm(planes, False, Wp, False, n, C, d_in, out=T[f"P{l}"].local[:n])
+        yield  # every rank's P rows are written
+        P_ext = part.pull(f"P{l}", part.pull_f)
+        last = l == L - 1
+        out, act, _, z, minv, bias = ops.edge_fwd(
+            P_ext, A.detach(), None if beta is None else beta.detach(), part.fwd_graph, H, F,
+            want_act=not last, apply_elu=True, act_lo=with_lo, out_buf=T["out"].local[:n] if last else None,
+            z_out=T[f"z{l}"].local[:part.E_fwd], minv_out=T[f"minv{l}"].local[:n])
+        saved.append(dict(xp=planes, WTp=WTp, out=out, bias=bias, A=A.detach(), d_in=d_in, has_beta=beta is not None))
+        planes = act
+    return out
+
+
+def backward_steps(part: PeerPartition, grad_out: torch.Tensor, saved: list, with_lo: bool,
+                   x0_needs_grad: bool = False) -> Generator[None, None, Tuple[Optional[torch.Tensor], list]]:
+    H, F, L = part.H, part.F, part.L
+    C, n = H * F, part.n_local
+    T, g = part.t, part.bwd_graph
+    grads: List[Optional[torch.Tensor]] = [None] * (3 * L)
+    dY, dX = grad_out.contiguous(), None
+    for l in reversed(range(L)):
+        s = saved[l]
+        ops.edge_bwd_prep(dY, s["out"], s["bias"], H, F, apply_elu=(l < L - 1), G_out=T[f"G{l}"].local[:n],
+                          t_out=T[f"t{l}"].local[:n], hsum_out=T[f"hsum{l}"].local[:n])
+        yield  # every rank's G / t / hsum rows are written
+        G_ext = part.pull(f"G{l}", part.pull_b)
+        t_ext, minv_ext, hsum_ext = (part.pull(f"{k}{l}", part.pull_b) for k in ("t", "minv", "hsum"))
+        z = torch.empty((part.E_bwd, H), dtype=torch.float32, device=dY.device)
+        ops.pull_rows(T[f"z{l}"].whole, part.z_index, z)  # 4·H bytes per out-edge, from the logits' owners
+        P_loc = T[f"P{l}"].local[:n]
+        _, dPp, dz = ops.edge_bwd_src(P_loc, G_ext, s["A"], z, minv_ext, t_ext, g, H, F,
+                                      want_fp32=False, want_planes=True, planes_lo=with_lo)
+        main = torch.cuda.current_stream(dY.device)
+        side = _side_stream(dY.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            dA, dbeta = ops.edge_bwd_rel(P_loc, dz, hsum_ext, g, H, F, want_dbeta=s["has_beta"])
+        d_in = s["d_in"]
+        dW = ops.gemm(dPp, True, s["xp"], True, C, d_in, n, splits_k=ops.pick_splits_k(C, d_in, n, dY.device))
+        grads[3 * l], grads[3 * l + 1], grads[3 * l + 2] = dW, dA, dbeta
+        if l > 0 or x0_needs_grad:
+            dX = ops.gemm(dPp, False, s["WTp"], False, n, d_in, C)
+            dY = dX
+        main.wait_stream(side)
+        for tns in (dA, dbeta):
+            if tns is not None:
+                tns.record_stream(main)
+        del dPp, dz, z
+    return (dX if x0_needs_grad else None), grads
+
+
+def drive(gen: Generator, sync) -> object:
+    """Runs a rank program, calling ``sync`` at every yield."""
+    try:
+        while True:
+            next(gen)
+            sync()
+    except StopIteration as stop:
+        return stop.value
+
+
+def drive_lockstep(gens: Sequence[Generator]) -> list:
+    """Single-process simulation: advances all rank programs phase by phase."""
+    results = [None] * len(gens)
+    live = list(range(len(gens)))
+    while live:
+        for i in list(live):
+            try:
+                next(gens[i])
+            except StopIteration as stop:
+                results[i] = stop.value
+                live.remove(i)
+        if live and len(live) != len(gens):
+            raise RuntimeError("rank programs disagree on the number of phases")
+    return results
+
+
+class PeerStackFunction(torch.autograd.Function):
+    """out_local = RelGAT stack over this rank's destinations, sources read from the peer tables.
+    Parameter gradients are this rank's partial sums (all-reduce them afterwards)."""
+
+    @staticmethod
+    def forward(ctx, x0_local, part: PeerPartition, precision: str, x0_planes, *params):
+        with_lo = precision == "fp32"
+        if not with_lo:
+            raise ValueError("the peer-table path stores fp32 rows (precision='fp32')")
+        planes = x0_planes if x0_planes is not None else ops.split_bf16(x0_local, with_lo)
+        saved: list = []
+        out = drive(forward_steps(part, planes, params, with_lo, saved, bool(x0_local.requires_grad)), part.sync)
+        ctx.saved, ctx.part, ctx.with_lo = saved, part, with_lo
+        ctx.x0_needs_grad = bool(x0_local.requires_grad)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        dX, grads = drive(backward_steps(ctx.part, grad_out, ctx.saved, ctx.with_lo, ctx.x0_needs_grad), ctx.part.sync)
+        ctx.saved = None
+        return (dX, None, None, None, *grads)
+
+
+class PeerBatchRows(torch.autograd.Function):
+    """rows[i] = x[ids[i]] for batch node ids anywhere in the graph: the last layer's output rows live in the
+    ``out`` peer table, so the gather is a read of mapped rows (no collective).  Backward folds the row
+    gradients (every rank computes all of them: the batch is replicated) into this rank's rows, in order."""
+
+    @staticmethod
+    def forward(ctx, x_local, ids, part: PeerPartition):
+        n = part.n_local
+        if x_local.data_ptr() != part.t["out"].local.data_ptr():  # the stack's last layer writes there directly
+            part.t["out"].local[:n].copy_(x_local)
+        part.sync()
+        rows = x_local.new_empty((ids.numel(), x_local.size(1)))
+        ops.pull_rows(part.t["out"].whole, part.row_id(ids), rows)
+        mine = torch.nonzero((ids >= part.lo) & (ids < part.hi)).flatten()
+        ctx.save_for_backward(ids, mine)
+        ctx.part = part
+        return rows
+
+    @staticmethod
+    def backward(ctx, grad_rows):
+        ids, mine = ctx.saved_tensors
+        part = ctx.part
+        dx = ops.index_add_sorted(grad_rows.contiguous()[mine], ids[mine] - part.lo, part.n_local)
+        return dx, None, None
+
+
+class PeerRelGAT:
+    """Per-rank driver around a replicated ``RelGATModel`` parameter set (same role as
+    ``dist.PartitionedRelGAT``, peer tables instead of an exchange)."""
+
+    def __init__(self, model, part: PeerPartition, x0_local: torch.Tensor):
+        self.model, self.part = model, part
+        self.layers = model._layers()
+        self.gat_params = [p for lyr in self.layers for p in lyr.parameters()]
+        self.x0_local = x0_local.contiguous()
+        self._planes = ops.split_bf16(self.x0_local, with_lo=True)
+
+    def node_repr_local(self) -> torch.Tensor:
+        flat = []
+        for lyr in self.layers:
+            flat += list(lyr.kernel_params())
+        return PeerStackFunction.apply(self.x0_local, self.part, self.model.precision, self._planes, *flat)
+
+    def scores(self, src_ids, rel_ids, dst_ids):
+        x_local = self.node_repr_local()
+        rows = PeerBatchRows.apply(x_local, torch.cat([src_ids, dst_ids]), self.part)
+        b = src_ids.numel()
+        return self.model.scorer(rows[:b], rel_ids, rows[b:])
+
+    def finish_backward(self) -> None:
+        allreduce_grads(self.gat_params)

@@ -297,3 +297,53 @@ def test_config5_imputation_and_relation_path_expansion(dev):
     # the unmasked forward is unchanged afterwards (input-plane cache was invalidated and rebuilt)
     with torch.no_grad():
         assert rel_err(m.get_node_repr().cpu().numpy(), c.z["x_final"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_table_partition_lockstep_equals_whole_graph(dev, world):
+    """The peer-table partition (relgat_projector_b200/peer.py) with all ranks' tables simulated inside one
+    tensor: the rank programs, stepped in lock-step on one GPU, reproduce the unpartitioned stack — node rows
+    bit-exactly (same per-destination summation order), input gradients to 1e-5 and parameter gradients to 1e-4
+    (different summation orders over a source's out-edges / over ranks)."""
+    from relgat_projector_b200 import functional as Fn, graph as G, peer as RP
+    from relgat_projector_b200 import synthetic as S
+    n, r, d_in, h, f, L_ = 900, 7, 64, 4, 24, 2
+    kg = S.tensor_kg(n, 6000, r, d_in, seed=11, device=str(dev), skew=0.8)
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    params = []
+    for l in range(L_):
+        di = d_in if l == 0 else h * f
+        params += [(torch.randn(h * f, di, generator=gen) / di ** 0.5).to(dev).requires_grad_(True),
+                   (torch.randn(h, r, f, generator=gen) * 0.3).to(dev).requires_grad_(True),
+                   (torch.randn(r, generator=gen) * 0.1).to(dev).requires_grad_(True)]
+    x0 = kg.node_emb.clone().requires_grad_(True)
+    grad_out = torch.randn(n, h * f, generator=gen).to(dev)
+    g_full = G.GraphIndex(kg.edge_index, kg.edge_type, n, r)
+    out_ref = Fn.RelGATStackFunction.apply(x0, g_full, h, f, "fp32", None, *params)
+    ref_grads = torch.autograd.grad(out_ref, [x0] + params, grad_out)
+
+    store = {}
+    parts = [RP.PeerPartition(kg.edge_index, kg.edge_type, n, r, rk, world,
+                              RP.PeerTables(world, rk, dev, mode="sim", sim_store=store), h, f, L_) for rk in range(world)]
+    assert sum(p.E_fwd for p in parts) == sum(p.E_bwd for p in parts) == kg.edge_index.size(1)
+    from relgat_projector_b200 import ops
+    saved = [[] for _ in range(world)]
+    x_loc = [x0.detach()[p.lo:p.hi].contiguous() for p in parts]
+    outs = RP.drive_lockstep([RP.forward_steps(parts[k], ops.split_bf16(x_loc[k]), [t.detach() for t in params], True,
+                                               saved[k], x0_needs_grad=True) for k in range(world)])
+    for p, o in zip(parts, outs):
+        assert torch.equal(o, out_ref.detach()[p.lo:p.hi])
+    res = RP.drive_lockstep([RP.backward_steps(parts[k], grad_out[parts[k].lo:parts[k].hi], saved[k], True,
+                                               x0_needs_grad=True) for k in range(world)])
+    for p, (dx, _) in zip(parts, res):
+        # a source's out-edges are summed in the order of the renumbered destinations: rounding-level difference
+        assert rel_err(dx.cpu().numpy(), ref_grads[0][p.lo:p.hi].cpu().numpy()) < 1e-5
+    for i in range(len(params)):
+        total = sum(res[k][1][i] for k in range(world))
+        assert rel_err(total.cpu().numpy(), ref_grads[1 + i].cpu().numpy()) < FP32_TOL, i
+    # batch rows through the mapped "out" table
+    ids = torch.randint(0, n, (64,), generator=gen).to(dev)
+    for p in parts:
+        rows = torch.empty(64, h * f, device=dev)
+        ops.pull_rows(p.t["out"].whole, p.row_id(ids), rows)
+        assert torch.equal(rows, out_ref.detach()[ids])

@@ -11,7 +11,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import relgat_projector_b200 as R  # noqa: E402
-from relgat_projector_b200 import dist as RD, loss as L, synthetic as S  # noqa: E402
+from relgat_projector_b200 import dist as RD, loss as L, peer as RP, synthetic as S  # noqa: E402
 
 
 def main():
@@ -31,15 +31,21 @@ def main():
     src, rel, dst = (x.to(dev) for x in S.sample_batch(kg.train_triples.cpu(), n, b, k, gen))
     rank_loss = L.RelGATLoss("margin", None, 1.0, None, {})
 
-    part = RD.DstPartition(kg.edge_index, kg.edge_type, n, r, rank, world)
-    prg = RD.PartitionedRelGAT(model, part)
+    if "--peer" in sys.argv:  # peer tables (mapped NVLink rows) instead of the halo exchange
+        tables = RP.PeerTables(world, rank, dev)
+        part = RP.PeerPartition(kg.edge_index, kg.edge_type, n, r, rank, world, tables, h, f, 2)
+        part.E_local = part.E_fwd
+        prg = RP.PeerRelGAT(model, part, kg.node_emb[part.lo:part.hi])
+    else:
+        part = RD.DstPartition(kg.edge_index, kg.edge_type, n, r, rank, world)
+        prg = RD.PartitionedRelGAT(model, part)
     scores = prg.scores(src, rel, dst)
     pos, neg = L.split_scores(scores, b, k)
     loss = rank_loss.prepare_scores_and_compute_loss(pos, neg)
     loss.backward()
     prg.finish_backward()
     got = {name: p.grad.clone() for name, p in model.named_parameters()}
-    x_local = prg.node_repr_local().detach()
+    x_local = prg.node_repr_local().detach().clone()
     model.zero_grad(set_to_none=True)
 
     scores_ref, _, _ = model(src, rel, dst, transform_to_input_if_possible=False)
