@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -143,10 +144,9 @@ namespace relgat {
 
 static inline bool al16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; }
 
-constexpr int kPullUnroll = 4;
 constexpr int kPullThreads = 256;
 
-template <int V>
+template <int V, int kPullUnroll>
 __global__ void __launch_bounds__(kPullThreads)
 pull_rows_kernel(const float* __restrict__ table, long long ld, const long long* __restrict__ ids, long long n, int D,
                  float* __restrict__ out, long long ldo) {
@@ -184,13 +184,24 @@ extern "C" int relgat_pull_rows(const float* table, long long ld, const long lon
   if (!table || !ids || !out) return RG_ERR_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool vec = D % 4 == 0 && ld % 4 == 0 && ldo % 4 == 0 && al16(table) && al16(out);
+  static const int unroll = []() {
+    const char* v = getenv("RELGAT_PULL_UNROLL");  // experiments; 2, 4 and 8 loads in flight per thread measured alike (link-bound)
+    const int u = v ? atoi(v) : 4;
+    return (u == 2 || u == 4 || u == 8) ? u : 4;
+  }();
   const long long total = n * (vec ? D / 4 : D);
-  const long long want = (total + static_cast<long long>(kPullThreads) * kPullUnroll - 1) / (kPullThreads * kPullUnroll);
+  const long long per_cta = static_cast<long long>(kPullThreads) * unroll;
+  const long long want = (total + per_cta - 1) / per_cta;
   const long long cap = static_cast<long long>(sm_count > 0 ? sm_count : 148) * 8;  // 8 resident CTAs of 256 threads per SM
   const unsigned blocks = static_cast<unsigned>(want < cap ? (want > 0 ? want : 1) : cap);
-  if (vec)
-    pull_rows_kernel<4><<<blocks, kPullThreads, 0, s>>>(table, ld, ids, n, D, out, ldo);
-  else
-    pull_rows_kernel<1><<<blocks, kPullThreads, 0, s>>>(table, ld, ids, n, D, out, ldo);
+#define RG_PULL(V_, U_) pull_rows_kernel<V_, U_><<<blocks, kPullThreads, 0, s>>>(table, ld, ids, n, D, out, ldo)
+  if (vec) {
+    if (unroll == 8) RG_PULL(4, 8);
+    else if (unroll == 4) RG_PULL(4, 4);
+    else RG_PULL(4, 2);
+  } else {
+    RG_PULL(1, 4);
+  }
+#undef RG_PULL
   return cuda_status(cudaGetLastError());
 }

@@ -45,6 +45,10 @@ from .functional import _side_stream
 from .graph import GraphIndex
 
 
+# dW GEMMs on the side stream as well (beside the NVLink-bound halo pulls); 0 = only the by-relation pass
+DEEP_OVERLAP = os.environ.get("RELGAT_PEER_DEEP_OVERLAP", "1") != "0"
+
+
 # ---------------------------------------------------------------------------------------------
 # peer tables
 # ---------------------------------------------------------------------------------------------
@@ -341,6 +345,7 @@ def backward_steps(part: PeerPartition, grad_out: torch.Tensor, saved: list, wit
     T, g = part.t, part.bwd_graph
     grads: List[Optional[torch.Tensor]] = [None] * (3 * L)
     dY, dX = grad_out.contiguous(), None
+    keep: list = []
     for l in reversed(range(L)):
         s = saved[l]
         ops.edge_bwd_prep(dY, s["out"], s["bias"], H, F, apply_elu=(l < L - 1), G_out=T[f"G{l}"].local[:n],
@@ -353,22 +358,31 @@ def backward_steps(part: PeerPartition, grad_out: torch.Tensor, saved: list, wit
         P_loc = T[f"P{l}"].local[:n]
         _, dPp, dz = ops.edge_bwd_src(P_loc, G_ext, s["A"], z, minv_ext, t_ext, g, H, F,
                                       want_fp32=False, want_planes=True, planes_lo=with_lo)
+        # dA / dbeta and dW are off the critical path (dX -> prep -> pull -> by-source pass of the layer below):
+        # they run on the side stream, beside the NVLink-bound pulls, and are joined once at the end
         main = torch.cuda.current_stream(dY.device)
         side = _side_stream(dY.device)
         side.wait_stream(main)
+        d_in = s["d_in"]
         with torch.cuda.stream(side):
             dA, dbeta = ops.edge_bwd_rel(P_loc, dz, hsum_ext, g, H, F, want_dbeta=s["has_beta"])
-        d_in = s["d_in"]
-        dW = ops.gemm(dPp, True, s["xp"], True, C, d_in, n, splits_k=ops.pick_splits_k(C, d_in, n, dY.device))
+            if DEEP_OVERLAP:
+                dW = ops.gemm(dPp, True, s["xp"], True, C, d_in, n, splits_k=ops.pick_splits_k(C, d_in, n, dY.device))
+        if not DEEP_OVERLAP:
+            dW = ops.gemm(dPp, True, s["xp"], True, C, d_in, n, splits_k=ops.pick_splits_k(C, d_in, n, dY.device))
         grads[3 * l], grads[3 * l + 1], grads[3 * l + 2] = dW, dA, dbeta
         if l > 0 or x0_needs_grad:
             dX = ops.gemm(dPp, False, s["WTp"], False, n, d_in, C)
             dY = dX
-        main.wait_stream(side)
-        for tns in (dA, dbeta):
-            if tns is not None:
-                tns.record_stream(main)
-        del dPp, dz, z
+        keep.append((dPp, dz, z))  # read on the side stream: released only after the join
+        if not DEEP_OVERLAP:
+            main.wait_stream(side)
+    main = torch.cuda.current_stream(grad_out.device)
+    main.wait_stream(_side_stream(grad_out.device))
+    for tns in grads:
+        if tns is not None:
+            tns.record_stream(main)
+    keep.clear()
     return (dX if x0_needs_grad else None), grads
 
 
