@@ -260,21 +260,39 @@ class PeerPartition:
             own = owner_of(ids)
             return slot_of[own] * self.stride_rows + (ids - starts[own])
 
-        def renumber(ids, halo):
+        def pull_order(halo):
+            """Position of every (sorted) halo id in the pulled block.  Sorted ids are grouped by owner, and all
+            ranks sweeping their lists in that order would read from the same peer at the same time (measured:
+            240 GB/s per GPU on 8 GPUs instead of 660).  The pulled block interleaves the owners round-robin,
+            starting at this rank's right-hand neighbour, so every window of the list touches every link."""
+            own = owner_of(halo)
+            cnt = torch.bincount(own, minlength=world)
+            j = torch.arange(halo.numel(), device=dev) - (torch.cumsum(cnt, 0) - cnt)[own]
+            perm = torch.argsort(j * world + (own - rank - 1) % world)
+            pos = torch.empty_like(perm)
+            pos[perm] = torch.arange(halo.numel(), device=dev)
+            return perm, pos
+
+        def renumber(ids, halo, pos):
             mine = (ids >= self.lo) & (ids < self.hi)
-            return torch.where(mine, ids - self.lo, n + torch.searchsorted(halo, ids))
+            if halo.numel() == 0:
+                return ids - self.lo
+            at = torch.searchsorted(halo, ids).clamp_(max=halo.numel() - 1)
+            return torch.where(mine, ids - self.lo, n + pos[at])
 
         self.owner_of, self.row_id = owner_of, row_id
-        self.pull_f, self.pull_b = row_id(halo_f), row_id(halo_b)  # rows of the mapped range to pull
+        perm_f, pos_f = pull_order(halo_f)
+        perm_b, pos_b = pull_order(halo_b)
+        self.pull_f, self.pull_b = row_id(halo_f[perm_f]), row_id(halo_b[perm_b])  # rows of the mapped range to pull
         # forward: in-edges of my destinations, original order (stable bucketing)
         sel_f = torch.nonzero(in_f).flatten()
         self.E_fwd = int(sel_f.numel())
-        self.fwd_graph = GraphIndex(torch.stack([renumber(src[sel_f], halo_f), dst[sel_f] - self.lo]), edge_type[sel_f],
+        self.fwd_graph = GraphIndex(torch.stack([renumber(src[sel_f], halo_f, pos_f), dst[sel_f] - self.lo]), edge_type[sel_f],
                                     max(n, 1), self.R, num_src_nodes=max(n + self.n_halo_f, 1), src_chunks=False)
         # backward: out-edges of my sources
         sel_b = torch.nonzero(in_b).flatten()
         self.E_bwd = int(sel_b.numel())
-        self.bwd_graph = GraphIndex(torch.stack([src[sel_b] - self.lo, renumber(dst[sel_b], halo_b)]), edge_type[sel_b],
+        self.bwd_graph = GraphIndex(torch.stack([src[sel_b] - self.lo, renumber(dst[sel_b], halo_b, pos_b)]), edge_type[sel_b],
                                     max(n + self.n_halo_b, 1), self.R, num_src_nodes=max(n, 1), fwd_chunks=False)
         # where the forward pass of the destination's owner stored the logit of each of my out-edges:
         # the owner's CSR order is the global stable by-destination order restricted to its range
