@@ -253,6 +253,9 @@ def main():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--exchange", default="peer", choices=["peer", "halo", "allgather"],
                     help="multi-GPU only: peer tables read over NVLink (default), or an NCCL exchange of halo / all rows")
+    ap.add_argument("--locality", type=float, default=0.0,
+                    help="multi-GPU supplementary runs: fraction of edges whose head is drawn from the tail's node block "
+                         "(default 0: uniformly random graph, the headline workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt-precision", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=3)

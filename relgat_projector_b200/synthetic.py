@@ -63,11 +63,23 @@ class TensorKG:
 
 
 def tensor_kg(n: int, t: int, r: int, d_in: int, seed: int = 42, train_ratio: float = 0.9,
-              device: str = "cpu", skew: float = 0.0, emb_on_device: bool = True) -> TensorKG:
+              device: str = "cpu", skew: float = 0.0, emb_on_device: bool = True,
+              locality: float = 0.0, blocks: int = 1) -> TensorKG:
     """Large-graph variant: same distributions, shuffled with a seeded permutation and split
-    int(train_ratio*T) / rest like reference dataset/relgat_dataset.py:70-88."""
+    int(train_ratio*T) / rest like reference dataset/relgat_dataset.py:70-88.
+    ``locality`` > 0 (multi-GPU supplementary runs only): that fraction of the triples gets its head
+    redrawn from the tail's block of ``blocks`` equal node ranges — a graph whose partition cuts few edges,
+    as a partitioner achieves on real KGs; 0 = uniformly random heads, the worst case for a partition."""
     rng = np.random.default_rng(seed)
     src, dst, rel = _triples(rng, n, t, r, skew)
+    if locality > 0 and blocks > 1:
+        size = -(-n // blocks)
+        pick = rng.random(t) < locality
+        lo = (dst // size) * size
+        hi = np.minimum(lo + size, n)
+        near = lo + (rng.random(t) * (hi - lo)).astype(np.int64)
+        near = np.where(near == dst, np.where(near + 1 < hi, near + 1, lo), near)  # no self-pairs
+        src = np.where(pick, near, src)
     perm = rng.permutation(t)
     src, dst, rel = src[perm], dst[perm], rel[perm]
     n_train = int(train_ratio * t)

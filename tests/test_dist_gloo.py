@@ -114,3 +114,51 @@ def test_partition_bounds_single_process():
             b = RD.partition_bounds(d, n, world, balance)
             assert b[0] == 0 and b[-1] == n and all(b[i] <= b[i + 1] for i in range(world))
             assert b == [int(v) for v in O.partition_bounds_np(dst, n, world, balance)]
+
+
+def _fd_worker(rank, world, port, ret):
+    """Each rank owns two temp files with distinct contents and hands their descriptors to every peer."""
+    import tempfile
+    os.environ["MASTER_PORT"] = str(port)
+    from relgat_projector_b200 import peer as RP
+    files = []
+    for i in range(2):
+        f = tempfile.TemporaryFile()
+        f.write(f"rank{rank}-fd{i}".encode())
+        f.flush()
+        files.append(f)
+    got = RP._exchange_fds([f.fileno() for f in files], world, rank, tag="unittest")
+    seen = {}
+    for g in range(world):
+        if g == rank:
+            assert got[g] == []
+            continue
+        for i, fd in enumerate(got[g]):
+            with os.fdopen(fd, "rb") as fh:
+                fh.seek(0)
+                seen[(g, i)] = fh.read().decode()
+    ret[rank] = seen
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_table_descriptor_exchange(world):
+    """Host plumbing of the peer tables (peer.py:_exchange_fds): every rank receives every peer's file
+    descriptors, in order, over AF_UNIX / SCM_RIGHTS — no GPU involved."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_fd_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    for rank in range(world):
+        want = {(g, i): f"rank{g}-fd{i}" for g in range(world) if g != rank for i in range(2)}
+        assert ret[rank] == want
+
+
+def test_peer_table_stride_rounding():
+    """Table strides: smallest row count whose byte size is a granularity multiple for every row size."""
+    from relgat_projector_b200 import peer as RP
+    t = RP.PeerTables.__new__(RP.PeerTables)
+    t.granularity = 2 << 20
+    rows = t.stride_rows(300_000, [3200, 16, 32])
+    assert rows >= 300_000 and all((rows * b) % t.granularity == 0 for b in (3200, 16, 32))
+    assert rows - 300_000 < 131072  # 2 MiB / 16 B rows
+    t.granularity = 1
+    assert t.stride_rows(7, [12]) == 7 and t.stride_rows(0, [4]) == 1
