@@ -192,9 +192,20 @@ extern "C" int relgat_pull_rows(const float* table, long long ld, const long lon
   const long long total = n * (vec ? D / 4 : D);
   const long long per_cta = static_cast<long long>(kPullThreads) * unroll;
   const long long want = (total + per_cta - 1) / per_cta;
-  const long long cap = static_cast<long long>(sm_count > 0 ? sm_count : 148) * 8;  // 8 resident CTAs of 256 threads per SM
+  // 4 CTAs of 256 threads x 4 loads per SM: ~10 MB in flight (the link needs ~3).  1, 2, 4 and 8 CTAs per SM were
+  // swept on 2 GPUs: 2..8 are alike (link-bound), 1 is 20 % slower
+  static const int per_sm = []() { const char* v = getenv("RELGAT_PULL_CTAS"); const int c = v ? atoi(v) : 4; return c > 0 && c <= 8 ? c : 4; }();
+  const long long cap = static_cast<long long>(sm_count > 0 ? sm_count : 148) * per_sm;
   const unsigned blocks = static_cast<unsigned>(want < cap ? (want > 0 ? want : 1) : cap);
-#define RG_PULL(V_, U_) pull_rows_kernel<V_, U_><<<blocks, kPullThreads, 0, s>>>(table, ld, ids, n, D, out, ldo)
+  // same shared-memory carve-out as the tcgen05 GEMM (max shared): kernels with different carve-outs cannot share
+  // an SM, and the pull is meant to run beside the GEMM of the next row block
+#define RG_PULL(V_, U_)                                                                                     \
+  do {                                                                                                      \
+    static const cudaError_t carve = cudaFuncSetAttribute(                                                  \
+        pull_rows_kernel<V_, U_>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+    (void)carve;                                                                                            \
+    pull_rows_kernel<V_, U_><<<blocks, kPullThreads, 0, s>>>(table, ld, ids, n, D, out, ldo);               \
+  } while (0)
   if (vec) {
     if (unroll == 8) RG_PULL(4, 8);
     else if (unroll == 4) RG_PULL(4, 4);

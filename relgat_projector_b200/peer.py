@@ -47,6 +47,18 @@ from .graph import GraphIndex
 
 # dW GEMMs on the side stream as well (beside the NVLink-bound halo pulls); 0 = only the by-relation pass
 DEEP_OVERLAP = os.environ.get("RELGAT_PEER_DEEP_OVERLAP", "1") != "0"
+# row blocks per writer kernel: the halo pull of block c runs (on its own stream) beside the GEMM / prep of block c+1.
+# Measured on 2 GPUs (three sweeps): 4 blocks are 0.3-1.0 ms/step (2-5 %) faster than 1; the overlap is far from
+# complete (the pull and the GEMM compete for the same SMs), see DESIGN.md section 6.
+PIPELINE_BLOCKS = max(1, int(os.environ.get("RELGAT_PEER_BLOCKS", "4")))
+_COMM_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _comm_stream(device) -> "torch.cuda.Stream":
+    key = torch.device(device).index
+    if key not in _COMM_STREAMS:
+        _COMM_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _COMM_STREAMS[key]
 
 
 # ---------------------------------------------------------------------------------------------
@@ -215,8 +227,9 @@ class PeerPartition:
 
     def __init__(self, edge_index: torch.Tensor, edge_type: torch.Tensor, num_nodes: int, num_rel: int,
                  rank: int, world: int, tables: PeerTables, heads: int, out_dim: int, num_layers: int,
-                 balance: str = "edges", tag: str = "p"):
+                 balance: str = "edges", tag: str = "p", blocks: Optional[int] = None):
         self.rank, self.world, self.N, self.R = rank, world, int(num_nodes), int(num_rel)
+        self.blocks = k_blocks = int(blocks if blocks is not None else PIPELINE_BLOCKS)
         self.H, self.F, self.L = heads, out_dim, num_layers
         self.tables = tables
         dev = edge_index.device
@@ -260,18 +273,26 @@ class PeerPartition:
             own = owner_of(ids)
             return slot_of[own] * self.stride_rows + (ids - starts[own])
 
+        sizes = torch.tensor([self.bounds[g + 1] - self.bounds[g] for g in range(world)], device=dev, dtype=torch.int64)
+
         def pull_order(halo):
-            """Position of every (sorted) halo id in the pulled block.  Sorted ids are grouped by owner, and all
-            ranks sweeping their lists in that order would read from the same peer at the same time (measured:
-            240 GB/s per GPU on 8 GPUs instead of 660).  The pulled block interleaves the owners round-robin,
-            starting at this rank's right-hand neighbour, so every window of the list touches every link."""
+            """Position of every (sorted) halo id in the pulled rows, and the row count per pipeline block.
+            Block c holds the rows that sit in block c of their OWNER's range (pulled as soon as every rank
+            has written its block c).  Inside a block the owners are interleaved round-robin, starting at this
+            rank's right-hand neighbour: sorted ids are grouped by owner, and all ranks sweeping their lists in
+            that order would read from the same peer at the same time (measured: 240 GB/s per GPU on 8 GPUs
+            instead of 660)."""
             own = owner_of(halo)
-            cnt = torch.bincount(own, minlength=world)
-            j = torch.arange(halo.numel(), device=dev) - (torch.cumsum(cnt, 0) - cnt)[own]
-            perm = torch.argsort(j * world + (own - rank - 1) % world)
+            blk = ((halo - starts[own]) * k_blocks) // sizes[own].clamp(min=1)  # row r of n is in block k*r // n
+            grp = own * k_blocks + blk  # ascending along the sorted ids
+            cnt = torch.bincount(grp, minlength=world * k_blocks)
+            j = torch.arange(halo.numel(), device=dev) - (torch.cumsum(cnt, 0) - cnt)[grp]
+            span = (int(j.max().item()) + 1 if halo.numel() else 1) * world
+            perm = torch.argsort(blk * span + j * world + (own - rank - 1) % world)
             pos = torch.empty_like(perm)
             pos[perm] = torch.arange(halo.numel(), device=dev)
-            return perm, pos
+            per_block = torch.bincount(blk, minlength=k_blocks).tolist()
+            return perm, pos, per_block
 
         def renumber(ids, halo, pos):
             mine = (ids >= self.lo) & (ids < self.hi)
@@ -281,9 +302,10 @@ class PeerPartition:
             return torch.where(mine, ids - self.lo, n + pos[at])
 
         self.owner_of, self.row_id = owner_of, row_id
-        perm_f, pos_f = pull_order(halo_f)
-        perm_b, pos_b = pull_order(halo_b)
+        perm_f, pos_f, self.blk_f = pull_order(halo_f)
+        perm_b, pos_b, self.blk_b = pull_order(halo_b)
         self.pull_f, self.pull_b = row_id(halo_f[perm_f]), row_id(halo_b[perm_b])  # rows of the mapped range to pull
+        self.row_blocks = [(-(-c * n // k_blocks), -(-(c + 1) * n // k_blocks)) for c in range(k_blocks)]  # own rows per block
         # forward: in-edges of my destinations, original order (stable bucketing)
         sel_f = torch.nonzero(in_f).flatten()
         self.E_fwd = int(sel_f.numel())
@@ -321,11 +343,16 @@ class PeerPartition:
         if self.tables.mode == "vmm" and self.world > 1:
             dist.all_reduce(self._token)
 
-    def pull(self, name: str, ids: torch.Tensor) -> torch.Tensor:
-        """Fills the halo rows of table ``name`` from their owners; returns the [own | halo] view."""
+    def pull(self, name: str, ids: torch.Tensor, per_block: Optional[List[int]] = None, block: Optional[int] = None):
+        """Fills the pulled rows of table ``name`` (all of them, or those of one pipeline block) from their
+        owners; returns the [own | pulled] view."""
         tb, n = self.t[name], self.n_local
         k = int(ids.numel())
-        ops.pull_rows(tb.whole, ids, tb.local[n:n + k])
+        a, b = 0, k
+        if block is not None:
+            a = sum(per_block[:block])
+            b = a + per_block[block]
+        ops.pull_rows(tb.whole, ids[a:b], tb.local[n + a:n + b])
         return tb.local[:n + k]
 
 
@@ -343,9 +370,18 @@ def forward_steps(part: PeerPartition, planes, params: Sequence[torch.Tensor], w
         d_in = W.size(1)
         Wp = ops.split_bf16(W.detach(), with_lo)
         WTp = ops.split_bf16(W.detach().t().contiguous(), with_lo) if (l > 0 or x0_needs_grad) else None
-        ops.gemm(planes, False, Wp, False, n, C, d_in, out=T[f"P{l}"].local[:n])
-        yield  # every rank's P rows are written
-        P_ext = part.pull(f"P{l}", part.pull_f)
+        main = torch.cuda.current_stream(W.device)
+        comm = _comm_stream(W.device)
+        P_ext = None
+        for c, (r0, r1) in enumerate(part.row_blocks):
+            if r1 > r0:
+                ops.gemm(tuple(None if p is None else p[r0:r1] for p in planes), False, Wp, False, r1 - r0, C, d_in,
+                         out=T[f"P{l}"].local[r0:r1])
+            yield  # every rank's block c of P is written
+            comm.wait_stream(main)
+            with torch.cuda.stream(comm):  # beside the GEMM of block c+1
+                P_ext = part.pull(f"P{l}", part.pull_f, part.blk_f, c)
+        main.wait_stream(comm)
         last = l == L - 1
         out, act, _, z, minv, bias = ops.edge_fwd(
             P_ext, A.detach(), None if beta is None else beta.detach(), part.fwd_graph, H, F,
@@ -366,19 +402,28 @@ def backward_steps(part: PeerPartition, grad_out: torch.Tensor, saved: list, wit
     keep: list = []
     for l in reversed(range(L)):
         s = saved[l]
-        ops.edge_bwd_prep(dY, s["out"], s["bias"], H, F, apply_elu=(l < L - 1), G_out=T[f"G{l}"].local[:n],
-                          t_out=T[f"t{l}"].local[:n], hsum_out=T[f"hsum{l}"].local[:n])
-        yield  # every rank's G / t / hsum rows are written
-        G_ext = part.pull(f"G{l}", part.pull_b)
-        t_ext, minv_ext, hsum_ext = (part.pull(f"{k}{l}", part.pull_b) for k in ("t", "minv", "hsum"))
+        main = torch.cuda.current_stream(dY.device)
+        comm = _comm_stream(dY.device)
         z = torch.empty((part.E_bwd, H), dtype=torch.float32, device=dY.device)
-        ops.pull_rows(T[f"z{l}"].whole, part.z_index, z)  # 4·H bytes per out-edge, from the logits' owners
+        comm.wait_stream(main)
+        with torch.cuda.stream(comm):  # 4·H bytes per out-edge, from the logits' owners (written in the forward pass)
+            ops.pull_rows(T[f"z{l}"].whole, part.z_index, z)
+        for c, (r0, r1) in enumerate(part.row_blocks):
+            if r1 > r0:
+                ops.edge_bwd_prep(dY[r0:r1], s["out"][r0:r1], s["bias"][r0:r1], H, F, apply_elu=(l < L - 1),
+                                  G_out=T[f"G{l}"].local[r0:r1], t_out=T[f"t{l}"].local[r0:r1],
+                                  hsum_out=T[f"hsum{l}"].local[r0:r1])
+            yield  # every rank's block c of G / t / hsum is written
+            comm.wait_stream(main)
+            with torch.cuda.stream(comm):  # beside the prep of block c+1
+                G_ext = part.pull(f"G{l}", part.pull_b, part.blk_b, c)
+                t_ext, minv_ext, hsum_ext = (part.pull(f"{k}{l}", part.pull_b, part.blk_b, c) for k in ("t", "minv", "hsum"))
+        main.wait_stream(comm)
         P_loc = T[f"P{l}"].local[:n]
         _, dPp, dz = ops.edge_bwd_src(P_loc, G_ext, s["A"], z, minv_ext, t_ext, g, H, F,
                                       want_fp32=False, want_planes=True, planes_lo=with_lo)
         # dA / dbeta and dW are off the critical path (dX -> prep -> pull -> by-source pass of the layer below):
         # they run on the side stream, beside the NVLink-bound pulls, and are joined once at the end
-        main = torch.cuda.current_stream(dY.device)
         side = _side_stream(dY.device)
         side.wait_stream(main)
         d_in = s["d_in"]

@@ -299,8 +299,8 @@ def test_config5_imputation_and_relation_path_expansion(dev):
         assert rel_err(m.get_node_repr().cpu().numpy(), c.z["x_final"]) < FP32_TOL
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_peer_table_partition_lockstep_equals_whole_graph(dev, world):
+@pytest.mark.parametrize("world,blocks", [(2, 2), (3, 1), (3, 4)])
+def test_peer_table_partition_lockstep_equals_whole_graph(dev, world, blocks):
     """The peer-table partition (relgat_projector_b200/peer.py) with all ranks' tables simulated inside one
     tensor: the rank programs, stepped in lock-step on one GPU, reproduce the unpartitioned stack — node rows
     bit-exactly (same per-destination summation order), input gradients to 1e-5 and parameter gradients to 1e-4
@@ -324,7 +324,8 @@ def test_peer_table_partition_lockstep_equals_whole_graph(dev, world):
 
     store = {}
     parts = [RP.PeerPartition(kg.edge_index, kg.edge_type, n, r, rk, world,
-                              RP.PeerTables(world, rk, dev, mode="sim", sim_store=store), h, f, L_) for rk in range(world)]
+                              RP.PeerTables(world, rk, dev, mode="sim", sim_store=store), h, f, L_, blocks=blocks)
+             for rk in range(world)]
     assert sum(p.E_fwd for p in parts) == sum(p.E_bwd for p in parts) == kg.edge_index.size(1)
     from relgat_projector_b200 import ops
     saved = [[] for _ in range(world)]
