@@ -83,9 +83,9 @@ __global__ void __launch_bounds__(kBwdWarps * 32) bwd_prep_kernel(const PrepArgs
 // row).  Two items are in flight per warp and the pipeline does not drain at source boundaries.
 // ------------------------------------------------------------------------------------
 constexpr int kSrcWarps = 12;      // plain variant
-constexpr int kSrcWarpsPipe = 8;   // register double-buffered variant (needs ~230 registers)
+constexpr int kSrcWarpsPipe = 12;  // two-slot ring variant (same register budget as the plain one)
 constexpr int kSrcPrefetchDist = 2;
-constexpr int kSrcPipeDefault = 0;  // default: edges ahead whose G[dst] rows are pulled into L2
+constexpr int kSrcPipeDefault = 1;  // two-slot ring (1.44 -> 1.38 ms on config 2); 0 = load two items, consume two
 
 __device__ __forceinline__ void prefetch_l2(const char* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -334,24 +334,32 @@ __global__ void __launch_bounds__((PIPE ? kSrcWarpsPipe : kSrcWarps) * 32, 1) bw
       t##S_##1 = __ldg(a.t + static_cast<long long>(ds##S_##1) * a.H + lm.hh);                 \
       mi##S_##1 = __ldg(reinterpret_cast<const float2*>(a.minv) + static_cast<long long>(ds##S_##1) * a.H + lm.hh); \
     }
+#define RG_FETCH1(S_, I_)                                                                      \
+    RG_NEXT(ty##S_##I_, nd##S_##I_, sl##S_##I_, ds##S_##I_, rl##S_##I_);                       \
+    RG_ISSUE(ty##S_##I_, nd##S_##I_, ds##S_##I_, x##S_##I_);                                   \
+    if (ty##S_##I_ == IT_EDGE) {                                                               \
+      z##S_##I_ = __ldg(a.z + static_cast<long long>(sl##S_##I_) * a.H + lm.hh);               \
+      t##S_##I_ = __ldg(a.t + static_cast<long long>(ds##S_##I_) * a.H + lm.hh);               \
+      mi##S_##I_ = __ldg(reinterpret_cast<const float2*>(a.minv) + static_cast<long long>(ds##S_##I_) * a.H + lm.hh); \
+    }
 #define RG_DRAIN(S_)                                                                           \
     RG_CONSUME(ty##S_##0, nd##S_##0, sl##S_##0, rl##S_##0, x##S_##0, z##S_##0, mi##S_##0, t##S_##0); \
     if (ty##S_##1 != IT_NONE)                                                                  \
       RG_CONSUME(ty##S_##1, nd##S_##1, sl##S_##1, rl##S_##1, x##S_##1, z##S_##1, mi##S_##1, t##S_##1);
 
     if (PIPE) {
-      // register double buffering: the loads of the next two items are in flight while the
-      // current two are consumed
+      // two-slot ring: a slot is refilled right after it has been consumed, so the row loads of one item are
+      // in flight while the other item is consumed (the plain variant loads two items, then consumes both:
+      // 25 % of its stall samples sit on the first use of the loaded row — profiles/r01_summary.md)
       RG_DECL(A)
-      RG_DECL(B)
-      RG_FETCH(A)
+      RG_FETCH1(A, 0)
       while (true) {
+        RG_FETCH1(A, 1)
         if (tyA0 == IT_NONE) break;
-        RG_FETCH(B)
-        RG_DRAIN(A)
-        if (tyB0 == IT_NONE) break;
-        RG_FETCH(A)
-        RG_DRAIN(B)
+        RG_CONSUME(tyA0, ndA0, slA0, rlA0, xA0, zA0, miA0, tA0);
+        RG_FETCH1(A, 0)
+        if (tyA1 == IT_NONE) break;
+        RG_CONSUME(tyA1, ndA1, slA1, rlA1, xA1, zA1, miA1, tA1);
       }
     } else {
       while (true) {
@@ -361,6 +369,7 @@ __global__ void __launch_bounds__((PIPE ? kSrcWarpsPipe : kSrcWarps) * 32, 1) bw
         RG_DRAIN(A)
       }
     }
+#undef RG_FETCH1
 #undef RG_DRAIN
 #undef RG_FETCH
 #undef RG_DECL
@@ -592,7 +601,10 @@ static int launch_src_kv(const SrcArgs<T, V>& a, int sm_count, cudaStream_t s) {
   const int lph = 32 / a.hg;
   constexpr bool kSpec8 = (V == 4 && KV == 7) || (V == 8 && KV == 4);  // F = 200, 4 heads per warp
   constexpr bool kSpec32 = (V == 4 && KV == 2);                        // F = 200, one head per warp
-  if (pipe) return launch_src_pipe<T, V, KV, 1, 0>(a, sm_count, s);
+  if (pipe) {
+    if (kSpec8 && lph == 8) return launch_src_pipe<T, V, KV, 1, kSpec8 ? 8 : 0>(a, sm_count, s);
+    return launch_src_pipe<T, V, KV, 1, 0>(a, sm_count, s);
+  }
   if (kSpec8 && lph == 8) return launch_src_pipe<T, V, KV, 0, kSpec8 ? 8 : 0>(a, sm_count, s);
   if (kSpec32 && lph == 32) return launch_src_pipe<T, V, KV, 0, kSpec32 ? 32 : 0>(a, sm_count, s);
   return launch_src_pipe<T, V, KV, 0, 0>(a, sm_count, s);
