@@ -53,6 +53,31 @@ DEEP_OVERLAP = os.environ.get("RELGAT_PEER_DEEP_OVERLAP", "1") != "0"
 PIPELINE_BLOCKS = max(1, int(os.environ.get("RELGAT_PEER_BLOCKS", "4")))
 _COMM_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
 
+# poor man's timeline (nsys is not in the image): RELGAT_PEER_TRACE=1 records a CUDA event per phase boundary on the
+# stream that runs the phase; trace_report() turns them into start / end offsets within the step
+TRACE = os.environ.get("RELGAT_PEER_TRACE", "0") == "1"
+_TRACE_EVENTS: List[Tuple[str, str, "torch.cuda.Event"]] = []
+
+
+def _mark(label: str, stream_name: str = "main") -> None:
+    if TRACE:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()  # on the current stream
+        _TRACE_EVENTS.append((label, stream_name, ev))
+
+
+def trace_reset() -> None:
+    _TRACE_EVENTS.clear()
+
+
+def trace_report() -> List[Tuple[str, str, float]]:
+    """(label, stream, ms since the first mark) for every mark since trace_reset(); synchronises the device."""
+    torch.cuda.synchronize()
+    if not _TRACE_EVENTS:
+        return []
+    t0 = _TRACE_EVENTS[0][2]
+    return [(label, st, t0.elapsed_time(ev)) for label, st, ev in _TRACE_EVENTS]
+
 
 def _comm_stream(device) -> "torch.cuda.Stream":
     key = torch.device(device).index
@@ -373,20 +398,26 @@ def forward_steps(part: PeerPartition, planes, params: Sequence[torch.Tensor], w
         main = torch.cuda.current_stream(W.device)
         comm = _comm_stream(W.device)
         P_ext = None
+        _mark(f"fwd{l} start")
         for c, (r0, r1) in enumerate(part.row_blocks):
             if r1 > r0:
                 ops.gemm(tuple(None if p is None else p[r0:r1] for p in planes), False, Wp, False, r1 - r0, C, d_in,
                          out=T[f"P{l}"].local[r0:r1])
+            _mark(f"fwd{l} gemm block {c} done")
             yield  # every rank's block c of P is written
+            _mark(f"fwd{l} rendezvous {c} done")
             comm.wait_stream(main)
             with torch.cuda.stream(comm):  # beside the GEMM of block c+1
                 P_ext = part.pull(f"P{l}", part.pull_f, part.blk_f, c)
+                _mark(f"fwd{l} pull block {c} done", "comm")
         main.wait_stream(comm)
+        _mark(f"fwd{l} pulls joined")
         last = l == L - 1
         out, act, _, z, minv, bias = ops.edge_fwd(
             P_ext, A.detach(), None if beta is None else beta.detach(), part.fwd_graph, H, F,
             want_act=not last, apply_elu=True, act_lo=with_lo, out_buf=T["out"].local[:n] if last else None,
             z_out=T[f"z{l}"].local[:part.E_fwd], minv_out=T[f"minv{l}"].local[:n])
+        _mark(f"fwd{l} edge kernel done")
         saved.append(dict(xp=planes, WTp=WTp, out=out, bias=bias, A=A.detach(), d_in=d_in, has_beta=beta is not None))
         planes = act
     return out
@@ -408,35 +439,46 @@ def backward_steps(part: PeerPartition, grad_out: torch.Tensor, saved: list, wit
         comm.wait_stream(main)
         with torch.cuda.stream(comm):  # 4·H bytes per out-edge, from the logits' owners (written in the forward pass)
             ops.pull_rows(T[f"z{l}"].whole, part.z_index, z)
+        _mark(f"bwd{l} start")
         for c, (r0, r1) in enumerate(part.row_blocks):
             if r1 > r0:
                 ops.edge_bwd_prep(dY[r0:r1], s["out"][r0:r1], s["bias"][r0:r1], H, F, apply_elu=(l < L - 1),
                                   G_out=T[f"G{l}"].local[r0:r1], t_out=T[f"t{l}"].local[r0:r1],
                                   hsum_out=T[f"hsum{l}"].local[r0:r1])
+            _mark(f"bwd{l} prep block {c} done")
             yield  # every rank's block c of G / t / hsum is written
+            _mark(f"bwd{l} rendezvous {c} done")
             comm.wait_stream(main)
             with torch.cuda.stream(comm):  # beside the prep of block c+1
                 G_ext = part.pull(f"G{l}", part.pull_b, part.blk_b, c)
                 t_ext, minv_ext, hsum_ext = (part.pull(f"{k}{l}", part.pull_b, part.blk_b, c) for k in ("t", "minv", "hsum"))
+                _mark(f"bwd{l} pull block {c} done", "comm")
         main.wait_stream(comm)
+        _mark(f"bwd{l} pulls joined")
         P_loc = T[f"P{l}"].local[:n]
         _, dPp, dz = ops.edge_bwd_src(P_loc, G_ext, s["A"], z, minv_ext, t_ext, g, H, F,
                                       want_fp32=False, want_planes=True, planes_lo=with_lo)
+        _mark(f"bwd{l} by-source kernel done")
         # dA / dbeta and dW are off the critical path (dX -> prep -> pull -> by-source pass of the layer below):
         # they run on the side stream, beside the NVLink-bound pulls, and are joined once at the end
         side = _side_stream(dY.device)
         side.wait_stream(main)
         d_in = s["d_in"]
+        deep = DEEP_OVERLAP and l > 0  # the layer processed last has no pulls below it: dW on the main stream beside dA
         with torch.cuda.stream(side):
             dA, dbeta = ops.edge_bwd_rel(P_loc, dz, hsum_ext, g, H, F, want_dbeta=s["has_beta"])
-            if DEEP_OVERLAP:
+            _mark(f"bwd{l} by-relation done", "side")
+            if deep:
                 dW = ops.gemm(dPp, True, s["xp"], True, C, d_in, n, splits_k=ops.pick_splits_k(C, d_in, n, dY.device))
-        if not DEEP_OVERLAP:
+                _mark(f"bwd{l} dW done", "side")
+        if not deep:
             dW = ops.gemm(dPp, True, s["xp"], True, C, d_in, n, splits_k=ops.pick_splits_k(C, d_in, n, dY.device))
+            _mark(f"bwd{l} dW done")
         grads[3 * l], grads[3 * l + 1], grads[3 * l + 2] = dW, dA, dbeta
         if l > 0 or x0_needs_grad:
             dX = ops.gemm(dPp, False, s["WTp"], False, n, d_in, C)
             dY = dX
+            _mark(f"bwd{l} dX done")
         keep.append((dPp, dz, z))  # read on the side stream: released only after the join
         if not DEEP_OVERLAP:
             main.wait_stream(side)
@@ -446,6 +488,7 @@ def backward_steps(part: PeerPartition, grad_out: torch.Tensor, saved: list, wit
         if tns is not None:
             tns.record_stream(main)
     keep.clear()
+    _mark("bwd side stream joined")
     return (dX if x0_needs_grad else None), grads
 
 
@@ -501,7 +544,8 @@ class PeerStackFunction(torch.autograd.Function):
 class PeerBatchRows(torch.autograd.Function):
     """rows[i] = x[ids[i]] for batch node ids anywhere in the graph: the last layer's output rows live in the
     ``out`` peer table, so the gather is a read of mapped rows (no collective).  Backward folds the row
-    gradients (every rank computes all of them: the batch is replicated) into this rank's rows, in order."""
+    gradients (every rank computes all of them: the batch is replicated) into this rank's rows, in order.
+    No host synchronisation: rows of other ranks are folded into scratch rows that are dropped."""
 
     @staticmethod
     def forward(ctx, x_local, ids, part: PeerPartition):
@@ -511,17 +555,17 @@ class PeerBatchRows(torch.autograd.Function):
         part.sync()
         rows = x_local.new_empty((ids.numel(), x_local.size(1)))
         ops.pull_rows(part.t["out"].whole, part.row_id(ids), rows)
-        mine = torch.nonzero((ids >= part.lo) & (ids < part.hi)).flatten()
-        ctx.save_for_backward(ids, mine)
-        ctx.part = part
+        mine = (ids >= part.lo) & (ids < part.hi)
+        # rows of other ranks get one scratch row each (a shared scratch row would be one long serial segment)
+        ctx.save_for_backward(torch.where(mine, ids - part.lo, n + torch.arange(ids.numel(), device=ids.device)))
+        ctx.n_local = n
         return rows
 
     @staticmethod
     def backward(ctx, grad_rows):
-        ids, mine = ctx.saved_tensors
-        part = ctx.part
-        dx = ops.index_add_sorted(grad_rows.contiguous()[mine], ids[mine] - part.lo, part.n_local)
-        return dx, None, None
+        (keys,) = ctx.saved_tensors
+        dx = ops.index_add_sorted(grad_rows.contiguous(), keys, ctx.n_local + keys.numel())
+        return dx[:ctx.n_local], None, None
 
 
 class PeerRelGAT:
