@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import json
 import os
+import sys
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -364,8 +365,14 @@ def bench_main(args, cfg, rank, world, local_rank, metric, unit, load_peaks, Clo
     exchange = getattr(args, "exchange", "peer")
     if args.precision != "fp32" and exchange == "peer":
         exchange = "halo"
-    if exchange == "peer":  # rows of other ranks are read in place over NVLink (peer.py); no exchange step
+    if exchange == "peer":
         from . import peer as RP
+        usable, why = RP.peer_tables_available(world, rank, dev)
+        if not usable:  # still a GPU path: the NCCL halo exchange below
+            if rank == 0:
+                print(f"[bench] peer tables unavailable ({why}); using the NCCL halo exchange", file=sys.stderr)
+            exchange = "halo"
+    if exchange == "peer":  # rows of other ranks are pulled from NVLink-mapped peer tables (peer.py); no exchange step
         part = RP.PeerPartition(kg.edge_index, kg.edge_type, n_nodes, cfg["R"], rank, world,
                                 RP.PeerTables(world, rank, dev), cfg["H"], cfg["F"], cfg["L"])
         part.E_local = part.E_fwd

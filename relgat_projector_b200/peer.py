@@ -240,6 +240,36 @@ class PeerTables:
         self._mapped.clear()
 
 
+def peer_tables_available(world: int, rank: int, device) -> Tuple[bool, str]:
+    """Collective probe: maps one granule per rank end to end (create, export, descriptor hand-off, import, map,
+    a remote read) and agrees on the outcome, so that every rank takes the same path afterwards."""
+    ok, why = 1, ""
+    try:
+        tables = PeerTables(world, rank, device)
+        rows = tables.stride_rows(1, [16])
+        tb = tables.allocate([("probe", rows, (4,), torch.float32)], tag="probe")["probe"]
+        tb.local.fill_(float(rank + 1))
+        torch.cuda.synchronize()
+    except Exception as exc:  # noqa: BLE001 - any failure means "use the NCCL exchange"
+        ok, why, tables, tb = 0, f"{type(exc).__name__}: {exc}", None, None
+    flag = torch.tensor([ok], device=device, dtype=torch.int32)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # also orders the fills before the remote reads below
+    if int(flag.item()) == 1 and world > 1:
+        nxt = (rank + 1) % world
+        got = float(tb.whole[tables.slot_of[nxt] * tb.stride_rows, 0].item())
+        flag.fill_(1 if got == float(nxt + 1) else 0)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) != 1 and not why:
+            why = "a read through the mapped range did not return the peer's data"
+    if tables is not None:
+        if world > 1:
+            dist.barrier()
+        del tb
+        tables.close()
+    return int(flag.item()) == 1, why
+
+
 # ---------------------------------------------------------------------------------------------
 # the partition: forward graph (in-edges of my destinations), backward graph (out-edges of my sources)
 # ---------------------------------------------------------------------------------------------
