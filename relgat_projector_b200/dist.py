@@ -20,9 +20,8 @@ Batch rows x[src_ids] / x[dst_ids] are exchanged with one all-reduce of a [2B', 
 from __future__ import annotations
 
 import json
-import os
 import sys
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
