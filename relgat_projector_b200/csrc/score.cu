@@ -210,8 +210,14 @@ index_add_sorted_kernel(const float* __restrict__ rows, const long long* __restr
   if (p0 >= M) return;
   const long long key = sorted_keys[p0];
   if (p0 > 0 && sorted_keys[p0 - 1] == key) return;
-  int p1 = p0 + 1;
-  while (p1 < M && sorted_keys[p1] == key) ++p1;
+  int p1 = p0 + 1;  // end of the key run: 32 positions per probe (all lanes are still active here)
+  while (true) {
+    const int q = p1 + lane;
+    const unsigned same = __ballot_sync(0xffffffffu, q < M && sorted_keys[q] == key);
+    if (same == 0xffffffffu) { p1 += 32; continue; }
+    p1 += __ffs(~same) - 1;
+    break;
+  }
   // blockIdx.y selects a 32*V-column slab, so a long key run (few relations, many triples) is
   // spread over D / (32*V) warps instead of one
   const int c = (blockIdx.y * 32 + lane) * V;
@@ -221,7 +227,23 @@ index_add_sorted_kernel(const float* __restrict__ rows, const long long* __restr
 #pragma unroll
   for (int v = 0; v < V; ++v) acc[v] = 0.f;
   if (accumulate) ldv<V>(o + c, acc);
-  for (int p = p0; p < p1; ++p) {
+  // the sum stays strictly in run order (reproducible, same result as a serial loop); only the loads of
+  // kRunUnroll rows are issued together — a run of ~100 rows (few relations) is latency-bound otherwise
+  constexpr int kRunUnroll = 8;
+  int p = p0;
+  for (; p + kRunUnroll <= p1; p += kRunUnroll) {
+    long long r[kRunUnroll];
+    float x[kRunUnroll][V];
+#pragma unroll
+    for (int u = 0; u < kRunUnroll; ++u) r[u] = perm[p + u];
+#pragma unroll
+    for (int u = 0; u < kRunUnroll; ++u) ldv<V>(rows + r[u] * D + c, x[u]);
+#pragma unroll
+    for (int u = 0; u < kRunUnroll; ++u)
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[v] += x[u][v];
+  }
+  for (; p < p1; ++p) {
     float x[V];
     ldv<V>(rows + perm[p] * D + c, x);
 #pragma unroll
