@@ -169,9 +169,17 @@ def kernel_work(cfg, E, n_chunks, precision):
         "edge_bwd_src": N * C * sf + E * (C * sf + 12 + 4 * H * 4) + N * C * plane_b + E * H * 4,
         # gathers P[src] + (slot, src, dst) ids + dz + hsum; writes chunk partials
         "edge_bwd_rel": E * (C * sf + 12 + 2 * H * 4) + n_chunks * C * s * 2,
-        # reads dY and out (fp32); G is written only when it differs from dY (activation or bf16 storage)
-        "edge_bwd_prep": 2 * N * C * s + 2 * N * H * 4 + (N * C * sf if precision != "fp32" else 0),
     }
+    # bwd_prep, average over the L calls of a step.  Hidden layers: read dY and out, write G (ELU').  Last layer,
+    # fp32: G aliases dY and only the <= 2*B*(1+K) rows the loss touched are read (t / hsum of the rest: memset);
+    # bf16 storage: dense read of dY and out, bf16 G written.
+    L = cfg["L"]
+    rows = min(N, 2 * cfg["B"] * (1 + cfg["K"]))
+    if precision == "fp32":
+        total = (L - 1) * (3 * N * C * s) + 2 * rows * C * s + L * 2 * N * H * 4
+    else:
+        total = L * (2 * N * C * s + N * C * sf + 2 * N * H * 4)
+    w["edge_bwd_prep"] = total // L
     return w
 
 

@@ -99,7 +99,9 @@ int relgat_layer_fwd(const void* P, int p_is_bf16, long long ldp, const float* A
 /* ---- RelGAT layer, edge part, backward (replaces the autograd replay of layer.py:220-318) ---
  * Feature storage: P and G are fp32, or both bf16 when the *_is_bf16 flags are set (F % 8 == 0).
  * bwd_prep: G = dY * act'(out) (fp32: in place allowed; or written as bf16), t[N,H] = <G, out - bias>,
- *           hsum[N,H] = sum_f G.
+ *           hsum[N,H] = sum_f G.  row_ids (int64[n_rows], may repeat; NULL = all rows): the caller knows that
+ *           only these rows of dY are non-zero (the loss reads B*(2+K) rows: reference model.py:136-137) — then
+ *           G must alias dY, apply_elu = 0, and only those rows are read; t / hsum of all other rows are set to 0.
  * bwd_src : by-source pass over chunks of the CSC order (work tables as in fwd, over sources;
  *           part_acc [n_parts, H*F] holds the partial rows of split sources):
  *           dP [N_src, H*F] (fp32 and/or bf16 hi/lo planes) and dz [E, H]; the attention weights
@@ -109,7 +111,8 @@ int relgat_layer_fwd(const void* P, int p_is_bf16, long long ldp, const float* A
  *           dA [H, R, F] and dbeta [R] (NULL to skip) with an ordered reduction of the partials
  *           partA [n_chunks, H*F], partB [n_chunks]. */
 int relgat_layer_bwd_prep(const float* dY, const float* out, const float* bias, void* G, int g_is_bf16,
-                          float* t, float* hsum, int N, int H, int F, int apply_elu, void* stream);
+                          float* t, float* hsum, int N, int H, int F, int apply_elu,
+                          const long long* row_ids, int n_rows, void* stream);
 int relgat_layer_bwd_src(const void* P, long long ldp, const void* G, int feat_is_bf16, const float* A,
                          const float* z, const float* minv, const float* t,
                          const int* colptr, const int* csc_slot, const int* csc_dst, const int* csc_rel,

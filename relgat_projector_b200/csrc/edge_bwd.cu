@@ -31,6 +31,7 @@ struct PrepArgs {
   float* t;            // [N, H]
   float* hsum;         // [N, H]
   int N, H, F, hg, apply_elu;
+  const long long* row_ids;  // optional: only these rows of dY are non-zero (N = their count); t / hsum pre-zeroed
 };
 
 template <typename TG, int V>
@@ -39,10 +40,11 @@ __global__ void __launch_bounds__(kBwdWarps * 32) bwd_prep_kernel(const PrepArgs
   const int groups = a.H / a.hg;
   const long long task = static_cast<long long>(blockIdx.x) * kBwdWarps + warp;
   if (task >= static_cast<long long>(a.N) * groups) return;
-  const int j = static_cast<int>(task / groups);
-  const int g = static_cast<int>(task - static_cast<long long>(j) * groups);
+  const int jt = static_cast<int>(task / groups);
+  const int g = static_cast<int>(task - static_cast<long long>(jt) * groups);
+  const long long j = a.row_ids ? __ldg(a.row_ids + jt) : jt;
   const LaneMap lm = make_lane_map<V>(lane, g, a.hg, a.F);
-  const long long row = static_cast<long long>(j) * a.H * a.F + lm.head_off;
+  const long long row = j * a.H * a.F + lm.head_off;
   const float b = a.bias ? __ldg(a.bias + j) : 0.f;
   float tt = 0.f, hs = 0.f;
 #pragma unroll
@@ -68,8 +70,8 @@ __global__ void __launch_bounds__(kBwdWarps * 32) bwd_prep_kernel(const PrepArgs
   tt = head_sum(tt, lm.lph);
   hs = head_sum(hs, lm.lph);
   if (lm.sub == 0) {
-    a.t[static_cast<long long>(j) * a.H + lm.hh] = tt;
-    a.hsum[static_cast<long long>(j) * a.H + lm.hh] = hs;
+    a.t[j * a.H + lm.hh] = tt;
+    a.hsum[j * a.H + lm.hh] = hs;
   }
 }
 
@@ -514,28 +516,39 @@ static inline bool al16(const void* p) { return reinterpret_cast<uintptr_t>(p) %
 using namespace relgat;
 
 extern "C" int relgat_layer_bwd_prep(const float* dY, const float* out, const float* bias, void* G, int g_is_bf16,
-                                     float* t, float* hsum, int N, int H, int F, int apply_elu, void* stream) {
-  if (!dY || !out || !G || !t || !hsum || N < 0 || H <= 0 || F <= 0) return RG_ERR_ARG;
+                                     float* t, float* hsum, int N, int H, int F, int apply_elu,
+                                     const long long* row_ids, int n_rows, void* stream) {
+  if (!dY || !out || !G || !t || !hsum || N < 0 || H <= 0 || F <= 0 || n_rows < 0) return RG_ERR_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rows = N;
+  if (row_ids) {
+    // sparse dY (the loss touches few rows): G must alias dY with no activation, so that every other row of G is
+    // already the zero it has to be; t / hsum of the other rows are zero
+    if (apply_elu || g_is_bf16 || G != static_cast<const void*>(dY)) return RG_ERR_ARG;
+    cudaError_t e = cudaMemsetAsync(t, 0, sizeof(float) * static_cast<size_t>(N) * H, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(hsum, 0, sizeof(float) * static_cast<size_t>(N) * H, s);
+    if (e != cudaSuccess) return cuda_status(e);
+    rows = n_rows;
+  }
   if (g_is_bf16) {
     if (F % 8 != 0) return RG_ERR_SHAPE;
     if (!al16(dY) || !al16(out) || !al16(G)) return RG_ERR_ALIGN;
     const int hg = pick_heads_per_warp(H, F, 8);
     if (!hg) return RG_ERR_SHAPE;
-    PrepArgs<__nv_bfloat16, 8> a{dY, out, bias, static_cast<__nv_bfloat16*>(G), t, hsum, N, H, F, hg, apply_elu};
-    return launch_tasks(bwd_prep_kernel<__nv_bfloat16, 8>, a, static_cast<long long>(N) * (H / hg), s);
+    PrepArgs<__nv_bfloat16, 8> a{dY, out, bias, static_cast<__nv_bfloat16*>(G), t, hsum, rows, H, F, hg, apply_elu, row_ids};
+    return launch_tasks(bwd_prep_kernel<__nv_bfloat16, 8>, a, static_cast<long long>(rows) * (H / hg), s);
   }
   float* Gf = static_cast<float*>(G);
   if (F % 4 == 0 && al16(dY) && al16(out) && al16(G)) {
     const int hg = pick_heads_per_warp(H, F, 4);
     if (!hg) return RG_ERR_SHAPE;
-    PrepArgs<float, 4> a{dY, out, bias, Gf, t, hsum, N, H, F, hg, apply_elu};
-    return launch_tasks(bwd_prep_kernel<float, 4>, a, static_cast<long long>(N) * (H / hg), s);
+    PrepArgs<float, 4> a{dY, out, bias, Gf, t, hsum, rows, H, F, hg, apply_elu, row_ids};
+    return launch_tasks(bwd_prep_kernel<float, 4>, a, static_cast<long long>(rows) * (H / hg), s);
   }
   const int hg = pick_heads_per_warp(H, F, 1);
   if (!hg) return RG_ERR_SHAPE;
-  PrepArgs<float, 1> a{dY, out, bias, Gf, t, hsum, N, H, F, hg, apply_elu};
-  return launch_tasks(bwd_prep_kernel<float, 1>, a, static_cast<long long>(N) * (H / hg), s);
+  PrepArgs<float, 1> a{dY, out, bias, Gf, t, hsum, rows, H, F, hg, apply_elu, row_ids};
+  return launch_tasks(bwd_prep_kernel<float, 1>, a, static_cast<long long>(rows) * (H / hg), s);
 }
 
 // dP rows of split sources: ordered sum of their parts.

@@ -29,6 +29,24 @@ def _side_stream(device) -> torch.cuda.Stream:
     return _SIDE_STREAMS[key]
 
 
+# ---------------------------------------------------------------------------------------------
+# sparse-gradient hint: the scorer's backward produces a dense [N, D] gradient whose non-zero rows are the
+# <= B*(2+K) batch rows (reference model.py:136-137: x[src_ids], x[dst_ids]).  It tags that tensor with the
+# row list; the stack's backward uses the tag to compute t / hsum of the last layer from those rows only
+# (every other row is an exact zero either way).  The tag is ignored unless the tensor is untouched since
+# it was tagged (autograd may accumulate other gradients into it in place: the version counter tells).
+# ---------------------------------------------------------------------------------------------
+def mark_sparse_rows(grad: torch.Tensor, rows: torch.Tensor) -> None:
+    grad._relgat_rows = (rows, grad._version)
+
+
+def sparse_rows_of(grad: torch.Tensor) -> Optional[torch.Tensor]:
+    tag = getattr(grad, "_relgat_rows", None)
+    if tag is None or tag[1] != grad._version:
+        return None
+    return tag[0]
+
+
 class RelGATStackFunction(torch.autograd.Function):
     """out = RelGAT_L(... ELU(RelGAT_1(x0)) ...) for layers sharing one graph.
 
@@ -84,12 +102,13 @@ class RelGATStackFunction(torch.autograd.Function):
         N = g.N
         grads: List[Optional[torch.Tensor]] = [None] * (3 * L)
         dY = grad_out.contiguous()
+        nz_rows = sparse_rows_of(grad_out) if dY is grad_out else None
         owned = False
         dX = None
         for l in reversed(range(L)):
             s = ctx.saved[l]
             G, t, hsum = ops.edge_bwd_prep(dY, s["out"], s["bias"], H, F, apply_elu=(l < L - 1), inplace=owned,
-                                           g_bf16=not with_lo)
+                                           g_bf16=not with_lo, nonzero_rows=nz_rows if l == L - 1 else None)
             _, dPp, dz = ops.edge_bwd_src(s["P"], G, s["A"], s["z"], s["minv"], t, g, H, F,
                                           want_fp32=False, want_planes=True, planes_lo=with_lo)
             main = torch.cuda.current_stream(dY.device)
@@ -145,7 +164,9 @@ class GatherScoreFunction(torch.autograd.Function):
         if need_x:
             if ddv is not None:
                 d_dst = d_dst + ddv
-            dx = ops.index_add_sorted(torch.cat([d_src, d_dst], 0), torch.cat([src_ids, dst_ids], 0), x.size(0))
+            dx, keys = ops.index_add_sorted(torch.cat([d_src, d_dst], 0), torch.cat([src_ids, dst_ids], 0), x.size(0),
+                                            return_keys=True)
+            mark_sparse_rows(dx, keys)
         if need_r:
             drel = ops.index_add_sorted(d_rel, rel_ids, rel_emb.size(0))
         return None, None, dx, None, None, drel, None, None, None

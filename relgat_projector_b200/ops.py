@@ -200,9 +200,10 @@ def edge_fwd(P: torch.Tensor, A: torch.Tensor, beta: Optional[torch.Tensor], g: 
 def edge_bwd_prep(dY: torch.Tensor, out: torch.Tensor, bias: torch.Tensor, H: int, F: int,
                   apply_elu: bool, inplace: bool = False, g_bf16: bool = False,
                   G_out: Optional[torch.Tensor] = None, t_out: Optional[torch.Tensor] = None,
-                  hsum_out: Optional[torch.Tensor] = None):
+                  hsum_out: Optional[torch.Tensor] = None, nonzero_rows: Optional[torch.Tensor] = None):
     """Returns (G [N,C] fp32 or bf16, t [N,H], hsum [N,H]).  ``G_out`` / ``t_out`` / ``hsum_out``:
-    caller-owned fp32 buffers (rows of a peer table on the partitioned path)."""
+    caller-owned fp32 buffers (rows of a peer table on the partitioned path).  ``nonzero_rows`` (int64, may
+    repeat): all other rows of dY are known to be zero; used only when G can alias dY (fp32, no activation)."""
     dY = _f32c(dY, "dY")
     out = _f32c(out, "out")
     N = out.size(0)
@@ -216,9 +217,13 @@ def edge_bwd_prep(dY: torch.Tensor, out: torch.Tensor, bias: torch.Tensor, H: in
         G = dY if (inplace or not apply_elu) else torch.empty_like(dY)
     t = _out_buf(t_out, (N, H), dY.device, "t_out")
     hsum = _out_buf(hsum_out, (N, H), dY.device, "hsum_out")
+    rows = None
+    if nonzero_rows is not None and not apply_elu and not g_bf16 and G.data_ptr() == dY.data_ptr():
+        rows = _ids(nonzero_rows, "nonzero_rows")
     with torch.cuda.device(dY.device):
         rc = _lib.load().relgat_layer_bwd_prep(_lib.ptr(dY), _lib.ptr(out), _lib.ptr(bias), _lib.ptr(G), int(g_bf16),
-                                               _lib.ptr(t), _lib.ptr(hsum), N, H, F, int(apply_elu), _stream(dY))
+                                               _lib.ptr(t), _lib.ptr(hsum), N, H, F, int(apply_elu),
+                                               _lib.ptr(rows), 0 if rows is None else int(rows.numel()), _stream(dY))
     _lib.check(rc, "relgat_layer_bwd_prep")
     _count(1)
     return G, t, hsum
@@ -331,7 +336,7 @@ def score_bwd(kind: str, normalize: bool, xs, src_idx, xd, dst_idx, rel_emb, rel
 
 
 def index_add_sorted(rows: torch.Tensor, keys: torch.Tensor, n_out: int, out: Optional[torch.Tensor] = None,
-                     presorted=None):
+                     presorted=None, return_keys: bool = False):
     """out[k] (+)= ordered sum of rows whose key == k.  ``keys`` int64 [M]; rows [M, D].
     ``presorted`` = (sorted_keys, perm) of a stable sort of ``keys`` when the caller cached it."""
     rows = _f32c(rows, "rows")
@@ -340,7 +345,7 @@ def index_add_sorted(rows: torch.Tensor, keys: torch.Tensor, n_out: int, out: Op
     if out is None:
         out = torch.zeros((n_out, D), dtype=torch.float32, device=rows.device)
     if M == 0:
-        return out
+        return (out, keys) if return_keys else out
     # plumbing: stable order = deterministic sum order
     sorted_keys, perm = presorted if presorted is not None else torch.sort(keys, stable=True)
     with torch.cuda.device(rows.device):
@@ -348,7 +353,7 @@ def index_add_sorted(rows: torch.Tensor, keys: torch.Tensor, n_out: int, out: Op
                                                  M, D, int(accumulate), _stream(rows))
     _lib.check(rc, "relgat_index_add_sorted")
     _count(1)
-    return out
+    return (out, sorted_keys) if return_keys else out
 
 
 def margin_loss(score: torch.Tensor, B: int, K: int, margin: float, projection_layout: bool = False):

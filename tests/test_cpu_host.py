@@ -184,3 +184,15 @@ def test_native_sampler_is_bit_exact_with_cpython_stream():
             break
         assert np.array_equal(s_.numpy(), z[f"batch{bi}_src"])
         assert np.array_equal(dd.numpy(), z[f"batch{bi}_dst"])
+
+
+def test_sparse_row_tag_is_dropped_after_in_place_edit():
+    """functional.mark_sparse_rows / sparse_rows_of: the row list travels with the gradient tensor and is ignored
+    as soon as anything (e.g. autograd's in-place accumulation of a second gradient) has written to the tensor."""
+    from relgat_projector_b200 import functional as Fn
+    g = torch.zeros(5, 3)
+    assert Fn.sparse_rows_of(g) is None
+    Fn.mark_sparse_rows(g, torch.tensor([1, 3]))
+    assert Fn.sparse_rows_of(g).tolist() == [1, 3]
+    g.add_(1.0)
+    assert Fn.sparse_rows_of(g) is None

@@ -348,3 +348,31 @@ def test_peer_table_partition_lockstep_equals_whole_graph(dev, world, blocks):
         rows = torch.empty(64, h * f, device=dev)
         ops.pull_rows(p.t["out"].whole, p.row_id(ids), rows)
         assert torch.equal(rows, out_ref.detach()[ids])
+
+
+def test_sparse_loss_gradient_rows_give_the_dense_result(dev, monkeypatch):
+    """The scorer's backward tags its dense [N, D] gradient with the batch rows; the stack's backward then computes
+    t / hsum of the last layer from those rows only.  Same gradients, bit for bit, as with the tag ignored — and the
+    tag is really used on the fused model path."""
+    from relgat_projector_b200 import functional as Fn, ops
+    c = Case("tiny_fp64") if "tiny_fp64" in MODEL_CASES else Case(MODEL_CASES[0])
+    seen = []
+    real = ops.edge_bwd_prep
+
+    def spy(*a, **kw):
+        seen.append(kw.get("nonzero_rows") is not None)
+        return real(*a, **kw)
+
+    monkeypatch.setattr(ops, "edge_bwd_prep", spy)
+    grads = []
+    for use_tag in (True, False):
+        if not use_tag:
+            monkeypatch.setattr(Fn, "sparse_rows_of", lambda g: None)
+        m = _load_model(c, dev).eval()  # no dropout masks: the two runs must be comparable bit for bit
+        loss, _, _ = _step(m, c, dev)
+        loss.backward()
+        grads.append({n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None})
+    assert any(seen[: len(seen) // 2]) and not any(seen[len(seen) // 2:])
+    assert grads[0].keys() == grads[1].keys()
+    for n in grads[0]:
+        assert torch.equal(grads[0][n], grads[1][n]), n
