@@ -273,30 +273,32 @@ def peer_tables_available(world: int, rank: int, device) -> Tuple[bool, str]:
 # ---------------------------------------------------------------------------------------------
 # the partition: forward graph (in-edges of my destinations), backward graph (out-edges of my sources)
 # ---------------------------------------------------------------------------------------------
-class PeerPartition:
-    """Index structures of one rank.  A node table of rank g holds [own rows | pulled rows]; row v of the
-    mapped range = slot_of[owner(v)] * stride_rows + (v - lo_owner).
+class PeerIndexPlan:
+    """Pure index arithmetic of one rank's share (torch ops on whatever device the edge list lives on — the CPU
+    tests replay a whole partitioned layer from these arrays with the numpy oracle).
 
-    forward graph : in-edges of my destinations; sources renumbered into [own | forward halo]
-    backward graph: out-edges of my sources;     destinations renumbered into [own | backward halo]"""
+    A node table of rank g holds [own rows | pulled rows]; row v of the mapped range =
+    ``slot_of[owner(v)] * stride_rows + (v - lo_owner)``.
+      forward edges : in-edges of my destinations, sources renumbered into [own | forward halo]
+      backward edges: out-edges of my sources, destinations renumbered into [own | backward halo]
+    ``stride_fn(min_rows, row_bytes)`` rounds a table stride (PeerTables.stride_rows); ``agree_max`` makes all
+    ranks agree on a maximum (an all-reduce in a real run)."""
 
-    def __init__(self, edge_index: torch.Tensor, edge_type: torch.Tensor, num_nodes: int, num_rel: int,
-                 rank: int, world: int, tables: PeerTables, heads: int, out_dim: int, num_layers: int,
-                 balance: str = "edges", tag: str = "p", blocks: Optional[int] = None):
-        self.rank, self.world, self.N, self.R = rank, world, int(num_nodes), int(num_rel)
-        self.blocks = k_blocks = int(blocks if blocks is not None else PIPELINE_BLOCKS)
-        self.H, self.F, self.L = heads, out_dim, num_layers
-        self.tables = tables
+    def __init__(self, edge_index: torch.Tensor, edge_type: torch.Tensor, num_nodes: int, rank: int, world: int,
+                 slot_of: Sequence[int], stride_fn, row_bytes: Sequence[int], slot_bytes: Sequence[int],
+                 blocks: int = 1, balance: str = "edges", agree_max=None):
+        self.rank, self.world, self.N = rank, world, int(num_nodes)
+        self.blocks = k_blocks = int(blocks)
         dev = edge_index.device
         src, dst = edge_index[0], edge_index[1]
         E = int(src.numel())
         self.bounds = partition_bounds(dst, self.N, world, balance)
         self.lo, self.hi = self.bounds[rank], self.bounds[rank + 1]
         self.n_local = n = self.hi - self.lo
-        C = heads * out_dim
         starts = torch.tensor(self.bounds[:-1], device=dev, dtype=torch.int64)
         inner = torch.tensor(self.bounds[1:-1], device=dev, dtype=torch.int64)
-        slot_of = torch.tensor(tables.slot_of, device=dev, dtype=torch.int64)
+        sizes = torch.tensor([self.bounds[g + 1] - self.bounds[g] for g in range(world)], device=dev, dtype=torch.int64)
+        slot_t = torch.tensor(list(slot_of), device=dev, dtype=torch.int64)
 
         def owner_of(ids):
             return torch.bucketize(ids, inner, right=True) if world > 1 else torch.zeros_like(ids)
@@ -311,24 +313,21 @@ class PeerPartition:
             return in_f, hf, in_b, hb
 
         in_f, halo_f, in_b, halo_b = halo_of(rank)
+        self.halo_f, self.halo_b = halo_f, halo_b
         self.n_halo_f, self.n_halo_b = int(halo_f.numel()), int(halo_b.numel())
         need = n + max(self.n_halo_f, self.n_halo_b)
-        if world > 1 and tables.mode == "vmm":  # all ranks must agree on the table stride
-            t = torch.tensor([need], device=dev, dtype=torch.int64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            need = int(t.item())
-        elif world > 1:  # single-process simulation: look at every rank's halo
+        if world > 1 and agree_max is not None:  # all ranks must agree on the table stride
+            need = int(agree_max(need))
+        elif world > 1:  # single process: look at every rank's halo
             for g in range(world):
                 if g != rank:
                     _, hf, _, hb = halo_of(g)
                     need = max(need, self.bounds[g + 1] - self.bounds[g] + max(int(hf.numel()), int(hb.numel())))
-        self.stride_rows = tables.stride_rows(need, [4 * C, 4 * heads, 8 * heads])
+        self.stride_rows = int(stride_fn(need, row_bytes))
 
         def row_id(ids):
             own = owner_of(ids)
-            return slot_of[own] * self.stride_rows + (ids - starts[own])
-
-        sizes = torch.tensor([self.bounds[g + 1] - self.bounds[g] for g in range(world)], device=dev, dtype=torch.int64)
+            return slot_t[own] * self.stride_rows + (ids - starts[own])
 
         def pull_order(halo):
             """Position of every (sorted) halo id in the pulled rows, and the row count per pipeline block.
@@ -364,13 +363,11 @@ class PeerPartition:
         # forward: in-edges of my destinations, original order (stable bucketing)
         sel_f = torch.nonzero(in_f).flatten()
         self.E_fwd = int(sel_f.numel())
-        self.fwd_graph = GraphIndex(torch.stack([renumber(src[sel_f], halo_f, pos_f), dst[sel_f] - self.lo]), edge_type[sel_f],
-                                    max(n, 1), self.R, num_src_nodes=max(n + self.n_halo_f, 1), src_chunks=False)
+        self.fwd_edges = (renumber(src[sel_f], halo_f, pos_f), dst[sel_f] - self.lo, edge_type[sel_f])
         # backward: out-edges of my sources
         sel_b = torch.nonzero(in_b).flatten()
         self.E_bwd = int(sel_b.numel())
-        self.bwd_graph = GraphIndex(torch.stack([src[sel_b] - self.lo, renumber(dst[sel_b], halo_b, pos_b)]), edge_type[sel_b],
-                                    max(n + self.n_halo_b, 1), self.R, num_src_nodes=max(n, 1), fwd_chunks=False)
+        self.bwd_edges = (src[sel_b] - self.lo, renumber(dst[sel_b], halo_b, pos_b), edge_type[sel_b])
         # where the forward pass of the destination's owner stored the logit of each of my out-edges:
         # the owner's CSR order is the global stable by-destination order restricted to its range
         own_dst = owner_of(dst)
@@ -379,9 +376,43 @@ class PeerPartition:
         order = torch.argsort(dst, stable=True)
         pos = torch.empty(E, dtype=torch.int64, device=dev)
         pos[order] = torch.arange(E, device=dev)
-        self.stride_slots = tables.stride_rows(int(per_owner.max().item()) if E else 1, [4 * heads])
-        z_row = slot_of[own_dst] * self.stride_slots + (pos - first[own_dst])
-        self.z_index = z_row[sel_b][self.bwd_graph.csr_perm.long()].contiguous()  # by slot of the backward graph
+        self.stride_slots = int(stride_fn(int(per_owner.max().item()) if E else 1, slot_bytes))
+        self.z_row_bwd = (slot_t[own_dst] * self.stride_slots + (pos - first[own_dst]))[sel_b]  # per backward edge
+
+
+class PeerPartition:
+    """One rank's share on the GPU: the index plan, the two graph indexes built from it, and the peer tables."""
+
+    def __init__(self, edge_index: torch.Tensor, edge_type: torch.Tensor, num_nodes: int, num_rel: int,
+                 rank: int, world: int, tables: PeerTables, heads: int, out_dim: int, num_layers: int,
+                 balance: str = "edges", tag: str = "p", blocks: Optional[int] = None):
+        self.rank, self.world, self.N, self.R = rank, world, int(num_nodes), int(num_rel)
+        self.H, self.F, self.L = heads, out_dim, num_layers
+        self.tables = tables
+        dev = edge_index.device
+        C = heads * out_dim
+
+        def agree_max(value: int) -> int:
+            t = torch.tensor([value], device=dev, dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return int(t.item())
+
+        plan = PeerIndexPlan(edge_index, edge_type, num_nodes, rank, world, tables.slot_of, tables.stride_rows,
+                             [4 * C, 4 * heads, 8 * heads], [4 * heads],
+                             blocks=int(blocks if blocks is not None else PIPELINE_BLOCKS), balance=balance,
+                             agree_max=agree_max if (world > 1 and tables.mode == "vmm") else None)
+        self.plan = plan
+        for name in ("bounds", "lo", "hi", "n_local", "blocks", "stride_rows", "stride_slots", "n_halo_f", "n_halo_b",
+                     "pull_f", "pull_b", "blk_f", "blk_b", "row_blocks", "E_fwd", "E_bwd", "owner_of", "row_id"):
+            setattr(self, name, getattr(plan, name))
+        n = self.n_local
+        fs, fd, fr = plan.fwd_edges
+        self.fwd_graph = GraphIndex(torch.stack([fs, fd]), fr, max(n, 1), self.R,
+                                    num_src_nodes=max(n + self.n_halo_f, 1), src_chunks=False)
+        bs, bd, br = plan.bwd_edges
+        self.bwd_graph = GraphIndex(torch.stack([bs, bd]), br, max(n + self.n_halo_b, 1), self.R,
+                                    num_src_nodes=max(n, 1), fwd_chunks=False)
+        self.z_index = plan.z_row_bwd[self.bwd_graph.csr_perm.long()].contiguous()  # by slot of the backward graph
         specs = []
         for l in range(num_layers):
             specs += [(f"P{l}", self.stride_rows, (C,), torch.float32), (f"G{l}", self.stride_rows, (C,), torch.float32),
