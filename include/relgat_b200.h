@@ -74,7 +74,7 @@ int relgat_gemm_bf16(const void* a_hi, const void* a_lo, long long lda, int a_mn
  * A: [H, R, F] (stacked attn_vec), beta: [R] or NULL.
  * Work tables (built once per graph, see relgat_projector_b200/graph.py StreamChunks):
  *   chunks int32[n_chunks][4] = (first destination, count <= 64, part slot or -1, 0): the CSR edge
- *     array cut at destination boundaries into ~64-edge chunks; one warp streams one chunk, so
+ *     array cut at destination boundaries into ~32-edge chunks; one warp streams one chunk, so
  *     short segments do not drain the load pipeline;
  *   parts int32[n_parts][2] = (first edge, end edge): a destination with more than 512 in-edges is
  *     split into 256-edge parts (one chunk each) whose partial softmax states (part_ml [n_parts,H,2],

@@ -77,9 +77,10 @@ __global__ void __launch_bounds__(kBwdWarps * 32) bwd_prep_kernel(const PrepArgs
 
 // ------------------------------------------------------------------------------------
 // bwd_src — edge-balanced streaming over the by-source (CSC) order.
-// The CSC edge array is cut at source boundaries into chunks of ~64 edges (graph.py:
-// src_chunk_node).  Persistent CTAs (one per SM, 12 warps) own one head-group and keep its
-// attention vectors in shared memory; a warp streams one chunk at a time as a sequence of row
+// The CSC edge array is cut at source boundaries into chunks of ~32 edges (graph.py: StreamChunks;
+// sources with more than 512 out-edges are split into 256-edge parts merged by bwd_src_merge_kernel).
+// Persistent CTAs (one per SM, 12 warps) own one head-group and keep its attention vectors in shared
+// memory; a warp claims one chunk at a time (atomic work counter) and streams it as a sequence of row
 // "items": OWN(i) = the source's own P row (needed for dalpha = <G[dst], P[i]>; parked in a
 // lane-private shared-memory slot), followed by one EDGE item per out-edge (the gathered G[dst]
 // row).  Two items are in flight per warp and the pipeline does not drain at source boundaries.

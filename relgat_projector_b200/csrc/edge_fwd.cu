@@ -3,8 +3,10 @@
 // weighted aggregation and relation bias in ONE pass over the CSR (by-destination) edges.
 //
 // Work decomposition: the CSR edge array is cut, at destination boundaries, into chunks of
-// ~64 edges (graph.py: fwd_chunk_node).  Persistent CTAs (one per SM, 12 warps) own one head-group
-// and keep its attention vectors in shared memory; a warp streams one chunk at a time: the source
+// ~32 edges (graph.py: StreamChunks; destinations with more than 512 in-edges are split into 256-edge
+// parts merged by edge_fwd_merge_kernel).  Persistent CTAs (one per SM, 12 warps) own one head-group
+// and keep its attention vectors in shared memory; a warp claims one chunk at a time (atomic work
+// counter: the tail of a static assignment cost more than the claims) and streams it: the source
 // rows P[src] are gathered with 128-bit streaming loads, two rows in flight per warp, and the
 // pipeline does not drain at destination boundaries — a destination is "finalised" (normalise,
 // add bias, write the row, save the softmax statistics) when the stream crosses into the next
