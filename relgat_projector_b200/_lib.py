@@ -53,6 +53,7 @@ SIGNATURES = {
     "relgat_pull_rows": (_I, [_P, _L, _P, _L, _I, _P, _L, _I, _P]),
 }
 
+ABI_VERSION = 2  # bumped whenever a signature in include/relgat_b200.h changes
 _lib = None
 
 
@@ -77,7 +78,7 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError = ABI mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.relgat_abi_version() != 1:
+    if lib.relgat_abi_version() != ABI_VERSION:
         raise RuntimeError("librelgat_b200.so: ABI version mismatch, rebuild with relgat_projector_b200/build.py")
     _lib = lib
     return lib
