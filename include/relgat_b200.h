@@ -101,7 +101,8 @@ int relgat_layer_fwd(const void* P, int p_is_bf16, long long ldp, const float* A
  * bwd_prep: G = dY * act'(out) (fp32: in place allowed; or written as bf16), t[N,H] = <G, out - bias>,
  *           hsum[N,H] = sum_f G.  row_ids (int64[n_rows], may repeat; NULL = all rows): the caller knows that
  *           only these rows of dY are non-zero (the loss reads B*(2+K) rows: reference model.py:136-137) — then
- *           G must alias dY, apply_elu = 0, and only those rows are read; t / hsum of all other rows are set to 0.
+ *           apply_elu must be 0 and G fp32; only those rows are read (and, when G does not alias dY, written: the
+ *           caller keeps every other row of G at zero); t / hsum of all other rows are set to 0.
  * bwd_src : by-source pass over chunks of the CSC order (work tables as in fwd, over sources;
  *           part_acc [n_parts, H*F] holds the partial rows of split sources):
  *           dP [N_src, H*F] (fp32 and/or bf16 hi/lo planes) and dz [E, H]; the attention weights
@@ -185,11 +186,12 @@ int relgat_peer_table_map(int device, int world, int rank, unsigned long long ow
                           unsigned long long bytes, void** base);
 int relgat_peer_table_unmap(void* base, int world, unsigned long long bytes, unsigned long long own_handle);
 int relgat_peer_table_last_driver_error(void);
-/* halo pull (device): out[i, :] = table[ids[i], :] for i < n; ids int64 row numbers of the mapped range
- * (a peer's rows arrive over NVLink), D floats per row, ld / ldo row strides in floats.  Run between the
- * writers' rendezvous and the edge kernel that consumes [own rows | pulled rows]. */
-int relgat_pull_rows(const float* table, long long ld, const long long* ids, long long n, int D,
-                     float* out, long long ldo, int sm_count, void* stream);
+/* halo pull (device): out[o(i), :] = table[ids[i], :] for i < n, o(i) = out_ids[i] (NULL: o(i) = i); ids int64 row
+ * numbers of the mapped range (a peer's rows arrive over NVLink), D floats per row, ld / ldo row strides in
+ * floats.  Run between the writers' rendezvous and the edge kernel that consumes [own rows | pulled rows].
+ * Rows with equal out_ids must carry equal data (the batch may name a node twice). */
+int relgat_pull_rows(const float* table, long long ld, const long long* ids, const long long* out_ids,
+                     long long n, int D, float* out, long long ldo, int sm_count, void* stream);
 
 #ifdef __cplusplus
 }

@@ -50,7 +50,7 @@ SIGNATURES = {
     "relgat_peer_table_map": (_I, [_I, _I, _I, c_ulonglong, _P, c_ulonglong, _P]),
     "relgat_peer_table_unmap": (_I, [_P, _I, c_ulonglong, c_ulonglong]),
     "relgat_peer_table_last_driver_error": (_I, []),
-    "relgat_pull_rows": (_I, [_P, _L, _P, _L, _I, _P, _L, _I, _P]),
+    "relgat_pull_rows": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _I, _P]),
 }
 
 ABI_VERSION = 2  # bumped whenever a signature in include/relgat_b200.h changes

@@ -523,9 +523,9 @@ extern "C" int relgat_layer_bwd_prep(const float* dY, const float* out, const fl
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int rows = N;
   if (row_ids) {
-    // sparse dY (the loss touches few rows): G must alias dY with no activation, so that every other row of G is
-    // already the zero it has to be; t / hsum of the other rows are zero
-    if (apply_elu || g_is_bf16 || G != static_cast<const void*>(dY)) return RG_ERR_ARG;
+    // sparse dY (the loss touches few rows), no activation: only the listed rows are read; G either aliases dY or is a
+    // buffer whose other rows the caller keeps at zero (peer tables); t / hsum of the other rows are zero
+    if (apply_elu || g_is_bf16) return RG_ERR_ARG;
     cudaError_t e = cudaMemsetAsync(t, 0, sizeof(float) * static_cast<size_t>(N) * H, s);
     if (e == cudaSuccess) e = cudaMemsetAsync(hsum, 0, sizeof(float) * static_cast<size_t>(N) * H, s);
     if (e != cudaSuccess) return cuda_status(e);

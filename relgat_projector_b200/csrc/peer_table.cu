@@ -148,8 +148,8 @@ constexpr int kPullThreads = 256;
 
 template <int V, int kPullUnroll>
 __global__ void __launch_bounds__(kPullThreads)
-pull_rows_kernel(const float* __restrict__ table, long long ld, const long long* __restrict__ ids, long long n, int D,
-                 float* __restrict__ out, long long ldo) {
+pull_rows_kernel(const float* __restrict__ table, long long ld, const long long* __restrict__ ids,
+                 const long long* __restrict__ out_ids, long long n, int D, float* __restrict__ out, long long ldo) {
   const int dv = D / V;  // vectors per row
   const long long total = n * dv;
   const long long stride = static_cast<long long>(gridDim.x) * kPullThreads;
@@ -170,14 +170,14 @@ pull_rows_kernel(const float* __restrict__ table, long long ld, const long long*
     }
 #pragma unroll
     for (int u = 0; u < kPullUnroll; ++u)
-      if (row[u] >= 0) RowVec<float, V>::store(out + row[u] * ldo + q[u] * V, v[u]);
+      if (row[u] >= 0) RowVec<float, V>::store(out + (out_ids ? __ldg(out_ids + row[u]) : row[u]) * ldo + q[u] * V, v[u]);
   }
 }
 
 }  // namespace relgat
 
-extern "C" int relgat_pull_rows(const float* table, long long ld, const long long* ids, long long n, int D,
-                                float* out, long long ldo, int sm_count, void* stream) {
+extern "C" int relgat_pull_rows(const float* table, long long ld, const long long* ids, const long long* out_ids,
+                                long long n, int D, float* out, long long ldo, int sm_count, void* stream) {
   using namespace relgat;
   if (n < 0 || D <= 0 || ld < D || ldo < D) return RG_ERR_ARG;
   if (n == 0) return RG_OK;
@@ -204,7 +204,7 @@ extern "C" int relgat_pull_rows(const float* table, long long ld, const long lon
     static const cudaError_t carve = cudaFuncSetAttribute(                                                  \
         pull_rows_kernel<V_, U_>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
     (void)carve;                                                                                            \
-    pull_rows_kernel<V_, U_><<<blocks, kPullThreads, 0, s>>>(table, ld, ids, n, D, out, ldo);               \
+    pull_rows_kernel<V_, U_><<<blocks, kPullThreads, 0, s>>>(table, ld, ids, out_ids, n, D, out, ldo);               \
   } while (0)
   if (vec) {
     if (unroll == 8) RG_PULL(4, 8);

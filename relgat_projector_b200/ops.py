@@ -218,8 +218,8 @@ def edge_bwd_prep(dY: torch.Tensor, out: torch.Tensor, bias: torch.Tensor, H: in
     t = _out_buf(t_out, (N, H), dY.device, "t_out")
     hsum = _out_buf(hsum_out, (N, H), dY.device, "hsum_out")
     rows = None
-    if nonzero_rows is not None and not apply_elu and not g_bf16 and G.data_ptr() == dY.data_ptr():
-        rows = _ids(nonzero_rows, "nonzero_rows")
+    if nonzero_rows is not None and not apply_elu and not g_bf16 and (G.data_ptr() == dY.data_ptr() or G_out is not None):
+        rows = _ids(nonzero_rows, "nonzero_rows")  # with G_out the caller keeps the other rows of G at zero
     with torch.cuda.device(dY.device):
         rc = _lib.load().relgat_layer_bwd_prep(_lib.ptr(dY), _lib.ptr(out), _lib.ptr(bias), _lib.ptr(G), int(g_bf16),
                                                _lib.ptr(t), _lib.ptr(hsum), N, H, F, int(apply_elu),
@@ -371,21 +371,27 @@ def margin_loss(score: torch.Tensor, B: int, K: int, margin: float, projection_l
     return loss, dscore
 
 
-def pull_rows(table: torch.Tensor, ids: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
-    """out[i] = table[ids[i]] (rows of a mapped peer table -> local rows).  ``table`` / ``out``: fp32 with
-    unit inner stride, any number of trailing dims (flattened); ``ids`` int64."""
+def pull_rows(table: torch.Tensor, ids: torch.Tensor, out: torch.Tensor, out_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[i] = table[ids[i]] (rows of a mapped peer table -> local rows); with ``out_ids`` the rows are scattered:
+    out[out_ids[i]] = table[ids[i]].  ``table`` / ``out``: fp32 with unit inner stride, any number of trailing dims
+    (flattened); ``ids`` / ``out_ids`` int64."""
     _lib.require_cuda(table, ids, out)
     if table.dtype != torch.float32 or out.dtype != torch.float32 or ids.dtype != torch.int64:
         raise TypeError("pull_rows: table / out must be float32 and ids int64")
     n = int(ids.numel())
     D = int(table[0].numel()) if table.size(0) else int(out[0].numel())
-    if out.size(0) != n or (n and int(out[0].numel()) != D) or not table.is_contiguous() or not out.is_contiguous():
-        raise ValueError("pull_rows: out must be a contiguous [len(ids), ...] tensor with the table's row shape")
+    if out_ids is None and out.size(0) != n:
+        raise ValueError("pull_rows: out must have len(ids) rows")
+    if out_ids is not None and (out_ids.dtype != torch.int64 or out_ids.numel() != n):
+        raise ValueError("pull_rows: out_ids must be int64 with len(ids) entries")
+    if (out.size(0) and int(out[0].numel()) != D) or not table.is_contiguous() or not out.is_contiguous():
+        raise ValueError("pull_rows: out must be a contiguous tensor with the table's row shape")
     if n == 0:
         return out
     with torch.cuda.device(out.device):
-        rc = _lib.load().relgat_pull_rows(_lib.ptr(table), D, _lib.ptr(ids.contiguous()), n, D, _lib.ptr(out), D,
-                                          sm_count(out.device), _stream(out))
+        rc = _lib.load().relgat_pull_rows(_lib.ptr(table), D, _lib.ptr(ids.contiguous()),
+                                          _lib.ptr(None if out_ids is None else out_ids.contiguous()), n, D,
+                                          _lib.ptr(out), D, sm_count(out.device), _stream(out))
     _lib.check(rc, "relgat_pull_rows")
     _count(1)
     return out

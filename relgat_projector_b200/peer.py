@@ -41,7 +41,7 @@ import torch.distributed as dist
 
 from . import _lib, ops
 from .dist import allreduce_grads, partition_bounds
-from .functional import _side_stream
+from .functional import _side_stream, mark_sparse_rows, sparse_rows_of
 from .graph import GraphIndex
 
 
@@ -51,6 +51,9 @@ DEEP_OVERLAP = os.environ.get("RELGAT_PEER_DEEP_OVERLAP", "1") != "0"
 # Measured on 2 GPUs (three sweeps): 4 blocks are 0.3-1.0 ms/step (2-5 %) faster than 1; the overlap is far from
 # complete (the pull and the GEMM compete for the same SMs), see DESIGN.md section 6.
 PIPELINE_BLOCKS = max(1, int(os.environ.get("RELGAT_PEER_BLOCKS", "4")))
+# last layer's backward: dY is zero outside the batch rows, so only those rows of G / t / hsum are written, pulled
+# and (afterwards) cleared — instead of moving a dense, almost-all-zero halo over NVLink
+SPARSE_LAST = os.environ.get("RELGAT_PEER_SPARSE_LAST", "1") != "0"
 _COMM_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
 
 # poor man's timeline (nsys is not in the image): RELGAT_PEER_TRACE=1 records a CUDA event per phase boundary on the
@@ -315,14 +318,14 @@ class PeerIndexPlan:
         in_f, halo_f, in_b, halo_b = halo_of(rank)
         self.halo_f, self.halo_b = halo_f, halo_b
         self.n_halo_f, self.n_halo_b = int(halo_f.numel()), int(halo_b.numel())
-        need = n + max(self.n_halo_f, self.n_halo_b)
+        need = n + max(self.n_halo_f, self.n_halo_b) + 1  # + one trash row behind the pulled rows (sparse pulls)
         if world > 1 and agree_max is not None:  # all ranks must agree on the table stride
             need = int(agree_max(need))
         elif world > 1:  # single process: look at every rank's halo
             for g in range(world):
                 if g != rank:
                     _, hf, _, hb = halo_of(g)
-                    need = max(need, self.bounds[g + 1] - self.bounds[g] + max(int(hf.numel()), int(hb.numel())))
+                    need = max(need, self.bounds[g + 1] - self.bounds[g] + max(int(hf.numel()), int(hb.numel())) + 1)
         self.stride_rows = int(stride_fn(need, row_bytes))
 
         def row_id(ids):
@@ -358,6 +361,7 @@ class PeerIndexPlan:
         self.owner_of, self.row_id = owner_of, row_id
         perm_f, pos_f, self.blk_f = pull_order(halo_f)
         perm_b, pos_b, self.blk_b = pull_order(halo_b)
+        self.pos_b = pos_b  # position of every (sorted) backward-halo id among the pulled rows
         self.pull_f, self.pull_b = row_id(halo_f[perm_f]), row_id(halo_b[perm_b])  # rows of the mapped range to pull
         self.row_blocks = [(-(-c * n // k_blocks), -(-(c + 1) * n // k_blocks)) for c in range(k_blocks)]  # own rows per block
         # forward: in-edges of my destinations, original order (stable bucketing)
@@ -403,7 +407,8 @@ class PeerPartition:
                              agree_max=agree_max if (world > 1 and tables.mode == "vmm") else None)
         self.plan = plan
         for name in ("bounds", "lo", "hi", "n_local", "blocks", "stride_rows", "stride_slots", "n_halo_f", "n_halo_b",
-                     "pull_f", "pull_b", "blk_f", "blk_b", "row_blocks", "E_fwd", "E_bwd", "owner_of", "row_id"):
+                     "pull_f", "pull_b", "blk_f", "blk_b", "row_blocks", "E_fwd", "E_bwd", "owner_of", "row_id",
+                     "halo_b", "pos_b"):
             setattr(self, name, getattr(plan, name))
         n = self.n_local
         fs, fd, fr = plan.fwd_edges
@@ -423,6 +428,21 @@ class PeerPartition:
         specs.append(("out", self.stride_rows, (C,), torch.float32))
         self.t = tables.allocate(specs, tag=tag)
         self._token = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.batch_ids: Optional[torch.Tensor] = None  # node ids of the current batch (set by PeerBatchRows)
+        self._sparse_clean = False  # last layer's G / t / hsum tables hold zeros outside the rows listed in _dirty
+        self._dirty: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+
+    def sparse_halo_targets(self, ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """For batch node ids: (rows of the mapped range to read, rows of the own table to write) so that every batch
+        node among this rank's backward halo lands in its pulled slot.  Ids that are not in the halo read own row 0
+        into the trash row behind the pulled block (no host synchronisation, fixed list length)."""
+        n, nh = self.n_local, self.n_halo_b
+        if nh == 0:
+            return torch.zeros_like(ids), torch.full_like(ids, n)
+        at = torch.searchsorted(self.halo_b, ids).clamp_(max=nh - 1)
+        hit = self.halo_b[at] == ids
+        pos = self.pos_b[at]
+        return torch.where(hit, self.pull_b[pos], torch.zeros_like(ids)), torch.where(hit, n + pos, torch.full_like(ids, n + nh))
 
     def sync(self) -> None:
         """Stream-ordered rendezvous of all ranks (see module docstring)."""
@@ -501,19 +521,51 @@ def backward_steps(part: PeerPartition, grad_out: torch.Tensor, saved: list, wit
         with torch.cuda.stream(comm):  # 4·H bytes per out-edge, from the logits' owners (written in the forward pass)
             ops.pull_rows(T[f"z{l}"].whole, part.z_index, z)
         _mark(f"bwd{l} start")
-        for c, (r0, r1) in enumerate(part.row_blocks):
-            if r1 > r0:
-                ops.edge_bwd_prep(dY[r0:r1], s["out"][r0:r1], s["bias"][r0:r1], H, F, apply_elu=(l < L - 1),
-                                  G_out=T[f"G{l}"].local[r0:r1], t_out=T[f"t{l}"].local[r0:r1],
-                                  hsum_out=T[f"hsum{l}"].local[r0:r1])
-            _mark(f"bwd{l} prep block {c} done")
-            yield  # every rank's block c of G / t / hsum is written
-            _mark(f"bwd{l} rendezvous {c} done")
+        rows_own = sparse_rows_of(grad_out) if (SPARSE_LAST and l == L - 1 and dY is grad_out) else None
+        if rows_own is not None and part.batch_ids is not None:
+            # dY is zero outside the batch rows: write / pull / clear only those rows of G, t, hsum
+            nh = part.n_halo_b
+            G_t, t_t, h_t = T[f"G{l}"], T[f"t{l}"], T[f"hsum{l}"]
+            if not part._sparse_clean:
+                G_t.local[:n + nh + 1].zero_()
+                t_t.local[n:n + nh + 1].zero_()
+                h_t.local[n:n + nh + 1].zero_()
+                part._sparse_clean = True
+            elif part._dirty is not None:  # rows the previous step wrote (every rank has long finished reading them)
+                own_prev, halo_prev = part._dirty
+                G_t.local.index_fill_(0, own_prev, 0.0)
+                for tb in (G_t, t_t, h_t):
+                    tb.local.index_fill_(0, halo_prev, 0.0)
+            ops.edge_bwd_prep(dY, s["out"], s["bias"], H, F, apply_elu=False, G_out=G_t.local[:n],
+                              t_out=t_t.local[:n], hsum_out=h_t.local[:n], nonzero_rows=rows_own)
+            _mark(f"bwd{l} sparse prep done")
+            yield  # every rank's batch rows of G / t / hsum are written
+            _mark(f"bwd{l} rendezvous done")
+            src_rows, dst_rows = part.sparse_halo_targets(part.batch_ids)
             comm.wait_stream(main)
-            with torch.cuda.stream(comm):  # beside the prep of block c+1
-                G_ext = part.pull(f"G{l}", part.pull_b, part.blk_b, c)
-                t_ext, minv_ext, hsum_ext = (part.pull(f"{k}{l}", part.pull_b, part.blk_b, c) for k in ("t", "minv", "hsum"))
-                _mark(f"bwd{l} pull block {c} done", "comm")
+            with torch.cuda.stream(comm):
+                for tb in (G_t, t_t, h_t):
+                    ops.pull_rows(tb.whole, src_rows, tb.local, out_ids=dst_rows)
+                minv_ext = part.pull(f"minv{l}", part.pull_b)
+                _mark(f"bwd{l} sparse pulls done", "comm")
+            G_ext, t_ext, hsum_ext = G_t.local[:n + nh], t_t.local[:n + nh], h_t.local[:n + nh]
+            part._dirty = (rows_own, dst_rows)
+        else:
+            if l == L - 1:
+                part._sparse_clean = False
+            for c, (r0, r1) in enumerate(part.row_blocks):
+                if r1 > r0:
+                    ops.edge_bwd_prep(dY[r0:r1], s["out"][r0:r1], s["bias"][r0:r1], H, F, apply_elu=(l < L - 1),
+                                      G_out=T[f"G{l}"].local[r0:r1], t_out=T[f"t{l}"].local[r0:r1],
+                                      hsum_out=T[f"hsum{l}"].local[r0:r1])
+                _mark(f"bwd{l} prep block {c} done")
+                yield  # every rank's block c of G / t / hsum is written
+                _mark(f"bwd{l} rendezvous {c} done")
+                comm.wait_stream(main)
+                with torch.cuda.stream(comm):  # beside the prep of block c+1
+                    G_ext = part.pull(f"G{l}", part.pull_b, part.blk_b, c)
+                    t_ext, minv_ext, hsum_ext = (part.pull(f"{k}{l}", part.pull_b, part.blk_b, c) for k in ("t", "minv", "hsum"))
+                    _mark(f"bwd{l} pull block {c} done", "comm")
         main.wait_stream(comm)
         _mark(f"bwd{l} pulls joined")
         P_loc = T[f"P{l}"].local[:n]
@@ -618,15 +670,18 @@ class PeerBatchRows(torch.autograd.Function):
         ops.pull_rows(part.t["out"].whole, part.row_id(ids), rows)
         mine = (ids >= part.lo) & (ids < part.hi)
         # rows of other ranks get one scratch row each (a shared scratch row would be one long serial segment)
-        ctx.save_for_backward(torch.where(mine, ids - part.lo, n + torch.arange(ids.numel(), device=ids.device)))
+        ctx.save_for_backward(torch.where(mine, ids - part.lo, n + torch.arange(ids.numel(), device=ids.device)),
+                              torch.where(mine, ids - part.lo, torch.zeros_like(ids)))
         ctx.n_local = n
+        part.batch_ids = ids
         return rows
 
     @staticmethod
     def backward(ctx, grad_rows):
-        (keys,) = ctx.saved_tensors
-        dx = ops.index_add_sorted(grad_rows.contiguous(), keys, ctx.n_local + keys.numel())
-        return dx[:ctx.n_local], None, None
+        keys, rows_own = ctx.saved_tensors
+        dx = ops.index_add_sorted(grad_rows.contiguous(), keys, ctx.n_local + keys.numel())[:ctx.n_local]
+        mark_sparse_rows(dx, rows_own)  # own batch rows (row 0 stands in for rows of other ranks: harmless, see peer.py)
+        return dx, None, None
 
 
 class PeerRelGAT:

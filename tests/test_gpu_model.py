@@ -376,3 +376,60 @@ def test_sparse_loss_gradient_rows_give_the_dense_result(dev, monkeypatch):
     assert grads[0].keys() == grads[1].keys()
     for n in grads[0]:
         assert torch.equal(grads[0][n], grads[1][n]), n
+
+
+def test_peer_table_sparse_last_layer_backward(dev):
+    """Peer-table path, last layer's backward with a batch-sparse dY: only the batch rows of G / t / hsum are written,
+    pulled and cleared.  Three rounds on the same forward (sparse, sparse with another batch, dense, sparse again)
+    must each reproduce the unpartitioned stack's gradients."""
+    from relgat_projector_b200 import functional as Fn, graph as G, ops, peer as RP
+    from relgat_projector_b200 import synthetic as S
+    world, n, r, d_in, h, f, L_ = 3, 700, 6, 48, 4, 16, 2
+    kg = S.tensor_kg(n, 5000, r, d_in, seed=21, device=str(dev), skew=0.7)
+    gen = torch.Generator(device="cpu").manual_seed(9)
+    params = []
+    for l in range(L_):
+        di = d_in if l == 0 else h * f
+        params += [(torch.randn(h * f, di, generator=gen) / di ** 0.5).to(dev).requires_grad_(True),
+                   (torch.randn(h, r, f, generator=gen) * 0.3).to(dev).requires_grad_(True),
+                   (torch.randn(r, generator=gen) * 0.1).to(dev).requires_grad_(True)]
+    x0 = kg.node_emb.clone().requires_grad_(True)
+    g_full = G.GraphIndex(kg.edge_index, kg.edge_type, n, r)
+    store = {}
+    parts = [RP.PeerPartition(kg.edge_index, kg.edge_type, n, r, rk, world,
+                              RP.PeerTables(world, rk, dev, mode="sim", sim_store=store), h, f, L_, blocks=2)
+             for rk in range(world)]
+    saved = [[] for _ in range(world)]
+    x_loc = [x0.detach()[p.lo:p.hi].contiguous() for p in parts]
+    RP.drive_lockstep([RP.forward_steps(parts[k], ops.split_bf16(x_loc[k]), [t.detach() for t in params], True,
+                                        saved[k], x0_needs_grad=True) for k in range(world)])
+
+    def run(ids, sparse):
+        dense = torch.zeros(n, h * f, device=dev)
+        uniq = torch.unique(ids)
+        dense[uniq] = torch.randn(uniq.numel(), h * f, generator=gen).to(dev)
+        out_again = Fn.RelGATStackFunction.apply(x0, g_full, h, f, "fp32", None, *params)  # its backward runs once
+        ref = torch.autograd.grad(out_again, [x0] + params, dense)
+        gens = []
+        for p in parts:
+            dx = dense[p.lo:p.hi].clone()
+            if sparse:
+                mine = (ids >= p.lo) & (ids < p.hi)
+                Fn.mark_sparse_rows(dx, torch.where(mine, ids - p.lo, torch.zeros_like(ids)))
+                p.batch_ids = ids
+            gens.append(RP.backward_steps(p, dx, saved[parts.index(p)], True, x0_needs_grad=True))
+        res = RP.drive_lockstep(gens)
+        for p, (dxk, _) in zip(parts, res):
+            assert rel_err(dxk.cpu().numpy(), ref[0][p.lo:p.hi].cpu().numpy()) < 1e-5
+        for i in range(len(params)):
+            total = sum(res[k][1][i] for k in range(world))
+            assert rel_err(total.cpu().numpy(), ref[1 + i].cpu().numpy()) < FP32_TOL, (i, sparse)
+
+    ids_a = torch.randint(0, n, (96,), generator=gen).to(dev)
+    ids_b = torch.randint(0, n, (96,), generator=gen).to(dev)
+    run(ids_a, sparse=True)
+    assert all(p._sparse_clean and p._dirty is not None for p in parts)
+    run(ids_b, sparse=True)   # clears the rows of the first batch
+    run(ids_a, sparse=False)  # dense pass dirties the tables
+    assert not any(p._sparse_clean for p in parts)
+    run(ids_b, sparse=True)   # ... and the next sparse pass re-zeroes them
