@@ -384,6 +384,19 @@ class PeerIndexPlan:
         self.z_row_bwd = (slot_t[own_dst] * self.stride_slots + (pos - first[own_dst]))[sel_b]  # per backward edge
 
 
+    def sparse_halo_targets(self, ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """For batch node ids: (rows of the mapped range to read, rows of the own table to write) so that every batch
+        node among this rank's backward halo lands in its pulled slot.  Ids that are not in the halo read own row 0
+        into the trash row behind the pulled block (no host synchronisation, fixed list length)."""
+        n, nh = self.n_local, self.n_halo_b
+        if nh == 0:
+            return torch.zeros_like(ids), torch.full_like(ids, n)
+        at = torch.searchsorted(self.halo_b, ids).clamp_(max=nh - 1)
+        hit = self.halo_b[at] == ids
+        pos = self.pos_b[at]
+        return torch.where(hit, self.pull_b[pos], torch.zeros_like(ids)), torch.where(hit, n + pos, torch.full_like(ids, n + nh))
+
+
 class PeerPartition:
     """One rank's share on the GPU: the index plan, the two graph indexes built from it, and the peer tables."""
 
@@ -433,16 +446,7 @@ class PeerPartition:
         self._dirty: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
 
     def sparse_halo_targets(self, ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """For batch node ids: (rows of the mapped range to read, rows of the own table to write) so that every batch
-        node among this rank's backward halo lands in its pulled slot.  Ids that are not in the halo read own row 0
-        into the trash row behind the pulled block (no host synchronisation, fixed list length)."""
-        n, nh = self.n_local, self.n_halo_b
-        if nh == 0:
-            return torch.zeros_like(ids), torch.full_like(ids, n)
-        at = torch.searchsorted(self.halo_b, ids).clamp_(max=nh - 1)
-        hit = self.halo_b[at] == ids
-        pos = self.pos_b[at]
-        return torch.where(hit, self.pull_b[pos], torch.zeros_like(ids)), torch.where(hit, n + pos, torch.full_like(ids, n + nh))
+        return self.plan.sparse_halo_targets(ids)
 
     def sync(self) -> None:
         """Stream-ordered rendezvous of all ranks (see module docstring)."""

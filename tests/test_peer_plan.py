@@ -118,3 +118,33 @@ def test_plan_world1_and_empty_rank():
     plans = [RP.PeerIndexPlan(ei2, et, 40, rk, 2, [(o - rk) % 2 for o in range(2)], lambda m, b: max(m, 1), [16], [16],
                               balance="nodes") for rk in range(2)]
     assert plans[1].E_fwd == 0 and plans[0].E_fwd == 200 and plans[0].E_bwd + plans[1].E_bwd == 200
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sparse_halo_targets_equal_the_dense_pull(world):
+    """Batch-sparse last layer: scattering only the batch rows that sit in a rank's backward halo into a zeroed pulled
+    block gives the same [own | pulled] table as pulling the whole (almost-all-zero) halo."""
+    n, e, r, w = 90, 1000, 4, 5
+    src, dst, rel = _graph(11 + world, n, e, r)
+    ei, et = torch.from_numpy(np.stack([src, dst])), torch.from_numpy(rel)
+    plans = [RP.PeerIndexPlan(ei, et, n, rk, world, [(o - rk) % world for o in range(world)],
+                              lambda m, b: max(m, 1), [16], [16], blocks=2) for rk in range(world)]
+    stride = plans[0].stride_rows
+    rng = np.random.default_rng(5)
+    ids = rng.integers(0, n, size=40)  # with repeats
+    G = np.zeros((n, w))
+    G[np.unique(ids)] = rng.standard_normal((len(np.unique(ids)), w))
+    tabs = []
+    for p in plans:
+        tb = np.zeros((stride, w))
+        tb[: p.n_local] = G[p.lo:p.hi]
+        tabs.append(tb)
+    for rk, p in enumerate(plans):
+        view = _mapped_view(tabs, rk, world)
+        dense = np.concatenate([G[p.lo:p.hi], view[p.pull_b.numpy()]], 0)
+        src_rows, dst_rows = (x.numpy() for x in p.sparse_halo_targets(torch.from_numpy(ids)))
+        assert len(src_rows) == len(ids) and dst_rows.max() <= p.n_local + p.n_halo_b < stride
+        local = np.zeros((stride, w))
+        local[: p.n_local] = G[p.lo:p.hi]
+        local[dst_rows] = view[src_rows]
+        np.testing.assert_array_equal(local[: p.n_local + p.n_halo_b], dense)
