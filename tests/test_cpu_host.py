@@ -196,3 +196,27 @@ def test_sparse_row_tag_is_dropped_after_in_place_edit():
     assert Fn.sparse_rows_of(g).tolist() == [1, 3]
     g.add_(1.0)
     assert Fn.sparse_rows_of(g) is None
+
+
+def test_save_and_load_pretrained_round_trip(tmp_path):
+    """(f)-4: the reference's get_config reads an attribute it never sets (model.py:188-194), so its own
+    save_pretrained cannot run; here config.json + pytorch_model.bin round-trip, with the reference's file names and
+    state-dict keys (a checkpoint written by the reference trainer's torch.save(state_dict) loads the same way)."""
+    from relgat_projector_b200 import synthetic as S
+    kg = S.tensor_kg(60, 300, 4, 12, seed=3)
+    torch.manual_seed(5)
+    m = R.RelGATModel(kg.node_emb, kg.edge_index, kg.edge_type, num_rel=4, scorer_type="transe", gat_out_dim=6,
+                      gat_heads=2, dropout=0.1, gat_num_layers=2, project_to_input_size=True, projection_layers=2)
+    out = tmp_path / "ckpt"
+    m.save_pretrained(str(out), add_files=[("run.json", {"note": "ok"})])
+    assert sorted(os.listdir(out)) == ["config.json", "pytorch_model.bin", "run.json"]
+    m2 = R.RelGATModel.load_from_pretrained(str(out), node_emb=kg.node_emb, edge_index=kg.edge_index,
+                                            edge_type=kg.edge_type)
+    assert m2.get_config() == m.get_config() and not m2.training
+    sd, sd2 = m.state_dict(), m2.state_dict()
+    assert list(sd) == list(sd2) and all(torch.equal(sd[k], sd2[k]) for k in sd)
+    with pytest.raises(ValueError):
+        R.RelGATModel.load_from_pretrained(str(out), node_emb=kg.node_emb[:, :5], edge_index=kg.edge_index,
+                                           edge_type=kg.edge_type)
+    with pytest.raises(FileNotFoundError):
+        R.RelGATModel.load_from_pretrained(str(tmp_path / "missing"), node_emb=kg.node_emb)
