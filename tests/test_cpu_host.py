@@ -220,3 +220,29 @@ def test_save_and_load_pretrained_round_trip(tmp_path):
                                            edge_type=kg.edge_type)
     with pytest.raises(FileNotFoundError):
         R.RelGATModel.load_from_pretrained(str(tmp_path / "missing"), node_emb=kg.node_emb)
+
+
+def test_node_table_matches_reference_matrix_and_is_memory_mapped(tmp_path):
+    """storage.py: the memory-mapped node table equals the matrix the reference builds from the pickled dict
+    (torch.stack over sorted ids, dataset/relgat_dataset.py:61-68), bit for bit."""
+    import pickle
+    from relgat_projector_b200 import storage
+    rng = np.random.default_rng(0)
+    node2emb = {}
+    for nid in rng.permutation(50)[:37] * 3 + 11:  # unordered, sparse ids; mixed containers like the reference accepts
+        v = rng.standard_normal(9).astype(np.float32)
+        node2emb[int(nid)] = [v.tolist(), v, torch.from_numpy(v.copy())][int(nid) % 3]
+    ref_ids = sorted(node2emb.keys())
+    ref = torch.stack([torch.as_tensor(node2emb[nid]) for nid in ref_ids], dim=0).to(torch.float32)
+    pk = tmp_path / "nodes.pkl"
+    with open(pk, "wb") as f:
+        pickle.dump({k: (v.numpy() if torch.is_tensor(v) else v) for k, v in node2emb.items()}, f)
+    assert storage.convert_pickled_nodes(str(pk), str(tmp_path / "tab")) == (37, 9)
+    ids, emb = storage.load_node_table(str(tmp_path / "tab"))
+    assert ids.tolist() == ref_ids and torch.equal(emb, ref)
+    assert storage.id_to_row(ids) == {nid: i for i, nid in enumerate(ref_ids)}
+    emb[0, 0] += 1.0  # copy-on-write: the file stays as written
+    _, again = storage.load_node_table(str(tmp_path / "tab"), mmap=False)
+    assert torch.equal(again, ref)
+    with pytest.raises(ValueError):
+        storage.write_node_table({1: [1.0, 2.0], 2: [1.0]}, str(tmp_path / "bad"))
