@@ -139,6 +139,26 @@ def relgat_stack(x0, graph, heads, out_dim, layer_params: Sequence, precision="f
     return RelGATStackFunction.apply(x0, graph, heads, out_dim, precision, x0_planes, *flat)
 
 
+class GatherRowsFunction(torch.autograd.Function):
+    """rows = x[ids] with a deterministic backward (ordered segmented sum instead of index_add's atomics); the dense
+    gradient it returns carries the row list (see mark_sparse_rows)."""
+
+    @staticmethod
+    def forward(ctx, x, ids):
+        out = x.new_empty((ids.numel(), x.size(1)))
+        ops.pull_rows(x.detach().contiguous(), ids, out)
+        ctx.save_for_backward(ids)
+        ctx.n_rows = x.size(0)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_rows):
+        (ids,) = ctx.saved_tensors
+        dx, keys = ops.index_add_sorted(grad_rows.contiguous(), ids, ctx.n_rows, return_keys=True)
+        mark_sparse_rows(dx, keys)
+        return dx, None
+
+
 class GatherScoreFunction(torch.autograd.Function):
     """scores = scorer(x[src_ids], rel_ids, x[dst_ids]) without materialising the gathers
     (reference model.py:136-141); optional side outputs: transform rows for the first

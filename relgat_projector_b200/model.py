@@ -46,6 +46,7 @@ class RelGATModel(nn.Module):
         self.projection_layers = projection_layers
         self.project_to_input_size = project_to_input_size
         self.precision = precision
+        self.project_batch_rows_only = True  # forward(): project only the rows the scorer reads (identical values)
         if project_to_input_size and self.projection_layers < 1:
             raise ValueError("projection_layers must be >= 1 when project_to_input_size=True")
         self._config = dict(
@@ -104,9 +105,8 @@ class RelGATModel(nn.Module):
     def _graph(self):
         return get_graph_index(self.edge_index, self.edge_type, self.node_emb_fixed.size(0), self.num_rel)
 
-    # -- reference API ------------------------------------------------------------------------
-    def single_gat_step(self) -> torch.Tensor:
-        """Full-graph node representations, optionally projected (reference model.py:274-292)."""
+    def _stack_output(self) -> torch.Tensor:
+        """Output of the GAT stack for every node, before the projection head."""
         layers = self._layers()
         for lyr in layers:
             lyr.check_supported()
@@ -123,17 +123,40 @@ class RelGATModel(nn.Module):
                 x = gat(x, self.edge_index, self.edge_type)
                 if self.act is not None and li < len(layers) - 1:
                     x = self.act(x)
+        return x
+
+    # -- reference API ------------------------------------------------------------------------
+    def single_gat_step(self) -> torch.Tensor:
+        """Full-graph node representations, optionally projected (reference model.py:274-292)."""
+        x = self._stack_output()
         if self.project_to_input_size:
             x = self.projection(x)
         return x
+
+    def _dropout_active(self) -> bool:
+        if not self.training:
+            return False
+        mods = [self._layers()[-1].dropout] + ([self.projection.dropout] if self.project_to_input_size else [])
+        return any(isinstance(m, torch.nn.Dropout) and m.p > 0.0 for m in mods)
 
     def forward(self, src_ids: torch.Tensor, rel_ids: torch.Tensor, dst_ids: torch.Tensor,
                 transform_to_input_if_possible: bool = True
                 ) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
         """Scores for a batch of triples (reference model.py:99-142): returns
         (scores [B], transformed [B, D_sc] or None, dst_vec [B, D_sc])."""
-        x = self.single_gat_step()
         want_tr = self.project_to_input_size and transform_to_input_if_possible
+        if self.project_to_input_size and self.project_batch_rows_only and not self._dropout_active():
+            # the projection head works row by row and the scorer reads only x[src_ids], x[dst_ids]: project those
+            # 2·B' rows instead of all N (same values for those rows; SURVEY.md 8(f)-1).  With an active dropout the
+            # random mask would be drawn for another shape, so that case keeps the reference's order of operations.
+            b = int(src_ids.numel())
+            rows = RF.GatherRowsFunction.apply(self._stack_output(), torch.cat([src_ids, dst_ids]))
+            y = self.projection(rows)
+            src_vec, dst_vec = y[:b], y[b:]
+            scores = self.scorer(src_vec, rel_ids, dst_vec)
+            transformed = self.scorer.transform(src_vec, rel_ids) if want_tr else None
+            return scores, transformed, dst_vec
+        x = self.single_gat_step()
         scores, transformed, dst_vec = self.scorer.gather_score(
             x, src_ids, rel_ids, dst_ids, n_transform=int(src_ids.numel()) if want_tr else 0, want_dst_vec=True)
         return scores, (transformed if want_tr else None), dst_vec

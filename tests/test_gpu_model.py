@@ -86,16 +86,20 @@ def test_model_forward_api_and_fused_scores(dev):
     c = Case("transe_proj_fp32")
     m = _load_model(c, dev).eval()
     src_ids, rel_ids, dst_ids = c.t("src_ids").to(dev), c.t("rel_ids").to(dev), c.t("dst_ids").to(dev)
+    close = lambda a, b: rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-6  # noqa: E731
     with torch.no_grad():
-        scores, transformed, dst_vec = m(src_ids, rel_ids, dst_ids)
-        x = m.get_node_repr()
-        assert transformed.shape == (src_ids.numel(), c.d_in) and torch.equal(dst_vec, x[dst_ids])
-        assert torch.equal(m.scorer(x[src_ids], rel_ids, x[dst_ids]), scores)
-        assert torch.equal(m.transform(src_ids, rel_ids), transformed)
+        scores, transformed, dst_vec = m(src_ids, rel_ids, dst_ids)  # projects only the batch rows
+        x = m.get_node_repr()                                        # projects all rows
+        assert transformed.shape == (src_ids.numel(), c.d_in) and close(dst_vec, x[dst_ids])
+        assert close(m.scorer(x[src_ids], rel_ids, x[dst_ids]), scores)
+        assert close(m.transform(src_ids, rel_ids), transformed)
         one = m.transform_from_vectors(x[src_ids], rel_ids[:1] * 0 + 2)
         assert torch.equal(one, m.scorer.transform(x[src_ids], torch.full_like(rel_ids, 2)))
         s2, t2, _ = m(src_ids, rel_ids, dst_ids, transform_to_input_if_possible=False)
         assert t2 is None and torch.equal(s2, scores)
+        m.project_batch_rows_only = False  # the reference's order: project everything, then gather
+        s3, t3, d3 = m(src_ids, rel_ids, dst_ids)
+        assert close(s3, scores) and close(t3, transformed) and torch.equal(d3, x[dst_ids])
 
 
 def test_layer_docstring_shape_and_input_gradient(dev):
@@ -433,3 +437,27 @@ def test_peer_table_sparse_last_layer_backward(dev):
     run(ids_a, sparse=False)  # dense pass dirties the tables
     assert not any(p._sparse_clean for p in parts)
     run(ids_b, sparse=True)   # ... and the next sparse pass re-zeroes them
+
+
+def test_projection_of_batch_rows_only_gives_the_same_gradients(dev):
+    """forward() with a projection head projects the 2·B' rows the scorer reads instead of all N:
+    same loss and parameter gradients as projecting everything; with an active dropout the full path is kept."""
+    c = Case("transe_proj_fp32")
+    src_ids, rel_ids, dst_ids = c.t("src_ids").to(dev), c.t("rel_ids").to(dev), c.t("dst_ids").to(dev)
+    res = []
+    for subset in (True, False):
+        m = _load_model(c, dev)  # training mode, all dropouts 0
+        m.project_batch_rows_only = subset
+        scores, tr, dv = m(src_ids, rel_ids, dst_ids)
+        loss = scores.square().mean() + 0.1 * tr.square().mean() + 0.1 * dv.square().mean()
+        loss.backward()
+        res.append((float(loss.detach()), {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}))
+    assert abs(res[0][0] - res[1][0]) <= 1e-6 * abs(res[1][0])
+    assert res[0][1].keys() == res[1][1].keys()
+    for n in res[0][1]:
+        # the two orders feed different operands to the bf16 hi/lo GEMMs (<= 2e-5 relative each): contract tolerance
+        err = rel_err(res[0][1][n].cpu().numpy(), res[1][1][n].cpu().numpy())
+        assert err < FP32_TOL, (n, err)
+    m = _load_model(c, dev)
+    m.projection.dropout = torch.nn.Dropout(0.5)
+    assert m._dropout_active() and not m.eval()._dropout_active()
