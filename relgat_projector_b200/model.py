@@ -183,38 +183,43 @@ class RelGATModel(nn.Module):
         never assigns, model.py:188-194; here it is populated so save/load round-trips)."""
         return dict(self._config)
 
+    CONFIG_FILE = "config.json"           # file names of the reference (model.py:196-216), so either side's
+    WEIGHTS_FILE = "pytorch_model.bin"    # checkpoints open with the other's loader
+    _CTOR_FROM_CONFIG = {                 # config key -> (constructor argument, type)
+        "num_rel": ("num_rel", int), "scorer_type": ("scorer_type", str), "gat_out_dim": ("gat_out_dim", int),
+        "gat_heads": ("gat_heads", int), "dropout": ("dropout", float),
+        "relation_attn_dropout": ("relation_attn_dropout", float), "gat_num_layers": ("gat_num_layers", int),
+        "project_to_input_size": ("project_to_input_size", bool), "projection_layers": ("projection_layers", int),
+        "projection_dropout": ("projection_dropout", float), "projection_hidden_dim": ("projection_hidden_dim", int),
+    }
+
     def save_pretrained(self, output_dir: str, add_files: Optional[List[Tuple[str, Dict[str, Any]]]] = None) -> None:
-        add_files = [] if add_files is None else list(add_files)
+        """Writes the weights, ``config.json`` and any extra (file name, JSON-able dict) pairs into ``output_dir``."""
         os.makedirs(output_dir, exist_ok=True)
-        add_files.append(("config.json", self.get_config()))
-        for name, content in add_files:
-            with open(os.path.join(output_dir, name), "w", encoding="utf-8") as f:
-                json.dump(content, f, ensure_ascii=False, indent=2)
-        torch.save(self.state_dict(), os.path.join(output_dir, "pytorch_model.bin"))
+        json_files = dict(add_files or [])
+        json_files[self.CONFIG_FILE] = self.get_config()
+        for file_name, payload in json_files.items():
+            with open(os.path.join(output_dir, file_name), "w", encoding="utf-8") as fh:
+                json.dump(payload, fh, ensure_ascii=False, indent=2)
+        torch.save(self.state_dict(), os.path.join(output_dir, self.WEIGHTS_FILE))
 
     @staticmethod
     def load_from_pretrained(input_dir: str, *, node_emb: Optional[torch.Tensor] = None,
                              edge_index: Optional[torch.Tensor] = None, edge_type: Optional[torch.Tensor] = None,
                              map_location=None, precision: str = "fp32") -> "RelGATModel":
-        cfg_path = os.path.join(input_dir, "config.json")
-        w_path = os.path.join(input_dir, "pytorch_model.bin")
-        if not os.path.isfile(cfg_path):
-            raise FileNotFoundError(f"Config file not found: {cfg_path}")
-        if not os.path.isfile(w_path):
-            raise FileNotFoundError(f"Weights file not found: {w_path}")
-        with open(cfg_path, "r", encoding="utf-8") as f:
-            cfg = json.load(f)
-        if int(cfg.get("input_dim")) != int(node_emb.size(1)):
-            raise ValueError(f"Input dim mismatch: config={cfg.get('input_dim')} vs node_emb={node_emb.size(1)}")
-        model = RelGATModel(
-            node_emb=node_emb, edge_index=edge_index, edge_type=edge_type, num_rel=int(cfg["num_rel"]),
-            scorer_type=str(cfg["scorer_type"]), gat_out_dim=int(cfg["gat_out_dim"]),
-            gat_heads=int(cfg["gat_heads"]), dropout=float(cfg["dropout"]),
-            relation_attn_dropout=float(cfg["relation_attn_dropout"]), gat_num_layers=int(cfg["gat_num_layers"]),
-            project_to_input_size=bool(cfg["project_to_input_size"]), projection_layers=int(cfg["projection_layers"]),
-            projection_dropout=float(cfg["projection_dropout"]),
-            projection_hidden_dim=int(cfg["projection_hidden_dim"]), precision=precision)
-        state = torch.load(w_path, map_location=map_location)
-        model.load_state_dict(state, strict=True)
-        model.eval()
-        return model
+        """Rebuilds a model saved by ``save_pretrained``; the graph tensors are not part of a checkpoint and must
+        be passed in (their feature width is checked against the saved configuration).  Returned in eval mode."""
+        paths = {kind: os.path.join(input_dir, name) for kind, name in
+                 (("Config", RelGATModel.CONFIG_FILE), ("Weights", RelGATModel.WEIGHTS_FILE))}
+        for kind, path in paths.items():
+            if not os.path.isfile(path):
+                raise FileNotFoundError(f"{kind} file not found: {path}")
+        with open(paths["Config"], "r", encoding="utf-8") as fh:
+            saved = json.load(fh)
+        width = None if node_emb is None else int(node_emb.size(1))
+        if int(saved["input_dim"]) != width:
+            raise ValueError(f"Input dim mismatch: config={saved['input_dim']} vs node_emb={width}")
+        kwargs = {arg: cast(saved[key]) for key, (arg, cast) in RelGATModel._CTOR_FROM_CONFIG.items()}
+        model = RelGATModel(node_emb, edge_index, edge_type, precision=precision, **kwargs)
+        model.load_state_dict(torch.load(paths["Weights"], map_location=map_location), strict=True)
+        return model.eval()

@@ -16,23 +16,22 @@ class ProjectionHead(nn.Module):
                  hidden_dim: Optional[int] = None, precision: str = "fp32"):
         super().__init__()
         self.precision = precision
-        self.in_dim = in_dim
-        self.out_dim = out_dim
-        self.hidden_dim = hidden_dim if hidden_dim is not None and hidden_dim > 0 else in_dim
-        self.num_layers = max(0, int(num_layers))
-        self.dropout = nn.Dropout(dropout) if dropout and dropout > 0 else nn.Identity()
-        if self.num_layers == 0 and in_dim == out_dim:
+        depth = max(0, int(num_layers))
+        width = hidden_dim if (hidden_dim is not None and hidden_dim > 0) else in_dim
+        self.in_dim, self.out_dim, self.hidden_dim, self.num_layers = in_dim, out_dim, width, depth
+        self.dropout = nn.Dropout(dropout) if (dropout and dropout > 0) else nn.Identity()
+        if depth == 0 and in_dim == out_dim:
             self.net = nn.Identity()
-        elif self.num_layers <= 1:
-            self.net = nn.Linear(in_dim, out_dim, bias=False)
-        else:
-            blocks = []
-            width = in_dim
-            for _ in range(self.num_layers - 1):  # Linear -> GELU -> LayerNorm blocks (projection.py:54-66)
-                blocks += [nn.Linear(width, self.hidden_dim, bias=False), nn.GELU(), nn.LayerNorm(self.hidden_dim)]
-                width = self.hidden_dim
-            blocks.append(nn.Linear(self.hidden_dim, out_dim, bias=False))
-            self.net = nn.Sequential(*blocks)
+            return
+        # chain of bias-free linears in_dim -> hidden ... -> out_dim; GELU + LayerNorm after every linear but the
+        # last.  Module order (hence state-dict keys net.0, net.3, ... and the init-RNG order) as in the reference.
+        dims = [in_dim] + [width] * max(depth - 1, 0) + [out_dim]
+        mods = []
+        for k in range(len(dims) - 1):
+            mods.append(nn.Linear(dims[k], dims[k + 1], bias=False))
+            if k < len(dims) - 2:
+                mods += [nn.GELU(), nn.LayerNorm(dims[k + 1])]
+        self.net = mods[0] if len(mods) == 1 else nn.Sequential(*mods)
 
     def _run(self, mod: nn.Module, x: torch.Tensor) -> torch.Tensor:
         if isinstance(mod, nn.Linear) and mod.bias is None and x.is_cuda and x.dtype == torch.float32:
