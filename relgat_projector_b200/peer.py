@@ -4,22 +4,23 @@ BASELINE.json's north_star partitions the graph by destination range and moves t
 rows between GPUs over NVLink.  Here every rank keeps the rows other ranks need (projected features P,
 output gradients G, per-node softmax statistics, raw logits) in *peer tables*
 (``csrc/peer_table.cu``): one allocation per rank, all of them mapped back to back into every process.
-The unchanged edge kernels gather a peer's rows with plain loads over NVLink / NVSwitch while they
-compute — there is no pack / all-gather / unpack and no reduction of partial results.  One gather
-kernel per edge pass pulls the distinct rows a rank's edges reference into its own table ahead of the
-edge kernel ([own rows | pulled rows]): reading them in place from inside the edge kernel moves every
-row once per EDGE instead of once per distinct row and cannot use the kernels' L2 prefetch
-(`prefetch.global.L2` on a peer address measured 70x slower than a plain load):
+A peer's rows are then ordinary addresses: loads travel over NVLink / NVSwitch, and there is no pack /
+all-gather / unpack and no reduction of partial results.  One gather kernel per edge pass
+(``relgat_pull_rows``) pulls the distinct rows a rank's edges reference into the tail of its own table
+([own rows | pulled rows]) ahead of the unchanged edge kernel: gathering them in place from inside the
+edge kernel would move every row once per EDGE instead of once per distinct row, and the kernels'
+`prefetch.global.L2` on a peer address measured 70x slower than a plain load.
 
-* forward:  a rank owns a destination range and the in-edges of those destinations; sources are
-  read from the mapped P table (global row ids).
+* forward:  a rank owns a destination range and the in-edges of those destinations; remote sources are
+  pulled from the mapped P table.
 * backward: a rank owns the SAME node range as sources and processes their out-edges (by-source pass
-  and by-relation pass), reading G / t / hsum / softmax statistics of the destinations and the saved
-  logits from the mapped tables.  Every dP row is complete on its owner: no cross-rank sum.  Forward node
+  and by-relation pass), pulling G / t / hsum / softmax statistics of the remote destinations and the
+  saved logits from the mapped tables; for the last layer only the rows of the batch (dY is zero
+  elsewhere) are written, pulled and cleared.  Every dP row is complete on its owner: no cross-rank sum.  Forward node
   rows are bit-identical to one GPU; gradients agree to rounding (a source's out-edges are summed in the
   order of the renumbered destinations).
 
-Ordering across ranks is a stream-ordered NCCL all-reduce of one integer after each writer kernel
+Ordering across ranks is a stream-ordered NCCL all-reduce of one integer after each row block of a writer kernel
 (``sync``): a reader kernel enqueued behind it cannot start before every rank's writer has finished.
 Parameter gradients are per-rank partial sums, all-reduced once per step (``dist.allreduce_grads``).
 
