@@ -246,3 +246,15 @@ def test_node_table_matches_reference_matrix_and_is_memory_mapped(tmp_path):
     assert torch.equal(again, ref)
     with pytest.raises(ValueError):
         storage.write_node_table({1: [1.0, 2.0], 2: [1.0]}, str(tmp_path / "bad"))
+
+
+def test_docs_quote_the_current_abi():
+    """DESIGN.md / INTEGRATION.md state the number of C entry points and the ABI version: keep them honest."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    want = (len(_lib.SIGNATURES), _lib.ABI_VERSION)
+    assert sorted(_lib.header_symbols()) == sorted(_lib.SIGNATURES)
+    for name in ("DESIGN.md", "INTEGRATION.md"):
+        with open(os.path.join(root, name), encoding="utf-8") as f:
+            m = re.search(r"(\d+) entry points \(ABI v(\d+)\)", f.read())
+        assert m and (int(m.group(1)), int(m.group(2))) == want, name
