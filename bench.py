@@ -8,9 +8,11 @@ One "step" = one full training step of the hot path over one batch: full-graph G
 parameter gradient and the Adam update (reference trainer/relgat_projector.py:442-469).
 ``value`` = message-passing edges processed per second by the whole job = E / t_step.
 
-Rank 0 prints ONE JSON line.  ``--impl reference`` times the CPU restatement of the reference's
-own torch/torch_scatter path (oracle/relgat_oracle.py, kind "port": the reference itself is not
-present on the GPU box) on the host cores on a bounded sample of the same workload.
+Rank 0 prints ONE JSON line.  ``--impl reference`` times the UNMODIFIED reference (its own ``RelGATModel`` /
+``RelGATLayer`` / scorer / loss classes, pip-installed into the git-ignored oracle/_ref by oracle/install_ref.py, with
+the torch_scatter stand-in) on the host cores, on the SAME configuration as this arm (kind "reference"; the number of
+timed steps is capped by a wall-clock budget and reported); without that install it falls back to the oracle port on a
+scaled-down sample (kind "port").  No product code runs in that arm.
 """
 from __future__ import annotations
 
@@ -32,7 +34,9 @@ import torch  # noqa: E402
 
 METRIC = "relgat_train_edges_per_sec_fwd_bwd"
 UNIT = "edges/s"
-CPU_SAMPLE_SCALE = 20  # the CPU arms run the named config at 1/20 of the nodes and edges
+CPU_SAMPLE_SCALE = 20    # oracle-port fallback: the named config at 1/20 of the nodes and edges
+CPU_BASELINE_SCALE = 5   # cpu_baseline leg of this arm: the reference at 1/5 scale (~10-20 s of CPU work)
+REF_BUDGET_S = float(os.environ.get("RELGAT_REF_BUDGET_S", "420"))  # wall-clock budget of the reference arm's timed steps
 
 
 def load_peaks():
@@ -107,7 +111,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 class KernelProfiler:
     NAMES = ["split_bf16", "gemm", "edge_fwd", "edge_bwd_prep", "edge_bwd_src", "edge_bwd_rel", "score_fwd",
-             "score_bwd", "index_add_sorted", "margin_loss"]
+             "score_bwd", "index_add_sorted", "margin_loss", "rank_loss", "recon_loss", "zero_rows", "pull_rows"]
 
     def __init__(self):
         from relgat_projector_b200 import ops
@@ -250,6 +254,101 @@ def run_cpu_port(cfg, steps, warmup, scale):
     return dict(value=E / dt, unit=UNIT, cores=cores, kind="port", sample=sample, ms_per_step=dt * 1e3, edges=E)
 
 
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the UNMODIFIED reference on the host cores (no product code)
+# ---------------------------------------------------------------------------------------------
+def _standalone_synthetic():
+    """The seeded KG generator, loaded as a plain file (no import of the product package: this arm must not depend on
+    it).  Same seeds -> the same graph and batches as the GPU arm."""
+    import importlib.util
+    name = "_relgat_bench_synthetic"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "relgat_projector_b200", "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def reference_installed() -> bool:
+    from oracle import ref_shim
+    return ref_shim.reference_available()
+
+
+def run_cpu_reference(cfg, steps, scale=1, budget_s=REF_BUDGET_S, seed=42):
+    """Training steps of the reference's own classes (trainer/relgat_projector.py:442-469, 498-557) on the CPU."""
+    from oracle import ref_shim
+    ref_shim.import_reference()
+    from relgat_projector.core.loss.multi_objective_loss import MultiObjectiveRelLoss
+    from relgat_projector.core.loss.relgat_loss import RelGATLoss
+    from relgat_projector.core.model.model import RelGATModel
+    S = _standalone_synthetic()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n, t = max(cfg["N"] // scale, 64), max(cfg["T"] // scale, 256)
+    kg = S.tensor_kg(n, t, cfg["R"], cfg["D_in"], seed=seed, device="cpu")
+    E = int(kg.edge_index.size(1))
+    torch.manual_seed(seed)
+    model = RelGATModel(node_emb=kg.node_emb, edge_index=kg.edge_index, edge_type=kg.edge_type, num_rel=cfg["R"],
+                        scorer_type=cfg["scorer"], gat_out_dim=cfg["F"], gat_heads=cfg["H"], dropout=0.0,
+                        relation_attn_dropout=0.0, gat_num_layers=cfg["L"], project_to_input_size=cfg["proj"],
+                        projection_layers=2)
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=2e-4)
+    rank = RelGATLoss("margin_ranking_loss", None, 1.0, 20, {})
+    multi = MultiObjectiveRelLoss(relgat_loss=rank, run_config={}) if cfg["proj"] else None
+    b, k = cfg["B"], cfg["K"]
+    gen = torch.Generator().manual_seed(seed)
+
+    def step():
+        src, rel, dst = S.sample_batch(kg.train_triples, n, b, k, gen)
+        opt.zero_grad(set_to_none=True)
+        if not cfg["proj"]:  # trainer:510-521 + _split_scores :657-676
+            scores, _, _ = model(src, rel, dst, transform_to_input_if_possible=False)
+            loss = rank.prepare_scores_and_compute_loss(pos_score=scores[:b],
+                                                        neg_score=scores[b:].view(k, b).transpose(0, 1).contiguous())
+        else:  # trainer:587-655
+            x = model.single_gat_step()
+            ps, pd = x[src[:b]], x[dst[:b]]
+            pos = model.scorer(ps, rel[:b], pd)
+            tr = model.scorer.transform(ps, rel[:b])
+            nd = x[dst[b:]]
+            neg = model.scorer(x[src[b:]], rel[b:], nd).view(b, k)
+            loss = multi(pos_score=pos, neg_score=neg, transformed_src=tr, dst_vec=pd,
+                         neg_dst_vec=nd.view(b, k, tr.shape[1]).permute(1, 0, 2).contiguous())
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+
+    t0 = time.perf_counter()
+    step()  # warm-up (allocator, thread pools)
+    t_warm = time.perf_counter() - t0
+    n_timed = max(1, min(int(steps), int(budget_s / max(t_warm, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(n_timed):
+        step()
+    dt = (time.perf_counter() - t0) / n_timed
+    what = "the full configuration" if scale == 1 else f"1/{scale} of the nodes and triplets"
+    sample = (f"{cfg['name']}, {what}: N={n} nodes, E={E} message-passing edges, R={cfg['R']}, D_in={cfg['D_in']}, "
+              f"L={cfg['L']}, H={cfg['H']}, F={cfg['F']}, B={b}, K={k}; UNMODIFIED reference classes (RelGATModel, "
+              f"RelGATLoss; torch_scatter stand-in) on {cores} host threads; 1 warm-up + {n_timed} timed steps "
+              f"({steps} requested, capped by a {budget_s:.0f} s budget), fp32, torch {torch.__version__} CPU")
+    return dict(value=E / dt, unit=UNIT, cores=cores, kind="reference", sample=sample, ms_per_step=dt * 1e3, edges=E,
+                steps=n_timed, scale=scale)
+
+
+def workload_config(cfg_name, cfg, E):
+    """``config`` of the JSON line: identical in both arms."""
+    return {"workload": f"{cfg_name}: synthetic KG {cfg['N']} nodes / {cfg['T']} triplets ({E} message-passing edges) / "
+                        f"{cfg['R']} relations, {cfg['D_in']}-d, {cfg['L']} layers, {cfg['H']} heads, gat-out-dim "
+                        f"{cfg['F']}, {cfg['scorer']}, batch {cfg['B']}, num-neg {cfg['K']}",
+            "precision": "fp32",
+            "step": "full-graph GAT fwd + gather-score + margin loss + bwd + Adam",
+            "l2": "inputs_exceed_L2 (P and G are ~1 GB each vs 126 MB L2)"}
+
+
 # ---------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -267,6 +366,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt-precision", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=3)
+    ap.add_argument("--ref-scale", type=int, default=1,
+                    help="--impl reference: run the configuration at 1/SCALE of its nodes and triplets (default 1: in full)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -279,17 +380,23 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        scale = CPU_SAMPLE_SCALE if cfg["N"] >= 100_000 else 1
-        r = run_cpu_port(cfg, args.steps, max(args.warmup, 1), scale)
+        # the per-GPU workload of this arm (weak scaling: every rank holds one such graph); one CPU host runs it once
+        if reference_installed():
+            r = run_cpu_reference(cfg, args.steps, scale=args.ref_scale)
+            n_warm = 1
+        else:
+            scale = CPU_SAMPLE_SCALE if cfg["N"] >= 100_000 else 1
+            n_warm = max(args.warmup, 1)
+            r = dict(run_cpu_port(cfg, args.steps, n_warm, scale), steps=args.steps, scale=scale)
+        e_full = int(0.9 * cfg["T"])
         line = {
             "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+            "steps": r["steps"], "warmup": n_warm, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": f"{cfg_name}: synthetic KG {cfg['N']} nodes / {cfg['T']} triplets, bounded sample",
-                       "precision": "fp32", "sample": r["sample"]},
+            "config": workload_config(cfg_name, cfg, e_full if r["scale"] == 1 else r["edges"]),
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0,
+            "gpu_launches": 0, "steps_requested": args.steps,
         }
         print(json.dumps(line))
         return 0
@@ -321,17 +428,12 @@ def main():
                     for _ in range(n_pool)]
     dev_batches = [tuple(t.to(dev) for t in hb) for hb in host_batches]
 
+    multi_loss = L.MultiObjectiveRelLoss(relgat_loss=rank_loss, run_config={}) if cfg["proj"] else None
+
     def train_step(src, rel, dst):
+        # the trainer's step (reference trainer/relgat_projector.py:442-469): _calculate_loss, backward, Adam
         opt.zero_grad(set_to_none=True)
-        if not cfg["proj"]:
-            scores, _, _ = model(src, rel, dst, transform_to_input_if_possible=False)
-            loss = L.fused_margin_ranking_loss(scores, b, k, rank_loss.margin)  # == RelGATLoss on split_scores
-        else:
-            scores, tr, dst_vec = model(src, rel, dst)
-            pos, neg = L.split_scores(scores, b, k, projection_path=True)
-            multi = L.MultiObjectiveRelLoss(relgat_loss=rank_loss, run_config={})
-            ndv = dst_vec[b:].view(b, k, -1).permute(1, 0, 2).contiguous()
-            loss = multi(pos_score=pos, neg_score=neg, transformed_src=tr[:b], dst_vec=dst_vec[:b], neg_dst_vec=ndv)
+        _, _, loss, *_ = L.calculate_loss(model, src, rel, dst, b, rank_loss, multi_loss)
         loss.backward()
         opt.step()
         return loss
@@ -437,22 +539,22 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline:
-        scale = CPU_SAMPLE_SCALE if cfg["N"] >= 100_000 else 1
-        r = run_cpu_port(cfg, steps=2, warmup=1, scale=scale)
+        big = cfg["N"] >= 100_000
+        if reference_installed():  # a bounded sample (~10-30 s of CPU work); the full configuration is --impl reference
+            r = run_cpu_reference(cfg, steps=1, scale=CPU_BASELINE_SCALE if big else 1, budget_s=30.0)
+        else:
+            r = run_cpu_port(cfg, steps=2, warmup=1, scale=CPU_SAMPLE_SCALE if big else 1)
         cpu = {kk: r[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
 
     line = {
         "metric": METRIC, "value": E / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32" if args.precision == "fp32" else "bf16", "data": "synthetic",
-        "config": {"workload": f"{cfg_name}: synthetic KG {cfg['N']} nodes / {cfg['T']} triplets ({E} message-passing "
-                               f"edges) / {cfg['R']} relations, {cfg['D_in']}-d, {cfg['L']} layers, {cfg['H']} heads, "
-                               f"gat-out-dim {cfg['F']}, {cfg['scorer']}, batch {b}, num-neg {k}",
-                   "precision": ("fp32 storage; tensor-core GEMMs on bf16 hi/lo splits (3 passes, ~fp32 accuracy)"
-                                 if args.precision == "fp32" else
-                                 "bf16 storage of P / G / dP rows; single-pass bf16 tensor-core GEMMs; fp32 accumulate"),
-                   "step": "full-graph GAT fwd + gather-score + margin loss + bwd + Adam", "layer_edges_per_sec":
-                   cfg["L"] * E / (ms * 1e-3), "l2": "inputs_exceed_L2 (P and G are ~1 GB each vs 126 MB L2)"},
+        "config": dict(workload_config(cfg_name, cfg, E), precision=args.precision),
+        "precision_note": ("fp32 storage; tensor-core GEMMs on bf16 hi/lo splits (3 passes, ~fp32 accuracy)"
+                           if args.precision == "fp32" else
+                           "bf16 storage of P / G / dP rows; single-pass bf16 tensor-core GEMMs; fp32 accumulate"),
+        "layer_edges_per_sec": cfg["L"] * E / (ms * 1e-3),
         "clocks": clocks.summary(),
         "e2e": {"value": E / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},

@@ -86,7 +86,13 @@ int relgat_gemm_bf16(const void* a_hi, const void* a_lo, long long lda, int a_mn
  * Outputs: out [N, H*F] fp32 pre-activation (may be NULL), optional bf16 (hi, lo) planes of
  * act(out) for the next layer's GEMM (act = ELU if apply_elu, reference model.py:286-287),
  * z [E, H] raw logits and minv [N, H, 2] = (segment max, 1/denominator) saved for backward,
- * alpha [E, H] attention weights (optional, NULL to skip), bias_out [N]. */
+ * alpha [E, H] attention weights (optional, NULL to skip), bias_out [N].
+ * Dropout (training; reference layer.py:296-297 attention dropout, :321-322 feature dropout): keep-bit masks,
+ * element i in word i >> 5, bit i & 31, 1 = keep (relgat_bernoulli_bits, or supplied by the caller); NULL = off.
+ *   drop_bits uint32[N][drop_words] (bit = column h*F + f), drop_scale = 1/(1-p): the finished row (bias included)
+ *     is multiplied before the activation; `out` then holds the POST-dropout row (what backward needs);
+ *   edge_bits uint32[ceil(E*H/32)] (bit = csr slot * H + head), edge_scale: alpha is multiplied after the softmax
+ *     normalisation (the denominator counts every edge). */
 int relgat_layer_fwd(const void* P, int p_is_bf16, long long ldp, const float* A, const float* beta,
                      const int* rowptr, const int* csr_src, const int* csr_rel,
                      const int* chunks, int n_chunks, const int* parts, int n_parts,
@@ -94,6 +100,8 @@ int relgat_layer_fwd(const void* P, int p_is_bf16, long long ldp, const float* A
                      float* part_ml, float* part_b, float* part_acc,
                      float* out, void* act_hi, void* act_lo, int apply_elu,
                      float* alpha, float* z, float* minv, float* bias_out,
+                     const unsigned int* drop_bits, int drop_words, float drop_scale,
+                     const unsigned int* edge_bits, float edge_scale,
                      int H, int F, int R, int sm_count, int* work_counter, void* stream);
 
 /* ---- RelGAT layer, edge part, backward (replaces the autograd replay of layer.py:220-318) ---
@@ -103,23 +111,27 @@ int relgat_layer_fwd(const void* P, int p_is_bf16, long long ldp, const float* A
  *           only these rows of dY are non-zero (the loss reads B*(2+K) rows: reference model.py:136-137) — then
  *           apply_elu must be 0 and G fp32; only those rows are read (and, when G does not alias dY, written: the
  *           caller keeps every other row of G at zero); t / hsum of all other rows are set to 0.
+ *           drop_bits / drop_words / drop_scale: the forward's feature-dropout mask (NULL = off); `out` is then the
+ *           post-dropout row y = out*m*s, G = dY*act'(y)*m*s and t = <dY*act'(y), y - bias*m*s>.
  * bwd_src : by-source pass over chunks of the CSC order (work tables as in fwd, over sources;
  *           part_acc [n_parts, H*F] holds the partial rows of split sources):
  *           dP [N_src, H*F] (fp32 and/or bf16 hi/lo planes) and dz [E, H]; the attention weights
- *           are recomputed from z and minv.
+ *           are recomputed from z and minv.  edge_bits / edge_scale: the forward's attention-dropout mask.
  * bwd_rel : by-relation pass over chunks [chunk_lo, chunk_hi) of rel_slot (a chunk never spans
  *           two relations; rel_chunk_ptr[R+1] gives each relation's chunk range):
  *           dA [H, R, F] and dbeta [R] (NULL to skip) with an ordered reduction of the partials
  *           partA [n_chunks, H*F], partB [n_chunks]. */
 int relgat_layer_bwd_prep(const float* dY, const float* out, const float* bias, void* G, int g_is_bf16,
                           float* t, float* hsum, int N, int H, int F, int apply_elu,
-                          const long long* row_ids, int n_rows, void* stream);
+                          const long long* row_ids, int n_rows,
+                          const unsigned int* drop_bits, int drop_words, float drop_scale, void* stream);
 int relgat_layer_bwd_src(const void* P, long long ldp, const void* G, int feat_is_bf16, const float* A,
                          const float* z, const float* minv, const float* t,
                          const int* colptr, const int* csc_slot, const int* csc_dst, const int* csc_rel,
                          const int* chunks, int n_chunks, const int* parts, int n_parts,
                          const int* long_node, const int* long_part_ptr, int n_long, float* part_acc,
                          float* dP, void* dP_hi, void* dP_lo, float* dz,
+                         const unsigned int* edge_bits, float edge_scale,
                          int H, int F, int R, int sm_count, int* work_counter, void* stream);
 int relgat_layer_bwd_rel(const void* P, int p_is_bf16, long long ldp, const float* dz, const float* hsum,
                          const int* rel_slot, const int* csr_src, const int* csr_dst,
@@ -152,6 +164,35 @@ int relgat_index_add_sorted(const float* rows, const long long* perm, const long
  * loss float[1] = mean relu(margin + neg - pos) and dscore float[B*(1+K)] = d loss / d score. */
 int relgat_margin_loss(const float* score, int B, int K, float margin, int bk_layout, float* loss,
                        float* dscore, void* stream);
+
+/* Ranking loss on pos[B] and neg[b*stride_b + k*stride_k] (element strides: both negative layouts of the reference
+ * trainer — view(K,B).T of trainer/relgat_projector.py:657-676 and view(B,K) of :628-630 — are views of the flat
+ * score vector).  type 0: margin ranking (core/loss/relgat_loss.py:51-54); type 1: self-adversarial
+ * (relgat_loss.py:56-71: -mean logsig(pos) - mean_b sum_k softmax_k(alpha*neg).detach()*logsig(-neg)).
+ * sanitize != 0 applies nan_to_num(nan=0, +-inf=+-1e9) first (trainer:584, 647-648; no gradient through a
+ * non-finite score).  Outputs: loss[1], dpos[B], dneg (neg's addressing) = d loss / d score. */
+#define RG_RANK_MARGIN 0
+#define RG_RANK_SELF_ADVERSARIAL 1
+int relgat_rank_loss(const float* pos, const float* neg, int B, int K, long long stride_b, long long stride_k,
+                     int type, float margin, float alpha, int sanitize, float* loss, float* dpos, float* dneg,
+                     void* stream);
+
+/* Reconstruction terms of MultiObjectiveRelLoss (core/loss/multi_objective_loss.py:47-83 with core/loss/cosine.py:4-13
+ * and core/loss/mse.py:4-10): tr = f_r(A) [B, D], dst [B, D], negative destinations nd(b,k) at
+ * negdst + b*neg_stride_b + k*neg_stride_k (the reference passes [K, B, D]: strides B*D... any layout works; K <= 256).
+ *   values[3] = (mean_b (1 - cos(tr_b, dst_b)), mean_{k,b} (1 - cos(tr_b, nd(b,k))), mean (tr - dst)^2)
+ *   d_tr, d_dst [B, D], d_negdst (negdst's addressing; may be NULL): gradient of
+ *     w_pos*values[0] + w_neg*(1 - values[1]) + w_mse*values[2]
+ * partial: float[B*3] scratch.  cos uses F.normalize's eps 1e-12. */
+int relgat_recon_loss(const float* tr, const float* dst, const float* negdst, int B, int K, int D,
+                      long long neg_stride_b, long long neg_stride_k, float w_pos, float w_neg, float w_mse,
+                      float* values, float* partial, float* d_tr, float* d_dst, float* d_negdst, void* stream);
+
+/* Keep-bit masks for the fused dropout: bits[w] bit j = 1 with probability 1 - p_drop (16-bit resolution), from
+ * Philox4x32-10(seed, counter = word index * 4 + q).  relgat_zero_rows: table[ids[i], 0:D] = 0 (clears the rows of
+ * the batch gradient that relgat_index_add_sorted scattered into a persistent zero table). */
+int relgat_bernoulli_bits(unsigned int* bits, long long n_words, float p_drop, unsigned long long seed, void* stream);
+int relgat_zero_rows(float* table, long long ld, const long long* ids, long long n, int D, void* stream);
 
 /* ---- host-side batch construction (HOST pointers; no GPU involved) --------------------------
  * Replaces the per-sample Python loop of dataset/edge.py:71-115 + trainer/components/

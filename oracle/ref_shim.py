@@ -1,9 +1,9 @@
 """Import shim that makes the UNMODIFIED reference importable (TEST INFRASTRUCTURE ONLY).
 
-Used by ``oracle/gen_golden.py`` and ``oracle/check_port_vs_reference.py`` in the
-build container, where ``/root/reference`` exists.  ``/root/reference`` does NOT
-exist on the GPU box, so nothing under ``tests/ -m gpu``, ``bench.py`` or
-``__graft_entry__.smoke()`` calls :func:`import_reference`.
+Used by ``oracle/gen_golden.py`` in the build container (where ``/root/reference`` exists), and — through the
+package installed into ``oracle/_ref`` by ``oracle/install_ref.py`` — by ``bench.py --impl reference`` /
+``cpu_baseline`` and ``tests/test_gpu_trainer_dropin.py`` on the GPU box, where ``/root/reference`` does not exist.
+The product package never imports this module.
 
 What it does (nothing is copied from the reference):
 * puts ``oracle/standin`` on ``sys.path`` so ``import torch_scatter`` resolves to
@@ -21,12 +21,24 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("RELGAT_REFERENCE_ROOT", "/root/reference")
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+def reference_root():
+    """Where the reference package can be imported from: $RELGAT_REFERENCE_ROOT, the read-only source tree in the build
+    container, or the copy pip-installed into oracle/_ref (the only one present on the GPU box); None if none is."""
+    cands = [os.environ.get("RELGAT_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "relgat_projector", "core", "model", "layer.py")):
+            return c
+    return None
+
+
+REFERENCE_ROOT = reference_root()
+
+
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "relgat_projector"))
+    return reference_root() is not None
 
 
 def _stub(name: str, **attrs) -> types.ModuleType:
@@ -42,13 +54,14 @@ def _stub(name: str, **attrs) -> types.ModuleType:
 
 def import_reference():
     """Returns the imported ``relgat_projector`` package of the reference."""
-    if not reference_available():
-        raise RuntimeError(f"reference not found under {REFERENCE_ROOT}")
+    root = reference_root()
+    if root is None:
+        raise RuntimeError("reference not found (neither /root/reference nor oracle/_ref: run oracle/install_ref.py)")
     standin = os.path.join(_HERE, "standin")
     if standin not in sys.path:
         sys.path.insert(0, standin)
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
 
     class WanDBHandler:  # logging sink, never reached with log_to_wandb=False
         @staticmethod

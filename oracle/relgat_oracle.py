@@ -72,6 +72,10 @@ def layer_forward_port(
     edge_index: torch.Tensor,  # [2, E] int64 (row 0 = src, row 1 = dst)
     edge_type: torch.Tensor,  # [E] int64
     return_attention: bool = False,
+    attn_keep: Optional[torch.Tensor] = None,  # [E, H] bool in COO edge order: keep mask of rel_attn_drop (layer.py:296-297)
+    attn_p: float = 0.0,
+    feat_keep: Optional[torch.Tensor] = None,  # [N, H*F] bool: keep mask of the output dropout (layer.py:321-322)
+    feat_p: float = 0.0,
 ):
     src, dst = edge_index[0], edge_index[1]
     n = x.size(0)
@@ -87,21 +91,28 @@ def layer_forward_port(
         m = seg_max_const(logits[h], dst, n)
         w = torch.exp(logits[h] - m[dst])
         den = seg_sum(w, dst, n).clamp_min(SOFTMAX_EPS)
-        alphas.append(w / den[dst])
+        a = w / den[dst]
+        if attn_keep is not None:  # F.dropout with a given mask: kept entries scaled by 1 / (1 - p)
+            a = a * attn_keep[:, h].to(a.dtype) / (1.0 - attn_p)
+        alphas.append(a)
     outs = [seg_sum(gathered[h] * alphas[h].unsqueeze(-1), dst, n) for h in range(heads)]  # :304-309
     if beta is not None:  # layer.py:313-318
         b = seg_sum(beta[edge_type], dst, n).unsqueeze(-1)
         outs = [o + b for o in outs]
     y = torch.cat(outs, dim=-1)  # layer.py:321 (dropout is identity at p=0 / eval)
+    if feat_keep is not None:
+        y = y * feat_keep.to(y.dtype) / (1.0 - feat_p)
     if return_attention:
         return y, torch.stack(logits, 1), torch.stack(alphas, 1)
     return y
 
 
-def gat_stack_port(x, layers: Sequence[Dict], edge_index, edge_type):
-    """``RelGATModel.single_gat_step`` without projection (reference model.py:274-287)."""
+def gat_stack_port(x, layers: Sequence[Dict], edge_index, edge_type, masks: Optional[Sequence[Dict]] = None):
+    """``RelGATModel.single_gat_step`` without projection (reference model.py:274-287).  ``masks``: per layer the
+    keyword arguments attn_keep / attn_p / feat_keep / feat_p of layer_forward_port (training-mode dropout replayed
+    with given masks)."""
     for li, lp in enumerate(layers):
-        x = layer_forward_port(x, lp["W"], lp["A"], lp["beta"], edge_index, edge_type)
+        x = layer_forward_port(x, lp["W"], lp["A"], lp["beta"], edge_index, edge_type, **(masks[li] if masks else {}))
         if len(layers) > 1 and li < len(layers) - 1:
             x = F.elu(x)
     return x

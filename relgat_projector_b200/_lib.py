@@ -26,6 +26,7 @@ ERRORS = {
 _P = c_void_p
 _I = c_int
 _L = c_longlong
+_F = ctypes.c_float
 
 # name -> (restype, argtypes); mirrors include/relgat_b200.h one to one
 SIGNATURES = {
@@ -35,14 +36,20 @@ SIGNATURES = {
     "relgat_split_bf16": (_I, [_P, _P, _P, _L, _P]),
     "relgat_gemm_workspace_bytes": (_L, [_I, _I, _I, _I, _I, _I]),
     "relgat_gemm_bf16": (_I, [_P, _P, _L, _I, _P, _P, _L, _I, _P, _I, _L, _I, _I, _I, _I, _P, _L, _I, _P]),
-    "relgat_layer_fwd": (_I, [_P, _I, _L, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
-    "relgat_layer_bwd_prep": (_I, [_P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P]),
-    "relgat_layer_bwd_src": (_I, [_P, _L, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "relgat_layer_fwd": (_I, [_P, _I, _L, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P,
+                              _P, _I, _F, _P, _F, _I, _I, _I, _I, _P, _P]),
+    "relgat_layer_bwd_prep": (_I, [_P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P, _I, _F, _P]),
+    "relgat_layer_bwd_src": (_I, [_P, _L, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P,
+                                  _P, _F, _I, _I, _I, _I, _P, _P]),
     "relgat_layer_bwd_rel": (_I, [_P, _I, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _P]),
     "relgat_score_fwd": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _P, _P, _P]),
     "relgat_score_bwd": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P]),
     "relgat_index_add_sorted": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "relgat_margin_loss": (_I, [_P, _I, _I, ctypes.c_float, _I, _P, _P, _P]),
+    "relgat_rank_loss": (_I, [_P, _P, _I, _I, _L, _L, _I, _F, _F, _I, _P, _P, _P, _P]),
+    "relgat_recon_loss": (_I, [_P, _P, _P, _I, _I, _I, _L, _L, _F, _F, _F, _P, _P, _P, _P, _P, _P]),
+    "relgat_bernoulli_bits": (_I, [_P, _L, _F, c_ulonglong, _P]),
+    "relgat_zero_rows": (_I, [_P, _L, _P, _L, _I, _P]),
     "relgat_host_sample_batch": (_I, [_P, _P, _L, _P, _I, _I, _L, _P, _P, _P]),
     "relgat_host_shuffle": (_I, [_P, _P, _L]),
     "relgat_peer_table_granularity": (_I, [_I, _P]),
@@ -53,7 +60,7 @@ SIGNATURES = {
     "relgat_pull_rows": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _I, _P]),
 }
 
-ABI_VERSION = 2  # bumped whenever a signature in include/relgat_b200.h changes
+ABI_VERSION = 3  # bumped whenever a signature in include/relgat_b200.h changes
 _lib = None
 
 

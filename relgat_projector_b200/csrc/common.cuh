@@ -190,6 +190,26 @@ __device__ __forceinline__ float fast_exp(float x) {
   return y;
 }
 
+// ---- dropout keep-bit masks (csrc/mask.cu): element i -> word i >> 5, bit i & 31; 1 = keep ------------
+// multiplier of V consecutive feature columns starting at col0 (V | 32 on the vector paths, so they share a word)
+template <int V>
+__device__ __forceinline__ void keep_scale(const uint32_t* __restrict__ row_bits, int col0, float scale, float (&m)[V]) {
+  if constexpr (V == 4 || V == 8) {
+    const uint32_t w = __ldg(row_bits + (col0 >> 5)) >> (col0 & 31);
+#pragma unroll
+    for (int v = 0; v < V; ++v) m[v] = ((w >> v) & 1u) ? scale : 0.f;
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int c = col0 + v;
+      m[v] = ((__ldg(row_bits + (c >> 5)) >> (c & 31)) & 1u) ? scale : 0.f;
+    }
+  }
+}
+__device__ __forceinline__ float keep_scale1(const uint32_t* __restrict__ bits, long long i, float scale) {
+  return ((__ldg(bits + (i >> 5)) >> (i & 31)) & 1u) ? scale : 0.f;
+}
+
 // ---- lane mapping ------------------------------------------------------------------
 struct LaneMap {
   int hh;        // absolute head owned by this lane

@@ -32,6 +32,10 @@ struct PrepArgs {
   float* hsum;         // [N, H]
   int N, H, F, hg, apply_elu;
   const long long* row_ids;  // optional: only these rows of dY are non-zero (N = their count); t / hsum pre-zeroed
+  // feature dropout of the forward (keep bits, nullptr = off): `out` then holds the POST-dropout rows y = out*m*s
+  const uint32_t* drop_bits;
+  int drop_words;
+  float drop_scale;
 };
 
 template <typename TG, int V>
@@ -43,6 +47,10 @@ __global__ void __launch_bounds__(kBwdWarps * 32) bwd_prep_kernel(const PrepArgs
   const int jt = static_cast<int>(task / groups);
   const int g = static_cast<int>(task - static_cast<long long>(jt) * groups);
   const long long j = a.row_ids ? __ldg(a.row_ids + jt) : jt;
+  // in-place dropout scaling must touch a row once: a row named twice (adjacent in the sorted list) is skipped
+  if (a.row_ids && a.drop_bits && static_cast<const void*>(a.G) == static_cast<const void*>(a.dY) && jt > 0 &&
+      __ldg(a.row_ids + jt - 1) == j)
+    return;
   const LaneMap lm = make_lane_map<V>(lane, g, a.hg, a.F);
   const long long row = j * a.H * a.F + lm.head_off;
   const float b = a.bias ? __ldg(a.bias + j) : 0.f;
@@ -51,19 +59,25 @@ __global__ void __launch_bounds__(kBwdWarps * 32) bwd_prep_kernel(const PrepArgs
   for (int k = 0; k < max_vec<V>(); ++k) {
     const int q = lm.sub + lm.lph * k;
     if (q < lm.vph) {
-      float dy[V], o[V];
+      float dy[V], o[V], ms[V];
       RowVec<float, V>::load_stream(a.dY + row + q * V, dy);
       RowVec<float, V>::load_stream(a.out + row + q * V, o);
 #pragma unroll
+      for (int v = 0; v < V; ++v) ms[v] = 1.f;
+      if (a.drop_bits) keep_scale<V>(a.drop_bits + j * a.drop_words, lm.head_off + q * V, a.drop_scale, ms);
+#pragma unroll
       for (int v = 0; v < V; ++v) {
         // ELU'(x) = 1 (x > 0) else exp(x)  (reference model.py:286-287, torch ELU alpha = 1)
-        float gg = a.apply_elu ? (o[v] > 0.f ? dy[v] : dy[v] * expf(o[v])) : dy[v];
+        // with dropout: y = out*ms is what was stored and activated; G = d/d out = dy*ELU'(y)*ms and
+        // <G, out - b> = sum dy*ELU'(y)*(y - b*ms)
+        const float gy = a.apply_elu ? (o[v] > 0.f ? dy[v] : dy[v] * expf(o[v])) : dy[v];
+        float gg = gy * ms[v];
         if (sizeof(TG) == 2) gg = bf16_round(gg);  // t / hsum consistent with the stored (rounded) G
         dy[v] = gg;
-        tt = fmaf(gg, o[v] - b, tt);
+        tt = a.drop_bits ? fmaf(gy, o[v] - b * ms[v], tt) : fmaf(gg, o[v] - b, tt);
         hs += gg;
       }
-      if (static_cast<const void*>(a.G) != static_cast<const void*>(a.dY) || a.apply_elu)
+      if (static_cast<const void*>(a.G) != static_cast<const void*>(a.dY) || a.apply_elu || a.drop_bits)
         RowVec<TG, V>::store(a.G + row + q * V, dy);
     }
   }
@@ -116,6 +130,8 @@ struct SrcArgs {
   int a_in_smem;
   int pf_dist;  // L2 prefetch distance in edges (0 = off)
   int* work_counter;  // zeroed device ints (one per head-group): dynamic chunk claim; nullptr = static
+  const uint32_t* edge_bits;  // attention-dropout keep bits (index = csr slot * H + head) or nullptr
+  float edge_scale;
 };
 
 template <typename T, int V, int KV, bool ASM, int PIPE, int LPHC>
@@ -272,8 +288,11 @@ __global__ void __launch_bounds__((PIPE ? kSrcWarpsPipe : kSrcWarps) * 32, 1) bw
     _Pragma("unroll") for (int v = 0; v < V; ++v) dd += sd[v];                                 \
     dd = head_sum(dd, lm.lph); /* dalpha */                                                    \
     const float ee = zz_ > 0.f ? zz_ : kLeakySlope * zz_;                                      \
-    const float al = __expf(ee - mi_.x) * mi_.y;                                               \
-    const float dzv = al * (dd - tt_) * (zz_ > 0.f ? 1.f : kLeakySlope);                       \
+    float al = __expf(ee - mi_.x) * mi_.y;                                                     \
+    /* attention dropout: out used alpha*m*s, so dalpha = m*s*<G,P> and the G term carries alpha*m*s */ \
+    const float ek = a.edge_bits ? keep_scale1(a.edge_bits, static_cast<long long>(sl_) * a.H + lm.hh, a.edge_scale) : 1.f; \
+    const float dzv = al * (dd * ek - tt_) * (zz_ > 0.f ? 1.f : kLeakySlope);                  \
+    al *= ek;                                                                                  \
     if (lm.sub == 0) a.dz[static_cast<long long>(sl_) * a.H + lm.hh] = dzv;                    \
     const float* ar = a_base + (rl_) * a.F;                                                    \
     _Pragma("unroll") for (int k = 0; k < KV; ++k) {                                           \
@@ -518,8 +537,10 @@ using namespace relgat;
 
 extern "C" int relgat_layer_bwd_prep(const float* dY, const float* out, const float* bias, void* G, int g_is_bf16,
                                      float* t, float* hsum, int N, int H, int F, int apply_elu,
-                                     const long long* row_ids, int n_rows, void* stream) {
+                                     const long long* row_ids, int n_rows,
+                                     const unsigned int* drop_bits, int drop_words, float drop_scale, void* stream) {
   if (!dY || !out || !G || !t || !hsum || N < 0 || H <= 0 || F <= 0 || n_rows < 0) return RG_ERR_ARG;
+  if (drop_bits && drop_words * 32 < H * F) return RG_ERR_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int rows = N;
   if (row_ids) {
@@ -536,19 +557,19 @@ extern "C" int relgat_layer_bwd_prep(const float* dY, const float* out, const fl
     if (!al16(dY) || !al16(out) || !al16(G)) return RG_ERR_ALIGN;
     const int hg = pick_heads_per_warp(H, F, 8);
     if (!hg) return RG_ERR_SHAPE;
-    PrepArgs<__nv_bfloat16, 8> a{dY, out, bias, static_cast<__nv_bfloat16*>(G), t, hsum, rows, H, F, hg, apply_elu, row_ids};
+    PrepArgs<__nv_bfloat16, 8> a{dY, out, bias, static_cast<__nv_bfloat16*>(G), t, hsum, rows, H, F, hg, apply_elu, row_ids, drop_bits, drop_words, drop_scale};
     return launch_tasks(bwd_prep_kernel<__nv_bfloat16, 8>, a, static_cast<long long>(rows) * (H / hg), s);
   }
   float* Gf = static_cast<float*>(G);
   if (F % 4 == 0 && al16(dY) && al16(out) && al16(G)) {
     const int hg = pick_heads_per_warp(H, F, 4);
     if (!hg) return RG_ERR_SHAPE;
-    PrepArgs<float, 4> a{dY, out, bias, Gf, t, hsum, rows, H, F, hg, apply_elu, row_ids};
+    PrepArgs<float, 4> a{dY, out, bias, Gf, t, hsum, rows, H, F, hg, apply_elu, row_ids, drop_bits, drop_words, drop_scale};
     return launch_tasks(bwd_prep_kernel<float, 4>, a, static_cast<long long>(rows) * (H / hg), s);
   }
   const int hg = pick_heads_per_warp(H, F, 1);
   if (!hg) return RG_ERR_SHAPE;
-  PrepArgs<float, 1> a{dY, out, bias, Gf, t, hsum, rows, H, F, hg, apply_elu, row_ids};
+  PrepArgs<float, 1> a{dY, out, bias, Gf, t, hsum, rows, H, F, hg, apply_elu, row_ids, drop_bits, drop_words, drop_scale};
   return launch_tasks(bwd_prep_kernel<float, 1>, a, static_cast<long long>(rows) * (H / hg), s);
 }
 
@@ -651,17 +672,20 @@ template <typename T, int V>
 static int run_src(const void* P, long long ldp, const void* G, const float* A, const float* z, const float* minv,
                    const float* t, const int* colptr, const int* csc_slot, const int* csc_dst, const int* csc_rel,
                    const int4* ch, int n_chunks, const int2* pt, const int* long_node, const int* long_part_ptr,
-                   int n_long, float* part_acc, float* dP, void* dP_hi, void* dP_lo, float* dz, int H, int F, int R,
+                   int n_long, float* part_acc, float* dP, void* dP_hi, void* dP_lo, float* dz,
+                   const uint32_t* edge_bits, float edge_scale, int H, int F, int R,
                    int sm_count, int* work_counter, cudaStream_t s) {
   const int hg = pick_heads_per_warp(H, F, V, R, smem_budget_override("RELGAT_SRC_BUDGET_KB", kSmemBudgetA));
   if (!hg) return RG_ERR_SHAPE;
+  if (H / hg > 32) return RG_ERR_SHAPE;  // work_counter holds 32 ints (one per head-group)
   if (work_counter) {
     cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int) * (H / hg), s);
     if (e != cudaSuccess) return cuda_status(e);
   }
   SrcArgs<T, V> a{static_cast<const T*>(P), static_cast<const T*>(G), A, z, minv, t, colptr, csc_slot, csc_dst,
                   csc_rel, ch, pt, part_acc, dP, static_cast<__nv_bfloat16*>(dP_hi),
-                  static_cast<__nv_bfloat16*>(dP_lo), dz, n_chunks, H, F, R, hg, ldp, 0, 0, work_counter};
+                  static_cast<__nv_bfloat16*>(dP_lo), dz, n_chunks, H, F, R, hg, ldp, 0, 0, work_counter,
+                  edge_bits, edge_scale};
   int rc = launch_src(a, sm_count, s);
   if (rc != RG_OK || n_long == 0) return rc;
   bwd_src_merge_kernel<T, V><<<n_long, 128, 0, s>>>(a, long_node, long_part_ptr, n_long);
@@ -674,6 +698,7 @@ extern "C" int relgat_layer_bwd_src(const void* P, long long ldp, const void* G,
                                     const int* chunks, int n_chunks, const int* parts, int n_parts,
                                     const int* long_node, const int* long_part_ptr, int n_long, float* part_acc,
                                     float* dP, void* dP_hi, void* dP_lo, float* dz,
+                                    const unsigned int* edge_bits, float edge_scale,
                                     int H, int F, int R, int sm_count, int* work_counter, void* stream) {
   if (!P || !G || !A || !colptr || n_chunks < 0 || n_parts < 0 || n_long < 0 || H <= 0 || F <= 0 || R <= 0)
     return RG_ERR_ARG;
@@ -689,14 +714,16 @@ extern "C" int relgat_layer_bwd_src(const void* P, long long ldp, const void* G,
     if (F % 8 != 0 || ldp % 8 != 0) return RG_ERR_SHAPE;
     if (!ok16) return RG_ERR_ALIGN;
     return run_src<__nv_bfloat16, 8>(P, ldp, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, ch, n_chunks, pt,
-                                     long_node, long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, H, F, R,
-                                     sm_count, work_counter, s);
+                                     long_node, long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, edge_bits, edge_scale,
+                                     H, F, R, sm_count, work_counter, s);
   }
   if (F % 4 == 0 && ldp % 4 == 0 && ok16)
     return run_src<float, 4>(P, ldp, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, ch, n_chunks, pt, long_node,
-                             long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, H, F, R, sm_count, work_counter, s);
+                             long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, edge_bits, edge_scale, H, F, R, sm_count,
+                             work_counter, s);
   return run_src<float, 1>(P, ldp, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, ch, n_chunks, pt, long_node,
-                           long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, H, F, R, sm_count, work_counter, s);
+                           long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, edge_bits, edge_scale, H, F, R, sm_count,
+                             work_counter, s);
 }
 
 template <typename T, int V>

@@ -57,6 +57,13 @@ struct FwdArgs {
   int a_in_smem;         // the head-group's slice of A (hg*R*F floats) is staged in shared memory
   int pf_dist;           // L2 prefetch distance in edges (0 = off)
   int* work_counter;     // zeroed device int: warps claim chunks dynamically (nullptr = static round-robin)
+  // dropout (training): keep-bit masks, nullptr = off.  Feature dropout (layer.py:321-322) multiplies the finished
+  // row; attention dropout (layer.py:296-297) multiplies alpha AFTER the softmax normalisation.
+  const uint32_t* drop_bits;  // [N, drop_words] words
+  int drop_words;
+  float drop_scale;           // 1 / (1 - p)
+  const uint32_t* edge_bits;  // bit index = csr slot * H + head
+  float edge_scale;
 };
 
 // ELU(x) = x (x > 0) else exp(x) - 1.  __expf keeps the absolute error at ~1e-7 (the inputs are
@@ -153,8 +160,9 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
     const float ev = (d_) > 0.f ? (d_) : kLeakySlope * (d_);                                       \
     const float mn = fmaxf(m, ev);                                                                 \
     const float sc = __expf(m - mn);                                                               \
-    const float w = __expf(ev - mn);                                                               \
-    l = fmaf(l, sc, w);                                                                            \
+    const float w0 = __expf(ev - mn);                                                              \
+    l = fmaf(l, sc, w0); /* the denominator counts every edge; attention dropout scales the kept terms */ \
+    const float w = a.edge_bits ? w0 * keep_scale1(a.edge_bits, static_cast<long long>(e_) * a.H + lm.hh, a.edge_scale) : w0; \
     _Pragma("unroll") for (int k = 0; k < KV; ++k) {                                               \
       _Pragma("unroll") for (int v = 0; v < V; ++v) acc[k][v] = fmaf(acc[k][v], sc, w * x_[k][v]); \
     }                                                                                              \
@@ -268,6 +276,12 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
                 o[v] = fmaf(acc[k][v], inv, bsum);  // bias on every head/channel, :313-318
                 acc[k][v] = 0.f;
               }
+              if (a.drop_bits) {  // feature dropout on the finished row (layer.py:321-322), before the activation
+                float ms[V];
+                keep_scale<V>(a.drop_bits + static_cast<long long>(j) * a.drop_words, lane_off + k * kstride, a.drop_scale, ms);
+#pragma unroll
+                for (int v = 0; v < V; ++v) o[v] *= ms[v];
+              }
               const long long off = row_off + k * kstride;
               if (a.out) RowVec<float, V>::store(a.out + off, o);
               if (a.act_hi) {
@@ -296,7 +310,7 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
                 const long long o = static_cast<long long>(seg_start + idx / a.hg) * a.H + g * a.hg + hgi;
                 const float zz = a.z[o];
                 const float ee = zz > 0.f ? zz : kLeakySlope * zz;
-                a.alpha[o] = __expf(ee - mh) * ih;
+                a.alpha[o] = __expf(ee - mh) * ih * (a.edge_bits ? keep_scale1(a.edge_bits, o, a.edge_scale) : 1.f);
               }
             }
           }
@@ -399,6 +413,12 @@ edge_fwd_merge_kernel(const FwdArgs<T, V> a, const int* __restrict__ long_node,
       float o[V];
 #pragma unroll
       for (int v = 0; v < V; ++v) o[v] = fmaf(acc[k][v], inv, bsum);
+      if (a.drop_bits) {
+        float ms[V];
+        keep_scale<V>(a.drop_bits + static_cast<long long>(j) * a.drop_words, lm.head_off + q * V, a.drop_scale, ms);
+#pragma unroll
+        for (int v = 0; v < V; ++v) o[v] *= ms[v];
+      }
       const long long off = static_cast<long long>(j) * C + lm.head_off + q * V;
       if (a.out) RowVec<float, V>::store(a.out + off, o);
       if (a.act_hi) {
@@ -425,7 +445,7 @@ edge_fwd_merge_kernel(const FwdArgs<T, V> a, const int* __restrict__ long_node,
         const long long o = static_cast<long long>(e0 + idx / a.hg) * a.H + g * a.hg + hgi;
         const float zz = a.z[o];
         const float ee = zz > 0.f ? zz : kLeakySlope * zz;
-        a.alpha[o] = __expf(ee - mh) * ih;
+        a.alpha[o] = __expf(ee - mh) * ih * (a.edge_bits ? keep_scale1(a.edge_bits, o, a.edge_scale) : 1.f);
       }
     }
   }
@@ -506,17 +526,20 @@ static int run_fwd(const void* P, long long ldp, const float* A, const float* be
                    const int* csr_src, const int* csr_rel, const int4* ch, int n_chunks, const int2* pt,
                    const int* long_node, const int* long_part_ptr, int n_long, float* part_ml, float* part_b,
                    float* part_acc, float* out, void* act_hi, void* act_lo, int apply_elu, float* alpha, float* z,
-                   float* minv, float* bias_out, int H, int F, int R, int sm_count, int* work_counter,
+                   float* minv, float* bias_out, const uint32_t* drop_bits, int drop_words, float drop_scale,
+                   const uint32_t* edge_bits, float edge_scale, int H, int F, int R, int sm_count, int* work_counter,
                    cudaStream_t s) {
   const int hg = pick_heads_per_warp(H, F, V, R, smem_budget_override("RELGAT_FWD_BUDGET_KB", kSmemBudgetA));
   if (!hg) return RG_ERR_SHAPE;
+  if (H / hg > 32) return RG_ERR_SHAPE;  // work_counter holds 32 ints (one per head-group)
   if (work_counter) {
     cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int) * (H / hg), s);
     if (e != cudaSuccess) return cuda_status(e);
   }
   FwdArgs<T, V> a{static_cast<const T*>(P), A, beta, rowptr, csr_src, csr_rel, ch, pt, part_ml, part_b,
                   part_acc, out, static_cast<__nv_bfloat16*>(act_hi), static_cast<__nv_bfloat16*>(act_lo),
-                  alpha, z, minv, bias_out, n_chunks, H, F, R, hg, ldp, apply_elu, 0, 0, work_counter};
+                  alpha, z, minv, bias_out, n_chunks, H, F, R, hg, ldp, apply_elu, 0, 0, work_counter,
+                  drop_bits, drop_words, drop_scale, edge_bits, edge_scale};
   int rc = launch_fwd(a, sm_count, s);
   if (rc != RG_OK || n_long == 0) return rc;
   const int tasks = n_long * (H / hg);
@@ -532,8 +555,10 @@ extern "C" int relgat_layer_fwd(
     float* part_ml, float* part_b, float* part_acc,
     float* out, void* act_hi, void* act_lo, int apply_elu,
     float* alpha, float* z, float* minv, float* bias_out,
+    const unsigned int* drop_bits, int drop_words, float drop_scale, const unsigned int* edge_bits, float edge_scale,
     int H, int F, int R, int sm_count, int* work_counter, void* stream) {
   if (!P || !A || !rowptr || n_chunks < 0 || n_parts < 0 || n_long < 0 || H <= 0 || F <= 0 || R <= 0) return RG_ERR_ARG;
+  if (drop_bits && drop_words * 32 < H * F) return RG_ERR_ARG;
   if (n_chunks > 0 && !chunks) return RG_ERR_ARG;
   if (n_parts > 0 && (!parts || !long_node || !long_part_ptr || !part_ml || !part_b || !part_acc)) return RG_ERR_ARG;
   if (n_chunks == 0) return RG_OK;
@@ -547,13 +572,16 @@ extern "C" int relgat_layer_fwd(
     if (!vec_ok) return RG_ERR_ALIGN;
     return run_fwd<__nv_bfloat16, 8>(P, ldp, A, beta, rowptr, csr_src, csr_rel, ch, n_chunks, pt, long_node,
                                      long_part_ptr, n_long, part_ml, part_b, part_acc, out, act_hi, act_lo, apply_elu,
-                                     alpha, z, minv, bias_out, H, F, R, sm_count, work_counter, s);
+                                     alpha, z, minv, bias_out, drop_bits, drop_words, drop_scale, edge_bits, edge_scale, H, F, R, sm_count,
+                                     work_counter, s);
   }
   if ((F % 4 == 0) && (ldp % 4 == 0) && vec_ok)
     return run_fwd<float, 4>(P, ldp, A, beta, rowptr, csr_src, csr_rel, ch, n_chunks, pt, long_node, long_part_ptr,
                              n_long, part_ml, part_b, part_acc, out, act_hi, act_lo, apply_elu, alpha, z, minv,
-                             bias_out, H, F, R, sm_count, work_counter, s);
+                             bias_out, drop_bits, drop_words, drop_scale, edge_bits, edge_scale, H, F, R, sm_count,
+                             work_counter, s);
   return run_fwd<float, 1>(P, ldp, A, beta, rowptr, csr_src, csr_rel, ch, n_chunks, pt, long_node, long_part_ptr,
                            n_long, part_ml, part_b, part_acc, out, act_hi, act_lo, apply_elu, alpha, z, minv,
-                           bias_out, H, F, R, sm_count, work_counter, s);
+                           bias_out, drop_bits, drop_words, drop_scale, edge_bits, edge_scale, H, F, R, sm_count,
+                           work_counter, s);
 }

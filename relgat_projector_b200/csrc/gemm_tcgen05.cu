@@ -40,7 +40,10 @@ struct GemmParams {
   long long d_split_stride;
   int a_tile_bytes, b_tile_bytes;   // per plane
   int b_boxes;           // MN-major B: number of 64-wide boxes per tile
+  int staged;            // 1: the epilogue transposes 32x16 (fp32) / 32x32 (bf16) blocks through shared memory
 };
+
+constexpr int kEpiStageBytes = 4 * 32 * 64;  // per epilogue warp: 32 rows x 64 bytes
 
 // ---------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -114,8 +117,65 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
   return d;
 }
 
+// Coalesced epilogue of one tile for one epilogue warp (TMEM lane quarter `ew`).  tcgen05.ld hands every lane ONE row
+// (TMEM lane) and 16 / 32 consecutive columns, so a direct store scatters 16-byte pieces over 32 rows per
+// instruction.  Each warp therefore transposes its 32 x 64-byte block through its own 2 KB of shared memory (16-byte
+// pieces XOR-swizzled by (row >> 1) & 3: conflict-free both ways) and stores 8 rows x 64 contiguous bytes per
+// instruction (whole 32-byte sectors).  Kept out of line so that its registers do not add to the kernel's (the
+// by-relation edge kernel runs beside the dW GEMM and needs the register file's other half).
+template <bool BF16>
+__device__ __noinline__ void epilogue_staged(const GemmParams& p, uint8_t* stg, uint32_t taddr, int row0, int col0,
+                                             int ks, bool empty_k, int lane) {
+  const int rsub = lane >> 2, q_rd = lane & 3;
+  constexpr int cols_per = BF16 ? 32 : 16;  // columns per 64-byte row piece
+  constexpr int elems16 = BF16 ? 8 : 4;     // elements per 16-byte piece
+  for (int c0 = 0; c0 < p.BN; c0 += cols_per) {
+    uint32_t r[BF16 ? 32 : 16];
+    const int width = min(cols_per, p.BN - c0);  // bf16: BN % 32 may be 16
+    if constexpr (BF16) {
+      if (width == 32) {
+        tmem_ld32(taddr + c0, r);
+      } else {
+        uint32_t t16[32];
+        tmem_ld16(taddr + c0, t16);
+#pragma unroll
+        for (int v = 0; v < 16; ++v) { r[v] = t16[v]; r[v + 16] = 0u; }
+      }
+#pragma unroll
+      for (int v = 0; v < 16; ++v)
+        r[v] = empty_k ? 0u : pack_bf16x2(__uint_as_float(r[2 * v]), __uint_as_float(r[2 * v + 1]));
+    } else {
+      uint32_t t16[32];
+      tmem_ld16(taddr + c0, t16);
+#pragma unroll
+      for (int v = 0; v < 16; ++v) r[v] = empty_k ? 0u : t16[v];
+    }
+    __syncwarp();  // the previous block has been read back by every lane
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
+          make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+    __syncwarp();
+    const int col = col0 + c0;
+    const bool piece_ok = col + (q_rd + 1) * elems16 <= p.N && q_rd * elems16 < width;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int rl = 8 * j + rsub;
+      const int row = row0 + rl;
+      const uint4 vv = *reinterpret_cast<const uint4*>(stg + rl * 64 + ((q_rd ^ ((rl >> 1) & 3)) << 4));
+      if (row < p.M && piece_ok) {
+        if constexpr (BF16)
+          *reinterpret_cast<uint4*>(p.d_bf16 + static_cast<long long>(row) * p.ldd + col + q_rd * 8) = vv;
+        else
+          *reinterpret_cast<uint4*>(p.d + static_cast<long long>(ks) * p.d_split_stride +
+                                    static_cast<long long>(row) * p.ldd + col + q_rd * 4) = vv;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------- the kernel
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __maxnreg__(88)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                          const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                          const GemmParams p) {
@@ -251,11 +311,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
       const bool empty_k = (ks * p.kb_per_split >= total_kb);
       mbar_wait(&tmem_full[acc], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(ew * 32) << 16);
+      if (p.staged) {
+        uint8_t* stg = smem + static_cast<size_t>(p.stages) * stage_bytes + ew * (32 * 64);
+        if (p.d_bf16) epilogue_staged<true>(p, stg, taddr, m_tile * kBM + ew * 32, n_tile * p.BN, ks, empty_k, lane);
+        else epilogue_staged<false>(p, stg, taddr, m_tile * kBM + ew * 32, n_tile * p.BN, ks, empty_k, lane);
+      } else {
       const int row = m_tile * kBM + ew * 32 + lane;
       float* drow = p.d ? p.d + static_cast<long long>(ks) * p.d_split_stride + static_cast<long long>(row) * p.ldd
                         : nullptr;
       __nv_bfloat16* hrow = p.d_bf16 ? p.d_bf16 + static_cast<long long>(row) * p.ldd : nullptr;
-      const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(ew * 32) << 16);
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t r[32];
         const int width = min(32, p.BN - c0);   // BN is a multiple of 16: width is 32 or 16
@@ -296,6 +361,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
               if (v < width && col + v < p.N) drow[col + v] = empty_k ? 0.f : __uint_as_float(r[v]);
           }
         }
+      }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -416,6 +482,10 @@ extern "C" int relgat_gemm_bf16(const void* a_hi, const void* a_lo, long long ld
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;
   p.BN = pick_bn(N);
+  if (const char* v = getenv("RELGAT_GEMM_BN")) {  // experiment knob: N tile (multiple of 16, <= 256)
+    const int bn = atoi(v);
+    if (bn >= 16 && bn <= 256 && bn % 16 == 0 && N > bn) p.BN = bn;
+  }
   p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
   p.split = a_lo ? 1 : 0;
   const int total_kb = (K + kBK - 1) / kBK;
@@ -427,9 +497,18 @@ extern "C" int relgat_gemm_bf16(const void* a_hi, const void* a_lo, long long ld
   p.b_tile_bytes = p.b_mn ? p.b_boxes * kBK * 128 : p.BN * kBK * 2;
   const int planes = p.split ? 2 : 1;
   const int stage_bytes = planes * (p.a_tile_bytes + p.b_tile_bytes);
-  const int smem_budget = 227 * 1024 - 2048;
+  // the coalesced epilogue needs whole 16-byte pieces: N and the row stride multiples of the piece width
+  const int piece = d_is_bf16 ? 8 : 4;
+  p.staged = (N % piece == 0 && (splits_k > 1 ? N : ldd) % piece == 0 &&
+              reinterpret_cast<uintptr_t>(splits_k > 1 ? workspace : d_out) % 16 == 0) ? 1 : 0;
+  if (getenv("RELGAT_GEMM_DIRECT_EPILOGUE")) p.staged = 0;  // experiment knob: the old one-row-per-lane stores
+  const int smem_budget = 227 * 1024 - 2048 - (p.staged ? kEpiStageBytes : 0);
   int stages = smem_budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  if (const char* v = getenv("RELGAT_GEMM_STAGES")) {
+    const int st = atoi(v);
+    if (st >= 2 && st <= stages) stages = st;
+  }
   if (stages < 2) return RG_ERR_SHAPE;
   p.stages = stages;
   if (splits_k > 1) {
@@ -457,7 +536,7 @@ extern "C" int relgat_gemm_bf16(const void* a_hi, const void* a_lo, long long ld
   const long long units = static_cast<long long>((M + kBM - 1) / kBM) * ((N + p.BN - 1) / p.BN) * splits_k;
   if (sm_count <= 0) sm_count = 148;
   const int grid = static_cast<int>(units < sm_count ? units : sm_count);
-  const int smem_bytes = stages * stage_bytes + 1024;
+  const int smem_bytes = stages * stage_bytes + 1024 + (p.staged ? kEpiStageBytes : 0);
   cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return cuda_status(e);
   gemm_bf16_tcgen05_kernel<<<grid, kGemmThreads, smem_bytes, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);

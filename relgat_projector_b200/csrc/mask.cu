@@ -1,0 +1,85 @@
+// Dropout masks for the fused layer (reference core/model/layer.py:296-297 attention dropout, :321-322 feature
+// dropout) and a row-clearing helper for the sparse hand-over of the batch gradient.
+//
+// A mask is a bit array: element i lives in word i >> 5, bit i & 31; bit = 1 means KEEP.  Feature masks index
+// i = row * (32 * words_per_row) + column (rows start on a word boundary), attention masks i = csr_slot * H + head.
+// The bits come from Philox4x32-10 keyed by a seed the host draws from torch's generator (so torch.manual_seed
+// governs them), or are supplied by the caller (tests inject a mask and replay it in the oracle).
+#include "common.cuh"
+
+namespace relgat {
+
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+
+__device__ __forceinline__ void philox4x32_10(uint64_t seed, uint64_t ctr, uint32_t (&out)[4]) {
+  uint32_t c[4] = {static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), 0u, 0u};
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) out[i] = c[i];
+}
+
+// One thread per 32-bit word: four Philox calls = 32 draws of 16 bits; keep when draw >= threshold.
+__global__ void bernoulli_bits_kernel(uint32_t* __restrict__ bits, long long n_words, uint32_t threshold, uint64_t seed) {
+  const long long w = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (w >= n_words) return;
+  uint32_t word = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t r[4];
+    philox4x32_10(seed, static_cast<uint64_t>(w) * 4 + q, r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      word |= ((r[i] & 0xffffu) >= threshold ? 1u : 0u) << (q * 8 + i * 2);
+      word |= ((r[i] >> 16) >= threshold ? 1u : 0u) << (q * 8 + i * 2 + 1);
+    }
+  }
+  bits[w] = word;
+}
+
+__global__ void zero_rows_kernel(float* __restrict__ table, long long ld, const long long* __restrict__ ids, long long n,
+                                 int D) {
+  const long long i = blockIdx.x;
+  if (i >= n) return;
+  float* row = table + ids[i] * ld;
+  if ((D & 3) == 0 && (ld & 3) == 0 && reinterpret_cast<uintptr_t>(table) % 16 == 0) {
+    for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4) *reinterpret_cast<float4*>(row + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    for (int c = threadIdx.x; c < D; c += blockDim.x) row[c] = 0.f;
+  }
+}
+
+}  // namespace relgat
+
+using namespace relgat;
+
+extern "C" int relgat_bernoulli_bits(unsigned int* bits, long long n_words, float p_drop, unsigned long long seed,
+                                     void* stream) {
+  if (!bits || n_words < 0 || !(p_drop >= 0.f) || p_drop > 1.f) return RG_ERR_ARG;
+  if (n_words == 0) return RG_OK;
+  // P(drop) = threshold / 65536 (16-bit draws: |p - P(drop)| <= 7.6e-6)
+  uint32_t threshold = static_cast<uint32_t>(p_drop * 65536.f + 0.5f);
+  if (threshold > 65536u) threshold = 65536u;
+  const int th = 256;
+  bernoulli_bits_kernel<<<static_cast<unsigned>((n_words + th - 1) / th), th, 0, static_cast<cudaStream_t>(stream)>>>(
+      bits, n_words, threshold, seed);
+  return cuda_status(cudaGetLastError());
+}
+
+extern "C" int relgat_zero_rows(float* table, long long ld, const long long* ids, long long n, int D, void* stream) {
+  if (n < 0 || D <= 0) return RG_ERR_ARG;
+  if (n == 0) return RG_OK;
+  if (!table || !ids) return RG_ERR_ARG;
+  zero_rows_kernel<<<static_cast<unsigned>(n), 128, 0, static_cast<cudaStream_t>(stream)>>>(table, ld, ids, n, D);
+  return cuda_status(cudaGetLastError());
+}

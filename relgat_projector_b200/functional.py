@@ -47,16 +47,79 @@ def sparse_rows_of(grad: torch.Tensor) -> Optional[torch.Tensor]:
     return tag[0]
 
 
+# ---------------------------------------------------------------------------------------------
+# persistent all-zero [N, C] tables.  The loss reads <= B*(2+K) rows of the stack's output (reference model.py:136-137),
+# so the gradient of that output is zero outside those rows.  The fused "stack + row gather" node scatters the batch
+# rows' gradients into such a table, runs the last layer's backward on it (the by-source pass gathers G[dst] for every
+# edge, so a dense table is needed) and clears the rows again: no [N, C] memset and no dense index_add per step.
+# ---------------------------------------------------------------------------------------------
+_ZERO_TABLES = {}
+
+
+def _take_zero_table(device, n: int, c: int) -> torch.Tensor:
+    key = (torch.device(device).index, int(n), int(c))
+    pool = _ZERO_TABLES.setdefault(key, [])
+    return pool.pop() if pool else torch.zeros((n, c), dtype=torch.float32, device=device)
+
+
+def _return_zero_table(t: torch.Tensor) -> None:
+    key = (t.device.index, int(t.size(0)), int(t.size(1)))
+    pool = _ZERO_TABLES.setdefault(key, [])
+    if len(pool) < 2:  # all rows are zero again (stream-ordered): ready for the next backward on this stream
+        pool.append(t)
+
+
+def clear_zero_tables() -> None:
+    _ZERO_TABLES.clear()
+
+
+def stable_sort_ids(ids: torch.Tensor, n_max: int):
+    """(sorted keys int64, perm int64) of a stable sort; the radix sort runs on the narrowest integer type that holds
+    ``n_max`` (CUB does 8 passes over int64 keys, 2 over int16: ~100 us -> ~35 us for a batch's ids)."""
+    narrow = torch.int16 if n_max < 2 ** 15 else (torch.int32 if n_max < 2 ** 31 else torch.int64)
+    keys, perm = torch.sort(ids.to(narrow) if narrow != ids.dtype else ids, stable=True)
+    return keys.to(torch.int64), perm
+
+
+def presort_on_side_stream(ids: torch.Tensor, n_max: int):
+    """Stable sort of a batch's id vector on the side stream (it is only needed by the backward: off the forward's
+    critical chain).  Returns (keys, perm, event); wait for ``event`` on the consuming stream before use."""
+    main = torch.cuda.current_stream(ids.device)
+    side = _side_stream(ids.device)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        keys, perm = stable_sort_ids(ids, n_max)
+        ev = torch.cuda.Event()
+        ev.record(side)
+    for t in (keys, perm):
+        t.record_stream(main)
+    ids.record_stream(side)
+    return keys, perm, ev
+
+
+class LayerDropout:
+    """Dropout state of one layer for one forward/backward: ``feat`` = ops.DropMask of the feature dropout on the
+    layer's output (reference layer.py:321-322) or None, ``edge`` = ops.DropMask of the attention dropout
+    (layer.py:296-297) or None."""
+
+    def __init__(self, feat=None, edge=None):
+        self.feat, self.edge = feat, edge
+
+
 class RelGATStackFunction(torch.autograd.Function):
     """out = RelGAT_L(... ELU(RelGAT_1(x0)) ...) for layers sharing one graph.
 
     args: x0 [N, D_in] fp32, then per layer (W [H*F, D_in_l], A [H, R, F], beta [R] or None).
     ``x0_planes`` may carry a cached bf16 split of a frozen x0 (reference model.py:32 keeps the
     input embeddings as a buffer, so the split is paid once, not per step).
+    ``drop``: None or one LayerDropout per layer (masks applied inside the edge kernels).
+    ``gather_ids``: None = return all N rows; int64 [n] = return out[gather_ids] only (the rows the scorer reads,
+    reference model.py:136-137) — backward then receives [n, C] and never builds a dense [N, C] gradient.
     """
 
     @staticmethod
-    def forward(ctx, x0, graph: GraphIndex, heads: int, out_dim: int, precision: str, x0_planes, *params):
+    def forward(ctx, x0, graph: GraphIndex, heads: int, out_dim: int, precision: str, x0_planes, drop, gather_ids,
+                *params):
         if precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {PRECISIONS}")
         if len(params) % 3 != 0 or not params:
@@ -83,34 +146,64 @@ class RelGATStackFunction(torch.autograd.Function):
             P = ops.gemm(planes, False, Wp, False, N, C, d_in,
                          out_dtype=torch.float32 if with_lo else torch.bfloat16)
             last = l == L - 1
+            dl = drop[l] if drop is not None else None
             out, act, _, z, minv, bias = ops.edge_fwd(P, A.detach(), None if beta is None else beta.detach(), graph,
-                                                      H, F, want_act=not last, apply_elu=True, act_lo=with_lo)
+                                                      H, F, want_act=not last, apply_elu=True, act_lo=with_lo,
+                                                      feat_drop=dl.feat if dl else None, edge_drop=dl.edge if dl else None)
             saved.append(dict(xp=planes, Wp=Wp, WTp=WTp, P=P, out=out, minv=minv, z=z, bias=bias, A=A.detach(),
-                              d_in=d_in, has_beta=beta is not None))
+                              d_in=d_in, has_beta=beta is not None, drop=dl))
             planes = act
         ctx.saved = saved
         ctx.graph = graph
         ctx.cfg = (H, F, L, with_lo)
         ctx.x0_needs_grad = bool(x0.requires_grad)
+        ctx.gather = None
+        if gather_ids is not None:
+            ids = gather_ids.contiguous()
+            ctx.gather = presort_on_side_stream(ids, N)  # (sorted keys, perm, event): summation order of backward
+            rows = out.new_empty((ids.numel(), C))
+            ops.pull_rows(out, ids, rows)
+            return rows
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
+        if ctx.saved is None:
+            raise RuntimeError("the RelGAT stack's saved state was released by a previous backward; re-run the forward "
+                               "(retain_graph is not supported by the fused stack)")
         H, F, L, with_lo = ctx.cfg
         g = ctx.graph
         C = H * F
         N = g.N
         grads: List[Optional[torch.Tensor]] = [None] * (3 * L)
-        dY = grad_out.contiguous()
-        nz_rows = sparse_rows_of(grad_out) if dY is grad_out else None
-        owned = False
+        table = None
+        if ctx.gather is not None:
+            # gradient of the gathered rows -> rows of a persistent zero table (ordered segmented sum: a node may be
+            # named several times by the batch); everything else stays exactly zero
+            keys, perm, ready = ctx.gather
+            torch.cuda.current_stream(grad_out.device).wait_event(ready)
+            table = _take_zero_table(grad_out.device, N, C)
+            ops.index_add_sorted(grad_out.contiguous(), keys, N, out=table, presorted=(keys, perm), accumulate=False)
+            dY, nz_rows, owned = table, keys, True
+        else:
+            dY = grad_out.contiguous()
+            nz_rows = sparse_rows_of(grad_out) if dY is grad_out else None
+            owned = False
         dX = None
         for l in reversed(range(L)):
             s = ctx.saved[l]
+            dl = s["drop"]
+            # fp32 storage: G aliases dY and only the batch rows are touched; bf16 storage writes a dense bf16 G
             G, t, hsum = ops.edge_bwd_prep(dY, s["out"], s["bias"], H, F, apply_elu=(l < L - 1), inplace=owned,
-                                           g_bf16=not with_lo, nonzero_rows=nz_rows if l == L - 1 else None)
+                                           g_bf16=not with_lo, nonzero_rows=nz_rows if l == L - 1 else None,
+                                           feat_drop=dl.feat if dl else None)
             _, dPp, dz = ops.edge_bwd_src(s["P"], G, s["A"], s["z"], s["minv"], t, g, H, F,
-                                          want_fp32=False, want_planes=True, planes_lo=with_lo)
+                                          want_fp32=False, want_planes=True, planes_lo=with_lo,
+                                          edge_drop=dl.edge if dl else None)
+            if table is not None and l == L - 1:
+                ops.zero_rows(table, nz_rows)  # the table's rows are consumed (G aliased it): make it all-zero again
+                _return_zero_table(table)
+                G = None
             main = torch.cuda.current_stream(dY.device)
             side = _side_stream(dY.device)
             side.wait_stream(main)
@@ -129,14 +222,15 @@ class RelGATStackFunction(torch.autograd.Function):
                     tns.record_stream(main)
             del G, dPp, dz
         ctx.saved = None
-        return (dX if ctx.x0_needs_grad else None, None, None, None, None, None, *grads)
+        return (dX if ctx.x0_needs_grad else None, None, None, None, None, None, None, None, *grads)
 
 
-def relgat_stack(x0, graph, heads, out_dim, layer_params: Sequence, precision="fp32", x0_planes=None):
+def relgat_stack(x0, graph, heads, out_dim, layer_params: Sequence, precision="fp32", x0_planes=None, drop=None,
+                 gather_ids=None):
     flat = []
     for W, A, beta in layer_params:
         flat += [W, A, beta]
-    return RelGATStackFunction.apply(x0, graph, heads, out_dim, precision, x0_planes, *flat)
+    return RelGATStackFunction.apply(x0, graph, heads, out_dim, precision, x0_planes, drop, gather_ids, *flat)
 
 
 class GatherRowsFunction(torch.autograd.Function):
@@ -194,7 +288,8 @@ class GatherScoreFunction(torch.autograd.Function):
 
 class ScoreRowsFunction(torch.autograd.Function):
     """Module-level scorer call on already gathered rows (reference scorer.py:58-84, 154-186)
-    and/or the relation operator ``transform`` (scorer.py:86-94, 188-201)."""
+    and/or the relation operator ``transform`` (scorer.py:86-94, 188-201).  ``want_transform``: True = every
+    triple, an int = the first that many triples."""
 
     @staticmethod
     def forward(ctx, kind, normalize, src_emb, dst_emb, rel_emb, rel_ids, want_score, want_transform):
@@ -202,9 +297,11 @@ class ScoreRowsFunction(torch.autograd.Function):
         B = int(rel_ids.numel())
         xd = dst_emb if dst_emb is not None else src_emb
         score, tr, _, _ = ops.score_fwd(kind, normalize, src_emb.detach(), None, xd.detach(), None, rel_emb.detach(),
-                                        rel_ids, n_transform=B if want_transform else 0)
+                                        rel_ids,
+                                        n_transform=B if want_transform is True else int(want_transform))
         ctx.save_for_backward(src_emb, xd, rel_emb, rel_ids)
         ctx.meta = (kind, normalize, dst_emb is not None)
+        ctx.rel_sort = presort_on_side_stream(rel_ids, rel_emb.size(0)) if rel_emb.requires_grad and B else None
         empty = src_emb.new_empty((0,))
         return (score if want_score else empty), (tr if tr is not None else empty)
 
@@ -216,7 +313,14 @@ class ScoreRowsFunction(torch.autograd.Function):
                                             want_src=ctx.needs_input_grad[2],
                                             want_dst=has_dst and ctx.needs_input_grad[3],
                                             want_rel=ctx.needs_input_grad[4])
-        drel = ops.index_add_sorted(d_rel, rel_ids, rel_emb.size(0)) if d_rel is not None else None
+        drel = None
+        if d_rel is not None:
+            pre = None
+            if ctx.rel_sort is not None:
+                keys, perm, ready = ctx.rel_sort
+                torch.cuda.current_stream(d_rel.device).wait_event(ready)
+                pre = (keys, perm)
+            drel = ops.index_add_sorted(d_rel, rel_ids, rel_emb.size(0), presorted=pre)
         return None, None, d_src, d_dst, drel, None, None, None
 
 
@@ -276,3 +380,56 @@ class MarginLossFunction(torch.autograd.Function):
 
 def fused_margin_loss(score, num_pos: int, num_neg: int, margin: float, projection_path: bool = False):
     return MarginLossFunction.apply(score, int(num_pos), int(num_neg), float(margin), bool(projection_path))
+
+
+class RankLossFunction(torch.autograd.Function):
+    """Ranking loss of reference core/loss/relgat_loss.py:32-71 on pos [B], neg [B, K] (any strides) as one kernel
+    that also yields d loss / d score; ``sanitize`` folds the trainer's nan_to_num (trainer:584, 647-648) in."""
+
+    @staticmethod
+    def forward(ctx, pos, neg, kind, margin, alpha, sanitize):
+        loss, dpos, dneg = ops.rank_loss(pos.detach(), neg.detach(), kind, margin, alpha, sanitize)
+        ctx.save_for_backward(dpos, dneg)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        dpos, dneg = ctx.saved_tensors
+        return dpos * g, dneg * g, None, None, None, None
+
+
+def fused_rank_loss(pos, neg, kind: str, margin: float = 1.0, alpha: float = 1.0, sanitize: bool = False):
+    return RankLossFunction.apply(pos, neg, kind, float(margin if margin is not None else 0.0),
+                                  float(alpha if alpha is not None else 1.0), bool(sanitize))
+
+
+class ReconLossFunction(torch.autograd.Function):
+    """Weighted reconstruction terms of reference core/loss/multi_objective_loss.py:62-80:
+    w_pos*CosineLoss(f_r(A), B) + w_neg*(1 - CosineLoss(f_r(A), negB)) + w_mse*MSE(f_r(A), B), one kernel producing
+    the three values and the gradients of the weighted sum.  Returns (weighted sum, values [3] detached)."""
+
+    @staticmethod
+    def forward(ctx, tr, dst, negdst, w_pos, w_neg, w_mse):
+        has_neg = negdst is not None and negdst.numel() > 0
+        values, d_tr, d_dst, d_neg = ops.recon_loss(tr.detach(), dst.detach(), negdst.detach() if has_neg else None,
+                                                    w_pos, w_neg if has_neg else 0.0, w_mse)
+        ctx.save_for_backward(d_tr, d_dst, d_neg)
+        ctx.has_neg = has_neg
+        ctx.mark_non_differentiable(values)
+        total = values.new_zeros(())
+        if w_pos != 0.0:  # zero-weight terms are dropped, as the reference does (multi_objective_loss.py:62-80)
+            total = total + w_pos * values[0]
+        if w_neg != 0.0:  # the mean over an empty negative set is nan in the reference too
+            total = total + w_neg * (1.0 - values[1])
+        if w_mse != 0.0:
+            total = total + w_mse * values[2]
+        return total, values
+
+    @staticmethod
+    def backward(ctx, g, _gv):
+        d_tr, d_dst, d_neg = ctx.saved_tensors
+        return d_tr * g, d_dst * g, (d_neg * g if ctx.has_neg else None), None, None, None
+
+
+def fused_recon_loss(transformed_src, dst_vec, neg_dst_vec, w_pos: float, w_neg: float, w_mse: float):
+    return ReconLossFunction.apply(transformed_src, dst_vec, neg_dst_vec, float(w_pos), float(w_neg), float(w_mse))

@@ -8,6 +8,7 @@ import torch
 import torch.nn as nn
 
 from . import functional as RF
+from . import ops
 from .graph import get_graph_index
 
 
@@ -70,16 +71,27 @@ class RelGATLayer(nn.Module):
         return self.packed_weight(), self.packed_attention(), self.rel_bias
 
     def check_supported(self):
-        if self.training and self.rel_attn_drop.p > 0.0:
-            raise NotImplementedError(
-                "relation_attn_dropout > 0 in training mode is not supported by the fused edge kernel "
-                "(the reference default is 0.0, core/model/model.py:24)")
+        """Kept for callers of round 1: every dropout configuration of the reference is supported now."""
+
+    def draw_dropout(self, num_nodes: int, num_edges: int, device) -> Optional[RF.LayerDropout]:
+        """Masks of this layer's two dropout sites for one step (None in eval mode or when both rates are 0):
+        feature dropout on the output rows (reference layer.py:321-322) and attention dropout on alpha
+        (layer.py:296-297).  Both are applied INSIDE the fused edge kernels; the bits come from Philox keyed by a
+        seed drawn from torch's generator (``torch.manual_seed`` governs them)."""
+        if not self.training:
+            return None
+        p_feat, p_attn = float(self.dropout.p), float(self.rel_attn_drop.p)
+        if p_feat <= 0.0 and p_attn <= 0.0:
+            return None
+        C = self.heads * self.out_dim
+        feat = ops.DropMask.draw((num_nodes, (C + 31) // 32), p_feat, device) if p_feat > 0.0 else None
+        edge = ops.DropMask.draw(((num_edges * self.heads + 31) // 32,), p_attn, device) if p_attn > 0.0 else None
+        return RF.LayerDropout(feat, edge)
 
     def forward(self, node_emb: torch.Tensor, edge_index: torch.Tensor, edge_type: torch.Tensor) -> torch.Tensor:
         """node_emb [N, in_dim] fp32, edge_index [2, E] int64 (row 0 = src, row 1 = dst),
         edge_type [E] int64  ->  [N, heads*out_dim] (column = h*out_dim + f)."""
-        self.check_supported()
         graph = get_graph_index(edge_index, edge_type, node_emb.size(0), self.num_rel)
-        out = RF.relgat_stack(node_emb, graph, self.heads, self.out_dim, [self.kernel_params()],
-                              precision=self.precision)
-        return self.dropout(out)
+        drop = self.draw_dropout(graph.N, graph.E, node_emb.device)
+        return RF.relgat_stack(node_emb, graph, self.heads, self.out_dim, [self.kernel_params()],
+                               precision=self.precision, drop=None if drop is None else [drop])

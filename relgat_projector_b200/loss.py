@@ -1,10 +1,11 @@
 """Ranking and reconstruction losses over the scorer outputs (reference
 relgat_projector/core/loss/{relgat_loss,multi_objective_loss,cosine,mse}.py).
 
-These act on ``[B]`` / ``[B, K]`` score tensors and ``[B, D]`` rows — a few kilobytes next to the
-full-graph message passing — and are expressed with torch tensor ops; the class names,
-constructor arguments and call signatures match the reference so the reference trainer can use
-either implementation.
+Class names, constructor arguments and call signatures match the reference, so the reference trainer can use
+either implementation.  CUDA float32 inputs run on the fused loss kernels of csrc/loss.cu (value and gradient in one
+launch, fixed summation order): ``RelGATLoss`` -> relgat_rank_loss, ``MultiObjectiveRelLoss`` -> relgat_rank_loss +
+relgat_recon_loss.  Host tensors (the CPU unit tests of the API contract) and float64 take the same formulas as
+torch tensor ops.
 """
 from __future__ import annotations
 
@@ -12,6 +13,11 @@ from typing import Any, Dict, Optional
 
 import torch
 import torch.nn.functional as F
+
+
+def _fusable(*tensors) -> bool:
+    """CUDA float32 tensors go to the fused loss kernels."""
+    return all(t is not None and t.is_cuda and t.dtype == torch.float32 for t in tensors)
 
 
 class CosineLoss:
@@ -42,7 +48,15 @@ class RelGATLoss:
             self.self_adv_alpha = float(self.self_adv_alpha)
         self.use_self_adv_neg = loss_type == "self_adversarial_loss"
 
-    def prepare_scores_and_compute_loss(self, pos_score: torch.Tensor, neg_score: torch.Tensor) -> torch.Tensor:
+    def prepare_scores_and_compute_loss(self, pos_score: torch.Tensor, neg_score: torch.Tensor,
+                                        sanitize: bool = False) -> torch.Tensor:
+        if _fusable(pos_score, neg_score) and neg_score.dim() == 2:
+            from .functional import fused_rank_loss
+            return fused_rank_loss(pos_score, neg_score, "self_adversarial_loss" if self.use_self_adv_neg else "margin",
+                                   self.margin, self.self_adv_alpha, sanitize)
+        if sanitize:
+            pos_score = torch.nan_to_num(pos_score, nan=0.0, neginf=-1e9, posinf=1e9)
+            neg_score = torch.nan_to_num(neg_score, nan=0.0, neginf=-1e9, posinf=1e9)
         if self.use_self_adv_neg:
             return self._self_adversarial_loss(pos_score, neg_score)
         return self._margin_ranking_loss(pos_score, neg_score)
@@ -69,11 +83,28 @@ class MultiObjectiveRelLoss:
         self.neg_cosine_weight = run_config.get("neg_cosine_weight", neg_cosine_weight)
         self.mse_weight = run_config.get("mse_weight", mse_weight)
         self.relgat_loss = relgat_loss
+        self.last_recon_values = None  # (cosine_pos, cosine_neg, mse) loss values of the last fused call
 
     def relgat_ranking_loss(self, pos_score, neg_score):
         return self.relgat_loss.prepare_scores_and_compute_loss(pos_score=pos_score, neg_score=neg_score)
 
-    def __call__(self, *, pos_score, neg_score, transformed_src, dst_vec, neg_dst_vec):
+    def __call__(self, *, pos_score, neg_score, transformed_src, dst_vec, neg_dst_vec, sanitize: bool = False):
+        weights = [w for w in (self.ranking_weight, self.pos_cosine_weight, self.neg_cosine_weight, self.mse_weight)
+                   if w != 0.0]
+        if not weights:
+            raise ValueError("At least one loss weight must be non-zero.")
+        self.last_recon_values = None
+        if _fusable(pos_score, neg_score, transformed_src, dst_vec, neg_dst_vec) and neg_dst_vec.dim() == 3:
+            from .functional import fused_recon_loss
+            total, self.last_recon_values = fused_recon_loss(transformed_src, dst_vec, neg_dst_vec, self.pos_cosine_weight,
+                                                             self.neg_cosine_weight, self.mse_weight)
+            if self.ranking_weight != 0.0:
+                total = total + self.ranking_weight * self.relgat_loss.prepare_scores_and_compute_loss(
+                    pos_score=pos_score, neg_score=neg_score, sanitize=sanitize)
+            return total / sum(weights)
+        if sanitize:
+            pos_score = torch.nan_to_num(pos_score, nan=0.0, neginf=-1e9, posinf=1e9)
+            neg_score = torch.nan_to_num(neg_score, nan=0.0, neginf=-1e9, posinf=1e9)
         terms = [
             (self.ranking_weight, lambda: self.relgat_ranking_loss(pos_score, neg_score)),
             (self.pos_cosine_weight, lambda: CosineLoss.calculate(transformed_src, dst_vec)),
@@ -84,6 +115,41 @@ class MultiObjectiveRelLoss:
         if not active:
             raise ValueError("At least one loss weight must be non-zero.")
         return torch.stack([w * fn() for w, fn in active]).sum() / sum(w for w, _ in active)
+
+
+def calculate_loss(model, src_ids, rel_ids, dst_ids, pos_examples_in_batch: int, relgat_loss: RelGATLoss,
+                   multi_loss: Optional[MultiObjectiveRelLoss] = None):
+    """The trainer's ``_calculate_loss`` (reference trainer/relgat_projector.py:498-557 with :559-655) on the fused
+    path: stack + batch-row gather -> [projection of those rows] -> score (+ transform of the positives) in one
+    launch -> ranking [+ reconstruction] loss kernels.  Same return tuple:
+    (pos_score [B], neg_score [B, K], loss, mse, cosine_pos, cosine_neg); the last three are 0-d tensors (the
+    reference calls ``.item()`` on them for logging) or None without projection.
+
+    The two negative layouts of the reference are reproduced as strided views of the flat score vector: without
+    projection ``view(K, B).T`` (trainer:671-675), with projection ``view(B, K)`` and ``neg_dst_vec.view(B, K, D)
+    .permute(1, 0, 2)`` (trainer:628-642).  Scores are sanitised like trainer:584 / 647-648."""
+    b = int(pos_examples_in_batch)
+    k = (int(src_ids.numel()) - b) // b if b else 0
+    if not model.project_to_input_size:
+        scores, _, _ = model(src_ids, rel_ids, dst_ids, transform_to_input_if_possible=False)
+        pos, neg = scores[:b], scores[b:].view(k, b).t()
+        loss = relgat_loss.prepare_scores_and_compute_loss(pos, neg, sanitize=True)
+        return pos, neg, loss, None, None, None
+    if multi_loss is None:
+        raise ValueError("project_to_input_size=True needs the MultiObjectiveRelLoss (trainer:528-534)")
+    scores, tr, dst_vec = model(src_ids, rel_ids, dst_ids, transform_rows=b)
+    pos, neg = scores[:b], scores[b:].view(b, k)
+    ndv = dst_vec[b:].view(b, k, dst_vec.size(1)).permute(1, 0, 2) if k > 0 else None
+    if ndv is None:
+        ndv = dst_vec.new_zeros((0, b, dst_vec.size(1)))
+    loss = multi_loss(pos_score=pos, neg_score=neg, transformed_src=tr, dst_vec=dst_vec[:b], neg_dst_vec=ndv,
+                      sanitize=True)
+    vals = getattr(multi_loss, "last_recon_values", None)
+    if vals is None:
+        with torch.no_grad():
+            vals = torch.stack([CosineLoss.calculate(tr, dst_vec[:b]), CosineLoss.calculate(tr, ndv),
+                                MSELoss.calculate(tr, dst_vec[:b])])
+    return pos, neg, loss, vals[2], vals[0], vals[1]
 
 
 def fused_margin_ranking_loss(scores: torch.Tensor, num_pos: int, num_neg: int, margin: float,

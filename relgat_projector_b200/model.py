@@ -46,7 +46,6 @@ class RelGATModel(nn.Module):
         self.projection_layers = projection_layers
         self.project_to_input_size = project_to_input_size
         self.precision = precision
-        self.project_batch_rows_only = True  # forward(): project only the rows the scorer reads (identical values)
         if project_to_input_size and self.projection_layers < 1:
             raise ValueError("projection_layers must be >= 1 when project_to_input_size=True")
         self._config = dict(
@@ -105,25 +104,19 @@ class RelGATModel(nn.Module):
     def _graph(self):
         return get_graph_index(self.edge_index, self.edge_type, self.node_emb_fixed.size(0), self.num_rel)
 
-    def _stack_output(self) -> torch.Tensor:
-        """Output of the GAT stack for every node, before the projection head."""
+    def _stack_output(self, gather_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Output of the GAT stack before the projection head: all N rows, or only ``x[gather_ids]``.
+
+        One autograd node for the whole stack: ELU between layers (reference model.py:286-287) and both dropouts of
+        every layer (layer.py:296-297, 321-322) are applied inside the edge kernels, so training with the
+        reference's default rates runs the same fused path as dropout 0."""
         layers = self._layers()
-        for lyr in layers:
-            lyr.check_supported()
-        inter_dropout = self.training and any(lyr.dropout.p > 0.0 for lyr in layers[:-1])
-        if not inter_dropout:
-            # one autograd node for the whole stack; ELU between layers fused into the edge kernel
-            x = RF.relgat_stack(self.node_emb_fixed, self._graph(), layers[0].heads, layers[0].out_dim,
-                                [lyr.kernel_params() for lyr in layers], precision=self.precision,
-                                x0_planes=self._input_planes())
-            x = layers[-1].dropout(x)
-        else:
-            x = self.node_emb_fixed
-            for li, gat in enumerate(layers):
-                x = gat(x, self.edge_index, self.edge_type)
-                if self.act is not None and li < len(layers) - 1:
-                    x = self.act(x)
-        return x
+        graph = self._graph()
+        drop = [lyr.draw_dropout(graph.N, graph.E, self.node_emb_fixed.device) for lyr in layers]
+        drop = [d if d is not None else RF.LayerDropout() for d in drop] if any(d is not None for d in drop) else None
+        return RF.relgat_stack(self.node_emb_fixed, graph, layers[0].heads, layers[0].out_dim,
+                               [lyr.kernel_params() for lyr in layers], precision=self.precision,
+                               x0_planes=self._input_planes(), drop=drop, gather_ids=gather_ids)
 
     # -- reference API ------------------------------------------------------------------------
     def single_gat_step(self) -> torch.Tensor:
@@ -133,32 +126,33 @@ class RelGATModel(nn.Module):
             x = self.projection(x)
         return x
 
-    def _dropout_active(self) -> bool:
-        if not self.training:
-            return False
-        mods = [self._layers()[-1].dropout] + ([self.projection.dropout] if self.project_to_input_size else [])
-        return any(isinstance(m, torch.nn.Dropout) and m.p > 0.0 for m in mods)
+    def _projection_dropout_active(self) -> bool:
+        return (self.training and self.project_to_input_size
+                and isinstance(self.projection.dropout, torch.nn.Dropout) and self.projection.dropout.p > 0.0)
+
+    def batch_rows(self, ids: torch.Tensor) -> torch.Tensor:
+        """``single_gat_step()[ids]`` without building all N projected rows or a dense [N, D] gradient: the stack
+        returns only the named rows (its backward scatters their gradients into a persistent zero table) and the
+        projection head — a row-wise map — runs on those rows.  Same values as the reference's order of operations
+        (model.py:135-137); with an active PROJECTION dropout the mask would be drawn per gathered row instead of per
+        node, so that case projects all rows first like the reference."""
+        if self._projection_dropout_active():
+            return self.single_gat_step()[ids]
+        rows = self._stack_output(gather_ids=ids)
+        return self.projection(rows) if self.project_to_input_size else rows
 
     def forward(self, src_ids: torch.Tensor, rel_ids: torch.Tensor, dst_ids: torch.Tensor,
-                transform_to_input_if_possible: bool = True
+                transform_to_input_if_possible: bool = True, transform_rows: Optional[int] = None
                 ) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
         """Scores for a batch of triples (reference model.py:99-142): returns
-        (scores [B], transformed [B, D_sc] or None, dst_vec [B, D_sc])."""
+        (scores [B], transformed [B, D_sc] or None, dst_vec [B, D_sc]).  ``transform_rows`` (extension): compute
+        ``transformed`` for the first that many triples only (the trainer uses the positives)."""
         want_tr = self.project_to_input_size and transform_to_input_if_possible
-        if self.project_to_input_size and self.project_batch_rows_only and not self._dropout_active():
-            # the projection head works row by row and the scorer reads only x[src_ids], x[dst_ids]: project those
-            # 2·B' rows instead of all N (same values for those rows; SURVEY.md 8(f)-1).  With an active dropout the
-            # random mask would be drawn for another shape, so that case keeps the reference's order of operations.
-            b = int(src_ids.numel())
-            rows = RF.GatherRowsFunction.apply(self._stack_output(), torch.cat([src_ids, dst_ids]))
-            y = self.projection(rows)
-            src_vec, dst_vec = y[:b], y[b:]
-            scores = self.scorer(src_vec, rel_ids, dst_vec)
-            transformed = self.scorer.transform(src_vec, rel_ids) if want_tr else None
-            return scores, transformed, dst_vec
-        x = self.single_gat_step()
-        scores, transformed, dst_vec = self.scorer.gather_score(
-            x, src_ids, rel_ids, dst_ids, n_transform=int(src_ids.numel()) if want_tr else 0, want_dst_vec=True)
+        b = int(src_ids.numel())
+        rows = self.batch_rows(torch.cat([src_ids, dst_ids]))
+        src_vec, dst_vec = rows[:b], rows[b:]
+        n_tr = (b if transform_rows is None else min(int(transform_rows), b)) if want_tr else 0
+        scores, transformed = self.scorer.score_and_transform(src_vec, rel_ids, dst_vec, n_tr)
         return scores, (transformed if want_tr else None), dst_vec
 
     @torch.no_grad()

@@ -151,16 +151,100 @@ def pick_splits_k(M: int, N: int, K: int, device) -> int:
     return best
 
 
+
+# ------------------------------------------------------------------------------------------
+# dropout masks (keep bits: element i -> word i >> 5, bit i & 31)
+# ------------------------------------------------------------------------------------------
+class DropMask:
+    """Keep-bit mask of one dropout site plus the 1/(1-p) scale of the kept elements.
+
+    Feature masks: ``bits`` int32 [rows, words] with words = ceil(C / 32) (bit = column inside the row);
+    attention masks: ``bits`` int32 [ceil(E*H / 32)] (bit index = csr slot * H + head)."""
+
+    def __init__(self, bits: torch.Tensor, scale: float):
+        _lib.require_cuda(bits)
+        if bits.dtype != torch.int32 or not bits.is_contiguous():
+            raise TypeError("DropMask bits must be a contiguous int32 tensor")
+        self.bits, self.scale = bits, float(scale)
+
+    @staticmethod
+    def draw(shape, p: float, device, seed: Optional[int] = None) -> "DropMask":
+        """Bernoulli(1-p) keep bits from Philox4x32-10; the seed is drawn from torch's default (CPU) generator, so
+        ``torch.manual_seed`` governs the masks and no device sync is needed."""
+        if not 0.0 <= p < 1.0:
+            raise ValueError(f"dropout probability has to be in [0, 1), got {p}")
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        bits = torch.empty(shape, dtype=torch.int32, device=device)
+        with torch.cuda.device(bits.device):
+            rc = _lib.load().relgat_bernoulli_bits(_lib.ptr(bits), bits.numel(), float(p), seed, _stream(bits))
+        _lib.check(rc, "relgat_bernoulli_bits")
+        _count(1)
+        return DropMask(bits, 1.0 / (1.0 - p))
+
+    @staticmethod
+    def feature_mask(keep: torch.Tensor, p: float) -> "DropMask":
+        """Packs a boolean keep tensor [rows, C] (tests inject masks this way and replay them in the oracle)."""
+        return DropMask(_pack_bits(keep.to(torch.bool), per_row=True), 1.0 / (1.0 - p))
+
+    @staticmethod
+    def edge_mask(keep: torch.Tensor, p: float) -> "DropMask":
+        """Packs a boolean keep tensor [E, H] in CSR slot order."""
+        return DropMask(_pack_bits(keep.to(torch.bool).reshape(1, -1), per_row=True).reshape(-1), 1.0 / (1.0 - p))
+
+
+def _pack_bits(keep: torch.Tensor, per_row: bool) -> torch.Tensor:
+    rows, cols = keep.shape
+    words = (cols + 31) // 32
+    pad = torch.zeros((rows, words * 32), dtype=torch.int64, device=keep.device)
+    pad[:, :cols] = keep.to(torch.int64)
+    w = (pad.view(rows, words, 32) << torch.arange(32, device=keep.device, dtype=torch.int64)).sum(-1)
+    w = torch.where(w >= 2 ** 31, w - 2 ** 32, w)  # two's complement into int32
+    return w.to(torch.int32).contiguous()
+
+
+def _feat_mask_args(m: Optional[DropMask], rows: int, C: int):
+    if m is None:
+        return None, 0, 1.0
+    if m.bits.dim() != 2 or m.bits.size(0) != rows or m.bits.size(1) * 32 < C:
+        raise ValueError(f"feature dropout mask must be int32 [{rows}, >= {(C + 31) // 32}], got {tuple(m.bits.shape)}")
+    return _lib.ptr(m.bits), int(m.bits.size(1)), m.scale
+
+
+def _edge_mask_args(m: Optional[DropMask], E: int, H: int):
+    if m is None:
+        return None, 1.0
+    if m.bits.numel() * 32 < E * H:
+        raise ValueError(f"attention dropout mask needs >= {(E * H + 31) // 32} words, got {m.bits.numel()}")
+    return _lib.ptr(m.bits), m.scale
+
+
+def zero_rows(table: torch.Tensor, ids: torch.Tensor) -> None:
+    """table[ids, :] = 0 (fp32 rows; ids int64, may repeat)."""
+    _lib.require_cuda(table, ids)
+    if table.dtype != torch.float32 or table.dim() != 2 or table.stride(1) != 1 or ids.dtype != torch.int64:
+        raise TypeError("zero_rows: table must be a 2-D float32 tensor with unit inner stride, ids int64")
+    if ids.numel() == 0:
+        return
+    with torch.cuda.device(table.device):
+        rc = _lib.load().relgat_zero_rows(_lib.ptr(table), table.stride(0), _lib.ptr(ids.contiguous()), ids.numel(),
+                                          table.size(1), _stream(table))
+    _lib.check(rc, "relgat_zero_rows")
+    _count(1)
+
 # ------------------------------------------------------------------------------------------
 # edge kernels
 # ------------------------------------------------------------------------------------------
 def edge_fwd(P: torch.Tensor, A: torch.Tensor, beta: Optional[torch.Tensor], g: GraphIndex, H: int, F: int,
              want_act: bool = False, apply_elu: bool = False, act_lo: bool = True, want_out: bool = True,
              want_alpha: bool = False, z_out: Optional[torch.Tensor] = None,
-             minv_out: Optional[torch.Tensor] = None, out_buf: Optional[torch.Tensor] = None):
+             minv_out: Optional[torch.Tensor] = None, out_buf: Optional[torch.Tensor] = None,
+             feat_drop: Optional["DropMask"] = None, edge_drop: Optional["DropMask"] = None):
     """Returns (out [N, H*F] fp32 or None, act planes or None, alpha [E,H] or None, z [E,H],
     minv [N,H,2], bias [N]).  ``z_out`` / ``minv_out`` / ``out_buf``: caller-owned buffers for the saved
-    statistics and the output rows (rows of a peer table on the partitioned path)."""
+    statistics and the output rows (rows of a peer table on the partitioned path).
+    ``feat_drop`` / ``edge_drop``: keep-bit masks of the feature dropout (reference layer.py:321-322; ``out`` then
+    holds the POST-dropout rows) and of the attention dropout (layer.py:296-297)."""
     P = _feat(P, "P")
     A = _f32c(A, "A")
     if beta is not None:
@@ -190,7 +274,8 @@ def edge_fwd(P: torch.Tensor, A: torch.Tensor, beta: Optional[torch.Tensor], g: 
             _lib.ptr(ck.long_node), _lib.ptr(ck.long_part_ptr), ck.n_long,
             _lib.ptr(part_ml), _lib.ptr(part_b), _lib.ptr(part_acc),
             _lib.ptr(out), _lib.ptr(hi), _lib.ptr(lo), int(apply_elu),
-            _lib.ptr(alpha), _lib.ptr(z), _lib.ptr(minv), _lib.ptr(bias), H, F, R, sm_count(dev),
+            _lib.ptr(alpha), _lib.ptr(z), _lib.ptr(minv), _lib.ptr(bias),
+            *_feat_mask_args(feat_drop, N, C), *_edge_mask_args(edge_drop, E, H), H, F, R, sm_count(dev),
             _lib.ptr(_work_counter(dev)), _stream(P))
     _lib.check(rc, "relgat_layer_fwd")
     _count(2 if ck.n_long else 1)
@@ -200,7 +285,8 @@ def edge_fwd(P: torch.Tensor, A: torch.Tensor, beta: Optional[torch.Tensor], g: 
 def edge_bwd_prep(dY: torch.Tensor, out: torch.Tensor, bias: torch.Tensor, H: int, F: int,
                   apply_elu: bool, inplace: bool = False, g_bf16: bool = False,
                   G_out: Optional[torch.Tensor] = None, t_out: Optional[torch.Tensor] = None,
-                  hsum_out: Optional[torch.Tensor] = None, nonzero_rows: Optional[torch.Tensor] = None):
+                  hsum_out: Optional[torch.Tensor] = None, nonzero_rows: Optional[torch.Tensor] = None,
+                  feat_drop: Optional["DropMask"] = None):
     """Returns (G [N,C] fp32 or bf16, t [N,H], hsum [N,H]).  ``G_out`` / ``t_out`` / ``hsum_out``:
     caller-owned fp32 buffers (rows of a peer table on the partitioned path).  ``nonzero_rows`` (int64, may
     repeat): all other rows of dY are known to be zero; used only when G can alias dY (fp32, no activation)."""
@@ -214,7 +300,7 @@ def edge_bwd_prep(dY: torch.Tensor, out: torch.Tensor, bias: torch.Tensor, H: in
         G = torch.empty(dY.shape, dtype=torch.bfloat16, device=dY.device)
     else:
         # without an activation G == dY: nothing to write, alias it (saves a full [N, C] copy)
-        G = dY if (inplace or not apply_elu) else torch.empty_like(dY)
+        G = dY if (inplace or not (apply_elu or feat_drop is not None)) else torch.empty_like(dY)
     t = _out_buf(t_out, (N, H), dY.device, "t_out")
     hsum = _out_buf(hsum_out, (N, H), dY.device, "hsum_out")
     rows = None
@@ -223,14 +309,15 @@ def edge_bwd_prep(dY: torch.Tensor, out: torch.Tensor, bias: torch.Tensor, H: in
     with torch.cuda.device(dY.device):
         rc = _lib.load().relgat_layer_bwd_prep(_lib.ptr(dY), _lib.ptr(out), _lib.ptr(bias), _lib.ptr(G), int(g_bf16),
                                                _lib.ptr(t), _lib.ptr(hsum), N, H, F, int(apply_elu),
-                                               _lib.ptr(rows), 0 if rows is None else int(rows.numel()), _stream(dY))
+                                               _lib.ptr(rows), 0 if rows is None else int(rows.numel()),
+                                               *_feat_mask_args(feat_drop, N, H * F), _stream(dY))
     _lib.check(rc, "relgat_layer_bwd_prep")
     _count(1)
     return G, t, hsum
 
 
 def edge_bwd_src(P, G, A, z, minv, t, g: GraphIndex, H: int, F: int, want_fp32: bool = True,
-                 want_planes: bool = False, planes_lo: bool = True):
+                 want_planes: bool = False, planes_lo: bool = True, edge_drop: Optional["DropMask"] = None):
     """Returns (dP fp32 or None, dP planes or None, dz [E,H])."""
     P = _feat(P, "P")
     G = _feat(G, "G")
@@ -253,8 +340,8 @@ def edge_bwd_src(P, G, A, z, minv, t, g: GraphIndex, H: int, F: int, want_fp32: 
             _lib.ptr(minv), _lib.ptr(t), _lib.ptr(g.colptr), _lib.ptr(g.csc_slot), _lib.ptr(g.csc_dst), _lib.ptr(g.csc_rel),
             _lib.ptr(ck.chunks), ck.n_chunks, _lib.ptr(ck.parts), ck.n_parts,
             _lib.ptr(ck.long_node), _lib.ptr(ck.long_part_ptr), ck.n_long, _lib.ptr(part_acc),
-            _lib.ptr(dP), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dz), H, F, g.R, sm_count(dev),
-            _lib.ptr(_work_counter(dev)), _stream(P))
+            _lib.ptr(dP), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dz), *_edge_mask_args(edge_drop, g.E, H),
+            H, F, g.R, sm_count(dev), _lib.ptr(_work_counter(dev)), _stream(P))
     _lib.check(rc, "relgat_layer_bwd_src")
     _count(2 if ck.n_long else 1)
     return dP, ((hi, lo) if want_planes else None), dz
@@ -292,11 +379,37 @@ def _ids(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
     return t.contiguous()
 
 
+CHECK_ID_RANGES = bool(int(os.environ.get("RELGAT_CHECK_IDS", "0")))  # debug: range-check ids (one device sync)
+
+
+def _check_score_args(xs, src_idx, xd, dst_idx, rel_emb, rel_ids, n_transform=0):
+    """Shape errors the reference would raise from torch (scorer.py:80-83, 176-186): every operand is [*, D] with
+    D = rel_emb.size(1), un-indexed operands carry one row per triple, index vectors one entry per triple."""
+    if rel_emb.dim() != 2 or xs.dim() != 2 or xd.dim() != 2:
+        raise ValueError("scorer operands must be 2-D: xs/xd [*, D], rel_emb [R, D]")
+    B, D = int(rel_ids.numel()), int(rel_emb.size(1))
+    if xs.size(1) != D or xd.size(1) != D:
+        raise ValueError(f"scorer width mismatch: xs [*, {xs.size(1)}], xd [*, {xd.size(1)}] vs rel_emb [*, {D}]")
+    for nm, idx, x in (("src", src_idx, xs), ("dst", dst_idx, xd)):
+        if idx is None:
+            if x.size(0) < B:
+                raise ValueError(f"{nm} rows: {x.size(0)} < {B} triples")
+        elif idx.dim() != 1 or idx.numel() != B:
+            raise ValueError(f"{nm}_idx must have one entry per triple ({B}), got {tuple(idx.shape)}")
+    if not 0 <= n_transform <= B:
+        raise ValueError(f"n_transform must be in [0, {B}]")
+    if CHECK_ID_RANGES and B:
+        for nm, idx, hi in (("src_idx", src_idx, xs.size(0)), ("dst_idx", dst_idx, xd.size(0)), ("rel_ids", rel_ids, rel_emb.size(0))):
+            if idx is not None and (int(idx.min()) < 0 or int(idx.max()) >= hi):
+                raise IndexError(f"{nm} out of range [0, {hi})")
+    return B, D
+
+
 def score_fwd(kind: str, normalize: bool, xs, src_idx, xd, dst_idx, rel_emb, rel_ids, *,
               n_transform: int = 0, want_src_vec: bool = False, want_dst_vec: bool = False):
     xs, xd, rel_emb = _f32c(xs, "xs"), _f32c(xd, "xd"), _f32c(rel_emb, "rel_emb")
     src_idx, dst_idx, rel_ids = _ids(src_idx, "src_idx"), _ids(dst_idx, "dst_idx"), _ids(rel_ids, "rel_ids")
-    B, D = int(rel_ids.numel()), int(rel_emb.size(1))
+    B, D = _check_score_args(xs, src_idx, xd, dst_idx, rel_emb, rel_ids, n_transform)
     dev = xs.device
     score = torch.empty((B,), dtype=torch.float32, device=dev)
     tr = torch.empty((n_transform, D), dtype=torch.float32, device=dev) if n_transform > 0 else None
@@ -315,14 +428,19 @@ def score_fwd(kind: str, normalize: bool, xs, src_idx, xd, dst_idx, rel_emb, rel
 def score_bwd(kind: str, normalize: bool, xs, src_idx, xd, dst_idx, rel_emb, rel_ids, dscore, dtransform, *,
               want_src: bool = True, want_dst: bool = True, want_rel: bool = True):
     xs, xd, rel_emb = _f32c(xs, "xs"), _f32c(xd, "xd"), _f32c(rel_emb, "rel_emb")
-    B, D = int(rel_ids.numel()), int(rel_emb.size(1))
+    src_idx, dst_idx, rel_ids = _ids(src_idx, "src_idx"), _ids(dst_idx, "dst_idx"), _ids(rel_ids, "rel_ids")
+    B, D = _check_score_args(xs, src_idx, xd, dst_idx, rel_emb, rel_ids)
     dev = xs.device
     if dscore is not None:
         dscore = _f32c(dscore, "dscore")
+        if dscore.numel() != B:
+            raise ValueError(f"dscore must have {B} entries, got {tuple(dscore.shape)}")
     n_tr = 0
     if dtransform is not None:
         dtransform = _f32c(dtransform, "dtransform")
         n_tr = int(dtransform.size(0))
+        if dtransform.dim() != 2 or dtransform.size(1) != D or n_tr > B:
+            raise ValueError(f"dtransform must be [<= {B}, {D}], got {tuple(dtransform.shape)}")
     mk = lambda w: torch.empty((B, D), dtype=torch.float32, device=dev) if w else None  # noqa: E731
     d_src, d_dst, d_rel = mk(want_src), mk(want_dst), mk(want_rel)
     with torch.cuda.device(dev):
@@ -336,12 +454,13 @@ def score_bwd(kind: str, normalize: bool, xs, src_idx, xd, dst_idx, rel_emb, rel
 
 
 def index_add_sorted(rows: torch.Tensor, keys: torch.Tensor, n_out: int, out: Optional[torch.Tensor] = None,
-                     presorted=None, return_keys: bool = False):
+                     presorted=None, return_keys: bool = False, accumulate: Optional[bool] = None):
     """out[k] (+)= ordered sum of rows whose key == k.  ``keys`` int64 [M]; rows [M, D].
     ``presorted`` = (sorted_keys, perm) of a stable sort of ``keys`` when the caller cached it."""
     rows = _f32c(rows, "rows")
     M, D = rows.shape
-    accumulate = out is not None
+    if accumulate is None:  # with accumulate=False only the rows named by ``keys`` are written (to the run sums)
+        accumulate = out is not None
     if out is None:
         out = torch.zeros((n_out, D), dtype=torch.float32, device=rows.device)
     if M == 0:
@@ -369,6 +488,77 @@ def margin_loss(score: torch.Tensor, B: int, K: int, margin: float, projection_l
     _lib.check(rc, "relgat_margin_loss")
     _count(1)
     return loss, dscore
+
+
+RANK_LOSS_KIND = {"margin": 0, "self_adversarial_loss": 1}
+
+
+def rank_loss(pos: torch.Tensor, neg: torch.Tensor, kind: str, margin: float = 1.0, alpha: float = 1.0,
+              sanitize: bool = False):
+    """Ranking loss of reference core/loss/relgat_loss.py:32-71 on pos [B] and neg [B, K] (any strides: the two
+    negative layouts of the reference trainer are views of the flat score vector).  Returns (loss [1], dpos [B],
+    dneg with neg's strides).  ``sanitize``: nan_to_num(nan=0, +-inf=+-1e9) as in trainer:584, 647-648."""
+    _lib.require_cuda(pos, neg)
+    if pos.dtype != torch.float32 or neg.dtype != torch.float32:
+        raise TypeError("rank_loss: scores must be float32")
+    if pos.dim() != 1 or neg.dim() != 2 or neg.size(0) != pos.size(0):
+        raise ValueError(f"rank_loss: pos [B] and neg [B, K] expected, got {tuple(pos.shape)} / {tuple(neg.shape)}")
+    if kind not in RANK_LOSS_KIND:
+        raise ValueError(f"unknown ranking loss {kind!r}")
+    B, K = int(neg.size(0)), int(neg.size(1))
+    pos = pos.contiguous()
+    dneg = torch.empty_like(neg)  # keeps the strides of a dense view
+    if dneg.stride() != neg.stride():
+        neg = neg.contiguous()
+        dneg = torch.empty_like(neg)
+    loss = torch.empty((1,), dtype=torch.float32, device=pos.device)
+    dpos = torch.empty_like(pos)
+    with torch.cuda.device(pos.device):
+        rc = _lib.load().relgat_rank_loss(_lib.ptr(pos), _lib.ptr(neg), B, K, neg.stride(0) if K else 0,
+                                          neg.stride(1) if K else 0, RANK_LOSS_KIND[kind], float(margin), float(alpha),
+                                          int(sanitize), _lib.ptr(loss), _lib.ptr(dpos), _lib.ptr(dneg), _stream(pos))
+    _lib.check(rc, "relgat_rank_loss")
+    _count(1)
+    return loss, dpos, dneg
+
+
+def recon_loss(tr: torch.Tensor, dst: torch.Tensor, negdst: Optional[torch.Tensor], w_pos: float, w_neg: float,
+               w_mse: float):
+    """Reconstruction terms of reference core/loss/multi_objective_loss.py:47-83 (cosine.py:4-13, mse.py:4-10):
+    tr = f_r(A) [B, D], dst [B, D], negdst [K, B, D] (any outer strides, unit inner stride; None = no negatives).
+    Returns (values [3] = (cos_pos, cos_neg, mse) losses, d_tr, d_dst, d_negdst) where the gradients are those of
+    w_pos*cos_pos + w_neg*(1 - cos_neg) + w_mse*mse."""
+    _lib.require_cuda(tr, dst)
+    tr, dst = _f32c(tr, "transformed_src"), _f32c(dst, "dst_vec")
+    if tr.dim() != 2 or tr.shape != dst.shape:
+        raise ValueError(f"recon_loss: transformed_src and dst_vec must both be [B, D], got {tuple(tr.shape)} / {tuple(dst.shape)}")
+    B, D = tr.shape
+    K, sb, sk = 0, 0, 0
+    d_neg = None
+    if negdst is not None and negdst.numel() > 0:
+        _lib.require_cuda(negdst)
+        if negdst.dim() != 3 or negdst.size(1) != B or negdst.size(2) != D or negdst.dtype != torch.float32:
+            raise ValueError(f"recon_loss: neg_dst_vec must be float32 [K, {B}, {D}], got {tuple(negdst.shape)}")
+        if negdst.stride(2) != 1:
+            negdst = negdst.contiguous()
+        d_neg = torch.empty_like(negdst)
+        if d_neg.stride() != negdst.stride():
+            negdst = negdst.contiguous()
+            d_neg = torch.empty_like(negdst)
+        K, sk, sb = int(negdst.size(0)), negdst.stride(0), negdst.stride(1)
+    else:
+        negdst = None
+    dev = tr.device
+    values = torch.empty((3,), dtype=torch.float32, device=dev)
+    partial = torch.empty((max(B, 1), 3), dtype=torch.float32, device=dev)
+    d_tr, d_dst = torch.empty_like(tr), torch.empty_like(dst)
+    with torch.cuda.device(dev):
+        rc = _lib.load().relgat_recon_loss(_lib.ptr(tr), _lib.ptr(dst), _lib.ptr(negdst), B, K, D, sb, sk, float(w_pos),
+                                           float(w_neg), float(w_mse), _lib.ptr(values), _lib.ptr(partial), _lib.ptr(d_tr),
+                                           _lib.ptr(d_dst), _lib.ptr(d_neg), _stream(tr))
+    _lib.check(rc, "relgat_recon_loss")
+    _count(2)
+    return values, d_tr, d_dst, d_neg
 
 
 def pull_rows(table: torch.Tensor, ids: torch.Tensor, out: torch.Tensor, out_ids: Optional[torch.Tensor] = None) -> torch.Tensor:

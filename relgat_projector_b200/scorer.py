@@ -32,6 +32,12 @@ class _ScorerBase(nn.Module):
                                            rel_ids, False, True)
         return tr
 
+    def score_and_transform(self, src_emb: torch.Tensor, rel_ids: torch.Tensor, dst_emb: torch.Tensor,
+                            n_transform: int = 0):
+        """forward() and transform() of the first ``n_transform`` triples in ONE kernel launch."""
+        return RF.ScoreRowsFunction.apply(self.kind, self._normalize, src_emb, dst_emb, self.rel_emb.weight, rel_ids,
+                                          True, int(n_transform))
+
     def gather_score(self, x: torch.Tensor, src_ids, rel_ids, dst_ids, n_transform: int = 0,
                      want_dst_vec: bool = False):
         """Fused x[src_ids], x[dst_ids] gather + score (+ transform of the first n_transform triples,

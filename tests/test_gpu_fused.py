@@ -1,0 +1,363 @@
+"""GPU parity tests of the round-2 additions: fused ranking / reconstruction loss kernels, dropout inside the edge
+kernels (injected masks replayed in the oracle), the stack + batch-row gather node (no dense [N, C] gradient), and
+parity at the sizes of BASELINE.json's configs (c1 in full against the oracle port; c2 through sampled destination
+rows and the parameter gradients they induce)."""
+import numpy as np
+import pytest
+import torch
+
+import relgat_projector_b200 as R
+from oracle import relgat_oracle as O
+from relgat_projector_b200 import functional as RF, loss as L, ops, synthetic as S
+from relgat_projector_b200.graph import GraphIndex
+from tests.helpers import Case, MODEL_CASES, rel_err
+
+pytestmark = pytest.mark.gpu
+FP32_TOL = 1e-4  # north_star tolerance (fp32): logits / embeddings / losses / gradients
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _load_model(c: Case, dev):
+    m = R.RelGATModel(
+        node_emb=c.t("x0").float().to(dev), edge_index=c.edge_index().to(dev), edge_type=c.t("rel").to(dev),
+        num_rel=c.r, scorer_type=c.scorer, gat_out_dim=c.f, gat_heads=c.h, dropout=0.0, relation_attn_dropout=0.0,
+        gat_num_layers=c.layers, project_to_input_size=c.projection, projection_layers=c.proj_layers,
+        projection_dropout=0.0, projection_hidden_dim=0).to(dev)
+    state = {k[len("param/"):]: torch.from_numpy(c.z[k]).float() for k in c.z.files if k.startswith("param/")}
+    state["node_emb_fixed"] = c.t("x0").float()
+    m.load_state_dict(state, strict=True)
+    return m.train()
+
+
+# ------------------------------------------------------------------------------------------------------
+# the trainer-level fused path against the reference's golden outputs
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", MODEL_CASES)
+def test_fused_calculate_loss_matches_reference_golden(dev, name):
+    """loss.calculate_loss = stack + row gather -> [projection of the batch rows] -> one score launch -> fused loss
+    kernels, checked against the values and parameter gradients the UNMODIFIED reference produced (tests/golden)."""
+    c = Case(name)
+    m = _load_model(c, dev)
+    rank = L.RelGATLoss("self_adversarial_loss" if c.loss_type == "self_adv" else "margin", 0.7, 1.0, None, {})
+    multi = L.MultiObjectiveRelLoss(relgat_loss=rank, run_config={}, relgat_weight=c.weights[0],
+                                    pos_cosine_weight=c.weights[1], neg_cosine_weight=c.weights[2],
+                                    mse_weight=c.weights[3]) if c.projection else None
+    ids = [c.t(k).to(dev) for k in ("src_ids", "rel_ids", "dst_ids")]
+    pos, neg, loss, mse, cpos, cneg = L.calculate_loss(m, *ids, c.b, rank, multi)
+    assert rel_err(pos.detach().cpu().numpy(), c.z["pos"]) < FP32_TOL
+    assert rel_err(neg.detach().cpu().numpy(), c.z["neg"]) < FP32_TOL
+    assert abs(float(loss.detach()) - float(c.z["loss"])) < FP32_TOL * max(1.0, abs(float(c.z["loss"])))
+    loss.backward()
+    for pname, p in m.named_parameters():
+        ref = c.z["grad/" + pname]
+        assert p.grad is not None, pname
+        tol = 5 * FP32_TOL if ref.size and np.abs(ref).max() < 1e-6 else FP32_TOL
+        assert rel_err(p.grad.cpu().numpy(), ref) < tol, pname
+    if c.projection:
+        assert all(torch.isfinite(v) for v in (mse, cpos, cneg))
+    # the zero table the backward borrowed is all-zero again
+    for pool in RF._ZERO_TABLES.values():
+        for t in pool:
+            assert not bool(t.any())
+
+
+# ------------------------------------------------------------------------------------------------------
+# loss kernels
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["margin", "self_adversarial_loss"])
+@pytest.mark.parametrize("layout", ["kmajor", "projection"])
+def test_rank_loss_kernel_vs_oracle(dev, kind, layout):
+    g = torch.Generator().manual_seed(3)
+    b, k = 37, 5
+    flat = (torch.randn(b * (1 + k), generator=g) * 3).float()
+    flat[5], flat[b + 7], flat[b + 11] = float("nan"), float("inf"), float("-inf")
+    ref_in = flat.double().clone().requires_grad_(True)
+    clean = torch.nan_to_num(ref_in, nan=0.0, neginf=-1e9, posinf=1e9)
+    rp, rn = (O.split_scores_kmajor if layout == "kmajor" else O.split_scores_projection_path)(clean, b, k)
+    ref = O.margin_ranking_loss_port(rp, rn, 0.8) if kind == "margin" else O.self_adversarial_loss_port(rp, rn, 0.6)
+    ref.backward()
+    x = flat.to(dev).requires_grad_(True)
+    pos = x[:b]
+    neg = x[b:].view(k, b).t() if layout == "kmajor" else x[b:].view(b, k)  # strided views, no copies
+    rl = L.RelGATLoss(kind, 0.6, 0.8, None, {})
+    loss = rl.prepare_scores_and_compute_loss(pos, neg, sanitize=True)
+    loss.backward()
+    assert abs(float(loss) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+    assert rel_err(x.grad.cpu().numpy(), ref_in.grad.numpy()) < 1e-5
+    # bitwise reproducible
+    loss2 = rl.prepare_scores_and_compute_loss(pos.detach(), neg.detach(), sanitize=True)
+    assert torch.equal(loss.detach(), loss2)
+    # finite scores: same value without the sanitising flag
+    fin = torch.nan_to_num(flat, nan=0.0, neginf=-5.0, posinf=5.0).to(dev)
+    a = rl.prepare_scores_and_compute_loss(fin[:b], fin[b:].view(b, k))
+    bb = rl.prepare_scores_and_compute_loss(fin[:b], fin[b:].view(b, k), sanitize=True)
+    assert torch.equal(a, bb)
+
+
+@pytest.mark.parametrize("weights", [(1.0, 1.0, 0.0), (0.5, 2.0, 0.3), (0.0, 1.0, 1.0)])
+def test_recon_loss_kernel_vs_oracle(dev, weights):
+    g = torch.Generator().manual_seed(5)
+    b, k, d = 19, 4, 72
+    tr = torch.randn(b, d, generator=g)
+    dst = torch.randn(b, d, generator=g)
+    flat_nd = torch.randn(b * k, d, generator=g)  # the trainer's flat negative rows; (b, k) = row b*k + k
+    tr[3] = 0.0  # F.normalize eps branch
+    rt, rd, rn = (t.double().clone().requires_grad_(True) for t in (tr, dst, flat_nd))
+    ndv = rn.view(b, k, d).permute(1, 0, 2).contiguous()
+    w_pos, w_neg, w_mse = weights
+    parts = []
+    if w_pos:
+        parts.append(w_pos * O.cosine_loss_port(rt, rd))
+    if w_neg:
+        parts.append(w_neg * (1.0 - O.cosine_loss_port(rt, ndv)))
+    if w_mse:
+        parts.append(w_mse * torch.nn.functional.mse_loss(rt, rd))
+    ref = torch.stack(parts).sum()
+    ref.backward()
+    xt, xd, xn = (t.to(dev).requires_grad_(True) for t in (tr, dst, flat_nd))
+    view = xn.view(b, k, d).permute(1, 0, 2)  # [K, B, D] strided view: no copy
+    total, values = RF.fused_recon_loss(xt, xd, view, w_pos, w_neg, w_mse)
+    total.backward()
+    assert abs(float(total) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+    with torch.no_grad():
+        want = [float(O.cosine_loss_port(rt, rd)), float(O.cosine_loss_port(rt, ndv)),
+                float(torch.nn.functional.mse_loss(rt, rd))]
+    assert np.allclose(values.cpu().numpy(), want, rtol=1e-5, atol=1e-6)
+    for got, exp in ((xt.grad, rt.grad), (xd.grad, rd.grad), (xn.grad, rn.grad)):
+        if exp is None:
+            assert got is None or not bool(got.any())
+            continue
+        assert rel_err(got.cpu().numpy(), exp.numpy()) < 1e-5
+    # MultiObjectiveRelLoss class, CUDA inputs -> the same kernels
+    rank = L.RelGATLoss("margin", None, 1.0, None, {})
+    multi = L.MultiObjectiveRelLoss(relgat_loss=rank, run_config={}, relgat_weight=1.0, pos_cosine_weight=w_pos,
+                                    neg_cosine_weight=w_neg, mse_weight=w_mse)
+    pos = torch.randn(b, generator=g)
+    neg = torch.randn(b, k, generator=g)
+    got = multi(pos_score=pos.to(dev), neg_score=neg.to(dev), transformed_src=tr.to(dev), dst_vec=dst.to(dev),
+                neg_dst_vec=flat_nd.view(b, k, d).permute(1, 0, 2).contiguous().to(dev))
+    exp = O.multi_objective_loss_port(pos.double(), neg.double(), tr.double(), dst.double(), ndv.detach(),
+                                      ranking_loss=lambda p, n: O.margin_ranking_loss_port(p, n, 1.0),
+                                      w_rank=1.0, w_pos=w_pos, w_neg=w_neg, w_mse=w_mse)
+    assert abs(float(got) - float(exp)) < 1e-5 * max(1.0, abs(float(exp)))
+
+
+def test_scorer_shape_errors_raise(dev):
+    """A wrong-width operand must raise like torch would in the reference (scorer.py:80-83), not read out of bounds."""
+    sc = R.DistMultScorer(5, 16).to(dev)
+    rel = torch.zeros(4, dtype=torch.long, device=dev)
+    with pytest.raises(ValueError):
+        sc(torch.randn(4, 24, device=dev), rel, torch.randn(4, 24, device=dev))
+    with pytest.raises(ValueError):
+        sc(torch.randn(3, 16, device=dev), rel, torch.randn(4, 16, device=dev))
+    with pytest.raises(ValueError):
+        sc.gather_score(torch.randn(9, 16, device=dev), rel[:3], rel, rel)
+    assert sc(torch.randn(4, 16, device=dev), rel, torch.randn(4, 16, device=dev)).shape == (4,)
+
+
+# ------------------------------------------------------------------------------------------------------
+# dropout inside the edge kernels
+# ------------------------------------------------------------------------------------------------------
+def test_bernoulli_bits_rate_and_seeding(dev):
+    p = 0.3
+    m = ops.DropMask.draw((4096, 25), p, dev, seed=1234)
+    ones = sum(int(((m.bits >> s) & 1).sum()) for s in range(32))
+    rate = ones / (4096 * 25 * 32)
+    assert abs(rate - (1 - p)) < 2e-3 and m.scale == pytest.approx(1 / (1 - p))
+    assert torch.equal(m.bits, ops.DropMask.draw((4096, 25), p, dev, seed=1234).bits)
+    assert not torch.equal(m.bits, ops.DropMask.draw((4096, 25), p, dev, seed=1235).bits)
+    torch.manual_seed(7)
+    a = ops.DropMask.draw((64, 3), p, dev).bits
+    torch.manual_seed(7)
+    assert torch.equal(a, ops.DropMask.draw((64, 3), p, dev).bits)  # torch.manual_seed governs the masks
+    keep = torch.rand(50, 70, device=dev) > 0.5
+    packed = ops.DropMask.feature_mask(keep, 0.5).bits
+    cols = torch.arange(70, device=dev)
+    back = ((packed[:, cols // 32] >> (cols % 32)) & 1).bool()
+    assert torch.equal(back, keep)
+
+
+@pytest.mark.parametrize("sites", ["feature", "attention", "both"])
+def test_dropout_inside_kernels_matches_oracle_with_injected_masks(dev, sites):
+    """Training-mode dropout (reference layer.py:296-297, 321-322; p = 0.3 / 0.2 in its scripts) runs inside the fused
+    stack.  The masks are injected, the oracle port replays them: outputs and every gradient agree at 1e-4."""
+    rng = np.random.default_rng(11)
+    n, e, r, d_in, f, h, L_ = 300, 2400, 6, 48, 24, 4, 2
+    p_feat, p_attn = 0.3, 0.2
+    x0 = torch.from_numpy(rng.standard_normal((n, d_in)).astype(np.float32))
+    ei = torch.from_numpy(np.stack([rng.integers(0, n, e), rng.integers(0, n - 10, e)]).astype(np.int64))
+    et = torch.from_numpy(rng.integers(0, r, e).astype(np.int64))
+    torch.manual_seed(1)
+    layers = [R.RelGATLayer(d_in if l == 0 else h * f, f, r, heads=h, dropout=0.0).to(dev) for l in range(L_)]
+    for lyr in layers:
+        torch.nn.init.normal_(lyr.rel_bias, std=0.1)
+    g = GraphIndex(ei.to(dev), et.to(dev), n, r)
+    perm = g.csr_perm.long().cpu()
+    drops, omasks = [], []
+    for l in range(L_):
+        fk = torch.from_numpy(rng.random((n, h * f)) >= p_feat) if sites in ("feature", "both") else None
+        ak = torch.from_numpy(rng.random((e, h)) >= p_attn) if sites in ("attention", "both") else None  # COO order
+        drops.append(RF.LayerDropout(ops.DropMask.feature_mask(fk.to(dev), p_feat) if fk is not None else None,
+                                     ops.DropMask.edge_mask(ak[perm].to(dev), p_attn) if ak is not None else None))
+        omasks.append(dict(feat_keep=fk, feat_p=p_feat if fk is not None else 0.0,
+                           attn_keep=ak, attn_p=p_attn if ak is not None else 0.0))
+    ids = torch.from_numpy(rng.integers(0, n, 80))
+    gout = torch.from_numpy(rng.standard_normal((80, h * f)).astype(np.float32))
+    rows = RF.relgat_stack(x0.to(dev), g, h, f, [lyr.kernel_params() for lyr in layers], drop=drops,
+                           gather_ids=ids.to(dev))
+    rows.backward(gout.to(dev))
+    ol = [{"W": [p.weight.detach().cpu().double().requires_grad_(True) for p in lyr.proj],
+           "A": [a.detach().cpu().double().requires_grad_(True) for a in lyr.attn_vec],
+           "beta": lyr.rel_bias.detach().cpu().double().requires_grad_(True)} for lyr in layers]
+    ref = O.gat_stack_port(x0.double(), ol, ei, et, masks=omasks)[ids]
+    ref.backward(gout.double())
+    assert rel_err(rows.detach().cpu().numpy(), ref.detach().numpy()) < FP32_TOL
+    for lyr, o in zip(layers, ol):
+        for hh in range(h):
+            assert rel_err(lyr.proj[hh].weight.grad.cpu().numpy(), o["W"][hh].grad.numpy()) < FP32_TOL
+            assert rel_err(lyr.attn_vec[hh].grad.cpu().numpy(), o["A"][hh].grad.numpy()) < FP32_TOL
+        assert rel_err(lyr.rel_bias.grad.cpu().numpy(), o["beta"].grad.numpy()) < FP32_TOL
+
+
+def test_training_with_reference_default_dropout_uses_one_fused_node(dev):
+    c = Case("tiny_fp64")
+    m = R.RelGATModel(node_emb=c.t("x0").float().to(dev), edge_index=c.edge_index().to(dev),
+                      edge_type=c.t("rel").to(dev), num_rel=c.r, gat_out_dim=c.f, gat_heads=c.h, dropout=0.3,
+                      relation_attn_dropout=0.1, gat_num_layers=2).to(dev).train()
+    x = m.single_gat_step()
+    assert type(x.grad_fn).__name__ == "RelGATStackFunctionBackward"  # no per-layer nodes, no ATen dropout
+    frac0 = float((x == 0).float().mean())
+    assert 0.2 < frac0 < 0.45
+    torch.manual_seed(3)
+    a = m.single_gat_step()
+    torch.manual_seed(3)
+    assert torch.equal(a, m.single_gat_step())  # masks follow torch's seed
+    x.sum().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.gat_layers.parameters())
+
+
+# ------------------------------------------------------------------------------------------------------
+# stack + batch-row gather
+# ------------------------------------------------------------------------------------------------------
+def test_stack_gather_equals_dense_stack_then_index(dev):
+    c = Case("f200_fp32")
+    ids = torch.cat([c.t("src_ids"), c.t("dst_ids")]).to(dev)
+    gout = torch.randn(ids.numel(), c.h * c.f, generator=torch.Generator().manual_seed(0)).to(dev)
+    res = []
+    for fused in (True, False):
+        m = _load_model(c, dev)
+        rows = m._stack_output(gather_ids=ids) if fused else m._stack_output()[ids]
+        rows.backward(gout)
+        res.append((rows.detach(), {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}))
+    assert torch.equal(res[0][0], res[1][0])
+    assert res[0][1].keys() == res[1][1].keys()
+    for nme in res[0][1]:  # torch's index backward sums duplicate rows with atomics: order differs, values agree
+        assert rel_err(res[0][1][nme].cpu().numpy(), res[1][1][nme].cpu().numpy()) < 1e-5, nme
+    # a second backward through the released state fails loudly instead of with a TypeError on None
+    m = _load_model(c, dev)
+    rows = m._stack_output(gather_ids=ids)
+    rows.sum().backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="released"):
+        rows.sum().backward()
+
+
+# ------------------------------------------------------------------------------------------------------
+# parity at the sizes of the named configs
+# ------------------------------------------------------------------------------------------------------
+def _oracle_layers(model):
+    return [{"W": [p.weight.detach().cpu().double().requires_grad_(True) for p in lyr.proj],
+             "A": [a.detach().cpu().double().requires_grad_(True) for a in lyr.attn_vec],
+             "beta": lyr.rel_bias.detach().cpu().double().requires_grad_(True)} for lyr in model._layers()]
+
+
+def test_config1_full_size_training_step_vs_oracle(dev):
+    """BASELINE.json configs[0] in full (10 k nodes / 50 k triplets -> 45 k message-passing edges, 1024-d, 2 layers,
+    4 heads x 200, DistMult, B = 256, K = 4): loss, sampled rows of the final embeddings and EVERY parameter gradient
+    against the oracle port of the reference's op sequence (fp64 on the CPU), 1e-4 relative."""
+    cfg = S.CONFIGS["c1"]
+    kg = S.tensor_kg(cfg["N"], cfg["T"], cfg["R"], cfg["D_in"], seed=42, device="cpu")
+    torch.manual_seed(42)
+    m = R.RelGATModel(kg.node_emb.to(dev), kg.edge_index.to(dev), kg.edge_type.to(dev), num_rel=cfg["R"],
+                      scorer_type="distmult", gat_out_dim=cfg["F"], gat_heads=cfg["H"], dropout=0.0,
+                      gat_num_layers=cfg["L"]).to(dev).train()
+    with torch.no_grad():
+        for lyr in m._layers():
+            torch.nn.init.normal_(lyr.rel_bias, std=0.05)  # the reference initialises it to zero: make the term count
+    b, k = cfg["B"], cfg["K"]
+    src, rel, dst = S.sample_batch(kg.train_triples, cfg["N"], b, k, torch.Generator().manual_seed(1))
+    rank = L.RelGATLoss("margin", None, 1.0, None, {})
+    pos, neg, loss, *_ = L.calculate_loss(m, src.to(dev), rel.to(dev), dst.to(dev), b, rank)
+    loss.backward()
+    with torch.no_grad():
+        xf = m.eval().single_gat_step()
+    layers = _oracle_layers(m)
+    rel_emb = m.scorer.rel_emb.weight.detach().cpu().double().requires_grad_(True)
+    ref_loss, rpos, rneg = O.train_step_port(kg.node_emb.double(), layers, rel_emb, kg.edge_index, kg.edge_type, src,
+                                             rel, dst, scorer="distmult", b=b, k=k, margin=1.0)
+    ref_loss.backward()
+    with torch.no_grad():
+        ref_x = O.gat_stack_port(kg.node_emb.double(), layers, kg.edge_index, kg.edge_type)
+    assert abs(float(loss) - float(ref_loss)) < FP32_TOL * max(1.0, abs(float(ref_loss)))
+    assert rel_err(pos.detach().cpu().numpy(), rpos.detach().numpy()) < FP32_TOL
+    assert rel_err(neg.detach().cpu().numpy(), rneg.detach().numpy()) < FP32_TOL
+    assert rel_err(xf.cpu().numpy(), ref_x.numpy()) < FP32_TOL
+    iso = (torch.bincount(kg.edge_index[1], minlength=cfg["N"]) == 0).to(dev)
+    assert bool(iso.any()) and not bool(xf[iso].any())  # nodes without in-edges: exactly zero rows
+    for lyr, o in zip(m._layers(), layers):
+        for hh in range(cfg["H"]):
+            assert rel_err(lyr.proj[hh].weight.grad.cpu().numpy(), o["W"][hh].grad.numpy()) < FP32_TOL
+            assert rel_err(lyr.attn_vec[hh].grad.cpu().numpy(), o["A"][hh].grad.numpy()) < FP32_TOL
+        assert rel_err(lyr.rel_bias.grad.cpu().numpy(), o["beta"].grad.numpy()) < FP32_TOL
+    assert rel_err(m.scorer.rel_emb.weight.grad.cpu().numpy(), rel_emb.grad.numpy()) < FP32_TOL
+
+
+def test_config2_size_layer_sampled_rows_and_gradients(dev):
+    """The 148-CTA persistent path at BASELINE.json configs[1] size (300 k nodes / 1.35 M edges, 1024-d, 4 heads x 200):
+    1 500 sampled destination rows of the layer output, and the parameter gradients induced by a gradient that lives on
+    those rows, against the fp64 closed form evaluated on the sampled rows' in-neighbourhood only."""
+    cfg = S.CONFIGS["c2"]
+    N, R_, H, F, D = cfg["N"], cfg["R"], cfg["H"], cfg["F"], cfg["D_in"]
+    kg = S.tensor_kg(N, cfg["T"], R_, D, seed=42, device=str(dev))
+    torch.manual_seed(0)
+    layer = R.RelGATLayer(D, F, R_, heads=H, dropout=0.0).to(dev)
+    with torch.no_grad():
+        torch.nn.init.normal_(layer.rel_bias, std=0.05)
+    out = layer(kg.node_emb, kg.edge_index, kg.edge_type)
+    rng = np.random.default_rng(0)
+    samp = np.sort(rng.choice(N, 1500, replace=False))
+    gs = rng.standard_normal((1500, H * F)).astype(np.float32)
+    dY = torch.zeros_like(out)
+    dY[torch.from_numpy(samp).to(dev)] = torch.from_numpy(gs).to(dev)
+    out.backward(dY)
+    # oracle on the in-neighbourhood of the sampled rows (original edge order preserved inside a destination)
+    src, dst = kg.edge_index[0].cpu().numpy(), kg.edge_index[1].cpu().numpy()
+    rel = kg.edge_type.cpu().numpy()
+    keep = np.isin(dst, samp)
+    s_e, d_e, r_e = src[keep], dst[keep], rel[keep]
+    nodes = np.unique(np.concatenate([s_e, samp]))
+    loc = {int(v): i for i, v in enumerate(nodes)}
+    ls = np.array([loc[int(v)] for v in s_e])
+    ld = np.array([loc[int(v)] for v in d_e])
+    X = kg.node_emb[torch.from_numpy(nodes).to(dev)].cpu().double().numpy()
+    W = layer.packed_weight().detach().cpu().double().numpy()          # [H*F, D]
+    A = layer.packed_attention().detach().cpu().double().numpy()       # [H, R, F]
+    beta = layer.rel_bias.detach().cpu().double().numpy()
+    P = (X @ W.T).reshape(len(nodes), H, F)
+    gi = O.graph_index_np(ls, ld, r_e, len(nodes), R_)
+    o_ref, z, alpha, _ = O.layer_forward_closed(P, A, beta, gi)
+    sl = np.array([loc[int(v)] for v in samp])
+    got = out.detach()[torch.from_numpy(samp).to(dev)].cpu().numpy()
+    assert rel_err(got, o_ref[sl].reshape(len(samp), H * F)) < FP32_TOL
+    G = np.zeros((len(nodes), H, F))
+    G[sl] = gs.reshape(-1, H, F)
+    dP, dA, dbeta, _ = O.layer_backward_closed(G, P, A, gi, z, alpha)
+    dW = dP.reshape(len(nodes), H * F).T @ X
+    assert rel_err(torch.stack([a.grad for a in layer.attn_vec]).cpu().numpy(), dA) < FP32_TOL
+    assert rel_err(layer.rel_bias.grad.cpu().numpy(), dbeta) < FP32_TOL
+    assert rel_err(torch.cat([p.weight.grad for p in layer.proj]).cpu().numpy(), dW) < FP32_TOL

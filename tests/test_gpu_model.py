@@ -97,9 +97,8 @@ def test_model_forward_api_and_fused_scores(dev):
         assert torch.equal(one, m.scorer.transform(x[src_ids], torch.full_like(rel_ids, 2)))
         s2, t2, _ = m(src_ids, rel_ids, dst_ids, transform_to_input_if_possible=False)
         assert t2 is None and torch.equal(s2, scores)
-        m.project_batch_rows_only = False  # the reference's order: project everything, then gather
-        s3, t3, d3 = m(src_ids, rel_ids, dst_ids)
-        assert close(s3, scores) and close(t3, transformed) and torch.equal(d3, x[dst_ids])
+        s3, t3, _ = m(src_ids, rel_ids, dst_ids, transform_rows=3)
+        assert t3.shape == (3, c.d_in) and torch.equal(s3, scores) and torch.equal(t3, transformed[:3])
 
 
 def test_layer_docstring_shape_and_input_gradient(dev):
@@ -140,10 +139,10 @@ def test_training_mode_dropout_path_runs_and_eval_is_deterministic(dev):
     m.eval()
     with torch.no_grad():
         assert torch.equal(m.single_gat_step(), m.single_gat_step())
-    lyr = R.RelGATLayer(8, 4, 3, heads=2, relation_attn_dropout=0.1).to(dev).train()
-    with pytest.raises(NotImplementedError):
-        lyr(torch.randn(5, 8, device=dev), torch.zeros(2, 3, dtype=torch.long, device=dev),
-            torch.zeros(3, dtype=torch.long, device=dev))
+    lyr = R.RelGATLayer(8, 4, 3, heads=2, relation_attn_dropout=0.5, dropout=0.0).to(dev).train()
+    ei = torch.randint(0, 5, (2, 40), device=dev)
+    y = lyr(torch.randn(5, 8, device=dev), ei, torch.zeros(40, dtype=torch.long, device=dev))
+    assert torch.isfinite(y).all()
 
 
 BF16_TOL = 2e-2       # stated tolerance of the bf16 mode: embeddings, scores, loss
@@ -323,7 +322,7 @@ def test_peer_table_partition_lockstep_equals_whole_graph(dev, world, blocks):
     x0 = kg.node_emb.clone().requires_grad_(True)
     grad_out = torch.randn(n, h * f, generator=gen).to(dev)
     g_full = G.GraphIndex(kg.edge_index, kg.edge_type, n, r)
-    out_ref = Fn.RelGATStackFunction.apply(x0, g_full, h, f, "fp32", None, *params)
+    out_ref = Fn.RelGATStackFunction.apply(x0, g_full, h, f, "fp32", None, None, None, *params)
     ref_grads = torch.autograd.grad(out_ref, [x0] + params, grad_out)
 
     store = {}
@@ -355,9 +354,10 @@ def test_peer_table_partition_lockstep_equals_whole_graph(dev, world, blocks):
 
 
 def test_sparse_loss_gradient_rows_give_the_dense_result(dev, monkeypatch):
-    """The scorer's backward tags its dense [N, D] gradient with the batch rows; the stack's backward then computes
-    t / hsum of the last layer from those rows only.  Same gradients, bit for bit, as with the tag ignored — and the
-    tag is really used on the fused model path."""
+    """Two hand-overs of the batch gradient to the stack's backward: (a) the fused stack + row gather node scatters the
+    batch rows' gradients into a persistent zero table and computes t / hsum of the last layer from those rows only;
+    (b) the module seam (GatherScoreFunction) returns a dense [N, D] gradient tagged with the row list.  Both must give
+    the gradients of the untagged dense path, bit for bit, and both must really take the sparse route."""
     from relgat_projector_b200 import functional as Fn, ops
     c = Case("tiny_fp64") if "tiny_fp64" in MODEL_CASES else Case(MODEL_CASES[0])
     seen = []
@@ -368,18 +368,25 @@ def test_sparse_loss_gradient_rows_give_the_dense_result(dev, monkeypatch):
         return real(*a, **kw)
 
     monkeypatch.setattr(ops, "edge_bwd_prep", spy)
-    grads = []
-    for use_tag in (True, False):
-        if not use_tag:
+    src_ids, rel_ids, dst_ids = c.t("src_ids").to(dev), c.t("rel_ids").to(dev), c.t("dst_ids").to(dev)
+    grads, used = [], []
+    for mode in ("fused_gather", "tagged_dense", "untagged_dense"):
+        if mode == "untagged_dense":
             monkeypatch.setattr(Fn, "sparse_rows_of", lambda g: None)
-        m = _load_model(c, dev).eval()  # no dropout masks: the two runs must be comparable bit for bit
-        loss, _, _ = _step(m, c, dev)
-        loss.backward()
+        m = _load_model(c, dev).eval()  # no dropout masks: the runs must be comparable bit for bit
+        if mode == "fused_gather":
+            scores, _, _ = m(src_ids, rel_ids, dst_ids, transform_to_input_if_possible=False)
+        else:
+            scores, _, _ = m.scorer.gather_score(m.single_gat_step(), src_ids, rel_ids, dst_ids)
+        del seen[:]
+        scores.square().mean().backward()
+        used.append(any(seen))
         grads.append({n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None})
-    assert any(seen[: len(seen) // 2]) and not any(seen[len(seen) // 2:])
-    assert grads[0].keys() == grads[1].keys()
+    assert used == [True, True, False]
+    assert grads[0].keys() == grads[1].keys() == grads[2].keys()
     for n in grads[0]:
-        assert torch.equal(grads[0][n], grads[1][n]), n
+        assert torch.equal(grads[1][n], grads[2][n]), n
+        assert torch.equal(grads[0][n], grads[2][n]), n
 
 
 def test_peer_table_sparse_last_layer_backward(dev):
@@ -412,7 +419,7 @@ def test_peer_table_sparse_last_layer_backward(dev):
         dense = torch.zeros(n, h * f, device=dev)
         uniq = torch.unique(ids)
         dense[uniq] = torch.randn(uniq.numel(), h * f, generator=gen).to(dev)
-        out_again = Fn.RelGATStackFunction.apply(x0, g_full, h, f, "fp32", None, *params)  # its backward runs once
+        out_again = Fn.RelGATStackFunction.apply(x0, g_full, h, f, "fp32", None, None, None, *params)  # its backward runs once
         ref = torch.autograd.grad(out_again, [x0] + params, dense)
         gens = []
         for p in parts:
@@ -440,15 +447,20 @@ def test_peer_table_sparse_last_layer_backward(dev):
 
 
 def test_projection_of_batch_rows_only_gives_the_same_gradients(dev):
-    """forward() with a projection head projects the 2·B' rows the scorer reads instead of all N:
-    same loss and parameter gradients as projecting everything; with an active dropout the full path is kept."""
+    """forward() gathers the 2·B' rows the scorer reads out of the fused stack and projects only those (SURVEY
+    8(f)-1): same loss and parameter gradients as the reference's order (project all N rows, then index); with an
+    active PROJECTION dropout the reference's order is kept."""
     c = Case("transe_proj_fp32")
     src_ids, rel_ids, dst_ids = c.t("src_ids").to(dev), c.t("rel_ids").to(dev), c.t("dst_ids").to(dev)
     res = []
     for subset in (True, False):
         m = _load_model(c, dev)  # training mode, all dropouts 0
-        m.project_batch_rows_only = subset
-        scores, tr, dv = m(src_ids, rel_ids, dst_ids)
+        if subset:
+            scores, tr, dv = m(src_ids, rel_ids, dst_ids)
+        else:
+            x = m.single_gat_step()
+            scores = m.scorer(x[src_ids], rel_ids, x[dst_ids])
+            tr, dv = m.scorer.transform(x[src_ids], rel_ids), x[dst_ids]
         loss = scores.square().mean() + 0.1 * tr.square().mean() + 0.1 * dv.square().mean()
         loss.backward()
         res.append((float(loss.detach()), {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}))
@@ -460,4 +472,4 @@ def test_projection_of_batch_rows_only_gives_the_same_gradients(dev):
         assert err < FP32_TOL, (n, err)
     m = _load_model(c, dev)
     m.projection.dropout = torch.nn.Dropout(0.5)
-    assert m._dropout_active() and not m.eval()._dropout_active()
+    assert m._projection_dropout_active() and not m.eval()._projection_dropout_active()
