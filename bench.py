@@ -36,7 +36,7 @@ METRIC = "relgat_train_edges_per_sec_fwd_bwd"
 UNIT = "edges/s"
 CPU_SAMPLE_SCALE = 20    # oracle-port fallback: the named config at 1/20 of the nodes and edges
 CPU_BASELINE_SCALE = 5   # cpu_baseline leg of this arm: the reference at 1/5 scale (~10-20 s of CPU work)
-REF_BUDGET_S = float(os.environ.get("RELGAT_REF_BUDGET_S", "420"))  # wall-clock budget of the reference arm's timed steps
+REF_BUDGET_S = float(os.environ.get("RELGAT_REF_BUDGET_S", "240"))  # wall-clock budget of the reference arm's timed steps
 
 
 def load_peaks():
@@ -111,7 +111,8 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 class KernelProfiler:
     NAMES = ["split_bf16", "gemm", "edge_fwd", "edge_bwd_prep", "edge_bwd_src", "edge_bwd_rel", "score_fwd",
-             "score_bwd", "index_add_sorted", "margin_loss", "rank_loss", "recon_loss", "zero_rows", "pull_rows"]
+             "score_bwd", "index_add_sorted", "margin_loss", "rank_loss", "recon_loss", "zero_rows", "pull_rows",
+             "edge_bwd_beta"]
 
     def __init__(self):
         from relgat_projector_b200 import ops
@@ -159,7 +160,7 @@ class KernelProfiler:
 # ---------------------------------------------------------------------------------------------
 # algorithmic bytes / flops (SURVEY.md §8(d) conventions; stated in DESIGN.md)
 # ---------------------------------------------------------------------------------------------
-def kernel_work(cfg, E, n_chunks, precision):
+def kernel_work(cfg, E, n_chunks, precision, use_ds=True):
     N, H, F, R = cfg["N"], cfg["H"], cfg["F"], cfg["R"]
     C = H * F
     s = 4
@@ -170,7 +171,8 @@ def kernel_work(cfg, E, n_chunks, precision):
         "edge_fwd": E * (C * sf + 8) + N * (C * s + 4 + 4 + H * 8) + E * H * 4,
         "edge_fwd_act": N * C * plane_b,
         # own P row + gather G[dst] + (slot, dst, rel) ids + z, (max, 1/den), t; writes dP planes and dz
-        "edge_bwd_src": N * C * sf + E * (C * sf + 12 + 4 * H * 4) + N * C * plane_b + E * H * 4,
+        "edge_bwd_src": (N * C * sf + E * (C * sf + 12 + 4 * H * 4) + N * C * plane_b
+                         + (N * H * R * plane_b if use_ds else E * H * 4)),  # dS columns, or dz per edge
         # gathers P[src] + (slot, src, dst) ids + dz + hsum; writes chunk partials
         "edge_bwd_rel": E * (C * sf + 12 + 2 * H * 4) + n_chunks * C * s * 2,
     }
@@ -472,7 +474,8 @@ def main():
             train_step(*dev_batches[i % n_pool])
         table = prof.table(psteps)
     g = model._graph()
-    work = kernel_work(cfg, E, g.n_chunks, args.precision)
+    from relgat_projector_b200 import functional as RFn
+    work = kernel_work(cfg, E, g.n_chunks, args.precision, use_ds=RFn.USE_DS)
     peaks = load_peaks()
     kernels = {}
     for tag, d in sorted(table.items(), key=lambda kv: -kv[1]["ms_per_step"]):
@@ -489,7 +492,7 @@ def main():
             ent["tensor_flops"] = flops
             ent["tflops"] = round(flops / (d["avg_ms"] * 1e-3) / 1e12, 1)
             ent["frac_tensor"] = round(ent["tflops"] / peaks["tflops"], 4)
-        if d["kernel"] == "edge_bwd_rel" or (d["kernel"] == "gemm" and tag.endswith("mnmn]")):
+        if not RFn.USE_DS and (d["kernel"] == "edge_bwd_rel" or (d["kernel"] == "gemm" and tag.endswith("mnmn]"))):
             # the by-relation pass runs on a side stream beside the dW GEMM: both elapsed times include
             # the other's interference (isolated: 0.69 ms at 96 % of HBM peak; 1.14 ms) — not "dominant"
             ent["overlapped"] = True

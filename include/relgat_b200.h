@@ -117,6 +117,11 @@ int relgat_layer_fwd(const void* P, int p_is_bf16, long long ldp, const float* A
  *           part_acc [n_parts, H*F] holds the partial rows of split sources):
  *           dP [N_src, H*F] (fp32 and/or bf16 hi/lo planes) and dz [E, H]; the attention weights
  *           are recomputed from z and minv.  edge_bits / edge_scale: the forward's attention-dropout mask.
+ *           want_ds != 0 (logit-table gradient, replaces the by-relation pass): the dP rows are ldo >= H*F + H*R wide
+ *           and columns H*F + h*R + r receive dS[i,h,r] = sum_{e: src=i, rel=r} dz[e,h]; dW_ext = dP_ext^T X then holds
+ *           dW in its first H*F rows and dS^T X below, and dA[h] = (dS_h^T X) W_h^T — no third gather of P.  dz may then
+ *           be NULL.  ldo = row stride (elements) of dP / dP_hi / dP_lo / part_acc (<= 0: H*F).
+ * bwd_beta: dbeta [R] alone (the P-free part of bwd_rel), partB [n_chunks] scratch.
  * bwd_rel : by-relation pass over chunks [chunk_lo, chunk_hi) of rel_slot (a chunk never spans
  *           two relations; rel_chunk_ptr[R+1] gives each relation's chunk range):
  *           dA [H, R, F] and dbeta [R] (NULL to skip) with an ordered reduction of the partials
@@ -131,8 +136,11 @@ int relgat_layer_bwd_src(const void* P, long long ldp, const void* G, int feat_i
                          const int* chunks, int n_chunks, const int* parts, int n_parts,
                          const int* long_node, const int* long_part_ptr, int n_long, float* part_acc,
                          float* dP, void* dP_hi, void* dP_lo, float* dz,
-                         const unsigned int* edge_bits, float edge_scale,
+                         const unsigned int* edge_bits, float edge_scale, int want_ds, long long ldo,
                          int H, int F, int R, int sm_count, int* work_counter, void* stream);
+int relgat_layer_bwd_beta(const float* hsum, const int* rel_slot, const int* csr_dst, const int* chunk_lo,
+                          const int* chunk_hi, const int* rel_chunk_ptr, int n_chunks, float* partB, float* dbeta,
+                          int H, int R, void* stream);
 int relgat_layer_bwd_rel(const void* P, int p_is_bf16, long long ldp, const float* dz, const float* hsum,
                          const int* rel_slot, const int* csr_src, const int* csr_dst,
                          const int* chunk_lo, const int* chunk_hi, const int* rel_chunk_ptr,

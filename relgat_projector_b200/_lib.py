@@ -40,7 +40,8 @@ SIGNATURES = {
                               _P, _I, _F, _P, _F, _I, _I, _I, _I, _P, _P]),
     "relgat_layer_bwd_prep": (_I, [_P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P, _I, _F, _P]),
     "relgat_layer_bwd_src": (_I, [_P, _L, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P,
-                                  _P, _F, _I, _I, _I, _I, _P, _P]),
+                                  _P, _F, _I, _L, _I, _I, _I, _I, _P, _P]),
+    "relgat_layer_bwd_beta": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _P]),
     "relgat_layer_bwd_rel": (_I, [_P, _I, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _P]),
     "relgat_score_fwd": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _P, _P, _P]),
     "relgat_score_bwd": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P]),
@@ -60,7 +61,7 @@ SIGNATURES = {
     "relgat_pull_rows": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _I, _P]),
 }
 
-ABI_VERSION = 3  # bumped whenever a signature in include/relgat_b200.h changes
+ABI_VERSION = 4  # bumped whenever a signature in include/relgat_b200.h changes
 _lib = None
 
 

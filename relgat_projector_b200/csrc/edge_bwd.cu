@@ -132,6 +132,11 @@ struct SrcArgs {
   int* work_counter;  // zeroed device ints (one per head-group): dynamic chunk claim; nullptr = static
   const uint32_t* edge_bits;  // attention-dropout keep bits (index = csr slot * H + head) or nullptr
   float edge_scale;
+  // logit-table gradient: with ds_on the dP rows are ldo = C + H*R wide and columns C + h*R + r
+  // receive dS[i, h, r] = sum_{e: src = i, rel = r} dz[e, h].  The dW GEMM over the widened rows then also yields
+  // dS^T X, from which dA = (dS^T X) W^T follows without a third gather of P (the by-relation pass).
+  int ds_on;
+  long long ldo;        // row stride of dP / dP_hi / dP_lo / part_acc in elements (C, or C + H*R with ds_on)
 };
 
 template <typename T, int V, int KV, bool ASM, int PIPE, int LPHC>
@@ -146,6 +151,9 @@ __global__ void __launch_bounds__((PIPE ? kSrcWarpsPipe : kSrcWarps) * 32, 1) bw
   const int hl = lm.hh - g * a.hg;
   float* p_own = dyn_sm + warp * kOwnFloats;
   float* a_sm = dyn_sm + kWarps * kOwnFloats;
+  const int ds_n = a.hg * a.R;  // dS entries of this warp's head-group for one source
+  float* ds_sm = a_sm + (ASM ? a.hg * a.R * a.F : 0) + warp * ds_n;
+  const int ds_col0 = C + g * ds_n;  // first dS column of this head-group inside an output row
 
   const int kstride = (LPHC > 0 ? LPHC : lm.lph) * V;  // compile-time on the specialised paths
   const int lane_off = lm.head_off + lm.sub * V;
@@ -206,6 +214,10 @@ __global__ void __launch_bounds__((PIPE ? kSrcWarpsPipe : kSrcWarps) * 32, 1) bw
     for (int k = 0; k < KV; ++k)
 #pragma unroll
       for (int v = 0; v < V; ++v) acc[k][v] = 0.f;
+    if (a.ds_on) {
+      for (int i = lane; i < ds_n; i += 32) ds_sm[i] = 0.f;
+      __syncwarp();
+    }
 
     // fetch cursor (item generation)
     int fk = 0;             // source whose items are being generated
@@ -293,7 +305,10 @@ __global__ void __launch_bounds__((PIPE ? kSrcWarpsPipe : kSrcWarps) * 32, 1) bw
     const float ek = a.edge_bits ? keep_scale1(a.edge_bits, static_cast<long long>(sl_) * a.H + lm.hh, a.edge_scale) : 1.f; \
     const float dzv = al * (dd * ek - tt_) * (zz_ > 0.f ? 1.f : kLeakySlope);                  \
     al *= ek;                                                                                  \
-    if (lm.sub == 0) a.dz[static_cast<long long>(sl_) * a.H + lm.hh] = dzv;                    \
+    if (lm.sub == 0) {                                                                         \
+      if (a.dz) a.dz[static_cast<long long>(sl_) * a.H + lm.hh] = dzv;                         \
+      if (a.ds_on) ds_sm[hl * a.R + (rl_)] += dzv; /* one lane per head owns the slot */       \
+    }                                                                                          \
     const float* ar = a_base + (rl_) * a.F;                                                    \
     _Pragma("unroll") for (int k = 0; k < KV; ++k) {                                           \
       if (RG_VALID(k)) {                                                                       \
@@ -312,12 +327,30 @@ __global__ void __launch_bounds__((PIPE ? kSrcWarpsPipe : kSrcWarps) * 32, 1) bw
   if (ty_ == IT_EDGE) {                                                                        \
     RG_EDGE_ITEM(sl_, rl_, x_, zz_, mi_, tt_)                                                  \
   } else {                                                                                     \
+    if (cur >= 0 && a.ds_on) { /* dS columns of the source being closed, then clear the slots */ \
+      __syncwarp();                                                                            \
+      const long long drow = (part >= 0 ? static_cast<long long>(part) : static_cast<long long>(n_lo + cur)) * a.ldo + ds_col0; \
+      for (int i = lane; i < ds_n; i += 32) {                                                  \
+        const float dv = ds_sm[i];                                                             \
+        ds_sm[i] = 0.f;                                                                        \
+        if (part >= 0) a.part_acc[drow + i] = dv;                                              \
+        else {                                                                                 \
+          if (a.dP) a.dP[drow + i] = dv;                                                       \
+          if (a.dP_hi) {                                                                       \
+            const float hv = bf16_round(dv);                                                   \
+            a.dP_hi[drow + i] = __float2bfloat16_rn(hv);                                       \
+            if (a.dP_lo) a.dP_lo[drow + i] = __float2bfloat16_rn(dv - hv);                     \
+          }                                                                                    \
+        }                                                                                      \
+      }                                                                                        \
+      __syncwarp();                                                                            \
+    }                                                                                          \
     if (cur >= 0 && part >= 0) { /* split source: park the partial row for the merge kernel */  \
-      const long long row_off = static_cast<long long>(part) * C + lane_off;                   \
+      const long long row_off = static_cast<long long>(part) * a.ldo + lane_off;               \
       _Pragma("unroll") for (int k = 0; k < KV; ++k)                                           \
         if (RG_VALID(k)) RowVec<float, V>::store(a.part_acc + row_off + k * kstride, acc[k]);  \
     } else if (cur >= 0) {                                                                     \
-      const long long row_off = static_cast<long long>(n_lo + cur) * C + lane_off;             \
+      const long long row_off = static_cast<long long>(n_lo + cur) * a.ldo + lane_off;         \
       _Pragma("unroll") for (int k = 0; k < KV; ++k) {                                         \
         if (RG_VALID(k)) {                                                                     \
           const long long off = row_off + k * kstride;                                         \
@@ -521,6 +554,38 @@ __global__ void bwd_rel_reduce_kernel(const float* __restrict__ partA, const flo
   }
 }
 
+
+// dbeta[r] = sum_{e: rel = r} sum_h hsum[dst_e, h] over the by-relation chunks (the part of the by-relation pass that
+// does not need P; used when dA comes from the widened dW GEMM).  One warp per chunk, fixed xor-tree per 32 edges,
+// chunk partials folded in chunk order by bwd_beta_reduce_kernel: reproducible.
+__global__ void __launch_bounds__(kBwdWarps * 32)
+bwd_beta_kernel(const float* __restrict__ hsum, const int* __restrict__ rel_slot, const int* __restrict__ csr_dst,
+                const int* __restrict__ chunk_lo, const int* __restrict__ chunk_hi, int n_chunks, int H,
+                float* __restrict__ partB) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * kBwdWarps + warp;
+  if (c >= n_chunks) return;
+  float bacc = 0.f;
+  for (int base = chunk_lo[c]; base < chunk_hi[c]; base += 32) {
+    float hs = 0.f;
+    if (base + lane < chunk_hi[c]) {
+      const int jd = __ldg(csr_dst + __ldg(rel_slot + base + lane));
+      for (int h = 0; h < H; ++h) hs += __ldg(hsum + static_cast<long long>(jd) * H + h);
+    }
+    bacc += warp_sum(hs);
+  }
+  if (lane == 0) partB[c] = bacc;
+}
+
+__global__ void bwd_beta_reduce_kernel(const float* __restrict__ partB, const int* __restrict__ rel_chunk_ptr,
+                                       float* __restrict__ dbeta, int R) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  float s = 0.f;
+  for (int c = rel_chunk_ptr[r]; c < rel_chunk_ptr[r + 1]; ++c) s += partB[c];
+  dbeta[r] = s;
+}
+
 template <typename Args, typename K>
 static int launch_tasks(K kernel, const Args& a, long long tasks, cudaStream_t s) {
   if (tasks == 0) return RG_OK;
@@ -589,13 +654,26 @@ bwd_src_merge_kernel(const SrcArgs<T, V> a, const int* __restrict__ long_node, c
     for (int v = 0; v < V; ++v) acc[v] = 0.f;
     for (int p = p_lo; p < p_hi; ++p) {
       float x[V];
-      RowVec<float, V>::load_cached(a.part_acc + static_cast<long long>(p) * C + c, x);
+      RowVec<float, V>::load_cached(a.part_acc + static_cast<long long>(p) * a.ldo + c, x);
 #pragma unroll
       for (int v = 0; v < V; ++v) acc[v] += x[v];
     }
-    const long long off = static_cast<long long>(i) * C + c;
+    const long long off = static_cast<long long>(i) * a.ldo + c;
     if (a.dP) RowVec<float, V>::store(a.dP + off, acc);
     if (a.dP_hi) store_split_bf16<V>(a.dP_hi + off, a.dP_lo ? a.dP_lo + off : nullptr, acc);
+  }
+  if (a.ds_on) {  // the dS columns of the split source: ordered sum of its parts
+    for (int c = C + threadIdx.x; c < C + a.H * a.R; c += blockDim.x) {
+      float acc = 0.f;
+      for (int p = p_lo; p < p_hi; ++p) acc += a.part_acc[static_cast<long long>(p) * a.ldo + c];
+      const long long off = static_cast<long long>(i) * a.ldo + c;
+      if (a.dP) a.dP[off] = acc;
+      if (a.dP_hi) {
+        const float hv = bf16_round(acc);
+        a.dP_hi[off] = __float2bfloat16_rn(hv);
+        if (a.dP_lo) a.dP_lo[off] = __float2bfloat16_rn(acc - hv);
+      }
+    }
   }
 }
 
@@ -608,9 +686,11 @@ static int launch_src_pipe(SrcArgs<T, V> a, int sm_count, cudaStream_t s) {
   if (ctas < 1) ctas = 1;
   const int need = (a.n_chunks + kWarps - 1) / kWarps;
   if (ctas > need) ctas = need;
+  const size_t ds_bytes = a.ds_on ? static_cast<size_t>(kWarps) * a.hg * a.R * sizeof(float) : 0;
   const size_t own_bytes = static_cast<size_t>(kWarps) * KV * 32 * V * sizeof(float);
   const size_t a_bytes = static_cast<size_t>(a.hg) * a.R * a.F * sizeof(float);
-  a.a_in_smem = a_bytes <= kSmemBudgetA ? 1 : 0;
+  a.a_in_smem = (a_bytes <= kSmemBudgetA && own_bytes + a_bytes + ds_bytes <= 227 * 1024) ? 1 : 0;
+  if (own_bytes + ds_bytes > 227 * 1024) return RG_ERR_SHAPE;
   {
     const char* pv = getenv("RELGAT_SRC_PF_DIST");
     a.pf_dist = pv ? atoi(pv) : kSrcPrefetchDist;
@@ -619,12 +699,16 @@ static int launch_src_pipe(SrcArgs<T, V> a, int sm_count, cudaStream_t s) {
   }
   if (a.a_in_smem) {
     cudaError_t e = cudaFuncSetAttribute(bwd_src_kernel<T, V, KV, true, PIPE, LPHC>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(own_bytes + kSmemBudgetA));
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return cuda_status(e);
-    bwd_src_kernel<T, V, KV, true, PIPE, LPHC><<<dim3(ctas, groups), kWarps * 32, own_bytes + a_bytes, s>>>(a);
+    bwd_src_kernel<T, V, KV, true, PIPE, LPHC><<<dim3(ctas, groups), kWarps * 32, own_bytes + a_bytes + ds_bytes, s>>>(a);
   } else {
-    bwd_src_kernel<T, V, KV, false, PIPE, LPHC><<<dim3(ctas, groups), kWarps * 32, own_bytes, s>>>(a);
+    if (own_bytes + ds_bytes > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(bwd_src_kernel<T, V, KV, false, PIPE, LPHC>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return cuda_status(e);
+    }
+    bwd_src_kernel<T, V, KV, false, PIPE, LPHC><<<dim3(ctas, groups), kWarps * 32, own_bytes + ds_bytes, s>>>(a);
   }
   return cuda_status(cudaGetLastError());
 }
@@ -673,7 +757,7 @@ static int run_src(const void* P, long long ldp, const void* G, const float* A, 
                    const float* t, const int* colptr, const int* csc_slot, const int* csc_dst, const int* csc_rel,
                    const int4* ch, int n_chunks, const int2* pt, const int* long_node, const int* long_part_ptr,
                    int n_long, float* part_acc, float* dP, void* dP_hi, void* dP_lo, float* dz,
-                   const uint32_t* edge_bits, float edge_scale, int H, int F, int R,
+                   const uint32_t* edge_bits, float edge_scale, int ds_on, long long ldo, int H, int F, int R,
                    int sm_count, int* work_counter, cudaStream_t s) {
   const int hg = pick_heads_per_warp(H, F, V, R, smem_budget_override("RELGAT_SRC_BUDGET_KB", kSmemBudgetA));
   if (!hg) return RG_ERR_SHAPE;
@@ -685,7 +769,7 @@ static int run_src(const void* P, long long ldp, const void* G, const float* A, 
   SrcArgs<T, V> a{static_cast<const T*>(P), static_cast<const T*>(G), A, z, minv, t, colptr, csc_slot, csc_dst,
                   csc_rel, ch, pt, part_acc, dP, static_cast<__nv_bfloat16*>(dP_hi),
                   static_cast<__nv_bfloat16*>(dP_lo), dz, n_chunks, H, F, R, hg, ldp, 0, 0, work_counter,
-                  edge_bits, edge_scale};
+                  edge_bits, edge_scale, ds_on, ldo};
   int rc = launch_src(a, sm_count, s);
   if (rc != RG_OK || n_long == 0) return rc;
   bwd_src_merge_kernel<T, V><<<n_long, 128, 0, s>>>(a, long_node, long_part_ptr, n_long);
@@ -698,10 +782,12 @@ extern "C" int relgat_layer_bwd_src(const void* P, long long ldp, const void* G,
                                     const int* chunks, int n_chunks, const int* parts, int n_parts,
                                     const int* long_node, const int* long_part_ptr, int n_long, float* part_acc,
                                     float* dP, void* dP_hi, void* dP_lo, float* dz,
-                                    const unsigned int* edge_bits, float edge_scale,
+                                    const unsigned int* edge_bits, float edge_scale, int want_ds, long long ldo,
                                     int H, int F, int R, int sm_count, int* work_counter, void* stream) {
   if (!P || !G || !A || !colptr || n_chunks < 0 || n_parts < 0 || n_long < 0 || H <= 0 || F <= 0 || R <= 0)
     return RG_ERR_ARG;
+  if (ldo <= 0) ldo = static_cast<long long>(H) * F;
+  if (ldo < static_cast<long long>(H) * F + (want_ds ? static_cast<long long>(H) * R : 0)) return RG_ERR_ARG;
   if (n_chunks > 0 && !chunks) return RG_ERR_ARG;
   if (n_parts > 0 && (!parts || !long_node || !long_part_ptr || !part_acc)) return RG_ERR_ARG;
   if (n_chunks == 0) return RG_OK;
@@ -711,19 +797,19 @@ extern "C" int relgat_layer_bwd_src(const void* P, long long ldp, const void* G,
   const int4* ch = reinterpret_cast<const int4*>(chunks);
   const int2* pt = reinterpret_cast<const int2*>(parts);
   if (feat_is_bf16) {
-    if (F % 8 != 0 || ldp % 8 != 0) return RG_ERR_SHAPE;
+    if (F % 8 != 0 || ldp % 8 != 0 || ldo % 8 != 0) return RG_ERR_SHAPE;
     if (!ok16) return RG_ERR_ALIGN;
     return run_src<__nv_bfloat16, 8>(P, ldp, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, ch, n_chunks, pt,
                                      long_node, long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, edge_bits, edge_scale,
-                                     H, F, R, sm_count, work_counter, s);
+                                     want_ds, ldo, H, F, R, sm_count, work_counter, s);
   }
-  if (F % 4 == 0 && ldp % 4 == 0 && ok16)
+  if (F % 4 == 0 && ldp % 4 == 0 && ldo % 4 == 0 && ok16)
     return run_src<float, 4>(P, ldp, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, ch, n_chunks, pt, long_node,
-                             long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, edge_bits, edge_scale, H, F, R, sm_count,
-                             work_counter, s);
+                             long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, edge_bits, edge_scale, want_ds, ldo, H, F, R,
+                             sm_count, work_counter, s);
   return run_src<float, 1>(P, ldp, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, ch, n_chunks, pt, long_node,
-                           long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, edge_bits, edge_scale, H, F, R, sm_count,
-                             work_counter, s);
+                           long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, edge_bits, edge_scale, want_ds, ldo, H, F, R,
+                             sm_count, work_counter, s);
 }
 
 template <typename T, int V>
@@ -765,5 +851,21 @@ extern "C" int relgat_layer_bwd_rel(const void* P, int p_is_bf16, long long ldp,
   const int threads = 256;
   const long long blocks = (total + threads - 1) / threads;
   bwd_rel_reduce_kernel<<<static_cast<unsigned>(blocks), threads, 0, s>>>(partA, partB, rel_chunk_ptr, dA, dbeta, R, H, F);
+  return cuda_status(cudaGetLastError());
+}
+
+extern "C" int relgat_layer_bwd_beta(const float* hsum, const int* rel_slot, const int* csr_dst, const int* chunk_lo,
+                                     const int* chunk_hi, const int* rel_chunk_ptr, int n_chunks, float* partB,
+                                     float* dbeta, int H, int R, void* stream) {
+  if (!hsum || !rel_chunk_ptr || !dbeta || n_chunks < 0 || H <= 0 || R <= 0) return RG_ERR_ARG;
+  if (n_chunks > 0 && (!rel_slot || !csr_dst || !chunk_lo || !chunk_hi || !partB)) return RG_ERR_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (n_chunks > 0) {
+    bwd_beta_kernel<<<(n_chunks + kBwdWarps - 1) / kBwdWarps, kBwdWarps * 32, 0, s>>>(hsum, rel_slot, csr_dst, chunk_lo,
+                                                                                    chunk_hi, n_chunks, H, partB);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_status(e);
+  }
+  bwd_beta_reduce_kernel<<<(R + 127) / 128, 128, 0, s>>>(partB, rel_chunk_ptr, dbeta, R);
   return cuda_status(cudaGetLastError());
 }

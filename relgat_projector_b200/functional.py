@@ -8,6 +8,7 @@ Nothing here does arithmetic in torch; torch allocates and orders the launches.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -16,6 +17,9 @@ from . import ops
 from .graph import GraphIndex
 
 PRECISIONS = ("fp32", "bf16")
+# dA through the logit-table gradient (dS columns beside dP, widened dW GEMM) instead of the by-relation gather pass
+# (SURVEY.md A.3); RELGAT_DS=0 restores the by-relation kernel (kept for the partitioned path and for A/B timing)
+USE_DS = os.environ.get("RELGAT_DS", "1") != "0"
 
 _SIDE_STREAMS = {}
 
@@ -199,17 +203,47 @@ class RelGATStackFunction(torch.autograd.Function):
                                            feat_drop=dl.feat if dl else None)
             _, dPp, dz = ops.edge_bwd_src(s["P"], G, s["A"], s["z"], s["minv"], t, g, H, F,
                                           want_fp32=False, want_planes=True, planes_lo=with_lo,
-                                          edge_drop=dl.edge if dl else None)
+                                          edge_drop=dl.edge if dl else None, want_ds=USE_DS)
             if table is not None and l == L - 1:
                 ops.zero_rows(table, nz_rows)  # the table's rows are consumed (G aliased it): make it all-zero again
                 _return_zero_table(table)
                 G = None
+            d_in = s["d_in"]
             main = torch.cuda.current_stream(dY.device)
             side = _side_stream(dY.device)
+            if USE_DS:
+                # widened rows [dP | dS]: ONE split-K GEMM gives dW (first C rows) and dS^T X (the H*R rows below);
+                # dA[h] = (dS_h^T X) W_h^T is a 200 x 800 x d_in GEMM; dbeta needs hsum only.  No gather of P.
+                HR = H * g.R
+                Wd = dPp[0].size(1)
+                dP_c = tuple(None if p_ is None else p_[:, :C] for p_ in dPp)
+                splits = ops.pick_splits_k(Wd, d_in, N, dY.device)
+                dW_ext = ops.gemm(dPp, True, s["xp"], True, Wd, d_in, N, splits_k=splits)
+                dw_ready = torch.cuda.Event()
+                dw_ready.record(main)
+                if l > 0 or ctx.x0_needs_grad:
+                    dX = ops.gemm(dP_c, False, s["WTp"], False, N, d_in, C)
+                side.wait_event(dw_ready)
+                with torch.cuda.stream(side):  # small tail work beside the next layer's kernels
+                    Tp = ops.split_bf16(dW_ext[C:C + HR].contiguous(), with_lo)
+                    dA_full = ops.gemm(Tp, False, s["Wp"], False, HR, C, d_in)
+                    dA = torch.stack([dA_full[h * g.R:(h + 1) * g.R, h * F:(h + 1) * F] for h in range(H)])
+                    dbeta = ops.edge_bwd_beta(hsum, g, H) if s["has_beta"] else None
+                for tns in (dW_ext, hsum):
+                    tns.record_stream(side)
+                for tns in (dA, dbeta):  # allocated on the side stream, consumed by the optimizer on the main one
+                    if tns is not None:
+                        tns.record_stream(main)
+                grads[3 * l], grads[3 * l + 1], grads[3 * l + 2] = dW_ext[:C], dA, dbeta
+                if l > 0 or ctx.x0_needs_grad:
+                    dY, owned = dX, True
+                if l == 0:
+                    main.wait_stream(side)
+                del G, dPp, dz
+                continue
             side.wait_stream(main)
             with torch.cuda.stream(side):  # dA / dbeta: gather-bound, overlaps the GEMMs below
                 dA, dbeta = ops.edge_bwd_rel(s["P"], dz, hsum, g, H, F, want_dbeta=s["has_beta"])
-            d_in = s["d_in"]
             splits = ops.pick_splits_k(C, d_in, N, dY.device)
             dW = ops.gemm(dPp, True, s["xp"], True, C, d_in, N, splits_k=splits)
             grads[3 * l], grads[3 * l + 1], grads[3 * l + 2] = dW, dA, dbeta

@@ -316,9 +316,16 @@ def edge_bwd_prep(dY: torch.Tensor, out: torch.Tensor, bias: torch.Tensor, H: in
     return G, t, hsum
 
 
+def ds_row_width(H: int, F: int, R: int) -> int:
+    """Row width of the widened dP rows [dP | dS] (multiple of 8 elements: TMA strides, 128-bit stores)."""
+    return (H * F + H * R + 7) // 8 * 8
+
+
 def edge_bwd_src(P, G, A, z, minv, t, g: GraphIndex, H: int, F: int, want_fp32: bool = True,
-                 want_planes: bool = False, planes_lo: bool = True, edge_drop: Optional["DropMask"] = None):
-    """Returns (dP fp32 or None, dP planes or None, dz [E,H])."""
+                 want_planes: bool = False, planes_lo: bool = True, edge_drop: Optional["DropMask"] = None,
+                 want_ds: bool = False):
+    """Returns (dP fp32 or None, dP planes or None, dz [E,H] or None).  ``want_ds``: the rows are
+    ``ds_row_width`` wide, columns H*F + h*R + r hold dS and dz is not written."""
     P = _feat(P, "P")
     G = _feat(G, "G")
     if P.dtype != G.dtype:
@@ -328,12 +335,14 @@ def edge_bwd_src(P, G, A, z, minv, t, g: GraphIndex, H: int, F: int, want_fp32: 
     n_src, C = P.size(0), H * F
     if n_src != g.N_src or G.size(0) != g.N:
         raise ValueError("P / G row counts do not match the graph index")
-    dP = torch.empty((n_src, C), dtype=torch.float32, device=dev) if want_fp32 else None
-    hi = torch.empty((n_src, C), dtype=torch.bfloat16, device=dev) if want_planes else None
-    lo = torch.empty((n_src, C), dtype=torch.bfloat16, device=dev) if (want_planes and planes_lo) else None
-    dz = torch.empty((g.E, H), dtype=torch.float32, device=dev)
+    W = ds_row_width(H, F, g.R) if want_ds else C
+    mk = torch.zeros if W > C + H * g.R else torch.empty  # padding columns feed the GEMM: keep them finite
+    dP = mk((n_src, W), dtype=torch.float32, device=dev) if want_fp32 else None
+    hi = mk((n_src, W), dtype=torch.bfloat16, device=dev) if want_planes else None
+    lo = mk((n_src, W), dtype=torch.bfloat16, device=dev) if (want_planes and planes_lo) else None
+    dz = None if want_ds else torch.empty((g.E, H), dtype=torch.float32, device=dev)
     ck = g.src_chunks
-    part_acc = torch.empty((ck.n_parts, C), dtype=torch.float32, device=dev) if ck.n_parts else None
+    part_acc = torch.empty((ck.n_parts, W), dtype=torch.float32, device=dev) if ck.n_parts else None
     with torch.cuda.device(dev):
         rc = _lib.load().relgat_layer_bwd_src(
             _lib.ptr(P), P.stride(0), _lib.ptr(G), int(P.dtype == torch.bfloat16), _lib.ptr(A), _lib.ptr(z),
@@ -341,10 +350,25 @@ def edge_bwd_src(P, G, A, z, minv, t, g: GraphIndex, H: int, F: int, want_fp32: 
             _lib.ptr(ck.chunks), ck.n_chunks, _lib.ptr(ck.parts), ck.n_parts,
             _lib.ptr(ck.long_node), _lib.ptr(ck.long_part_ptr), ck.n_long, _lib.ptr(part_acc),
             _lib.ptr(dP), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dz), *_edge_mask_args(edge_drop, g.E, H),
-            H, F, g.R, sm_count(dev), _lib.ptr(_work_counter(dev)), _stream(P))
+            int(want_ds), W, H, F, g.R, sm_count(dev), _lib.ptr(_work_counter(dev)), _stream(P))
     _lib.check(rc, "relgat_layer_bwd_src")
     _count(2 if ck.n_long else 1)
     return dP, ((hi, lo) if want_planes else None), dz
+
+
+def edge_bwd_beta(hsum: torch.Tensor, g: GraphIndex, H: int) -> torch.Tensor:
+    """dbeta [R] = sum over the edges of a relation of sum_h hsum[dst] (reference layer.py:313-318 backward)."""
+    hsum = _f32c(hsum, "hsum")
+    dev = hsum.device
+    partB = torch.empty((max(g.n_chunks, 1),), dtype=torch.float32, device=dev)
+    dbeta = torch.empty((g.R,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().relgat_layer_bwd_beta(_lib.ptr(hsum), _lib.ptr(g.rel_slot), _lib.ptr(g.csr_dst),
+                                               _lib.ptr(g.chunk_lo), _lib.ptr(g.chunk_hi), _lib.ptr(g.rel_chunk_ptr),
+                                               g.n_chunks, _lib.ptr(partB), _lib.ptr(dbeta), H, g.R, _stream(hsum))
+    _lib.check(rc, "relgat_layer_bwd_beta")
+    _count(2)
+    return dbeta
 
 
 def edge_bwd_rel(P, dz, hsum, g: GraphIndex, H: int, F: int, want_dbeta: bool = True):
