@@ -67,6 +67,19 @@ int relgat_gemm_bf16(const void* a_hi, const void* a_lo, long long lda, int a_mn
                      void* d, int d_is_bf16, long long ldd, int M, int N, int K, int splits_k,
                      void* workspace, long long workspace_bytes, int sm_count, void* stream);
 
+/* N-tile width the GEMM uses for an N-column output, and the dX GEMM of a layer (A = dP [M, K] hi/lo planes, B = W^T
+ * [N, K] planes, both K-major, fp32-parity or single-plane mode) with relgat_layer_bwd_prep of the layer below FUSED
+ * into its epilogue (the tile is d loss / d act(y) while it sits in tensor memory): writes G [M, N] = dX * act'(y) * m
+ * instead of dX, and t / hsum [M, H] from per-(row, tile) partials (tpart / hpart: float [M * n_tiles * 2] scratch,
+ * n_tiles = ceil(N / relgat_gemm_tile_n(N))).  y = the layer below's (post-dropout) pre-activation rows [M, N = H*F],
+ * bias [M] its relation-bias sums, drop_* its feature-dropout mask (NULL = off), apply_elu: act = ELU else identity.
+ * Needs relgat_gemm_tile_n(N) <= F (a tile inside at most two heads), else RG_ERR_SHAPE (use the unfused pair). */
+int relgat_gemm_tile_n(int N);
+int relgat_gemm_dx_prep(const void* a_hi, const void* a_lo, long long lda, const void* b_hi, const void* b_lo,
+                        long long ldb, float* G, int M, int N, int K, const float* y, const float* bias,
+                        const unsigned int* drop_bits, int drop_words, float drop_scale, int H, int F,
+                        int apply_elu, float* tpart, float* hpart, float* t, float* hsum, int sm_count, void* stream);
+
 /* ---- RelGAT layer, edge part, forward ------------------------------------------------------
  * Replaces core/model/layer.py:220 (the [src] gather) through :318: logits + LeakyReLU(0.2),
  * per-destination stable softmax (torch_scatter.scatter_max / scatter_add), weighted

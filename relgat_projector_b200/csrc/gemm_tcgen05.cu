@@ -41,6 +41,18 @@ struct GemmParams {
   int a_tile_bytes, b_tile_bytes;   // per plane
   int b_boxes;           // MN-major B: number of 64-wide boxes per tile
   int staged;            // 1: the epilogue transposes 32x16 (fp32) / 32x32 (bf16) blocks through shared memory
+  // fused "backward prep" epilogue of the dX GEMM (replaces relgat_layer_bwd_prep for a hidden layer): the tile is
+  // dX = d loss / d act(y); written instead: G = dX * act'(y) * m, and per (row, tile) partial sums of
+  // t = <dX * act'(y), y - bias * m> and hsum = sum G for the (at most two) heads the tile touches (BN <= F).
+  const float* epi_y;    // [M, N] post-dropout pre-activation rows of the layer below (nullptr = plain GEMM)
+  const float* epi_bias; // [M]
+  float* epi_tpart;      // [M, n_tiles, 2]
+  float* epi_hpart;      // [M, n_tiles, 2]
+  const uint32_t* epi_drop_bits;  // keep bits [M, epi_drop_words] or nullptr
+  int epi_drop_words;
+  float epi_drop_scale;
+  int epi_F;             // head width
+  int epi_elu;           // act = ELU, else identity
 };
 
 constexpr int kEpiStageBytes = 4 * 32 * 64;  // per epilogue warp: 32 rows x 64 bytes
@@ -129,6 +141,8 @@ __device__ __noinline__ void epilogue_staged(const GemmParams& p, uint8_t* stg, 
   const int rsub = lane >> 2, q_rd = lane & 3;
   constexpr int cols_per = BF16 ? 32 : 16;  // columns per 64-byte row piece
   constexpr int elems16 = BF16 ? 8 : 4;     // elements per 16-byte piece
+  float epi_t0 = 0.f, epi_t1 = 0.f, epi_h0 = 0.f, epi_h1 = 0.f, epi_b = 0.f;
+  if (!BF16 && p.epi_y && p.epi_bias && row0 + lane < p.M) epi_b = __ldg(p.epi_bias + row0 + lane);
   for (int c0 = 0; c0 < p.BN; c0 += cols_per) {
     uint32_t r[BF16 ? 32 : 16];
     const int width = min(cols_per, p.BN - c0);  // bf16: BN % 32 may be 16
@@ -149,6 +163,34 @@ __device__ __noinline__ void epilogue_staged(const GemmParams& p, uint8_t* stg, 
       tmem_ld16(taddr + c0, t16);
 #pragma unroll
       for (int v = 0; v < 16; ++v) r[v] = empty_k ? 0u : t16[v];
+      if (p.epi_y) {
+        // this lane holds dX[row, col .. col+15]; fold in act'(y), the dropout mask and the row sums of backward prep
+        const int row_me = row0 + lane;
+        const int colb = col0 + c0;
+        if (row_me < p.M && colb + 16 <= p.N) {
+          const float4* yp = reinterpret_cast<const float4*>(p.epi_y + static_cast<long long>(row_me) * p.N + colb);
+          float y[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 t4 = __ldg(yp + q);
+            y[4 * q] = t4.x; y[4 * q + 1] = t4.y; y[4 * q + 2] = t4.z; y[4 * q + 3] = t4.w;
+          }
+          uint32_t keep = 0xffffu;
+          if (p.epi_drop_bits)
+            keep = (__ldg(p.epi_drop_bits + static_cast<long long>(row_me) * p.epi_drop_words + (colb >> 5)) >> (colb & 31)) & 0xffffu;
+          const int split = (col0 / p.epi_F + 1) * p.epi_F;  // first column of the tile's second head
+#pragma unroll
+          for (int v = 0; v < 16; ++v) {
+            const float dx = __uint_as_float(r[v]);
+            const float gy = p.epi_elu ? (y[v] > 0.f ? dx : dx * expf(y[v])) : dx;
+            const float ms = p.epi_drop_bits ? (((keep >> v) & 1u) ? p.epi_drop_scale : 0.f) : 1.f;
+            const float gg = gy * ms;
+            const float tv = gy * (y[v] - epi_b * ms);
+            if (colb + v < split) { epi_t0 += tv; epi_h0 += gg; } else { epi_t1 += tv; epi_h1 += gg; }
+            r[v] = __float_as_uint(gg);
+          }
+        }
+      }
     }
     __syncwarp();  // the previous block has been read back by every lane
 #pragma unroll
@@ -170,6 +212,14 @@ __device__ __noinline__ void epilogue_staged(const GemmParams& p, uint8_t* stg, 
           *reinterpret_cast<uint4*>(p.d + static_cast<long long>(ks) * p.d_split_stride +
                                     static_cast<long long>(row) * p.ldd + col + q_rd * 4) = vv;
       }
+    }
+  }
+  if constexpr (!BF16) {
+    if (p.epi_y && row0 + lane < p.M) {
+      const int n_tiles = (p.N + p.BN - 1) / p.BN;
+      const long long o = (static_cast<long long>(row0 + lane) * n_tiles + col0 / p.BN) * 2;
+      p.epi_tpart[o] = epi_t0; p.epi_tpart[o + 1] = epi_t1;
+      p.epi_hpart[o] = epi_h0; p.epi_hpart[o + 1] = epi_h1;
     }
   }
 }
@@ -387,6 +437,24 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __re
   out[i] = s;
 }
 
+// t[j, h], hsum[j, h] from the per-tile partials of the fused prep epilogue, tiles in ascending order (fixed order)
+__global__ void prep_combine_kernel(const float* __restrict__ tpart, const float* __restrict__ hpart, float* __restrict__ t,
+                                    float* __restrict__ hsum, long long rows, int n_tiles, int BN, int F, int H) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * H) return;
+  const long long j = i / H;
+  const int h = static_cast<int>(i - j * H);
+  float ts = 0.f, hs = 0.f;
+  for (int tl = 0; tl < n_tiles; ++tl) {
+    const int h0 = (tl * BN) / F;  // head of the tile's first column; slot 1 is head h0 + 1
+    const long long o = (j * n_tiles + tl) * 2;
+    if (h0 == h) { ts += tpart[o]; hs += hpart[o]; }
+    else if (h0 + 1 == h) { ts += tpart[o + 1]; hs += hpart[o + 1]; }
+  }
+  t[i] = ts;
+  hsum[i] = hs;
+}
+
 // fp32 -> bf16 hi (+ lo residual) planes
 __global__ void split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
                                   __nv_bfloat16* __restrict__ lo, long long n) {
@@ -434,6 +502,10 @@ static int make_map(CUtensorMap* m, const void* base, long long rows, long long 
 }
 
 static int pick_bn(int N) {
+  if (const char* v = getenv("RELGAT_GEMM_BN")) {  // experiment knob: N tile (multiple of 16, <= 256)
+    const int bn = atoi(v);
+    if (bn >= 16 && bn <= 256 && bn % 16 == 0 && N > bn) return bn;
+  }
   if (N <= 256) return (N + 15) / 16 * 16;
   for (int bn = 256; bn >= 128; bn -= 16)
     if (N % bn == 0) return bn;
@@ -466,10 +538,21 @@ extern "C" long long relgat_gemm_workspace_bytes(int M, int N, int K, int a_mn, 
 //   a_mn == 0: A is [M, K] row-major (stride lda);  a_mn == 1: A is stored [K, M] row-major (stride lda)
 //   b_mn == 0: B is [N, K] row-major (stride ldb);  b_mn == 1: B is stored [K, N] row-major (stride ldb)
 //   a_lo / b_lo: residual planes of the fp32 split (both or neither); nullptr = plain bf16 GEMM
-extern "C" int relgat_gemm_bf16(const void* a_hi, const void* a_lo, long long lda, int a_mn,
-                                const void* b_hi, const void* b_lo, long long ldb, int b_mn,
-                                void* d_out, int d_is_bf16, long long ldd, int M, int N, int K, int splits_k,
-                                void* workspace, long long workspace_bytes, int sm_count, void* stream) {
+struct PrepEpilogue {
+  const float* y = nullptr;
+  const float* bias = nullptr;
+  float* tpart = nullptr;
+  float* hpart = nullptr;
+  const uint32_t* drop_bits = nullptr;
+  int drop_words = 0;
+  float drop_scale = 1.f;
+  int F = 0, elu = 0;
+};
+
+static int gemm_launch(const void* a_hi, const void* a_lo, long long lda, int a_mn,
+                       const void* b_hi, const void* b_lo, long long ldb, int b_mn,
+                       void* d_out, int d_is_bf16, long long ldd, int M, int N, int K, int splits_k,
+                       void* workspace, long long workspace_bytes, int sm_count, void* stream, const PrepEpilogue* epi) {
   if (!a_hi || !b_hi || !d_out || M <= 0 || N <= 0 || K <= 0 || splits_k < 1) return RG_ERR_ARG;
   if (d_is_bf16 && splits_k > 1) return RG_ERR_ARG;  // split-K partials are fp32
   float* d = d_is_bf16 ? nullptr : static_cast<float*>(d_out);
@@ -482,10 +565,6 @@ extern "C" int relgat_gemm_bf16(const void* a_hi, const void* a_lo, long long ld
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;
   p.BN = pick_bn(N);
-  if (const char* v = getenv("RELGAT_GEMM_BN")) {  // experiment knob: N tile (multiple of 16, <= 256)
-    const int bn = atoi(v);
-    if (bn >= 16 && bn <= 256 && bn % 16 == 0 && N > bn) p.BN = bn;
-  }
   p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
   p.split = a_lo ? 1 : 0;
   const int total_kb = (K + kBK - 1) / kBK;
@@ -502,6 +581,16 @@ extern "C" int relgat_gemm_bf16(const void* a_hi, const void* a_lo, long long ld
   p.staged = (N % piece == 0 && (splits_k > 1 ? N : ldd) % piece == 0 &&
               reinterpret_cast<uintptr_t>(splits_k > 1 ? workspace : d_out) % 16 == 0) ? 1 : 0;
   if (getenv("RELGAT_GEMM_DIRECT_EPILOGUE")) p.staged = 0;  // experiment knob: the old one-row-per-lane stores
+  if (epi) {
+    // the fused prep epilogue needs: fp32 output rows of width N (ldd == N), whole 16-column pieces, a tile inside
+    // at most two heads, no split-K
+    if (!p.staged || d_is_bf16 || splits_k != 1 || ldd != N || N % 16 != 0 || epi->F <= 0 || p.BN > epi->F ||
+        N % epi->F != 0 || !epi->y || !epi->tpart || !epi->hpart)
+      return RG_ERR_SHAPE;
+    p.epi_y = epi->y; p.epi_bias = epi->bias; p.epi_tpart = epi->tpart; p.epi_hpart = epi->hpart;
+    p.epi_drop_bits = epi->drop_bits; p.epi_drop_words = epi->drop_words; p.epi_drop_scale = epi->drop_scale;
+    p.epi_F = epi->F; p.epi_elu = epi->elu;
+  }
   const int smem_budget = 227 * 1024 - 2048 - (p.staged ? kEpiStageBytes : 0);
   int stages = smem_budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -548,4 +637,36 @@ extern "C" int relgat_gemm_bf16(const void* a_hi, const void* a_lo, long long ld
     return cuda_status(cudaGetLastError());
   }
   return RG_OK;
+}
+
+extern "C" int relgat_gemm_bf16(const void* a_hi, const void* a_lo, long long lda, int a_mn,
+                                const void* b_hi, const void* b_lo, long long ldb, int b_mn,
+                                void* d_out, int d_is_bf16, long long ldd, int M, int N, int K, int splits_k,
+                                void* workspace, long long workspace_bytes, int sm_count, void* stream) {
+  return gemm_launch(a_hi, a_lo, lda, a_mn, b_hi, b_lo, ldb, b_mn, d_out, d_is_bf16, ldd, M, N, K, splits_k, workspace,
+                     workspace_bytes, sm_count, stream, nullptr);
+}
+
+extern "C" int relgat_gemm_tile_n(int N) { return N > 0 ? pick_bn(N) : RG_ERR_ARG; }
+
+// dX GEMM (A = dP [M, K] planes, B = W^T [N, K] planes, both K-major) with the backward prep of the layer below fused
+// into its epilogue: G [M, N] = (A·B^T) * act'(y) * m is written instead of dX, t / hsum [M, H] follow from per-tile
+// partials (tpart / hpart: float [M, n_tiles, 2] scratch, n_tiles = ceil(N / relgat_gemm_tile_n(N))).
+extern "C" int relgat_gemm_dx_prep(const void* a_hi, const void* a_lo, long long lda, const void* b_hi, const void* b_lo,
+                                   long long ldb, float* G, int M, int N, int K, const float* y, const float* bias,
+                                   const unsigned int* drop_bits, int drop_words, float drop_scale, int H, int F,
+                                   int apply_elu, float* tpart, float* hpart, float* t, float* hsum, int sm_count,
+                                   void* stream) {
+  if (!G || !y || !tpart || !hpart || !t || !hsum || H <= 0 || F <= 0 || N != H * F) return RG_ERR_ARG;
+  if (drop_bits && drop_words * 32 < N) return RG_ERR_ARG;
+  PrepEpilogue e;
+  e.y = y; e.bias = bias; e.tpart = tpart; e.hpart = hpart; e.drop_bits = drop_bits; e.drop_words = drop_words;
+  e.drop_scale = drop_scale; e.F = F; e.elu = apply_elu;
+  int rc = gemm_launch(a_hi, a_lo, lda, 0, b_hi, b_lo, ldb, 0, G, 0, N, M, N, K, 1, nullptr, 0, sm_count, stream, &e);
+  if (rc != RG_OK) return rc;
+  const int bn = pick_bn(N);
+  const long long total = static_cast<long long>(M) * H;
+  prep_combine_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      tpart, hpart, t, hsum, M, (N + bn - 1) / bn, bn, F, H);
+  return cuda_status(cudaGetLastError());
 }

@@ -20,6 +20,8 @@ PRECISIONS = ("fp32", "bf16")
 # dA through the logit-table gradient (dS columns beside dP, widened dW GEMM) instead of the by-relation gather pass
 # (SURVEY.md A.3); RELGAT_DS=0 restores the by-relation kernel (kept for the partitioned path and for A/B timing)
 USE_DS = os.environ.get("RELGAT_DS", "1") != "0"
+# backward prep of a hidden layer fused into the epilogue of the dX GEMM above it (RELGAT_FUSE_PREP=0: separate kernel)
+FUSE_PREP = os.environ.get("RELGAT_FUSE_PREP", "1") != "0"
 
 _SIDE_STREAMS = {}
 
@@ -194,13 +196,19 @@ class RelGATStackFunction(torch.autograd.Function):
             nz_rows = sparse_rows_of(grad_out) if dY is grad_out else None
             owned = False
         dX = None
+        prepped = None  # (G, t, hsum) of layer l when the dX GEMM of layer l+1 produced them in its epilogue
+        fuse_prep = USE_DS and FUSE_PREP and with_lo and ops.gemm_dx_prep_supported(C, F)
         for l in reversed(range(L)):
             s = ctx.saved[l]
             dl = s["drop"]
-            # fp32 storage: G aliases dY and only the batch rows are touched; bf16 storage writes a dense bf16 G
-            G, t, hsum = ops.edge_bwd_prep(dY, s["out"], s["bias"], H, F, apply_elu=(l < L - 1), inplace=owned,
-                                           g_bf16=not with_lo, nonzero_rows=nz_rows if l == L - 1 else None,
-                                           feat_drop=dl.feat if dl else None)
+            if prepped is not None:
+                G, t, hsum = prepped
+                prepped = None
+            else:
+                # fp32 storage: G aliases dY and only the batch rows are touched; bf16 storage writes a dense bf16 G
+                G, t, hsum = ops.edge_bwd_prep(dY, s["out"], s["bias"], H, F, apply_elu=(l < L - 1), inplace=owned,
+                                               g_bf16=not with_lo, nonzero_rows=nz_rows if l == L - 1 else None,
+                                               feat_drop=dl.feat if dl else None)
             _, dPp, dz = ops.edge_bwd_src(s["P"], G, s["A"], s["z"], s["minv"], t, g, H, F,
                                           want_fp32=False, want_planes=True, planes_lo=with_lo,
                                           edge_drop=dl.edge if dl else None, want_ds=USE_DS)
@@ -221,7 +229,15 @@ class RelGATStackFunction(torch.autograd.Function):
                 dW_ext = ops.gemm(dPp, True, s["xp"], True, Wd, d_in, N, splits_k=splits)
                 dw_ready = torch.cuda.Event()
                 dw_ready.record(main)
-                if l > 0 or ctx.x0_needs_grad:
+                if l > 0 and fuse_prep:
+                    # dX never reaches memory: the GEMM's epilogue applies ELU'(y), the dropout mask and the row sums
+                    # of the layer below (what edge_bwd_prep would do in a second pass over dX and y)
+                    below = ctx.saved[l - 1]
+                    bd = below["drop"]
+                    prepped = ops.gemm_dx_prep(dP_c, s["WTp"], N, d_in, C, below["out"], below["bias"], H, F,
+                                               apply_elu=True, feat_drop=bd.feat if bd else None)
+                    dX = prepped[0]
+                elif l > 0 or ctx.x0_needs_grad:
                     dX = ops.gemm(dP_c, False, s["WTp"], False, N, d_in, C)
                 side.wait_event(dw_ready)
                 with torch.cuda.stream(side):  # small tail work beside the next layer's kernels

@@ -131,6 +131,43 @@ def gemm(a: Planes, a_mn: bool, b: Planes, b_mn: bool, M: int, N: int, K: int,
     return out
 
 
+def gemm_dx_prep_supported(N: int, F: int) -> bool:
+    """The fused prep epilogue needs an N tile inside at most two heads (tile width <= F) and 16-column pieces."""
+    return N % 16 == 0 and N % F == 0 and int(_lib.load().relgat_gemm_tile_n(int(N))) <= F
+
+
+def gemm_dx_prep(dP: Planes, WT: Planes, M: int, N: int, K: int, y: torch.Tensor, bias: torch.Tensor, H: int, F: int,
+                 apply_elu: bool, feat_drop: Optional["DropMask"] = None):
+    """dX = dP · W with the backward prep of the layer below fused into the GEMM epilogue.
+    Returns (G [M, N] = dX * act'(y) * mask, t [M, H], hsum [M, H]) — what ``edge_bwd_prep(dX, y, bias, ...)`` returns,
+    without materialising dX (saves one [M, N] write and two [M, N] reads per hidden layer)."""
+    a_hi, a_lo = dP
+    b_hi, b_lo = WT
+    _lib.require_cuda(a_hi, b_hi, y, bias)
+    if tuple(a_hi.shape) != (M, K) or tuple(b_hi.shape) != (N, K) or (a_lo is None) != (b_lo is None):
+        raise ValueError("gemm_dx_prep: dP planes [M, K], W^T planes [N, K] expected")
+    y, bias = _f32c(y, "y"), _f32c(bias, "bias")
+    if tuple(y.shape) != (M, N) or N != H * F or bias.numel() != M:
+        raise ValueError("gemm_dx_prep: y [M, H*F] and bias [M] expected")
+    a_hi, a_lo, b_hi, b_lo = _tma_ready(a_hi), _tma_ready(a_lo), _tma_ready(b_hi), _tma_ready(b_lo)
+    dev = y.device
+    lib = _lib.load()
+    n_tiles = -(-N // int(lib.relgat_gemm_tile_n(N)))
+    G = torch.empty((M, N), dtype=torch.float32, device=dev)
+    tpart = torch.empty((M, n_tiles, 2), dtype=torch.float32, device=dev)
+    hpart = torch.empty((M, n_tiles, 2), dtype=torch.float32, device=dev)
+    t = torch.empty((M, H), dtype=torch.float32, device=dev)
+    hsum = torch.empty((M, H), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.relgat_gemm_dx_prep(_lib.ptr(a_hi), _lib.ptr(a_lo), a_hi.stride(0), _lib.ptr(b_hi), _lib.ptr(b_lo),
+                                     b_hi.stride(0), _lib.ptr(G), M, N, K, _lib.ptr(y), _lib.ptr(bias),
+                                     *_feat_mask_args(feat_drop, M, N), H, F, int(apply_elu), _lib.ptr(tpart),
+                                     _lib.ptr(hpart), _lib.ptr(t), _lib.ptr(hsum), sm_count(dev), _stream(y))
+    _lib.check(rc, "relgat_gemm_dx_prep")
+    _count(2)
+    return G, t, hsum
+
+
 def pick_splits_k(M: int, N: int, K: int, device) -> int:
     """Split-K factor for GEMMs with few output tiles and a long reduction (the dW GEMMs): the one
     (<= 16) that fills the persistent grid's waves best, smaller factors winning ties."""

@@ -361,3 +361,28 @@ def test_config2_size_layer_sampled_rows_and_gradients(dev):
     assert rel_err(torch.stack([a.grad for a in layer.attn_vec]).cpu().numpy(), dA) < FP32_TOL
     assert rel_err(layer.rel_bias.grad.cpu().numpy(), dbeta) < FP32_TOL
     assert rel_err(torch.cat([p.weight.grad for p in layer.proj]).cpu().numpy(), dW) < FP32_TOL
+
+
+@pytest.mark.parametrize("with_drop", [False, True])
+def test_dx_gemm_with_fused_backward_prep(dev, with_drop):
+    """relgat_gemm_dx_prep: the dX GEMM whose epilogue applies ELU'(y), the dropout mask and the per-head row sums of
+    the layer below, against the unfused pair (GEMM, then relgat_layer_bwd_prep on its output)."""
+    g = torch.Generator(device=dev).manual_seed(2)
+    M, H, F, K = 1000, 4, 200, 800
+    N = H * F
+    assert ops.gemm_dx_prep_supported(N, F) and not ops.gemm_dx_prep_supported(64, 16)
+    dP = ops.split_bf16(torch.randn((M, K), generator=g, device=dev), True)
+    WT = ops.split_bf16(torch.randn((N, K), generator=g, device=dev) / K ** 0.5, True)
+    y = torch.randn((M, N), generator=g, device=dev)
+    bias = torch.randn((M,), generator=g, device=dev)
+    drop = ops.DropMask.feature_mask(torch.rand((M, N), generator=g, device=dev) >= 0.3, 0.3) if with_drop else None
+    if with_drop:  # what the forward would have stored: post-dropout rows
+        cols = torch.arange(N, device=dev)
+        keep = ((drop.bits[:, cols // 32] >> (cols % 32)) & 1).bool()
+        y = torch.where(keep, y, torch.zeros_like(y))
+    G, t, hsum = ops.gemm_dx_prep(dP, WT, M, N, K, y, bias, H, F, apply_elu=True, feat_drop=drop)
+    dX = ops.gemm(dP, False, WT, False, M, N, K)
+    G2, t2, hsum2 = ops.edge_bwd_prep(dX, y, bias, H, F, apply_elu=True, feat_drop=drop)
+    assert rel_err(G.cpu().numpy(), G2.cpu().numpy()) < 1e-6
+    assert rel_err(t.cpu().numpy(), t2.cpu().numpy()) < 1e-5
+    assert rel_err(hsum.cpu().numpy(), hsum2.cpu().numpy()) < 1e-5
