@@ -440,22 +440,30 @@ def main():
         opt.step()
         return loss
 
-    def timed(fn, steps):
+    step_stats = {}
+
+    def timed(fn, steps, tag=None):
+        """Mean step time over EXACTLY ``steps`` steps (one pair of CUDA events around the whole region); the events
+        recorded after every step only feed the per-step spread reported beside it."""
         torch.cuda.synchronize()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        marks[0].record()
         for i in range(steps):
             fn(i)
-        e.record()
+            marks[i + 1].record()
         torch.cuda.synchronize()
-        return s.elapsed_time(e) / max(steps, 1)
+        if tag and steps:
+            per = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(steps))
+            step_stats[tag] = {"min_ms": round(per[0], 3), "median_ms": round(per[len(per) // 2], 3),
+                               "max_ms": round(per[-1], 3)}
+        return marks[0].elapsed_time(marks[-1]) / max(steps, 1)
 
     warm = max(args.warmup, 3)
     for i in range(warm):
         train_step(*dev_batches[i % n_pool])
     ops.LAUNCHES = 0
     with ClockSampler(local_rank) as clocks:
-        ms = timed(lambda i: train_step(*dev_batches[i % n_pool]), args.steps)
+        ms = timed(lambda i: train_step(*dev_batches[i % n_pool]), args.steps, "value")
     launches = ops.LAUNCHES
 
     # end to end through the public API: ids come from pinned host memory, the loss goes back
@@ -464,7 +472,7 @@ def main():
         src, rel, dst = (t.to(dev, non_blocking=True) for t in hb)
         return float(train_step(src, rel, dst).item())
     e2e_step(0)
-    ms_e2e = timed(e2e_step, args.steps)
+    ms_e2e = timed(e2e_step, args.steps, "e2e")
     h2d = 3 * b * (1 + k) * 8
 
     # per-kernel device times (extra steps, CUDA events around every C-ABI call on the launch stream)
@@ -557,7 +565,7 @@ def main():
         "precision_note": ("fp32 storage; tensor-core GEMMs on bf16 hi/lo splits (3 passes, ~fp32 accuracy)"
                            if args.precision == "fp32" else
                            "bf16 storage of P / G / dP rows; single-pass bf16 tensor-core GEMMs; fp32 accumulate"),
-        "layer_edges_per_sec": cfg["L"] * E / (ms * 1e-3),
+        "layer_edges_per_sec": cfg["L"] * E / (ms * 1e-3), "per_step_spread": step_stats,
         "clocks": clocks.summary(),
         "e2e": {"value": E / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},

@@ -250,6 +250,14 @@ __device__ __forceinline__ float head_sum(float x, int lph) {
   return x;
 }
 
+// same with a compile-time lane count: only log2(LPH) shuffles are issued
+template <int LPH>
+__device__ __forceinline__ float head_sum_c(float x) {
+#pragma unroll
+  for (int o = LPH / 2; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
 __device__ __forceinline__ float warp_sum(float x) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);

@@ -74,7 +74,8 @@ __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : fast_exp(x
 // grid = (CTAs per head-group, head-groups); every CTA is persistent and owns one head-group, so
 // it stages only that group's attention vectors (ncu on the first version showed the per-edge
 // A-row reads missing L1 ~40-70% of the time and doubling the L2->SM traffic).
-template <typename T, int V, int KV, bool ASM, int NP, int LPHC>
+// DROP: a dropout mask is active (training); false compiles every mask test out of the hot loop
+template <typename T, int V, int KV, bool ASM, int NP, int LPHC, bool DROP>
 __global__ void __launch_bounds__((NP == 2 ? kFwdWarps : kFwdWarpsSingle) * 32, 1)
 edge_fwd_kernel(const FwdArgs<T, V> a) {
   constexpr int kWarps = NP == 2 ? kFwdWarps : kFwdWarpsSingle;
@@ -162,7 +163,7 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
     const float sc = __expf(m - mn);                                                               \
     const float w0 = __expf(ev - mn);                                                              \
     l = fmaf(l, sc, w0); /* the denominator counts every edge; attention dropout scales the kept terms */ \
-    const float w = a.edge_bits ? w0 * keep_scale1(a.edge_bits, static_cast<long long>(e_) * a.H + lm.hh, a.edge_scale) : w0; \
+    const float w = (DROP && a.edge_bits) ? w0 * keep_scale1(a.edge_bits, static_cast<long long>(e_) * a.H + lm.hh, a.edge_scale) : w0; \
     _Pragma("unroll") for (int k = 0; k < KV; ++k) {                                               \
       _Pragma("unroll") for (int v = 0; v < V; ++v) acc[k][v] = fmaf(acc[k][v], sc, w * x_[k][v]); \
     }                                                                                              \
@@ -241,8 +242,8 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
         }
 #pragma unroll
         for (int v = 0; v < V; ++v) { d0 += s0[v]; d1 += s1[v]; }
-        d0 = head_sum(d0, lm.lph);
-        d1 = head_sum(d1, lm.lph);
+        if constexpr (LPHC > 0) { d0 = head_sum_c<LPHC>(d0); d1 = head_sum_c<LPHC>(d1); }
+        else { d0 = head_sum(d0, lm.lph); d1 = head_sum(d1, lm.lph); }
       }
       // consume the pair; destinations are finalised (ONE code site) whenever the edge cursor
       // reaches the end of the current segment, including empty and trailing destinations
@@ -276,7 +277,7 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
                 o[v] = fmaf(acc[k][v], inv, bsum);  // bias on every head/channel, :313-318
                 acc[k][v] = 0.f;
               }
-              if (a.drop_bits) {  // feature dropout on the finished row (layer.py:321-322), before the activation
+              if (DROP && a.drop_bits) {  // feature dropout on the finished row (layer.py:321-322), before the activation
                 float ms[V];
                 keep_scale<V>(a.drop_bits + static_cast<long long>(j) * a.drop_words, lane_off + k * kstride, a.drop_scale, ms);
 #pragma unroll
@@ -451,8 +452,8 @@ edge_fwd_merge_kernel(const FwdArgs<T, V> a, const int* __restrict__ long_node,
   }
 }
 
-template <typename T, int V, int KV, int NP, int LPHC>
-static int launch_fwd_np(FwdArgs<T, V> a, int sm_count, cudaStream_t stream) {
+template <typename T, int V, int KV, int NP, int LPHC, bool DROP>
+static int launch_fwd_drop(FwdArgs<T, V> a, int sm_count, cudaStream_t stream) {
   constexpr int kWarps = NP == 2 ? kFwdWarps : kFwdWarpsSingle;
   const int groups = a.H / a.hg;
   if (sm_count <= 0) sm_count = 148;
@@ -469,14 +470,20 @@ static int launch_fwd_np(FwdArgs<T, V> a, int sm_count, cudaStream_t stream) {
     if (a.pf_dist > 30) a.pf_dist = 30;
   }
   if (a.a_in_smem) {
-    cudaError_t e = cudaFuncSetAttribute(edge_fwd_kernel<T, V, KV, true, NP, LPHC>,
+    cudaError_t e = cudaFuncSetAttribute(edge_fwd_kernel<T, V, KV, true, NP, LPHC, DROP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudgetA));
     if (e != cudaSuccess) return cuda_status(e);
-    edge_fwd_kernel<T, V, KV, true, NP, LPHC><<<dim3(ctas, groups), kWarps * 32, a_bytes, stream>>>(a);
+    edge_fwd_kernel<T, V, KV, true, NP, LPHC, DROP><<<dim3(ctas, groups), kWarps * 32, a_bytes, stream>>>(a);
   } else {
-    edge_fwd_kernel<T, V, KV, false, NP, LPHC><<<dim3(ctas, groups), kWarps * 32, 0, stream>>>(a);
+    edge_fwd_kernel<T, V, KV, false, NP, LPHC, DROP><<<dim3(ctas, groups), kWarps * 32, 0, stream>>>(a);
   }
   return cuda_status(cudaGetLastError());
+}
+
+template <typename T, int V, int KV, int NP, int LPHC>
+static int launch_fwd_np(const FwdArgs<T, V>& a, int sm_count, cudaStream_t stream) {
+  if (a.drop_bits || a.edge_bits) return launch_fwd_drop<T, V, KV, NP, LPHC, true>(a, sm_count, stream);
+  return launch_fwd_drop<T, V, KV, NP, LPHC, false>(a, sm_count, stream);
 }
 
 template <typename T, int V, int KV>

@@ -22,6 +22,8 @@ PRECISIONS = ("fp32", "bf16")
 USE_DS = os.environ.get("RELGAT_DS", "1") != "0"
 # backward prep of a hidden layer fused into the epilogue of the dX GEMM above it (RELGAT_FUSE_PREP=0: separate kernel)
 FUSE_PREP = os.environ.get("RELGAT_FUSE_PREP", "1") != "0"
+# the small tail of the dS path (dA = T W^T, dbeta) on the side stream (1) or in line on the main stream (0)
+TAIL_ON_SIDE = os.environ.get("RELGAT_TAIL_SIDE", "1") != "0"
 
 _SIDE_STREAMS = {}
 
@@ -239,21 +241,27 @@ class RelGATStackFunction(torch.autograd.Function):
                     dX = prepped[0]
                 elif l > 0 or ctx.x0_needs_grad:
                     dX = ops.gemm(dP_c, False, s["WTp"], False, N, d_in, C)
-                side.wait_event(dw_ready)
-                with torch.cuda.stream(side):  # small tail work beside the next layer's kernels
+                def tail():
                     Tp = ops.split_bf16(dW_ext[C:C + HR].contiguous(), with_lo)
                     dA_full = ops.gemm(Tp, False, s["Wp"], False, HR, C, d_in)
-                    dA = torch.stack([dA_full[h * g.R:(h + 1) * g.R, h * F:(h + 1) * F] for h in range(H)])
-                    dbeta = ops.edge_bwd_beta(hsum, g, H) if s["has_beta"] else None
-                for tns in (dW_ext, hsum):
-                    tns.record_stream(side)
-                for tns in (dA, dbeta):  # allocated on the side stream, consumed by the optimizer on the main one
-                    if tns is not None:
-                        tns.record_stream(main)
+                    dA_ = torch.stack([dA_full[h * g.R:(h + 1) * g.R, h * F:(h + 1) * F] for h in range(H)])
+                    return dA_, (ops.edge_bwd_beta(hsum, g, H) if s["has_beta"] else None)
+
+                if TAIL_ON_SIDE:
+                    side.wait_event(dw_ready)
+                    with torch.cuda.stream(side):  # small tail work beside the next layer's kernels
+                        dA, dbeta = tail()
+                    for tns in (dW_ext, hsum):
+                        tns.record_stream(side)
+                    for tns in (dA, dbeta):  # allocated on the side stream, consumed by the optimizer on the main one
+                        if tns is not None:
+                            tns.record_stream(main)
+                else:
+                    dA, dbeta = tail()
                 grads[3 * l], grads[3 * l + 1], grads[3 * l + 2] = dW_ext[:C], dA, dbeta
                 if l > 0 or ctx.x0_needs_grad:
                     dY, owned = dX, True
-                if l == 0:
+                if l == 0 and TAIL_ON_SIDE:
                     main.wait_stream(side)
                 del G, dPp, dz
                 continue
