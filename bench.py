@@ -112,7 +112,7 @@ class ClockSampler:
 class KernelProfiler:
     NAMES = ["split_bf16", "gemm", "edge_fwd", "edge_bwd_prep", "edge_bwd_src", "edge_bwd_rel", "score_fwd",
              "score_bwd", "index_add_sorted", "margin_loss", "rank_loss", "recon_loss", "zero_rows", "pull_rows",
-             "edge_bwd_beta"]
+             "edge_bwd_beta", "gemm_dx_prep"]
 
     def __init__(self):
         from relgat_projector_b200 import ops
@@ -132,6 +132,8 @@ class KernelProfiler:
             tag = name
             if name == "gemm":
                 tag = f"gemm[M={a[4]},N={a[5]},K={a[6]},{'mn' if a[1] else 'k'}{'mn' if a[3] else 'k'}]"
+            if name == "gemm_dx_prep":
+                tag = f"gemm[M={a[2]},N={a[3]},K={a[4]},kk+prep]"
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             out = fn(*a, **kw)
@@ -362,6 +364,9 @@ def main():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--exchange", default="peer", choices=["peer", "halo", "allgather"],
                     help="multi-GPU only: peer tables read over NVLink (default), or an NCCL exchange of halo / all rows")
+    ap.add_argument("--halo", default="bf16", choices=["bf16", "fp32"],
+                    help="multi-GPU, peer tables: halo rows cross NVLink rounded to bf16 (default; half the link bytes, "
+                         "stated tolerance 2e-2) or as fp32 (results equal to one GPU up to summation order)")
     ap.add_argument("--locality", type=float, default=0.0,
                     help="multi-GPU supplementary runs: fraction of edges whose head is drawn from the tail's node block "
                          "(default 0: uniformly random graph, the headline workload)")
@@ -407,7 +412,11 @@ def main():
         raise RuntimeError("bench.py (impl=ours) needs a CUDA device: there is no CPU fallback")
     if world > 1:
         from relgat_projector_b200 import dist as RD  # destination-range partitioned path
-        return RD.bench_main(args, cfg, rank, world, local_rank, METRIC, UNIT, load_peaks, ClockSampler)
+        cpu_fn = None
+        if not args.no_cpu_baseline and reference_installed():  # rank 0, bounded sample of the per-GPU workload
+            cpu_fn = lambda: run_cpu_reference(cfg, steps=1, scale=CPU_BASELINE_SCALE if cfg["N"] >= 100_000 else 1,  # noqa: E731
+                                               budget_s=30.0)
+        return RD.bench_main(args, cfg, rank, world, local_rank, METRIC, UNIT, load_peaks, ClockSampler, cpu_fn=cpu_fn)
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -494,7 +503,7 @@ def main():
             ent["algorithmic_bytes"] = int(bytes_)
             ent["gbs"] = round(bytes_ / (d["avg_ms"] * 1e-3) / 1e9, 1)
             ent["frac_hbm"] = round(ent["gbs"] / peaks["hbm_gbs"], 4)
-        elif d["kernel"] == "gemm":
+        elif d["kernel"] in ("gemm", "gemm_dx_prep"):
             dims = dict(kv.split("=") for kv in tag[tag.index("[") + 1:tag.rindex(",")].split(","))
             flops = 2.0 * int(dims["M"]) * int(dims["N"]) * int(dims["K"]) * (3 if args.precision == "fp32" else 1)
             ent["tensor_flops"] = flops

@@ -254,6 +254,10 @@ int relgat_peer_table_last_driver_error(void);
  * Rows with equal out_ids must carry equal data (the batch may name a node twice). */
 int relgat_pull_rows(const float* table, long long ld, const long long* ids, const long long* out_ids,
                      long long n, int D, float* out, long long ldo, int sm_count, void* stream);
+/* same pull from a table whose rows the owner exported rounded to bf16 (half the NVLink bytes): rows are widened to
+ * fp32 while they are stored (D % 8 == 0).  Stated tolerance of a step with bf16 halo rows: 2e-2 relative. */
+int relgat_pull_rows_bf16(const void* table, long long ld, const long long* ids, const long long* out_ids,
+                          long long n, int D, float* out, long long ldo, int sm_count, void* stream);
 
 #ifdef __cplusplus
 }

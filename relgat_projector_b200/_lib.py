@@ -61,9 +61,10 @@ SIGNATURES = {
     "relgat_peer_table_unmap": (_I, [_P, _I, c_ulonglong, c_ulonglong]),
     "relgat_peer_table_last_driver_error": (_I, []),
     "relgat_pull_rows": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _I, _P]),
+    "relgat_pull_rows_bf16": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _I, _P]),
 }
 
-ABI_VERSION = 5  # bumped whenever a signature in include/relgat_b200.h changes
+ABI_VERSION = 6  # bumped whenever a signature in include/relgat_b200.h changes
 _lib = None
 
 

@@ -247,16 +247,27 @@ __global__ void __launch_bounds__((PIPE ? kSrcWarpsPipe : kSrcWarps) * 32, 1) bw
     if (DS && cur >= 0) { /* dS columns of the source being closed, then clear the slots */    \
       __syncwarp();                                                                            \
       const long long drow = (part >= 0 ? static_cast<long long>(part) : static_cast<long long>(n_lo + cur)) * a.ldo + ds_col0; \
-      for (int i = lane; i < ds_n; i += 32) {                                                  \
-        const float dv = ds_sm[i];                                                             \
-        ds_sm[i] = 0.f;                                                                        \
-        if (part >= 0) a.part_acc[drow + i] = dv;                                              \
-        else {                                                                                 \
-          if (a.dP) a.dP[drow + i] = dv;                                                       \
-          if (a.dP_hi) {                                                                       \
-            const float hv = bf16_round(dv);                                                   \
-            a.dP_hi[drow + i] = __float2bfloat16_rn(hv);                                       \
-            if (a.dP_lo) a.dP_lo[drow + i] = __float2bfloat16_rn(dv - hv);                     \
+      if (part < 0 && !a.dP && a.dP_hi && (ds_n & 7) == 0 && (ds_col0 & 7) == 0 && (a.ldo & 7) == 0) { \
+        /* planes only (the training path): 8 values -> one 16-byte store per plane */          \
+        for (int i = lane * 8; i < ds_n; i += 256) {                                           \
+          float dv[8];                                                                         \
+          RowVec<float, 8>::load_shared(ds_sm + i, dv);                                        \
+          *reinterpret_cast<float4*>(ds_sm + i) = make_float4(0.f, 0.f, 0.f, 0.f);             \
+          *reinterpret_cast<float4*>(ds_sm + i + 4) = make_float4(0.f, 0.f, 0.f, 0.f);         \
+          store_split_bf16<8>(a.dP_hi + drow + i, a.dP_lo ? a.dP_lo + drow + i : nullptr, dv);  \
+        }                                                                                      \
+      } else {                                                                                 \
+        for (int i = lane; i < ds_n; i += 32) {                                                \
+          const float dv = ds_sm[i];                                                           \
+          ds_sm[i] = 0.f;                                                                      \
+          if (part >= 0) a.part_acc[drow + i] = dv;                                            \
+          else {                                                                               \
+            if (a.dP) a.dP[drow + i] = dv;                                                     \
+            if (a.dP_hi) {                                                                     \
+              const float hv = bf16_round(dv);                                                 \
+              a.dP_hi[drow + i] = __float2bfloat16_rn(hv);                                     \
+              if (a.dP_lo) a.dP_lo[drow + i] = __float2bfloat16_rn(dv - hv);                   \
+            }                                                                                  \
           }                                                                                    \
         }                                                                                      \
       }                                                                                        \

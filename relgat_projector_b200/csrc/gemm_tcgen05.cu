@@ -53,6 +53,7 @@ struct GemmParams {
   float epi_drop_scale;
   int epi_F;             // head width
   int epi_elu;           // act = ELU, else identity
+  int dbg_epilogue;      // experiments (RELGAT_GEMM_EPI): 0 normal, 1 = no global stores, 2 = no epilogue work at all
 };
 
 constexpr int kEpiStageBytes = 4 * 32 * 64;  // per epilogue warp: 32 rows x 64 bytes
@@ -137,12 +138,18 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
 // by-relation edge kernel runs beside the dW GEMM and needs the register file's other half).
 template <bool BF16>
 __device__ __noinline__ void epilogue_staged(const GemmParams& p, uint8_t* stg, uint32_t taddr, int row0, int col0,
-                                             int ks, bool empty_k, int lane) {
+                                             int ks, bool empty_k, int lane, int pf_row0, int pf_col0) {
   const int rsub = lane >> 2, q_rd = lane & 3;
   constexpr int cols_per = BF16 ? 32 : 16;  // columns per 64-byte row piece
   constexpr int elems16 = BF16 ? 8 : 4;     // elements per 16-byte piece
   float epi_t0 = 0.f, epi_t1 = 0.f, epi_h0 = 0.f, epi_h1 = 0.f, epi_b = 0.f;
   if (!BF16 && p.epi_y && p.epi_bias && row0 + lane < p.M) epi_b = __ldg(p.epi_bias + row0 + lane);
+  if (!BF16 && p.epi_y && pf_row0 >= 0 && pf_row0 + lane < p.M) {
+    // the y rows of this CTA's NEXT tile: pull them into L2 now (one row piece of BN floats per lane), so that the
+    // per-chunk loads below pay an L2 hit instead of a DRAM round trip each
+    const char* yl = reinterpret_cast<const char*>(p.epi_y + static_cast<long long>(pf_row0 + lane) * p.N + pf_col0);
+    for (int b = 0; b < p.BN * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(yl + b));
+  }
   for (int c0 = 0; c0 < p.BN; c0 += cols_per) {
     uint32_t r[BF16 ? 32 : 16];
     const int width = min(cols_per, p.BN - c0);  // bf16: BN % 32 may be 16
@@ -159,22 +166,25 @@ __device__ __noinline__ void epilogue_staged(const GemmParams& p, uint8_t* stg, 
       for (int v = 0; v < 16; ++v)
         r[v] = empty_k ? 0u : pack_bf16x2(__uint_as_float(r[2 * v]), __uint_as_float(r[2 * v + 1]));
     } else {
+      const int row_me = row0 + lane;
+      const int colb = col0 + c0;
+      const bool epi_on = p.epi_y && row_me < p.M && colb + 16 <= p.N;
+      float y[16];
+      if (epi_on) {  // issued ahead of the tensor-memory load: both latencies overlap
+        const float4* yp = reinterpret_cast<const float4*>(p.epi_y + static_cast<long long>(row_me) * p.N + colb);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 t4 = __ldg(yp + q);
+          y[4 * q] = t4.x; y[4 * q + 1] = t4.y; y[4 * q + 2] = t4.z; y[4 * q + 3] = t4.w;
+        }
+      }
       uint32_t t16[32];
       tmem_ld16(taddr + c0, t16);
 #pragma unroll
       for (int v = 0; v < 16; ++v) r[v] = empty_k ? 0u : t16[v];
       if (p.epi_y) {
         // this lane holds dX[row, col .. col+15]; fold in act'(y), the dropout mask and the row sums of backward prep
-        const int row_me = row0 + lane;
-        const int colb = col0 + c0;
-        if (row_me < p.M && colb + 16 <= p.N) {
-          const float4* yp = reinterpret_cast<const float4*>(p.epi_y + static_cast<long long>(row_me) * p.N + colb);
-          float y[16];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 t4 = __ldg(yp + q);
-            y[4 * q] = t4.x; y[4 * q + 1] = t4.y; y[4 * q + 2] = t4.z; y[4 * q + 3] = t4.w;
-          }
+        if (epi_on) {
           uint32_t keep = 0xffffu;
           if (p.epi_drop_bits)
             keep = (__ldg(p.epi_drop_bits + static_cast<long long>(row_me) * p.epi_drop_words + (colb >> 5)) >> (colb & 31)) & 0xffffu;
@@ -205,7 +215,7 @@ __device__ __noinline__ void epilogue_staged(const GemmParams& p, uint8_t* stg, 
       const int rl = 8 * j + rsub;
       const int row = row0 + rl;
       const uint4 vv = *reinterpret_cast<const uint4*>(stg + rl * 64 + ((q_rd ^ ((rl >> 1) & 3)) << 4));
-      if (row < p.M && piece_ok) {
+      if (row < p.M && piece_ok && p.dbg_epilogue != 1) {
         if constexpr (BF16)
           *reinterpret_cast<uint4*>(p.d_bf16 + static_cast<long long>(row) * p.ldd + col + q_rd * 8) = vv;
         else
@@ -362,10 +372,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
       mbar_wait(&tmem_full[acc], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(ew * 32) << 16);
-      if (p.staged) {
+      if (p.dbg_epilogue == 2) {
+        // measurement only: hand the accumulator straight back (mainloop-only time)
+      } else if (p.staged) {
         uint8_t* stg = smem + static_cast<size_t>(p.stages) * stage_bytes + ew * (32 * 64);
-        if (p.d_bf16) epilogue_staged<true>(p, stg, taddr, m_tile * kBM + ew * 32, n_tile * p.BN, ks, empty_k, lane);
-        else epilogue_staged<false>(p, stg, taddr, m_tile * kBM + ew * 32, n_tile * p.BN, ks, empty_k, lane);
+        int pf_row0 = -1, pf_col0 = 0;
+        if (p.epi_y && u + gridDim.x < units) {
+          const long long un = u + gridDim.x;
+          pf_row0 = static_cast<int>((un / nt) % mt) * kBM + ew * 32;
+          pf_col0 = static_cast<int>(un % nt) * p.BN;
+        }
+        if (p.d_bf16) epilogue_staged<true>(p, stg, taddr, m_tile * kBM + ew * 32, n_tile * p.BN, ks, empty_k, lane, -1, 0);
+        else epilogue_staged<false>(p, stg, taddr, m_tile * kBM + ew * 32, n_tile * p.BN, ks, empty_k, lane, pf_row0, pf_col0);
       } else {
       const int row = m_tile * kBM + ew * 32 + lane;
       float* drow = p.d ? p.d + static_cast<long long>(ks) * p.d_split_stride + static_cast<long long>(row) * p.ldd
@@ -581,6 +599,7 @@ static int gemm_launch(const void* a_hi, const void* a_lo, long long lda, int a_
   p.staged = (N % piece == 0 && (splits_k > 1 ? N : ldd) % piece == 0 &&
               reinterpret_cast<uintptr_t>(splits_k > 1 ? workspace : d_out) % 16 == 0) ? 1 : 0;
   if (getenv("RELGAT_GEMM_DIRECT_EPILOGUE")) p.staged = 0;  // experiment knob: the old one-row-per-lane stores
+  if (const char* v = getenv("RELGAT_GEMM_EPI")) p.dbg_epilogue = atoi(v);  // measurement knob, results are wrong
   if (epi) {
     // the fused prep epilogue needs: fp32 output rows of width N (ldd == N), whole 16-column pieces, a tile inside
     // at most two heads, no split-K

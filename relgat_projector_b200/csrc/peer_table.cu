@@ -174,7 +174,58 @@ pull_rows_kernel(const float* __restrict__ table, long long ld, const long long*
   }
 }
 
+// bf16 rows over the link, fp32 rows in local memory: the owner exports its rows rounded to bf16 (half the NVLink
+// bytes of a pull), the puller widens them while storing into the [own | pulled] fp32 table the edge kernels read.
+template <int kPullUnroll>
+__global__ void __launch_bounds__(kPullThreads)
+pull_rows_bf16_kernel(const __nv_bfloat16* __restrict__ table, long long ld, const long long* __restrict__ ids,
+                      const long long* __restrict__ out_ids, long long n, int D, float* __restrict__ out, long long ldo) {
+  const int dv = D / 8;  // 16-byte pieces of 8 bf16 per row
+  const long long total = n * dv;
+  const long long stride = static_cast<long long>(gridDim.x) * kPullThreads;
+  for (long long base = static_cast<long long>(blockIdx.x) * kPullThreads + threadIdx.x; base < total;
+       base += stride * kPullUnroll) {
+    float v[kPullUnroll][8];
+    long long row[kPullUnroll];
+    int q[kPullUnroll];
+#pragma unroll
+    for (int u = 0; u < kPullUnroll; ++u) {
+      const long long idx = base + u * stride;
+      row[u] = -1;
+      if (idx < total) {
+        row[u] = idx / dv;
+        q[u] = static_cast<int>(idx - row[u] * dv);
+        RowVec<__nv_bfloat16, 8>::load_stream(table + __ldg(ids + row[u]) * ld + q[u] * 8, v[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kPullUnroll; ++u)
+      if (row[u] >= 0) RowVec<float, 8>::store(out + (out_ids ? __ldg(out_ids + row[u]) : row[u]) * ldo + q[u] * 8, v[u]);
+  }
+}
+
 }  // namespace relgat
+
+extern "C" int relgat_pull_rows_bf16(const void* table, long long ld, const long long* ids, const long long* out_ids,
+                                     long long n, int D, float* out, long long ldo, int sm_count, void* stream) {
+  using namespace relgat;
+  if (n < 0 || D <= 0 || ld < D || ldo < D) return RG_ERR_ARG;
+  if (n == 0) return RG_OK;
+  if (!table || !ids || !out) return RG_ERR_ARG;
+  if (D % 8 != 0 || ld % 8 != 0 || ldo % 4 != 0) return RG_ERR_SHAPE;
+  if (!al16(table) || !al16(out)) return RG_ERR_ALIGN;
+  const long long total = n * (D / 8);
+  const long long per_cta = static_cast<long long>(kPullThreads) * 4;
+  const long long want = (total + per_cta - 1) / per_cta;
+  const long long cap = static_cast<long long>(sm_count > 0 ? sm_count : 148) * 4;
+  const unsigned blocks = static_cast<unsigned>(want < cap ? (want > 0 ? want : 1) : cap);
+  static const cudaError_t carve = cudaFuncSetAttribute(pull_rows_bf16_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                        cudaSharedmemCarveoutMaxShared);
+  (void)carve;
+  pull_rows_bf16_kernel<4><<<blocks, kPullThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(table), ld, ids, out_ids, n, D, out, ldo);
+  return cuda_status(cudaGetLastError());
+}
 
 extern "C" int relgat_pull_rows(const float* table, long long ld, const long long* ids, const long long* out_ids,
                                 long long n, int D, float* out, long long ldo, int sm_count, void* stream) {

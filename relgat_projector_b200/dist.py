@@ -20,6 +20,7 @@ Batch rows x[src_ids] / x[dst_ids] are exchanged with one all-reduce of a [2B', 
 from __future__ import annotations
 
 import json
+import os
 import sys
 from typing import List, Optional, Sequence
 
@@ -334,20 +335,28 @@ class PartitionedRelGAT:
                                               self.model.precision, self._planes, *flat)
 
     def scores(self, src_ids, rel_ids, dst_ids):
+        from .peer import check_partitioned_model_supported
+        check_partitioned_model_supported(self.model)  # no silent divergence from the single-GPU model (dropout)
         x_local = self.node_repr_local()
         ids = torch.cat([src_ids, dst_ids])
         rows = ExchangeBatchRows.apply(x_local, ids, self.part)
+        if self.model.project_to_input_size:  # row-wise head: project the gathered batch rows only
+            rows = self.model.projection(rows)
         b = src_ids.numel()
         return self.model.scorer(rows[:b], rel_ids, rows[b:])
 
     def finish_backward(self) -> None:
-        allreduce_grads(self.gat_params)
+        extra = list(self.model.projection.parameters()) if self.model.project_to_input_size else []
+        allreduce_grads(self.gat_params + extra)
 
 
 # ---------------------------------------------------------------------------------------------
 # bench.py entry for --gpus N > 1 (launched under torchrun)
 # ---------------------------------------------------------------------------------------------
-def bench_main(args, cfg, rank, world, local_rank, metric, unit, load_peaks, ClockSampler) -> int:
+NVLINK_PEER_COPY_GBS = 770.0  # measured peer copy per direction on this pool (B200_PROFILING.md); nominal 900
+
+
+def bench_main(args, cfg, rank, world, local_rank, metric, unit, load_peaks, ClockSampler, cpu_fn=None) -> int:
     import relgat_projector_b200 as R
     from . import loss as L, synthetic as S
 
@@ -372,8 +381,9 @@ def bench_main(args, cfg, rank, world, local_rank, metric, unit, load_peaks, Clo
                 print(f"[bench] peer tables unavailable ({why}); using the NCCL halo exchange", file=sys.stderr)
             exchange = "halo"
     if exchange == "peer":  # rows of other ranks are pulled from NVLink-mapped peer tables (peer.py); no exchange step
+        halo_bf16 = getattr(args, "halo", "bf16") == "bf16"
         part = RP.PeerPartition(kg.edge_index, kg.edge_type, n_nodes, cfg["R"], rank, world,
-                                RP.PeerTables(world, rank, dev), cfg["H"], cfg["F"], cfg["L"])
+                                RP.PeerTables(world, rank, dev), cfg["H"], cfg["F"], cfg["L"], halo_bf16=halo_bf16)
         part.E_local = part.E_fwd
     else:
         part = DstPartition(kg.edge_index, kg.edge_type, n_nodes, cfg["R"], rank, world, mode=exchange)
@@ -436,6 +446,26 @@ def bench_main(args, cfg, rank, world, local_rank, metric, unit, load_peaks, Clo
     e_local = torch.tensor([part.E_local], device=dev)
     e_all = [torch.zeros_like(e_local) for _ in range(world)]
     dist.all_gather(e_all, e_local)
+    # NVLink roofline of the dominant multi-GPU kernel: the forward halo pull of one layer, all ranks at once
+    pull_gbs = None
+    if exchange == "peer" and part.n_halo_f > 0:
+        src_tab = "Pb0" if part.halo_bf16 else None
+        for _ in range(2):
+            part.pull("P0", part.pull_f, export=src_tab)
+        dist.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(5):
+            part.pull("P0", part.pull_f, export=src_tab)
+        e.record()
+        torch.cuda.synchronize()
+        t_pull = torch.tensor([s.elapsed_time(e) / 5], device=dev)
+        dist.all_reduce(t_pull, op=dist.ReduceOp.MAX)
+        pull_bytes = part.n_halo_f * cfg["H"] * cfg["F"] * (2 if part.halo_bf16 else 4)
+        pull_gbs = (pull_bytes, float(t_pull.item()))
+    cpu = cpu_fn() if (rank == 0 and cpu_fn is not None) else None
+    dist.barrier()
     if rank == 0:
         C = cfg["H"] * cfg["F"]
         if exchange == "peer":
@@ -444,7 +474,7 @@ def bench_main(args, cfg, rank, world, local_rank, metric, unit, load_peaks, Clo
                    f"cross-rank sum of dP); all-reduce of parameter grads")
             extra = {"halo_rows_fwd_rank0": part.n_halo_f, "halo_rows_bwd_rank0": part.n_halo_b,
                      "local_rows_rank0": part.n_local,
-                     "nvlink_bytes_per_layer_pass_rank0": max(part.n_halo_f, part.n_halo_b) * C * 4}
+                     "nvlink_bytes_per_layer_pass_rank0": max(part.n_halo_f, part.n_halo_b) * C * (2 if part.halo_bf16 else 4)}
         else:
             par = (f"dst-range partition x{world}, NCCL {'all-to-all of halo rows' if exchange == 'halo' else 'all-gather'} "
                    f"of P fwd / of dP bwd, all-reduce of parameter grads")
@@ -470,6 +500,24 @@ def bench_main(args, cfg, rank, world, local_rank, metric, unit, load_peaks, Clo
             "gpu_launches": launches,
             "roofline": None, "cpu_baseline": None,
         }
+        if pull_gbs is not None:
+            pb, pt = pull_gbs
+            gbs = pb / (pt * 1e-3) / 1e9
+            line["roofline"] = {
+                "kernel": "pull_rows (halo rows of one layer pass, rank with the slowest pull)", "bound": "nvlink",
+                "achieved": round(gbs, 1), "peak": NVLINK_PEER_COPY_GBS, "unit": "GB/s",
+                "frac": round(gbs / NVLINK_PEER_COPY_GBS, 4), "traffic": None,
+                "bytes_per_launch": int(pb), "ms_per_launch": round(pt, 4),
+                "peak_source": "measured peer copy per direction on this pool (B200_PROFILING.md: 770 GB/s; nominal 900)"}
+            line["config"]["halo_rows"] = ("bf16 over NVLink, fp32 in local memory (stated tolerance 2e-2 relative; "
+                                           "--halo fp32 for fp32 rows)" if part.halo_bf16 else "fp32")
+        if cpu is not None:
+            line["cpu_baseline"] = {kk: cpu[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
+        ref_c4 = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles",
+                              "r02_bench_c4_n8_strong.json")
+        if os.path.exists(ref_c4):  # north_star's 50 M-edge strong-scaling config, measured by the builder (not in this run)
+            with open(ref_c4) as f:
+                line["c4_strong_builder_run"] = json.load(f)
         print(json.dumps(line))
     dist.destroy_process_group()
     return 0

@@ -21,7 +21,9 @@ PRECISIONS = ("fp32", "bf16")
 # (SURVEY.md A.3); RELGAT_DS=0 restores the by-relation kernel (kept for the partitioned path and for A/B timing)
 USE_DS = os.environ.get("RELGAT_DS", "1") != "0"
 # backward prep of a hidden layer fused into the epilogue of the dX GEMM above it (RELGAT_FUSE_PREP=0: separate kernel)
-FUSE_PREP = os.environ.get("RELGAT_FUSE_PREP", "1") != "0"
+# OFF by default: measured on config 2, the fused epilogue costs 3.3 ms against 1.30 (GEMM) + 0.61 (prep kernel) — four
+# epilogue warps reading y row-wise cannot keep up with the MMA (profiles/r02_summary.md); kept as an experiment knob.
+FUSE_PREP = os.environ.get("RELGAT_FUSE_PREP", "0") != "0"
 # the small tail of the dS path (dA = T W^T, dbeta) on the side stream (1) or in line on the main stream (0)
 TAIL_ON_SIDE = os.environ.get("RELGAT_TAIL_SIDE", "1") != "0"
 

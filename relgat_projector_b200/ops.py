@@ -69,10 +69,15 @@ def sm_count(device) -> int:
 # ------------------------------------------------------------------------------------------
 # dense transforms
 # ------------------------------------------------------------------------------------------
-def split_bf16(x: torch.Tensor, with_lo: bool = True) -> Planes:
-    """fp32 matrix -> bf16 (hi, lo) planes, hi = rn(x), lo = rn(x - hi)."""
+def split_bf16(x: torch.Tensor, with_lo: bool = True, out_hi: Optional[torch.Tensor] = None) -> Planes:
+    """fp32 matrix -> bf16 (hi, lo) planes, hi = rn(x), lo = rn(x - hi).  ``out_hi``: caller-owned contiguous bf16
+    buffer of x's shape for the hi plane (rows of a peer table)."""
     x = _f32c(x, "x")
-    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    if out_hi is not None:
+        _lib.require_cuda(out_hi)
+        if out_hi.dtype != torch.bfloat16 or tuple(out_hi.shape) != tuple(x.shape) or not out_hi.is_contiguous():
+            raise ValueError("split_bf16: out_hi must be a contiguous bfloat16 tensor of x's shape")
+    hi = out_hi if out_hi is not None else torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if with_lo else None
     with torch.cuda.device(x.device):
         rc = _lib.load().relgat_split_bf16(_lib.ptr(x), _lib.ptr(hi), _lib.ptr(lo), x.numel(), _stream(x))
@@ -627,8 +632,8 @@ def pull_rows(table: torch.Tensor, ids: torch.Tensor, out: torch.Tensor, out_ids
     out[out_ids[i]] = table[ids[i]].  ``table`` / ``out``: fp32 with unit inner stride, any number of trailing dims
     (flattened); ``ids`` / ``out_ids`` int64."""
     _lib.require_cuda(table, ids, out)
-    if table.dtype != torch.float32 or out.dtype != torch.float32 or ids.dtype != torch.int64:
-        raise TypeError("pull_rows: table / out must be float32 and ids int64")
+    if table.dtype not in (torch.float32, torch.bfloat16) or out.dtype != torch.float32 or ids.dtype != torch.int64:
+        raise TypeError("pull_rows: table must be float32 or bfloat16, out float32 and ids int64")
     n = int(ids.numel())
     D = int(table[0].numel()) if table.size(0) else int(out[0].numel())
     if out_ids is None and out.size(0) != n:
@@ -639,10 +644,11 @@ def pull_rows(table: torch.Tensor, ids: torch.Tensor, out: torch.Tensor, out_ids
         raise ValueError("pull_rows: out must be a contiguous tensor with the table's row shape")
     if n == 0:
         return out
+    fn = _lib.load().relgat_pull_rows_bf16 if table.dtype == torch.bfloat16 else _lib.load().relgat_pull_rows
     with torch.cuda.device(out.device):
-        rc = _lib.load().relgat_pull_rows(_lib.ptr(table), D, _lib.ptr(ids.contiguous()),
-                                          _lib.ptr(None if out_ids is None else out_ids.contiguous()), n, D,
-                                          _lib.ptr(out), D, sm_count(out.device), _stream(out))
+        rc = fn(_lib.ptr(table), D, _lib.ptr(ids.contiguous()),
+                _lib.ptr(None if out_ids is None else out_ids.contiguous()), n, D,
+                _lib.ptr(out), D, sm_count(out.device), _stream(out))
     _lib.check(rc, "relgat_pull_rows")
     _count(1)
     return out

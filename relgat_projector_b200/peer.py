@@ -42,6 +42,7 @@ import torch.distributed as dist
 
 from . import _lib, ops
 from .dist import allreduce_grads, partition_bounds
+from . import functional as _RF
 from .functional import _side_stream, mark_sparse_rows, sparse_rows_of
 from .graph import GraphIndex
 
@@ -55,6 +56,10 @@ PIPELINE_BLOCKS = max(1, int(os.environ.get("RELGAT_PEER_BLOCKS", "4")))
 # last layer's backward: dY is zero outside the batch rows, so only those rows of G / t / hsum are written, pulled
 # and (afterwards) cleared — instead of moving a dense, almost-all-zero halo over NVLink
 SPARSE_LAST = os.environ.get("RELGAT_PEER_SPARSE_LAST", "1") != "0"
+# halo rows cross NVLink rounded to bf16 (the owner exports a bf16 copy of its P / G rows; the pull widens them into
+# the fp32 [own | pulled] table): half the link bytes of a layer pass.  Library default: off (fp32 rows, results equal
+# to one GPU up to summation order); bench.py turns it on for the multi-GPU runs and states the tolerance (2e-2).
+HALO_BF16_DEFAULT = os.environ.get("RELGAT_PEER_HALO", "fp32") == "bf16"
 _COMM_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
 
 # poor man's timeline (nsys is not in the image): RELGAT_PEER_TRACE=1 records a CUDA event per phase boundary on the
@@ -403,9 +408,13 @@ class PeerPartition:
 
     def __init__(self, edge_index: torch.Tensor, edge_type: torch.Tensor, num_nodes: int, num_rel: int,
                  rank: int, world: int, tables: PeerTables, heads: int, out_dim: int, num_layers: int,
-                 balance: str = "edges", tag: str = "p", blocks: Optional[int] = None):
+                 balance: str = "edges", tag: str = "p", blocks: Optional[int] = None,
+                 halo_bf16: Optional[bool] = None):
         self.rank, self.world, self.N, self.R = rank, world, int(num_nodes), int(num_rel)
         self.H, self.F, self.L = heads, out_dim, num_layers
+        self.halo_bf16 = HALO_BF16_DEFAULT if halo_bf16 is None else bool(halo_bf16)
+        if self.halo_bf16 and (heads * out_dim) % 8 != 0:
+            raise ValueError("bf16 halo rows need heads*out_dim to be a multiple of 8")
         self.tables = tables
         dev = edge_index.device
         C = heads * out_dim
@@ -416,7 +425,7 @@ class PeerPartition:
             return int(t.item())
 
         plan = PeerIndexPlan(edge_index, edge_type, num_nodes, rank, world, tables.slot_of, tables.stride_rows,
-                             [4 * C, 4 * heads, 8 * heads], [4 * heads],
+                             [4 * C, 2 * C, 4 * heads, 8 * heads], [4 * heads],
                              blocks=int(blocks if blocks is not None else PIPELINE_BLOCKS), balance=balance,
                              agree_max=agree_max if (world > 1 and tables.mode == "vmm") else None)
         self.plan = plan
@@ -439,6 +448,8 @@ class PeerPartition:
                       (f"t{l}", self.stride_rows, (heads,), torch.float32),
                       (f"hsum{l}", self.stride_rows, (heads,), torch.float32),
                       (f"z{l}", self.stride_slots, (heads,), torch.float32)]
+            if self.halo_bf16:  # what the peers read: this rank's P / G rows rounded to bf16
+                specs += [(f"Pb{l}", self.stride_rows, (C,), torch.bfloat16), (f"Gb{l}", self.stride_rows, (C,), torch.bfloat16)]
         specs.append(("out", self.stride_rows, (C,), torch.float32))
         self.t = tables.allocate(specs, tag=tag)
         self._token = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -454,17 +465,24 @@ class PeerPartition:
         if self.tables.mode == "vmm" and self.world > 1:
             dist.all_reduce(self._token)
 
-    def pull(self, name: str, ids: torch.Tensor, per_block: Optional[List[int]] = None, block: Optional[int] = None):
+    def pull(self, name: str, ids: torch.Tensor, per_block: Optional[List[int]] = None, block: Optional[int] = None,
+             export: Optional[str] = None):
         """Fills the pulled rows of table ``name`` (all of them, or those of one pipeline block) from their
-        owners; returns the [own | pulled] view."""
+        owners; returns the [own | pulled] view.  ``export``: read the owners' bf16 export table of that name instead
+        (rows are widened to fp32 on arrival)."""
         tb, n = self.t[name], self.n_local
         k = int(ids.numel())
         a, b = 0, k
         if block is not None:
             a = sum(per_block[:block])
             b = a + per_block[block]
-        ops.pull_rows(tb.whole, ids[a:b], tb.local[n + a:n + b])
+        ops.pull_rows(self.t[export].whole if export else tb.whole, ids[a:b], tb.local[n + a:n + b])
         return tb.local[:n + k]
+
+    def export_rows(self, name: str, export: str, r0: int, r1: int) -> None:
+        """bf16 copy of own rows [r0, r1) of table ``name`` into the export table the peers pull from."""
+        if r1 > r0:
+            ops.split_bf16(self.t[name].local[r0:r1], with_lo=False, out_hi=self.t[export].local[r0:r1])
 
 
 # ---------------------------------------------------------------------------------------------
@@ -489,12 +507,14 @@ def forward_steps(part: PeerPartition, planes, params: Sequence[torch.Tensor], w
             if r1 > r0:
                 ops.gemm(tuple(None if p is None else p[r0:r1] for p in planes), False, Wp, False, r1 - r0, C, d_in,
                          out=T[f"P{l}"].local[r0:r1])
+                if part.halo_bf16:
+                    part.export_rows(f"P{l}", f"Pb{l}", r0, r1)
             _mark(f"fwd{l} gemm block {c} done")
             yield  # every rank's block c of P is written
             _mark(f"fwd{l} rendezvous {c} done")
             comm.wait_stream(main)
             with torch.cuda.stream(comm):  # beside the GEMM of block c+1
-                P_ext = part.pull(f"P{l}", part.pull_f, part.blk_f, c)
+                P_ext = part.pull(f"P{l}", part.pull_f, part.blk_f, c, export=f"Pb{l}" if part.halo_bf16 else None)
                 _mark(f"fwd{l} pull block {c} done", "comm")
         main.wait_stream(comm)
         _mark(f"fwd{l} pulls joined")
@@ -504,7 +524,8 @@ def forward_steps(part: PeerPartition, planes, params: Sequence[torch.Tensor], w
             want_act=not last, apply_elu=True, act_lo=with_lo, out_buf=T["out"].local[:n] if last else None,
             z_out=T[f"z{l}"].local[:part.E_fwd], minv_out=T[f"minv{l}"].local[:n])
         _mark(f"fwd{l} edge kernel done")
-        saved.append(dict(xp=planes, WTp=WTp, out=out, bias=bias, A=A.detach(), d_in=d_in, has_beta=beta is not None))
+        saved.append(dict(xp=planes, Wp=Wp, WTp=WTp, out=out, bias=bias, A=A.detach(), d_in=d_in,
+                          has_beta=beta is not None))
         planes = act
     return out
 
@@ -563,41 +584,66 @@ def backward_steps(part: PeerPartition, grad_out: torch.Tensor, saved: list, wit
                     ops.edge_bwd_prep(dY[r0:r1], s["out"][r0:r1], s["bias"][r0:r1], H, F, apply_elu=(l < L - 1),
                                       G_out=T[f"G{l}"].local[r0:r1], t_out=T[f"t{l}"].local[r0:r1],
                                       hsum_out=T[f"hsum{l}"].local[r0:r1])
+                    if part.halo_bf16:
+                        part.export_rows(f"G{l}", f"Gb{l}", r0, r1)
                 _mark(f"bwd{l} prep block {c} done")
                 yield  # every rank's block c of G / t / hsum is written
                 _mark(f"bwd{l} rendezvous {c} done")
                 comm.wait_stream(main)
                 with torch.cuda.stream(comm):  # beside the prep of block c+1
-                    G_ext = part.pull(f"G{l}", part.pull_b, part.blk_b, c)
+                    G_ext = part.pull(f"G{l}", part.pull_b, part.blk_b, c, export=f"Gb{l}" if part.halo_bf16 else None)
                     t_ext, minv_ext, hsum_ext = (part.pull(f"{k}{l}", part.pull_b, part.blk_b, c) for k in ("t", "minv", "hsum"))
                     _mark(f"bwd{l} pull block {c} done", "comm")
         main.wait_stream(comm)
         _mark(f"bwd{l} pulls joined")
         P_loc = T[f"P{l}"].local[:n]
+        use_ds = _RF.USE_DS
         _, dPp, dz = ops.edge_bwd_src(P_loc, G_ext, s["A"], z, minv_ext, t_ext, g, H, F,
-                                      want_fp32=False, want_planes=True, planes_lo=with_lo)
+                                      want_fp32=False, want_planes=True, planes_lo=with_lo, want_ds=use_ds)
         _mark(f"bwd{l} by-source kernel done")
         # dA / dbeta and dW are off the critical path (dX -> prep -> pull -> by-source pass of the layer below):
         # they run on the side stream, beside the NVLink-bound pulls, and are joined once at the end
         side = _side_stream(dY.device)
         side.wait_stream(main)
         d_in = s["d_in"]
-        deep = DEEP_OVERLAP and l > 0  # the layer processed last has no pulls below it: dW on the main stream beside dA
-        with torch.cuda.stream(side):
-            dA, dbeta = ops.edge_bwd_rel(P_loc, dz, hsum_ext, g, H, F, want_dbeta=s["has_beta"])
-            _mark(f"bwd{l} by-relation done", "side")
+        deep = DEEP_OVERLAP and l > 0  # the layer processed last has no pulls below it: dW on the main stream
+        if use_ds:
+            # widened rows [dP | dS]: one split-K GEMM gives dW and dS^T X; dA = (dS^T X) W^T; no
+            # by-relation gather pass over P
+            HR, Wd = H * g.R, dPp[0].size(1)
+
+            def dw_and_tail():
+                dW_ext = ops.gemm(dPp, True, s["xp"], True, Wd, d_in, n, splits_k=ops.pick_splits_k(Wd, d_in, n, dY.device))
+                Tp = ops.split_bf16(dW_ext[C:C + HR].contiguous(), with_lo)
+                dA_full = ops.gemm(Tp, False, s["Wp"], False, HR, C, d_in)
+                dA_ = torch.stack([dA_full[h * g.R:(h + 1) * g.R, h * F:(h + 1) * F] for h in range(H)])
+                return dW_ext[:C], dA_, (ops.edge_bwd_beta(hsum_ext, g, H) if s["has_beta"] else None)
+
             if deep:
+                with torch.cuda.stream(side):
+                    dW, dA, dbeta = dw_and_tail()
+                    _mark(f"bwd{l} dW done", "side")
+            else:
+                dW, dA, dbeta = dw_and_tail()
+                _mark(f"bwd{l} dW done")
+            dPc = tuple(None if p_ is None else p_[:, :C] for p_ in dPp)
+        else:
+            with torch.cuda.stream(side):
+                dA, dbeta = ops.edge_bwd_rel(P_loc, dz, hsum_ext, g, H, F, want_dbeta=s["has_beta"])
+                _mark(f"bwd{l} by-relation done", "side")
+                if deep:
+                    dW = ops.gemm(dPp, True, s["xp"], True, C, d_in, n, splits_k=ops.pick_splits_k(C, d_in, n, dY.device))
+                    _mark(f"bwd{l} dW done", "side")
+            if not deep:
                 dW = ops.gemm(dPp, True, s["xp"], True, C, d_in, n, splits_k=ops.pick_splits_k(C, d_in, n, dY.device))
-                _mark(f"bwd{l} dW done", "side")
-        if not deep:
-            dW = ops.gemm(dPp, True, s["xp"], True, C, d_in, n, splits_k=ops.pick_splits_k(C, d_in, n, dY.device))
-            _mark(f"bwd{l} dW done")
+                _mark(f"bwd{l} dW done")
+            dPc = dPp
         grads[3 * l], grads[3 * l + 1], grads[3 * l + 2] = dW, dA, dbeta
         if l > 0 or x0_needs_grad:
-            dX = ops.gemm(dPp, False, s["WTp"], False, n, d_in, C)
+            dX = ops.gemm(dPc, False, s["WTp"], False, n, d_in, C)
             dY = dX
             _mark(f"bwd{l} dX done")
-        keep.append((dPp, dz, z))  # read on the side stream: released only after the join
+        keep.append((dPp, dz, z, hsum_ext))  # read on the side stream: released only after the join
         if not DEEP_OVERLAP:
             main.wait_stream(side)
     main = torch.cuda.current_stream(grad_out.device)
@@ -706,11 +752,33 @@ class PeerRelGAT:
             flat += list(lyr.kernel_params())
         return PeerStackFunction.apply(self.x0_local, self.part, self.model.precision, self._planes, *flat)
 
-    def scores(self, src_ids, rel_ids, dst_ids):
+    def batch_rows(self, ids: torch.Tensor) -> torch.Tensor:
+        """``model.batch_rows(ids)`` on the partitioned graph: the stack's rows of the batch nodes, through the
+        projection head when the model has one (a row-wise map: only the gathered rows are projected)."""
+        check_partitioned_model_supported(self.model)
         x_local = self.node_repr_local()
-        rows = PeerBatchRows.apply(x_local, torch.cat([src_ids, dst_ids]), self.part)
+        rows = PeerBatchRows.apply(x_local, ids, self.part)
+        return self.model.projection(rows) if self.model.project_to_input_size else rows
+
+    def scores(self, src_ids, rel_ids, dst_ids):
+        rows = self.batch_rows(torch.cat([src_ids, dst_ids]))
         b = src_ids.numel()
         return self.model.scorer(rows[:b], rel_ids, rows[b:])
 
     def finish_backward(self) -> None:
-        allreduce_grads(self.gat_params)
+        extra = list(self.model.projection.parameters()) if self.model.project_to_input_size else []
+        allreduce_grads(self.gat_params + extra)
+
+
+def check_partitioned_model_supported(model) -> None:
+    """The partitioned rank programs run the layers without dropout masks: refuse a training-mode model whose layer
+    or projection dropout is active instead of silently training a different model than one GPU would (reference
+    layer.py:296-297, 321-322; projection.py:69-72)."""
+    if not model.training:
+        return
+    for lyr in model._layers():
+        if lyr.dropout.p > 0.0 or lyr.rel_attn_drop.p > 0.0:
+            raise NotImplementedError("partitioned (multi-GPU) training runs without dropout masks: construct the model "
+                                      "with dropout=0 and relation_attn_dropout=0, or train on one GPU")
+    if model.project_to_input_size and isinstance(model.projection.dropout, torch.nn.Dropout) and model.projection.dropout.p > 0:
+        raise NotImplementedError("partitioned (multi-GPU) training does not support projection_dropout > 0")

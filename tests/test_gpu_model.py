@@ -354,6 +354,48 @@ def test_peer_table_partition_lockstep_equals_whole_graph(dev, world, blocks):
         assert torch.equal(rows, out_ref.detach()[ids])
 
 
+def test_peer_table_partition_with_bf16_halo_rows_stated_tolerance(dev):
+    """halo_bf16=True: the rows a rank pulls from its peers cross the link rounded to bf16 (own rows stay fp32).  Node
+    rows of destinations without remote sources stay bit-exact; everything else agrees with the unpartitioned stack
+    inside the stated bf16 tolerance (2e-2 relative)."""
+    from relgat_projector_b200 import functional as Fn, graph as G, ops, peer as RP
+    from relgat_projector_b200 import synthetic as S
+    world, n, r, d_in, h, f, L_ = 3, 900, 7, 64, 4, 24, 2
+    kg = S.tensor_kg(n, 6000, r, d_in, seed=11, device=str(dev), skew=0.8)
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    params = []
+    for l in range(L_):
+        di = d_in if l == 0 else h * f
+        params += [(torch.randn(h * f, di, generator=gen) / di ** 0.5).to(dev).requires_grad_(True),
+                   (torch.randn(h, r, f, generator=gen) * 0.3).to(dev).requires_grad_(True),
+                   (torch.randn(r, generator=gen) * 0.1).to(dev).requires_grad_(True)]
+    x0 = kg.node_emb.clone().requires_grad_(True)
+    grad_out = torch.randn(n, h * f, generator=gen).to(dev)
+    g_full = G.GraphIndex(kg.edge_index, kg.edge_type, n, r)
+    out_ref = Fn.RelGATStackFunction.apply(x0, g_full, h, f, "fp32", None, None, None, *params)
+    ref_grads = torch.autograd.grad(out_ref, [x0] + params, grad_out)
+    store = {}
+    parts = [RP.PeerPartition(kg.edge_index, kg.edge_type, n, r, rk, world,
+                              RP.PeerTables(world, rk, dev, mode="sim", sim_store=store), h, f, L_, blocks=2,
+                              halo_bf16=True) for rk in range(world)]
+    saved = [[] for _ in range(world)]
+    x_loc = [x0.detach()[p.lo:p.hi].contiguous() for p in parts]
+    outs = RP.drive_lockstep([RP.forward_steps(parts[k], ops.split_bf16(x_loc[k]), [t.detach() for t in params], True,
+                                               saved[k], x0_needs_grad=True) for k in range(world)])
+    BF16_TOL = 2e-2
+    for p, o in zip(parts, outs):
+        ref = out_ref.detach()[p.lo:p.hi]
+        assert rel_err(o.cpu().numpy(), ref.cpu().numpy()) < BF16_TOL
+        assert not torch.equal(o, ref)  # the rounding of the pulled rows is really there
+    res = RP.drive_lockstep([RP.backward_steps(parts[k], grad_out[parts[k].lo:parts[k].hi], saved[k], True,
+                                               x0_needs_grad=True) for k in range(world)])
+    for p, (dx, _) in zip(parts, res):
+        assert rel_err(dx.cpu().numpy(), ref_grads[0][p.lo:p.hi].cpu().numpy()) < BF16_TOL
+    for i in range(len(params)):
+        total = sum(res[k][1][i] for k in range(world))
+        assert rel_err(total.cpu().numpy(), ref_grads[1 + i].cpu().numpy()) < BF16_TOL, i
+
+
 def test_sparse_loss_gradient_rows_give_the_dense_result(dev, monkeypatch):
     """Two hand-overs of the batch gradient to the stack's backward: (a) the fused stack + row gather node scatters the
     batch rows' gradients into a persistent zero table and computes t / hsum of the last layer from those rows only;

@@ -33,7 +33,8 @@ def main():
 
     if "--peer" in sys.argv:  # peer tables (mapped NVLink rows) instead of the halo exchange
         tables = RP.PeerTables(world, rank, dev)
-        part = RP.PeerPartition(kg.edge_index, kg.edge_type, n, r, rank, world, tables, h, f, 2)
+        part = RP.PeerPartition(kg.edge_index, kg.edge_type, n, r, rank, world, tables, h, f, 2,
+                                halo_bf16="--halo-bf16" in sys.argv)
         part.E_local = part.E_fwd
         prg = RP.PeerRelGAT(model, part, kg.node_emb[part.lo:part.hi])
     else:
@@ -63,7 +64,8 @@ def main():
     worst = max(errs.values())
     print(f"rank {rank}/{world}: rows [{part.lo},{part.hi}) edges {part.E_local} worst rel err {worst:.2e} "
           f"({max(errs, key=errs.get)})", flush=True)
-    ok = torch.tensor([1 if worst < 1e-4 else 0], device=dev)
+    tol = 2e-2 if "--halo-bf16" in sys.argv else 1e-4  # stated tolerance of bf16 halo rows / fp32 contract
+    ok = torch.tensor([1 if worst < tol else 0], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
     if int(ok.item()) != 1:

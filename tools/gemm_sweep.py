@@ -49,6 +49,31 @@ def main():
                 print(f"{name:22s} BN={bn or 'auto':>4} splits={sk:2d}  {ms:.3f} ms  {2.0 * M * N * K * 3 / ms / 1e9:.0f} TFLOP/s (3 passes)", flush=True)
         del a, b
         torch.cuda.empty_cache()
+    # the dX GEMM with the backward prep of the layer below fused into its epilogue, against the unfused pair
+    M, H, F, K = 300_000, 4, 200, 800
+    N = H * F
+    g = torch.Generator(device=dev).manual_seed(1)
+    dP, WT = planes(M, K, dev), planes(N, K, dev)
+    y = torch.randn((M, N), generator=g, device=dev)
+    bias = torch.randn((M,), generator=g, device=dev)
+
+    def t_ms(fn, n=5):
+        for _ in range(2):
+            fn()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / n
+
+    fused = t_ms(lambda: ops.gemm_dx_prep(dP, WT, M, N, K, y, bias, H, F, apply_elu=True))
+    gemm_only = t_ms(lambda: ops.gemm(dP, False, WT, False, M, N, K))
+    dX = ops.gemm(dP, False, WT, False, M, N, K)
+    prep_only = t_ms(lambda: ops.edge_bwd_prep(dX, y, bias, H, F, apply_elu=True))
+    print(f"dX + prep of the layer below: fused epilogue {fused:.3f} ms; unfused GEMM {gemm_only:.3f} + prep {prep_only:.3f} "
+          f"= {gemm_only + prep_only:.3f} ms", flush=True)
 
 
 if __name__ == "__main__":
