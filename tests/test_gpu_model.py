@@ -389,11 +389,18 @@ def test_peer_table_partition_with_bf16_halo_rows_stated_tolerance(dev):
         assert not torch.equal(o, ref)  # the rounding of the pulled rows is really there
     res = RP.drive_lockstep([RP.backward_steps(parts[k], grad_out[parts[k].lo:parts[k].hi], saved[k], True,
                                                x0_needs_grad=True) for k in range(world)])
+    # gradients: the stated tolerance of the bf16 mode (BF16_GRAD_TOL max-norm, cosine >= BF16_GRAD_COS), see
+    # test_bf16_storage_mode_stated_tolerance
+    def close(a, b):
+        a, b = a.flatten().double(), b.flatten().double()
+        cos = float(torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-30))
+        return rel_err(a.cpu().numpy(), b.cpu().numpy()) < BF16_GRAD_TOL and cos >= BF16_GRAD_COS
+
     for p, (dx, _) in zip(parts, res):
-        assert rel_err(dx.cpu().numpy(), ref_grads[0][p.lo:p.hi].cpu().numpy()) < BF16_TOL
+        assert close(dx, ref_grads[0][p.lo:p.hi])
     for i in range(len(params)):
         total = sum(res[k][1][i] for k in range(world))
-        assert rel_err(total.cpu().numpy(), ref_grads[1 + i].cpu().numpy()) < BF16_TOL, i
+        assert close(total, ref_grads[1 + i]), i
 
 
 def test_sparse_loss_gradient_rows_give_the_dense_result(dev, monkeypatch):
