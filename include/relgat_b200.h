@@ -151,6 +151,18 @@ int relgat_layer_bwd_src(const void* P, long long ldp, const void* G, int feat_i
                          float* dP, void* dP_hi, void* dP_lo, float* dz,
                          const unsigned int* edge_bits, float edge_scale, int want_ds, long long ldo,
                          int H, int F, int R, int sm_count, int* work_counter, void* stream);
+/* Training-path variant of relgat_layer_bwd_src (second generation): fp32 P / G rows with F % 4 == 0, bf16 planes out,
+ * want_ds semantics (rows ldo >= H*F + H*R wide, dS behind dP, no dz).  A pre-pass turns the per-edge gathers of z,
+ * t and the softmax statistics (and the exp) into three coefficients per edge and head (coef: float [E*3*H] scratch,
+ * by-source order), which the main loop streams; see csrc/edge_bwd_src2.cu.  Returns RG_ERR_SHAPE for layouts it does
+ * not cover (use relgat_layer_bwd_src). */
+int relgat_layer_bwd_src2(const float* P, long long ldp, const float* G, const float* A, const float* z,
+                          const float* minv, const float* t, const int* colptr, const int* csc_slot,
+                          const int* csc_dst, const int* csc_rel, const int* chunks, int n_chunks,
+                          const int* parts, int n_parts, const int* long_node, const int* long_part_ptr, int n_long,
+                          float* part_acc, void* dP_hi, void* dP_lo, float* coef, long long E,
+                          const unsigned int* edge_bits, float edge_scale, long long ldo, int H, int F, int R,
+                          int sm_count, int* work_counter, void* stream);
 int relgat_layer_bwd_beta(const float* hsum, const int* rel_slot, const int* csr_dst, const int* chunk_lo,
                           const int* chunk_hi, const int* rel_chunk_ptr, int n_chunks, float* partB, float* dbeta,
                           int H, int R, void* stream);

@@ -358,6 +358,9 @@ def edge_bwd_prep(dY: torch.Tensor, out: torch.Tensor, bias: torch.Tensor, H: in
     return G, t, hsum
 
 
+SRC_V2 = os.environ.get("RELGAT_SRC_V2", "1") != "0"  # second-generation by-source kernel on the training path
+
+
 def ds_row_width(H: int, F: int, R: int) -> int:
     """Row width of the widened dP rows [dP | dS] (multiple of 8 elements: TMA strides, 128-bit stores)."""
     return (H * F + H * R + 7) // 8 * 8
@@ -385,6 +388,23 @@ def edge_bwd_src(P, G, A, z, minv, t, g: GraphIndex, H: int, F: int, want_fp32: 
     dz = None if want_ds else torch.empty((g.E, H), dtype=torch.float32, device=dev)
     ck = g.src_chunks
     part_acc = torch.empty((ck.n_parts, W), dtype=torch.float32, device=dev) if ck.n_parts else None
+    if (SRC_V2 and want_ds and want_planes and not want_fp32 and P.dtype == torch.float32 and F % 4 == 0
+            and P.stride(0) % 4 == 0):
+        # second-generation kernel of the training path (coefficient pre-pass + lean edge loop)
+        coef = torch.empty((max(g.E, 1), 3, H), dtype=torch.float32, device=dev)
+        mask_ptr, mask_scale = _edge_mask_args(edge_drop, g.E, H)
+        with torch.cuda.device(dev):
+            rc = _lib.load().relgat_layer_bwd_src2(
+                _lib.ptr(P), P.stride(0), _lib.ptr(G), _lib.ptr(A), _lib.ptr(z), _lib.ptr(minv), _lib.ptr(t),
+                _lib.ptr(g.colptr), _lib.ptr(g.csc_slot), _lib.ptr(g.csc_dst), _lib.ptr(g.csc_rel),
+                _lib.ptr(ck.chunks), ck.n_chunks, _lib.ptr(ck.parts), ck.n_parts,
+                _lib.ptr(ck.long_node), _lib.ptr(ck.long_part_ptr), ck.n_long, _lib.ptr(part_acc),
+                _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(coef), g.E, mask_ptr, mask_scale, W, H, F, g.R, sm_count(dev),
+                _lib.ptr(_work_counter(dev)), _stream(P))
+        if rc != -2:  # RG_ERR_SHAPE: layout not covered -> first-generation kernel below
+            _lib.check(rc, "relgat_layer_bwd_src2")
+            _count(3 if ck.n_long else 2)
+            return dP, (hi, lo), dz
     with torch.cuda.device(dev):
         rc = _lib.load().relgat_layer_bwd_src(
             _lib.ptr(P), P.stride(0), _lib.ptr(G), int(P.dtype == torch.bfloat16), _lib.ptr(A), _lib.ptr(z),

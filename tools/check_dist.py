@@ -64,8 +64,11 @@ def main():
     worst = max(errs.values())
     print(f"rank {rank}/{world}: rows [{part.lo},{part.hi}) edges {part.E_local} worst rel err {worst:.2e} "
           f"({max(errs, key=errs.get)})", flush=True)
-    tol = 2e-2 if "--halo-bf16" in sys.argv else 1e-4  # stated tolerance of bf16 halo rows / fp32 contract
-    ok = torch.tensor([1 if worst < tol else 0], device=dev)
+    if "--halo-bf16" in sys.argv:  # stated tolerance of the bf16 mode: 2e-2 on values, 2e-1 max-norm on gradients
+        good = all(v < (2e-2 if k in ("loss", "x_local") else 2e-1) for k, v in errs.items())
+    else:
+        good = worst < 1e-4  # fp32 contract
+    ok = torch.tensor([1 if good else 0], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
     if int(ok.item()) != 1:
