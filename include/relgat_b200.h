@@ -227,6 +227,18 @@ int relgat_recon_loss(const float* tr, const float* dst, const float* negdst, in
 int relgat_bernoulli_bits(unsigned int* bits, long long n_words, float p_drop, unsigned long long seed, void* stream);
 int relgat_zero_rows(float* table, long long ld, const long long* ids, long long n, int D, void* stream);
 
+/* ---- ProjectionHead hidden block (core/model/projection.py:48-67: Linear -> GELU -> LayerNorm) ------------------
+ * GELU (exact, erf form) + LayerNorm (biased variance, eps inside the root) of h [M, D] in one pass per direction; the
+ * linears around it run on relgat_gemm_bf16.  fwd: y [M, D], mean / rstd [M] saved.  bwd: dh [M, D], dgamma / dbeta [D]
+ * (NULL to skip) through per-group partials part_g / part_b: float [relgat_gelu_layernorm_groups(M) * D] scratch each,
+ * reduced in group order (reproducible).  gamma / beta may be NULL (no affine). */
+int relgat_gelu_layernorm_fwd(const float* h, const float* gamma, const float* beta, float* y, float* mean,
+                              float* rstd, int M, int D, float eps, void* stream);
+int relgat_gelu_layernorm_groups(int M);
+int relgat_gelu_layernorm_bwd(const float* dy, const float* h, const float* gamma, const float* mean,
+                              const float* rstd, float* dh, float* part_g, float* part_b, float* dgamma,
+                              float* dbeta, int M, int D, void* stream);
+
 /* ---- host-side batch construction (HOST pointers; no GPU involved) --------------------------
  * Replaces the per-sample Python loop of dataset/edge.py:71-115 + trainer/components/
  * relgat_batching.py:5-19 bit for bit: `state` is CPython's MT19937 state (624 words + position, i.e.

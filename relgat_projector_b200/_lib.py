@@ -53,6 +53,9 @@ SIGNATURES = {
     "relgat_margin_loss": (_I, [_P, _I, _I, ctypes.c_float, _I, _P, _P, _P]),
     "relgat_rank_loss": (_I, [_P, _P, _I, _I, _L, _L, _I, _F, _F, _I, _P, _P, _P, _P]),
     "relgat_recon_loss": (_I, [_P, _P, _P, _I, _I, _I, _L, _L, _F, _F, _F, _P, _P, _P, _P, _P, _P]),
+    "relgat_gelu_layernorm_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _F, _P]),
+    "relgat_gelu_layernorm_groups": (_I, [_I]),
+    "relgat_gelu_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "relgat_bernoulli_bits": (_I, [_P, _L, _F, c_ulonglong, _P]),
     "relgat_zero_rows": (_I, [_P, _L, _P, _L, _I, _P]),
     "relgat_host_sample_batch": (_I, [_P, _P, _L, _P, _I, _I, _L, _P, _P, _P]),
@@ -66,7 +69,7 @@ SIGNATURES = {
     "relgat_pull_rows_bf16": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _I, _P]),
 }
 
-ABI_VERSION = 7  # bumped whenever a signature in include/relgat_b200.h changes
+ABI_VERSION = 8  # bumped whenever a signature in include/relgat_b200.h changes
 _lib = None
 
 

@@ -493,3 +493,30 @@ class ReconLossFunction(torch.autograd.Function):
 
 def fused_recon_loss(transformed_src, dst_vec, neg_dst_vec, w_pos: float, w_neg: float, w_mse: float):
     return ReconLossFunction.apply(transformed_src, dst_vec, neg_dst_vec, float(w_pos), float(w_neg), float(w_mse))
+
+
+class GeluLayerNormFunction(torch.autograd.Function):
+    """LayerNorm(GELU(h)) of a ProjectionHead hidden block (reference core/model/projection.py:56-62) as one kernel
+    per direction instead of the two ATen element-wise passes."""
+
+    @staticmethod
+    def forward(ctx, h, gamma, beta, eps):
+        shape = h.shape
+        h2 = h.reshape(-1, shape[-1])
+        y, mean, rstd = ops.gelu_layernorm_fwd(h2.detach(), None if gamma is None else gamma.detach(),
+                                               None if beta is None else beta.detach(), eps)
+        ctx.save_for_backward(h2, gamma, mean, rstd)
+        ctx.has_affine = gamma is not None
+        ctx.shape = shape
+        return y.view(shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        h2, gamma, mean, rstd = ctx.saved_tensors
+        want = ctx.has_affine and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        dh, dgamma, dbeta = ops.gelu_layernorm_bwd(dy.reshape(h2.shape).contiguous(), h2, gamma, mean, rstd, want_params=want)
+        return dh.view(ctx.shape), (dgamma if ctx.has_affine else None), (dbeta if ctx.has_affine else None), None
+
+
+def gelu_layernorm(h, gamma, beta, eps: float = 1e-5):
+    return GeluLayerNormFunction.apply(h, gamma, beta, float(eps))

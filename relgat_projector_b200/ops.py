@@ -576,6 +576,44 @@ def margin_loss(score: torch.Tensor, B: int, K: int, margin: float, projection_l
     return loss, dscore
 
 
+def gelu_layernorm_fwd(h: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor], eps: float):
+    """y = LayerNorm(GELU(h)) over the last dim of h [M, D]; returns (y, mean [M], rstd [M])."""
+    h = _f32c(h, "h")
+    M, D = h.shape
+    y = torch.empty_like(h)
+    mean = torch.empty((M,), dtype=torch.float32, device=h.device)
+    rstd = torch.empty((M,), dtype=torch.float32, device=h.device)
+    with torch.cuda.device(h.device):
+        rc = _lib.load().relgat_gelu_layernorm_fwd(_lib.ptr(h), _lib.ptr(None if gamma is None else _f32c(gamma, "gamma")),
+                                                   _lib.ptr(None if beta is None else _f32c(beta, "beta")), _lib.ptr(y),
+                                                   _lib.ptr(mean), _lib.ptr(rstd), M, D, float(eps), _stream(h))
+    _lib.check(rc, "relgat_gelu_layernorm_fwd")
+    _count(1)
+    return y, mean, rstd
+
+
+def gelu_layernorm_bwd(dy: torch.Tensor, h: torch.Tensor, gamma: Optional[torch.Tensor], mean: torch.Tensor,
+                       rstd: torch.Tensor, want_params: bool = True):
+    """Returns (dh [M, D], dgamma [D] or None, dbeta [D] or None)."""
+    dy, h = _f32c(dy, "dy"), _f32c(h, "h")
+    M, D = h.shape
+    lib = _lib.load()
+    groups = max(int(lib.relgat_gelu_layernorm_groups(M)), 1)
+    dev = h.device
+    dh = torch.empty_like(h)
+    part_g = torch.empty((groups, D), dtype=torch.float32, device=dev)
+    part_b = torch.empty((groups, D), dtype=torch.float32, device=dev)
+    dgamma = torch.empty((D,), dtype=torch.float32, device=dev) if want_params else None
+    dbeta = torch.empty((D,), dtype=torch.float32, device=dev) if want_params else None
+    with torch.cuda.device(dev):
+        rc = lib.relgat_gelu_layernorm_bwd(_lib.ptr(dy), _lib.ptr(h), _lib.ptr(None if gamma is None else _f32c(gamma, "gamma")),
+                                           _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(dh), _lib.ptr(part_g), _lib.ptr(part_b),
+                                           _lib.ptr(dgamma), _lib.ptr(dbeta), M, D, _stream(h))
+    _lib.check(rc, "relgat_gelu_layernorm_bwd")
+    _count(2)
+    return dh, dgamma, dbeta
+
+
 RANK_LOSS_KIND = {"margin": 0, "self_adversarial_loss": 1}
 
 

@@ -1,8 +1,8 @@
 """``ProjectionHead`` with the reference's structure and state-dict keys (reference
 relgat_projector/core/model/projection.py:7-72).  "Next" row §8(f)-1: on CUDA its bias-free linears
 run on the tcgen05 GEMM of the hot path (fp32-accurate bf16 hi/lo split, or single-pass bf16),
-because torch's fp32 SGEMM over all N rows would cost more than the whole GAT stack; GELU and
-LayerNorm stay ATen element-wise ops."""
+because torch's fp32 SGEMM over all N rows would cost more than the whole GAT stack; the GELU + LayerNorm
+between them is one fused kernel per direction (csrc/gelu_ln.cu)."""
 from __future__ import annotations
 
 from typing import Optional
@@ -41,8 +41,21 @@ class ProjectionHead(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if isinstance(self.net, nn.Sequential):
-            for mod in self.net:
+            mods = list(self.net)
+            i = 0
+            while i < len(mods):
+                mod = mods[i]
+                nxt = mods[i + 1] if i + 1 < len(mods) else None
+                if (isinstance(mod, nn.GELU) and getattr(mod, "approximate", "none") == "none"
+                        and isinstance(nxt, nn.LayerNorm) and len(nxt.normalized_shape) == 1
+                        and x.is_cuda and x.dtype == torch.float32):
+                    # GELU + LayerNorm of a hidden block: one fused kernel per direction (csrc/gelu_ln.cu)
+                    from .functional import gelu_layernorm
+                    x = gelu_layernorm(x, nxt.weight, nxt.bias, nxt.eps)
+                    i += 2
+                    continue
                 x = self._run(mod, x)
+                i += 1
         else:
             x = self._run(self.net, x)
         return self.dropout(x)

@@ -386,3 +386,30 @@ def test_dx_gemm_with_fused_backward_prep(dev, with_drop):
     assert rel_err(G.cpu().numpy(), G2.cpu().numpy()) < 1e-6
     assert rel_err(t.cpu().numpy(), t2.cpu().numpy()) < 1e-5
     assert rel_err(hsum.cpu().numpy(), hsum2.cpu().numpy()) < 1e-5
+
+
+def test_fused_gelu_layernorm_matches_torch(dev):
+    """ProjectionHead hidden block (reference core/model/projection.py:56-62): LayerNorm(GELU(h)) fused, forward and
+    every gradient against torch's fp64 ops; and the head as a whole against the ATen composition of the same modules."""
+    g = torch.Generator().manual_seed(4)
+    M, D = 777, 1600
+    h = torch.randn(M, D, generator=g) * 2
+    gamma, beta = torch.randn(D, generator=g), torch.randn(D, generator=g)
+    dy = torch.randn(M, D, generator=g)
+    hr, gr, br = (t.double().clone().requires_grad_(True) for t in (h, gamma, beta))
+    ref = torch.nn.functional.layer_norm(torch.nn.functional.gelu(hr), (D,), gr, br, 1e-5)
+    ref.backward(dy.double())
+    hx, gx, bx = (t.to(dev).requires_grad_(True) for t in (h, gamma, beta))
+    y = RF.gelu_layernorm(hx, gx, bx, 1e-5)
+    y.backward(dy.to(dev))
+    assert rel_err(y.detach().cpu().numpy(), ref.detach().numpy()) < 1e-5
+    assert rel_err(hx.grad.cpu().numpy(), hr.grad.numpy()) < 1e-5
+    assert rel_err(gx.grad.cpu().numpy(), gr.grad.numpy()) < 1e-5
+    assert rel_err(bx.grad.cpu().numpy(), br.grad.numpy()) < 1e-5
+    torch.manual_seed(0)
+    head = R.ProjectionHead(64, 48, num_layers=3, hidden_dim=80).to(dev)
+    x = torch.randn(33, 64, device=dev)
+    want = x
+    for mod in head.net:  # the same modules, composed with ATen ops
+        want = torch.nn.functional.linear(want, mod.weight) if isinstance(mod, torch.nn.Linear) else mod(want)
+    assert rel_err(head(x).detach().cpu().numpy(), want.detach().cpu().numpy()) < 1e-4
