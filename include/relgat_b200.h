@@ -153,7 +153,7 @@ int relgat_layer_bwd_src(const void* P, long long ldp, const void* G, int feat_i
                          int H, int F, int R, int sm_count, int* work_counter, void* stream);
 /* Training-path variant of relgat_layer_bwd_src (second generation): fp32 P / G rows with F % 4 == 0, bf16 planes out,
  * want_ds semantics (rows ldo >= H*F + H*R wide, dS behind dP, no dz).  A pre-pass turns the per-edge gathers of z,
- * t and the softmax statistics (and the exp) into three coefficients per edge and head (coef: float [E*3*H] scratch,
+ * t and the softmax statistics (and the exp) into three coefficients per edge and head (coef: float [E*H*4] scratch,
  * by-source order), which the main loop streams; see csrc/edge_bwd_src2.cu.  Returns RG_ERR_SHAPE for layouts it does
  * not cover (use relgat_layer_bwd_src). */
 int relgat_layer_bwd_src2(const float* P, long long ldp, const float* G, const float* A, const float* z,

@@ -7,7 +7,7 @@
 // t[dst], (max, 1/den)[dst]) and the exp that rebuilds alpha — at 12 warps per SM every one of those instructions
 // costs ~9 cycles of warp time, so the kernel is bound by its instruction count, not by HBM.  Here:
 //   * a pre-pass (bwd_coef_kernel, one thread per edge and head, fully parallel) turns the three gathers and the exp
-//     into three coefficients per edge and head, stored in by-source order:
+//     into three coefficients per edge and head, stored in by-source order as one 16-byte record:
 //         c0 = alpha * m            (weight of G[dst] in dP; m = attention-dropout keep scale or 1)
 //         c1 = alpha * slope * m,   c2 = alpha * slope * t[dst]        =>  dz = c1 * <G[dst], P[src]> - c2
 //     the main loop reads them as a sequential stream;
@@ -27,7 +27,7 @@ struct CoefArgs {
   const int* csc_dst;    // [E]
   const uint32_t* edge_bits;
   float edge_scale;
-  float* coef;           // [E, 3, H]
+  float* coef;           // [E, H, 4] = (c0, c1, c2, 0)
   long long n;           // E * H
   int H;
 };
@@ -46,10 +46,7 @@ __global__ void __launch_bounds__(256) bwd_coef_kernel(const CoefArgs a) {
   const float al = __expf(ee - mi.x) * mi.y;
   const float sl = zz > 0.f ? 1.f : kLeakySlope;
   const float ek = a.edge_bits ? keep_scale1(a.edge_bits, static_cast<long long>(slot) * a.H + h, a.edge_scale) : 1.f;
-  float* c = a.coef + p * 3 * a.H + h;
-  c[0] = al * ek;
-  c[a.H] = al * sl * ek;
-  c[2 * a.H] = al * sl * tt;
+  reinterpret_cast<float4*>(a.coef)[i] = make_float4(al * ek, al * sl * ek, al * sl * tt, 0.f);  // i == p * H + h
 }
 
 constexpr int kSrc2Warps = 12;
@@ -80,9 +77,9 @@ bwd_src2_kernel(const SrcArgs<float, 4> a, const float* __restrict__ coef) {
   const char* p_lane = reinterpret_cast<const char*>(a.P + lane_off);
   const char* g_lane = reinterpret_cast<const char*>(a.G + lane_off);
   const char* g_pf = reinterpret_cast<const char*>(a.G + g * a.hg * a.F) + lane * 128;
+  const char* p_pf = reinterpret_cast<const char*>(a.P + g * a.hg * a.F) + lane * 128;
   const bool pf_lane_ok = lane * 128 < row_bytes;
-  const float* cf_lane = coef + lm.hh;  // + e * 3 * H (+ H, + 2 H)
-  const int cf_stride = 3 * a.H;
+  const float4* cf_lane = reinterpret_cast<const float4*>(coef) + lm.hh;  // + e * H: one 16-byte load per edge
 #define RG_VALID(k_) ((k_) < KV - 1 || last_ok)
 
   const float* a_base;
@@ -105,9 +102,9 @@ bwd_src2_kernel(const SrcArgs<float, 4> a, const float* __restrict__ coef) {
 
   // the three row buffers live for the whole kernel: the guarded last vector is zeroed ONCE (a lane whose last
   // vector lies outside its head never loads into it)
-  float x0[KV][V], x1[KV][V], own_nx[KV][V];
+  float x0[KV][V], x1[KV][V];
 #pragma unroll
-  for (int v = 0; v < V; ++v) { x0[KV - 1][v] = 0.f; x1[KV - 1][v] = 0.f; own_nx[KV - 1][v] = 0.f; }
+  for (int v = 0; v < V; ++v) { x0[KV - 1][v] = 0.f; x1[KV - 1][v] = 0.f; }
 
   int* counter = a.work_counter ? a.work_counter + g : nullptr;
   for (int c = claim_chunk(counter, lane, blockIdx.x * kSrc2Warps + warp); c < a.n_chunks;
@@ -136,14 +133,13 @@ bwd_src2_kernel(const SrcArgs<float, 4> a, const float* __restrict__ coef) {
 #define RG_WIN(arr_, e_) __shfl_sync(0xffffffffu, ((e_) - base < 32) ? arr_##0 : arr_##1, ((e_) - base) & 31)
 
     // issue the loads of edge e_ into buffer x_ (row of G[dst]) and its coefficients; L2 prefetch further ahead
-#define RG_ISSUE(e_, x_, q0_, q1_, q2_)                                                        \
+#define RG_ISSUE(e_, x_, q_)                                                        \
   if ((e_) < e_hi) {                                                                           \
     const int jd = RG_WIN(w_dst, e_);                                                          \
     const float* rowp = reinterpret_cast<const float*>(g_lane + static_cast<unsigned long long>(jd) * g_stride_b); \
     _Pragma("unroll") for (int k = 0; k < KV; ++k)                                             \
       if (RG_VALID(k)) RowVec<float, V>::load_stream(rowp + k * kstride, x_[k]);               \
-    const float* cf = cf_lane + static_cast<long long>(e_) * cf_stride;                        \
-    q0_ = __ldg(cf); q1_ = __ldg(cf + a.H); q2_ = __ldg(cf + 2 * a.H);                         \
+    q_ = __ldg(cf_lane + static_cast<long long>(e_) * a.H);                                    \
     const int ep = (e_) + kSrc2Prefetch - 2;                                                   \
     if (ep < e_hi && ep - base < 64) {                                                         \
       const int jp = RG_WIN(w_dst, ep);                                                        \
@@ -151,12 +147,6 @@ bwd_src2_kernel(const SrcArgs<float, 4> a, const float* __restrict__ coef) {
     }                                                                                          \
   }
 
-#define RG_LOAD_OWN(k_)                                                                        \
-  if ((k_) < nn) {                                                                             \
-    const float* rowp = reinterpret_cast<const float*>(p_lane + static_cast<unsigned long long>(n_lo + (k_)) * p_stride_b); \
-    _Pragma("unroll") for (int kk = 0; kk < KV; ++kk)                                          \
-      if (RG_VALID(kk)) RowVec<float, V>::load_stream(rowp + kk * kstride, own_nx[kk]);        \
-  }
 
     // write the finished row of source k_ (dP planes + dS columns, or the partial row of a split source), clear acc
 #define RG_CLOSE(k_)                                                                           \
@@ -199,16 +189,23 @@ bwd_src2_kernel(const SrcArgs<float, 4> a, const float* __restrict__ coef) {
     __syncwarp();                                                                              \
   }
 
-    // make source k_ current: park its own row (already in own_nx) in shared memory, start loading the next one
+    // make source k_ current: its own row (pulled into L2 when the previous source was opened) goes to the
+    // lane-private shared-memory slots; the next source's row is prefetched.  Sources are consecutive rows of P.
 #define RG_OPEN(k_)                                                                            \
   {                                                                                            \
+    const char* rown = p_lane + static_cast<unsigned long long>(n_lo + (k_)) * p_stride_b;     \
+    if ((k_) + 1 < nn && pf_lane_ok)                                                           \
+      prefetch_l2(p_pf + static_cast<unsigned long long>(n_lo + (k_) + 1) * p_stride_b);       \
+    float ow[KV][V];                                                                           \
+    _Pragma("unroll") for (int v = 0; v < V; ++v) ow[KV - 1][v] = 0.f;                         \
     _Pragma("unroll") for (int kk = 0; kk < KV; ++kk)                                          \
-      RowVec<float, V>::store(p_own + kk * 32 * V, own_nx[kk]);                                \
-    RG_LOAD_OWN((k_) + 1)                                                                      \
+      if (RG_VALID(kk)) RowVec<float, V>::load_stream(reinterpret_cast<const float*>(rown) + kk * kstride, ow[kk]); \
+    _Pragma("unroll") for (int kk = 0; kk < KV; ++kk)                                          \
+      RowVec<float, V>::store(p_own + kk * 32 * V, ow[kk]);                                    \
   }
 
     // one edge: dalpha = <G[dst], P[src]>, dz from the coefficients, dP += c0 * G + dz * A[rel], dS[rel] += dz
-#define RG_EDGE(e_, x_, q0_, q1_, q2_)                                                         \
+#define RG_EDGE(e_, x_, q_)                                                         \
   {                                                                                            \
     while ((e_) == seg_end) { /* the edge belongs to a later source: finish this one */        \
       RG_CLOSE(k_cur)                                                                          \
@@ -226,7 +223,7 @@ bwd_src2_kernel(const SrcArgs<float, 4> a, const float* __restrict__ coef) {
     }                                                                                          \
     float dd = (sd[0] + sd[1]) + (sd[2] + sd[3]);                                              \
     if constexpr (LPHC > 0) dd = head_sum_c<LPHC>(dd); else dd = head_sum(dd, lm.lph);         \
-    const float dzv = fmaf(q1_, dd, -(q2_));                                                   \
+    const float dzv = fmaf(q_.y, dd, -q_.z);                                                   \
     if (lm.sub == 0) ds_sm[hl * a.R + rl] += dzv;                                              \
     const float* ar = a_base + rl * a.F;                                                       \
     _Pragma("unroll") for (int kk = 0; kk < KV; ++kk) {                                        \
@@ -235,7 +232,7 @@ bwd_src2_kernel(const SrcArgs<float, 4> a, const float* __restrict__ coef) {
         if (ASM) RowVec<float, V>::load_shared(ar + kk * kstride, av);                         \
         else RowVec<float, V>::load_cached(ar + kk * kstride, av);                             \
         _Pragma("unroll") for (int v = 0; v < V; ++v)                                          \
-          acc[kk][v] = fmaf(q0_, x_[kk][v], fmaf(dzv, av[v], acc[kk][v]));                     \
+          acc[kk][v] = fmaf(q_.x, x_[kk][v], fmaf(dzv, av[v], acc[kk][v]));                    \
       }                                                                                        \
     }                                                                                          \
   }
@@ -245,13 +242,12 @@ bwd_src2_kernel(const SrcArgs<float, 4> a, const float* __restrict__ coef) {
     for (int kk = 0; kk < KV; ++kk)
 #pragma unroll
       for (int v = 0; v < V; ++v) acc[kk][v] = 0.f;
-    float c00 = 0.f, c01 = 0.f, c02 = 0.f, c10 = 0.f, c11 = 0.f, c12 = 0.f;
+    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
 
     int k_cur = 0;
     int seg_end = part >= 0 ? e_hi : RG_CP(1);
-    RG_LOAD_OWN(0)
-    RG_ISSUE(e_lo, x0, c00, c01, c02)
-    RG_ISSUE(e_lo + 1, x1, c10, c11, c12)
+    RG_ISSUE(e_lo, x0, q0)
+    RG_ISSUE(e_lo + 1, x1, q1)
     RG_OPEN(0)
     int e = e_lo;
     while (e < e_hi) {
@@ -261,11 +257,11 @@ bwd_src2_kernel(const SrcArgs<float, 4> a, const float* __restrict__ coef) {
         w_dst1 = 0; w_rel1 = 0;
         if (base + 32 + lane < e_hi) { w_dst1 = __ldg(a.csc_dst + base + 32 + lane); w_rel1 = __ldg(a.csc_rel + base + 32 + lane); }
       }
-      RG_EDGE(e, x0, c00, c01, c02)
-      RG_ISSUE(e + 2, x0, c00, c01, c02)
+      RG_EDGE(e, x0, q0)
+      RG_ISSUE(e + 2, x0, q0)
       if (e + 1 < e_hi) {
-        RG_EDGE(e + 1, x1, c10, c11, c12)
-        RG_ISSUE(e + 3, x1, c10, c11, c12)
+        RG_EDGE(e + 1, x1, q1)
+        RG_ISSUE(e + 3, x1, q1)
       }
       e += 2;
     }
@@ -279,7 +275,6 @@ bwd_src2_kernel(const SrcArgs<float, 4> a, const float* __restrict__ coef) {
 #undef RG_EDGE
 #undef RG_OPEN
 #undef RG_CLOSE
-#undef RG_LOAD_OWN
 #undef RG_ISSUE
 #undef RG_WIN
 #undef RG_CP
@@ -319,7 +314,7 @@ static int launch_src2(SrcArgs<float, 4> a, const float* coef, int sm_count, cud
 using namespace relgat;
 
 // Training-path variant of relgat_layer_bwd_src (fp32 P / G rows with F % 4 == 0, planes out, want_ds semantics:
-// rows ldo >= H*F + H*R wide, dS in the columns behind dP, no dz).  coef: float [E * 3 * H] scratch.
+// rows ldo >= H*F + H*R wide, dS in the columns behind dP, no dz).  coef: float [E * H * 4] scratch (16-byte aligned).
 // Returns RG_ERR_SHAPE for layouts it does not cover — the caller then uses relgat_layer_bwd_src.
 extern "C" int relgat_layer_bwd_src2(const float* P, long long ldp, const float* G, const float* A, const float* z,
                                      const float* minv, const float* t, const int* colptr, const int* csc_slot,

@@ -251,3 +251,31 @@ def test_node_table_matches_reference_matrix_and_is_memory_mapped(tmp_path):
     assert torch.equal(again, ref)
     with pytest.raises(ValueError):
         storage.write_node_table({1: [1.0, 2.0], 2: [1.0]}, str(tmp_path / "bad"))
+
+
+def test_checkpoint_without_the_frozen_node_table(tmp_path):
+    """storage.save_trainable_state leaves the [N, D_in] input buffer out of the checkpoint (the reference stores it
+    in every one) and load_trainable_state restores every trainable tensor, checking the table's fingerprint."""
+    from relgat_projector_b200 import storage
+    torch.manual_seed(0)
+    x = torch.randn(300, 64)
+    ei = torch.randint(0, 300, (2, 900))
+    et = torch.randint(0, 5, (900,))
+    kw = dict(num_rel=5, gat_out_dim=8, gat_heads=2, gat_num_layers=2, project_to_input_size=True, projection_layers=2)
+    m = R.RelGATModel(x, ei, et, **kw)
+    full = tmp_path / "full.pt"
+    torch.save(m.state_dict(), full)
+    small = storage.save_trainable_state(m, str(tmp_path / "small.pt"))
+    assert small < os.path.getsize(full) - x.numel() * 4 + 4096
+    torch.manual_seed(1)
+    m2 = R.RelGATModel(x.clone(), ei, et, **kw)
+    storage.load_trainable_state(m2, str(tmp_path / "small.pt"))
+    for (k1, v1), (k2, v2) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2), k1
+    storage.load_trainable_state(m2, str(full))  # the reference's own format loads too
+    m3 = R.RelGATModel(x + 1.0, ei, et, **kw)
+    with pytest.raises(ValueError):
+        storage.load_trainable_state(m3, str(tmp_path / "small.pt"))
+    m4 = R.RelGATModel(x, ei, et, **dict(kw, gat_heads=1))
+    with pytest.raises((KeyError, RuntimeError)):
+        storage.load_trainable_state(m4, str(tmp_path / "small.pt"))

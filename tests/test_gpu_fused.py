@@ -413,3 +413,28 @@ def test_fused_gelu_layernorm_matches_torch(dev):
     for mod in head.net:  # the same modules, composed with ATen ops
         want = torch.nn.functional.linear(want, mod.weight) if isinstance(mod, torch.nn.Linear) else mod(want)
     assert rel_err(head(x).detach().cpu().numpy(), want.detach().cpu().numpy()) < 1e-4
+
+
+def test_second_generation_by_source_kernel_equals_the_first(dev, monkeypatch):
+    """csrc/edge_bwd_src2.cu (opt-in, RELGAT_SRC_V2=1) against the default by-source kernel on the training path:
+    same dP planes and dS columns (rounding-level differences: the attention weights are rebuilt in a pre-pass)."""
+    from relgat_projector_b200.graph import GraphIndex
+    gen = torch.Generator(device=dev).manual_seed(8)
+    n, e, r, h, f = 3000, 20000, 11, 4, 40
+    ei = torch.randint(0, n, (2, e), generator=gen, device=dev)
+    ei[1, :1500] = 7  # a destination / source hub exercises the split-segment path
+    ei[0, 1500:2200] = 9
+    et = torch.randint(0, r, (e,), generator=gen, device=dev)
+    g = GraphIndex(ei, et, n, r)
+    P = torch.randn((n, h * f), generator=gen, device=dev)
+    A = torch.randn((h, r, f), generator=gen, device=dev) * 0.2
+    beta = torch.randn((r,), generator=gen, device=dev) * 0.1
+    dY = torch.randn((n, h * f), generator=gen, device=dev)
+    out, _, _, z, minv, bias = ops.edge_fwd(P, A, beta, g, h, f)
+    G, t, _ = ops.edge_bwd_prep(dY, out, bias, h, f, apply_elu=False)
+    res = []
+    for v2 in (False, True):
+        monkeypatch.setattr(ops, "SRC_V2", v2)
+        _, (hi, lo), _ = ops.edge_bwd_src(P, G, A, z, minv, t, g, h, f, want_fp32=False, want_planes=True, want_ds=True)
+        res.append(hi.float() + lo.float())
+    assert rel_err(res[1].cpu().numpy(), res[0].cpu().numpy()) < 1e-5

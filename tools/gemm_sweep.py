@@ -15,6 +15,9 @@ SHAPES = [  # (name, M, N, K, a_mn, b_mn, splits)
     ("P1 = X1 W1^T / dX1", 300_000, 800, 800, False, False, 1),
     ("dW0 = dP^T X0", 800, 1024, 300_000, True, True, None),
     ("dW1 = dP^T X1", 800, 800, 300_000, True, True, None),
+    ("dW0x = [dP|dS]^T X0", 1000, 1024, 300_000, True, True, None),
+    ("dW1x = [dP|dS]^T X1", 1000, 800, 300_000, True, True, None),
+    ("dW1x^T = X1^T [dP|dS]", 800, 1000, 300_000, True, True, None),
 ]
 
 
