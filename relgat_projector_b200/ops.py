@@ -173,6 +173,15 @@ def gemm_dx_prep(dP: Planes, WT: Planes, M: int, N: int, K: int, y: torch.Tensor
     return G, t, hsum
 
 
+def gemm_cost_model(M: int, N: int) -> float:
+    """Padded MMA work of a [M, N] output tile grid, weighted by the measured efficiency of the N tile (tiles narrower
+    than 224 columns run the 3-pass MMA at ~0.8 of the 256-wide rate: tools/gemm_sweep.py) — used to choose which
+    operand of a split-K weight-gradient GEMM becomes M."""
+    bn = int(_lib.load().relgat_gemm_tile_n(int(N)))
+    eff = 1.0 if bn >= 224 else 0.8
+    return (-(-M // 128) * 128) * (-(-N // bn) * bn) / eff
+
+
 def pick_splits_k(M: int, N: int, K: int, device) -> int:
     """Split-K factor for GEMMs with few output tiles and a long reduction (the dW GEMMs): the one
     (<= 16) that fills the persistent grid's waves best, smaller factors winning ties."""

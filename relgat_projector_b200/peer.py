@@ -613,7 +613,7 @@ def backward_steps(part: PeerPartition, grad_out: torch.Tensor, saved: list, wit
             HR, Wd = H * g.R, dPp[0].size(1)
 
             def dw_and_tail():
-                dW_ext = ops.gemm(dPp, True, s["xp"], True, Wd, d_in, n, splits_k=ops.pick_splits_k(Wd, d_in, n, dY.device))
+                dW_ext = _RF.weight_grad_gemm(dPp, s["xp"], Wd, d_in, n, dY.device)
                 Tp = ops.split_bf16(dW_ext[C:C + HR].contiguous(), with_lo)
                 dA_full = ops.gemm(Tp, False, s["Wp"], False, HR, C, d_in)
                 dA_ = torch.stack([dA_full[h * g.R:(h + 1) * g.R, h * F:(h + 1) * F] for h in range(H)])
