@@ -523,9 +523,10 @@ def main():
         roofline = {"kernel": top_tag, "bound": "hbm", "achieved": top.get("gbs"), "peak": peaks["hbm_gbs"],
                     "unit": "GB/s", "frac": top.get("frac_hbm"), "traffic": None}
     roofline["peak_source"] = peaks["source"]
-    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this same
-    # command (profiles/r01_ncu_traffic.json); only meaningful for the configuration it was taken on
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this same command
+    # (profiles/r02_ncu_traffic.json; a number taken under a profiler in an earlier call, labelled as such — ncu cannot
+    # run inside a timed benchmark); only meaningful for the configuration it was taken on
+    tpath = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
     sub = {"edge_fwd": "edge_fwd_kernel", "edge_bwd_src": "bwd_src_kernel", "edge_bwd_rel": "bwd_rel_kernel",
            "edge_bwd_prep": "bwd_prep_kernel", "gemm": "gemm_bf16_tcgen05"}.get(top_tag.split("[")[0])
     if sub and cfg_name == "c2" and args.precision == "fp32" and os.path.exists(tpath):
@@ -534,7 +535,9 @@ def main():
                 if sub in kname:
                     v = rec["dram_bytes_per_launch"]
                     roofline["traffic"] = int(sum(v) / len(v))
-                    roofline["traffic_source"] = "profiles/r01_ncu_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum)"
+                    roofline["traffic_source"] = ("profiles/r02_ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of "
+                                                  "this kernel in the committed ncu --set full capture of this command "
+                                                  "(not measured in this run)")
     sbytes = step_bytes_survey(cfg, E, args.precision)
     step_roof = {"algorithmic_bytes_per_step": sbytes, "achieved_gbs": round(sbytes / (ms * 1e-3) / 1e9, 1),
                  "frac_of_hbm_peak": round(sbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),

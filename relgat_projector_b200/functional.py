@@ -24,8 +24,9 @@ USE_DS = os.environ.get("RELGAT_DS", "1") != "0"
 # OFF by default: measured on config 2, the fused epilogue costs 3.3 ms against 1.30 (GEMM) + 0.61 (prep kernel) — four
 # epilogue warps reading y row-wise cannot keep up with the MMA (profiles/r02_summary.md); kept as an experiment knob.
 FUSE_PREP = os.environ.get("RELGAT_FUSE_PREP", "0") != "0"
-# the small tail of the dS path (dA = T W^T, dbeta) on the side stream (1) or in line on the main stream (0)
-TAIL_ON_SIDE = os.environ.get("RELGAT_TAIL_SIDE", "1") != "0"
+# the small tail of the dS path (dA = T W^T, dbeta: ~60 us per layer) in line on the main stream (0, default) or on the
+# side stream (1); measured alike (13.48 vs 13.52 ms per step), in line keeps the per-kernel timings of bench.py exact
+TAIL_ON_SIDE = os.environ.get("RELGAT_TAIL_SIDE", "0") != "0"
 
 _SIDE_STREAMS = {}
 
