@@ -560,6 +560,25 @@ def main():
         alt = {"dtype": "bf16 feature storage + single-pass bf16 tensor-core operands, fp32 accumulate", "value": E / (ms_alt * 1e-3),
                "unit": UNIT, "ms_per_step": ms_alt, "tolerance": "2e-2 relative (stated, tested)"}
 
+    # side record: the same step with the reference's training dropout (training_scripts/run-relgat-trainer-base-model.sh:
+    # dropout 0.3) — masks drawn per step, applied inside the fused edge kernels
+    drop_rec = None
+    if not args.no_alt_precision:
+        model = opt = None
+        torch.cuda.empty_cache()
+        torch.manual_seed(42)
+        model = R.RelGATModel(kg.node_emb, kg.edge_index, kg.edge_type, num_rel=cfg["R"], scorer_type=cfg["scorer"],
+                              gat_out_dim=cfg["F"], gat_heads=cfg["H"], dropout=0.3, gat_num_layers=cfg["L"],
+                              project_to_input_size=cfg["proj"], projection_layers=2, precision=args.precision).to(dev)
+        model.train()
+        opt = torch.optim.Adam(model.parameters(), lr=2e-4)
+        for i in range(3):
+            train_step(*dev_batches[i % n_pool])
+        ms_drop = timed(lambda i: train_step(*dev_batches[i % n_pool]), max(args.steps // 2, 5))
+        drop_rec = {"dropout": 0.3, "relation_attn_dropout": 0.0, "ms_per_step": ms_drop, "value": E / (ms_drop * 1e-3),
+                    "unit": UNIT, "slowdown_vs_dropout0": round(ms_drop / ms - 1.0, 4),
+                    "note": "one fused autograd node as with dropout 0; keep-bit masks from Philox, applied in edge_fwd / bwd_prep"}
+
     cpu = None
     if not args.no_cpu_baseline:
         big = cfg["N"] >= 100_000
@@ -583,7 +602,7 @@ def main():
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
         "roofline": roofline, "step_roofline": step_roof, "kernels": kernels, "cpu_baseline": cpu,
-        "alt_precision": alt,
+        "alt_precision": alt, "training_dropout": drop_rec,
     }
     print(json.dumps(line))
     return 0

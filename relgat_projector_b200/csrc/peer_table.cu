@@ -95,25 +95,36 @@ extern "C" int relgat_peer_table_map(int device, int world, int rank, unsigned l
   auto release = driver_fn<ReleaseFn>("cuMemRelease");
   if (!importfn || !reserve || !map || !access || !release) return relgat::RG_ERR_DRIVER;
   if (cudaSetDevice(device) != cudaSuccess || cudaFree(nullptr) != cudaSuccess) return relgat::RG_ERR_DRIVER;
+  auto unmap = driver_fn<UnmapFn>("cuMemUnmap");
+  auto freeva = driver_fn<FreeVaFn>("cuMemAddressFree");
+  if (!unmap || !freeva) return relgat::RG_ERR_DRIVER;
   CUdeviceptr va = 0;
   if (int rc = drv(reserve(&va, bytes * world, 0, 0, 0))) return rc;
+  int mapped = 0;
+  // every failure path gives back what has been taken so far: the slots already mapped and the reserved range
+  auto undo = [&](int rc) {
+    for (int s = 0; s < mapped; ++s) unmap(va + static_cast<CUdeviceptr>(s) * bytes, bytes);
+    freeva(va, bytes * world);
+    return rc;
+  };
   for (int s = 0; s < world; ++s) {
     const int owner = (rank + s) % world;
     CUmemGenericAllocationHandle h = own_handle;
     if (owner != rank) {
       if (int rc = drv(importfn(&h, reinterpret_cast<void*>(static_cast<uintptr_t>(peer_fds[owner])),
                                 CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR)))
-        return rc;
+        return undo(rc);
     }
     const int rc = drv(map(va + static_cast<CUdeviceptr>(s) * bytes, bytes, 0, h, 0));
     if (owner != rank) release(h);  // the mapping keeps the peer's allocation alive
-    if (rc) return rc;
+    if (rc) return undo(rc);
+    ++mapped;
   }
   CUmemAccessDesc desc = {};
   desc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
   desc.location.id = device;
   desc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
-  if (int rc = drv(access(va, bytes * world, &desc, 1))) return rc;
+  if (int rc = drv(access(va, bytes * world, &desc, 1))) return undo(rc);
   *base = reinterpret_cast<void*>(va);
   return 0;
 }

@@ -115,50 +115,87 @@ class _DevicePointer:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
 
 
-def _exchange_fds(my_fds: List[int], world: int, rank: int, tag: str) -> List[List[int]]:
-    """Every rank hands its file descriptors to every peer over AF_UNIX sockets (SCM_RIGHTS)."""
-    base = f"/tmp/relgat_peer_{os.environ.get('MASTER_PORT', '0')}_{tag}"
+def _private_socket_dir() -> str:
+    """A directory only this user can enter (mode 0700, ownership verified): the rendezvous sockets live there, so
+    another local user can neither plant a socket under the expected name nor connect to ours."""
+    base = os.path.join(os.environ.get("XDG_RUNTIME_DIR") or "/tmp", f"relgat_peer_{os.getuid()}")
+    os.makedirs(base, mode=0o700, exist_ok=True)
+    st = os.lstat(base)
+    import stat
+    if not stat.S_ISDIR(st.st_mode) or st.st_uid != os.getuid() or (st.st_mode & 0o077):
+        raise RuntimeError(f"peer table exchange: {base} is not a private directory of this user")
+    return base
+
+
+def _peer_uid(conn: socket.socket) -> int:
+    import struct
+    cred = conn.getsockopt(socket.SOL_SOCKET, socket.SO_PEERCRED, struct.calcsize("3i"))
+    _pid, uid, _gid = struct.unpack("3i", cred)
+    return uid
+
+
+def _exchange_fds(my_fds: List[int], world: int, rank: int, tag: str, timeout: float = 120.0) -> List[List[int]]:
+    """Every rank hands its file descriptors to every peer over AF_UNIX sockets (SCM_RIGHTS).  Sockets live in a
+    private per-user directory, a connecting peer must run under the same uid (SO_PEERCRED), and every blocking step
+    has a timeout: a dead peer raises instead of hanging all ranks."""
+    base = os.path.join(_private_socket_dir(), f"{os.environ.get('MASTER_PORT', '0')}_{tag}")
     path = f"{base}_{rank}.sock"
     if os.path.exists(path):
         os.unlink(path)
     srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
     srv.bind(path)
     srv.listen(world)
+    srv.settimeout(timeout)
+    errors: List[BaseException] = []
 
     def serve():
-        for _ in range(world - 1):
-            conn, _addr = srv.accept()
-            with conn:
-                socket.send_fds(conn, [b"f"], my_fds)
-                conn.recv(1)  # the peer confirms it holds the descriptors before we move on
+        try:
+            served = 0
+            while served < world - 1:
+                conn, _addr = srv.accept()
+                with conn:
+                    conn.settimeout(timeout)
+                    if _peer_uid(conn) != os.getuid():
+                        continue  # not one of our ranks: no descriptors for it
+                    socket.send_fds(conn, [b"f"], my_fds)
+                    conn.recv(1)  # the peer confirms it holds the descriptors before we move on
+                    served += 1
+        except BaseException as exc:  # surfaced by the joining thread
+            errors.append(exc)
 
     th = threading.Thread(target=serve, daemon=True)
     th.start()
     got: List[List[int]] = [[] for _ in range(world)]
-    for g in range(world):
-        if g == rank:
-            continue
-        peer_path = f"{base}_{g}.sock"
-        deadline = time.time() + 120
-        while True:
-            try:
+    try:
+        for g in range(world):
+            if g == rank:
+                continue
+            peer_path = f"{base}_{g}.sock"
+            deadline = time.time() + timeout
+            while True:
                 c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-                c.connect(peer_path)
-                break
-            except (FileNotFoundError, ConnectionRefusedError):
-                c.close()
-                if time.time() > deadline:
-                    raise RuntimeError(f"peer table exchange: rank {g} never opened {peer_path}")
-                time.sleep(0.05)
-        with c:
-            _msg, fds, _flags, _addr = socket.recv_fds(c, 16, len(my_fds))
-            if len(fds) != len(my_fds):
-                raise RuntimeError("peer table exchange: short descriptor list")
-            got[g] = list(fds)
-            c.send(b"k")
-    th.join()
-    srv.close()
-    os.unlink(path)
+                try:
+                    c.connect(peer_path)
+                    break
+                except (FileNotFoundError, ConnectionRefusedError):
+                    c.close()
+                    if time.time() > deadline:
+                        raise RuntimeError(f"peer table exchange: rank {g} never opened {peer_path}")
+                    time.sleep(0.05)
+            with c:
+                c.settimeout(timeout)
+                _msg, fds, _flags, _addr = socket.recv_fds(c, 16, len(my_fds))
+                if len(fds) != len(my_fds):
+                    raise RuntimeError("peer table exchange: short descriptor list")
+                got[g] = list(fds)
+                c.send(b"k")
+        th.join(timeout + 10.0)
+        if th.is_alive() or errors:
+            raise RuntimeError(f"peer table exchange: serving the peers failed ({errors[0] if errors else 'timeout'})")
+    finally:
+        srv.close()
+        if os.path.exists(path):
+            os.unlink(path)
     return got
 
 
