@@ -142,7 +142,9 @@ int relgat_layer_fwd(const void* P, int p_is_bf16, long long ldp, const float* A
 int relgat_layer_bwd_prep(const float* dY, const float* out, const float* bias, void* G, int g_is_bf16,
                           float* t, float* hsum, int N, int H, int F, int apply_elu,
                           const long long* row_ids, int n_rows,
-                          const unsigned int* drop_bits, int drop_words, float drop_scale, void* stream);
+                          const unsigned int* drop_bits, int drop_words, float drop_scale,
+                          void* G_export_bf16 /* optional bf16 copy of G for the peers' pulls; NULL = none */,
+                          void* stream);
 int relgat_layer_bwd_src(const void* P, long long ldp, const void* G, int feat_is_bf16, const float* A,
                          const float* z, const float* minv, const float* t,
                          const int* colptr, const int* csc_slot, const int* csc_dst, const int* csc_rel,

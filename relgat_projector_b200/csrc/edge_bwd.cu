@@ -36,6 +36,7 @@ struct PrepArgs {
   const uint32_t* drop_bits;
   int drop_words;
   float drop_scale;
+  __nv_bfloat16* G_export;  // optional bf16 copy of G (what the peers pull on the partitioned path); fp32 G only
 };
 
 template <typename TG, int V>
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32) bwd_prep_kernel(const PrepArgs
       }
       if (static_cast<const void*>(a.G) != static_cast<const void*>(a.dY) || a.apply_elu || a.drop_bits)
         RowVec<TG, V>::store(a.G + row + q * V, dy);
+      if (a.G_export) store_split_bf16<V>(a.G_export + row + q * V, nullptr, dy);
     }
   }
   tt = head_sum(tt, lm.lph);
@@ -280,9 +282,11 @@ extern template int run_src<__nv_bfloat16, 8>(const void*, long long, const void
 extern "C" int relgat_layer_bwd_prep(const float* dY, const float* out, const float* bias, void* G, int g_is_bf16,
                                      float* t, float* hsum, int N, int H, int F, int apply_elu,
                                      const long long* row_ids, int n_rows,
-                                     const unsigned int* drop_bits, int drop_words, float drop_scale, void* stream) {
+                                     const unsigned int* drop_bits, int drop_words, float drop_scale,
+                                     void* G_export_bf16, void* stream) {
   if (!dY || !out || !G || !t || !hsum || N < 0 || H <= 0 || F <= 0 || n_rows < 0) return RG_ERR_ARG;
   if (drop_bits && drop_words * 32 < H * F) return RG_ERR_ARG;
+  if (G_export_bf16 && (g_is_bf16 || F % 4 != 0 || reinterpret_cast<uintptr_t>(G_export_bf16) % 8 != 0)) return RG_ERR_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int rows = N;
   if (row_ids) {
@@ -299,19 +303,22 @@ extern "C" int relgat_layer_bwd_prep(const float* dY, const float* out, const fl
     if (!al16(dY) || !al16(out) || !al16(G)) return RG_ERR_ALIGN;
     const int hg = pick_heads_per_warp(H, F, 8);
     if (!hg) return RG_ERR_SHAPE;
-    PrepArgs<__nv_bfloat16, 8> a{dY, out, bias, static_cast<__nv_bfloat16*>(G), t, hsum, rows, H, F, hg, apply_elu, row_ids, drop_bits, drop_words, drop_scale};
+    PrepArgs<__nv_bfloat16, 8> a{dY, out, bias, static_cast<__nv_bfloat16*>(G), t, hsum, rows, H, F, hg, apply_elu, row_ids, drop_bits, drop_words, drop_scale,
+                                      static_cast<__nv_bfloat16*>(G_export_bf16)};
     return launch_tasks(bwd_prep_kernel<__nv_bfloat16, 8>, a, static_cast<long long>(rows) * (H / hg), s);
   }
   float* Gf = static_cast<float*>(G);
   if (F % 4 == 0 && al16(dY) && al16(out) && al16(G)) {
     const int hg = pick_heads_per_warp(H, F, 4);
     if (!hg) return RG_ERR_SHAPE;
-    PrepArgs<float, 4> a{dY, out, bias, Gf, t, hsum, rows, H, F, hg, apply_elu, row_ids, drop_bits, drop_words, drop_scale};
+    PrepArgs<float, 4> a{dY, out, bias, Gf, t, hsum, rows, H, F, hg, apply_elu, row_ids, drop_bits, drop_words, drop_scale,
+                                      static_cast<__nv_bfloat16*>(G_export_bf16)};
     return launch_tasks(bwd_prep_kernel<float, 4>, a, static_cast<long long>(rows) * (H / hg), s);
   }
   const int hg = pick_heads_per_warp(H, F, 1);
   if (!hg) return RG_ERR_SHAPE;
-  PrepArgs<float, 1> a{dY, out, bias, Gf, t, hsum, rows, H, F, hg, apply_elu, row_ids, drop_bits, drop_words, drop_scale};
+  PrepArgs<float, 1> a{dY, out, bias, Gf, t, hsum, rows, H, F, hg, apply_elu, row_ids, drop_bits, drop_words, drop_scale,
+                                      static_cast<__nv_bfloat16*>(G_export_bf16)};
   return launch_tasks(bwd_prep_kernel<float, 1>, a, static_cast<long long>(rows) * (H / hg), s);
 }
 

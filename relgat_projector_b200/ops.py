@@ -333,11 +333,20 @@ def edge_fwd(P: torch.Tensor, A: torch.Tensor, beta: Optional[torch.Tensor], g: 
     return out, ((hi, lo) if want_act else None), alpha, z, minv, bias
 
 
+def _export_buf(buf: Optional[torch.Tensor], like: torch.Tensor) -> Optional[torch.Tensor]:
+    if buf is None:
+        return None
+    _lib.require_cuda(buf)
+    if buf.dtype != torch.bfloat16 or tuple(buf.shape) != tuple(like.shape) or not buf.is_contiguous():
+        raise ValueError("g_export must be a contiguous bfloat16 tensor of dY's shape")
+    return buf
+
+
 def edge_bwd_prep(dY: torch.Tensor, out: torch.Tensor, bias: torch.Tensor, H: int, F: int,
                   apply_elu: bool, inplace: bool = False, g_bf16: bool = False,
                   G_out: Optional[torch.Tensor] = None, t_out: Optional[torch.Tensor] = None,
                   hsum_out: Optional[torch.Tensor] = None, nonzero_rows: Optional[torch.Tensor] = None,
-                  feat_drop: Optional["DropMask"] = None):
+                  feat_drop: Optional["DropMask"] = None, g_export: Optional[torch.Tensor] = None):
     """Returns (G [N,C] fp32 or bf16, t [N,H], hsum [N,H]).  ``G_out`` / ``t_out`` / ``hsum_out``:
     caller-owned fp32 buffers (rows of a peer table on the partitioned path).  ``nonzero_rows`` (int64, may
     repeat): all other rows of dY are known to be zero; used only when G can alias dY (fp32, no activation)."""
@@ -361,7 +370,8 @@ def edge_bwd_prep(dY: torch.Tensor, out: torch.Tensor, bias: torch.Tensor, H: in
         rc = _lib.load().relgat_layer_bwd_prep(_lib.ptr(dY), _lib.ptr(out), _lib.ptr(bias), _lib.ptr(G), int(g_bf16),
                                                _lib.ptr(t), _lib.ptr(hsum), N, H, F, int(apply_elu),
                                                _lib.ptr(rows), 0 if rows is None else int(rows.numel()),
-                                               *_feat_mask_args(feat_drop, N, H * F), _stream(dY))
+                                               *_feat_mask_args(feat_drop, N, H * F), _lib.ptr(_export_buf(g_export, dY)),
+                                               _stream(dY))
     _lib.check(rc, "relgat_layer_bwd_prep")
     _count(1)
     return G, t, hsum

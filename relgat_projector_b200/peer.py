@@ -620,9 +620,8 @@ def backward_steps(part: PeerPartition, grad_out: torch.Tensor, saved: list, wit
                 if r1 > r0:
                     ops.edge_bwd_prep(dY[r0:r1], s["out"][r0:r1], s["bias"][r0:r1], H, F, apply_elu=(l < L - 1),
                                       G_out=T[f"G{l}"].local[r0:r1], t_out=T[f"t{l}"].local[r0:r1],
-                                      hsum_out=T[f"hsum{l}"].local[r0:r1])
-                    if part.halo_bf16:
-                        part.export_rows(f"G{l}", f"Gb{l}", r0, r1)
+                                      hsum_out=T[f"hsum{l}"].local[r0:r1],
+                                      g_export=T[f"Gb{l}"].local[r0:r1] if part.halo_bf16 else None)
                 _mark(f"bwd{l} prep block {c} done")
                 yield  # every rank's block c of G / t / hsum is written
                 _mark(f"bwd{l} rendezvous {c} done")

@@ -13,6 +13,7 @@ import os
 import re
 import sys
 import tempfile
+import time
 
 import torch
 
@@ -64,7 +65,8 @@ def main():
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         for i in range(3):
             step(i)
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()  # a clear gap between steps (the idle time right after it is launch latency)
+            time.sleep(0.02)
     tmp = tempfile.mktemp(suffix=".json")
     prof.export_chrome_trace(tmp)
     with open(tmp) as f:
