@@ -373,6 +373,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt-precision", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=3)
+    ap.add_argument("--backward", default="dense", choices=["dense", "sparse"],
+                    help="dense (headline): the by-source pass gathers G[dst] for every edge, SURVEY.md §8(d)'s unit of work; "
+                         "sparse: edges into rows whose gradient is an exact zero are skipped (the library's default; same "
+                         "gradients bit for bit) — always reported beside the headline as exact_sparse_backward")
     ap.add_argument("--ref-scale", type=int, default=1,
                     help="--impl reference: run the configuration at 1/SCALE of its nodes and triplets (default 1: in full)")
     args = ap.parse_args()
@@ -421,7 +425,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     import relgat_projector_b200 as R
-    from relgat_projector_b200 import loss as L, ops
+    from relgat_projector_b200 import functional as RFn, loss as L, ops
+    RFn.SPARSE_BWD = args.backward == "sparse"
 
     kg = S.tensor_kg(cfg["N"], cfg["T"], cfg["R"], cfg["D_in"], seed=42, device=str(dev))
     E = int(kg.edge_index.size(1))
@@ -491,7 +496,6 @@ def main():
             train_step(*dev_batches[i % n_pool])
         table = prof.table(psteps)
     g = model._graph()
-    from relgat_projector_b200 import functional as RFn
     work = kernel_work(cfg, E, g.n_chunks, args.precision, use_ds=RFn.USE_DS)
     peaks = load_peaks()
     kernels = {}
@@ -543,6 +547,26 @@ def main():
                  "frac_of_hbm_peak": round(sbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
                  "formula": "SURVEY.md §8(d) bytes_step, fp32"}
 
+    # side record: the same step with the exact-zero rows of the output gradient skipped in the by-source passes (the
+    # library default, functional.SPARSE_BWD): identical gradients, fewer gathers; a different unit of work than §8(d)'s
+    sparse_rec = None
+    if args.backward == "dense" and not args.no_alt_precision and RFn.USE_DS:
+        RFn.SPARSE_BWD = True
+        for i in range(3):
+            train_step(*dev_batches[i % n_pool])
+        ms_sp = timed(lambda i: train_step(*dev_batches[i % n_pool]), max(args.steps // 2, 5))
+        with KernelProfiler() as prof:
+            for i in range(psteps):
+                train_step(*dev_batches[i % n_pool])
+            tsp = prof.table(psteps)
+        RFn.SPARSE_BWD = False
+        sparse_rec = {"ms_per_step": ms_sp, "value": E / (ms_sp * 1e-3), "unit": UNIT,
+                      "speedup_vs_dense": round(ms / ms_sp, 4),
+                      "edge_bwd_src_avg_ms": [round(d["avg_ms"], 4) for t_, d in tsp.items() if d["kernel"] == "edge_bwd_src"],
+                      "note": "edges into rows of dL/d out that are exact zeros (outside the batch rows at the last layer, "
+                              "outside their in-neighbourhood one layer down) are skipped; bit-identical gradients "
+                              "(tests/test_gpu_fused.py); edges/s still counts all E edges of the graph"}
+
     # secondary record: single-pass bf16 tensor-core operands (stated tolerance 2e-2, tests/test_gpu_model.py)
     alt = None
     if args.precision == "fp32" and not args.no_alt_precision:
@@ -593,6 +617,7 @@ def main():
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32" if args.precision == "fp32" else "bf16", "data": "synthetic",
         "config": dict(workload_config(cfg_name, cfg, E), precision=args.precision),
+        "backward": args.backward,
         "precision_note": ("fp32 storage; tensor-core GEMMs on bf16 hi/lo splits (3 passes, ~fp32 accuracy)"
                            if args.precision == "fp32" else
                            "bf16 storage of P / G / dP rows; single-pass bf16 tensor-core GEMMs; fp32 accumulate"),
@@ -602,7 +627,7 @@ def main():
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
         "roofline": roofline, "step_roofline": step_roof, "kernels": kernels, "cpu_baseline": cpu,
-        "alt_precision": alt, "training_dropout": drop_rec,
+        "alt_precision": alt, "training_dropout": drop_rec, "exact_sparse_backward": sparse_rec,
     }
     print(json.dumps(line))
     return 0

@@ -151,8 +151,10 @@ int relgat_layer_bwd_src(const void* P, long long ldp, const void* G, int feat_i
                          const int* chunks, int n_chunks, const int* parts, int n_parts,
                          const int* long_node, const int* long_part_ptr, int n_long, float* part_acc,
                          float* dP, void* dP_hi, void* dP_lo, float* dz,
-                         const unsigned int* edge_bits, float edge_scale, int want_ds, long long ldo,
-                         int H, int F, int R, int sm_count, int* work_counter, void* stream);
+                         const unsigned int* edge_bits, float edge_scale,
+                         const unsigned int* dst_nz_bits /* want_ds only: bit j = row j of G may be non-zero (edges into
+                            other rows are skipped: their G[dst], t[dst] and hence dz are exact zeros); NULL = all rows */,
+                         int want_ds, long long ldo, int H, int F, int R, int sm_count, int* work_counter, void* stream);
 /* Training-path variant of relgat_layer_bwd_src (second generation): fp32 P / G rows with F % 4 == 0, bf16 planes out,
  * want_ds semantics (rows ldo >= H*F + H*R wide, dS behind dP, no dz).  A pre-pass turns the per-edge gathers of z,
  * t and the softmax statistics (and the exp) into three coefficients per edge and head (coef: float [E*H*4] scratch,
@@ -228,6 +230,16 @@ int relgat_recon_loss(const float* tr, const float* dst, const float* negdst, in
  * the batch gradient that relgat_index_add_sorted scattered into a persistent zero table). */
 int relgat_bernoulli_bits(unsigned int* bits, long long n_words, float p_drop, unsigned long long seed, void* stream);
 int relgat_zero_rows(float* table, long long ld, const long long* ids, long long n, int D, void* stream);
+
+/* Row-set bitmaps for the backward's exact-zero hint (dst_nz_bits of relgat_layer_bwd_src).  The loss reads
+ * <= B*(2+K) rows of the stack's output (model.py:136-137), so the gradient of the last layer's output is zero outside
+ * them, and the gradient of layer l's output is zero outside the sources of the edges into layer l+1's non-zero rows.
+ * bits: uint32[ceil(n_rows / 32)], caller-zeroed, bit j = row j may be non-zero.
+ *   relgat_mark_rows:    bits |= {ids[i]}                       (ids outside [0, n_rows) are ignored)
+ *   relgat_mark_sources: src_bits |= {csr_src[e] : rowptr[j] <= e < rowptr[j+1], j marked in dst_bits} */
+int relgat_mark_rows(const long long* ids, long long n, long long n_rows, unsigned int* bits, void* stream);
+int relgat_mark_sources(const unsigned int* dst_bits, const int* rowptr, const int* csr_src, int n_dst,
+                        unsigned int* src_bits, void* stream);
 
 /* ---- ProjectionHead hidden block (core/model/projection.py:48-67: Linear -> GELU -> LayerNorm) ------------------
  * GELU (exact, erf form) + LayerNorm (biased variance, eps inside the root) of h [M, D] in one pass per direction; the

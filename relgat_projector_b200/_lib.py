@@ -42,7 +42,9 @@ SIGNATURES = {
                               _P, _I, _F, _P, _F, _I, _I, _I, _I, _P, _P]),
     "relgat_layer_bwd_prep": (_I, [_P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P, _I, _F, _P, _P]),
     "relgat_layer_bwd_src": (_I, [_P, _L, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P,
-                                  _P, _F, _I, _L, _I, _I, _I, _I, _P, _P]),
+                                  _P, _F, _P, _I, _L, _I, _I, _I, _I, _P, _P]),
+    "relgat_mark_rows": (_I, [_P, _L, _L, _P, _P]),
+    "relgat_mark_sources": (_I, [_P, _P, _P, _I, _P, _P]),
     "relgat_layer_bwd_src2": (_I, [_P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _L,
                                    _P, _F, _L, _I, _I, _I, _I, _P, _P]),
     "relgat_layer_bwd_beta": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _P]),
@@ -69,7 +71,7 @@ SIGNATURES = {
     "relgat_pull_rows_bf16": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _I, _P]),
 }
 
-ABI_VERSION = 9  # bumped whenever a signature in include/relgat_b200.h changes
+ABI_VERSION = 10  # bumped whenever a signature in include/relgat_b200.h changes
 _lib = None
 
 

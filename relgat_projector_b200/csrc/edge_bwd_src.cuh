@@ -53,6 +53,10 @@ struct SrcArgs {
   // dS^T X, from which dA = (dS^T X) W^T follows without a third gather of P (the by-relation pass).
   int ds_on;
   long long ldo;        // row stride of dP / dP_hi / dP_lo / part_acc in elements (C, or C + H*R with ds_on)
+  // exact-zero hint (ds_on only): bit j set = row j of G may be non-zero.  An edge into a row whose bit is clear has
+  // G[dst] = 0 and t[dst] = 0, hence dz = 0 and no contribution to dP or dS: it is skipped without touching memory.
+  // nullptr = every row may be non-zero.
+  const uint32_t* nz_bits;
 };
 
 // DS: logit-table gradient columns on (a.ds_on), compile-time so that the plain variants carry none of its code.
@@ -144,6 +148,7 @@ __global__ void __launch_bounds__((PIPE ? kSrcWarpsPipe : kSrcWarps) * 32, 1) bw
     bool end_done = false;  // the closing IT_END item already handed out
     int base = e_lo - 32;   // edge-metadata window [base, base + 32) held across the lanes
     int my_slot = 0, my_dst = 0, my_rel = 0;
+    unsigned nzmask = 0xffffffffu;  // window lanes whose destination row may be non-zero (a.nz_bits)
     int cur = -1;           // source being accumulated by the consumer (-1: none yet)
 
     // next item of the stream: OWN(k) | ZERO(k) (source without out-edges) | EDGE | END | NONE
@@ -166,21 +171,32 @@ __global__ void __launch_bounds__((PIPE ? kSrcWarpsPipe : kSrcWarps) * 32, 1) bw
         if (fe >= base + 32) {                                                                 \
           base = fe;                                                                           \
           const int idx = base + lane;                                                         \
+          int my_nz = 0;                                                                       \
           if (idx < e_hi) {                                                                    \
             my_slot = __ldg(a.csc_slot + idx);                                                 \
             my_dst = __ldg(a.csc_dst + idx);                                                   \
             my_rel = __ldg(a.csc_rel + idx);                                                   \
+            my_nz = (DS && a.nz_bits) ? ((__ldg(a.nz_bits + (my_dst >> 5)) >> (my_dst & 31)) & 1u) : 1; \
           }                                                                                    \
+          nzmask = __ballot_sync(0xffffffffu, my_nz);                                          \
           for (int pf = 0; pf < a.pf_dist; ++pf) { /* warm L2 with the window's first rows */  \
             const int jp = __shfl_sync(0xffffffffu, my_dst, pf);                               \
-            if (pf_lane_ok && base + pf < e_hi)                                                \
+            if (pf_lane_ok && ((nzmask >> pf) & 1u))                                           \
               prefetch_l2(g_pf + static_cast<unsigned long long>(jp) * g_stride_b);            \
+          }                                                                                    \
+        }                                                                                      \
+        if (DS && a.nz_bits) { /* jump over the edges whose gradient row is an exact zero */   \
+          const unsigned rem = nzmask >> (fe - base);                                          \
+          const int skip = rem ? __ffs(rem) - 1 : 32;                                          \
+          if (skip) {                                                                          \
+            fe = min(fe + skip, min(base + 32, f_end));                                        \
+            continue;                                                                          \
           }                                                                                    \
         }                                                                                      \
         if (a.pf_dist > 0) { /* rolling prefetch, pf_dist edges ahead inside the window */      \
           const int tp = fe - base + a.pf_dist;                                                \
           const int jp = __shfl_sync(0xffffffffu, my_dst, tp & 31);                            \
-          if (pf_lane_ok && tp < 32 && base + tp < e_hi)                                       \
+          if (pf_lane_ok && tp < 32 && ((nzmask >> tp) & 1u))                                  \
             prefetch_l2(g_pf + static_cast<unsigned long long>(jp) * g_stride_b);              \
         }                                                                                      \
         sl_ = __shfl_sync(0xffffffffu, my_slot, fe - base);                                    \
@@ -490,8 +506,8 @@ int run_src(const void* P, long long ldp, const void* G, const float* A, const f
                    const float* t, const int* colptr, const int* csc_slot, const int* csc_dst, const int* csc_rel,
                    const int4* ch, int n_chunks, const int2* pt, const int* long_node, const int* long_part_ptr,
                    int n_long, float* part_acc, float* dP, void* dP_hi, void* dP_lo, float* dz,
-                   const uint32_t* edge_bits, float edge_scale, int ds_on, long long ldo, int H, int F, int R,
-                   int sm_count, int* work_counter, cudaStream_t s) {
+                   const uint32_t* edge_bits, float edge_scale, const uint32_t* nz_bits, int ds_on, long long ldo,
+                   int H, int F, int R, int sm_count, int* work_counter, cudaStream_t s) {
   const int hg = pick_heads_per_warp(H, F, V, R, smem_budget_override("RELGAT_SRC_BUDGET_KB", kSmemBudgetA));
   if (!hg) return RG_ERR_SHAPE;
   if (H / hg > 32) return RG_ERR_SHAPE;  // work_counter holds 32 ints (one per head-group)
@@ -502,7 +518,7 @@ int run_src(const void* P, long long ldp, const void* G, const float* A, const f
   SrcArgs<T, V> a{static_cast<const T*>(P), static_cast<const T*>(G), A, z, minv, t, colptr, csc_slot, csc_dst,
                   csc_rel, ch, pt, part_acc, dP, static_cast<__nv_bfloat16*>(dP_hi),
                   static_cast<__nv_bfloat16*>(dP_lo), dz, n_chunks, H, F, R, hg, ldp, 0, 0, work_counter,
-                  edge_bits, edge_scale, ds_on, ldo};
+                  edge_bits, edge_scale, ds_on, ldo, ds_on ? nz_bits : nullptr};
   int rc = launch_src(a, sm_count, s);
   if (rc != RG_OK || n_long == 0) return rc;
   bwd_src_merge_kernel<T, V><<<n_long, 128, 0, s>>>(a, long_node, long_part_ptr, n_long);

@@ -59,9 +59,52 @@ __global__ void zero_rows_kernel(float* __restrict__ table, long long ld, const 
   }
 }
 
+// row-set bitmaps of the backward's exact-zero hint (relgat_layer_bwd_src, dst_nz_bits): bit j = row j of the
+// gradient table may be non-zero.  atomicOr is idempotent, so the result does not depend on the thread order.
+__global__ void mark_rows_kernel(const long long* __restrict__ ids, long long n, long long n_rows,
+                                 uint32_t* __restrict__ bits) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const long long j = ids[i];
+  if (j >= 0 && j < n_rows) atomicOr(bits + (j >> 5), 1u << (j & 31));
+}
+
+// sources of the edges into marked destinations: the rows of dP — hence of the gradient handed to the layer below —
+// that can be non-zero
+__global__ void mark_sources_kernel(const uint32_t* __restrict__ dst_bits, const int* __restrict__ rowptr,
+                                    const int* __restrict__ csr_src, int n_dst, uint32_t* __restrict__ src_bits) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_dst) return;
+  if (!((__ldg(dst_bits + (j >> 5)) >> (j & 31)) & 1u)) return;
+  const int e1 = __ldg(rowptr + j + 1);
+  for (int e = __ldg(rowptr + j); e < e1; ++e) {
+    const int i = __ldg(csr_src + e);
+    atomicOr(src_bits + (i >> 5), 1u << (i & 31));
+  }
+}
+
 }  // namespace relgat
 
 using namespace relgat;
+
+extern "C" int relgat_mark_rows(const long long* ids, long long n, long long n_rows, unsigned int* bits, void* stream) {
+  if (n < 0 || n_rows < 0) return RG_ERR_ARG;
+  if (n == 0) return RG_OK;
+  if (!ids || !bits) return RG_ERR_ARG;
+  mark_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(ids, n, n_rows,
+                                                                                                       bits);
+  return cuda_status(cudaGetLastError());
+}
+
+extern "C" int relgat_mark_sources(const unsigned int* dst_bits, const int* rowptr, const int* csr_src, int n_dst,
+                                   unsigned int* src_bits, void* stream) {
+  if (n_dst < 0) return RG_ERR_ARG;
+  if (n_dst == 0) return RG_OK;
+  if (!dst_bits || !rowptr || !csr_src || !src_bits) return RG_ERR_ARG;
+  mark_sources_kernel<<<(n_dst + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(dst_bits, rowptr, csr_src,
+                                                                                         n_dst, src_bits);
+  return cuda_status(cudaGetLastError());
+}
 
 extern "C" int relgat_bernoulli_bits(unsigned int* bits, long long n_words, float p_drop, unsigned long long seed,
                                      void* stream) {

@@ -27,6 +27,12 @@ FUSE_PREP = os.environ.get("RELGAT_FUSE_PREP", "0") != "0"
 # the small tail of the dS path (dA = T W^T, dbeta: ~60 us per layer) in line on the main stream (0, default) or on the
 # side stream (1); measured alike (13.48 vs 13.52 ms per step), in line keeps the per-kernel timings of bench.py exact
 TAIL_ON_SIDE = os.environ.get("RELGAT_TAIL_SIDE", "0") != "0"
+# exact-zero rows of the output gradient: the loss reads <= B*(2+K) rows of the stack's output, so dL/d out_L is zero
+# outside them and dL/d out_l is zero outside the sources of the edges into layer l+1's non-zero rows.  The by-source
+# pass skips the edges into rows known to be zero (their dz and their contribution to dP are exact zeros): same gradient,
+# fewer gathers.  RELGAT_SPARSE_BWD=0 gathers every edge (bench.py's headline does, so that its unit of work stays the
+# dense pass of SURVEY.md §8(d); the sparse pass is reported beside it).
+SPARSE_BWD = os.environ.get("RELGAT_SPARSE_BWD", "1") != "0"
 
 _SIDE_STREAMS = {}
 
@@ -210,6 +216,7 @@ class RelGATStackFunction(torch.autograd.Function):
             dY = grad_out.contiguous()
             nz_rows = sparse_rows_of(grad_out) if dY is grad_out else None
             owned = False
+        nz_bits = ops.mark_rows(nz_rows, N) if (SPARSE_BWD and USE_DS and nz_rows is not None) else None
         dX = None
         prepped = None  # (G, t, hsum) of layer l when the dX GEMM of layer l+1 produced them in its epilogue
         fuse_prep = USE_DS and FUSE_PREP and with_lo and ops.gemm_dx_prep_supported(C, F)
@@ -226,7 +233,9 @@ class RelGATStackFunction(torch.autograd.Function):
                                                feat_drop=dl.feat if dl else None)
             _, dPp, dz = ops.edge_bwd_src(s["P"], G, s["A"], s["z"], s["minv"], t, g, H, F,
                                           want_fp32=False, want_planes=True, planes_lo=with_lo,
-                                          edge_drop=dl.edge if dl else None, want_ds=USE_DS)
+                                          edge_drop=dl.edge if dl else None, want_ds=USE_DS, dst_nz=nz_bits)
+            if nz_bits is not None and l > 0:
+                nz_bits = ops.mark_sources(nz_bits, g)  # rows of dP, hence of dL/d out_{l-1}, that can be non-zero
             if table is not None and l == L - 1:
                 ops.zero_rows(table, nz_rows)  # the table's rows are consumed (G aliased it): make it all-zero again
                 _return_zero_table(table)

@@ -389,9 +389,11 @@ def ds_row_width(H: int, F: int, R: int) -> int:
 
 def edge_bwd_src(P, G, A, z, minv, t, g: GraphIndex, H: int, F: int, want_fp32: bool = True,
                  want_planes: bool = False, planes_lo: bool = True, edge_drop: Optional["DropMask"] = None,
-                 want_ds: bool = False):
+                 want_ds: bool = False, dst_nz: Optional[torch.Tensor] = None):
     """Returns (dP fp32 or None, dP planes or None, dz [E,H] or None).  ``want_ds``: the rows are
-    ``ds_row_width`` wide, columns H*F + h*R + r hold dS and dz is not written."""
+    ``ds_row_width`` wide, columns H*F + h*R + r hold dS and dz is not written.
+    ``dst_nz`` (want_ds only): row bitmap from ``mark_rows`` / ``mark_sources`` — rows of G outside it are exact zeros
+    (and so are their t), the edges into them are skipped."""
     P = _feat(P, "P")
     G = _feat(G, "G")
     if P.dtype != G.dtype:
@@ -409,8 +411,13 @@ def edge_bwd_src(P, G, A, z, minv, t, g: GraphIndex, H: int, F: int, want_fp32: 
     dz = None if want_ds else torch.empty((g.E, H), dtype=torch.float32, device=dev)
     ck = g.src_chunks
     part_acc = torch.empty((ck.n_parts, W), dtype=torch.float32, device=dev) if ck.n_parts else None
+    if dst_nz is not None:
+        if not want_ds:
+            raise ValueError("dst_nz needs want_ds (the dz output of the plain variant is not written for skipped edges)")
+        if dst_nz.dtype != torch.int32 or dst_nz.device != dev or dst_nz.numel() < (g.N + 31) // 32:
+            raise ValueError("dst_nz must be an int32 bitmap of ceil(N / 32) words on the feature device")
     if (SRC_V2 and want_ds and want_planes and not want_fp32 and P.dtype == torch.float32 and F % 4 == 0
-            and P.stride(0) % 4 == 0):
+            and P.stride(0) % 4 == 0 and dst_nz is None):
         # second-generation kernel of the training path (coefficient pre-pass + lean edge loop)
         coef = torch.empty((max(g.E, 1), H, 4), dtype=torch.float32, device=dev)
         mask_ptr, mask_scale = _edge_mask_args(edge_drop, g.E, H)
@@ -433,10 +440,41 @@ def edge_bwd_src(P, G, A, z, minv, t, g: GraphIndex, H: int, F: int, want_fp32: 
             _lib.ptr(ck.chunks), ck.n_chunks, _lib.ptr(ck.parts), ck.n_parts,
             _lib.ptr(ck.long_node), _lib.ptr(ck.long_part_ptr), ck.n_long, _lib.ptr(part_acc),
             _lib.ptr(dP), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dz), *_edge_mask_args(edge_drop, g.E, H),
-            int(want_ds), W, H, F, g.R, sm_count(dev), _lib.ptr(_work_counter(dev)), _stream(P))
+            _lib.ptr(dst_nz), int(want_ds), W, H, F, g.R, sm_count(dev), _lib.ptr(_work_counter(dev)), _stream(P))
     _lib.check(rc, "relgat_layer_bwd_src")
     _count(2 if ck.n_long else 1)
     return dP, ((hi, lo) if want_planes else None), dz
+
+
+def row_bitmap(n_rows: int, device) -> torch.Tensor:
+    """All-clear row bitmap (int32 words, bit j of word j >> 5 = row j) for mark_rows / mark_sources."""
+    return torch.zeros(((n_rows + 31) // 32,), dtype=torch.int32, device=device)
+
+
+def mark_rows(ids: torch.Tensor, n_rows: int, bits: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bits |= {ids}: the rows of a gradient table that may be non-zero (ids outside [0, n_rows) are ignored)."""
+    _lib.require_cuda(ids)
+    if ids.dtype != torch.int64 or ids.dim() != 1:
+        raise TypeError("mark_rows: ids must be a 1-D int64 tensor")
+    ids = ids.contiguous()
+    if bits is None:
+        bits = row_bitmap(n_rows, ids.device)
+    with torch.cuda.device(ids.device):
+        _lib.check(_lib.load().relgat_mark_rows(_lib.ptr(ids), ids.numel(), n_rows, _lib.ptr(bits), _stream(ids)),
+                   "relgat_mark_rows")
+    _count(1 if ids.numel() else 0)
+    return bits
+
+
+def mark_sources(dst_bits: torch.Tensor, g: GraphIndex) -> torch.Tensor:
+    """Bitmap of the sources of the edges into the rows marked in ``dst_bits``: the rows of dP — and of the gradient
+    handed to the layer below — that can be non-zero."""
+    src_bits = row_bitmap(g.N_src, dst_bits.device)
+    with torch.cuda.device(dst_bits.device):
+        _lib.check(_lib.load().relgat_mark_sources(_lib.ptr(dst_bits), _lib.ptr(g.rowptr), _lib.ptr(g.csr_src), g.N,
+                                                   _lib.ptr(src_bits), _stream(dst_bits)), "relgat_mark_sources")
+    _count(1 if g.N else 0)
+    return src_bits
 
 
 def edge_bwd_beta(hsum: torch.Tensor, g: GraphIndex, H: int) -> torch.Tensor:

@@ -438,3 +438,81 @@ def test_second_generation_by_source_kernel_equals_the_first(dev, monkeypatch):
         _, (hi, lo), _ = ops.edge_bwd_src(P, G, A, z, minv, t, g, h, f, want_fp32=False, want_planes=True, want_ds=True)
         res.append(hi.float() + lo.float())
     assert rel_err(res[1].cpu().numpy(), res[0].cpu().numpy()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------------
+# exact-zero rows of the output gradient (functional.SPARSE_BWD)
+# ------------------------------------------------------------------------------------------------------
+def _bits_to_rows(bits: torch.Tensor, n: int) -> np.ndarray:
+    w = bits.cpu().numpy().view(np.uint32)
+    return np.nonzero((w[np.arange(n) >> 5] >> (np.arange(n) & 31).astype(np.uint32)) & 1)[0]
+
+
+def test_row_bitmaps_mark_rows_and_their_sources(dev):
+    gen = torch.Generator(device=dev).manual_seed(3)
+    n, e, r = 5000, 21000, 7
+    ei = torch.randint(0, n, (2, e), generator=gen, device=dev)
+    et = torch.randint(0, r, (e,), generator=gen, device=dev)
+    g = GraphIndex(ei, et, n, r)
+    ids = torch.randint(0, n, (300,), generator=gen, device=dev)
+    bits = ops.mark_rows(ids, n)
+    assert np.array_equal(_bits_to_rows(bits, n), np.unique(ids.cpu().numpy()))
+    src_bits = ops.mark_sources(bits, g)
+    marked = torch.zeros(n, dtype=torch.bool, device=dev)
+    marked[ids] = True
+    want = torch.unique(ei[0][marked[ei[1]]]).cpu().numpy()
+    assert np.array_equal(_bits_to_rows(src_bits, n), want)
+    # empty id list: nothing marked; out-of-range ids are ignored rather than written out of bounds
+    assert _bits_to_rows(ops.mark_rows(ids[:0], n), n).size == 0
+    assert np.array_equal(_bits_to_rows(ops.mark_rows(torch.tensor([-1, 5, n, n + 77], device=dev), n), n), [5])
+
+
+@pytest.mark.parametrize("storage", ["fp32", "bf16"])
+def test_by_source_pass_with_zero_row_hint_equals_the_full_pass(dev, storage):
+    """Edges into rows of G that are exact zeros contribute exact zeros: skipping them changes no bit of [dP | dS]."""
+    gen = torch.Generator(device=dev).manual_seed(9)
+    n, e, r, h, f = 3000, 20000, 11, 4, 40
+    ei = torch.randint(0, n, (2, e), generator=gen, device=dev)
+    ei[1, :1500] = 7   # destination hub (in the non-zero set below)
+    ei[0, 1500:2200] = 9  # source hub: split-segment path with skipped edges inside its parts
+    et = torch.randint(0, r, (e,), generator=gen, device=dev)
+    g = GraphIndex(ei, et, n, r)
+    dt = torch.float32 if storage == "fp32" else torch.bfloat16
+    P = torch.randn((n, h * f), generator=gen, device=dev)
+    A = torch.randn((h, r, f), generator=gen, device=dev) * 0.2
+    beta = torch.randn((r,), generator=gen, device=dev) * 0.1
+    rows = torch.unique(torch.cat([torch.randint(0, n, (150,), generator=gen, device=dev),
+                                   torch.tensor([7, 0, n - 1], device=dev)]))
+    dY = torch.zeros((n, h * f), device=dev)
+    dY[rows] = torch.randn((rows.numel(), h * f), generator=gen, device=dev)
+    out, _, _, z, minv, bias = ops.edge_fwd(P.to(dt), A, beta, g, h, f)
+    G, t, _ = ops.edge_bwd_prep(dY, out, bias, h, f, apply_elu=False, g_bf16=storage == "bf16")
+    res = []
+    for hint in (None, ops.mark_rows(rows, n)):
+        _, (hi, lo), _ = ops.edge_bwd_src(P.to(dt), G, A, z, minv, t, g, h, f, want_fp32=False, want_planes=True,
+                                          want_ds=True, dst_nz=hint)
+        res.append((hi.clone(), lo.clone()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    assert float(res[0][0].float().abs().sum()) > 0
+    # the hint is refused where it would leave dz unwritten, and when it is not a bitmap of the graph's rows
+    with pytest.raises(ValueError):
+        ops.edge_bwd_src(P.to(dt), G, A, z, minv, t, g, h, f, want_ds=False, dst_nz=ops.mark_rows(rows, n))
+    with pytest.raises(ValueError):
+        ops.edge_bwd_src(P.to(dt), G, A, z, minv, t, g, h, f, want_ds=True, dst_nz=torch.zeros(3, dtype=torch.int32, device=dev))
+
+
+@pytest.mark.parametrize("name", ["f200_fp32", "transe_proj_fp32", "tiny_fp64"])
+def test_training_step_with_and_without_zero_row_skipping_is_bit_identical(dev, name, monkeypatch):
+    c = Case(name)
+    res = []
+    for sparse in (True, False):
+        monkeypatch.setattr(RF, "SPARSE_BWD", sparse)
+        m = _load_model(c, dev)
+        m.train()
+        src, rel, dst = (c.t(k).to(dev) for k in ("src_ids", "rel_ids", "dst_ids"))
+        scores = m(src, rel, dst)
+        (scores * torch.linspace(-1, 1, scores.numel(), device=dev)).sum().backward()
+        res.append({n_: p.grad.clone() for n_, p in m.named_parameters() if p.grad is not None})
+    assert res[0].keys() == res[1].keys() and len(res[0]) > 0
+    for n_ in res[0]:
+        assert torch.equal(res[0][n_], res[1][n_]), n_
