@@ -52,6 +52,22 @@ int relgat_graph_index_build(const long long* src, const long long* dst, const l
                              int* relptr, int* rel_slot,
                              void* workspace, long long workspace_bytes, void* stream);
 
+/* Work tables of the streaming edge kernels (the chunks / parts / long_node / long_part_ptr arguments of
+ * relgat_layer_fwd and relgat_layer_bwd_src) from a CSR pointer array ptr[n+1], built on the device without a host
+ * read (the per-step receptive-field blocks build one per layer and step).  A chunk is a run of whole segments
+ * covering ~chunk_edges edges and <= chunk_nodes (<= 64) segments; a segment with more than long_segment edges stands
+ * alone and is cut into parts of part_edges edges, one chunk per part.  Order: parts first (segment, then part order),
+ * then the ordinary chunks in segment order.
+ *   chunks int32[max_chunks][4] = (first segment, segments, part slot or -1, 0); parts int32[max_parts][2] = (first edge,
+ *   end edge); long_node[max_long]; long_part_ptr[max_long + 1]; counts int32[3] = (n_chunks, n_parts, n_long) on the
+ *   device — n_chunks = -1 if a table was too small (nothing else is then valid).  Safe sizes for E edges:
+ *   max_long = E / (long_segment + 1) + 1, max_parts = E / part_edges + max_long, max_chunks = n + max_parts. */
+long long relgat_stream_chunks_workspace_bytes(int n);
+int relgat_stream_chunks_build(const int* ptr, int n, int chunk_edges, int chunk_nodes, int long_segment,
+                               int part_edges, int* chunks, int max_chunks, int* parts, int max_parts,
+                               int* long_node, int* long_part_ptr, int max_long, int* counts,
+                               void* workspace, long long workspace_bytes, void* stream);
+
 /* ---- dense feature transform (tcgen05 + TMA) ---------------------------------------------
  * Replaces `lin(node_emb)` of core/model/layer.py:220 (all heads in one GEMM) and its autograd
  * GEMMs.  D[M,N] = A·Bᵀ, bf16 operands, fp32 accumulation in tensor memory; D is written as fp32,

@@ -43,6 +43,8 @@ SIGNATURES = {
     "relgat_layer_bwd_prep": (_I, [_P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P, _I, _F, _P, _P]),
     "relgat_layer_bwd_src": (_I, [_P, _L, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P,
                                   _P, _F, _P, _I, _L, _I, _I, _I, _I, _P, _P]),
+    "relgat_stream_chunks_workspace_bytes": (_L, [_I]),
+    "relgat_stream_chunks_build": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _I, _P, _P, _L, _P]),
     "relgat_mark_rows": (_I, [_P, _L, _L, _P, _P]),
     "relgat_mark_sources": (_I, [_P, _P, _P, _I, _P, _P]),
     "relgat_layer_bwd_src2": (_I, [_P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _L,

@@ -142,6 +142,8 @@ class RelGATStackFunction(torch.autograd.Function):
     ``drop``: None or one LayerDropout per layer (masks applied inside the edge kernels).
     ``gather_ids``: None = return all N rows; int64 [n] = return out[gather_ids] only (the rows the scorer reads,
     reference model.py:136-137) — backward then receives [n, C] and never builds a dense [N, C] gradient.
+    ``graph``: one GraphIndex shared by the layers, or a list with one bipartite block per layer (blocks.py: layer l
+    maps block.N_src input rows to block.N output rows, and block l+1's sources are block l's destinations).
     """
 
     @staticmethod
@@ -154,10 +156,15 @@ class RelGATStackFunction(torch.autograd.Function):
         L = len(params) // 3
         H, F = heads, out_dim
         C = H * F
-        N = graph.N
+        blocks = isinstance(graph, (list, tuple))
+        graphs = list(graph) if blocks else [graph] * L
+        if len(graphs) != L:
+            raise ValueError(f"{len(graphs)} blocks for {L} layers")
+        for l in range(L):
+            want = graphs[l - 1].N if l else (x0_planes[0].size(0) if x0 is None else x0.size(0))
+            if graphs[l].N_src != want:
+                raise ValueError(f"layer {l}: {want} input rows but the graph's sources index {graphs[l].N_src} rows")
         with_lo = precision == "fp32"
-        if x0.size(0) != N:
-            raise ValueError(f"node_emb has {x0.size(0)} rows but the graph has {N} nodes")
         planes = x0_planes if x0_planes is not None else ops.split_bf16(x0, with_lo)
         saved = []
         out = None
@@ -166,28 +173,31 @@ class RelGATStackFunction(torch.autograd.Function):
             d_in = W.size(1)
             if W.size(0) != C:
                 raise ValueError(f"layer {l}: W must be [{C}, D_in]")
+            gl = graphs[l]
+            x0_grad = x0 is not None and x0.requires_grad
             Wp = ops.split_bf16(W.detach(), with_lo)
             # K-major copy of Wᵀ for dX = dP·W (3 MB transpose; the K-major B path is ~12% faster than MN-major)
-            WTp = ops.split_bf16(W.detach().t().contiguous(), with_lo) if (l > 0 or x0.requires_grad) else None
+            WTp = ops.split_bf16(W.detach().t().contiguous(), with_lo) if (l > 0 or x0_grad) else None
             # "bf16": projected features are stored in bf16 (halves every gather of the edge kernels)
-            P = ops.gemm(planes, False, Wp, False, N, C, d_in,
+            P = ops.gemm(planes, False, Wp, False, gl.N_src, C, d_in,
                          out_dtype=torch.float32 if with_lo else torch.bfloat16)
             last = l == L - 1
             dl = drop[l] if drop is not None else None
-            out, act, _, z, minv, bias = ops.edge_fwd(P, A.detach(), None if beta is None else beta.detach(), graph,
+            out, act, _, z, minv, bias = ops.edge_fwd(P, A.detach(), None if beta is None else beta.detach(), gl,
                                                       H, F, want_act=not last, apply_elu=True, act_lo=with_lo,
                                                       feat_drop=dl.feat if dl else None, edge_drop=dl.edge if dl else None)
             saved.append(dict(xp=planes, Wp=Wp, WTp=WTp, P=P, out=out, minv=minv, z=z, bias=bias, A=A.detach(),
                               d_in=d_in, has_beta=beta is not None, drop=dl))
             planes = act
         ctx.saved = saved
-        ctx.graph = graph
+        ctx.graphs = graphs
+        ctx.blocks = blocks
         ctx.cfg = (H, F, L, with_lo)
-        ctx.x0_needs_grad = bool(x0.requires_grad)
+        ctx.x0_needs_grad = bool(x0 is not None and x0.requires_grad)
         ctx.gather = None
         if gather_ids is not None:
             ids = gather_ids.contiguous()
-            ctx.gather = presort_on_side_stream(ids, N)  # (sorted keys, perm, event): summation order of backward
+            ctx.gather = presort_on_side_stream(ids, graphs[-1].N)  # (sorted keys, perm, event): summation order of backward
             rows = out.new_empty((ids.numel(), C))
             ops.pull_rows(out, ids, rows)
             return rows
@@ -199,9 +209,9 @@ class RelGATStackFunction(torch.autograd.Function):
             raise RuntimeError("the RelGAT stack's saved state was released by a previous backward; re-run the forward "
                                "(retain_graph is not supported by the fused stack)")
         H, F, L, with_lo = ctx.cfg
-        g = ctx.graph
+        graphs, blocks = ctx.graphs, ctx.blocks
         C = H * F
-        N = g.N
+        N = graphs[-1].N  # rows of the stack's output
         grads: List[Optional[torch.Tensor]] = [None] * (3 * L)
         table = None
         if ctx.gather is not None:
@@ -209,19 +219,24 @@ class RelGATStackFunction(torch.autograd.Function):
             # named several times by the batch); everything else stays exactly zero
             keys, perm, ready = ctx.gather
             torch.cuda.current_stream(grad_out.device).wait_event(ready)
-            table = _take_zero_table(grad_out.device, N, C)
+            # blocks: the last block has only the batch's own rows (a different count every step): a fresh small table
+            table = (torch.zeros((N, C), dtype=torch.float32, device=grad_out.device) if blocks
+                     else _take_zero_table(grad_out.device, N, C))
             ops.index_add_sorted(grad_out.contiguous(), keys, N, out=table, presorted=(keys, perm), accumulate=False)
-            dY, nz_rows, owned = table, keys, True
+            dY, nz_rows, owned = table, (None if blocks else keys), True
         else:
             dY = grad_out.contiguous()
             nz_rows = sparse_rows_of(grad_out) if dY is grad_out else None
             owned = False
-        nz_bits = ops.mark_rows(nz_rows, N) if (SPARSE_BWD and USE_DS and nz_rows is not None) else None
+        # (blocks hold nothing but the rows the batch reaches: there is nothing to skip)
+        nz_bits = ops.mark_rows(nz_rows, N) if (SPARSE_BWD and USE_DS and nz_rows is not None and not blocks) else None
         dX = None
         prepped = None  # (G, t, hsum) of layer l when the dX GEMM of layer l+1 produced them in its epilogue
         fuse_prep = USE_DS and FUSE_PREP and with_lo and ops.gemm_dx_prep_supported(C, F)
         for l in reversed(range(L)):
             s = ctx.saved[l]
+            g = graphs[l]
+            n_src = g.N_src
             dl = s["drop"]
             if prepped is not None:
                 G, t, hsum = prepped
@@ -237,8 +252,9 @@ class RelGATStackFunction(torch.autograd.Function):
             if nz_bits is not None and l > 0:
                 nz_bits = ops.mark_sources(nz_bits, g)  # rows of dP, hence of dL/d out_{l-1}, that can be non-zero
             if table is not None and l == L - 1:
-                ops.zero_rows(table, nz_rows)  # the table's rows are consumed (G aliased it): make it all-zero again
-                _return_zero_table(table)
+                if not blocks:
+                    ops.zero_rows(table, nz_rows)  # the table's rows are consumed (G aliased it): all-zero again
+                    _return_zero_table(table)
                 G = None
             d_in = s["d_in"]
             main = torch.cuda.current_stream(dY.device)
@@ -249,7 +265,7 @@ class RelGATStackFunction(torch.autograd.Function):
                 HR = H * g.R
                 Wd = dPp[0].size(1)
                 dP_c = tuple(None if p_ is None else p_[:, :C] for p_ in dPp)
-                dW_ext = weight_grad_gemm(dPp, s["xp"], Wd, d_in, N, dY.device)
+                dW_ext = weight_grad_gemm(dPp, s["xp"], Wd, d_in, n_src, dY.device)
                 dw_ready = torch.cuda.Event()
                 dw_ready.record(main)
                 if l > 0 and fuse_prep:
@@ -257,11 +273,12 @@ class RelGATStackFunction(torch.autograd.Function):
                     # of the layer below (what edge_bwd_prep would do in a second pass over dX and y)
                     below = ctx.saved[l - 1]
                     bd = below["drop"]
-                    prepped = ops.gemm_dx_prep(dP_c, s["WTp"], N, d_in, C, below["out"], below["bias"], H, F,
+                    prepped = ops.gemm_dx_prep(dP_c, s["WTp"], n_src, d_in, C, below["out"], below["bias"], H, F,
                                                apply_elu=True, feat_drop=bd.feat if bd else None)
                     dX = prepped[0]
                 elif l > 0 or ctx.x0_needs_grad:
-                    dX = ops.gemm(dP_c, False, s["WTp"], False, N, d_in, C)
+                    dX = ops.gemm(dP_c, False, s["WTp"], False, n_src, d_in, C)
+
                 def tail():
                     Tp = ops.split_bf16(dW_ext[C:C + HR].contiguous(), with_lo)
                     dA_full = ops.gemm(Tp, False, s["Wp"], False, HR, C, d_in)
@@ -289,11 +306,11 @@ class RelGATStackFunction(torch.autograd.Function):
             side.wait_stream(main)
             with torch.cuda.stream(side):  # dA / dbeta: gather-bound, overlaps the GEMMs below
                 dA, dbeta = ops.edge_bwd_rel(s["P"], dz, hsum, g, H, F, want_dbeta=s["has_beta"])
-            splits = ops.pick_splits_k(C, d_in, N, dY.device)
-            dW = ops.gemm(dPp, True, s["xp"], True, C, d_in, N, splits_k=splits)
+            splits = ops.pick_splits_k(C, d_in, n_src, dY.device)
+            dW = ops.gemm(dPp, True, s["xp"], True, C, d_in, n_src, splits_k=splits)
             grads[3 * l], grads[3 * l + 1], grads[3 * l + 2] = dW, dA, dbeta
             if l > 0 or ctx.x0_needs_grad:
-                dX = ops.gemm(dPp, False, s["WTp"], False, N, d_in, C)
+                dX = ops.gemm(dPp, False, s["WTp"], False, n_src, d_in, C)
                 dY, owned = dX, True
             main.wait_stream(side)  # join before any buffer of this layer is released or reused
             for tns in (dA, dbeta):

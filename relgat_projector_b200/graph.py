@@ -89,17 +89,62 @@ class StreamChunks:
         self.long_part_ptr = part_ptr.to(torch.int32)
         self.n_chunks = int(self.chunks.size(0))
 
+    # -- the same tables built by the device-side builder (csrc/stream_chunks.cu): no host read until ``finish`` ----
+    @classmethod
+    def launch(cls, ptr: torch.Tensor, n_edges: int, chunk_edges: int = STREAM_CHUNK_EDGES,
+               chunk_nodes: int = STREAM_CHUNK_NODES, long_segment: int = LONG_SEGMENT,
+               part_edges: int = PART_EDGES) -> "StreamChunks":
+        """Enqueue the build on the current stream; ``counts`` (int32 [3] on the device) holds (n_chunks, n_parts,
+        n_long) once it ran.  Call ``finish(counts_on_host)`` after reading them back."""
+        self = cls.__new__(cls)
+        dev = ptr.device
+        n = ptr.numel() - 1
+        i32 = dict(dtype=torch.int32, device=dev)
+        max_long = n_edges // (long_segment + 1) + 1
+        max_parts = n_edges // part_edges + max_long
+        max_chunks = max(n, 0) + max_parts
+        self.chunks = torch.empty((max_chunks, 4), **i32)
+        self.parts = torch.empty((max_parts, 2), **i32)
+        self.long_node = torch.empty((max_long,), **i32)
+        self.long_part_ptr = torch.empty((max_long + 1,), **i32)
+        self.counts = torch.empty((3,), **i32)
+        lib = _lib.load()
+        ws_bytes = int(lib.relgat_stream_chunks_workspace_bytes(max(n, 0)))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.relgat_stream_chunks_build(
+                _lib.ptr(ptr), max(n, 0), chunk_edges, chunk_nodes, long_segment, part_edges,
+                _lib.ptr(self.chunks), max_chunks, _lib.ptr(self.parts), max_parts, _lib.ptr(self.long_node),
+                _lib.ptr(self.long_part_ptr), max_long, _lib.ptr(self.counts), _lib.ptr(ws), ws_bytes,
+                torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "relgat_stream_chunks_build")
+        self.n_chunks = self.n_parts = self.n_long = None
+        return self
+
+    def finish(self, counts) -> "StreamChunks":
+        n_chunks, n_parts, n_long = (int(v) for v in counts)
+        if n_chunks < 0:
+            raise RuntimeError("relgat_stream_chunks_build: table bounds exceeded")
+        self.n_chunks, self.n_parts, self.n_long = n_chunks, n_parts, n_long
+        self.chunks = self.chunks[:n_chunks]
+        self.parts = self.parts[:n_parts]
+        self.long_node = self.long_node[:n_long]
+        self.long_part_ptr = self.long_part_ptr[:n_long + 1]
+        return self
+
 
 class GraphIndex:
     """All integer structures of one message-passing graph, as int32 CUDA tensors."""
 
     def __init__(self, edge_index: torch.Tensor, edge_type: torch.Tensor, num_nodes: int, num_rel: int,
                  validate: bool = True, num_src_nodes: Optional[int] = None,
-                 fwd_chunks: bool = True, src_chunks: bool = True):
+                 fwd_chunks: bool = True, src_chunks: bool = True, degrees: bool = True, lean: bool = False):
         """``num_nodes`` = destination rows (segments); ``num_src_nodes`` = rows of the feature matrix
         the sources index (defaults to ``num_nodes``; larger on a destination-range partition).
         ``fwd_chunks`` / ``src_chunks``: build the work tables of the forward / by-source kernel (a
-        partitioned graph that only ever runs one of the two skips the other)."""
+        partitioned graph that only ever runs one of the two skips the other).  ``degrees``: also read back the maximum
+        in / out degree (two host syncs; the per-batch blocks skip them).  ``lean``: the per-step path — no validation,
+        no degrees, work tables from the device-side builder, ONE host read for all the sizes the launches need."""
         _lib.require_cuda(edge_index, edge_type)
         if edge_index.dim() != 2 or edge_index.size(0) != 2:
             raise ValueError("edge_index must have shape [2, E]")
@@ -111,7 +156,7 @@ class GraphIndex:
         E = int(edge_index.size(1))
         N, R = int(num_nodes), int(num_rel)
         NS = int(num_src_nodes) if num_src_nodes is not None else N
-        if validate and E > 0:
+        if validate and not lean and E > 0:
             lo = int(min(edge_index.min().item(), edge_type.min().item()))
             if (lo < 0 or int(edge_index[0].max().item()) >= NS or int(edge_index[1].max().item()) >= N
                     or int(edge_type.max().item()) >= R):
@@ -139,28 +184,39 @@ class GraphIndex:
                 _lib.ptr(self.csc_rel), _lib.ptr(self.relptr), _lib.ptr(self.rel_slot),
                 _lib.ptr(ws), ws_bytes, stream)
         _lib.check(rc, "relgat_graph_index_build")
+        self.max_in_degree = self.max_out_degree = None
+        if lean:
+            self.fwd_chunks = StreamChunks.launch(self.rowptr, E) if fwd_chunks else None
+            self.src_chunks = StreamChunks.launch(self.colptr, E) if src_chunks else None
+            pend = [ck for ck in (self.fwd_chunks, self.src_chunks) if ck is not None]
+            host = torch.cat([ck.counts for ck in pend] + [self.relptr]).cpu().numpy()  # the one host read
+            for k, ck in enumerate(pend):
+                ck.finish(host[3 * k:3 * k + 3])
+            self._build_rel_chunks(host[3 * len(pend):])
+            del ws
+            return
         self._build_rel_chunks()
         self.fwd_chunks = StreamChunks(self.rowptr) if fwd_chunks else None
         self.src_chunks = StreamChunks(self.colptr) if src_chunks else None
-        self.max_in_degree = int((self.rowptr[1:] - self.rowptr[:-1]).max().item()) if N > 0 else 0
-        self.max_out_degree = int((self.colptr[1:] - self.colptr[:-1]).max().item()) if NS > 0 else 0
+        if degrees:
+            self.max_in_degree = int((self.rowptr[1:] - self.rowptr[:-1]).max().item()) if N > 0 else 0
+            self.max_out_degree = int((self.colptr[1:] - self.colptr[:-1]).max().item()) if NS > 0 else 0
         del ws
 
-    def _build_rel_chunks(self) -> None:
+    def _build_rel_chunks(self, relptr_host=None) -> None:
         """Fixed-size chunks of the by-relation order; a chunk never spans two relations."""
-        relptr = self.relptr.cpu().tolist()  # R+1 ints, one-off
-        lo, hi, cptr = [], [], [0]
-        for r in range(self.R):
-            a, b = relptr[r], relptr[r + 1]
-            for s in range(a, b, REL_CHUNK):
-                lo.append(s)
-                hi.append(min(b, s + REL_CHUNK))
-            cptr.append(len(lo))
-        i32 = dict(dtype=torch.int32, device=self.device)
-        self.n_chunks = len(lo)
-        self.chunk_lo = torch.tensor(lo if lo else [0], **i32)[: self.n_chunks]
-        self.chunk_hi = torch.tensor(hi if hi else [0], **i32)[: self.n_chunks]
-        self.rel_chunk_ptr = torch.tensor(cptr, **i32)
+        import numpy as np
+        relptr = (self.relptr.cpu().numpy() if relptr_host is None else np.asarray(relptr_host)).astype(np.int64)
+        a, b = relptr[:-1], relptr[1:]
+        per = (b - a + REL_CHUNK - 1) // REL_CHUNK          # chunks of each relation
+        cptr = np.concatenate([[0], np.cumsum(per)])
+        n = int(cptr[-1])
+        owner = np.repeat(np.arange(self.R), per)
+        lo = a[owner] + (np.arange(n) - cptr[:-1][owner]) * REL_CHUNK
+        hi = np.minimum(lo + REL_CHUNK, b[owner])
+        self.n_chunks = n
+        packed = torch.from_numpy(np.concatenate([lo, hi, cptr]).astype(np.int32)).to(self.device)  # one upload
+        self.chunk_lo, self.chunk_hi, self.rel_chunk_ptr = packed[:n], packed[n:2 * n], packed[2 * n:]
 
     def as_numpy(self) -> Dict[str, "object"]:
         keys = ["rowptr", "csr_perm", "csr_src", "csr_rel", "csr_dst", "colptr", "csc_slot", "csc_dst",

@@ -12,6 +12,7 @@ import torch.nn as nn
 
 from . import functional as RF
 from . import ops
+from .blocks import build_blocks
 from .graph import get_graph_index
 from .layer import RelGATLayer
 from .projection import ProjectionHead
@@ -46,6 +47,11 @@ class RelGATModel(nn.Module):
         self.projection_layers = projection_layers
         self.project_to_input_size = project_to_input_size
         self.precision = precision
+        # extension (not a constructor argument of the reference): run the batch-row path (forward / batch_rows) on the
+        # batch's receptive-field blocks instead of the whole graph — same rows, same gradients, less work (blocks.py);
+        # single_gat_step / evaluation always run the full graph
+        self.receptive_field = os.environ.get("RELGAT_RECEPTIVE_FIELD", "0") != "0"
+        self.last_block_edges = None
         if project_to_input_size and self.projection_layers < 1:
             raise ValueError("projection_layers must be >= 1 when project_to_input_size=True")
         self._config = dict(
@@ -112,7 +118,18 @@ class RelGATModel(nn.Module):
         reference's default rates runs the same fused path as dropout 0."""
         layers = self._layers()
         graph = self._graph()
-        drop = [lyr.draw_dropout(graph.N, graph.E, self.node_emb_fixed.device) for lyr in layers]
+        dev = self.node_emb_fixed.device
+        if gather_ids is not None and self.receptive_field:
+            # one bipartite block per layer, holding the batch's L-hop in-neighbourhood only
+            blk = build_blocks(graph, gather_ids, len(layers))
+            self.last_block_edges = blk.n_edges
+            drop = [lyr.draw_dropout(g.N, g.E, dev) for lyr, g in zip(layers, blk.graphs)]
+            drop = [d if d is not None else RF.LayerDropout() for d in drop] if any(d is not None for d in drop) else None
+            planes = tuple(None if p is None else ops.gather_plane_rows(p, blk.input_rows) for p in self._input_planes())
+            return RF.relgat_stack(None, blk.graphs, layers[0].heads, layers[0].out_dim,
+                                   [lyr.kernel_params() for lyr in layers], precision=self.precision,
+                                   x0_planes=planes, drop=drop, gather_ids=blk.out_pos)
+        drop = [lyr.draw_dropout(graph.N, graph.E, dev) for lyr in layers]
         drop = [d if d is not None else RF.LayerDropout() for d in drop] if any(d is not None for d in drop) else None
         return RF.relgat_stack(self.node_emb_fixed, graph, layers[0].heads, layers[0].out_dim,
                                [lyr.kernel_params() for lyr in layers], precision=self.precision,

@@ -744,6 +744,22 @@ def recon_loss(tr: torch.Tensor, dst: torch.Tensor, negdst: Optional[torch.Tenso
     return values, d_tr, d_dst, d_neg
 
 
+def gather_plane_rows(plane: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+    """rows ``ids`` of a bf16 plane [N, D] as a new bf16 [n, D] (byte copy of whole rows; the input rows of a batch's
+    first receptive-field block)."""
+    _lib.require_cuda(plane, ids)
+    if plane.dtype != torch.bfloat16 or plane.dim() != 2 or not plane.is_contiguous() or ids.dtype != torch.int64:
+        raise TypeError("gather_plane_rows: contiguous 2-D bfloat16 plane and int64 ids expected")
+    n, D = int(ids.numel()), int(plane.size(1))
+    out = torch.empty((n, D), dtype=torch.bfloat16, device=plane.device)
+    if n == 0:
+        return out
+    if D % 2:  # odd width: rows are not whole 32-bit words
+        return torch.index_select(plane, 0, ids)
+    pull_rows(plane.view(torch.float32), ids, out.view(torch.float32))
+    return out
+
+
 def pull_rows(table: torch.Tensor, ids: torch.Tensor, out: torch.Tensor, out_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[i] = table[ids[i]] (rows of a mapped peer table -> local rows); with ``out_ids`` the rows are scattered:
     out[out_ids[i]] = table[ids[i]].  ``table`` / ``out``: fp32 with unit inner stride, any number of trailing dims

@@ -511,8 +511,104 @@ def test_training_step_with_and_without_zero_row_skipping_is_bit_identical(dev, 
         m.train()
         src, rel, dst = (c.t(k).to(dev) for k in ("src_ids", "rel_ids", "dst_ids"))
         scores = m(src, rel, dst)
+        scores = scores[0] if isinstance(scores, tuple) else scores  # (scores, transform rows, ...) with a projection
         (scores * torch.linspace(-1, 1, scores.numel(), device=dev)).sum().backward()
         res.append({n_: p.grad.clone() for n_, p in m.named_parameters() if p.grad is not None})
     assert res[0].keys() == res[1].keys() and len(res[0]) > 0
     for n_ in res[0]:
         assert torch.equal(res[0][n_], res[1][n_]), n_
+
+
+# ------------------------------------------------------------------------------------------------------
+# receptive-field blocks
+# ------------------------------------------------------------------------------------------------------
+def test_blocks_hold_every_in_edge_of_their_destinations_in_graph_order(dev):
+    from relgat_projector_b200.blocks import build_blocks
+    gen = torch.Generator(device=dev).manual_seed(5)
+    n, e, r = 4000, 18000, 9
+    ei = torch.randint(0, n, (2, e), generator=gen, device=dev)
+    ei[1, :700] = 11  # a hub with more in-edges than a split segment holds
+    et = torch.randint(0, r, (e,), generator=gen, device=dev)
+    full = GraphIndex(ei, et, n, r)
+    ids = torch.randint(0, n, (200,), generator=gen, device=dev)
+    ids[:3] = torch.tensor([11, 11, 0], device=dev)
+    blk = build_blocks(full, ids, 2)
+    torch.cuda.synchronize()
+    rowptr, csr_src, csr_rel = (getattr(full, k).cpu().numpy() for k in ("rowptr", "csr_src", "csr_rel"))
+    rows = blk.input_rows.cpu().numpy()            # D_0
+    D = np.unique(ids.cpu().numpy())               # D_2
+    assert np.array_equal(D[blk.out_pos.cpu().numpy()], ids.cpu().numpy())
+    for g in reversed(blk.graphs):                 # walk down from the last block
+        assert g.N == D.size
+        bp, bs, br = (getattr(g, k).cpu().numpy() for k in ("rowptr", "csr_src", "csr_rel"))
+        srcs = np.unique(np.concatenate([csr_src[rowptr[j]:rowptr[j + 1]] for j in D] + [np.zeros(0, np.int32)]))
+        assert g.N_src == srcs.size
+        for k, j in enumerate(D):                  # same edges, same order, sources relabelled into the sorted set
+            assert np.array_equal(srcs[bs[bp[k]:bp[k + 1]]], csr_src[rowptr[j]:rowptr[j + 1]])
+            assert np.array_equal(br[bp[k]:bp[k + 1]], csr_rel[rowptr[j]:rowptr[j + 1]])
+        D = srcs
+    assert np.array_equal(rows, D)
+    assert blk.n_edges == sum(g.E for g in blk.graphs)
+
+
+@pytest.mark.parametrize("name", MODEL_CASES)
+def test_receptive_field_step_equals_the_full_graph_step(dev, name):
+    """forward on the batch's blocks: the same scores (bit for bit — every destination keeps all its in-edges in order)
+    and the same parameter gradients (the weight-gradient GEMMs sum over fewer, reordered rows: rounding only)."""
+    c = Case(name)
+    res = []
+    for rf in (False, True):
+        m = _load_model(c, dev)
+        m.receptive_field = rf
+        src, rel, dst = (c.t(k).to(dev) for k in ("src_ids", "rel_ids", "dst_ids"))
+        scores = m(src, rel, dst)[0]
+        (scores * torch.linspace(-1, 1, scores.numel(), device=dev)).sum().backward()
+        res.append((scores.detach().clone(), {n_: p.grad.clone() for n_, p in m.named_parameters() if p.grad is not None}))
+        if rf:
+            assert m.last_block_edges is not None and m.last_block_edges <= c.layers * c.e
+    assert torch.equal(res[0][0], res[1][0])
+    assert res[0][1].keys() == res[1][1].keys() and len(res[0][1]) > 0
+    for n_ in res[0][1]:
+        assert rel_err(res[1][1][n_].cpu().numpy(), res[0][1][n_].cpu().numpy()) < 2e-5, n_
+
+
+def test_receptive_field_step_with_dropout_and_losses_runs_and_is_finite(dev):
+    c = Case("transe_proj_fp32")
+    m = _load_model(c, dev)
+    m.receptive_field = True
+    for lyr in m._layers():
+        lyr.dropout.p, lyr.rel_attn_drop.p = 0.3, 0.1
+    torch.manual_seed(0)
+    rank = L.RelGATLoss("self_adversarial_loss", 1.0, None, None, {})
+    multi = L.MultiObjectiveRelLoss(relgat_loss=rank, run_config={})
+    src, rel, dst = (c.t(k).to(dev) for k in ("src_ids", "rel_ids", "dst_ids"))
+    _, _, loss, *_ = L.calculate_loss(m, src, rel, dst, c.b, rank, multi)
+    loss.backward()
+    assert torch.isfinite(loss)
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
+
+
+@pytest.mark.parametrize("shape", ["uniform", "hubs", "empty_segments", "single", "none"])
+def test_device_built_work_tables_equal_the_host_formulation(dev, shape):
+    """csrc/stream_chunks.cu against graph.py::StreamChunks (torch ops, used once per full graph): same tables."""
+    from relgat_projector_b200.graph import StreamChunks
+    gen = torch.Generator().manual_seed(11)
+    if shape == "uniform":
+        deg = torch.randint(0, 12, (5000,), generator=gen)
+    elif shape == "hubs":
+        deg = torch.randint(0, 9, (3000,), generator=gen)
+        deg[[0, 17, 18, 1500, 2999]] = torch.tensor([513, 2000, 700, 5121, 512])
+    elif shape == "empty_segments":
+        deg = torch.zeros(300, dtype=torch.int64)
+        deg[[5, 250]] = torch.tensor([40, 3])
+    elif shape == "single":
+        deg = torch.tensor([7])
+    else:
+        deg = torch.zeros(0, dtype=torch.int64)
+    ptr = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(deg, 0)]).to(torch.int32).to(dev)
+    want = StreamChunks(ptr)
+    got = StreamChunks.launch(ptr, int(deg.sum()))
+    got.finish(got.counts.cpu().numpy())
+    assert (got.n_chunks, got.n_parts, got.n_long) == (want.n_chunks, want.n_parts, want.n_long)
+    for k in ("chunks", "parts", "long_node", "long_part_ptr"):
+        assert torch.equal(getattr(got, k), getattr(want, k)), k
