@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--config", default="c2")
     ap.add_argument("--precision", default="fp32")
     ap.add_argument("--dropout", type=float, default=0.0)
+    ap.add_argument("--receptive-field", action="store_true", help="run the step on the batch's blocks (blocks.py)")
     ap.add_argument("--out", default="gpurun_out/trace_step.md")
     args = ap.parse_args()
     cfg = S.CONFIGS[args.config]
@@ -44,6 +45,7 @@ def main():
                           gat_out_dim=cfg["F"], gat_heads=cfg["H"], dropout=args.dropout, gat_num_layers=cfg["L"],
                           project_to_input_size=cfg["proj"], projection_layers=2, precision=args.precision).to(dev)
     model.train()
+    model.receptive_field = args.receptive_field
     opt = torch.optim.Adam(model.parameters(), lr=2e-4)
     b, k = cfg["B"], cfg["K"]
     gen = torch.Generator().manual_seed(42)
@@ -81,7 +83,8 @@ def main():
     st = steps[1]
     t0 = st[0]["ts"]
     t1 = max(e["ts"] + e["dur"] for e in st)
-    lines = [f"# Kernel timeline of one training step ({args.config}, {args.precision}, dropout {args.dropout}); "
+    lines = [f"# Kernel timeline of one training step ({args.config}, {args.precision}, dropout {args.dropout}"
+             f"{', receptive-field blocks' if args.receptive_field else ''}); "
              f"torch.profiler / CUPTI, step 2 of 3 after 4 warm-ups", "",
              f"step span {(t1 - t0) / 1e3:.3f} ms, {len(st)} device activities", "",
              "| start us | dur us | stream | idle before (any stream) us | activity |", "|---|---|---|---|---|"]
