@@ -612,3 +612,27 @@ def test_device_built_work_tables_equal_the_host_formulation(dev, shape):
     assert (got.n_chunks, got.n_parts, got.n_long) == (want.n_chunks, want.n_parts, want.n_long)
     for k in ("chunks", "parts", "long_node", "long_part_ptr"):
         assert torch.equal(getattr(got, k), getattr(want, k)), k
+
+
+def test_config1_full_size_receptive_field_step_vs_full_graph_step(dev):
+    """Config 1 (10 k nodes / 45 k edges / 1024-d / 2 layers / 4x200, B = 256, K = 4) through calculate_loss: the step on
+    the batch's blocks against the full-graph step (itself checked against the fp64 oracle above)."""
+    cfg = S.CONFIGS["c1"]
+    kg = S.tensor_kg(cfg["N"], cfg["T"], cfg["R"], cfg["D_in"], seed=3, device=dev)
+    gen = torch.Generator().manual_seed(5)
+    src, rel, dst = (t.to(dev) for t in S.sample_batch(kg.train_triples.cpu(), cfg["N"], cfg["B"], cfg["K"], gen))
+    rank = L.RelGATLoss("margin", None, 1.0, None, {})
+    res = []
+    for rf in (False, True):
+        torch.manual_seed(11)
+        m = R.RelGATModel(kg.node_emb, kg.edge_index, kg.edge_type, num_rel=cfg["R"], scorer_type=cfg["scorer"],
+                          gat_out_dim=cfg["F"], gat_heads=cfg["H"], dropout=0.0, gat_num_layers=cfg["L"]).to(dev).train()
+        m.receptive_field = rf
+        _, _, loss, *_ = L.calculate_loss(m, src, rel, dst, cfg["B"], rank, None)
+        loss.backward()
+        res.append((float(loss), {n_: p.grad.clone() for n_, p in m.named_parameters() if p.grad is not None}))
+        if rf:
+            assert 0 < m.last_block_edges < cfg["L"] * kg.edge_index.size(1)
+    assert res[0][0] == res[1][0]  # every batch row is computed from the same terms in the same order
+    for n_ in res[0][1]:
+        assert rel_err(res[1][1][n_].cpu().numpy(), res[0][1][n_].cpu().numpy()) < 2e-5, n_

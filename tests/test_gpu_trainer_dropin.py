@@ -102,14 +102,19 @@ def _run_trainer(device, tmp_path, *, projection, self_adv, patch, fused_seam=Fa
         ref_trainer_mod.RelGATTrainer._calculate_loss = saved_calc
 
 
-@pytest.mark.parametrize("projection,self_adv,fused_seam", [
-    (False, False, False),   # DistMult, margin ranking loss: model.forward seam
-    (True, True, False),     # the reference's shipped recipe: TransE + projection + self-adversarial + reconstruction
-    (True, True, True),      # same, plus the trainer-level seam (fused batch rows, score and loss kernels)
-    (False, True, True),
+@pytest.mark.parametrize("projection,self_adv,fused_seam,receptive_field", [
+    (False, False, False, False),   # DistMult, margin ranking loss: model.forward seam
+    (True, True, False, False),     # the reference's shipped recipe: TransE + projection + self-adversarial + reconstruction
+    (True, True, True, False),      # same, plus the trainer-level seam (fused batch rows, score and loss kernels)
+    (False, True, True, False),
+    (True, True, True, True),       # ... and every train / eval batch on its receptive-field blocks (blocks.py)
+    (False, False, False, True),
 ])
-def test_reference_trainer_with_dropin_classes_matches_reference_on_cpu(dev, tmp_path, projection, self_adv, fused_seam):
+def test_reference_trainer_with_dropin_classes_matches_reference_on_cpu(dev, tmp_path, monkeypatch, projection, self_adv,
+                                                                        fused_seam, receptive_field):
     ref = _run_trainer("cpu", tmp_path, projection=projection, self_adv=self_adv, patch=False)
+    if receptive_field:
+        monkeypatch.setenv("RELGAT_RECEPTIVE_FIELD", "1")  # read by the drop-in RelGATModel's constructor
     got = _run_trainer(dev, tmp_path, projection=projection, self_adv=self_adv, patch=True, fused_seam=fused_seam)
     assert ref["model_module"].startswith("relgat_projector.") and got["model_module"].startswith("relgat_projector_b200")
     assert len(ref["losses"]) == len(got["losses"]) >= 10
