@@ -62,6 +62,8 @@ def build_blocks(full: GraphIndex, ids: torch.Tensor, num_layers: int) -> Blocks
             src_global = full.csr_src[pos].to(torch.int64)
             rel = full.csr_rel[pos].to(torch.int64)
             S = torch.unique(src_global)
+            if S.numel() == 0:  # destinations without in-edges: keep one (unread) source row so no layer has 0 rows
+                S = torch.zeros(1, dtype=torch.int64, device=dev)
             src_local = torch.searchsorted(S, src_global)
             g = GraphIndex(torch.stack([src_local, dst_local]), rel, int(D.numel()), full.R, validate=False,
                            num_src_nodes=int(S.numel()), lean=True)

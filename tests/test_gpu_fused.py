@@ -636,3 +636,29 @@ def test_config1_full_size_receptive_field_step_vs_full_graph_step(dev):
     assert res[0][0] == res[1][0]  # every batch row is computed from the same terms in the same order
     for n_ in res[0][1]:
         assert rel_err(res[1][1][n_].cpu().numpy(), res[0][1][n_].cpu().numpy()) < 2e-5, n_
+
+
+def test_receptive_field_edge_cases_isolated_nodes_and_repeated_ids(dev):
+    """Batch nodes without in-edges (empty blocks all the way down), a batch naming one node many times, and a one-layer
+    model: the block path must agree with the full-graph path."""
+    gen = torch.Generator().manual_seed(2)
+    n, r, d_in = 400, 5, 32
+    ei = torch.randint(0, 300, (2, 1500), generator=gen)      # nodes 300..399 are isolated
+    et = torch.randint(0, r, (1500,), generator=gen)
+    x0 = torch.randn(n, d_in, generator=gen)
+    for layers, ids in ((2, torch.tensor([350, 399, 350])),             # isolated only: every block has E = 0
+                        (2, torch.tensor([7, 7, 7, 350, 7])),           # repeats + an isolated node
+                        (1, torch.randint(0, n, (64,), generator=gen))):
+        res = []
+        for rf in (False, True):
+            torch.manual_seed(4)
+            m = R.RelGATModel(x0.to(dev), ei.to(dev), et.to(dev), num_rel=r, gat_out_dim=8, gat_heads=2, dropout=0.0,
+                              gat_num_layers=layers).to(dev).train()
+            m.receptive_field = rf
+            rows = m.batch_rows(ids.to(dev))
+            (rows * torch.linspace(-1, 1, rows.numel(), device=dev).view_as(rows)).sum().backward()
+            res.append((rows.detach().clone(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}))
+        assert torch.equal(res[0][0], res[1][0])
+        assert res[0][1].keys() == res[1][1].keys()
+        for k in res[0][1]:
+            assert rel_err(res[1][1][k].cpu().numpy(), res[0][1][k].cpu().numpy()) < 2e-5, (layers, k)
