@@ -160,6 +160,8 @@ int relgat_layer_bwd_prep(const float* dY, const float* out, const float* bias, 
                           const long long* row_ids, int n_rows,
                           const unsigned int* drop_bits, int drop_words, float drop_scale,
                           void* G_export_bf16 /* optional bf16 copy of G for the peers' pulls; NULL = none */,
+                          int dy_compact /* with row_ids: dY holds the listed rows only (row k <-> node row_ids[k]); G is
+                             a separate table whose other rows the caller keeps at zero; apply_elu allowed */,
                           void* stream);
 int relgat_layer_bwd_src(const void* P, long long ldp, const void* G, int feat_is_bf16, const float* A,
                          const float* z, const float* minv, const float* t,
@@ -170,6 +172,8 @@ int relgat_layer_bwd_src(const void* P, long long ldp, const void* G, int feat_i
                          const unsigned int* edge_bits, float edge_scale,
                          const unsigned int* dst_nz_bits /* want_ds only: bit j = row j of G may be non-zero (edges into
                             other rows are skipped: their G[dst], t[dst] and hence dz are exact zeros); NULL = all rows */,
+                         const int* src_row /* want_ds only: output row of each source, -1 = skip the source (it has no
+                            edge into a non-zero row); from relgat_bitmap_ranks; NULL = row i for source i */,
                          int want_ds, long long ldo, int H, int F, int R, int sm_count, int* work_counter, void* stream);
 /* Training-path variant of relgat_layer_bwd_src (second generation): fp32 P / G rows with F % 4 == 0, bf16 planes out,
  * want_ds semantics (rows ldo >= H*F + H*R wide, dS behind dP, no dz).  A pre-pass turns the per-edge gathers of z,
@@ -256,6 +260,13 @@ int relgat_zero_rows(float* table, long long ld, const long long* ids, long long
 int relgat_mark_rows(const long long* ids, long long n, long long n_rows, unsigned int* bits, void* stream);
 int relgat_mark_sources(const unsigned int* dst_bits, const int* rowptr, const int* csr_src, int n_dst,
                         unsigned int* src_bits, void* stream);
+/* Compact numbering of a row bitmap: rank[i] = position of row i among the marked rows (ascending) or -1, list[k] = the
+ * k-th marked row, *count = their number (all on the device; rank / list may be NULL).  The compacted backward writes
+ * dP rows at rank[src] (src_row of relgat_layer_bwd_src), gathers the matching input rows by list and sizes its GEMMs
+ * by count. */
+long long relgat_bitmap_ranks_workspace_bytes(long long n_rows);
+int relgat_bitmap_ranks(const unsigned int* bits, long long n_rows, int* rank, long long* list, int* count,
+                        void* workspace, long long workspace_bytes, void* stream);
 
 /* ---- ProjectionHead hidden block (core/model/projection.py:48-67: Linear -> GELU -> LayerNorm) ------------------
  * GELU (exact, erf form) + LayerNorm (biased variance, eps inside the root) of h [M, D] in one pass per direction; the

@@ -37,6 +37,7 @@ struct PrepArgs {
   int drop_words;
   float drop_scale;
   __nv_bfloat16* G_export;  // optional bf16 copy of G (what the peers pull on the partitioned path); fp32 G only
+  int dy_compact;           // with row_ids: row k of dY belongs to node row_ids[k] (dY holds the listed rows only)
 };
 
 template <typename TG, int V>
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32) bwd_prep_kernel(const PrepArgs
     return;
   const LaneMap lm = make_lane_map<V>(lane, g, a.hg, a.F);
   const long long row = j * a.H * a.F + lm.head_off;
+  const long long row_y = a.dy_compact ? static_cast<long long>(jt) * a.H * a.F + lm.head_off : row;
   const float b = a.bias ? __ldg(a.bias + j) : 0.f;
   float tt = 0.f, hs = 0.f;
 #pragma unroll
@@ -61,7 +63,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32) bwd_prep_kernel(const PrepArgs
     const int q = lm.sub + lm.lph * k;
     if (q < lm.vph) {
       float dy[V], o[V], ms[V];
-      RowVec<float, V>::load_stream(a.dY + row + q * V, dy);
+      RowVec<float, V>::load_stream(a.dY + row_y + q * V, dy);
       RowVec<float, V>::load_stream(a.out + row + q * V, o);
 #pragma unroll
       for (int v = 0; v < V; ++v) ms[v] = 1.f;
@@ -262,20 +264,20 @@ int run_src(const void* P, long long ldp, const void* G, const float* A, const f
             const float* t, const int* colptr, const int* csc_slot, const int* csc_dst, const int* csc_rel,
             const int4* ch, int n_chunks, const int2* pt, const int* long_node, const int* long_part_ptr,
             int n_long, float* part_acc, float* dP, void* dP_hi, void* dP_lo, float* dz,
-            const uint32_t* edge_bits, float edge_scale, const uint32_t* nz_bits, int ds_on, long long ldo,
-            int H, int F, int R, int sm_count, int* work_counter, cudaStream_t s);
+            const uint32_t* edge_bits, float edge_scale, const uint32_t* nz_bits, const int* src_row, int ds_on,
+            long long ldo, int H, int F, int R, int sm_count, int* work_counter, cudaStream_t s);
 extern template int run_src<float, 4>(const void*, long long, const void*, const float*, const float*, const float*,
                                       const float*, const int*, const int*, const int*, const int*, const int4*, int,
                                       const int2*, const int*, const int*, int, float*, float*, void*, void*, float*,
-                                      const uint32_t*, float, const uint32_t*, int, long long, int, int, int, int, int*, cudaStream_t);
+                                      const uint32_t*, float, const uint32_t*, const int*, int, long long, int, int, int, int, int*, cudaStream_t);
 extern template int run_src<float, 1>(const void*, long long, const void*, const float*, const float*, const float*,
                                       const float*, const int*, const int*, const int*, const int*, const int4*, int,
                                       const int2*, const int*, const int*, int, float*, float*, void*, void*, float*,
-                                      const uint32_t*, float, const uint32_t*, int, long long, int, int, int, int, int*, cudaStream_t);
+                                      const uint32_t*, float, const uint32_t*, const int*, int, long long, int, int, int, int, int*, cudaStream_t);
 extern template int run_src<__nv_bfloat16, 8>(const void*, long long, const void*, const float*, const float*,
                                               const float*, const float*, const int*, const int*, const int*, const int*,
                                               const int4*, int, const int2*, const int*, const int*, int, float*, float*,
-                                              void*, void*, float*, const uint32_t*, float, const uint32_t*, int, long long, int, int, int,
+                                              void*, void*, float*, const uint32_t*, float, const uint32_t*, const int*, int, long long, int, int, int,
                                               int, int*, cudaStream_t);
 }  // namespace relgat
 
@@ -283,8 +285,9 @@ extern "C" int relgat_layer_bwd_prep(const float* dY, const float* out, const fl
                                      float* t, float* hsum, int N, int H, int F, int apply_elu,
                                      const long long* row_ids, int n_rows,
                                      const unsigned int* drop_bits, int drop_words, float drop_scale,
-                                     void* G_export_bf16, void* stream) {
+                                     void* G_export_bf16, int dy_compact, void* stream) {
   if (!dY || !out || !G || !t || !hsum || N < 0 || H <= 0 || F <= 0 || n_rows < 0) return RG_ERR_ARG;
+  if (dy_compact && (!row_ids || g_is_bf16 || static_cast<const void*>(G) == static_cast<const void*>(dY))) return RG_ERR_ARG;
   if (drop_bits && drop_words * 32 < H * F) return RG_ERR_ARG;
   if (G_export_bf16 && (g_is_bf16 || F % 4 != 0 || reinterpret_cast<uintptr_t>(G_export_bf16) % 8 != 0)) return RG_ERR_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -292,7 +295,8 @@ extern "C" int relgat_layer_bwd_prep(const float* dY, const float* out, const fl
   if (row_ids) {
     // sparse dY (the loss touches few rows), no activation: only the listed rows are read; G either aliases dY or is a
     // buffer whose other rows the caller keeps at zero (peer tables); t / hsum of the other rows are zero
-    if (apply_elu || g_is_bf16) return RG_ERR_ARG;
+    // (compact dY: G is a separate table, so the activation derivative may be applied)
+    if ((apply_elu && !dy_compact) || g_is_bf16) return RG_ERR_ARG;
     cudaError_t e = cudaMemsetAsync(t, 0, sizeof(float) * static_cast<size_t>(N) * H, s);
     if (e == cudaSuccess) e = cudaMemsetAsync(hsum, 0, sizeof(float) * static_cast<size_t>(N) * H, s);
     if (e != cudaSuccess) return cuda_status(e);
@@ -304,7 +308,7 @@ extern "C" int relgat_layer_bwd_prep(const float* dY, const float* out, const fl
     const int hg = pick_heads_per_warp(H, F, 8);
     if (!hg) return RG_ERR_SHAPE;
     PrepArgs<__nv_bfloat16, 8> a{dY, out, bias, static_cast<__nv_bfloat16*>(G), t, hsum, rows, H, F, hg, apply_elu, row_ids, drop_bits, drop_words, drop_scale,
-                                      static_cast<__nv_bfloat16*>(G_export_bf16)};
+                                      static_cast<__nv_bfloat16*>(G_export_bf16), dy_compact};
     return launch_tasks(bwd_prep_kernel<__nv_bfloat16, 8>, a, static_cast<long long>(rows) * (H / hg), s);
   }
   float* Gf = static_cast<float*>(G);
@@ -312,13 +316,13 @@ extern "C" int relgat_layer_bwd_prep(const float* dY, const float* out, const fl
     const int hg = pick_heads_per_warp(H, F, 4);
     if (!hg) return RG_ERR_SHAPE;
     PrepArgs<float, 4> a{dY, out, bias, Gf, t, hsum, rows, H, F, hg, apply_elu, row_ids, drop_bits, drop_words, drop_scale,
-                                      static_cast<__nv_bfloat16*>(G_export_bf16)};
+                                      static_cast<__nv_bfloat16*>(G_export_bf16), dy_compact};
     return launch_tasks(bwd_prep_kernel<float, 4>, a, static_cast<long long>(rows) * (H / hg), s);
   }
   const int hg = pick_heads_per_warp(H, F, 1);
   if (!hg) return RG_ERR_SHAPE;
   PrepArgs<float, 1> a{dY, out, bias, Gf, t, hsum, rows, H, F, hg, apply_elu, row_ids, drop_bits, drop_words, drop_scale,
-                                      static_cast<__nv_bfloat16*>(G_export_bf16)};
+                                      static_cast<__nv_bfloat16*>(G_export_bf16), dy_compact};
   return launch_tasks(bwd_prep_kernel<float, 1>, a, static_cast<long long>(rows) * (H / hg), s);
 }
 
@@ -330,7 +334,7 @@ extern "C" int relgat_layer_bwd_src(const void* P, long long ldp, const void* G,
                                     const int* long_node, const int* long_part_ptr, int n_long, float* part_acc,
                                     float* dP, void* dP_hi, void* dP_lo, float* dz,
                                     const unsigned int* edge_bits, float edge_scale, const unsigned int* dst_nz_bits,
-                                    int want_ds, long long ldo, int H, int F, int R, int sm_count, int* work_counter,
+                                    const int* src_row, int want_ds, long long ldo, int H, int F, int R, int sm_count, int* work_counter,
                                     void* stream) {
   if (!P || !G || !A || !colptr || n_chunks < 0 || n_parts < 0 || n_long < 0 || H <= 0 || F <= 0 || R <= 0)
     return RG_ERR_ARG;
@@ -349,14 +353,14 @@ extern "C" int relgat_layer_bwd_src(const void* P, long long ldp, const void* G,
     if (!ok16) return RG_ERR_ALIGN;
     return run_src<__nv_bfloat16, 8>(P, ldp, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, ch, n_chunks, pt,
                                      long_node, long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, edge_bits, edge_scale,
-                                     dst_nz_bits, want_ds, ldo, H, F, R, sm_count, work_counter, s);
+                                     dst_nz_bits, src_row, want_ds, ldo, H, F, R, sm_count, work_counter, s);
   }
   if (F % 4 == 0 && ldp % 4 == 0 && ldo % 4 == 0 && ok16)
     return run_src<float, 4>(P, ldp, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, ch, n_chunks, pt, long_node,
-                             long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, edge_bits, edge_scale, dst_nz_bits, want_ds, ldo, H, F, R,
+                             long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, edge_bits, edge_scale, dst_nz_bits, src_row, want_ds, ldo, H, F, R,
                              sm_count, work_counter, s);
   return run_src<float, 1>(P, ldp, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, ch, n_chunks, pt, long_node,
-                           long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, edge_bits, edge_scale, dst_nz_bits, want_ds, ldo, H, F, R,
+                           long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, edge_bits, edge_scale, dst_nz_bits, src_row, want_ds, ldo, H, F, R,
                              sm_count, work_counter, s);
 }
 

@@ -57,6 +57,9 @@ struct SrcArgs {
   // G[dst] = 0 and t[dst] = 0, hence dz = 0 and no contribution to dP or dS: it is skipped without touching memory.
   // nullptr = every row may be non-zero.
   const uint32_t* nz_bits;
+  // compacted output (ds_on only): src_row[i] = row of dP / dP_hi / dP_lo that receives source i, or -1 = source i has
+  // no edge into a non-zero row: it is skipped altogether (no read of its P row, no output row).  nullptr = row i.
+  const int* src_row;
 };
 
 // DS: logit-table gradient columns on (a.ds_on), compile-time so that the plain variants carry none of its code.
@@ -119,6 +122,13 @@ __global__ void __launch_bounds__((PIPE ? kSrcWarpsPipe : kSrcWarps) * 32, 1) bw
     if (lane <= nn) cp0 = __ldg(a.colptr + n_lo + lane);
     if (32 + lane <= nn) cp1 = __ldg(a.colptr + n_lo + 32 + lane);
     if (64 + lane <= nn) cp2 = __ldg(a.colptr + n_lo + 64 + lane);
+    int sr0 = 0, sr1 = 0;  // output rows of the chunk's sources (nn <= 64)
+    if (DS && a.src_row) {
+      if (lane < nn) sr0 = __ldg(a.src_row + n_lo + lane);
+      if (32 + lane < nn) sr1 = __ldg(a.src_row + n_lo + 32 + lane);
+    }
+#define RG_SR(k_) ((k_) < 32 ? __shfl_sync(0xffffffffu, sr0, (k_) & 31) : __shfl_sync(0xffffffffu, sr1, (k_) & 31))
+#define RG_OROW(k_) ((DS && a.src_row) ? RG_SR(k_) : n_lo + (k_))
 #define RG_CP(k_) ((k_) < 32 ? __shfl_sync(0xffffffffu, cp0, (k_) & 31)       \
                              : ((k_) < 64 ? __shfl_sync(0xffffffffu, cp1, (k_) & 31) \
                                           : __shfl_sync(0xffffffffu, cp2, (k_) & 31)))
@@ -160,11 +170,19 @@ __global__ void __launch_bounds__((PIPE ? kSrcWarpsPipe : kSrcWarps) * 32, 1) bw
         if (!end_done) { end_done = true; ty_ = IT_END; }                                      \
         break;                                                                                 \
       }                                                                                        \
+      if (!own_done && DS && a.src_row && RG_SR(fk) < 0) { /* no edge into a non-zero row */    \
+        fe = f_end; ++fk;                                                                      \
+        if (fk < nn) f_end = RG_CP(fk + 1);                                                    \
+        continue;                                                                              \
+      }                                                                                        \
       if (!own_done) {                                                                         \
         own_done = true; nd_ = fk;                                                             \
         ty_ = (f_end == fe) ? IT_ZERO : IT_OWN;                                                \
-        if (pf_lane_ok && a.pf_dist > 0 && fk + 2 < nn) /* own rows: keep two ahead in L2 */     \
-          prefetch_l2(p_pf + static_cast<unsigned long long>(n_lo + fk + 2) * p_stride_b);     \
+        if (a.pf_dist > 0 && fk + 2 < nn) { /* own rows: keep two ahead in L2 */                \
+          const bool wanted = !(DS && a.src_row) || RG_SR(fk + 2) >= 0;                        \
+          if (pf_lane_ok && wanted)                                                            \
+            prefetch_l2(p_pf + static_cast<unsigned long long>(n_lo + fk + 2) * p_stride_b);   \
+        }                                                                                      \
         break;                                                                                 \
       }                                                                                        \
       if (fe < f_end) {                                                                        \
@@ -262,7 +280,7 @@ __global__ void __launch_bounds__((PIPE ? kSrcWarpsPipe : kSrcWarps) * 32, 1) bw
   } else {                                                                                     \
     if (DS && cur >= 0) { /* dS columns of the source being closed, then clear the slots */    \
       __syncwarp();                                                                            \
-      const long long drow = (part >= 0 ? static_cast<long long>(part) : static_cast<long long>(n_lo + cur)) * a.ldo + ds_col0; \
+      const long long drow = (part >= 0 ? static_cast<long long>(part) : static_cast<long long>(RG_OROW(cur))) * a.ldo + ds_col0; \
       if (part < 0 && !a.dP && a.dP_hi && (ds_n & 7) == 0 && (ds_col0 & 7) == 0 && (a.ldo & 7) == 0) { \
         /* planes only (the training path): 8 values -> one 16-byte store per plane */          \
         for (int i = lane * 8; i < ds_n; i += 256) {                                           \
@@ -294,7 +312,7 @@ __global__ void __launch_bounds__((PIPE ? kSrcWarpsPipe : kSrcWarps) * 32, 1) bw
       _Pragma("unroll") for (int k = 0; k < KV; ++k)                                           \
         if (RG_VALID(k)) RowVec<float, V>::store(a.part_acc + row_off + k * kstride, acc[k]);  \
     } else if (cur >= 0) {                                                                     \
-      const long long row_off = static_cast<long long>(n_lo + cur) * a.ldo + lane_off;         \
+      const long long row_off = static_cast<long long>(RG_OROW(cur)) * a.ldo + lane_off;       \
       _Pragma("unroll") for (int k = 0; k < KV; ++k) {                                         \
         if (RG_VALID(k)) {                                                                     \
           const long long off = row_off + k * kstride;                                         \
@@ -377,6 +395,8 @@ __global__ void __launch_bounds__((PIPE ? kSrcWarpsPipe : kSrcWarps) * 32, 1) bw
 #undef RG_ISSUE
 #undef RG_NEXT
 #undef RG_CP
+#undef RG_OROW
+#undef RG_SR
   }
 #undef RG_VALID
 }
@@ -389,7 +409,9 @@ bwd_src_merge_kernel(const SrcArgs<T, V> a, const int* __restrict__ long_node, c
   const int C = a.H * a.F;
   const int li = blockIdx.x;
   if (li >= n_long) return;
-  const int i = long_node[li];
+  const int node = long_node[li];
+  const int i = a.src_row ? a.src_row[node] : node;  // output row
+  if (i < 0) return;                                  // skipped source: its parts were not written
   const int p_lo = long_part_ptr[li], p_hi = long_part_ptr[li + 1];
   for (int c = threadIdx.x * V; c < C; c += blockDim.x * V) {
     float acc[V];
@@ -506,8 +528,8 @@ int run_src(const void* P, long long ldp, const void* G, const float* A, const f
                    const float* t, const int* colptr, const int* csc_slot, const int* csc_dst, const int* csc_rel,
                    const int4* ch, int n_chunks, const int2* pt, const int* long_node, const int* long_part_ptr,
                    int n_long, float* part_acc, float* dP, void* dP_hi, void* dP_lo, float* dz,
-                   const uint32_t* edge_bits, float edge_scale, const uint32_t* nz_bits, int ds_on, long long ldo,
-                   int H, int F, int R, int sm_count, int* work_counter, cudaStream_t s) {
+                   const uint32_t* edge_bits, float edge_scale, const uint32_t* nz_bits, const int* src_row, int ds_on,
+                   long long ldo, int H, int F, int R, int sm_count, int* work_counter, cudaStream_t s) {
   const int hg = pick_heads_per_warp(H, F, V, R, smem_budget_override("RELGAT_SRC_BUDGET_KB", kSmemBudgetA));
   if (!hg) return RG_ERR_SHAPE;
   if (H / hg > 32) return RG_ERR_SHAPE;  // work_counter holds 32 ints (one per head-group)
@@ -518,7 +540,8 @@ int run_src(const void* P, long long ldp, const void* G, const float* A, const f
   SrcArgs<T, V> a{static_cast<const T*>(P), static_cast<const T*>(G), A, z, minv, t, colptr, csc_slot, csc_dst,
                   csc_rel, ch, pt, part_acc, dP, static_cast<__nv_bfloat16*>(dP_hi),
                   static_cast<__nv_bfloat16*>(dP_lo), dz, n_chunks, H, F, R, hg, ldp, 0, 0, work_counter,
-                  edge_bits, edge_scale, ds_on, ldo, ds_on ? nz_bits : nullptr};
+                  edge_bits, edge_scale, ds_on, ldo, ds_on ? nz_bits : nullptr,
+                  ds_on ? src_row : nullptr};
   int rc = launch_src(a, sm_count, s);
   if (rc != RG_OK || n_long == 0) return rc;
   bwd_src_merge_kernel<T, V><<<n_long, 128, 0, s>>>(a, long_node, long_part_ptr, n_long);

@@ -33,6 +33,12 @@ TAIL_ON_SIDE = os.environ.get("RELGAT_TAIL_SIDE", "0") != "0"
 # fewer gathers.  RELGAT_SPARSE_BWD=0 gathers every edge (bench.py's headline does, so that its unit of work stays the
 # dense pass of SURVEY.md §8(d); the sparse pass is reported beside it).
 SPARSE_BWD = os.environ.get("RELGAT_SPARSE_BWD", "1") != "0"
+# ... and, on top of it (fp32 mode), the backward is COMPACTED to those rows: the by-source pass writes only the dP rows
+# of sources with an edge into a non-zero row, the weight-gradient / dX GEMMs run over those rows only, the hidden layers'
+# prep touches only them.  The row sets depend on the batch ids and the graph alone, so they (and their sizes, which the
+# host needs for the GEMM shapes) are prepared on the side stream during the forward.  RELGAT_COMPACT_BWD=0: skip edges
+# only (dense rows).
+COMPACT_BWD = os.environ.get("RELGAT_COMPACT_BWD", "1") != "0"
 
 _SIDE_STREAMS = {}
 
@@ -124,6 +130,35 @@ def weight_grad_gemm(dPp, xp, Wd: int, d_in: int, rows: int, device) -> torch.Te
     return ops.gemm(dPp, True, xp, True, Wd, d_in, rows, splits_k=ops.pick_splits_k(Wd, d_in, rows, device))
 
 
+def _plan_compact_backward(gather, g: GraphIndex, L: int):
+    """Row sets of the compacted backward, one entry per layer (first layer first): ``dst_bits`` = rows of dL/d out_l
+    that can be non-zero, ``rank`` / ``list`` = compact numbering of the sources of the edges into them (= the rows of
+    dP_l, and the non-zero rows one layer down), ``counts`` = their sizes in pinned host memory once ``ready`` fired.
+    Everything runs on the side stream behind the id sort: it is off the forward's critical chain."""
+    keys, _, sorted_ev = gather
+    dev = keys.device
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev)
+    side.wait_event(sorted_ev)
+    with torch.cuda.stream(side):
+        bits = ops.mark_rows(keys, g.N)
+        layers = []
+        for _ in range(L):
+            sbits = ops.mark_sources(bits, g)
+            rank, lst, cnt = ops.bitmap_ranks(sbits, g.N_src)
+            layers.append(dict(dst_bits=bits, rank=rank, list=lst, count=cnt))
+            bits = sbits
+        layers.reverse()
+        counts = torch.empty((L,), dtype=torch.int32, pin_memory=True)
+        counts.copy_(torch.cat([p["count"] for p in layers]), non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(side)
+    for p in layers:
+        for k in ("dst_bits", "rank", "list"):
+            p[k].record_stream(main)
+    return dict(layers=layers, counts=counts, ready=ready)
+
+
 class LayerDropout:
     """Dropout state of one layer for one forward/backward: ``feat`` = ops.DropMask of the feature dropout on the
     layer's output (reference layer.py:321-322) or None, ``edge`` = ops.DropMask of the attention dropout
@@ -195,9 +230,13 @@ class RelGATStackFunction(torch.autograd.Function):
         ctx.cfg = (H, F, L, with_lo)
         ctx.x0_needs_grad = bool(x0 is not None and x0.requires_grad)
         ctx.gather = None
+        ctx.plan = None
         if gather_ids is not None:
             ids = gather_ids.contiguous()
             ctx.gather = presort_on_side_stream(ids, graphs[-1].N)  # (sorted keys, perm, event): summation order of backward
+            ctx.plan = None
+            if SPARSE_BWD and COMPACT_BWD and USE_DS and with_lo and not blocks and not ctx.x0_needs_grad:
+                ctx.plan = _plan_compact_backward(ctx.gather, graphs[-1], L)
             rows = out.new_empty((ids.numel(), C))
             ops.pull_rows(out, ids, rows)
             return rows
@@ -228,6 +267,10 @@ class RelGATStackFunction(torch.autograd.Function):
             dY = grad_out.contiguous()
             nz_rows = sparse_rows_of(grad_out) if dY is grad_out else None
             owned = False
+        if ctx.plan is not None and table is not None and SPARSE_BWD and COMPACT_BWD:
+            grads = _backward_compact(ctx, table, keys)
+            ctx.saved = None
+            return (None, None, None, None, None, None, None, None, *grads)
         # (blocks hold nothing but the rows the batch reaches: there is nothing to skip)
         nz_bits = ops.mark_rows(nz_rows, N) if (SPARSE_BWD and USE_DS and nz_rows is not None and not blocks) else None
         dX = None
@@ -319,6 +362,61 @@ class RelGATStackFunction(torch.autograd.Function):
             del G, dPp, dz
         ctx.saved = None
         return (dX if ctx.x0_needs_grad else None, None, None, None, None, None, None, None, *grads)
+
+
+def _backward_compact(ctx, table: torch.Tensor, keys: torch.Tensor) -> List[Optional[torch.Tensor]]:
+    """Backward of the stack restricted to the rows that can be non-zero (see COMPACT_BWD): per layer
+    sparse prep -> by-source pass over the marked edges, dP rows written compactly -> gather of the matching input rows
+    -> [dP | dS]^T X and dP W over those rows only.  ``table`` = the zero table holding the batch rows' gradients."""
+    H, F, L, with_lo = ctx.cfg
+    g = ctx.graphs[-1]
+    C, N, HR = H * F, g.N, H * g.R
+    dev = table.device
+    plan = ctx.plan
+    plan["ready"].synchronize()  # sizes of the row sets (computed during the forward: long done)
+    counts = [int(v) for v in plan["counts"].tolist()]
+    torch.cuda.current_stream(dev).wait_event(plan["ready"])
+    grads: List[Optional[torch.Tensor]] = [None] * (3 * L)
+    dX_c, G_table, prev_rows = None, None, None
+    for l in reversed(range(L)):
+        s, pl, n_s = ctx.saved[l], plan["layers"][l], counts[l]
+        dl = s["drop"]
+        if l == L - 1:
+            G, t, hsum = ops.edge_bwd_prep(table, s["out"], s["bias"], H, F, apply_elu=False, inplace=True,
+                                           nonzero_rows=keys, feat_drop=dl.feat if dl else None)
+            clear_rows = keys
+        else:
+            G_table = _take_zero_table(dev, N, C)
+            G, t, hsum = ops.edge_bwd_prep(dX_c, s["out"], s["bias"], H, F, apply_elu=True, G_out=G_table,
+                                           compact_rows=prev_rows, feat_drop=dl.feat if dl else None)
+            clear_rows = prev_rows
+        dPp = None
+        if n_s > 0:
+            _, dPp, _ = ops.edge_bwd_src(s["P"], G, s["A"], s["z"], s["minv"], t, g, H, F, want_fp32=False,
+                                         want_planes=True, planes_lo=True, edge_drop=dl.edge if dl else None,
+                                         want_ds=True, dst_nz=pl["dst_bits"], src_rows=(pl["rank"], n_s))
+        ops.zero_rows(G, clear_rows)  # the table's rows are consumed: all-zero again for the next step
+        _return_zero_table(G)
+        if n_s == 0:  # no edge reaches a non-zero row: this layer's and every lower layer's gradients are zero
+            for k in range(l + 1):
+                sk = ctx.saved[k]
+                grads[3 * k] = torch.zeros((C, sk["d_in"]), dtype=torch.float32, device=dev)
+                grads[3 * k + 1] = torch.zeros_like(sk["A"])
+                grads[3 * k + 2] = torch.zeros((g.R,), dtype=torch.float32, device=dev) if sk["has_beta"] else None
+            break
+        rows = pl["list"][:n_s]
+        xp_c = tuple(None if p_ is None else ops.gather_plane_rows(p_, rows) for p_ in s["xp"])
+        d_in = s["d_in"]
+        dW_ext = weight_grad_gemm(dPp, xp_c, dPp[0].size(1), d_in, n_s, dev)
+        if l > 0:
+            dX_c = ops.gemm(tuple(p_[:, :C] for p_ in dPp), False, s["WTp"], False, n_s, d_in, C)
+            prev_rows = rows
+        Tp = ops.split_bf16(dW_ext[C:C + HR].contiguous(), with_lo)
+        dA_full = ops.gemm(Tp, False, s["Wp"], False, HR, C, d_in)
+        grads[3 * l] = dW_ext[:C]
+        grads[3 * l + 1] = torch.stack([dA_full[h * g.R:(h + 1) * g.R, h * F:(h + 1) * F] for h in range(H)])
+        grads[3 * l + 2] = ops.edge_bwd_beta(hsum, g, H) if s["has_beta"] else None
+    return grads
 
 
 def relgat_stack(x0, graph, heads, out_dim, layer_params: Sequence, precision="fp32", x0_planes=None, drop=None,

@@ -346,13 +346,32 @@ def edge_bwd_prep(dY: torch.Tensor, out: torch.Tensor, bias: torch.Tensor, H: in
                   apply_elu: bool, inplace: bool = False, g_bf16: bool = False,
                   G_out: Optional[torch.Tensor] = None, t_out: Optional[torch.Tensor] = None,
                   hsum_out: Optional[torch.Tensor] = None, nonzero_rows: Optional[torch.Tensor] = None,
-                  feat_drop: Optional["DropMask"] = None, g_export: Optional[torch.Tensor] = None):
+                  feat_drop: Optional["DropMask"] = None, g_export: Optional[torch.Tensor] = None,
+                  compact_rows: Optional[torch.Tensor] = None):
     """Returns (G [N,C] fp32 or bf16, t [N,H], hsum [N,H]).  ``G_out`` / ``t_out`` / ``hsum_out``:
     caller-owned fp32 buffers (rows of a peer table on the partitioned path).  ``nonzero_rows`` (int64, may
-    repeat): all other rows of dY are known to be zero; used only when G can alias dY (fp32, no activation)."""
+    repeat): all other rows of dY are known to be zero; used only when G can alias dY (fp32, no activation).
+    ``compact_rows`` (int64 [n], distinct): dY is [n, C] and holds the gradient of node compact_rows[k] in row k; G_out
+    is an [N, C] table whose other rows are zero (the caller clears the written rows afterwards); t / hsum come back
+    dense with zeros elsewhere."""
     dY = _f32c(dY, "dY")
     out = _f32c(out, "out")
     N = out.size(0)
+    if compact_rows is not None:
+        rows = _ids(compact_rows, "compact_rows")
+        if G_out is None or tuple(G_out.shape) != tuple(out.shape) or dY.size(0) != rows.numel() or dY.size(1) != out.size(1):
+            raise ValueError("compact_rows: dY must be [len(rows), C] and G_out an [N, C] table")
+        G = _out_buf(G_out, tuple(out.shape), dY.device, "G_out")
+        t = _out_buf(t_out, (N, H), dY.device, "t_out")
+        hsum = _out_buf(hsum_out, (N, H), dY.device, "hsum_out")
+        with torch.cuda.device(dY.device):
+            rc = _lib.load().relgat_layer_bwd_prep(_lib.ptr(dY), _lib.ptr(out), _lib.ptr(bias), _lib.ptr(G), 0,
+                                                   _lib.ptr(t), _lib.ptr(hsum), N, H, F, int(apply_elu),
+                                                   _lib.ptr(rows), int(rows.numel()),
+                                                   *_feat_mask_args(feat_drop, N, H * F), None, 1, _stream(dY))
+        _lib.check(rc, "relgat_layer_bwd_prep")
+        _count(1 if rows.numel() else 0)
+        return G, t, hsum
     if G_out is not None:
         G = _out_buf(G_out, tuple(dY.shape), dY.device, "G_out")
         g_bf16 = False
@@ -371,7 +390,7 @@ def edge_bwd_prep(dY: torch.Tensor, out: torch.Tensor, bias: torch.Tensor, H: in
                                                _lib.ptr(t), _lib.ptr(hsum), N, H, F, int(apply_elu),
                                                _lib.ptr(rows), 0 if rows is None else int(rows.numel()),
                                                *_feat_mask_args(feat_drop, N, H * F), _lib.ptr(_export_buf(g_export, dY)),
-                                               _stream(dY))
+                                               0, _stream(dY))
     _lib.check(rc, "relgat_layer_bwd_prep")
     _count(1)
     return G, t, hsum
@@ -389,11 +408,14 @@ def ds_row_width(H: int, F: int, R: int) -> int:
 
 def edge_bwd_src(P, G, A, z, minv, t, g: GraphIndex, H: int, F: int, want_fp32: bool = True,
                  want_planes: bool = False, planes_lo: bool = True, edge_drop: Optional["DropMask"] = None,
-                 want_ds: bool = False, dst_nz: Optional[torch.Tensor] = None):
+                 want_ds: bool = False, dst_nz: Optional[torch.Tensor] = None,
+                 src_rows: Optional[Tuple[torch.Tensor, int]] = None):
     """Returns (dP fp32 or None, dP planes or None, dz [E,H] or None).  ``want_ds``: the rows are
     ``ds_row_width`` wide, columns H*F + h*R + r hold dS and dz is not written.
     ``dst_nz`` (want_ds only): row bitmap from ``mark_rows`` / ``mark_sources`` — rows of G outside it are exact zeros
-    (and so are their t), the edges into them are skipped."""
+    (and so are their t), the edges into them are skipped.  ``src_rows`` = (rank int32 [N_src], n) from
+    ``bitmap_ranks`` of the sources of the marked rows: the output has n rows, source i is written to row rank[i] and
+    sources with rank -1 are skipped altogether."""
     P = _feat(P, "P")
     G = _feat(G, "G")
     if P.dtype != G.dtype:
@@ -405,9 +427,16 @@ def edge_bwd_src(P, G, A, z, minv, t, g: GraphIndex, H: int, F: int, want_fp32: 
         raise ValueError("P / G row counts do not match the graph index")
     W = ds_row_width(H, F, g.R) if want_ds else C
     mk = torch.zeros if W > C + H * g.R else torch.empty  # padding columns feed the GEMM: keep them finite
-    dP = mk((n_src, W), dtype=torch.float32, device=dev) if want_fp32 else None
-    hi = mk((n_src, W), dtype=torch.bfloat16, device=dev) if want_planes else None
-    lo = mk((n_src, W), dtype=torch.bfloat16, device=dev) if (want_planes and planes_lo) else None
+    n_out, rank = n_src, None
+    if src_rows is not None:
+        rank, n_out = src_rows[0], int(src_rows[1])
+        if not want_ds or dst_nz is None:
+            raise ValueError("src_rows needs want_ds and dst_nz (the sources of the marked rows)")
+        if rank.dtype != torch.int32 or rank.device != dev or rank.numel() != n_src or not rank.is_contiguous():
+            raise ValueError("src_rows: rank must be a contiguous int32 [N_src] tensor on the feature device")
+    dP = mk((n_out, W), dtype=torch.float32, device=dev) if want_fp32 else None
+    hi = mk((n_out, W), dtype=torch.bfloat16, device=dev) if want_planes else None
+    lo = mk((n_out, W), dtype=torch.bfloat16, device=dev) if (want_planes and planes_lo) else None
     dz = None if want_ds else torch.empty((g.E, H), dtype=torch.float32, device=dev)
     ck = g.src_chunks
     part_acc = torch.empty((ck.n_parts, W), dtype=torch.float32, device=dev) if ck.n_parts else None
@@ -440,7 +469,7 @@ def edge_bwd_src(P, G, A, z, minv, t, g: GraphIndex, H: int, F: int, want_fp32: 
             _lib.ptr(ck.chunks), ck.n_chunks, _lib.ptr(ck.parts), ck.n_parts,
             _lib.ptr(ck.long_node), _lib.ptr(ck.long_part_ptr), ck.n_long, _lib.ptr(part_acc),
             _lib.ptr(dP), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dz), *_edge_mask_args(edge_drop, g.E, H),
-            _lib.ptr(dst_nz), int(want_ds), W, H, F, g.R, sm_count(dev), _lib.ptr(_work_counter(dev)), _stream(P))
+            _lib.ptr(dst_nz), _lib.ptr(rank), int(want_ds), W, H, F, g.R, sm_count(dev), _lib.ptr(_work_counter(dev)), _stream(P))
     _lib.check(rc, "relgat_layer_bwd_src")
     _count(2 if ck.n_long else 1)
     return dP, ((hi, lo) if want_planes else None), dz
@@ -475,6 +504,26 @@ def mark_sources(dst_bits: torch.Tensor, g: GraphIndex) -> torch.Tensor:
                                                    _lib.ptr(src_bits), _stream(dst_bits)), "relgat_mark_sources")
     _count(1 if g.N else 0)
     return src_bits
+
+
+def bitmap_ranks(bits: torch.Tensor, n_rows: int, want_list: bool = True):
+    """(rank int32 [n_rows] — position of each marked row among the marked rows or -1, list int64 [n_rows] whose first
+    ``count`` entries are the marked rows in ascending order (or None), count int32 [1]) — all on the device."""
+    _lib.require_cuda(bits)
+    if bits.dtype != torch.int32 or bits.numel() < (n_rows + 31) // 32 or not bits.is_contiguous():
+        raise ValueError("bits must be a contiguous int32 bitmap of ceil(n_rows / 32) words")
+    dev = bits.device
+    rank = torch.empty((n_rows,), dtype=torch.int32, device=dev)
+    lst = torch.empty((n_rows,), dtype=torch.int64, device=dev) if want_list else None
+    count = torch.empty((1,), dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    ws_bytes = int(lib.relgat_bitmap_ranks_workspace_bytes(n_rows))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.relgat_bitmap_ranks(_lib.ptr(bits), n_rows, _lib.ptr(rank), _lib.ptr(lst), _lib.ptr(count),
+                                           _lib.ptr(ws), ws_bytes, _stream(bits)), "relgat_bitmap_ranks")
+    _count(3 if n_rows else 0)
+    return rank, lst, count
 
 
 def edge_bwd_beta(hsum: torch.Tensor, g: GraphIndex, H: int) -> torch.Tensor:

@@ -501,10 +501,14 @@ def test_by_source_pass_with_zero_row_hint_equals_the_full_pass(dev, storage):
         ops.edge_bwd_src(P.to(dt), G, A, z, minv, t, g, h, f, want_ds=True, dst_nz=torch.zeros(3, dtype=torch.int32, device=dev))
 
 
-@pytest.mark.parametrize("name", ["f200_fp32", "transe_proj_fp32", "tiny_fp64"])
-def test_training_step_with_and_without_zero_row_skipping_is_bit_identical(dev, name, monkeypatch):
+@pytest.mark.parametrize("compact", [False, True])
+@pytest.mark.parametrize("name", ["f200_fp32", "transe_proj_fp32", "tiny_fp64", "adversarial_fp32"])
+def test_training_step_with_and_without_zero_row_skipping(dev, name, compact, monkeypatch):
+    """Skipping the edges into exact-zero rows changes no bit of the gradients; compacting the backward to the rows that
+    can be non-zero (fewer rows in the weight-gradient GEMMs' sums) changes only their rounding."""
     c = Case(name)
     res = []
+    monkeypatch.setattr(RF, "COMPACT_BWD", compact)
     for sparse in (True, False):
         monkeypatch.setattr(RF, "SPARSE_BWD", sparse)
         m = _load_model(c, dev)
@@ -516,7 +520,10 @@ def test_training_step_with_and_without_zero_row_skipping_is_bit_identical(dev, 
         res.append({n_: p.grad.clone() for n_, p in m.named_parameters() if p.grad is not None})
     assert res[0].keys() == res[1].keys() and len(res[0]) > 0
     for n_ in res[0]:
-        assert torch.equal(res[0][n_], res[1][n_]), n_
+        if compact:
+            assert rel_err(res[0][n_].cpu().numpy(), res[1][n_].cpu().numpy()) < 2e-5, n_
+        else:
+            assert torch.equal(res[0][n_], res[1][n_]), n_
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -662,3 +669,58 @@ def test_receptive_field_edge_cases_isolated_nodes_and_repeated_ids(dev):
         assert res[0][1].keys() == res[1][1].keys()
         for k in res[0][1]:
             assert rel_err(res[1][1][k].cpu().numpy(), res[0][1][k].cpu().numpy()) < 2e-5, (layers, k)
+
+
+def test_bitmap_ranks_numbering(dev):
+    gen = torch.Generator(device=dev).manual_seed(4)
+    for n in (1, 31, 32, 33, 5000):
+        ids = torch.randint(0, n, (max(1, n // 3),), generator=gen, device=dev)
+        bits = ops.mark_rows(ids, n)
+        rank, lst, cnt = ops.bitmap_ranks(bits, n)
+        want = np.unique(ids.cpu().numpy())
+        assert int(cnt) == want.size
+        assert np.array_equal(lst[:want.size].cpu().numpy(), want)
+        r = rank.cpu().numpy()
+        assert np.array_equal(np.nonzero(r >= 0)[0], want) and np.array_equal(r[want], np.arange(want.size))
+    rank, lst, cnt = ops.bitmap_ranks(ops.row_bitmap(100, dev), 100)
+    assert int(cnt) == 0 and bool((rank == -1).all())
+
+
+def test_compacted_by_source_pass_equals_rows_of_the_full_pass(dev):
+    """src_rows: the output holds exactly the rows of the sources with an edge into a marked row, in ascending source
+    order, bit-identical to those rows of the uncompacted output; every other row of the full output is zero."""
+    gen = torch.Generator(device=dev).manual_seed(10)
+    n, e, r, h, f = 3000, 20000, 11, 4, 40
+    ei = torch.randint(0, n, (2, e), generator=gen, device=dev)
+    ei[1, :1500] = 7
+    ei[0, 1500:2200] = 9     # split source, reaches marked rows
+    ei[0][ei[0] == 10] = 11  # source 10 gets exactly the 700 edges below
+    ei[0, 2200:2900] = 10    # split source ...
+    ei[1, 2200:2900] = torch.randint(100, 200, (700,), generator=gen, device=dev)  # ... into unmarked rows only
+    et = torch.randint(0, r, (e,), generator=gen, device=dev)
+    g = GraphIndex(ei, et, n, r)
+    P = torch.randn((n, h * f), generator=gen, device=dev)
+    A = torch.randn((h, r, f), generator=gen, device=dev) * 0.2
+    beta = torch.randn((r,), generator=gen, device=dev) * 0.1
+    rows = torch.unique(torch.cat([torch.randint(200, n, (120,), generator=gen, device=dev), torch.tensor([7], device=dev)]))
+    dY = torch.zeros((n, h * f), device=dev)
+    dY[rows] = torch.randn((rows.numel(), h * f), generator=gen, device=dev)
+    out, _, _, z, minv, bias = ops.edge_fwd(P, A, beta, g, h, f)
+    G, t, _ = ops.edge_bwd_prep(dY, out, bias, h, f, apply_elu=False)
+    bits = ops.mark_rows(rows, n)
+    _, (hi, lo), _ = ops.edge_bwd_src(P, G, A, z, minv, t, g, h, f, want_fp32=False, want_planes=True, want_ds=True, dst_nz=bits)
+    rank, lst, cnt = ops.bitmap_ranks(ops.mark_sources(bits, g), n)
+    n_s = int(cnt)
+    _, (chi, clo), _ = ops.edge_bwd_src(P, G, A, z, minv, t, g, h, f, want_fp32=False, want_planes=True, want_ds=True,
+                                        dst_nz=bits, src_rows=(rank, n_s))
+    keep = lst[:n_s]
+    assert 0 < n_s < n and chi.size(0) == n_s
+    assert torch.equal(chi, hi[keep]) and torch.equal(clo, lo[keep])
+    other = torch.ones(n, dtype=torch.bool, device=dev)
+    other[keep] = False
+    assert float(hi[other].float().abs().sum()) == 0.0 and bool(other[10])
+    # compact prep: the gradient rows of the listed nodes only -> rows of a zero table
+    Gt = torch.zeros_like(dY)
+    G2, t2, h2 = ops.edge_bwd_prep(dY[rows].contiguous(), out, bias, h, f, apply_elu=True, G_out=Gt, compact_rows=rows)
+    G1, t1, h1 = ops.edge_bwd_prep(dY, out, bias, h, f, apply_elu=True)
+    assert torch.equal(G2, G1) and torch.equal(t2, t1) and torch.equal(h2, h1)
