@@ -375,8 +375,8 @@ def main():
     ap.add_argument("--profile-steps", type=int, default=3)
     ap.add_argument("--backward", default="dense", choices=["dense", "sparse"],
                     help="dense (headline): the by-source pass gathers G[dst] for every edge, SURVEY.md §8(d)'s unit of work; "
-                         "sparse: edges into rows whose gradient is an exact zero are skipped (the library's default; same "
-                         "gradients bit for bit) — always reported beside the headline as exact_sparse_backward")
+                         "sparse: the backward covers only the rows whose gradient can be non-zero (the library's default; "
+                         "same gradients) — always reported beside the headline as exact_sparse_backward")
     ap.add_argument("--ref-scale", type=int, default=1,
                     help="--impl reference: run the configuration at 1/SCALE of its nodes and triplets (default 1: in full)")
     args = ap.parse_args()
@@ -547,8 +547,8 @@ def main():
                  "frac_of_hbm_peak": round(sbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
                  "formula": "SURVEY.md §8(d) bytes_step, fp32"}
 
-    # side record: the same step with the exact-zero rows of the output gradient skipped in the by-source passes (the
-    # library default, functional.SPARSE_BWD): identical gradients, fewer gathers; a different unit of work than §8(d)'s
+    # side record: the same step with the backward restricted to the rows of the output gradient that can be non-zero
+    # (the library default, functional.SPARSE_BWD / COMPACT_BWD): same gradients, a different unit of work than §8(d)'s
     sparse_rec = None
     if args.backward == "dense" and not args.no_alt_precision and RFn.USE_DS:
         RFn.SPARSE_BWD = True
@@ -563,9 +563,12 @@ def main():
         sparse_rec = {"ms_per_step": ms_sp, "value": E / (ms_sp * 1e-3), "unit": UNIT,
                       "speedup_vs_dense": round(ms / ms_sp, 4),
                       "edge_bwd_src_avg_ms": [round(d["avg_ms"], 4) for t_, d in tsp.items() if d["kernel"] == "edge_bwd_src"],
-                      "note": "edges into rows of dL/d out that are exact zeros (outside the batch rows at the last layer, "
-                              "outside their in-neighbourhood one layer down) are skipped; bit-identical gradients "
-                              "(tests/test_gpu_fused.py); edges/s still counts all E edges of the graph"}
+                      "compacted": bool(RFn.COMPACT_BWD),
+                      "note": "full-graph forward; backward restricted to the rows of dL/d out that can be non-zero "
+                              "(the batch rows at the last layer, their in-neighbourhood one layer down): edges into "
+                              "exact-zero rows are skipped (bit-identical gradients) and, compacted, the dP rows and the "
+                              "weight-gradient / dX GEMMs cover those rows only (gradients equal to rounding, 2e-5; "
+                              "tests/test_gpu_fused.py); edges/s still counts all E edges of the graph"}
 
     # side record: the same step on the batch's receptive-field blocks — per step, the L-hop
     # in-neighbourhood of the batch's nodes is extracted on the GPU (inside the timed region) and the same kernels run on
