@@ -59,14 +59,22 @@ int relgat_graph_index_build(const long long* src, const long long* dst, const l
  * alone and is cut into parts of part_edges edges, one chunk per part.  Order: parts first (segment, then part order),
  * then the ordinary chunks in segment order.
  *   chunks int32[max_chunks][4] = (first segment, segments, part slot or -1, 0); parts int32[max_parts][2] = (first edge,
- *   end edge); long_node[max_long]; long_part_ptr[max_long + 1]; counts int32[3] = (n_chunks, n_parts, n_long) on the
- *   device — n_chunks = -1 if a table was too small (nothing else is then valid).  Safe sizes for E edges:
+ *   end edge); long_node[max_long]; long_part_ptr[max_long + 1]; counts int32[4] = (n_chunks, n_parts, n_long, edges
+ *   covered) on the device — n_chunks = -1 if a table was too small (nothing else is then valid).  Safe sizes for E edges:
  *   max_long = E / (long_segment + 1) + 1, max_parts = E / part_edges + max_long, max_chunks = n + max_parts. */
 long long relgat_stream_chunks_workspace_bytes(int n);
 int relgat_stream_chunks_build(const int* ptr, int n, int chunk_edges, int chunk_nodes, int long_segment,
                                int part_edges, int* chunks, int max_chunks, int* parts, int max_parts,
                                int* long_node, int* long_part_ptr, int max_long, int* counts,
                                void* workspace, long long workspace_bytes, void* stream);
+/* The same tables restricted to a list of segments (the destinations one batch needs, ascending): one chunk per listed
+ * segment, split segments as above.  rows int64[n_rows]; n_rows_dev (optional, device): the list's true length when
+ * only an upper bound n_rows is known to the host (entries beyond it are ignored).  Workspace as for n = n_rows;
+ * safe sizes: max_chunks = n_rows + max_parts. */
+int relgat_stream_chunks_for_rows(const int* ptr, const long long* rows, int n_rows, const int* n_rows_dev,
+                                  int long_segment, int part_edges, int* chunks, int max_chunks, int* parts,
+                                  int max_parts, int* long_node, int* long_part_ptr, int max_long, int* counts,
+                                  void* workspace, long long workspace_bytes, void* stream);
 
 /* ---- dense feature transform (tcgen05 + TMA) ---------------------------------------------
  * Replaces `lin(node_emb)` of core/model/layer.py:220 (all heads in one GEMM) and its autograd
@@ -131,6 +139,10 @@ int relgat_layer_fwd(const void* P, int p_is_bf16, long long ldp, const float* A
                      float* alpha, float* z, float* minv, float* bias_out,
                      const unsigned int* drop_bits, int drop_words, float drop_scale,
                      const unsigned int* edge_bits, float edge_scale,
+                     const int* src_row /* NULL, or: P holds only the rows the processed destinations read, source i at
+                        row src_row[i] (relgat_bitmap_ranks); with a chunk table that lists only the destinations a
+                        batch needs (relgat_stream_chunks_for_rows) this is the receptive-field forward: the other rows
+                        of out / act / minv / bias_out and the other edges' z are NOT written */,
                      int H, int F, int R, int sm_count, int* work_counter, void* stream);
 
 /* ---- RelGAT layer, edge part, backward (replaces the autograd replay of layer.py:220-318) ---
@@ -174,6 +186,7 @@ int relgat_layer_bwd_src(const void* P, long long ldp, const void* G, int feat_i
                             other rows are skipped: their G[dst], t[dst] and hence dz are exact zeros); NULL = all rows */,
                          const int* src_row /* want_ds only: output row of each source, -1 = skip the source (it has no
                             edge into a non-zero row); from relgat_bitmap_ranks; NULL = row i for source i */,
+                         int p_compact /* with src_row: P itself holds the kept sources' rows only (row src_row[i]) */,
                          int want_ds, long long ldo, int H, int F, int R, int sm_count, int* work_counter, void* stream);
 /* Training-path variant of relgat_layer_bwd_src (second generation): fp32 P / G rows with F % 4 == 0, bf16 planes out,
  * want_ds semantics (rows ldo >= H*F + H*R wide, dS behind dP, no dz).  A pre-pass turns the per-edge gathers of z,

@@ -39,14 +39,15 @@ SIGNATURES = {
     "relgat_gemm_tile_n": (_I, [_I]),
     "relgat_gemm_dx_prep": (_I, [_P, _P, _L, _P, _P, _L, _P, _I, _I, _I, _P, _P, _P, _I, _F, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
     "relgat_layer_fwd": (_I, [_P, _I, _L, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P,
-                              _P, _I, _F, _P, _F, _I, _I, _I, _I, _P, _P]),
+                              _P, _I, _F, _P, _F, _P, _I, _I, _I, _I, _P, _P]),
     "relgat_layer_bwd_prep": (_I, [_P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P, _I, _F, _P, _I, _P]),
     "relgat_layer_bwd_src": (_I, [_P, _L, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P,
-                                  _P, _F, _P, _P, _I, _L, _I, _I, _I, _I, _P, _P]),
+                                  _P, _F, _P, _P, _I, _I, _L, _I, _I, _I, _I, _P, _P]),
     "relgat_bitmap_ranks_workspace_bytes": (_L, [_L]),
     "relgat_bitmap_ranks": (_I, [_P, _L, _P, _P, _P, _P, _L, _P]),
     "relgat_stream_chunks_workspace_bytes": (_L, [_I]),
     "relgat_stream_chunks_build": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _I, _P, _P, _L, _P]),
+    "relgat_stream_chunks_for_rows": (_I, [_P, _P, _I, _P, _I, _I, _P, _I, _P, _I, _P, _P, _I, _P, _P, _L, _P]),
     "relgat_mark_rows": (_I, [_P, _L, _L, _P, _P]),
     "relgat_mark_sources": (_I, [_P, _P, _P, _I, _P, _P]),
     "relgat_layer_bwd_src2": (_I, [_P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _L,
@@ -75,7 +76,7 @@ SIGNATURES = {
     "relgat_pull_rows_bf16": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _I, _P]),
 }
 
-ABI_VERSION = 11  # bumped whenever a signature in include/relgat_b200.h changes
+ABI_VERSION = 12  # bumped whenever a signature in include/relgat_b200.h changes
 _lib = None
 
 

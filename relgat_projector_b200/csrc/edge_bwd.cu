@@ -264,20 +264,20 @@ int run_src(const void* P, long long ldp, const void* G, const float* A, const f
             const float* t, const int* colptr, const int* csc_slot, const int* csc_dst, const int* csc_rel,
             const int4* ch, int n_chunks, const int2* pt, const int* long_node, const int* long_part_ptr,
             int n_long, float* part_acc, float* dP, void* dP_hi, void* dP_lo, float* dz,
-            const uint32_t* edge_bits, float edge_scale, const uint32_t* nz_bits, const int* src_row, int ds_on,
-            long long ldo, int H, int F, int R, int sm_count, int* work_counter, cudaStream_t s);
+            const uint32_t* edge_bits, float edge_scale, const uint32_t* nz_bits, const int* src_row, int p_compact,
+            int ds_on, long long ldo, int H, int F, int R, int sm_count, int* work_counter, cudaStream_t s);
 extern template int run_src<float, 4>(const void*, long long, const void*, const float*, const float*, const float*,
                                       const float*, const int*, const int*, const int*, const int*, const int4*, int,
                                       const int2*, const int*, const int*, int, float*, float*, void*, void*, float*,
-                                      const uint32_t*, float, const uint32_t*, const int*, int, long long, int, int, int, int, int*, cudaStream_t);
+                                      const uint32_t*, float, const uint32_t*, const int*, int, int, long long, int, int, int, int, int*, cudaStream_t);
 extern template int run_src<float, 1>(const void*, long long, const void*, const float*, const float*, const float*,
                                       const float*, const int*, const int*, const int*, const int*, const int4*, int,
                                       const int2*, const int*, const int*, int, float*, float*, void*, void*, float*,
-                                      const uint32_t*, float, const uint32_t*, const int*, int, long long, int, int, int, int, int*, cudaStream_t);
+                                      const uint32_t*, float, const uint32_t*, const int*, int, int, long long, int, int, int, int, int*, cudaStream_t);
 extern template int run_src<__nv_bfloat16, 8>(const void*, long long, const void*, const float*, const float*,
                                               const float*, const float*, const int*, const int*, const int*, const int*,
                                               const int4*, int, const int2*, const int*, const int*, int, float*, float*,
-                                              void*, void*, float*, const uint32_t*, float, const uint32_t*, const int*, int, long long, int, int, int,
+                                              void*, void*, float*, const uint32_t*, float, const uint32_t*, const int*, int, int, long long, int, int, int,
                                               int, int*, cudaStream_t);
 }  // namespace relgat
 
@@ -334,7 +334,8 @@ extern "C" int relgat_layer_bwd_src(const void* P, long long ldp, const void* G,
                                     const int* long_node, const int* long_part_ptr, int n_long, float* part_acc,
                                     float* dP, void* dP_hi, void* dP_lo, float* dz,
                                     const unsigned int* edge_bits, float edge_scale, const unsigned int* dst_nz_bits,
-                                    const int* src_row, int want_ds, long long ldo, int H, int F, int R, int sm_count, int* work_counter,
+                                    const int* src_row, int p_compact, int want_ds, long long ldo, int H, int F, int R, int sm_count,
+                                    int* work_counter,
                                     void* stream) {
   if (!P || !G || !A || !colptr || n_chunks < 0 || n_parts < 0 || n_long < 0 || H <= 0 || F <= 0 || R <= 0)
     return RG_ERR_ARG;
@@ -353,14 +354,14 @@ extern "C" int relgat_layer_bwd_src(const void* P, long long ldp, const void* G,
     if (!ok16) return RG_ERR_ALIGN;
     return run_src<__nv_bfloat16, 8>(P, ldp, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, ch, n_chunks, pt,
                                      long_node, long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, edge_bits, edge_scale,
-                                     dst_nz_bits, src_row, want_ds, ldo, H, F, R, sm_count, work_counter, s);
+                                     dst_nz_bits, src_row, p_compact, want_ds, ldo, H, F, R, sm_count, work_counter, s);
   }
   if (F % 4 == 0 && ldp % 4 == 0 && ldo % 4 == 0 && ok16)
     return run_src<float, 4>(P, ldp, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, ch, n_chunks, pt, long_node,
-                             long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, edge_bits, edge_scale, dst_nz_bits, src_row, want_ds, ldo, H, F, R,
+                             long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, edge_bits, edge_scale, dst_nz_bits, src_row, p_compact, want_ds, ldo, H, F, R,
                              sm_count, work_counter, s);
   return run_src<float, 1>(P, ldp, G, A, z, minv, t, colptr, csc_slot, csc_dst, csc_rel, ch, n_chunks, pt, long_node,
-                           long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, edge_bits, edge_scale, dst_nz_bits, src_row, want_ds, ldo, H, F, R,
+                           long_part_ptr, n_long, part_acc, dP, dP_hi, dP_lo, dz, edge_bits, edge_scale, dst_nz_bits, src_row, p_compact, want_ds, ldo, H, F, R,
                              sm_count, work_counter, s);
 }
 

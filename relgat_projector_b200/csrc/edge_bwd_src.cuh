@@ -60,6 +60,7 @@ struct SrcArgs {
   // compacted output (ds_on only): src_row[i] = row of dP / dP_hi / dP_lo that receives source i, or -1 = source i has
   // no edge into a non-zero row: it is skipped altogether (no read of its P row, no output row).  nullptr = row i.
   const int* src_row;
+  int p_compact;  // with src_row: P holds the rows of the kept sources only, source i at row src_row[i]
 };
 
 // DS: logit-table gradient columns on (a.ds_on), compile-time so that the plain variants carry none of its code.
@@ -129,6 +130,7 @@ __global__ void __launch_bounds__((PIPE ? kSrcWarpsPipe : kSrcWarps) * 32, 1) bw
     }
 #define RG_SR(k_) ((k_) < 32 ? __shfl_sync(0xffffffffu, sr0, (k_) & 31) : __shfl_sync(0xffffffffu, sr1, (k_) & 31))
 #define RG_OROW(k_) ((DS && a.src_row) ? RG_SR(k_) : n_lo + (k_))
+#define RG_PROW(k_) ((DS && a.src_row && a.p_compact) ? RG_SR(k_) : n_lo + (k_))
 #define RG_CP(k_) ((k_) < 32 ? __shfl_sync(0xffffffffu, cp0, (k_) & 31)       \
                              : ((k_) < 64 ? __shfl_sync(0xffffffffu, cp1, (k_) & 31) \
                                           : __shfl_sync(0xffffffffu, cp2, (k_) & 31)))
@@ -180,8 +182,9 @@ __global__ void __launch_bounds__((PIPE ? kSrcWarpsPipe : kSrcWarps) * 32, 1) bw
         ty_ = (f_end == fe) ? IT_ZERO : IT_OWN;                                                \
         if (a.pf_dist > 0 && fk + 2 < nn) { /* own rows: keep two ahead in L2 */                \
           const bool wanted = !(DS && a.src_row) || RG_SR(fk + 2) >= 0;                        \
+          const int prow = RG_PROW(fk + 2); /* shuffles: every lane takes part */               \
           if (pf_lane_ok && wanted)                                                            \
-            prefetch_l2(p_pf + static_cast<unsigned long long>(n_lo + fk + 2) * p_stride_b);   \
+            prefetch_l2(p_pf + static_cast<unsigned long long>(prow) * p_stride_b);            \
         }                                                                                      \
         break;                                                                                 \
       }                                                                                        \
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__((PIPE ? kSrcWarpsPipe : kSrcWarps) * 32, 1) bw
   _Pragma("unroll") for (int v = 0; v < V; ++v) x_[KV - 1][v] = 0.f;                           \
   if (ty_ == IT_OWN || ty_ == IT_EDGE) {                                                       \
     const T* rowp = reinterpret_cast<const T*>((ty_ == IT_OWN)                                 \
-        ? p_lane + static_cast<unsigned long long>(n_lo + (nd_)) * p_stride_b                  \
+        ? p_lane + static_cast<unsigned long long>(RG_PROW(nd_)) * p_stride_b                  \
         : g_lane + static_cast<unsigned long long>(ds_) * g_stride_b);                         \
     _Pragma("unroll") for (int k = 0; k < KV; ++k)                                             \
       if (RG_VALID(k)) RowVec<T, V>::load_stream(rowp + k * kstride, x_[k]);                   \
@@ -395,6 +398,7 @@ __global__ void __launch_bounds__((PIPE ? kSrcWarpsPipe : kSrcWarps) * 32, 1) bw
 #undef RG_ISSUE
 #undef RG_NEXT
 #undef RG_CP
+#undef RG_PROW
 #undef RG_OROW
 #undef RG_SR
   }
@@ -528,8 +532,8 @@ int run_src(const void* P, long long ldp, const void* G, const float* A, const f
                    const float* t, const int* colptr, const int* csc_slot, const int* csc_dst, const int* csc_rel,
                    const int4* ch, int n_chunks, const int2* pt, const int* long_node, const int* long_part_ptr,
                    int n_long, float* part_acc, float* dP, void* dP_hi, void* dP_lo, float* dz,
-                   const uint32_t* edge_bits, float edge_scale, const uint32_t* nz_bits, const int* src_row, int ds_on,
-                   long long ldo, int H, int F, int R, int sm_count, int* work_counter, cudaStream_t s) {
+                   const uint32_t* edge_bits, float edge_scale, const uint32_t* nz_bits, const int* src_row, int p_compact,
+                   int ds_on, long long ldo, int H, int F, int R, int sm_count, int* work_counter, cudaStream_t s) {
   const int hg = pick_heads_per_warp(H, F, V, R, smem_budget_override("RELGAT_SRC_BUDGET_KB", kSmemBudgetA));
   if (!hg) return RG_ERR_SHAPE;
   if (H / hg > 32) return RG_ERR_SHAPE;  // work_counter holds 32 ints (one per head-group)
@@ -541,7 +545,7 @@ int run_src(const void* P, long long ldp, const void* G, const float* A, const f
                   csc_rel, ch, pt, part_acc, dP, static_cast<__nv_bfloat16*>(dP_hi),
                   static_cast<__nv_bfloat16*>(dP_lo), dz, n_chunks, H, F, R, hg, ldp, 0, 0, work_counter,
                   edge_bits, edge_scale, ds_on, ldo, ds_on ? nz_bits : nullptr,
-                  ds_on ? src_row : nullptr};
+                  ds_on ? src_row : nullptr, p_compact};
   int rc = launch_src(a, sm_count, s);
   if (rc != RG_OK || n_long == 0) return rc;
   bwd_src_merge_kernel<T, V><<<n_long, 128, 0, s>>>(a, long_node, long_part_ptr, n_long);

@@ -64,6 +64,9 @@ struct FwdArgs {
   float drop_scale;           // 1 / (1 - p)
   const uint32_t* edge_bits;  // bit index = csr slot * H + head
   float edge_scale;
+  // compacted sources (receptive-field step): P holds only the rows the listed destinations read, row src_row[i] for
+  // source i (relgat_bitmap_ranks); nullptr = row i
+  const int* src_row;
 };
 
 // ELU(x) = x (x > 0) else exp(x) - 1.  __expf keeps the absolute error at ~1e-7 (the inputs are
@@ -178,6 +181,7 @@ edge_fwd_kernel(const FwdArgs<T, V> a) {
         const int idx = base + lane;
         if (idx < e_hi) {
           my_src = __ldg(a.csr_src + idx);
+          if (a.src_row) my_src = __ldg(a.src_row + my_src);
           my_rel = __ldg(a.csr_rel + idx);
           my_beta = a.beta ? __ldg(a.beta + my_rel) : 0.f;
         }
@@ -534,8 +538,8 @@ static int run_fwd(const void* P, long long ldp, const float* A, const float* be
                    const int* long_node, const int* long_part_ptr, int n_long, float* part_ml, float* part_b,
                    float* part_acc, float* out, void* act_hi, void* act_lo, int apply_elu, float* alpha, float* z,
                    float* minv, float* bias_out, const uint32_t* drop_bits, int drop_words, float drop_scale,
-                   const uint32_t* edge_bits, float edge_scale, int H, int F, int R, int sm_count, int* work_counter,
-                   cudaStream_t s) {
+                   const uint32_t* edge_bits, float edge_scale, const int* src_row, int H, int F, int R, int sm_count,
+                   int* work_counter, cudaStream_t s) {
   const int hg = pick_heads_per_warp(H, F, V, R, smem_budget_override("RELGAT_FWD_BUDGET_KB", kSmemBudgetA));
   if (!hg) return RG_ERR_SHAPE;
   if (H / hg > 32) return RG_ERR_SHAPE;  // work_counter holds 32 ints (one per head-group)
@@ -546,7 +550,7 @@ static int run_fwd(const void* P, long long ldp, const float* A, const float* be
   FwdArgs<T, V> a{static_cast<const T*>(P), A, beta, rowptr, csr_src, csr_rel, ch, pt, part_ml, part_b,
                   part_acc, out, static_cast<__nv_bfloat16*>(act_hi), static_cast<__nv_bfloat16*>(act_lo),
                   alpha, z, minv, bias_out, n_chunks, H, F, R, hg, ldp, apply_elu, 0, 0, work_counter,
-                  drop_bits, drop_words, drop_scale, edge_bits, edge_scale};
+                  drop_bits, drop_words, drop_scale, edge_bits, edge_scale, src_row};
   int rc = launch_fwd(a, sm_count, s);
   if (rc != RG_OK || n_long == 0) return rc;
   const int tasks = n_long * (H / hg);
@@ -563,7 +567,7 @@ extern "C" int relgat_layer_fwd(
     float* out, void* act_hi, void* act_lo, int apply_elu,
     float* alpha, float* z, float* minv, float* bias_out,
     const unsigned int* drop_bits, int drop_words, float drop_scale, const unsigned int* edge_bits, float edge_scale,
-    int H, int F, int R, int sm_count, int* work_counter, void* stream) {
+    const int* src_row, int H, int F, int R, int sm_count, int* work_counter, void* stream) {
   if (!P || !A || !rowptr || n_chunks < 0 || n_parts < 0 || n_long < 0 || H <= 0 || F <= 0 || R <= 0) return RG_ERR_ARG;
   if (drop_bits && drop_words * 32 < H * F) return RG_ERR_ARG;
   if (n_chunks > 0 && !chunks) return RG_ERR_ARG;
@@ -579,16 +583,16 @@ extern "C" int relgat_layer_fwd(
     if (!vec_ok) return RG_ERR_ALIGN;
     return run_fwd<__nv_bfloat16, 8>(P, ldp, A, beta, rowptr, csr_src, csr_rel, ch, n_chunks, pt, long_node,
                                      long_part_ptr, n_long, part_ml, part_b, part_acc, out, act_hi, act_lo, apply_elu,
-                                     alpha, z, minv, bias_out, drop_bits, drop_words, drop_scale, edge_bits, edge_scale, H, F, R, sm_count,
+                                     alpha, z, minv, bias_out, drop_bits, drop_words, drop_scale, edge_bits, edge_scale, src_row, H, F, R, sm_count,
                                      work_counter, s);
   }
   if ((F % 4 == 0) && (ldp % 4 == 0) && vec_ok)
     return run_fwd<float, 4>(P, ldp, A, beta, rowptr, csr_src, csr_rel, ch, n_chunks, pt, long_node, long_part_ptr,
                              n_long, part_ml, part_b, part_acc, out, act_hi, act_lo, apply_elu, alpha, z, minv,
-                             bias_out, drop_bits, drop_words, drop_scale, edge_bits, edge_scale, H, F, R, sm_count,
+                             bias_out, drop_bits, drop_words, drop_scale, edge_bits, edge_scale, src_row, H, F, R, sm_count,
                              work_counter, s);
   return run_fwd<float, 1>(P, ldp, A, beta, rowptr, csr_src, csr_rel, ch, n_chunks, pt, long_node, long_part_ptr,
                            n_long, part_ml, part_b, part_acc, out, act_hi, act_lo, apply_elu, alpha, z, minv,
-                           bias_out, drop_bits, drop_words, drop_scale, edge_bits, edge_scale, H, F, R, sm_count,
+                           bias_out, drop_bits, drop_words, drop_scale, edge_bits, edge_scale, src_row, H, F, R, sm_count,
                            work_counter, s);
 }

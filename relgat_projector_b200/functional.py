@@ -130,11 +130,13 @@ def weight_grad_gemm(dPp, xp, Wd: int, d_in: int, rows: int, device) -> torch.Te
     return ops.gemm(dPp, True, xp, True, Wd, d_in, rows, splits_k=ops.pick_splits_k(Wd, d_in, rows, device))
 
 
-def _plan_compact_backward(gather, g: GraphIndex, L: int):
+def _plan_compact_backward(gather, g: GraphIndex, L: int, forward: bool = False):
     """Row sets of the compacted backward, one entry per layer (first layer first): ``dst_bits`` = rows of dL/d out_l
     that can be non-zero, ``rank`` / ``list`` = compact numbering of the sources of the edges into them (= the rows of
     dP_l, and the non-zero rows one layer down), ``counts`` = their sizes in pinned host memory once ``ready`` fired.
-    Everything runs on the side stream behind the id sort: it is off the forward's critical chain."""
+    ``forward``: also ``fwd_chunks`` = the forward kernel's work table over exactly the destinations layer l must produce
+    (the receptive-field forward).  Everything runs on the side stream behind the id sort: off the critical chain."""
+    from .graph import StreamChunks
     keys, _, sorted_ev = gather
     dev = keys.device
     main = torch.cuda.current_stream(dev)
@@ -142,21 +144,53 @@ def _plan_compact_backward(gather, g: GraphIndex, L: int):
     side.wait_event(sorted_ev)
     with torch.cuda.stream(side):
         bits = ops.mark_rows(keys, g.N)
+        dst_list = dst_count = None
+        if forward:
+            _, dst_list, dst_count = ops.bitmap_ranks(bits, g.N)
         layers = []
         for _ in range(L):
             sbits = ops.mark_sources(bits, g)
             rank, lst, cnt = ops.bitmap_ranks(sbits, g.N_src)
-            layers.append(dict(dst_bits=bits, rank=rank, list=lst, count=cnt))
+            p = dict(dst_bits=bits, rank=rank, list=lst, count=cnt)
+            if forward:
+                p["fwd_chunks"] = StreamChunks.launch_for_rows(g.rowptr, g.E, dst_list, dst_count)
+                dst_list, dst_count = lst, cnt
+            layers.append(p)
             bits = sbits
         layers.reverse()
-        counts = torch.empty((L,), dtype=torch.int32, pin_memory=True)
-        counts.copy_(torch.cat([p["count"] for p in layers]), non_blocking=True)
+        dev_counts = [p["count"] for p in layers] + ([p["fwd_chunks"].counts for p in layers] if forward else [])
+        counts = torch.empty((L * (5 if forward else 1),), dtype=torch.int32, pin_memory=True)
+        counts.copy_(torch.cat(dev_counts), non_blocking=True)
         ready = torch.cuda.Event()
         ready.record(side)
     for p in layers:
         for k in ("dst_bits", "rank", "list"):
             p[k].record_stream(main)
-    return dict(layers=layers, counts=counts, ready=ready)
+        if forward:
+            for t in vars(p["fwd_chunks"]).values():
+                if isinstance(t, torch.Tensor):
+                    t.record_stream(main)
+    return dict(layers=layers, counts=counts, ready=ready, n_layers=L)
+
+
+LAST_PRUNED_EDGES = None  # layer-edges processed by the latest receptive-field forward (diagnostic, bench.py)
+
+
+def _plan_counts(plan) -> List[int]:
+    """Host copy of the plan's sizes (waits for the side stream's few small kernels, not for the main stream) and,
+    for a forward plan, the work tables cut to their true sizes."""
+    if "sizes" not in plan:
+        plan["ready"].synchronize()
+        host = [int(v) for v in plan["counts"].tolist()]
+        L = plan["n_layers"]
+        plan["sizes"] = host[:L]
+        for l, p in enumerate(plan["layers"]):
+            if "fwd_chunks" in p:
+                p["fwd_chunks"].finish(host[L + 4 * l:L + 4 * l + 4])
+        if plan["layers"] and "fwd_chunks" in plan["layers"][0]:
+            global LAST_PRUNED_EDGES
+            LAST_PRUNED_EDGES = sum(p["fwd_chunks"].n_edges for p in plan["layers"])
+    return plan["sizes"]
 
 
 class LayerDropout:
@@ -183,7 +217,7 @@ class RelGATStackFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x0, graph: GraphIndex, heads: int, out_dim: int, precision: str, x0_planes, drop, gather_ids,
-                *params):
+                prune, *params):
         if precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {PRECISIONS}")
         if len(params) % 3 != 0 or not params:
@@ -203,6 +237,17 @@ class RelGATStackFunction(torch.autograd.Function):
         planes = x0_planes if x0_planes is not None else ops.split_bf16(x0, with_lo)
         saved = []
         out = None
+        ctx.gather = ctx.plan = None
+        # receptive-field forward: only the rows the batch's rows depend on are produced (see _plan_compact_backward)
+        prune = bool(prune) and gather_ids is not None and USE_DS and with_lo and not blocks and \
+            not (x0 is not None and x0.requires_grad)
+        sizes = None
+        if prune:
+            ctx.gather = presort_on_side_stream(gather_ids.contiguous(), graphs[-1].N)
+            ctx.plan = _plan_compact_backward(ctx.gather, graphs[-1], L, forward=True)
+            sizes = _plan_counts(ctx.plan)
+            torch.cuda.current_stream(planes[0].device).wait_event(ctx.plan["ready"])
+        ctx.pruned = prune
         for l in range(L):
             W, A, beta = params[3 * l], params[3 * l + 1], params[3 * l + 2]
             d_in = W.size(1)
@@ -214,13 +259,23 @@ class RelGATStackFunction(torch.autograd.Function):
             # K-major copy of Wᵀ for dX = dP·W (3 MB transpose; the K-major B path is ~12% faster than MN-major)
             WTp = ops.split_bf16(W.detach().t().contiguous(), with_lo) if (l > 0 or x0_grad) else None
             # "bf16": projected features are stored in bf16 (halves every gather of the edge kernels)
-            P = ops.gemm(planes, False, Wp, False, gl.N_src, C, d_in,
-                         out_dtype=torch.float32 if with_lo else torch.bfloat16)
             last = l == L - 1
             dl = drop[l] if drop is not None else None
+            pl = ctx.plan["layers"][l] if prune else None
+            if prune:
+                # the input rows this layer's destinations read -> compact planes -> compact P (row rank[src])
+                n_s = sizes[l]
+                if n_s > 0:
+                    planes = tuple(None if p_ is None else ops.gather_plane_rows(p_, pl["list"][:n_s]) for p_ in planes)
+                else:  # no edge reaches the batch's rows at this layer: one unread zero row keeps the shapes valid
+                    planes = tuple(None if p_ is None else p_.new_zeros((1, d_in)) for p_ in planes)
+            P = ops.gemm(planes, False, Wp, False, planes[0].size(0) if prune else gl.N_src, C, d_in,
+                         out_dtype=torch.float32 if with_lo else torch.bfloat16)
             out, act, _, z, minv, bias = ops.edge_fwd(P, A.detach(), None if beta is None else beta.detach(), gl,
                                                       H, F, want_act=not last, apply_elu=True, act_lo=with_lo,
-                                                      feat_drop=dl.feat if dl else None, edge_drop=dl.edge if dl else None)
+                                                      feat_drop=dl.feat if dl else None, edge_drop=dl.edge if dl else None,
+                                                      chunks=pl["fwd_chunks"] if prune else None,
+                                                      src_row=pl["rank"] if prune else None)
             saved.append(dict(xp=planes, Wp=Wp, WTp=WTp, P=P, out=out, minv=minv, z=z, bias=bias, A=A.detach(),
                               d_in=d_in, has_beta=beta is not None, drop=dl))
             planes = act
@@ -229,13 +284,12 @@ class RelGATStackFunction(torch.autograd.Function):
         ctx.blocks = blocks
         ctx.cfg = (H, F, L, with_lo)
         ctx.x0_needs_grad = bool(x0 is not None and x0.requires_grad)
-        ctx.gather = None
-        ctx.plan = None
         if gather_ids is not None:
             ids = gather_ids.contiguous()
-            ctx.gather = presort_on_side_stream(ids, graphs[-1].N)  # (sorted keys, perm, event): summation order of backward
-            ctx.plan = None
-            if SPARSE_BWD and COMPACT_BWD and USE_DS and with_lo and not blocks and not ctx.x0_needs_grad:
+            if ctx.gather is None:
+                ctx.gather = presort_on_side_stream(ids, graphs[-1].N)  # (sorted keys, perm, event): summation order of backward
+            if ctx.plan is None and SPARSE_BWD and COMPACT_BWD and USE_DS and with_lo and not blocks and \
+                    not ctx.x0_needs_grad:
                 ctx.plan = _plan_compact_backward(ctx.gather, graphs[-1], L)
             rows = out.new_empty((ids.numel(), C))
             ops.pull_rows(out, ids, rows)
@@ -267,10 +321,10 @@ class RelGATStackFunction(torch.autograd.Function):
             dY = grad_out.contiguous()
             nz_rows = sparse_rows_of(grad_out) if dY is grad_out else None
             owned = False
-        if ctx.plan is not None and table is not None and SPARSE_BWD and COMPACT_BWD:
+        if ctx.plan is not None and table is not None and (ctx.pruned or (SPARSE_BWD and COMPACT_BWD)):
             grads = _backward_compact(ctx, table, keys)
             ctx.saved = None
-            return (None, None, None, None, None, None, None, None, *grads)
+            return (None, None, None, None, None, None, None, None, None, *grads)
         # (blocks hold nothing but the rows the batch reaches: there is nothing to skip)
         nz_bits = ops.mark_rows(nz_rows, N) if (SPARSE_BWD and USE_DS and nz_rows is not None and not blocks) else None
         dX = None
@@ -361,7 +415,7 @@ class RelGATStackFunction(torch.autograd.Function):
                     tns.record_stream(main)
             del G, dPp, dz
         ctx.saved = None
-        return (dX if ctx.x0_needs_grad else None, None, None, None, None, None, None, None, *grads)
+        return (dX if ctx.x0_needs_grad else None, None, None, None, None, None, None, None, None, *grads)
 
 
 def _backward_compact(ctx, table: torch.Tensor, keys: torch.Tensor) -> List[Optional[torch.Tensor]]:
@@ -373,9 +427,9 @@ def _backward_compact(ctx, table: torch.Tensor, keys: torch.Tensor) -> List[Opti
     C, N, HR = H * F, g.N, H * g.R
     dev = table.device
     plan = ctx.plan
-    plan["ready"].synchronize()  # sizes of the row sets (computed during the forward: long done)
-    counts = [int(v) for v in plan["counts"].tolist()]
+    counts = _plan_counts(plan)  # sizes of the row sets (computed during the forward: long done)
     torch.cuda.current_stream(dev).wait_event(plan["ready"])
+    pruned = ctx.pruned  # receptive-field forward: P and the input planes are already compact
     grads: List[Optional[torch.Tensor]] = [None] * (3 * L)
     dX_c, G_table, prev_rows = None, None, None
     for l in reversed(range(L)):
@@ -394,7 +448,8 @@ def _backward_compact(ctx, table: torch.Tensor, keys: torch.Tensor) -> List[Opti
         if n_s > 0:
             _, dPp, _ = ops.edge_bwd_src(s["P"], G, s["A"], s["z"], s["minv"], t, g, H, F, want_fp32=False,
                                          want_planes=True, planes_lo=True, edge_drop=dl.edge if dl else None,
-                                         want_ds=True, dst_nz=pl["dst_bits"], src_rows=(pl["rank"], n_s))
+                                         want_ds=True, dst_nz=pl["dst_bits"], src_rows=(pl["rank"], n_s),
+                                         p_compact=pruned)
         ops.zero_rows(G, clear_rows)  # the table's rows are consumed: all-zero again for the next step
         _return_zero_table(G)
         if n_s == 0:  # no edge reaches a non-zero row: this layer's and every lower layer's gradients are zero
@@ -405,7 +460,7 @@ def _backward_compact(ctx, table: torch.Tensor, keys: torch.Tensor) -> List[Opti
                 grads[3 * k + 2] = torch.zeros((g.R,), dtype=torch.float32, device=dev) if sk["has_beta"] else None
             break
         rows = pl["list"][:n_s]
-        xp_c = tuple(None if p_ is None else ops.gather_plane_rows(p_, rows) for p_ in s["xp"])
+        xp_c = s["xp"] if pruned else tuple(None if p_ is None else ops.gather_plane_rows(p_, rows) for p_ in s["xp"])
         d_in = s["d_in"]
         dW_ext = weight_grad_gemm(dPp, xp_c, dPp[0].size(1), d_in, n_s, dev)
         if l > 0:
@@ -420,11 +475,13 @@ def _backward_compact(ctx, table: torch.Tensor, keys: torch.Tensor) -> List[Opti
 
 
 def relgat_stack(x0, graph, heads, out_dim, layer_params: Sequence, precision="fp32", x0_planes=None, drop=None,
-                 gather_ids=None):
+                 gather_ids=None, prune=False):
+    """``prune`` (with ``gather_ids``, fp32 mode): receptive-field step on the full graph's index — per layer only the
+    rows the requested rows depend on are produced, and the backward covers the same rows."""
     flat = []
     for W, A, beta in layer_params:
         flat += [W, A, beta]
-    return RelGATStackFunction.apply(x0, graph, heads, out_dim, precision, x0_planes, drop, gather_ids, *flat)
+    return RelGATStackFunction.apply(x0, graph, heads, out_dim, precision, x0_planes, drop, gather_ids, prune, *flat)
 
 
 class GatherRowsFunction(torch.autograd.Function):

@@ -107,7 +107,7 @@ class StreamChunks:
         self.parts = torch.empty((max_parts, 2), **i32)
         self.long_node = torch.empty((max_long,), **i32)
         self.long_part_ptr = torch.empty((max_long + 1,), **i32)
-        self.counts = torch.empty((3,), **i32)
+        self.counts = torch.empty((4,), **i32)
         lib = _lib.load()
         ws_bytes = int(lib.relgat_stream_chunks_workspace_bytes(max(n, 0)))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -121,8 +121,39 @@ class StreamChunks:
         self.n_chunks = self.n_parts = self.n_long = None
         return self
 
+    @classmethod
+    def launch_for_rows(cls, ptr: torch.Tensor, n_edges: int, rows: torch.Tensor, n_rows_dev: torch.Tensor,
+                        long_segment: int = LONG_SEGMENT, part_edges: int = PART_EDGES) -> "StreamChunks":
+        """Table over the listed segments only (``rows`` int64, ascending; its true length is the device int
+        ``n_rows_dev``, ``rows.numel()`` an upper bound): one chunk per listed segment.  ``finish`` as for ``launch``."""
+        self = cls.__new__(cls)
+        dev = ptr.device
+        n = int(rows.numel())
+        i32 = dict(dtype=torch.int32, device=dev)
+        max_long = n_edges // (long_segment + 1) + 1
+        max_parts = n_edges // part_edges + max_long
+        max_chunks = n + max_parts
+        self.chunks = torch.empty((max_chunks, 4), **i32)
+        self.parts = torch.empty((max_parts, 2), **i32)
+        self.long_node = torch.empty((max_long,), **i32)
+        self.long_part_ptr = torch.empty((max_long + 1,), **i32)
+        self.counts = torch.empty((4,), **i32)
+        lib = _lib.load()
+        ws_bytes = int(lib.relgat_stream_chunks_workspace_bytes(n))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.relgat_stream_chunks_for_rows(
+                _lib.ptr(ptr), _lib.ptr(rows), n, _lib.ptr(n_rows_dev), long_segment, part_edges,
+                _lib.ptr(self.chunks), max_chunks, _lib.ptr(self.parts), max_parts, _lib.ptr(self.long_node),
+                _lib.ptr(self.long_part_ptr), max_long, _lib.ptr(self.counts), _lib.ptr(ws), ws_bytes,
+                torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "relgat_stream_chunks_for_rows")
+        self.n_chunks = self.n_parts = self.n_long = None
+        return self
+
     def finish(self, counts) -> "StreamChunks":
-        n_chunks, n_parts, n_long = (int(v) for v in counts)
+        n_chunks, n_parts, n_long = (int(v) for v in counts[:3])
+        self.n_edges = int(counts[3]) if len(counts) > 3 else None
         if n_chunks < 0:
             raise RuntimeError("relgat_stream_chunks_build: table bounds exceeded")
         self.n_chunks, self.n_parts, self.n_long = n_chunks, n_parts, n_long
@@ -191,8 +222,8 @@ class GraphIndex:
             pend = [ck for ck in (self.fwd_chunks, self.src_chunks) if ck is not None]
             host = torch.cat([ck.counts for ck in pend] + [self.relptr]).cpu().numpy()  # the one host read
             for k, ck in enumerate(pend):
-                ck.finish(host[3 * k:3 * k + 3])
-            self._build_rel_chunks(host[3 * len(pend):])
+                ck.finish(host[4 * k:4 * k + 4])
+            self._build_rel_chunks(host[4 * len(pend):])
             del ws
             return
         self._build_rel_chunks()

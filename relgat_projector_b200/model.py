@@ -51,6 +51,9 @@ class RelGATModel(nn.Module):
         # batch's receptive-field blocks instead of the whole graph — same rows, same gradients, less work (blocks.py);
         # single_gat_step / evaluation always run the full graph
         self.receptive_field = os.environ.get("RELGAT_RECEPTIVE_FIELD", "0") != "0"
+        # how: "masked" (default; fp32 mode) = the full graph's index with per-step work tables over the needed
+        # destinations and compact source rows; "blocks" = per-step bipartite sub-indexes (blocks.py; any precision)
+        self.receptive_field_mode = os.environ.get("RELGAT_RF_MODE", "masked")
         self.last_block_edges = None
         if project_to_input_size and self.projection_layers < 1:
             raise ValueError("projection_layers must be >= 1 when project_to_input_size=True")
@@ -119,7 +122,8 @@ class RelGATModel(nn.Module):
         layers = self._layers()
         graph = self._graph()
         dev = self.node_emb_fixed.device
-        if gather_ids is not None and self.receptive_field:
+        masked = self.receptive_field and self.receptive_field_mode == "masked" and self.precision == "fp32"
+        if gather_ids is not None and self.receptive_field and not masked:
             # one bipartite block per layer, holding the batch's L-hop in-neighbourhood only
             blk = build_blocks(graph, gather_ids, len(layers))
             self.last_block_edges = blk.n_edges
@@ -131,9 +135,13 @@ class RelGATModel(nn.Module):
                                    x0_planes=planes, drop=drop, gather_ids=blk.out_pos)
         drop = [lyr.draw_dropout(graph.N, graph.E, dev) for lyr in layers]
         drop = [d if d is not None else RF.LayerDropout() for d in drop] if any(d is not None for d in drop) else None
-        return RF.relgat_stack(self.node_emb_fixed, graph, layers[0].heads, layers[0].out_dim,
+        rows = RF.relgat_stack(self.node_emb_fixed, graph, layers[0].heads, layers[0].out_dim,
                                [lyr.kernel_params() for lyr in layers], precision=self.precision,
-                               x0_planes=self._input_planes(), drop=drop, gather_ids=gather_ids)
+                               x0_planes=self._input_planes(), drop=drop, gather_ids=gather_ids,
+                               prune=masked and gather_ids is not None)
+        if masked and gather_ids is not None:
+            self.last_block_edges = RF.LAST_PRUNED_EDGES
+        return rows
 
     # -- reference API ------------------------------------------------------------------------
     def single_gat_step(self) -> torch.Tensor:

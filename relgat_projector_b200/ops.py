@@ -290,19 +290,28 @@ def edge_fwd(P: torch.Tensor, A: torch.Tensor, beta: Optional[torch.Tensor], g: 
              want_act: bool = False, apply_elu: bool = False, act_lo: bool = True, want_out: bool = True,
              want_alpha: bool = False, z_out: Optional[torch.Tensor] = None,
              minv_out: Optional[torch.Tensor] = None, out_buf: Optional[torch.Tensor] = None,
-             feat_drop: Optional["DropMask"] = None, edge_drop: Optional["DropMask"] = None):
+             feat_drop: Optional["DropMask"] = None, edge_drop: Optional["DropMask"] = None,
+             chunks=None, src_row: Optional[torch.Tensor] = None):
     """Returns (out [N, H*F] fp32 or None, act planes or None, alpha [E,H] or None, z [E,H],
     minv [N,H,2], bias [N]).  ``z_out`` / ``minv_out`` / ``out_buf``: caller-owned buffers for the saved
     statistics and the output rows (rows of a peer table on the partitioned path).
     ``feat_drop`` / ``edge_drop``: keep-bit masks of the feature dropout (reference layer.py:321-322; ``out`` then
-    holds the POST-dropout rows) and of the attention dropout (layer.py:296-297)."""
+    holds the POST-dropout rows) and of the attention dropout (layer.py:296-297).
+    ``chunks`` (a StreamChunks over a list of destinations) + ``src_row`` (int32 [N_src] compact numbering of the rows
+    P holds): the receptive-field forward — only the listed destinations are computed, every other row of the outputs
+    is left unwritten."""
     P = _feat(P, "P")
     A = _f32c(A, "A")
     if beta is not None:
         beta = _f32c(beta, "beta")
     dev = P.device
     N, E, R, C = g.N, g.E, g.R, H * F
-    if P.dim() != 2 or P.size(1) != C or P.size(0) != g.N_src:
+    if src_row is not None:
+        if src_row.dtype != torch.int32 or src_row.device != dev or src_row.numel() != g.N_src or not src_row.is_contiguous():
+            raise ValueError("src_row must be a contiguous int32 [N_src] tensor on the feature device")
+        if want_alpha or P.dim() != 2 or P.size(1) != C:
+            raise ValueError(f"compacted sources: P must be [rows, {C}] and alpha cannot be requested")
+    elif P.dim() != 2 or P.size(1) != C or P.size(0) != g.N_src:
         raise ValueError(f"P must be [{g.N_src}, {C}], got {tuple(P.shape)}")
     if tuple(A.shape) != (H, R, F):
         raise ValueError(f"A must be [{H}, {R}, {F}], got {tuple(A.shape)}")
@@ -313,7 +322,7 @@ def edge_fwd(P: torch.Tensor, A: torch.Tensor, beta: Optional[torch.Tensor], g: 
     z = _out_buf(z_out, (E, H), dev, "z_out")
     minv = _out_buf(minv_out, (N, H, 2), dev, "minv_out")
     bias = torch.empty((N,), dtype=torch.float32, device=dev)
-    ck = g.fwd_chunks
+    ck = chunks if chunks is not None else g.fwd_chunks
     part_ml = torch.empty((ck.n_parts, H, 2), dtype=torch.float32, device=dev) if ck.n_parts else None
     part_b = torch.empty((ck.n_parts,), dtype=torch.float32, device=dev) if ck.n_parts else None
     part_acc = torch.empty((ck.n_parts, C), dtype=torch.float32, device=dev) if ck.n_parts else None
@@ -326,8 +335,8 @@ def edge_fwd(P: torch.Tensor, A: torch.Tensor, beta: Optional[torch.Tensor], g: 
             _lib.ptr(part_ml), _lib.ptr(part_b), _lib.ptr(part_acc),
             _lib.ptr(out), _lib.ptr(hi), _lib.ptr(lo), int(apply_elu),
             _lib.ptr(alpha), _lib.ptr(z), _lib.ptr(minv), _lib.ptr(bias),
-            *_feat_mask_args(feat_drop, N, C), *_edge_mask_args(edge_drop, E, H), H, F, R, sm_count(dev),
-            _lib.ptr(_work_counter(dev)), _stream(P))
+            *_feat_mask_args(feat_drop, N, C), *_edge_mask_args(edge_drop, E, H), _lib.ptr(src_row), H, F, R,
+            sm_count(dev), _lib.ptr(_work_counter(dev)), _stream(P))
     _lib.check(rc, "relgat_layer_fwd")
     _count(2 if ck.n_long else 1)
     return out, ((hi, lo) if want_act else None), alpha, z, minv, bias
@@ -409,21 +418,23 @@ def ds_row_width(H: int, F: int, R: int) -> int:
 def edge_bwd_src(P, G, A, z, minv, t, g: GraphIndex, H: int, F: int, want_fp32: bool = True,
                  want_planes: bool = False, planes_lo: bool = True, edge_drop: Optional["DropMask"] = None,
                  want_ds: bool = False, dst_nz: Optional[torch.Tensor] = None,
-                 src_rows: Optional[Tuple[torch.Tensor, int]] = None):
+                 src_rows: Optional[Tuple[torch.Tensor, int]] = None, p_compact: bool = False):
     """Returns (dP fp32 or None, dP planes or None, dz [E,H] or None).  ``want_ds``: the rows are
     ``ds_row_width`` wide, columns H*F + h*R + r hold dS and dz is not written.
     ``dst_nz`` (want_ds only): row bitmap from ``mark_rows`` / ``mark_sources`` — rows of G outside it are exact zeros
     (and so are their t), the edges into them are skipped.  ``src_rows`` = (rank int32 [N_src], n) from
     ``bitmap_ranks`` of the sources of the marked rows: the output has n rows, source i is written to row rank[i] and
-    sources with rank -1 are skipped altogether."""
+    sources with rank -1 are skipped altogether; ``p_compact``: P itself is compact (row rank[i] holds source i)."""
     P = _feat(P, "P")
     G = _feat(G, "G")
     if P.dtype != G.dtype:
         raise TypeError("P and G must share one storage type (both fp32 or both bf16)")
     A = _f32c(A, "A")
     dev = P.device
-    n_src, C = P.size(0), H * F
-    if n_src != g.N_src or G.size(0) != g.N:
+    n_src, C = g.N_src, H * F
+    if p_compact and src_rows is None:
+        raise ValueError("p_compact needs src_rows")
+    if (P.size(0) != (int(src_rows[1]) if p_compact else n_src)) or G.size(0) != g.N:
         raise ValueError("P / G row counts do not match the graph index")
     W = ds_row_width(H, F, g.R) if want_ds else C
     mk = torch.zeros if W > C + H * g.R else torch.empty  # padding columns feed the GEMM: keep them finite
@@ -469,7 +480,7 @@ def edge_bwd_src(P, G, A, z, minv, t, g: GraphIndex, H: int, F: int, want_fp32: 
             _lib.ptr(ck.chunks), ck.n_chunks, _lib.ptr(ck.parts), ck.n_parts,
             _lib.ptr(ck.long_node), _lib.ptr(ck.long_part_ptr), ck.n_long, _lib.ptr(part_acc),
             _lib.ptr(dP), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dz), *_edge_mask_args(edge_drop, g.E, H),
-            _lib.ptr(dst_nz), _lib.ptr(rank), int(want_ds), W, H, F, g.R, sm_count(dev), _lib.ptr(_work_counter(dev)), _stream(P))
+            _lib.ptr(dst_nz), _lib.ptr(rank), int(p_compact), int(want_ds), W, H, F, g.R, sm_count(dev), _lib.ptr(_work_counter(dev)), _stream(P))
     _lib.check(rc, "relgat_layer_bwd_src")
     _count(2 if ck.n_long else 1)
     return dP, ((hi, lo) if want_planes else None), dz

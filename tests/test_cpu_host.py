@@ -22,13 +22,13 @@ def test_library_loads_and_exports_header_symbols():
     assert set(names) == set(_lib.SIGNATURES.keys())
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/relgat_b200.h but not exported"
-    assert lib.relgat_abi_version() == _lib.ABI_VERSION == 11
+    assert lib.relgat_abi_version() == _lib.ABI_VERSION == 12
     # host-side argument validation needs no GPU
     assert lib.relgat_graph_index_workspace_bytes(-1) == -1
     assert lib.relgat_gemm_workspace_bytes(128, 128, 64, 0, 0, 1) == 0
     assert lib.relgat_gemm_workspace_bytes(128, 64, 640, 1, 1, 4) == 4 * 128 * 64 * 4
     assert lib.relgat_layer_fwd(None, 0, 0, None, None, None, None, None, None, 0, None, 0, None, None, 0, None, None,
-                                None, None, None, None, 0, None, None, None, None, None, 0, 1.0, None, 1.0,
+                                None, None, None, None, 0, None, None, None, None, None, 0, 1.0, None, 1.0, None,
                                 1, 4, 1, 148, None, None) == -1
     assert lib.relgat_rank_loss(None, None, 1, 1, 1, 1, 0, 1.0, 1.0, 0, None, None, None, None) == -1
     assert lib.relgat_recon_loss(None, None, None, 1, 0, 4, 0, 0, 1.0, 1.0, 0.0, None, None, None, None, None, None) == -1

@@ -558,15 +558,16 @@ def test_blocks_hold_every_in_edge_of_their_destinations_in_graph_order(dev):
     assert blk.n_edges == sum(g.E for g in blk.graphs)
 
 
+@pytest.mark.parametrize("mode", ["masked", "blocks"])
 @pytest.mark.parametrize("name", MODEL_CASES)
-def test_receptive_field_step_equals_the_full_graph_step(dev, name):
+def test_receptive_field_step_equals_the_full_graph_step(dev, name, mode):
     """forward on the batch's blocks: the same scores (bit for bit — every destination keeps all its in-edges in order)
     and the same parameter gradients (the weight-gradient GEMMs sum over fewer, reordered rows: rounding only)."""
     c = Case(name)
     res = []
     for rf in (False, True):
         m = _load_model(c, dev)
-        m.receptive_field = rf
+        m.receptive_field, m.receptive_field_mode = rf, mode
         src, rel, dst = (c.t(k).to(dev) for k in ("src_ids", "rel_ids", "dst_ids"))
         scores = m(src, rel, dst)[0]
         (scores * torch.linspace(-1, 1, scores.numel(), device=dev)).sum().backward()
@@ -579,10 +580,11 @@ def test_receptive_field_step_equals_the_full_graph_step(dev, name):
         assert rel_err(res[1][1][n_].cpu().numpy(), res[0][1][n_].cpu().numpy()) < 2e-5, n_
 
 
-def test_receptive_field_step_with_dropout_and_losses_runs_and_is_finite(dev):
+@pytest.mark.parametrize("mode", ["masked", "blocks"])
+def test_receptive_field_step_with_dropout_and_losses_runs_and_is_finite(dev, mode):
     c = Case("transe_proj_fp32")
     m = _load_model(c, dev)
-    m.receptive_field = True
+    m.receptive_field, m.receptive_field_mode = True, mode
     for lyr in m._layers():
         lyr.dropout.p, lyr.rel_attn_drop.p = 0.3, 0.1
     torch.manual_seed(0)
@@ -621,7 +623,8 @@ def test_device_built_work_tables_equal_the_host_formulation(dev, shape):
         assert torch.equal(getattr(got, k), getattr(want, k)), k
 
 
-def test_config1_full_size_receptive_field_step_vs_full_graph_step(dev):
+@pytest.mark.parametrize("mode", ["masked", "blocks"])
+def test_config1_full_size_receptive_field_step_vs_full_graph_step(dev, mode):
     """Config 1 (10 k nodes / 45 k edges / 1024-d / 2 layers / 4x200, B = 256, K = 4) through calculate_loss: the step on
     the batch's blocks against the full-graph step (itself checked against the fp64 oracle above)."""
     cfg = S.CONFIGS["c1"]
@@ -634,7 +637,7 @@ def test_config1_full_size_receptive_field_step_vs_full_graph_step(dev):
         torch.manual_seed(11)
         m = R.RelGATModel(kg.node_emb, kg.edge_index, kg.edge_type, num_rel=cfg["R"], scorer_type=cfg["scorer"],
                           gat_out_dim=cfg["F"], gat_heads=cfg["H"], dropout=0.0, gat_num_layers=cfg["L"]).to(dev).train()
-        m.receptive_field = rf
+        m.receptive_field, m.receptive_field_mode = rf, mode
         _, _, loss, *_ = L.calculate_loss(m, src, rel, dst, cfg["B"], rank, None)
         loss.backward()
         res.append((float(loss), {n_: p.grad.clone() for n_, p in m.named_parameters() if p.grad is not None}))
@@ -645,7 +648,8 @@ def test_config1_full_size_receptive_field_step_vs_full_graph_step(dev):
         assert rel_err(res[1][1][n_].cpu().numpy(), res[0][1][n_].cpu().numpy()) < 2e-5, n_
 
 
-def test_receptive_field_edge_cases_isolated_nodes_and_repeated_ids(dev):
+@pytest.mark.parametrize("mode", ["masked", "blocks"])
+def test_receptive_field_edge_cases_isolated_nodes_and_repeated_ids(dev, mode):
     """Batch nodes without in-edges (empty blocks all the way down), a batch naming one node many times, and a one-layer
     model: the block path must agree with the full-graph path."""
     gen = torch.Generator().manual_seed(2)
@@ -661,7 +665,7 @@ def test_receptive_field_edge_cases_isolated_nodes_and_repeated_ids(dev):
             torch.manual_seed(4)
             m = R.RelGATModel(x0.to(dev), ei.to(dev), et.to(dev), num_rel=r, gat_out_dim=8, gat_heads=2, dropout=0.0,
                               gat_num_layers=layers).to(dev).train()
-            m.receptive_field = rf
+            m.receptive_field, m.receptive_field_mode = rf, mode
             rows = m.batch_rows(ids.to(dev))
             (rows * torch.linspace(-1, 1, rows.numel(), device=dev).view_as(rows)).sum().backward()
             res.append((rows.detach().clone(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}))
@@ -724,3 +728,46 @@ def test_compacted_by_source_pass_equals_rows_of_the_full_pass(dev):
     G2, t2, h2 = ops.edge_bwd_prep(dY[rows].contiguous(), out, bias, h, f, apply_elu=True, G_out=Gt, compact_rows=rows)
     G1, t1, h1 = ops.edge_bwd_prep(dY, out, bias, h, f, apply_elu=True)
     assert torch.equal(G2, G1) and torch.equal(t2, t1) and torch.equal(h2, h1)
+
+
+def test_masked_receptive_field_step_uses_the_same_dropout_masks_as_the_full_graph_step(dev):
+    """The masked mode keeps the full graph's row and edge numbering, so a given seed draws the same dropout masks:
+    with dropout active the batch rows still equal the full-graph step's bit for bit."""
+    c = Case("transe_proj_fp32")
+    res = []
+    for rf in (False, True):
+        m = _load_model(c, dev)
+        m.receptive_field, m.receptive_field_mode = rf, "masked"
+        for lyr in m._layers():
+            lyr.dropout.p, lyr.rel_attn_drop.p = 0.3, 0.2
+        torch.manual_seed(21)
+        ids = torch.cat([c.t("src_ids"), c.t("dst_ids")]).to(dev)
+        rows = m._stack_output(gather_ids=ids)
+        rows.square().sum().backward()
+        res.append((rows.detach().clone(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}))
+    assert torch.equal(res[0][0], res[1][0])
+    for k in res[0][1]:
+        assert rel_err(res[1][1][k].cpu().numpy(), res[0][1][k].cpu().numpy()) < 2e-5, k
+
+
+def test_work_table_over_a_list_of_destinations(dev):
+    from relgat_projector_b200.graph import LONG_SEGMENT, PART_EDGES, StreamChunks
+    gen = torch.Generator().manual_seed(13)
+    deg = torch.randint(0, 9, (2000,), generator=gen)
+    deg[[3, 900]] = torch.tensor([LONG_SEGMENT + 1, 3 * PART_EDGES + 5])
+    ptr = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(deg, 0)]).to(torch.int32).to(dev)
+    rows = torch.tensor([0, 3, 4, 17, 900, 1999], dtype=torch.int64)
+    padded = torch.cat([rows, torch.full((50,), 12345678, dtype=torch.int64)]).to(dev)  # entries beyond the count: ignored
+    ck = StreamChunks.launch_for_rows(ptr, int(deg.sum()), padded, torch.tensor([rows.numel()], dtype=torch.int32, device=dev))
+    ck.finish(ck.counts.cpu().numpy())
+    p = ptr.cpu().numpy()
+    parts, chunks = [], []
+    for j in (3, 900):
+        for lo in range(p[j], p[j + 1], PART_EDGES):
+            chunks.append([j, 1, len(parts), 0])
+            parts.append([lo, min(lo + PART_EDGES, p[j + 1])])
+    chunks += [[j, 1, -1, 0] for j in (0, 4, 17, 1999)]
+    assert (ck.n_chunks, ck.n_parts, ck.n_long) == (len(chunks), len(parts), 2)
+    assert ck.chunks.cpu().tolist() == chunks and ck.parts.cpu().tolist() == parts
+    assert ck.long_node.cpu().tolist() == [3, 900] and ck.long_part_ptr.cpu().tolist() == [0, 3, 7]
+    assert ck.n_edges == int(deg[rows].sum())

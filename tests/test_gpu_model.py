@@ -323,7 +323,7 @@ def test_peer_table_partition_lockstep_equals_whole_graph(dev, world, blocks):
     x0 = kg.node_emb.clone().requires_grad_(True)
     grad_out = torch.randn(n, h * f, generator=gen).to(dev)
     g_full = G.GraphIndex(kg.edge_index, kg.edge_type, n, r)
-    out_ref = Fn.RelGATStackFunction.apply(x0, g_full, h, f, "fp32", None, None, None, *params)
+    out_ref = Fn.RelGATStackFunction.apply(x0, g_full, h, f, "fp32", None, None, None, False, *params)
     ref_grads = torch.autograd.grad(out_ref, [x0] + params, grad_out)
 
     store = {}
@@ -372,7 +372,7 @@ def test_peer_table_partition_with_bf16_halo_rows_stated_tolerance(dev):
     x0 = kg.node_emb.clone().requires_grad_(True)
     grad_out = torch.randn(n, h * f, generator=gen).to(dev)
     g_full = G.GraphIndex(kg.edge_index, kg.edge_type, n, r)
-    out_ref = Fn.RelGATStackFunction.apply(x0, g_full, h, f, "fp32", None, None, None, *params)
+    out_ref = Fn.RelGATStackFunction.apply(x0, g_full, h, f, "fp32", None, None, None, False, *params)
     ref_grads = torch.autograd.grad(out_ref, [x0] + params, grad_out)
     store = {}
     parts = [RP.PeerPartition(kg.edge_index, kg.edge_type, n, r, rk, world,
@@ -469,7 +469,7 @@ def test_peer_table_sparse_last_layer_backward(dev):
         dense = torch.zeros(n, h * f, device=dev)
         uniq = torch.unique(ids)
         dense[uniq] = torch.randn(uniq.numel(), h * f, generator=gen).to(dev)
-        out_again = Fn.RelGATStackFunction.apply(x0, g_full, h, f, "fp32", None, None, None, *params)  # its backward runs once
+        out_again = Fn.RelGATStackFunction.apply(x0, g_full, h, f, "fp32", None, None, None, False, *params)  # its backward runs once
         ref = torch.autograd.grad(out_again, [x0] + params, dense)
         gens = []
         for p in parts:

@@ -103,18 +103,20 @@ def _run_trainer(device, tmp_path, *, projection, self_adv, patch, fused_seam=Fa
 
 
 @pytest.mark.parametrize("projection,self_adv,fused_seam,receptive_field", [
-    (False, False, False, False),   # DistMult, margin ranking loss: model.forward seam
-    (True, True, False, False),     # the reference's shipped recipe: TransE + projection + self-adversarial + reconstruction
-    (True, True, True, False),      # same, plus the trainer-level seam (fused batch rows, score and loss kernels)
-    (False, True, True, False),
-    (True, True, True, True),       # ... and every train / eval batch on its receptive-field blocks (blocks.py)
-    (False, False, False, True),
+    (False, False, False, None),   # DistMult, margin ranking loss: model.forward seam
+    (True, True, False, None),     # the reference's shipped recipe: TransE + projection + self-adversarial + reconstruction
+    (True, True, True, None),       # same, plus the trainer-level seam (fused batch rows, score and loss kernels)
+    (False, True, True, None),
+    (True, True, True, "masked"),   # ... and every train / eval batch restricted to its receptive field
+    (False, False, False, "masked"),
+    (True, True, True, "blocks"),   # ... through per-batch bipartite sub-indexes (blocks.py)
 ])
 def test_reference_trainer_with_dropin_classes_matches_reference_on_cpu(dev, tmp_path, monkeypatch, projection, self_adv,
                                                                         fused_seam, receptive_field):
     ref = _run_trainer("cpu", tmp_path, projection=projection, self_adv=self_adv, patch=False)
     if receptive_field:
         monkeypatch.setenv("RELGAT_RECEPTIVE_FIELD", "1")  # read by the drop-in RelGATModel's constructor
+        monkeypatch.setenv("RELGAT_RF_MODE", receptive_field)
     got = _run_trainer(dev, tmp_path, projection=projection, self_adv=self_adv, patch=True, fused_seam=fused_seam)
     assert ref["model_module"].startswith("relgat_projector.") and got["model_module"].startswith("relgat_projector_b200")
     assert len(ref["losses"]) == len(got["losses"]) >= 10
