@@ -583,7 +583,8 @@ def main():
         rf_rec = {"ms_per_step": ms_rf, "steps_per_sec": 1e3 / ms_rf, "speedup_vs_full_graph_step": round(ms / ms_rf, 3),
                   "block_edges_per_step": int(model.last_block_edges), "layer_edges_full_graph": cfg["L"] * E,
                   "graph_edges_per_sec_equivalent": E / (ms_rf * 1e-3),
-                  "note": "receptive-field pruning: block extraction + forward + loss + backward + Adam per step; "
+                  "mode": getattr(model, "receptive_field_mode", None),
+                  "note": "receptive-field pruning: row-set plan + forward + loss + backward + Adam per step; "
                           "'graph_edges_per_sec_equivalent' divides ALL E edges by the step time for comparison only"}
         model.receptive_field = False
 
