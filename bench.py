@@ -586,6 +586,11 @@ def main():
                   "mode": getattr(model, "receptive_field_mode", None),
                   "note": "receptive-field pruning: row-set plan + forward + loss + backward + Adam per step; "
                           "'graph_edges_per_sec_equivalent' divides ALL E edges by the step time for comparison only"}
+        model.receptive_field_mode = "blocks"  # the alternative implementation: per-batch bipartite sub-indexes
+        for i in range(3):
+            train_step(*dev_batches[i % n_pool])
+        rf_rec["blocks_mode_ms_per_step"] = timed(lambda i: train_step(*dev_batches[i % n_pool]), max(args.steps // 2, 5))
+        model.receptive_field_mode = "masked"
         model.receptive_field = False
 
     # secondary record: single-pass bf16 tensor-core operands (stated tolerance 2e-2, tests/test_gpu_model.py)
