@@ -502,7 +502,10 @@ def main():
     for tag, d in sorted(table.items(), key=lambda kv: -kv[1]["ms_per_step"]):
         ent = {"calls_per_step": d["calls"] / psteps, "avg_ms": round(d["avg_ms"], 4),
                "ms_per_step": round(d["ms_per_step"], 4), "share_of_step": round(d["ms_per_step"] / ms, 4)}
-        if d["kernel"] in work:
+        if args.backward == "sparse" and d["kernel"] in ("edge_bwd_src", "edge_bwd_prep"):
+            # rows restricted to the batch's in-neighbourhood: §8(d)'s dense byte count does not describe this launch
+            ent["note"] = "restricted to the rows that can be non-zero; no algorithmic-byte figure (see profiles/r02_ncu_sparse_bwd_src.md for its measured DRAM traffic)"
+        elif d["kernel"] in work:
             bytes_ = work[d["kernel"]] + (work["edge_fwd_act"] * (cfg["L"] - 1) / cfg["L"] if d["kernel"] == "edge_fwd" else 0)
             ent["algorithmic_bytes"] = int(bytes_)
             ent["gbs"] = round(bytes_ / (d["avg_ms"] * 1e-3) / 1e9, 1)
