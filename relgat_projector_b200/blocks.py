@@ -48,6 +48,8 @@ def build_blocks(full: GraphIndex, ids: torch.Tensor, num_layers: int) -> Blocks
     ids.record_stream(side)
     with torch.cuda.stream(side):
         D = torch.unique(ids)  # sorted
+        if D.numel() == 0:  # nothing requested: one (unread) destination keeps every block non-empty
+            D = torch.zeros(1, dtype=torch.int64, device=dev)
         out_pos = torch.searchsorted(D, ids)
         graphs: List[GraphIndex] = []
         n_edges = 0

@@ -771,3 +771,18 @@ def test_work_table_over_a_list_of_destinations(dev):
     assert ck.chunks.cpu().tolist() == chunks and ck.parts.cpu().tolist() == parts
     assert ck.long_node.cpu().tolist() == [3, 900] and ck.long_part_ptr.cpu().tolist() == [0, 3, 7]
     assert ck.n_edges == int(deg[rows].sum())
+
+
+@pytest.mark.parametrize("mode", [None, "masked", "blocks"])
+def test_batch_rows_with_an_empty_id_list(dev, mode):
+    """No row requested: an empty result, and a backward that yields all-zero parameter gradients (full-graph step,
+    compacted backward and both receptive-field modes)."""
+    c = Case("tiny_fp64")
+    m = _load_model(c, dev)
+    if mode:
+        m.receptive_field, m.receptive_field_mode = True, mode
+    rows = m.batch_rows(torch.empty(0, dtype=torch.int64, device=dev))
+    assert tuple(rows.shape) == (0, c.h * c.f)
+    rows.sum().backward()
+    grads = [p.grad for n_, p in m.named_parameters() if n_.startswith("gat_layer") and p.grad is not None]
+    assert grads and all(float(g_.abs().sum()) == 0.0 for g_ in grads)
