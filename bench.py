@@ -360,7 +360,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default=None, help="c1|c2|c3|c4|tiny (default: c2 on 1 GPU, c4 sharded on >1)")
+    ap.add_argument("--config", default=None, help="c1|c2|c3|c4|tiny (default c2: on N > 1 GPUs every rank holds one c2-sized share of an N-times larger graph = "
+                                                         "weak scaling; an explicitly named config is sharded as it is = strong scaling)")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--exchange", default="peer", choices=["peer", "halo", "allgather"],
                     help="multi-GPU only: peer tables read over NVLink (default), or an NCCL exchange of halo / all rows")
