@@ -260,7 +260,8 @@ int relgat_recon_loss(const float* tr, const float* dst, const float* negdst, in
 
 /* Keep-bit masks for the fused dropout: bits[w] bit j = 1 with probability 1 - p_drop (16-bit resolution), from
  * Philox4x32-10(seed, counter = word index * 4 + q).  relgat_zero_rows: table[ids[i], 0:D] = 0 (clears the rows of
- * the batch gradient that relgat_index_add_sorted scattered into a persistent zero table). */
+ * the batch gradient that relgat_index_add_sorted scattered into a persistent zero table); entries with ids[i] < 0 are
+ * skipped. */
 int relgat_bernoulli_bits(unsigned int* bits, long long n_words, float p_drop, unsigned long long seed, void* stream);
 int relgat_zero_rows(float* table, long long ld, const long long* ids, long long n, int D, void* stream);
 
@@ -329,7 +330,8 @@ int relgat_peer_table_last_driver_error(void);
 /* halo pull (device): out[o(i), :] = table[ids[i], :] for i < n, o(i) = out_ids[i] (NULL: o(i) = i); ids int64 row
  * numbers of the mapped range (a peer's rows arrive over NVLink), D floats per row, ld / ldo row strides in
  * floats.  Run between the writers' rendezvous and the edge kernel that consumes [own rows | pulled rows].
- * Rows with equal out_ids must carry equal data (the batch may name a node twice). */
+ * Rows with equal out_ids must carry equal data (the batch may name a node twice).  An entry with ids[i] < 0 is
+ * skipped (the caller knows that row to be all zero at its owner and keeps its local copy at zero). */
 int relgat_pull_rows(const float* table, long long ld, const long long* ids, const long long* out_ids,
                      long long n, int D, float* out, long long ldo, int sm_count, void* stream);
 /* same pull from a table whose rows the owner exported rounded to bf16 (half the NVLink bytes): rows are widened to

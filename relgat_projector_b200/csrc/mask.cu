@@ -49,13 +49,16 @@ __global__ void bernoulli_bits_kernel(uint32_t* __restrict__ bits, long long n_w
 
 __global__ void zero_rows_kernel(float* __restrict__ table, long long ld, const long long* __restrict__ ids, long long n,
                                  int D) {
-  const long long i = blockIdx.x;
-  if (i >= n) return;
-  float* row = table + ids[i] * ld;
-  if ((D & 3) == 0 && (ld & 3) == 0 && reinterpret_cast<uintptr_t>(table) % 16 == 0) {
-    for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4) *reinterpret_cast<float4*>(row + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-  } else {
-    for (int c = threadIdx.x; c < D; c += blockDim.x) row[c] = 0.f;
+  const bool vec = (D & 3) == 0 && (ld & 3) == 0 && reinterpret_cast<uintptr_t>(table) % 16 == 0;
+  for (long long i = blockIdx.x; i < n; i += gridDim.x) {
+    const long long id = ids[i];
+    if (id < 0) continue;  // entry switched off by the caller
+    float* row = table + id * ld;
+    if (vec) {
+      for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4) *reinterpret_cast<float4*>(row + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      for (int c = threadIdx.x; c < D; c += blockDim.x) row[c] = 0.f;
+    }
   }
 }
 
@@ -123,6 +126,7 @@ extern "C" int relgat_zero_rows(float* table, long long ld, const long long* ids
   if (n < 0 || D <= 0) return RG_ERR_ARG;
   if (n == 0) return RG_OK;
   if (!table || !ids) return RG_ERR_ARG;
-  zero_rows_kernel<<<static_cast<unsigned>(n), 128, 0, static_cast<cudaStream_t>(stream)>>>(table, ld, ids, n, D);
+  const long long cap = 148 * 16;  // a grid-stride loop: long lists with most entries switched off stay cheap
+  zero_rows_kernel<<<static_cast<unsigned>(n < cap ? n : cap), 128, 0, static_cast<cudaStream_t>(stream)>>>(table, ld, ids, n, D);
   return cuda_status(cudaGetLastError());
 }

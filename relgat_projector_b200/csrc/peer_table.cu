@@ -176,7 +176,9 @@ pull_rows_kernel(const float* __restrict__ table, long long ld, const long long*
       if (idx < total) {
         row[u] = idx / dv;
         q[u] = static_cast<int>(idx - row[u] * dv);
-        RowVec<float, V>::load_stream(table + __ldg(ids + row[u]) * ld + q[u] * V, v[u]);
+        const long long src_row = __ldg(ids + row[u]);
+        if (src_row < 0) row[u] = -1;  // entry switched off by the caller (a row known to be all zero at its owner)
+        else RowVec<float, V>::load_stream(table + src_row * ld + q[u] * V, v[u]);
       }
     }
 #pragma unroll
@@ -206,7 +208,9 @@ pull_rows_bf16_kernel(const __nv_bfloat16* __restrict__ table, long long ld, con
       if (idx < total) {
         row[u] = idx / dv;
         q[u] = static_cast<int>(idx - row[u] * dv);
-        RowVec<__nv_bfloat16, 8>::load_stream(table + __ldg(ids + row[u]) * ld + q[u] * 8, v[u]);
+        const long long src_row = __ldg(ids + row[u]);
+        if (src_row < 0) row[u] = -1;  // entry switched off by the caller
+        else RowVec<__nv_bfloat16, 8>::load_stream(table + src_row * ld + q[u] * 8, v[u]);
       }
     }
 #pragma unroll

@@ -35,6 +35,7 @@ import os
 import socket
 import threading
 import time
+import types
 from typing import Dict, Generator, List, Optional, Sequence, Tuple
 
 import torch
@@ -56,6 +57,12 @@ PIPELINE_BLOCKS = max(1, int(os.environ.get("RELGAT_PEER_BLOCKS", "4")))
 # last layer's backward: dY is zero outside the batch rows, so only those rows of G / t / hsum are written, pulled
 # and (afterwards) cleared — instead of moving a dense, almost-all-zero halo over NVLink
 SPARSE_LAST = os.environ.get("RELGAT_PEER_SPARSE_LAST", "1") != "0"
+# hidden layers' backward: the gradient rows of a hidden layer are exact zeros outside the in-neighbourhood of the
+# batch's nodes (sources of the edges into them, and so on down).  Every rank holds the whole graph's in-edge lists, so
+# it can tell which of ITS pulled rows are such zeros without asking their owners: those rows are not fetched (their
+# local copies are kept at zero), the by-source pass still gathers every row.  Same arithmetic, ~1 % of the NVLink bytes
+# of that pull.  Needs the sparse last layer (the batch ids).
+NZ_PULL = os.environ.get("RELGAT_PEER_NZ_PULL", "1") != "0"
 # halo rows cross NVLink rounded to bf16 (the owner exports a bf16 copy of its P / G rows; the pull widens them into
 # the fp32 [own | pulled] table): half the link bytes of a layer pass.  Library default: off (fp32 rows, results equal
 # to one GPU up to summation order); bench.py turns it on for the multi-GPU runs and states the tolerance (2e-2).
@@ -406,6 +413,14 @@ class PeerIndexPlan:
         perm_b, pos_b, self.blk_b = pull_order(halo_b)
         self.pos_b = pos_b  # position of every (sorted) backward-halo id among the pulled rows
         self.pull_f, self.pull_b = row_id(halo_f[perm_f]), row_id(halo_b[perm_b])  # rows of the mapped range to pull
+        self.pull_gid_b = halo_b[perm_b]  # global node id of every pulled backward-halo row (pull order)
+        # in-edges of EVERY node, by destination (int32): lets a rank work out, without asking anyone, which rows of a
+        # hidden layer's gradient can be non-zero for a batch (sources of the edges into the batch's nodes, and so on
+        # down) — the other rows are exact zeros at their owners and need not cross NVLink (see backward_steps)
+        order = torch.argsort(dst, stable=True)
+        self.in_src = src[order].to(torch.int32)
+        self.in_rowptr = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev),
+                                    torch.cumsum(torch.bincount(dst, minlength=self.N), 0)]).to(torch.int32)
         self.row_blocks = [(-(-c * n // k_blocks), -(-(c + 1) * n // k_blocks)) for c in range(k_blocks)]  # own rows per block
         # forward: in-edges of my destinations, original order (stable bucketing)
         sel_f = torch.nonzero(in_f).flatten()
@@ -468,8 +483,11 @@ class PeerPartition:
         self.plan = plan
         for name in ("bounds", "lo", "hi", "n_local", "blocks", "stride_rows", "stride_slots", "n_halo_f", "n_halo_b",
                      "pull_f", "pull_b", "blk_f", "blk_b", "row_blocks", "E_fwd", "E_bwd", "owner_of", "row_id",
-                     "halo_b", "pos_b"):
+                     "halo_b", "pos_b", "pull_gid_b"):
             setattr(self, name, getattr(plan, name))
+        # (rowptr, sources) of the whole graph's in-edges in the shape ops.mark_sources expects
+        self.in_graph = types.SimpleNamespace(rowptr=plan.in_rowptr.contiguous(), csr_src=plan.in_src.contiguous(),
+                                              N=self.N, N_src=self.N)
         n = self.n_local
         fs, fd, fr = plan.fwd_edges
         self.fwd_graph = GraphIndex(torch.stack([fs, fd]), fr, max(n, 1), self.R,
@@ -493,6 +511,9 @@ class PeerPartition:
         self.batch_ids: Optional[torch.Tensor] = None  # node ids of the current batch (set by PeerBatchRows)
         self._sparse_clean = False  # last layer's G / t / hsum tables hold zeros outside the rows listed in _dirty
         self._dirty: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+        # hidden layers, NZ_PULL: the pulled region of G{l} holds zeros outside the rows listed in _nz_dirty[l]
+        self._nz_clean: Dict[int, bool] = {}
+        self._nz_dirty: Dict[int, torch.Tensor] = {}
 
     def sparse_halo_targets(self, ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         return self.plan.sparse_halo_targets(ids)
@@ -575,6 +596,16 @@ def backward_steps(part: PeerPartition, grad_out: torch.Tensor, saved: list, wit
     grads: List[Optional[torch.Tensor]] = [None] * (3 * L)
     dY, dX = grad_out.contiguous(), None
     keep: list = []
+    # NZ_PULL: per hidden layer, the pull list with the entries of known-zero rows switched off (-1)
+    nz_pull: Dict[int, torch.Tensor] = {}
+    if (NZ_PULL and SPARSE_LAST and L > 1 and part.batch_ids is not None and part.n_halo_b > 0
+            and sparse_rows_of(grad_out) is not None and dY is grad_out):
+        bits = ops.mark_rows(part.batch_ids, part.N)
+        gid = part.pull_gid_b
+        for l in range(L - 2, -1, -1):
+            bits = ops.mark_sources(bits, part.in_graph)  # rows of dL/d out_l that can be non-zero
+            live = ((bits[gid >> 5] >> (gid & 31).to(torch.int32)) & 1).bool()
+            nz_pull[l] = torch.where(live, part.pull_b, torch.full_like(part.pull_b, -1))
     for l in reversed(range(L)):
         s = saved[l]
         main = torch.cuda.current_stream(dY.device)
@@ -616,6 +647,19 @@ def backward_steps(part: PeerPartition, grad_out: torch.Tensor, saved: list, wit
         else:
             if l == L - 1:
                 part._sparse_clean = False
+            ids_l = nz_pull.get(l)
+            nh = part.n_halo_b
+            if ids_l is not None:
+                halo_G = T[f"G{l}"].local[n:n + nh]
+                if not part._nz_clean.get(l):
+                    halo_G.zero_()
+                    part._nz_clean[l] = True
+                elif l in part._nz_dirty:  # rows the previous step fetched (its by-source pass has long read them)
+                    ops.zero_rows(halo_G, part._nz_dirty[l])
+                pos = torch.arange(nh, device=dY.device)
+                part._nz_dirty[l] = torch.where(ids_l >= 0, pos, torch.full_like(pos, -1))
+            else:
+                part._nz_clean[l] = False
             for c, (r0, r1) in enumerate(part.row_blocks):
                 if r1 > r0:
                     ops.edge_bwd_prep(dY[r0:r1], s["out"][r0:r1], s["bias"][r0:r1], H, F, apply_elu=(l < L - 1),
@@ -627,7 +671,8 @@ def backward_steps(part: PeerPartition, grad_out: torch.Tensor, saved: list, wit
                 _mark(f"bwd{l} rendezvous {c} done")
                 comm.wait_stream(main)
                 with torch.cuda.stream(comm):  # beside the prep of block c+1
-                    G_ext = part.pull(f"G{l}", part.pull_b, part.blk_b, c, export=f"Gb{l}" if part.halo_bf16 else None)
+                    G_ext = part.pull(f"G{l}", part.pull_b if ids_l is None else ids_l, part.blk_b, c,
+                                      export=f"Gb{l}" if part.halo_bf16 else None)
                     t_ext, minv_ext, hsum_ext = (part.pull(f"{k}{l}", part.pull_b, part.blk_b, c) for k in ("t", "minv", "hsum"))
                     _mark(f"bwd{l} pull block {c} done", "comm")
         main.wait_stream(comm)
