@@ -99,6 +99,11 @@ int relgat_gemm_bf16(const void* a_hi, const void* a_lo, long long lda, int a_mn
  * bias [M] its relation-bias sums, drop_* its feature-dropout mask (NULL = off), apply_elu: act = ELU else identity.
  * Needs relgat_gemm_tile_n(N) <= F (a tile inside at most two heads), else RG_ERR_SHAPE (use the unfused pair). */
 int relgat_gemm_tile_n(int N);
+/* Tile shape relgat_gemm_bf16 uses for an [M, N] output (rows: 256 when the kernel runs as CTA pairs — tcgen05
+ * cta_group::2, M > 128 — else 128; columns chosen by the bytes the tile moves from L2 to shared memory; b_mn as in
+ * relgat_gemm_bf16) and the modelled cost of one k-block over all tiles in SM clocks.  Host-side split-K and
+ * orientation choices use it.  (relgat_gemm_tile_n is the N tile of relgat_gemm_dx_prep only.) */
+long long relgat_gemm_plan(int M, int N, int b_mn, int* tile_m, int* tile_n);
 int relgat_gemm_dx_prep(const void* a_hi, const void* a_lo, long long lda, const void* b_hi, const void* b_lo,
                         long long ldb, float* G, int M, int N, int K, const float* y, const float* bias,
                         const unsigned int* drop_bits, int drop_words, float drop_scale, int H, int F,

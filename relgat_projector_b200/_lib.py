@@ -37,6 +37,7 @@ SIGNATURES = {
     "relgat_gemm_workspace_bytes": (_L, [_I, _I, _I, _I, _I, _I]),
     "relgat_gemm_bf16": (_I, [_P, _P, _L, _I, _P, _P, _L, _I, _P, _I, _L, _I, _I, _I, _I, _P, _L, _I, _P]),
     "relgat_gemm_tile_n": (_I, [_I]),
+    "relgat_gemm_plan": (_L, [_I, _I, _I, _P, _P]),
     "relgat_gemm_dx_prep": (_I, [_P, _P, _L, _P, _P, _L, _P, _I, _I, _I, _P, _P, _P, _I, _F, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
     "relgat_layer_fwd": (_I, [_P, _I, _L, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P,
                               _P, _I, _F, _P, _F, _P, _I, _I, _I, _I, _P, _P]),
@@ -76,7 +77,7 @@ SIGNATURES = {
     "relgat_pull_rows_bf16": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _I, _P]),
 }
 
-ABI_VERSION = 12  # bumped whenever a signature in include/relgat_b200.h changes
+ABI_VERSION = 13  # bumped whenever a signature in include/relgat_b200.h changes
 _lib = None
 
 

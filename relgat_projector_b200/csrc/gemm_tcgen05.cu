@@ -97,6 +97,47 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+
+// ---- CTA-pair (cta_group::2) variants: two CTAs of one cluster (one TPC) run ONE 256-row MMA; each CTA stages its own
+// 128 rows of A and HALF of the B tile, the leader (cluster rank 0) issues the MMAs and reads both CTAs' shared memory.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// address of the same shared-memory object in CTA `rank` of this cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  __syncthreads();  // reconverges every warp of this CTA: the .aligned cluster barrier below needs whole warps
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on an mbarrier of any CTA of the cluster (address from mapa_shared)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into this CTA's shared memory whose completion bytes are signalled on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// completion of the pair's MMAs arrives on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3)) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -254,6 +295,11 @@ __device__ __noinline__ void epilogue_staged(const GemmParams& p, const CUtensor
 }
 
 // ---------------------------------------------------------------------------- the kernel
+// CG = 1: one CTA per 128-row tile (cta_group::1).  CG = 2: launched as clusters of two CTAs; the pair owns a 256-row
+// tile (rank r: rows r*128..), each CTA loads its A rows and B columns [r*BN/2, (r+1)*BN/2), the leader issues
+// tcgen05.mma.cta_group::2 (M = 256) whose completion is multicast to both CTAs' barriers.  Per CTA and k-block this
+// moves (128 + BN/2) operand rows through L2 -> shared memory instead of (128 + BN).
+template <int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                          const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -268,7 +314,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
   const int planes = p.split ? 2 : 1;
   const int stage_bytes = planes * (p.a_tile_bytes + p.b_tile_bytes);
 
-  const int mt = (p.M + kBM - 1) / kBM;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int group_id = blockIdx.x / CG;       // persistent CTA (pair) index
+  const int n_groups = gridDim.x / CG;
+  constexpr int kTileM = kBM * CG;            // rows of one unit
+  const int bn_cta = p.BN / CG;               // B rows (output columns) this CTA stages
+  const int mt = (p.M + kTileM - 1) / kTileM;
   const int nt = (p.N + p.BN - 1) / p.BN;
   const int total_kb = (p.K + kBK - 1) / kBK;
   const long long units = static_cast<long long>(mt) * nt * p.splits_k;
@@ -284,16 +335,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4 * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(kTmemCols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if constexpr (CG == 2) {  // the same columns are reserved in both CTAs' tensor memory
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(kTmemCols));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(kTmemCols));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
+  else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_slot;
 
@@ -301,32 +358,39 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+      for (long long u = group_id; u < units; u += n_groups) {
         const int n_tile = static_cast<int>(u % nt);
         const int m_tile = static_cast<int>((u / nt) % mt);
         const int ks = static_cast<int>(u / (static_cast<long long>(nt) * mt));
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+        const int a_row0 = m_tile * kTileM + static_cast<int>(cta_rank) * kBM;      // this CTA's A rows
+        const int b_row0 = n_tile * p.BN + static_cast<int>(cta_rank) * bn_cta;     // this CTA's share of the B tile
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + static_cast<size_t>(stage) * stage_bytes;
-          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          // pair: both CTAs' bytes are counted on the leader's barrier (a peer's bytes may land before the leader's
+          // expect_tx of the same phase: the pending arrival keeps the phase open)
+          if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], stage_bytes * CG);
+          const uint32_t bar_leader = (CG == 2) ? mapa_shared(smem_u32(&full_bar[stage]), 0) : 0u;
+          auto load = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
+            if constexpr (CG == 2) tma_load_2d_pair(dst, m, bar_leader, c0, c1);
+            else tma_load_2d(dst, m, &full_bar[stage], c0, c1);
+          };
           for (int pl = 0; pl < planes; ++pl) {
             const CUtensorMap* ma = pl ? &map_a_lo : &map_a_hi;
             const CUtensorMap* mb = pl ? &map_b_lo : &map_b_hi;
             uint8_t* sa = st + pl * p.a_tile_bytes;
             uint8_t* sb = st + planes * p.a_tile_bytes + pl * p.b_tile_bytes;
             if (!p.a_mn) {
-              tma_load_2d(sa, ma, &full_bar[stage], kb * kBK, m_tile * kBM);
+              load(sa, ma, kb * kBK, a_row0);
             } else {
-              for (int bx = 0; bx < kBM / 64; ++bx)
-                tma_load_2d(sa + bx * (kBK * 128), ma, &full_bar[stage], m_tile * kBM + bx * 64, kb * kBK);
+              for (int bx = 0; bx < kBM / 64; ++bx) load(sa + bx * (kBK * 128), ma, a_row0 + bx * 64, kb * kBK);
             }
             if (!p.b_mn) {
-              tma_load_2d(sb, mb, &full_bar[stage], kb * kBK, n_tile * p.BN);
+              load(sb, mb, kb * kBK, b_row0);
             } else {
-              for (int bx = 0; bx < p.b_boxes; ++bx)
-                tma_load_2d(sb + bx * (kBK * 128), mb, &full_bar[stage], n_tile * p.BN + bx * 64, kb * kBK);
+              for (int bx = 0; bx < p.b_boxes; ++bx) load(sb + bx * (kBK * 128), mb, b_row0 + bx * 64, kb * kBK);
             }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -335,16 +399,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && cta_rank == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(p.a_mn) << 15) |
                              (static_cast<uint32_t>(p.b_mn) << 16) | (static_cast<uint32_t>(p.BN >> 3) << 17) |
-                             (static_cast<uint32_t>(kBM >> 4) << 24);
+                             (static_cast<uint32_t>(kTileM >> 4) << 24);
       const uint32_t a_lbo = p.a_mn ? kBK * 128 : 16, b_lbo = p.b_mn ? kBK * 128 : 16;
       const uint32_t a_kstep = p.a_mn ? kUmmaK * 128 : kUmmaK * 2;  // bytes per UMMA_K step
       const uint32_t b_kstep = p.b_mn ? kUmmaK * 128 : kUmmaK * 2;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+      for (long long u = group_id; u < units; u += n_groups) {
         const int ks = static_cast<int>(u / (static_cast<long long>(nt) * mt));
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(total_kb, kb0 + p.kb_per_split);
@@ -366,17 +430,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
             for (int k = 0; k < kBK / kUmmaK; ++k) {
               const uint64_t da = make_desc(sa + k * a_kstep, a_lbo, 1024);
               const uint64_t db = make_desc(sb + k * b_kstep, b_lbo, 1024);
-              umma_bf16(tmem_d, da, db, idesc, accumulate);
+              if constexpr (CG == 2) umma_bf16_pair(tmem_d, da, db, idesc, accumulate);
+              else umma_bf16(tmem_d, da, db, idesc, accumulate);
               accumulate = 1;
             }
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem stage when the MMAs above retire
+          // frees the smem stage (in both CTAs of a pair) when the MMAs above retire
+          if constexpr (CG == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         if (kb1 <= kb0) {
           // empty K range (possible for the last split): publish a zero tile via the epilogue flag
         }
-        umma_commit(&tmem_full[acc]);
+        if constexpr (CG == 2) umma_commit_pair(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -384,11 +450,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
     // ===================== epilogue =====================
     const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
     int acc = 0; uint32_t acc_phase = 0;
-    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+    for (long long u = group_id; u < units; u += n_groups) {
       const int n_tile = static_cast<int>(u % nt);
       const int m_tile = static_cast<int>((u / nt) % mt);
       const int ks = static_cast<int>(u / (static_cast<long long>(nt) * mt));
       const bool empty_k = (ks * p.kb_per_split >= total_kb);
+      const int row_base = m_tile * kTileM + static_cast<int>(cta_rank) * kBM + ew * 32;  // this warp's 32 rows
       mbar_wait(&tmem_full[acc], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(ew * 32) << 16);
@@ -397,15 +464,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
       } else if (p.staged) {
         uint8_t* stg = smem + static_cast<size_t>(p.stages) * stage_bytes + ew * (32 * 64);
         int pf_row0 = -1, pf_col0 = 0;
-        if (p.epi_y && u + gridDim.x < units) {
-          const long long un = u + gridDim.x;
-          pf_row0 = static_cast<int>((un / nt) % mt) * kBM + ew * 32;
+        if (p.epi_y && u + n_groups < units) {
+          const long long un = u + n_groups;
+          pf_row0 = static_cast<int>((un / nt) % mt) * kTileM + static_cast<int>(cta_rank) * kBM + ew * 32;
           pf_col0 = static_cast<int>(un % nt) * p.BN;
         }
-        if (p.d_bf16) epilogue_staged<true>(p, &map_d, stg, taddr, m_tile * kBM + ew * 32, n_tile * p.BN, ks, empty_k, lane, -1, 0);
-        else epilogue_staged<false>(p, &map_d, stg, taddr, m_tile * kBM + ew * 32, n_tile * p.BN, ks, empty_k, lane, pf_row0, pf_col0);
+        if (p.d_bf16) epilogue_staged<true>(p, &map_d, stg, taddr, row_base, n_tile * p.BN, ks, empty_k, lane, -1, 0);
+        else epilogue_staged<false>(p, &map_d, stg, taddr, row_base, n_tile * p.BN, ks, empty_k, lane, pf_row0, pf_col0);
       } else {
-      const int row = m_tile * kBM + ew * 32 + lane;
+      const int row = row_base + lane;
       float* drow = p.d ? p.d + static_cast<long long>(ks) * p.d_split_stride + static_cast<long long>(row) * p.ldd
                         : nullptr;
       __nv_bfloat16* hrow = p.d_bf16 ? p.d_bf16 + static_cast<long long>(row) * p.ldd : nullptr;
@@ -453,16 +520,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {  // the leader's issuer waits for the epilogue warps of both CTAs
+        if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   if (p.tma_store && warp >= 4 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // neither CTA leaves (or frees tensor memory) while its peer still works
+  else __syncthreads();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    if constexpr (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
   }
 }
 
@@ -556,7 +630,8 @@ static int make_map_d(CUtensorMap* m, const void* base, bool bf16, long long row
   return r == CUDA_SUCCESS ? RG_OK : RG_ERR_DRIVER;
 }
 
-static int pick_bn(int N) {
+// N tile of the fused-prep dX GEMM (single CTA per tile): the widest divisor of N, so that a tile stays inside two heads
+static int pick_bn_prep(int N) {
   if (const char* v = getenv("RELGAT_GEMM_BN")) {  // experiment knob: N tile (multiple of 16, <= 256)
     const int bn = atoi(v);
     if (bn >= 16 && bn <= 256 && bn % 16 == 0 && N > bn) return bn;
@@ -565,6 +640,38 @@ static int pick_bn(int N) {
   for (int bn = 256; bn >= 128; bn -= 16)
     if (N % bn == 0) return bn;
   return 256;
+}
+
+static int gemm_cta_group(int M, bool prep_epilogue, int sm_count) {
+  if (const char* v = getenv("RELGAT_GEMM_CG")) { if (atoi(v) == 1) return 1; }
+  return (M > kBM && !prep_epilogue && sm_count >= 2) ? 2 : 1;
+}
+
+// Cost of ONE k-block of a CTA's tile in SM clocks: the slower of the MMA pipe (fp32-parity mode: 12 instructions of
+// 128 x bn / 256 clocks) and the L2 -> shared-memory operand stream.  Measured (tools/gemm_sweep.py, 300k x 800 x 1024,
+// N tiles 128 / 160 / 208 / 256: 1.42 / 1.18 / 1.07 / 1.14 ms): the two-plane GEMMs run at the pace of that stream,
+// ≈ 30 bytes per clock and SM (8.5 TB/s over the chip), not of the tensor pipe — so tiles are chosen by bytes moved.
+static double kblock_cost(int bn, int cg, int b_mn) {
+  const int bn_cta = bn / cg;
+  const double a_bytes = 2.0 * kBM * kBK * 2;
+  const double b_bytes = 2.0 * (b_mn ? ((bn_cta + 63) / 64) * kBK * 128 : bn_cta * kBK * 2);
+  const double mma = 6.0 * bn, l2 = (a_bytes + b_bytes) / 30.0;
+  return mma > l2 ? mma : l2;
+}
+
+static int pick_bn(int N, int cg, int b_mn) {
+  if (const char* v = getenv("RELGAT_GEMM_BN")) {  // experiment knob: N tile (multiple of 16, <= 256)
+    const int bn = atoi(v);
+    if (bn >= 16 && bn <= 256 && bn % 16 == 0 && N > bn) return bn;
+  }
+  if (N <= 256) return (N + 15) / 16 * 16;
+  int best = 256;
+  double best_cost = 0.0;
+  for (int bn = 256; bn >= 128; bn -= 16) {  // widest first: ties go to the wider tile
+    const double c = ((N + bn - 1) / bn) * kblock_cost(bn, cg, b_mn);
+    if (bn == 256 || c < best_cost * 0.999) { best = bn; best_cost = c; }
+  }
+  return best;
 }
 
 }  // namespace relgat
@@ -619,16 +726,21 @@ static int gemm_launch(const void* a_hi, const void* a_lo, long long lda, int a_
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;
-  p.BN = pick_bn(N);
+  if (sm_count <= 0) sm_count = 148;
+  // CTA pairs (cta_group::2, 256-row tiles) whenever there is more than one 128-row tile; the fused-prep epilogue keeps
+  // the single-CTA form.  RELGAT_GEMM_CG=1 is the A/B knob.
+  const int cg = gemm_cta_group(M, epi != nullptr, sm_count);
+  p.BN = epi ? pick_bn_prep(N) : pick_bn(N, cg, b_mn ? 1 : 0);
   p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
   p.split = a_lo ? 1 : 0;
   const int total_kb = (K + kBK - 1) / kBK;
   if (splits_k > total_kb) splits_k = total_kb;
   p.splits_k = splits_k;
   p.kb_per_split = (total_kb + splits_k - 1) / splits_k;
+  const int bn_cta = p.BN / cg;  // BN is a multiple of 16: each CTA's share is a multiple of 8 rows
   p.a_tile_bytes = kBM * kBK * 2;
-  p.b_boxes = (p.BN + 63) / 64;
-  p.b_tile_bytes = p.b_mn ? p.b_boxes * kBK * 128 : p.BN * kBK * 2;
+  p.b_boxes = (bn_cta + 63) / 64;
+  p.b_tile_bytes = p.b_mn ? p.b_boxes * kBK * 128 : bn_cta * kBK * 2;
   const int planes = p.split ? 2 : 1;
   const int stage_bytes = planes * (p.a_tile_bytes + p.b_tile_bytes);
   // the coalesced epilogue needs whole 16-byte pieces: N and the row stride multiples of the piece width
@@ -669,7 +781,7 @@ static int gemm_launch(const void* a_hi, const void* a_lo, long long lda, int a_
   // K-major: matrix [MN rows, K cols], box rows = tile MN extent.  MN-major: matrix [K rows, MN cols], box rows = BK.
   const long long a_rows = p.a_mn ? K : M, a_cols = p.a_mn ? M : K;
   const long long b_rows = p.b_mn ? K : N, b_cols = p.b_mn ? N : K;
-  const int a_box = p.a_mn ? kBK : kBM, b_box = p.b_mn ? kBK : p.BN;
+  const int a_box = p.a_mn ? kBK : kBM, b_box = p.b_mn ? kBK : bn_cta;
   if ((rc = make_map(&ma_hi, a_hi, a_rows, a_cols, lda, a_box)) != RG_OK) return rc;
   if ((rc = make_map(&mb_hi, b_hi, b_rows, b_cols, ldb, b_box)) != RG_OK) return rc;
   if (p.split) {
@@ -685,13 +797,30 @@ static int gemm_launch(const void* a_hi, const void* a_lo, long long lda, int a_
   if (p.staged && splits_k == 1 && !epi && !getenv("RELGAT_GEMM_NO_TMA_STORE") && (ldd * (d_is_bf16 ? 2 : 4)) % 16 == 0) {
     if (make_map_d(&md, d_out, d_is_bf16 != 0, M, N, ldd) == RG_OK) p.tma_store = 1;
   }
-  const long long units = static_cast<long long>((M + kBM - 1) / kBM) * ((N + p.BN - 1) / p.BN) * splits_k;
-  if (sm_count <= 0) sm_count = 148;
-  const int grid = static_cast<int>(units < sm_count ? units : sm_count);
+  const int tile_m = kBM * cg;
+  const long long units = static_cast<long long>((M + tile_m - 1) / tile_m) * ((N + p.BN - 1) / p.BN) * splits_k;
+  const int groups = static_cast<int>(units < sm_count / cg ? units : sm_count / cg);
   const int smem_bytes = stages * stage_bytes + 1024 + (p.staged ? kEpiStageBytes : 0);
-  cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-  if (e != cudaSuccess) return cuda_status(e);
-  gemm_bf16_tcgen05_kernel<<<grid, kGemmThreads, smem_bytes, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, md, p);
+  cudaError_t e;
+  if (cg == 2) {
+    e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return cuda_status(e);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(groups * 2));
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = static_cast<size_t>(smem_bytes);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;  // the two CTAs of a pair share one TPC
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<2>, ma_hi, ma_lo, mb_hi, mb_lo, md, p);
+    if (e != cudaSuccess) return cuda_status(e);
+  } else {
+    e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return cuda_status(e);
+    gemm_bf16_tcgen05_kernel<1><<<groups, kGemmThreads, smem_bytes, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, md, p);
+  }
   if ((e = cudaGetLastError()) != cudaSuccess) return cuda_status(e);
   if (splits_k > 1) {
     const long long n = static_cast<long long>(M) * N;
@@ -710,7 +839,19 @@ extern "C" int relgat_gemm_bf16(const void* a_hi, const void* a_lo, long long ld
                      workspace_bytes, sm_count, stream, nullptr);
 }
 
-extern "C" int relgat_gemm_tile_n(int N) { return N > 0 ? pick_bn(N) : RG_ERR_ARG; }
+extern "C" int relgat_gemm_tile_n(int N) { return N > 0 ? pick_bn_prep(N) : RG_ERR_ARG; }
+
+// Tile shape relgat_gemm_bf16 uses for an [M, N] output (b_mn: B stored [K, N]) and the modelled cost of one k-block
+// over all tiles (SM clocks; comparable between the two orientations of a weight-gradient GEMM).
+extern "C" long long relgat_gemm_plan(int M, int N, int b_mn, int* tile_m, int* tile_n) {
+  if (M <= 0 || N <= 0) return RG_ERR_ARG;
+  const int cg = gemm_cta_group(M, false, 148);
+  const int bn = pick_bn(N, cg, b_mn ? 1 : 0);
+  if (tile_m) *tile_m = kBM * cg;
+  if (tile_n) *tile_n = bn;
+  const long long tiles = static_cast<long long>((M + kBM * cg - 1) / (kBM * cg)) * ((N + bn - 1) / bn);
+  return static_cast<long long>(tiles * cg * kblock_cost(bn, cg, b_mn ? 1 : 0));
+}
 
 // dX GEMM (A = dP [M, K] planes, B = W^T [N, K] planes, both K-major) with the backward prep of the layer below fused
 // into its epilogue: G [M, N] = (A·B^T) * act'(y) * m is written instead of dX, t / hsum [M, H] follow from per-tile
@@ -727,7 +868,7 @@ extern "C" int relgat_gemm_dx_prep(const void* a_hi, const void* a_lo, long long
   e.drop_scale = drop_scale; e.F = F; e.elu = apply_elu;
   int rc = gemm_launch(a_hi, a_lo, lda, 0, b_hi, b_lo, ldb, 0, G, 0, N, M, N, K, 1, nullptr, 0, sm_count, stream, &e);
   if (rc != RG_OK) return rc;
-  const int bn = pick_bn(N);
+  const int bn = pick_bn_prep(N);
   const long long total = static_cast<long long>(M) * H;
   prep_combine_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       tpart, hpart, t, hsum, M, (N + bn - 1) / bn, bn, F, H);

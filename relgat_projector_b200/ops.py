@@ -6,6 +6,7 @@ torch.  CPU tensors are rejected (no fallback).
 """
 from __future__ import annotations
 
+import ctypes
 import os
 from typing import Optional, Tuple
 
@@ -198,34 +199,41 @@ def gemm_dx_prep(dP: Planes, WT: Planes, M: int, N: int, K: int, y: torch.Tensor
     return G, t, hsum
 
 
+def gemm_plan(M: int, N: int, b_mn: bool = True):
+    """(cost, tile_m, tile_n) of the tcgen05 GEMM for an [M, N] output: rows per tile (256 when it runs as CTA pairs),
+    the N tile the kernel picks, and the modelled cost of one k-block over all tiles (L2 -> shared-memory bytes or MMA
+    clocks, whichever is slower) — comparable between the two orientations of a weight-gradient GEMM."""
+    tm, tn = ctypes.c_int(0), ctypes.c_int(0)
+    cost = int(_lib.load().relgat_gemm_plan(int(M), int(N), int(b_mn), ctypes.byref(tm), ctypes.byref(tn)))
+    if cost < 0:
+        _lib.check(cost, "relgat_gemm_plan")
+    return cost, tm.value, tn.value
+
+
 def gemm_cost_model(M: int, N: int) -> float:
-    """Padded MMA work of a [M, N] output tile grid, weighted by the measured efficiency of the N tile (tiles narrower
-    than 224 columns run the 3-pass MMA at ~0.8 of the 256-wide rate: tools/gemm_sweep.py) — used to choose which
-    operand of a split-K weight-gradient GEMM becomes M."""
-    bn = int(_lib.load().relgat_gemm_tile_n(int(N)))
-    eff = 1.0 if bn >= 224 else 0.8
-    return (-(-M // 128) * 128) * (-(-N // bn) * bn) / eff
+    """Modelled cost of a split-K weight-gradient GEMM (both operands MN-major) with an [M, N] output — used to choose
+    which operand becomes M."""
+    return float(gemm_plan(M, N, True)[0])
 
 
 def pick_splits_k(M: int, N: int, K: int, device) -> int:
-    """Split-K factor for GEMMs with few output tiles and a long reduction (the dW GEMMs): the one
-    (<= 16) that fills the persistent grid's waves best, smaller factors winning ties."""
-    bn = (N + 15) // 16 * 16 if N <= 256 else next((b for b in range(256, 127, -16) if N % b == 0), 256)
-    tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
+    """Split-K factor for GEMMs with few output tiles and a long reduction (the dW GEMMs): the one (<= 16) that fills
+    the waves of the persistent grid (one CTA, or one CTA pair, per tile) best, smaller factors winning ties."""
+    _, tm, bn = gemm_plan(M, N, True)
+    tiles = (-(-M // tm)) * (-(-N // bn))
     kb = (K + 63) // 64
-    sms = sm_count(device)
-    if tiles >= 4 * sms or kb < 16:
+    slots = max(1, sm_count(device) // (tm // 128))
+    if tiles >= 4 * slots or kb < 16:
         return 1
     best, best_eff = 1, 0.0
     for sk in range(1, 17):
         if kb // sk < 8:
             break
         units = tiles * sk
-        eff = units / (-(-units // sms) * sms)
+        eff = units / (-(-units // slots) * slots)
         if eff > best_eff + 0.02:
             best, best_eff = sk, eff
     return best
-
 
 
 # ------------------------------------------------------------------------------------------

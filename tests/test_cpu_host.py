@@ -22,7 +22,7 @@ def test_library_loads_and_exports_header_symbols():
     assert set(names) == set(_lib.SIGNATURES.keys())
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/relgat_b200.h but not exported"
-    assert lib.relgat_abi_version() == _lib.ABI_VERSION == 12
+    assert lib.relgat_abi_version() == _lib.ABI_VERSION == 13
     # host-side argument validation needs no GPU
     assert lib.relgat_graph_index_workspace_bytes(-1) == -1
     assert lib.relgat_gemm_workspace_bytes(128, 128, 64, 0, 0, 1) == 0

@@ -60,6 +60,8 @@ def test_graph_index_rejects_bad_input(dev):
 GEMM_SHAPES = [
     # M, N, K
     (128, 64, 64), (300, 200, 136), (1000, 800, 1024), (257, 48, 72), (130, 1024, 200), (4096, 160, 64),
+    # CTA-pair tiles (256 rows): a second CTA whose rows are all / partly outside M, odd tile counts, 16-column output
+    (129, 16, 64), (513, 1000, 128), (1024, 256, 192), (40000, 800, 264),
 ]
 
 
