@@ -99,11 +99,13 @@ int relgat_gemm_bf16(const void* a_hi, const void* a_lo, long long lda, int a_mn
  * bias [M] its relation-bias sums, drop_* its feature-dropout mask (NULL = off), apply_elu: act = ELU else identity.
  * Needs relgat_gemm_tile_n(N) <= F (a tile inside at most two heads), else RG_ERR_SHAPE (use the unfused pair). */
 int relgat_gemm_tile_n(int N);
-/* Tile shape relgat_gemm_bf16 uses for an [M, N] output (rows: 256 when the kernel runs as CTA pairs — tcgen05
- * cta_group::2, M > 128 — else 128; columns chosen by the bytes the tile moves from L2 to shared memory; b_mn as in
- * relgat_gemm_bf16) and the modelled cost of one k-block over all tiles in SM clocks.  Host-side split-K and
- * orientation choices use it.  (relgat_gemm_tile_n is the N tile of relgat_gemm_dx_prep only.) */
-long long relgat_gemm_plan(int M, int N, int b_mn, int* tile_m, int* tile_n);
+/* Work-unit shape relgat_gemm_bf16 uses for an [M, N] output on a device with sm_count SMs (b_mn as in
+ * relgat_gemm_bf16): tile_m = 256 rows when the kernel runs as CTA pairs (tcgen05 cta_group::2, M > 128), else 128;
+ * tile_n = columns of one unit (the N tile, chosen by the bytes a tile moves from L2 to shared memory; twice the N tile
+ * when clusters of two pairs share their A rows by TMA multicast); slots = units in flight at once.  Returns the
+ * modelled cost of one k-block over all tiles in SM clocks.  Host-side split-K and orientation choices use it.
+ * (relgat_gemm_tile_n is the N tile of relgat_gemm_dx_prep only.) */
+long long relgat_gemm_plan(int M, int N, int b_mn, int sm_count, int* tile_m, int* tile_n, int* slots);
 int relgat_gemm_dx_prep(const void* a_hi, const void* a_lo, long long lda, const void* b_hi, const void* b_lo,
                         long long ldb, float* G, int M, int N, int K, const float* y, const float* bias,
                         const unsigned int* drop_bits, int drop_words, float drop_scale, int H, int F,
@@ -205,6 +207,19 @@ int relgat_layer_bwd_src2(const float* P, long long ldp, const float* G, const f
                           float* part_acc, void* dP_hi, void* dP_lo, float* coef, long long E,
                           const unsigned int* edge_bits, float edge_scale, long long ldo, int H, int F, int R,
                           int sm_count, int* work_counter, void* stream);
+/* Third-generation by-source pass (csrc/edge_bwd_src3.cu): the gathered rows reach shared memory as bulk async copies
+ * (cp.async.bulk + mbarrier), several rows deep per warp, and the per-edge term dz * A[rel] is NOT added: the rows are
+ * [dPa | dS] with dPa[i] = sum_e alpha_e G[dst_e]; the caller folds dP = dPa + dS·A into the GEMMs that consume them
+ * (dW = dPa^T X + A^T (dS^T X); dX = [dPa | dS] · [W ; A·W]), which keeps the attention vectors out of shared memory.
+ * fp32 P / G rows, F % 4 == 0; arguments as relgat_layer_bwd_src with want_ds = 1 (no A, no dz).  RG_ERR_SHAPE:
+ * layout not covered. */
+int relgat_layer_bwd_src3(const float* P, long long ldp, const float* G, const float* z, const float* minv,
+                          const float* t, const int* colptr, const int* csc_slot, const int* csc_dst,
+                          const int* csc_rel, const int* chunks, int n_chunks, const int* parts, int n_parts,
+                          const int* long_node, const int* long_part_ptr, int n_long, float* part_acc,
+                          float* dP, void* dP_hi, void* dP_lo, const unsigned int* edge_bits, float edge_scale,
+                          const unsigned int* dst_nz_bits, const int* src_row, int p_compact, long long ldo,
+                          int H, int F, int R, int sm_count, int* work_counter, void* stream);
 int relgat_layer_bwd_beta(const float* hsum, const int* rel_slot, const int* csr_dst, const int* chunk_lo,
                           const int* chunk_hi, const int* rel_chunk_ptr, int n_chunks, float* partB, float* dbeta,
                           int H, int R, void* stream);

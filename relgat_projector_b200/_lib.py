@@ -37,7 +37,7 @@ SIGNATURES = {
     "relgat_gemm_workspace_bytes": (_L, [_I, _I, _I, _I, _I, _I]),
     "relgat_gemm_bf16": (_I, [_P, _P, _L, _I, _P, _P, _L, _I, _P, _I, _L, _I, _I, _I, _I, _P, _L, _I, _P]),
     "relgat_gemm_tile_n": (_I, [_I]),
-    "relgat_gemm_plan": (_L, [_I, _I, _I, _P, _P]),
+    "relgat_gemm_plan": (_L, [_I, _I, _I, _I, _P, _P, _P]),
     "relgat_gemm_dx_prep": (_I, [_P, _P, _L, _P, _P, _L, _P, _I, _I, _I, _P, _P, _P, _I, _F, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
     "relgat_layer_fwd": (_I, [_P, _I, _L, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P,
                               _P, _I, _F, _P, _F, _P, _I, _I, _I, _I, _P, _P]),
@@ -53,6 +53,8 @@ SIGNATURES = {
     "relgat_mark_sources": (_I, [_P, _P, _P, _I, _P, _P]),
     "relgat_layer_bwd_src2": (_I, [_P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _L,
                                    _P, _F, _L, _I, _I, _I, _I, _P, _P]),
+    "relgat_layer_bwd_src3": (_I, [_P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _F,
+                                   _P, _P, _I, _L, _I, _I, _I, _I, _P, _P]),
     "relgat_layer_bwd_beta": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _P]),
     "relgat_layer_bwd_rel": (_I, [_P, _I, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _P]),
     "relgat_score_fwd": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _P, _P, _P]),

@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librelgat_b200.so")
 SOURCES = ["api.cu", "graph_index.cu", "gemm_tcgen05.cu", "edge_fwd.cu", "edge_bwd.cu", "score.cu", "host_sampler.cu",
            "peer_table.cu", "loss.cu", "mask.cu", "edge_bwd_src_f32.cu", "edge_bwd_src_f32s.cu",
-           "edge_bwd_src_bf16.cu", "edge_bwd_src2.cu", "gelu_ln.cu", "stream_chunks.cu", "rowset.cu"]
+           "edge_bwd_src_bf16.cu", "edge_bwd_src2.cu", "edge_bwd_src3.cu", "gelu_ln.cu", "stream_chunks.cu", "rowset.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",

@@ -133,10 +133,28 @@ __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t da, uin
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
-// completion of the pair's MMAs arrives on the barrier at this offset in BOTH CTAs
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+// completion of the pair's MMAs arrives on the barrier at this offset in every CTA of `mask` (cluster ranks)
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3)) : "memory");
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+// TMA load delivered to the same shared-memory offset of every CTA in `mask`; each receiver's own mbarrier (same offset)
+// is credited with the bytes
+__device__ __forceinline__ void tma_load_2d_mcast(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {  // pairs with a remote release.cluster arrive
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  } while (!done);
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&r)[32]) {
   asm volatile(
@@ -299,13 +317,20 @@ __device__ __noinline__ void epilogue_staged(const GemmParams& p, const CUtensor
 // tile (rank r: rows r*128..), each CTA loads its A rows and B columns [r*BN/2, (r+1)*BN/2), the leader issues
 // tcgen05.mma.cta_group::2 (M = 256) whose completion is multicast to both CTAs' barriers.  Per CTA and k-block this
 // moves (128 + BN/2) operand rows through L2 -> shared memory instead of (128 + BN).
-template <int CG>
+//
+// MC = 2 (needs CG = 2): clusters of FOUR CTAs = two pairs working on the same 256 rows and two neighbouring N tiles.
+// The A rows of CTA r of pair 0 and of CTA r of pair 1 are the same: each of the two loads HALF of them (64 rows) and
+// TMA-multicasts its half into both, so every CTA pulls (64 + BN/2) operand rows per k-block through L2 instead of
+// (128 + BN/2).  Barriers: every CTA counts the bytes landing in its OWN shared memory; the odd CTA of a pair forwards
+// "my stage is full" to its leader (one remote arrive per stage); a stage is free when BOTH pairs have consumed it
+// (the commits of both leaders are multicast to all four CTAs).
+template <int CG, int MC>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                          const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                          const __grid_constant__ CUtensorMap map_d, const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tmem_full[2], tmem_empty[2];
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], peer_full[kMaxStages], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5;
@@ -314,13 +339,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
   const int planes = p.split ? 2 : 1;
   const int stage_bytes = planes * (p.a_tile_bytes + p.b_tile_bytes);
 
-  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
-  const int group_id = blockIdx.x / CG;       // persistent CTA (pair) index
-  const int n_groups = gridDim.x / CG;
+  static_assert(MC == 1 || CG == 2, "operand multicast is built on CTA pairs");
+  constexpr int kCluster = CG * MC;
+  const uint32_t cl_rank = (kCluster > 1) ? cluster_ctarank() : 0u;
+  const uint32_t cta_rank = cl_rank & (CG - 1);     // which 128 rows of the pair's tile
+  const uint32_t pair_in_cl = cl_rank >> 1;          // MC = 2: which of the cluster's two N tiles
+  const uint32_t leader = cl_rank & ~1u;             // cluster rank of this CTA's MMA issuer
+  const int group_id = blockIdx.x / kCluster;        // persistent cluster (or CTA) index
+  const int n_groups = gridDim.x / kCluster;
   constexpr int kTileM = kBM * CG;            // rows of one unit
   const int bn_cta = p.BN / CG;               // B rows (output columns) this CTA stages
   const int mt = (p.M + kTileM - 1) / kTileM;
-  const int nt = (p.N + p.BN - 1) / p.BN;
+  const int nt = ((p.N + p.BN - 1) / p.BN) / MC;  // N tiles (MC = 2: pairs of N tiles; the host checked evenness)
   const int total_kb = (p.K + kBK - 1) / kBK;
   const long long units = static_cast<long long>(mt) * nt * p.splits_k;
 
@@ -334,7 +364,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
     }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], MC); mbar_init(&peer_full[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4 * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -359,7 +389,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (long long u = group_id; u < units; u += n_groups) {
-        const int n_tile = static_cast<int>(u % nt);
+        const int n_tile = static_cast<int>(u % nt) * MC + static_cast<int>(MC == 2 ? pair_in_cl : 0u);
         const int m_tile = static_cast<int>((u / nt) % mt);
         const int ks = static_cast<int>(u / (static_cast<long long>(nt) * mt));
         const int kb0 = ks * p.kb_per_split;
@@ -371,10 +401,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
           uint8_t* st = smem + static_cast<size_t>(stage) * stage_bytes;
           // pair: both CTAs' bytes are counted on the leader's barrier (a peer's bytes may land before the leader's
           // expect_tx of the same phase: the pending arrival keeps the phase open)
-          if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], stage_bytes * CG);
-          const uint32_t bar_leader = (CG == 2) ? mapa_shared(smem_u32(&full_bar[stage]), 0) : 0u;
+          if constexpr (MC == 2) mbar_expect_tx(&full_bar[stage], stage_bytes);  // what lands in THIS CTA's smem
+          else if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], stage_bytes * CG);
+          const uint32_t bar_leader = (CG == 2 && MC == 1) ? mapa_shared(smem_u32(&full_bar[stage]), 0) : 0u;
           auto load = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
-            if constexpr (CG == 2) tma_load_2d_pair(dst, m, bar_leader, c0, c1);
+            if constexpr (CG == 2 && MC == 1) tma_load_2d_pair(dst, m, bar_leader, c0, c1);
             else tma_load_2d(dst, m, &full_bar[stage], c0, c1);
           };
           for (int pl = 0; pl < planes; ++pl) {
@@ -382,7 +413,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
             const CUtensorMap* mb = pl ? &map_b_lo : &map_b_hi;
             uint8_t* sa = st + pl * p.a_tile_bytes;
             uint8_t* sb = st + planes * p.a_tile_bytes + pl * p.b_tile_bytes;
-            if (!p.a_mn) {
+            if constexpr (MC == 2) {
+              // my half (64 rows = one 8 KB box in either layout) of the A rows I share with CTA cta_rank of the
+              // other pair, delivered to both of us
+              const uint16_t both = static_cast<uint16_t>((1u << cta_rank) | (1u << (cta_rank + 2)));
+              uint8_t* dst = sa + pair_in_cl * (kBK * 128);
+              const int r0 = a_row0 + static_cast<int>(pair_in_cl) * 64;
+              if (!p.a_mn) tma_load_2d_mcast(dst, ma, &full_bar[stage], kb * kBK, r0, both);
+              else tma_load_2d_mcast(dst, ma, &full_bar[stage], r0, kb * kBK, both);
+            } else if (!p.a_mn) {
               load(sa, ma, kb * kBK, a_row0);
             } else {
               for (int bx = 0; bx < kBM / 64; ++bx) load(sa + bx * (kBK * 128), ma, a_row0 + bx * 64, kb * kBK);
@@ -418,6 +457,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
         uint32_t accumulate = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          if constexpr (MC == 2) mbar_wait_cluster(&peer_full[stage], phase);  // the odd CTA's stage, forwarded
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t st = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
           const uint32_t sa_hi = st, sa_lo = st + p.a_tile_bytes;
@@ -436,14 +476,29 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
             }
           }
           // frees the smem stage (in both CTAs of a pair) when the MMAs above retire
-          if constexpr (CG == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+          if constexpr (CG == 2) umma_commit_pair(&empty_bar[stage], MC == 2 ? 0xF : 0x3); else umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         if (kb1 <= kb0) {
           // empty K range (possible for the last split): publish a zero tile via the epilogue flag
         }
-        if constexpr (CG == 2) umma_commit_pair(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
+        if constexpr (CG == 2) umma_commit_pair(&tmem_full[acc], static_cast<uint16_t>(0x3u << leader)); else umma_commit(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (MC == 2 && warp == 2 && cta_rank == 1) {
+    // ===================== odd CTA of a pair: tell the leader when a stage of MY shared memory is full ==========
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (long long u = group_id; u < units; u += n_groups) {
+        const int ks = static_cast<int>(u / (static_cast<long long>(nt) * mt));
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          mbar_arrive_cluster(mapa_shared(smem_u32(&peer_full[stage]), leader));
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp >= 4) {
@@ -451,7 +506,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
     const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
     int acc = 0; uint32_t acc_phase = 0;
     for (long long u = group_id; u < units; u += n_groups) {
-      const int n_tile = static_cast<int>(u % nt);
+      const int n_tile = static_cast<int>(u % nt) * MC + static_cast<int>(MC == 2 ? pair_in_cl : 0u);
       const int m_tile = static_cast<int>((u / nt) % mt);
       const int ks = static_cast<int>(u / (static_cast<long long>(nt) * mt));
       const bool empty_k = (ks * p.kb_per_split >= total_kb);
@@ -467,7 +522,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
         if (p.epi_y && u + n_groups < units) {
           const long long un = u + n_groups;
           pf_row0 = static_cast<int>((un / nt) % mt) * kTileM + static_cast<int>(cta_rank) * kBM + ew * 32;
-          pf_col0 = static_cast<int>(un % nt) * p.BN;
+          pf_col0 = static_cast<int>(un % nt) * MC * p.BN;
         }
         if (p.d_bf16) epilogue_staged<true>(p, &map_d, stg, taddr, row_base, n_tile * p.BN, ks, empty_k, lane, -1, 0);
         else epilogue_staged<false>(p, &map_d, stg, taddr, row_base, n_tile * p.BN, ks, empty_k, lane, pf_row0, pf_col0);
@@ -521,7 +576,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) {  // the leader's issuer waits for the epilogue warps of both CTAs
-        if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+        if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), leader));
         else mbar_arrive(&tmem_empty[acc]);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -651,27 +706,81 @@ static int gemm_cta_group(int M, bool prep_epilogue, int sm_count) {
 // 128 x bn / 256 clocks) and the L2 -> shared-memory operand stream.  Measured (tools/gemm_sweep.py, 300k x 800 x 1024,
 // N tiles 128 / 160 / 208 / 256: 1.42 / 1.18 / 1.07 / 1.14 ms): the two-plane GEMMs run at the pace of that stream,
 // ≈ 30 bytes per clock and SM (8.5 TB/s over the chip), not of the tensor pipe — so tiles are chosen by bytes moved.
-static double kblock_cost(int bn, int cg, int b_mn) {
+static double kblock_cost(int bn, int cg, int mc, int b_mn) {
   const int bn_cta = bn / cg;
-  const double a_bytes = 2.0 * kBM * kBK * 2;
+  const double a_bytes = 2.0 * kBM * kBK * 2 / mc;  // multicast: each CTA fetches half of its A rows
   const double b_bytes = 2.0 * (b_mn ? ((bn_cta + 63) / 64) * kBK * 128 : bn_cta * kBK * 2);
   const double mma = 6.0 * bn, l2 = (a_bytes + b_bytes) / 30.0;
   return mma > l2 ? mma : l2;
 }
 
-static int pick_bn(int N, int cg, int b_mn) {
+struct GemmPlan {
+  int cg;       // CTAs per 128-row-pair tile: 2 = tcgen05 cta_group::2
+  int mc;       // 2: clusters of two pairs on neighbouring N tiles, A halves multicast
+  int bn;       // N tile
+  double cost;  // modelled SM clocks of one k-block over all tiles
+};
+
+// Clusters of four CTAs cannot use every SM (GPCs hold 16 / 18 / 20 SMs): the kernel reports what fits (132 of 148 on
+// B200); the plan charges the stranded SMs to the multicast variant.
+constexpr double kClusterOf4SmShare = 132.0 / 148.0;
+
+static GemmPlan plan_gemm(int M, int N, int b_mn, bool prep_epilogue, int sm_count, bool bf16_out = false) {
+  GemmPlan g{};
+  g.cg = gemm_cta_group(M, prep_epilogue, sm_count);
+  g.mc = 1;
+  const long long mt = (M + kBM * g.cg - 1) / (kBM * g.cg);
+  if (prep_epilogue) { g.bn = pick_bn_prep(N); g.cost = static_cast<double>(mt * ((N + g.bn - 1) / g.bn)) * g.cg * kblock_cost(g.bn, g.cg, 1, b_mn); return g; }
+  int forced_bn = 0;
   if (const char* v = getenv("RELGAT_GEMM_BN")) {  // experiment knob: N tile (multiple of 16, <= 256)
     const int bn = atoi(v);
-    if (bn >= 16 && bn <= 256 && bn % 16 == 0 && N > bn) return bn;
+    if (bn >= 16 && bn <= 256 && bn % 16 == 0 && N > bn) forced_bn = bn;
   }
-  if (N <= 256) return (N + 15) / 16 * 16;
-  int best = 256;
-  double best_cost = 0.0;
-  for (int bn = 256; bn >= 128; bn -= 16) {  // widest first: ties go to the wider tile
-    const double c = ((N + bn - 1) / bn) * kblock_cost(bn, cg, b_mn);
-    if (bn == 256 || c < best_cost * 0.999) { best = bn; best_cost = c; }
+  // Operand multicast over clusters of two pairs is OFF unless RELGAT_GEMM_MC=2: measured slower on every config-2
+  // shape (300k x 800 x 1024: 1.19 vs 1.07 ms; [dP|dS]^T X: 1.47 vs 1.22 ms) — the bytes each SM receives, not the bytes
+  // L2 sends, set the pace, so sharing the fetch saves nothing and clusters of four leave 16 of the 148 SMs idle.
+  bool mc_ok = false;
+  if (const char* v = getenv("RELGAT_GEMM_MC")) { mc_ok = atoi(v) == 2 && g.cg == 2 && sm_count >= 4; }
+  bool have = false;
+  auto consider = [&](int bn, int mc) {
+    const long long nt = (N + bn - 1) / bn;
+    if (mc == 2 && (nt % 2 != 0 || mt * (nt / 2) < 8)) return;  // pairs of N tiles; not worth a cluster launch for a handful of tiles
+    double c = static_cast<double>(mt * nt) * g.cg * kblock_cost(bn, g.cg, mc, b_mn);
+    if (mc == 2) c /= kClusterOf4SmShare;
+    if (!have || c < g.cost * 0.999) { have = true; g.bn = bn; g.mc = mc; g.cost = c; }
+  };
+  if (forced_bn) { if (mc_ok) consider(forced_bn, 2); consider(forced_bn, 1); return g; }
+  if (N <= 256) { consider((N + 15) / 16 * 16, 1); return g; }
+  // bf16 output: the epilogue's TMA store boxes are 32 columns wide, a 16-column tail would spill into the next tile
+  const int step = bf16_out ? 32 : 16;
+  for (int bn = 256; bn >= 128; bn -= step) {  // widest first: ties go to the wider tile
+    if (mc_ok) consider(bn, 2);
+    consider(bn, 1);
   }
-  return best;
+  return g;
+}
+
+// how many clusters of `cluster` CTAs of this kernel the device runs at once (cached per cluster size)
+template <int CG, int MC>
+static int max_active_clusters(int smem_bytes, int sm_count) {
+  static int cached = -1;
+  if (cached > 0) return cached;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(sm_count / (CG * MC) * (CG * MC)));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem_bytes);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG * MC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, gemm_bf16_tcgen05_kernel<CG, MC>, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = static_cast<int>(sm_count / (CG * MC) * (MC == 2 ? kClusterOf4SmShare : 1.0) + 0.5);
+    return n > 0 ? n : 1;  // not cached: the query may succeed later
+  }
+  cached = n;
+  return n;
 }
 
 }  // namespace relgat
@@ -729,8 +838,9 @@ static int gemm_launch(const void* a_hi, const void* a_lo, long long lda, int a_
   if (sm_count <= 0) sm_count = 148;
   // CTA pairs (cta_group::2, 256-row tiles) whenever there is more than one 128-row tile; the fused-prep epilogue keeps
   // the single-CTA form.  RELGAT_GEMM_CG=1 is the A/B knob.
-  const int cg = gemm_cta_group(M, epi != nullptr, sm_count);
-  p.BN = epi ? pick_bn_prep(N) : pick_bn(N, cg, b_mn ? 1 : 0);
+  const GemmPlan plan = plan_gemm(M, N, b_mn ? 1 : 0, epi != nullptr, sm_count, d_is_bf16 != 0);
+  const int cg = plan.cg, mc = plan.mc;
+  p.BN = plan.bn;
   p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
   p.split = a_lo ? 1 : 0;
   const int total_kb = (K + kBK - 1) / kBK;
@@ -781,7 +891,7 @@ static int gemm_launch(const void* a_hi, const void* a_lo, long long lda, int a_
   // K-major: matrix [MN rows, K cols], box rows = tile MN extent.  MN-major: matrix [K rows, MN cols], box rows = BK.
   const long long a_rows = p.a_mn ? K : M, a_cols = p.a_mn ? M : K;
   const long long b_rows = p.b_mn ? K : N, b_cols = p.b_mn ? N : K;
-  const int a_box = p.a_mn ? kBK : kBM, b_box = p.b_mn ? kBK : bn_cta;
+  const int a_box = p.a_mn ? kBK : (mc == 2 ? kBM / 2 : kBM), b_box = p.b_mn ? kBK : bn_cta;  // multicast: half tiles
   if ((rc = make_map(&ma_hi, a_hi, a_rows, a_cols, lda, a_box)) != RG_OK) return rc;
   if ((rc = make_map(&mb_hi, b_hi, b_rows, b_cols, ldb, b_box)) != RG_OK) return rc;
   if (p.split) {
@@ -798,28 +908,31 @@ static int gemm_launch(const void* a_hi, const void* a_lo, long long lda, int a_
     if (make_map_d(&md, d_out, d_is_bf16 != 0, M, N, ldd) == RG_OK) p.tma_store = 1;
   }
   const int tile_m = kBM * cg;
-  const long long units = static_cast<long long>((M + tile_m - 1) / tile_m) * ((N + p.BN - 1) / p.BN) * splits_k;
-  const int groups = static_cast<int>(units < sm_count / cg ? units : sm_count / cg);
+  const long long units = static_cast<long long>((M + tile_m - 1) / tile_m) * (((N + p.BN - 1) / p.BN) / mc) * splits_k;
   const int smem_bytes = stages * stage_bytes + 1024 + (p.staged ? kEpiStageBytes : 0);
   cudaError_t e;
   if (cg == 2) {
-    e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    auto kernel = mc == 2 ? gemm_bf16_tcgen05_kernel<2, 2> : gemm_bf16_tcgen05_kernel<2, 1>;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return cuda_status(e);
+    const int slots = mc == 2 ? max_active_clusters<2, 2>(smem_bytes, sm_count) : sm_count / 2;
+    const int groups = static_cast<int>(units < slots ? units : slots);
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(static_cast<unsigned>(groups * 2));
+    cfg.gridDim = dim3(static_cast<unsigned>(groups * cg * mc));
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = static_cast<size_t>(smem_bytes);
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;  // the two CTAs of a pair share one TPC
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = static_cast<unsigned>(cg * mc); attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<2>, ma_hi, ma_lo, mb_hi, mb_lo, md, p);
+    e = cudaLaunchKernelEx(&cfg, kernel, ma_hi, ma_lo, mb_hi, mb_lo, md, p);
     if (e != cudaSuccess) return cuda_status(e);
   } else {
-    e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    const int groups = static_cast<int>(units < sm_count ? units : sm_count);
+    e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return cuda_status(e);
-    gemm_bf16_tcgen05_kernel<1><<<groups, kGemmThreads, smem_bytes, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, md, p);
+    gemm_bf16_tcgen05_kernel<1, 1><<<groups, kGemmThreads, smem_bytes, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, md, p);
   }
   if ((e = cudaGetLastError()) != cudaSuccess) return cuda_status(e);
   if (splits_k > 1) {
@@ -843,14 +956,14 @@ extern "C" int relgat_gemm_tile_n(int N) { return N > 0 ? pick_bn_prep(N) : RG_E
 
 // Tile shape relgat_gemm_bf16 uses for an [M, N] output (b_mn: B stored [K, N]) and the modelled cost of one k-block
 // over all tiles (SM clocks; comparable between the two orientations of a weight-gradient GEMM).
-extern "C" long long relgat_gemm_plan(int M, int N, int b_mn, int* tile_m, int* tile_n) {
+extern "C" long long relgat_gemm_plan(int M, int N, int b_mn, int sm_count, int* tile_m, int* tile_n, int* slots) {
   if (M <= 0 || N <= 0) return RG_ERR_ARG;
-  const int cg = gemm_cta_group(M, false, 148);
-  const int bn = pick_bn(N, cg, b_mn ? 1 : 0);
-  if (tile_m) *tile_m = kBM * cg;
-  if (tile_n) *tile_n = bn;
-  const long long tiles = static_cast<long long>((M + kBM * cg - 1) / (kBM * cg)) * ((N + bn - 1) / bn);
-  return static_cast<long long>(tiles * cg * kblock_cost(bn, cg, b_mn ? 1 : 0));
+  if (sm_count <= 0) sm_count = 148;
+  const GemmPlan g = plan_gemm(M, N, b_mn ? 1 : 0, false, sm_count);
+  if (tile_m) *tile_m = kBM * g.cg;
+  if (tile_n) *tile_n = g.bn * g.mc;  // a unit of the multicast variant spans two N tiles
+  if (slots) *slots = g.mc == 2 ? static_cast<int>(sm_count / 4 * kClusterOf4SmShare + 0.5) : sm_count / g.cg;
+  return static_cast<long long>(g.cost);
 }
 
 // dX GEMM (A = dP [M, K] planes, B = W^T [N, K] planes, both K-major) with the backward prep of the layer below fused

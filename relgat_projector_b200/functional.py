@@ -40,6 +40,11 @@ SPARSE_BWD = os.environ.get("RELGAT_SPARSE_BWD", "1") != "0"
 # only (dense rows).
 COMPACT_BWD = os.environ.get("RELGAT_COMPACT_BWD", "1") != "0"
 
+# third-generation by-source pass (csrc/edge_bwd_src3.cu, fp32 mode): gathered rows as bulk async copies into a per-warp
+# shared-memory ring, rows [dPa | dS] WITHOUT the per-edge dz * A[rel] term; dP = dPa + dS·A is folded into the GEMMs
+# that consume the rows (fold_operands below).  1.41 -> 1.12 ms per launch at config 2.  RELGAT_SRC_V3=0: first generation.
+SRC_V3 = os.environ.get("RELGAT_SRC_V3", "1") != "0"
+
 _SIDE_STREAMS = {}
 
 
@@ -118,6 +123,27 @@ def presort_on_side_stream(ids: torch.Tensor, n_max: int):
         t.record_stream(main)
     ids.record_stream(side)
     return keys, perm, ev
+
+
+def fold_operands(A: torch.Tensor, Wp, WTp, H: int, F: int, R: int, d_in: int):
+    """GEMM operands that fold dP = dPa + dS·A_bd (A_bd [H*R, C]: block-diagonal attention vectors, row h*R + r holds
+    A[h, r, :] in columns h*F .. (h+1)*F) into the consumers of the rows [dPa | dS] the third-generation by-source pass
+    writes — parameters only, prepared once per step and layer in the forward:
+      * ``Abd``: planes of A_bd;  dW = dPaᵀX + A_bdᵀ (dSᵀX)  (weight_grad_gemm gives both products in one launch);
+      * ``Bext`` (layers with a dX): planes of [Wᵀ | (A_bd·W)ᵀ | 0] [d_in, Wd]:  dX = [dPa | dS] · [W ; A_bd·W]."""
+    C, HR = H * F, H * R
+    Wd = ops.ds_row_width(H, F, R)
+    Abd = torch.zeros((HR, C), dtype=torch.float32, device=A.device)
+    idx = torch.arange(H, device=A.device)
+    Abd.view(H, R, H, F)[idx, :, idx, :] = A
+    Abd_p = ops.split_bf16(Abd, True)
+    Bext = None
+    if WTp is not None:
+        AW = ops.gemm(Abd_p, False, Wp, True, HR, d_in, C)  # [H*R, d_in] = A_bd · W
+        AWt_p = ops.split_bf16(AW.t().contiguous(), True)
+        pad = [WTp[0].new_zeros((d_in, Wd - C - HR))] if Wd > C + HR else []
+        Bext = tuple(torch.cat([w_, a_] + pad, dim=1) for w_, a_ in zip(WTp, AWt_p))
+    return dict(Abd=Abd_p, Bext=Bext)
 
 
 def weight_grad_gemm(dPp, xp, Wd: int, d_in: int, rows: int, device) -> torch.Tensor:
@@ -276,8 +302,11 @@ class RelGATStackFunction(torch.autograd.Function):
                                                       feat_drop=dl.feat if dl else None, edge_drop=dl.edge if dl else None,
                                                       chunks=pl["fwd_chunks"] if prune else None,
                                                       src_row=pl["rank"] if prune else None)
+            fold = None
+            if SRC_V3 and USE_DS and with_lo and ops.src3_supported(P, F):
+                fold = fold_operands(A.detach(), Wp, WTp, H, F, gl.R, d_in)
             saved.append(dict(xp=planes, Wp=Wp, WTp=WTp, P=P, out=out, minv=minv, z=z, bias=bias, A=A.detach(),
-                              d_in=d_in, has_beta=beta is not None, drop=dl))
+                              d_in=d_in, has_beta=beta is not None, drop=dl, fold=fold))
             planes = act
         ctx.saved = saved
         ctx.graphs = graphs
@@ -343,9 +372,11 @@ class RelGATStackFunction(torch.autograd.Function):
                 G, t, hsum = ops.edge_bwd_prep(dY, s["out"], s["bias"], H, F, apply_elu=(l < L - 1), inplace=owned,
                                                g_bf16=not with_lo, nonzero_rows=nz_rows if l == L - 1 else None,
                                                feat_drop=dl.feat if dl else None)
+            fold = s["fold"] if (USE_DS and ops.src3_supported(G, F)) else None  # rows [dPa | dS], dS·A folded below
             _, dPp, dz = ops.edge_bwd_src(s["P"], G, s["A"], s["z"], s["minv"], t, g, H, F,
                                           want_fp32=False, want_planes=True, planes_lo=with_lo,
-                                          edge_drop=dl.edge if dl else None, want_ds=USE_DS, dst_nz=nz_bits)
+                                          edge_drop=dl.edge if dl else None, want_ds=USE_DS, dst_nz=nz_bits,
+                                          a_term=fold is None)
             if nz_bits is not None and l > 0:
                 nz_bits = ops.mark_sources(nz_bits, g)  # rows of dP, hence of dL/d out_{l-1}, that can be non-zero
             if table is not None and l == L - 1:
@@ -365,7 +396,12 @@ class RelGATStackFunction(torch.autograd.Function):
                 dW_ext = weight_grad_gemm(dPp, s["xp"], Wd, d_in, n_src, dY.device)
                 dw_ready = torch.cuda.Event()
                 dw_ready.record(main)
-                if l > 0 and fuse_prep:
+                dW = dW_ext[:C]
+                Tp = None
+                if fold is not None:
+                    Tp = ops.split_bf16(dW_ext[C:C + HR].contiguous(), with_lo)
+                    dW = dW + ops.gemm(fold["Abd"], True, Tp, True, C, d_in, HR)  # + A_bd^T (dS^T X)
+                if l > 0 and fuse_prep and fold is None:
                     # dX never reaches memory: the GEMM's epilogue applies ELU'(y), the dropout mask and the row sums
                     # of the layer below (what edge_bwd_prep would do in a second pass over dX and y)
                     below = ctx.saved[l - 1]
@@ -374,10 +410,14 @@ class RelGATStackFunction(torch.autograd.Function):
                                                apply_elu=True, feat_drop=bd.feat if bd else None)
                     dX = prepped[0]
                 elif l > 0 or ctx.x0_needs_grad:
-                    dX = ops.gemm(dP_c, False, s["WTp"], False, n_src, d_in, C)
+                    if fold is not None:  # dX = [dPa | dS] · [W ; A_bd·W]
+                        dX = ops.gemm(dPp, False, fold["Bext"], False, n_src, d_in, Wd)
+                    else:
+                        dX = ops.gemm(dP_c, False, s["WTp"], False, n_src, d_in, C)
 
-                def tail():
-                    Tp = ops.split_bf16(dW_ext[C:C + HR].contiguous(), with_lo)
+                def tail(Tp=Tp):
+                    if Tp is None:
+                        Tp = ops.split_bf16(dW_ext[C:C + HR].contiguous(), with_lo)
                     dA_full = ops.gemm(Tp, False, s["Wp"], False, HR, C, d_in)
                     dA_ = torch.stack([dA_full[h * g.R:(h + 1) * g.R, h * F:(h + 1) * F] for h in range(H)])
                     return dA_, (ops.edge_bwd_beta(hsum, g, H) if s["has_beta"] else None)
@@ -393,7 +433,7 @@ class RelGATStackFunction(torch.autograd.Function):
                             tns.record_stream(main)
                 else:
                     dA, dbeta = tail()
-                grads[3 * l], grads[3 * l + 1], grads[3 * l + 2] = dW_ext[:C], dA, dbeta
+                grads[3 * l], grads[3 * l + 1], grads[3 * l + 2] = dW, dA, dbeta
                 if l > 0 or ctx.x0_needs_grad:
                     dY, owned = dX, True
                 if l == 0 and TAIL_ON_SIDE:
@@ -445,11 +485,12 @@ def _backward_compact(ctx, table: torch.Tensor, keys: torch.Tensor) -> List[Opti
                                            compact_rows=prev_rows, feat_drop=dl.feat if dl else None)
             clear_rows = prev_rows
         dPp = None
+        fold = s["fold"] if (n_s > 0 and ops.src3_supported(G, F) and ops.src3_supported(s["P"], F)) else None
         if n_s > 0:
             _, dPp, _ = ops.edge_bwd_src(s["P"], G, s["A"], s["z"], s["minv"], t, g, H, F, want_fp32=False,
                                          want_planes=True, planes_lo=True, edge_drop=dl.edge if dl else None,
                                          want_ds=True, dst_nz=pl["dst_bits"], src_rows=(pl["rank"], n_s),
-                                         p_compact=pruned)
+                                         p_compact=pruned, a_term=fold is None)
         ops.zero_rows(G, clear_rows)  # the table's rows are consumed: all-zero again for the next step
         _return_zero_table(G)
         if n_s == 0:  # no edge reaches a non-zero row: this layer's and every lower layer's gradients are zero
@@ -463,12 +504,18 @@ def _backward_compact(ctx, table: torch.Tensor, keys: torch.Tensor) -> List[Opti
         xp_c = s["xp"] if pruned else tuple(None if p_ is None else ops.gather_plane_rows(p_, rows) for p_ in s["xp"])
         d_in = s["d_in"]
         dW_ext = weight_grad_gemm(dPp, xp_c, dPp[0].size(1), d_in, n_s, dev)
-        if l > 0:
-            dX_c = ops.gemm(tuple(p_[:, :C] for p_ in dPp), False, s["WTp"], False, n_s, d_in, C)
-            prev_rows = rows
         Tp = ops.split_bf16(dW_ext[C:C + HR].contiguous(), with_lo)
+        dW = dW_ext[:C]
+        if fold is not None:  # rows are [dPa | dS]: dW += A_bd^T (dS^T X), dX = [dPa | dS] · [W ; A_bd·W]
+            dW = dW + ops.gemm(fold["Abd"], True, Tp, True, C, d_in, HR)
+        if l > 0:
+            if fold is not None:
+                dX_c = ops.gemm(dPp, False, fold["Bext"], False, n_s, d_in, dPp[0].size(1))
+            else:
+                dX_c = ops.gemm(tuple(p_[:, :C] for p_ in dPp), False, s["WTp"], False, n_s, d_in, C)
+            prev_rows = rows
         dA_full = ops.gemm(Tp, False, s["Wp"], False, HR, C, d_in)
-        grads[3 * l] = dW_ext[:C]
+        grads[3 * l] = dW
         grads[3 * l + 1] = torch.stack([dA_full[h * g.R:(h + 1) * g.R, h * F:(h + 1) * F] for h in range(H)])
         grads[3 * l + 2] = ops.edge_bwd_beta(hsum, g, H) if s["has_beta"] else None
     return grads

@@ -199,15 +199,17 @@ def gemm_dx_prep(dP: Planes, WT: Planes, M: int, N: int, K: int, y: torch.Tensor
     return G, t, hsum
 
 
-def gemm_plan(M: int, N: int, b_mn: bool = True):
-    """(cost, tile_m, tile_n) of the tcgen05 GEMM for an [M, N] output: rows per tile (256 when it runs as CTA pairs),
-    the N tile the kernel picks, and the modelled cost of one k-block over all tiles (L2 -> shared-memory bytes or MMA
-    clocks, whichever is slower) — comparable between the two orientations of a weight-gradient GEMM."""
-    tm, tn = ctypes.c_int(0), ctypes.c_int(0)
-    cost = int(_lib.load().relgat_gemm_plan(int(M), int(N), int(b_mn), ctypes.byref(tm), ctypes.byref(tn)))
+def gemm_plan(M: int, N: int, b_mn: bool = True, sms: int = 148):
+    """(cost, tile_m, tile_n, slots) of the tcgen05 GEMM for an [M, N] output: rows and columns of one work unit (256
+    rows when it runs as CTA pairs; two N tiles when clusters of two pairs multicast their shared A rows), the units
+    in flight at once, and the modelled cost of one k-block over all tiles (L2 -> shared-memory bytes or MMA clocks,
+    whichever is slower) — comparable between the two orientations of a weight-gradient GEMM."""
+    tm, tn, sl = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+    cost = int(_lib.load().relgat_gemm_plan(int(M), int(N), int(b_mn), int(sms), ctypes.byref(tm), ctypes.byref(tn),
+                                            ctypes.byref(sl)))
     if cost < 0:
         _lib.check(cost, "relgat_gemm_plan")
-    return cost, tm.value, tn.value
+    return cost, tm.value, tn.value, sl.value
 
 
 def gemm_cost_model(M: int, N: int) -> float:
@@ -218,11 +220,10 @@ def gemm_cost_model(M: int, N: int) -> float:
 
 def pick_splits_k(M: int, N: int, K: int, device) -> int:
     """Split-K factor for GEMMs with few output tiles and a long reduction (the dW GEMMs): the one (<= 16) that fills
-    the waves of the persistent grid (one CTA, or one CTA pair, per tile) best, smaller factors winning ties."""
-    _, tm, bn = gemm_plan(M, N, True)
-    tiles = (-(-M // tm)) * (-(-N // bn))
+    the waves of the persistent grid (one CTA, CTA pair or cluster per work unit) best, smaller factors winning ties."""
+    _, tm, tn, slots = gemm_plan(M, N, True, sm_count(device))
+    tiles = (-(-M // tm)) * (-(-N // tn))
     kb = (K + 63) // 64
-    slots = max(1, sm_count(device) // (tm // 128))
     if tiles >= 4 * slots or kb < 16:
         return 1
     best, best_eff = 1, 0.0
@@ -448,10 +449,17 @@ def ds_row_width(H: int, F: int, R: int) -> int:
     return (H * F + H * R + 7) // 8 * 8
 
 
+def src3_supported(P: torch.Tensor, F: int) -> bool:
+    """Layouts the third-generation by-source kernel covers: fp32 rows, 128-bit vectors, 16-byte aligned row starts."""
+    return (P.dtype == torch.float32 and F % 4 == 0 and P.dim() == 2 and P.stride(1) == 1 and P.stride(0) % 4 == 0
+            and P.data_ptr() % 16 == 0)
+
+
 def edge_bwd_src(P, G, A, z, minv, t, g: GraphIndex, H: int, F: int, want_fp32: bool = True,
                  want_planes: bool = False, planes_lo: bool = True, edge_drop: Optional["DropMask"] = None,
                  want_ds: bool = False, dst_nz: Optional[torch.Tensor] = None,
-                 src_rows: Optional[Tuple[torch.Tensor, int]] = None, p_compact: bool = False):
+                 src_rows: Optional[Tuple[torch.Tensor, int]] = None, p_compact: bool = False,
+                 a_term: bool = True):
     """Returns (dP fp32 or None, dP planes or None, dz [E,H] or None).  ``want_ds``: the rows are
     ``ds_row_width`` wide, columns H*F + h*R + r hold dS and dz is not written.
     ``dst_nz`` (want_ds only): row bitmap from ``mark_rows`` / ``mark_sources`` — rows of G outside it are exact zeros
@@ -489,6 +497,23 @@ def edge_bwd_src(P, G, A, z, minv, t, g: GraphIndex, H: int, F: int, want_fp32: 
             raise ValueError("dst_nz needs want_ds (the dz output of the plain variant is not written for skipped edges)")
         if dst_nz.dtype != torch.int32 or dst_nz.device != dev or dst_nz.numel() < (g.N + 31) // 32:
             raise ValueError("dst_nz must be an int32 bitmap of ceil(N / 32) words on the feature device")
+    if not a_term:
+        # third generation (csrc/edge_bwd_src3.cu): rows [dPa | dS] WITHOUT the dz * A[rel] term — the caller folds
+        # dS·A into the GEMMs that consume the rows; gathered rows travel as bulk async copies, 4 deep per warp
+        if not want_ds or not src3_supported(P, F) or not src3_supported(G, F):
+            raise ValueError("a_term=False needs want_ds and fp32 rows with F % 4 == 0 (see src3_supported)")
+        with _on(dev):
+            rc = _lib.load().relgat_layer_bwd_src3(
+                _lib.ptr(P), P.stride(0), _lib.ptr(G), _lib.ptr(z), _lib.ptr(minv), _lib.ptr(t),
+                _lib.ptr(g.colptr), _lib.ptr(g.csc_slot), _lib.ptr(g.csc_dst), _lib.ptr(g.csc_rel),
+                _lib.ptr(ck.chunks), ck.n_chunks, _lib.ptr(ck.parts), ck.n_parts,
+                _lib.ptr(ck.long_node), _lib.ptr(ck.long_part_ptr), ck.n_long, _lib.ptr(part_acc),
+                _lib.ptr(dP), _lib.ptr(hi), _lib.ptr(lo), *_edge_mask_args(edge_drop, g.E, H),
+                _lib.ptr(dst_nz), _lib.ptr(rank), int(p_compact), W, H, F, g.R, sm_count(dev),
+                _lib.ptr(_work_counter(dev)), _stream(P))
+        _lib.check(rc, "relgat_layer_bwd_src3")
+        _count(2 if ck.n_long else 1)
+        return dP, ((hi, lo) if want_planes else None), dz
     if (SRC_V2 and want_ds and want_planes and not want_fp32 and P.dtype == torch.float32 and F % 4 == 0
             and P.stride(0) % 4 == 0 and dst_nz is None):
         # second-generation kernel of the training path (coefficient pre-pass + lean edge loop)

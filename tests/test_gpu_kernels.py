@@ -89,6 +89,20 @@ def test_gemm_all_layouts(dev, a_mn, b_mn, split):
         assert err < tol, (M, N, K, a_mn, b_mn, split, err)
 
 
+@pytest.mark.parametrize("M,N,K", [(1000, 800, 1024), (700, 208, 136), (3000, 1000, 200)])
+def test_gemm_bf16_output_tiles_do_not_overlap(dev, M, N, K):
+    """bf16 output (the bf16 feature-storage mode): N tiles whose width is not a multiple of the 32-column store box
+    must not spill into their neighbours."""
+    from relgat_projector_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(21)
+    A = torch.randn((M, K), generator=g, device=dev)
+    B = torch.randn((N, K), generator=g, device=dev)
+    for split in (False, True):
+        D = ops.gemm(ops.split_bf16(A, split), False, ops.split_bf16(B, split), False, M, N, K, out_dtype=torch.bfloat16)
+        ref = (A.double() @ B.double().t()) if split else (A.bfloat16().double() @ B.bfloat16().double().t())
+        assert rel_err(D.float().cpu().numpy(), ref.cpu().numpy()) < 1e-2  # bf16 rounding of the output
+
+
 def test_split_planes_reconstruct_fp32(dev):
     from relgat_projector_b200 import ops
     x = torch.randn(1000, 77, device=dev) * 37.0
@@ -173,6 +187,36 @@ def test_edge_forward_and_backward_vs_closed_form(dev, n, e, r, H, F, isolated, 
     dA2, dbeta2 = ops.edge_bwd_rel(Pd, dz, hsum, g, H, F)
     assert torch.equal(out, out2) and torch.equal(alpha, alpha2) and torch.equal(dP, dP2)
     assert torch.equal(dA, dA2) and torch.equal(dbeta, dbeta2)
+
+
+@pytest.mark.parametrize("n,e,r,H,F,isolated,hub", [s_ for s_ in LAYER_SHAPES if s_[4] % 4 == 0])
+def test_bwd_src_third_generation_matches_first(dev, n, e, r, H, F, isolated, hub):
+    """relgat_layer_bwd_src3 (bulk-copy ring, no attention-vector term): its dS columns equal the first generation's,
+    its dPa rows equal the first generation's dP minus dS·A (fp32 rows and bf16 planes), bitwise reproducible."""
+    from relgat_projector_b200 import ops
+    from relgat_projector_b200.graph import GraphIndex
+    rng = np.random.default_rng(e + H + 1)
+    src, dst, rel = _graph(rng, n, e, r, isolated, hub)
+    g = GraphIndex(torch.from_numpy(np.stack([src, dst])).to(dev), torch.from_numpy(rel).to(dev), n, r)
+    Pd = torch.from_numpy(rng.standard_normal((n, H * F)).astype(np.float32)).to(dev)
+    Ad = torch.from_numpy((rng.standard_normal((H, r, F)) / np.sqrt(F)).astype(np.float32)).to(dev)
+    bd = torch.from_numpy((rng.standard_normal(r) * 0.1).astype(np.float32)).to(dev)
+    out, _, _, z, minv, bias = ops.edge_fwd(Pd, Ad, bd, g, H, F)
+    Gd = torch.from_numpy(rng.standard_normal((n, H * F)).astype(np.float32)).to(dev)
+    G, t, _ = ops.edge_bwd_prep(Gd, out, bias, H, F, apply_elu=False)
+    C = H * F
+    ref, _, _ = ops.edge_bwd_src(Pd, G, Ad, z, minv, t, g, H, F, want_fp32=True, want_ds=True)
+    got, planes, _ = ops.edge_bwd_src(Pd, G, Ad, z, minv, t, g, H, F, want_fp32=True, want_planes=True, want_ds=True,
+                                      a_term=False)
+    dS = ref[:, C:C + H * r].double()
+    assert rel_err(got[:, C:C + H * r].cpu().numpy(), dS.cpu().numpy()) < 1e-5 or not e
+    a_part = torch.einsum("nhr,hrf->nhf", dS.view(n, H, r), Ad.double()).reshape(n, C)
+    want = ref[:, :C].double() - a_part
+    assert rel_err(got[:, :C].cpu().numpy(), want.cpu().numpy()) < FP32_TOL or not e
+    rec = planes[0].float() + planes[1].float()
+    assert rel_err(rec[:, :C + H * r].cpu().numpy(), got[:, :C + H * r].cpu().numpy()) < 2e-5 or not e
+    got2, _, _ = ops.edge_bwd_src(Pd, G, Ad, z, minv, t, g, H, F, want_fp32=True, want_ds=True, a_term=False)
+    assert torch.equal(got[:, :C + H * r], got2[:, :C + H * r])
 
 
 def test_bwd_prep_elu_gradient(dev):

@@ -32,7 +32,7 @@ def main():
     A = torch.randn((H, cfg["R"], F), generator=gen, device=dev) / F ** 0.5
     beta = torch.randn((cfg["R"],), generator=gen, device=dev) * 0.1
     dY = torch.randn((N, H * F), generator=gen, device=dev)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
     for it in range(args.iters):
         ev[0].record()
         out, act, _, z, minv, bias = ops.edge_fwd(P, A, beta, g, H, F, want_act=True, apply_elu=True, act_lo=not args.bf16)
@@ -47,9 +47,12 @@ def main():
         ops.edge_bwd_src(P, G, A, z, minv, t, g, H, F, want_fp32=False, want_planes=True, planes_lo=not args.bf16,
                          want_ds=True)  # the training path: dS columns; RELGAT_SRC_V2=0 selects the first-generation kernel
         ev[5].record()
+        if not args.bf16:  # third generation: bulk-copy ring, rows [dPa | dS] (RELGAT_SRC3_DEPTH = ring depth)
+            ops.edge_bwd_src(P, G, A, z, minv, t, g, H, F, want_fp32=False, want_planes=True, want_ds=True, a_term=False)
+        ev[6].record()
         torch.cuda.synchronize()
-        print("iter", it, "fwd %.3f prep %.3f src %.3f rel %.3f src(dS) %.3f ms"
-              % tuple(ev[i].elapsed_time(ev[i + 1]) for i in range(5)))
+        print("iter", it, "fwd %.3f prep %.3f src %.3f rel %.3f src(dS) %.3f src3 %.3f ms"
+              % tuple(ev[i].elapsed_time(ev[i + 1]) for i in range(6)))
 
 
 if __name__ == "__main__":
