@@ -342,7 +342,9 @@ def test_peer_table_partition_lockstep_equals_whole_graph(dev, world, blocks):
                                                x0_needs_grad=True) for k in range(world)])
     for p, (dx, _) in zip(parts, res):
         # a source's out-edges are summed in the order of the renumbered destinations: rounding-level difference
-        assert rel_err(dx.cpu().numpy(), ref_grads[0][p.lo:p.hi].cpu().numpy()) < 1e-5
+        # (the unpartitioned stack folds dS·A into its GEMMs, the partitioned path adds it per edge: same value,
+        # different rounding)
+        assert rel_err(dx.cpu().numpy(), ref_grads[0][p.lo:p.hi].cpu().numpy()) < 3e-5
     for i in range(len(params)):
         total = sum(res[k][1][i] for k in range(world))
         assert rel_err(total.cpu().numpy(), ref_grads[1 + i].cpu().numpy()) < FP32_TOL, i
@@ -481,7 +483,7 @@ def test_peer_table_sparse_last_layer_backward(dev):
             gens.append(RP.backward_steps(p, dx, saved[parts.index(p)], True, x0_needs_grad=True))
         res = RP.drive_lockstep(gens)
         for p, (dxk, _) in zip(parts, res):
-            assert rel_err(dxk.cpu().numpy(), ref[0][p.lo:p.hi].cpu().numpy()) < 1e-5
+            assert rel_err(dxk.cpu().numpy(), ref[0][p.lo:p.hi].cpu().numpy()) < 3e-5  # see above
         for i in range(len(params)):
             total = sum(res[k][1][i] for k in range(world))
             assert rel_err(total.cpu().numpy(), ref[1 + i].cpu().numpy()) < FP32_TOL, (i, sparse)
