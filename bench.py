@@ -119,6 +119,7 @@ class KernelProfiler:
         self.ops = ops
         self.records = []  # (name, tag, start, end)
         self.orig = {}
+        self.main = torch.cuda.current_stream()
 
     def __enter__(self):
         for name in self.NAMES:
@@ -135,10 +136,11 @@ class KernelProfiler:
             if name == "gemm_dx_prep":
                 tag = f"gemm[M={a[2]},N={a[3]},K={a[4]},kk+prep]"
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            side = torch.cuda.current_stream() != self.main
             s.record()
             out = fn(*a, **kw)
             e.record()
-            self.records.append((name, tag, s, e))
+            self.records.append((name, tag + (" (side stream)" if side else ""), s, e))
             return out
         return wrapped
 
@@ -436,7 +438,7 @@ def main():
                           gat_out_dim=cfg["F"], gat_heads=cfg["H"], dropout=0.0, gat_num_layers=cfg["L"],
                           project_to_input_size=cfg["proj"], projection_layers=2, precision=args.precision).to(dev)
     model.train()
-    opt = torch.optim.Adam(model.parameters(), lr=2e-4)
+    opt = torch.optim.Adam(model.parameters(), lr=2e-4, fused=True)  # the reference trainer's Adam (trainer:265); torch's single-kernel implementation
     rank_loss = L.RelGATLoss("margin", None, 1.0, None, {})
     b, k = cfg["B"], cfg["K"]
     gen = torch.Generator().manual_seed(42)
@@ -517,6 +519,11 @@ def main():
             ent["tensor_flops"] = flops
             ent["tflops"] = round(flops / (d["avg_ms"] * 1e-3) / 1e12, 1)
             ent["frac_tensor"] = round(ent["tflops"] / peaks["tflops"], 4)
+        if tag.endswith("(side stream)"):
+            # parameter-only operand prep (fold_operands) launched beside the layer's GEMM: its elapsed time is the
+            # big kernel's, not its own (isolated: 8-30 us per launch, profiles/r02_bench_c2_fp32_src3.json)
+            ent["overlapped"] = True
+            ent.pop("tflops", None); ent.pop("frac_tensor", None)
         if not RFn.USE_DS and (d["kernel"] == "edge_bwd_rel" or (d["kernel"] == "gemm" and tag.endswith("mnmn]"))):
             # the by-relation pass runs on a side stream beside the dW GEMM: both elapsed times include
             # the other's interference (isolated: 0.69 ms at 96 % of HBM peak; 1.14 ms) — not "dominant"
@@ -534,18 +541,24 @@ def main():
     # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this same command
     # (profiles/r02_ncu_traffic.json; a number taken under a profiler in an earlier call, labelled as such — ncu cannot
     # run inside a timed benchmark); only meaningful for the configuration it was taken on
-    tpath = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
-    sub = {"edge_fwd": "edge_fwd_kernel", "edge_bwd_src": "bwd_src_kernel", "edge_bwd_rel": "bwd_rel_kernel",
-           "edge_bwd_prep": "bwd_prep_kernel", "gemm": "gemm_bf16_tcgen05"}.get(top_tag.split("[")[0])
-    if sub and cfg_name == "c2" and args.precision == "fp32" and os.path.exists(tpath):
+    # (the edge kernels: the capture of the same launches at the same shapes by tools/profile_layer.py)
+    src3 = RFn.SRC_V3 and RFn.USE_DS
+    sub = {"edge_fwd": "edge_fwd_kernel", "edge_bwd_src": "bwd_src3_kernel" if src3 else "bwd_src_kernel",
+           "edge_bwd_rel": "bwd_rel_kernel", "edge_bwd_prep": "bwd_prep_kernel",
+           "gemm": "gemm_bf16_tcgen05"}.get(top_tag.split("[")[0])
+    for tfile in ("r02_ncu_src3_traffic.json", "r02_ncu_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tfile)
+        if roofline["traffic"] is not None or not (sub and cfg_name == "c2" and args.precision == "fp32" and os.path.exists(tpath)):
+            continue
         with open(tpath) as f:
             for kname, rec in json.load(f).items():
                 if sub in kname:
                     v = rec["dram_bytes_per_launch"]
                     roofline["traffic"] = int(sum(v) / len(v))
-                    roofline["traffic_source"] = ("profiles/r02_ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of "
-                                                  "this kernel in the committed ncu --set full capture of this command "
+                    roofline["traffic_source"] = (f"profiles/{tfile}: dram__bytes_read.sum + dram__bytes_write.sum of "
+                                                  "this kernel in the committed ncu --set full capture of the same launch "
                                                   "(not measured in this run)")
+                    break
     sbytes = step_bytes_survey(cfg, E, args.precision)
     step_roof = {"algorithmic_bytes_per_step": sbytes, "achieved_gbs": round(sbytes / (ms * 1e-3) / 1e9, 1),
                  "frac_of_hbm_peak": round(sbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
@@ -607,7 +620,7 @@ def main():
                               gat_out_dim=cfg["F"], gat_heads=cfg["H"], dropout=0.0, gat_num_layers=cfg["L"],
                               project_to_input_size=cfg["proj"], projection_layers=2, precision="bf16").to(dev)
         model.train()
-        opt = torch.optim.Adam(model.parameters(), lr=2e-4)
+        opt = torch.optim.Adam(model.parameters(), lr=2e-4, fused=True)  # the reference trainer's Adam (trainer:265); torch's single-kernel implementation
         for i in range(3):
             train_step(*dev_batches[i % n_pool])
         ms_alt = timed(lambda i: train_step(*dev_batches[i % n_pool]), max(args.steps // 2, 5))
@@ -625,7 +638,7 @@ def main():
                               gat_out_dim=cfg["F"], gat_heads=cfg["H"], dropout=0.3, gat_num_layers=cfg["L"],
                               project_to_input_size=cfg["proj"], projection_layers=2, precision=args.precision).to(dev)
         model.train()
-        opt = torch.optim.Adam(model.parameters(), lr=2e-4)
+        opt = torch.optim.Adam(model.parameters(), lr=2e-4, fused=True)  # the reference trainer's Adam (trainer:265); torch's single-kernel implementation
         for i in range(3):
             train_step(*dev_batches[i % n_pool])
         ms_drop = timed(lambda i: train_step(*dev_batches[i % n_pool]), max(args.steps // 2, 5))
@@ -656,6 +669,7 @@ def main():
         "e2e": {"value": E / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
+        "optimizer": "torch.optim.Adam(lr=2e-4, fused=True): the reference trainer's optimizer (trainer/relgat_projector.py:265) in torch's single-kernel implementation",
         "roofline": roofline, "step_roofline": step_roof, "kernels": kernels, "cpu_baseline": cpu,
         "alt_precision": alt, "training_dropout": drop_rec, "exact_sparse_backward": sparse_rec, "receptive_field": rf_rec,
     }

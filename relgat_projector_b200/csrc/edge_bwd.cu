@@ -18,6 +18,7 @@
 namespace relgat {
 
 constexpr int kBwdWarps = 4;
+constexpr long long kPrepBlocks = 148 * 4;  // resident blocks of the grid-stride prep kernel (4 x 128 threads per SM)
 
 // ------------------------------------------------------------------------------------
 // bwd_prep
@@ -44,27 +45,41 @@ template <typename TG, int V>
 __global__ void __launch_bounds__(kBwdWarps * 32) bwd_prep_kernel(const PrepArgs<TG, V> a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int groups = a.H / a.hg;
-  const long long task = static_cast<long long>(blockIdx.x) * kBwdWarps + warp;
-  if (task >= static_cast<long long>(a.N) * groups) return;
+  const long long n_tasks = static_cast<long long>(a.N) * groups;
+  // grid-stride over (row, head-group) tasks: a capped grid of resident warps streams the table (one short-lived block
+  // per four rows — 75 k blocks at config 2 — ran at 0.68 of the copy bandwidth)
+  for (long long task = static_cast<long long>(blockIdx.x) * kBwdWarps + warp; task < n_tasks;
+       task += static_cast<long long>(gridDim.x) * kBwdWarps) {
   const int jt = static_cast<int>(task / groups);
   const int g = static_cast<int>(task - static_cast<long long>(jt) * groups);
   const long long j = a.row_ids ? __ldg(a.row_ids + jt) : jt;
   // in-place dropout scaling must touch a row once: a row named twice (adjacent in the sorted list) is skipped
   if (a.row_ids && a.drop_bits && static_cast<const void*>(a.G) == static_cast<const void*>(a.dY) && jt > 0 &&
       __ldg(a.row_ids + jt - 1) == j)
-    return;
+    continue;
   const LaneMap lm = make_lane_map<V>(lane, g, a.hg, a.F);
   const long long row = j * a.H * a.F + lm.head_off;
   const long long row_y = a.dy_compact ? static_cast<long long>(jt) * a.H * a.F + lm.head_off : row;
   const float b = a.bias ? __ldg(a.bias + j) : 0.f;
   float tt = 0.f, hs = 0.f;
+  // every load of the row first (2 x KMAX 128-bit requests in flight per lane), then the arithmetic: with the loads
+  // issued pair by pair inside the loop the pass ran at 0.68 of the copy bandwidth (a warp serves one row and leaves)
+  float dyv[max_vec<V>()][V], ov[max_vec<V>()][V];
 #pragma unroll
   for (int k = 0; k < max_vec<V>(); ++k) {
     const int q = lm.sub + lm.lph * k;
     if (q < lm.vph) {
-      float dy[V], o[V], ms[V];
-      RowVec<float, V>::load_stream(a.dY + row_y + q * V, dy);
-      RowVec<float, V>::load_stream(a.out + row + q * V, o);
+      RowVec<float, V>::load_stream(a.dY + row_y + q * V, dyv[k]);
+      RowVec<float, V>::load_stream(a.out + row + q * V, ov[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < max_vec<V>(); ++k) {
+    const int q = lm.sub + lm.lph * k;
+    if (q < lm.vph) {
+      float ms[V];
+      float (&dy)[V] = dyv[k];
+      float (&o)[V] = ov[k];
 #pragma unroll
       for (int v = 0; v < V; ++v) ms[v] = 1.f;
       if (a.drop_bits) keep_scale<V>(a.drop_bits + j * a.drop_words, lm.head_off + q * V, a.drop_scale, ms);
@@ -73,7 +88,8 @@ __global__ void __launch_bounds__(kBwdWarps * 32) bwd_prep_kernel(const PrepArgs
         // ELU'(x) = 1 (x > 0) else exp(x)  (reference model.py:286-287, torch ELU alpha = 1)
         // with dropout: y = out*ms is what was stored and activated; G = d/d out = dy*ELU'(y)*ms and
         // <G, out - b> = sum dy*ELU'(y)*(y - b*ms)
-        const float gy = a.apply_elu ? (o[v] > 0.f ? dy[v] : dy[v] * expf(o[v])) : dy[v];
+        // (MUFU exp: ncu counted ~1050 warp instructions per row with the library expf — issue-bound, 0.57 of DRAM peak)
+        const float gy = a.apply_elu ? (o[v] > 0.f ? dy[v] : dy[v] * fast_exp(o[v])) : dy[v];
         float gg = gy * ms[v];
         if (sizeof(TG) == 2) gg = bf16_round(gg);  // t / hsum consistent with the stored (rounded) G
         dy[v] = gg;
@@ -90,6 +106,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32) bwd_prep_kernel(const PrepArgs
   if (lm.sub == 0) {
     a.t[j * a.H + lm.hh] = tt;
     a.hsum[j * a.H + lm.hh] = hs;
+  }
   }
 }
 
@@ -250,6 +267,16 @@ static int launch_tasks(K kernel, const Args& a, long long tasks, cudaStream_t s
   return cuda_status(cudaGetLastError());
 }
 
+// grid-stride kernels: at most `cap` blocks
+template <typename K, typename Args>
+static int launch_tasks_capped(K kernel, const Args& a, long long tasks, long long cap, cudaStream_t s) {
+  if (tasks == 0) return RG_OK;
+  long long blocks = (tasks + kBwdWarps - 1) / kBwdWarps;
+  if (blocks > cap) blocks = cap;
+  kernel<<<static_cast<unsigned>(blocks), kBwdWarps * 32, 0, s>>>(a);
+  return cuda_status(cudaGetLastError());
+}
+
 static inline bool al16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; }
 
 }  // namespace relgat
@@ -309,7 +336,7 @@ extern "C" int relgat_layer_bwd_prep(const float* dY, const float* out, const fl
     if (!hg) return RG_ERR_SHAPE;
     PrepArgs<__nv_bfloat16, 8> a{dY, out, bias, static_cast<__nv_bfloat16*>(G), t, hsum, rows, H, F, hg, apply_elu, row_ids, drop_bits, drop_words, drop_scale,
                                       static_cast<__nv_bfloat16*>(G_export_bf16), dy_compact};
-    return launch_tasks(bwd_prep_kernel<__nv_bfloat16, 8>, a, static_cast<long long>(rows) * (H / hg), s);
+    return launch_tasks_capped(bwd_prep_kernel<__nv_bfloat16, 8>, a, static_cast<long long>(rows) * (H / hg), kPrepBlocks, s);
   }
   float* Gf = static_cast<float*>(G);
   if (F % 4 == 0 && al16(dY) && al16(out) && al16(G)) {
@@ -317,13 +344,13 @@ extern "C" int relgat_layer_bwd_prep(const float* dY, const float* out, const fl
     if (!hg) return RG_ERR_SHAPE;
     PrepArgs<float, 4> a{dY, out, bias, Gf, t, hsum, rows, H, F, hg, apply_elu, row_ids, drop_bits, drop_words, drop_scale,
                                       static_cast<__nv_bfloat16*>(G_export_bf16), dy_compact};
-    return launch_tasks(bwd_prep_kernel<float, 4>, a, static_cast<long long>(rows) * (H / hg), s);
+    return launch_tasks_capped(bwd_prep_kernel<float, 4>, a, static_cast<long long>(rows) * (H / hg), kPrepBlocks, s);
   }
   const int hg = pick_heads_per_warp(H, F, 1);
   if (!hg) return RG_ERR_SHAPE;
   PrepArgs<float, 1> a{dY, out, bias, Gf, t, hsum, rows, H, F, hg, apply_elu, row_ids, drop_bits, drop_words, drop_scale,
                                       static_cast<__nv_bfloat16*>(G_export_bf16), dy_compact};
-  return launch_tasks(bwd_prep_kernel<float, 1>, a, static_cast<long long>(rows) * (H / hg), s);
+  return launch_tasks_capped(bwd_prep_kernel<float, 1>, a, static_cast<long long>(rows) * (H / hg), kPrepBlocks, s);
 }
 
 // dP rows of split sources: ordered sum of their parts.

@@ -55,6 +55,11 @@ struct GemmParams {
   int epi_elu;           // act = ELU, else identity
   int dbg_epilogue;      // experiments (RELGAT_GEMM_EPI): 0 normal, 1 = no global stores, 2 = no epilogue work at all
   int tma_store;         // 1: the staged blocks leave shared memory through TMA bulk stores (map_d), not st.global
+  // N tiles per work unit (1 or 2).  With 2 the unit is 256 (128) rows x 2·BN columns: both tiles use the SAME A stage —
+  // per k-block a CTA receives (128 + 2·BN/cg) operand rows for two tiles' MMAs instead of 2·(128 + BN/cg) — and their
+  // accumulators sit side by side in tensor memory (2 x <=256 columns = all of it: the epilogue of a unit is no longer
+  // hidden behind the next unit's main loop).
+  int nt_unit;
 };
 
 constexpr int kEpiStageBytes = 4 * 32 * 64;  // per epilogue warp: 32 rows x 64 bytes
@@ -337,7 +342,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
   const int lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int planes = p.split ? 2 : 1;
-  const int stage_bytes = planes * (p.a_tile_bytes + p.b_tile_bytes);
+  const int ntu = p.nt_unit;
+  const int stage_bytes = planes * (p.a_tile_bytes + ntu * p.b_tile_bytes);
+  const int n_acc = ntu == 2 ? 1 : 2;  // accumulator stages in tensor memory
 
   static_assert(MC == 1 || CG == 2, "operand multicast is built on CTA pairs");
   constexpr int kCluster = CG * MC;
@@ -350,7 +357,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
   constexpr int kTileM = kBM * CG;            // rows of one unit
   const int bn_cta = p.BN / CG;               // B rows (output columns) this CTA stages
   const int mt = (p.M + kTileM - 1) / kTileM;
-  const int nt = ((p.N + p.BN - 1) / p.BN) / MC;  // N tiles (MC = 2: pairs of N tiles; the host checked evenness)
+  const int nt_tiles = (p.N + p.BN - 1) / p.BN;
+  // N positions of the unit grid (MC = 2: pairs of N tiles, the host checked evenness; ntu = 2: two tiles per unit)
+  const int nt = MC == 2 ? nt_tiles / 2 : (nt_tiles + ntu - 1) / ntu;
   const int total_kb = (p.K + kBK - 1) / kBK;
   const long long units = static_cast<long long>(mt) * nt * p.splits_k;
 
@@ -389,20 +398,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (long long u = group_id; u < units; u += n_groups) {
-        const int n_tile = static_cast<int>(u % nt) * MC + static_cast<int>(MC == 2 ? pair_in_cl : 0u);
+        const int n_tile = MC == 2 ? static_cast<int>(u % nt) * 2 + static_cast<int>(pair_in_cl) : static_cast<int>(u % nt) * ntu;
+        const int tiles_here = MC == 2 ? 1 : min(ntu, nt_tiles - n_tile);
         const int m_tile = static_cast<int>((u / nt) % mt);
         const int ks = static_cast<int>(u / (static_cast<long long>(nt) * mt));
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(total_kb, kb0 + p.kb_per_split);
         const int a_row0 = m_tile * kTileM + static_cast<int>(cta_rank) * kBM;      // this CTA's A rows
-        const int b_row0 = n_tile * p.BN + static_cast<int>(cta_rank) * bn_cta;     // this CTA's share of the B tile
+        const int b_row0 = n_tile * p.BN + static_cast<int>(cta_rank) * bn_cta;     // this CTA's share of the (first) B tile
+        const int fill_bytes = planes * (p.a_tile_bytes + tiles_here * p.b_tile_bytes);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + static_cast<size_t>(stage) * stage_bytes;
           // pair: both CTAs' bytes are counted on the leader's barrier (a peer's bytes may land before the leader's
           // expect_tx of the same phase: the pending arrival keeps the phase open)
-          if constexpr (MC == 2) mbar_expect_tx(&full_bar[stage], stage_bytes);  // what lands in THIS CTA's smem
-          else if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], stage_bytes * CG);
+          if constexpr (MC == 2) mbar_expect_tx(&full_bar[stage], fill_bytes);  // what lands in THIS CTA's smem
+          else if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], fill_bytes * CG);
           const uint32_t bar_leader = (CG == 2 && MC == 1) ? mapa_shared(smem_u32(&full_bar[stage]), 0) : 0u;
           auto load = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
             if constexpr (CG == 2 && MC == 1) tma_load_2d_pair(dst, m, bar_leader, c0, c1);
@@ -412,7 +423,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
             const CUtensorMap* ma = pl ? &map_a_lo : &map_a_hi;
             const CUtensorMap* mb = pl ? &map_b_lo : &map_b_hi;
             uint8_t* sa = st + pl * p.a_tile_bytes;
-            uint8_t* sb = st + planes * p.a_tile_bytes + pl * p.b_tile_bytes;
             if constexpr (MC == 2) {
               // my half (64 rows = one 8 KB box in either layout) of the A rows I share with CTA cta_rank of the
               // other pair, delivered to both of us
@@ -426,10 +436,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
             } else {
               for (int bx = 0; bx < kBM / 64; ++bx) load(sa + bx * (kBK * 128), ma, a_row0 + bx * 64, kb * kBK);
             }
-            if (!p.b_mn) {
-              load(sb, mb, kb * kBK, b_row0);
-            } else {
-              for (int bx = 0; bx < p.b_boxes; ++bx) load(sb + bx * (kBK * 128), mb, b_row0 + bx * 64, kb * kBK);
+            for (int t = 0; t < tiles_here; ++t) {  // the unit's B tiles, one after the other behind the A planes
+              uint8_t* sb = st + planes * p.a_tile_bytes + (t * planes + pl) * p.b_tile_bytes;
+              const int br = b_row0 + t * p.BN;
+              if (!p.b_mn) {
+                load(sb, mb, kb * kBK, br);
+              } else {
+                for (int bx = 0; bx < p.b_boxes; ++bx) load(sb + bx * (kBK * 128), mb, br + bx * 64, kb * kBK);
+              }
             }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -451,28 +465,30 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
         const int ks = static_cast<int>(u / (static_cast<long long>(nt) * mt));
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+        const int tiles_here = MC == 2 ? 1 : min(ntu, nt_tiles - static_cast<int>(u % nt) * ntu);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tmem_d = tmem_base + acc * 256;
-        uint32_t accumulate = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           if constexpr (MC == 2) mbar_wait_cluster(&peer_full[stage], phase);  // the odd CTA's stage, forwarded
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t st = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
           const uint32_t sa_hi = st, sa_lo = st + p.a_tile_bytes;
-          const uint32_t sb_hi = st + planes * p.a_tile_bytes, sb_lo = sb_hi + p.b_tile_bytes;
           const int passes = p.split ? 3 : 1;
-          for (int ps = 0; ps < passes; ++ps) {
-            const uint32_t sa = (ps == 2) ? sa_lo : sa_hi;   // hi·hi, hi·lo, lo·hi
-            const uint32_t sb = (ps == 1) ? sb_lo : sb_hi;
+          for (int t = 0; t < tiles_here; ++t) {  // the unit's N tiles: same A stage, accumulators side by side
+            const uint32_t tmem_d = tmem_base + (acc + t) * 256;
+            const uint32_t sb_hi = st + planes * p.a_tile_bytes + t * planes * p.b_tile_bytes, sb_lo = sb_hi + p.b_tile_bytes;
+            for (int ps = 0; ps < passes; ++ps) {
+              const uint32_t sa = (ps == 2) ? sa_lo : sa_hi;   // hi·hi, hi·lo, lo·hi
+              const uint32_t sb = (ps == 1) ? sb_lo : sb_hi;
 #pragma unroll
-            for (int k = 0; k < kBK / kUmmaK; ++k) {
-              const uint64_t da = make_desc(sa + k * a_kstep, a_lbo, 1024);
-              const uint64_t db = make_desc(sb + k * b_kstep, b_lbo, 1024);
-              if constexpr (CG == 2) umma_bf16_pair(tmem_d, da, db, idesc, accumulate);
-              else umma_bf16(tmem_d, da, db, idesc, accumulate);
-              accumulate = 1;
+              for (int k = 0; k < kBK / kUmmaK; ++k) {
+                const uint64_t da = make_desc(sa + k * a_kstep, a_lbo, 1024);
+                const uint64_t db = make_desc(sb + k * b_kstep, b_lbo, 1024);
+                const uint32_t accumulate = (kb > kb0 || ps > 0 || k > 0) ? 1u : 0u;
+                if constexpr (CG == 2) umma_bf16_pair(tmem_d, da, db, idesc, accumulate);
+                else umma_bf16(tmem_d, da, db, idesc, accumulate);
+              }
             }
           }
           // frees the smem stage (in both CTAs of a pair) when the MMAs above retire
@@ -483,7 +499,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
           // empty K range (possible for the last split): publish a zero tile via the epilogue flag
         }
         if constexpr (CG == 2) umma_commit_pair(&tmem_full[acc], static_cast<uint16_t>(0x3u << leader)); else umma_commit(&tmem_full[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (MC == 2 && warp == 2 && cta_rank == 1) {
@@ -506,14 +522,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
     const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
     int acc = 0; uint32_t acc_phase = 0;
     for (long long u = group_id; u < units; u += n_groups) {
-      const int n_tile = static_cast<int>(u % nt) * MC + static_cast<int>(MC == 2 ? pair_in_cl : 0u);
+      const int n_tile0 = MC == 2 ? static_cast<int>(u % nt) * 2 + static_cast<int>(pair_in_cl) : static_cast<int>(u % nt) * ntu;
+      const int tiles_here = MC == 2 ? 1 : min(ntu, nt_tiles - n_tile0);
       const int m_tile = static_cast<int>((u / nt) % mt);
       const int ks = static_cast<int>(u / (static_cast<long long>(nt) * mt));
       const bool empty_k = (ks * p.kb_per_split >= total_kb);
       const int row_base = m_tile * kTileM + static_cast<int>(cta_rank) * kBM + ew * 32;  // this warp's 32 rows
       mbar_wait(&tmem_full[acc], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + acc * 256 + (static_cast<uint32_t>(ew * 32) << 16);
+      for (int t = 0; t < tiles_here; ++t) {
+      const int n_tile = n_tile0 + t;
+      const uint32_t taddr = tmem_base + (acc + t) * 256 + (static_cast<uint32_t>(ew * 32) << 16);
       if (p.dbg_epilogue == 2) {
         // measurement only: hand the accumulator straight back (mainloop-only time)
       } else if (p.staged) {
@@ -522,7 +541,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
         if (p.epi_y && u + n_groups < units) {
           const long long un = u + n_groups;
           pf_row0 = static_cast<int>((un / nt) % mt) * kTileM + static_cast<int>(cta_rank) * kBM + ew * 32;
-          pf_col0 = static_cast<int>(un % nt) * MC * p.BN;
+          pf_col0 = static_cast<int>(un % nt) * p.BN;
         }
         if (p.d_bf16) epilogue_staged<true>(p, &map_d, stg, taddr, row_base, n_tile * p.BN, ks, empty_k, lane, -1, 0);
         else epilogue_staged<false>(p, &map_d, stg, taddr, row_base, n_tile * p.BN, ks, empty_k, lane, pf_row0, pf_col0);
@@ -573,13 +592,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
         }
       }
       }
+      }  // tiles of the unit
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) {  // the leader's issuer waits for the epilogue warps of both CTAs
         if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), leader));
         else mbar_arrive(&tmem_empty[acc]);
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -706,11 +726,12 @@ static int gemm_cta_group(int M, bool prep_epilogue, int sm_count) {
 // 128 x bn / 256 clocks) and the L2 -> shared-memory operand stream.  Measured (tools/gemm_sweep.py, 300k x 800 x 1024,
 // N tiles 128 / 160 / 208 / 256: 1.42 / 1.18 / 1.07 / 1.14 ms): the two-plane GEMMs run at the pace of that stream,
 // ≈ 30 bytes per clock and SM (8.5 TB/s over the chip), not of the tensor pipe — so tiles are chosen by bytes moved.
-static double kblock_cost(int bn, int cg, int mc, int b_mn) {
+static double kblock_cost(int bn, int cg, int mc, int b_mn, int ntu = 1) {
   const int bn_cta = bn / cg;
   const double a_bytes = 2.0 * kBM * kBK * 2 / mc;  // multicast: each CTA fetches half of its A rows
   const double b_bytes = 2.0 * (b_mn ? ((bn_cta + 63) / 64) * kBK * 128 : bn_cta * kBK * 2);
-  const double mma = 6.0 * bn, l2 = (a_bytes + b_bytes) / 30.0;
+  // ntu N tiles of a unit share the A stage
+  const double mma = 6.0 * bn * ntu, l2 = (a_bytes + ntu * b_bytes) / 30.0;
   return mma > l2 ? mma : l2;
 }
 
@@ -718,6 +739,7 @@ struct GemmPlan {
   int cg;       // CTAs per 128-row-pair tile: 2 = tcgen05 cta_group::2
   int mc;       // 2: clusters of two pairs on neighbouring N tiles, A halves multicast
   int bn;       // N tile
+  int ntu;      // N tiles per work unit (2: they share the A stage, accumulators side by side in tensor memory)
   double cost;  // modelled SM clocks of one k-block over all tiles
 };
 
@@ -729,6 +751,7 @@ static GemmPlan plan_gemm(int M, int N, int b_mn, bool prep_epilogue, int sm_cou
   GemmPlan g{};
   g.cg = gemm_cta_group(M, prep_epilogue, sm_count);
   g.mc = 1;
+  g.ntu = 1;
   const long long mt = (M + kBM * g.cg - 1) / (kBM * g.cg);
   if (prep_epilogue) { g.bn = pick_bn_prep(N); g.cost = static_cast<double>(mt * ((N + g.bn - 1) / g.bn)) * g.cg * kblock_cost(g.bn, g.cg, 1, b_mn); return g; }
   int forced_bn = 0;
@@ -741,13 +764,28 @@ static GemmPlan plan_gemm(int M, int N, int b_mn, bool prep_epilogue, int sm_cou
   // L2 sends, set the pace, so sharing the fetch saves nothing and clusters of four leave 16 of the 148 SMs idle.
   bool mc_ok = false;
   if (const char* v = getenv("RELGAT_GEMM_MC")) { mc_ok = atoi(v) == 2 && g.cg == 2 && sm_count >= 4; }
+  // two N tiles per unit (RELGAT_GEMM_NTU=1 switches it off): needs two pipeline stages of A + 2 B tiles in shared memory
+  bool ntu_ok = true;
+  if (const char* v = getenv("RELGAT_GEMM_NTU")) { if (atoi(v) == 1) ntu_ok = false; }
   bool have = false;
   auto consider = [&](int bn, int mc) {
     const long long nt = (N + bn - 1) / bn;
     if (mc == 2 && (nt % 2 != 0 || mt * (nt / 2) < 8)) return;  // pairs of N tiles; not worth a cluster launch for a handful of tiles
     double c = static_cast<double>(mt * nt) * g.cg * kblock_cost(bn, g.cg, mc, b_mn);
     if (mc == 2) c /= kClusterOf4SmShare;
-    if (!have || c < g.cost * 0.999) { have = true; g.bn = bn; g.mc = mc; g.cost = c; }
+    if (!have || c < g.cost * 0.999) { have = true; g.bn = bn; g.mc = mc; g.ntu = 1; g.cost = c; }
+    // measured (tools/gemm_sweep.py): the weight-gradient shapes gain 3-4 % (1.255 -> 1.209 ms), the 300k-row GEMMs with
+    // a full-size output lose 6 % (their epilogue is exposed and only two pipeline stages fit): few-row-tile shapes only
+    if (mc == 1 && ntu_ok && nt >= 2 && mt <= 16) {
+      const int bn_cta = bn / g.cg;
+      const long long b_tile = b_mn ? ((bn_cta + 63) / 64) * kBK * 128 : bn_cta * kBK * 2;
+      const long long stage = 2 * (kBM * kBK * 2 + 2 * b_tile);  // two planes
+      if (2 * stage <= 227 * 1024 - 2048 - kEpiStageBytes) {
+        // (+4 % for the unit's epilogue, no longer hidden behind the next unit's main loop)
+        const double c2 = static_cast<double>(mt * ((nt + 1) / 2)) * g.cg * kblock_cost(bn, g.cg, 1, b_mn, 2) * 1.04;
+        if (c2 < g.cost * 0.999) { g.bn = bn; g.mc = 1; g.ntu = 2; g.cost = c2; }
+      }
+    }
   };
   if (forced_bn) { if (mc_ok) consider(forced_bn, 2); consider(forced_bn, 1); return g; }
   if (N <= 256) { consider((N + 15) / 16 * 16, 1); return g; }
@@ -841,6 +879,7 @@ static int gemm_launch(const void* a_hi, const void* a_lo, long long lda, int a_
   const GemmPlan plan = plan_gemm(M, N, b_mn ? 1 : 0, epi != nullptr, sm_count, d_is_bf16 != 0);
   const int cg = plan.cg, mc = plan.mc;
   p.BN = plan.bn;
+  p.nt_unit = plan.ntu;
   p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
   p.split = a_lo ? 1 : 0;
   const int total_kb = (K + kBK - 1) / kBK;
@@ -852,7 +891,7 @@ static int gemm_launch(const void* a_hi, const void* a_lo, long long lda, int a_
   p.b_boxes = (bn_cta + 63) / 64;
   p.b_tile_bytes = p.b_mn ? p.b_boxes * kBK * 128 : bn_cta * kBK * 2;
   const int planes = p.split ? 2 : 1;
-  const int stage_bytes = planes * (p.a_tile_bytes + p.b_tile_bytes);
+  const int stage_bytes = planes * (p.a_tile_bytes + p.nt_unit * p.b_tile_bytes);
   // the coalesced epilogue needs whole 16-byte pieces: N and the row stride multiples of the piece width
   const int piece = d_is_bf16 ? 8 : 4;
   p.staged = (N % piece == 0 && (splits_k > 1 ? N : ldd) % piece == 0 &&
@@ -908,7 +947,8 @@ static int gemm_launch(const void* a_hi, const void* a_lo, long long lda, int a_
     if (make_map_d(&md, d_out, d_is_bf16 != 0, M, N, ldd) == RG_OK) p.tma_store = 1;
   }
   const int tile_m = kBM * cg;
-  const long long units = static_cast<long long>((M + tile_m - 1) / tile_m) * (((N + p.BN - 1) / p.BN) / mc) * splits_k;
+  const long long n_pos = mc == 2 ? ((N + p.BN - 1) / p.BN) / 2 : (((N + p.BN - 1) / p.BN) + p.nt_unit - 1) / p.nt_unit;
+  const long long units = static_cast<long long>((M + tile_m - 1) / tile_m) * n_pos * splits_k;
   const int smem_bytes = stages * stage_bytes + 1024 + (p.staged ? kEpiStageBytes : 0);
   cudaError_t e;
   if (cg == 2) {
@@ -961,7 +1001,7 @@ extern "C" long long relgat_gemm_plan(int M, int N, int b_mn, int sm_count, int*
   if (sm_count <= 0) sm_count = 148;
   const GemmPlan g = plan_gemm(M, N, b_mn ? 1 : 0, false, sm_count);
   if (tile_m) *tile_m = kBM * g.cg;
-  if (tile_n) *tile_n = g.bn * g.mc;  // a unit of the multicast variant spans two N tiles
+  if (tile_n) *tile_n = g.bn * g.mc * g.ntu;  // a unit may span two N tiles
   if (slots) *slots = g.mc == 2 ? static_cast<int>(sm_count / 4 * kClusterOf4SmShare + 0.5) : sm_count / g.cg;
   return static_cast<long long>(g.cost);
 }

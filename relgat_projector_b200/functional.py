@@ -45,6 +45,11 @@ COMPACT_BWD = os.environ.get("RELGAT_COMPACT_BWD", "1") != "0"
 # that consume the rows (fold_operands below).  1.41 -> 1.12 ms per launch at config 2.  RELGAT_SRC_V3=0: first generation.
 SRC_V3 = os.environ.get("RELGAT_SRC_V3", "1") != "0"
 
+# SM split of the backward (fp32 mode, third-generation by-source pass): the weight-gradient GEMM of layer l (tensor-
+# bound, little HBM traffic) runs on OVERLAP_SMS SMs of the side stream while the HBM-bound prep + by-source pass of layer
+# l-1 run on the remaining SMs of the main stream (they depend on dX, not on dW).  0 = everything in line.
+OVERLAP_SMS = int(os.environ.get("RELGAT_OVERLAP_SMS", "0"))
+
 _SIDE_STREAMS = {}
 
 
@@ -53,7 +58,7 @@ def _side_stream(device) -> torch.cuda.Stream:
     dW / dX GEMMs (they only share read-only inputs)."""
     key = torch.device(device).index
     if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device, priority=-1)  # its CTAs are placed first when SMs free up
     return _SIDE_STREAMS[key]
 
 
@@ -274,6 +279,9 @@ class RelGATStackFunction(torch.autograd.Function):
             sizes = _plan_counts(ctx.plan)
             torch.cuda.current_stream(planes[0].device).wait_event(ctx.plan["ready"])
         ctx.pruned = prune
+        if gather_ids is not None and ctx.gather is None:
+            # (sorted keys, perm, event) = the summation order of backward: sorted on the side stream beside the forward
+            ctx.gather = presort_on_side_stream(gather_ids.contiguous(), graphs[-1].N)
         for l in range(L):
             W, A, beta = params[3 * l], params[3 * l + 1], params[3 * l + 2]
             d_in = W.size(1)
@@ -284,6 +292,20 @@ class RelGATStackFunction(torch.autograd.Function):
             Wp = ops.split_bf16(W.detach(), with_lo)
             # K-major copy of Wᵀ for dX = dP·W (3 MB transpose; the K-major B path is ~12% faster than MN-major)
             WTp = ops.split_bf16(W.detach().t().contiguous(), with_lo) if (l > 0 or x0_grad) else None
+            fold = None
+            if SRC_V3 and USE_DS and with_lo and F % 4 == 0:
+                # parameters only: prepared on the side stream beside this layer's GEMM, waited for in backward
+                main, side = torch.cuda.current_stream(W.device), _side_stream(W.device)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    fold = fold_operands(A.detach(), Wp, WTp, H, F, gl.R, d_in)
+                    fold["ready"] = torch.cuda.Event()
+                    fold["ready"].record(side)
+                for pp in (Wp, WTp, fold["Abd"], fold["Bext"]):
+                    for tns in (pp or ()):
+                        if tns is not None:
+                            tns.record_stream(side)
+                            tns.record_stream(main)
             # "bf16": projected features are stored in bf16 (halves every gather of the edge kernels)
             last = l == L - 1
             dl = drop[l] if drop is not None else None
@@ -302,9 +324,6 @@ class RelGATStackFunction(torch.autograd.Function):
                                                       feat_drop=dl.feat if dl else None, edge_drop=dl.edge if dl else None,
                                                       chunks=pl["fwd_chunks"] if prune else None,
                                                       src_row=pl["rank"] if prune else None)
-            fold = None
-            if SRC_V3 and USE_DS and with_lo and ops.src3_supported(P, F):
-                fold = fold_operands(A.detach(), Wp, WTp, H, F, gl.R, d_in)
             saved.append(dict(xp=planes, Wp=Wp, WTp=WTp, P=P, out=out, minv=minv, z=z, bias=bias, A=A.detach(),
                               d_in=d_in, has_beta=beta is not None, drop=dl, fold=fold))
             planes = act
@@ -357,6 +376,7 @@ class RelGATStackFunction(torch.autograd.Function):
         # (blocks hold nothing but the rows the batch reaches: there is nothing to skip)
         nz_bits = ops.mark_rows(nz_rows, N) if (SPARSE_BWD and USE_DS and nz_rows is not None and not blocks) else None
         dX = None
+        main_sms = None  # SM budget of the main stream while the layer above's dW GEMM runs beside it (OVERLAP_SMS)
         prepped = None  # (G, t, hsum) of layer l when the dX GEMM of layer l+1 produced them in its epilogue
         fuse_prep = USE_DS and FUSE_PREP and with_lo and ops.gemm_dx_prep_supported(C, F)
         for l in reversed(range(L)):
@@ -364,19 +384,25 @@ class RelGATStackFunction(torch.autograd.Function):
             g = graphs[l]
             n_src = g.N_src
             dl = s["drop"]
-            if prepped is not None:
-                G, t, hsum = prepped
-                prepped = None
-            else:
-                # fp32 storage: G aliases dY and only the batch rows are touched; bf16 storage writes a dense bf16 G
-                G, t, hsum = ops.edge_bwd_prep(dY, s["out"], s["bias"], H, F, apply_elu=(l < L - 1), inplace=owned,
-                                               g_bf16=not with_lo, nonzero_rows=nz_rows if l == L - 1 else None,
-                                               feat_drop=dl.feat if dl else None)
-            fold = s["fold"] if (USE_DS and ops.src3_supported(G, F)) else None  # rows [dPa | dS], dS·A folded below
-            _, dPp, dz = ops.edge_bwd_src(s["P"], G, s["A"], s["z"], s["minv"], t, g, H, F,
-                                          want_fp32=False, want_planes=True, planes_lo=with_lo,
-                                          edge_drop=dl.edge if dl else None, want_ds=USE_DS, dst_nz=nz_bits,
-                                          a_term=fold is None)
+            with ops.sm_limit(main_sms):
+                if prepped is not None:
+                    G, t, hsum = prepped
+                    prepped = None
+                else:
+                    # fp32 storage: G aliases dY and only the batch rows are touched; bf16 storage writes a dense bf16 G
+                    G, t, hsum = ops.edge_bwd_prep(dY, s["out"], s["bias"], H, F, apply_elu=(l < L - 1), inplace=owned,
+                                                   g_bf16=not with_lo, nonzero_rows=nz_rows if l == L - 1 else None,
+                                                   feat_drop=dl.feat if dl else None)
+                fold = s["fold"] if (USE_DS and ops.src3_supported(G, F) and ops.src3_supported(s["P"], F)) else None
+                if fold is not None:  # rows [dPa | dS], dS·A folded into the GEMMs below
+                    torch.cuda.current_stream(dY.device).wait_event(fold["ready"])
+                _, dPp, dz = ops.edge_bwd_src(s["P"], G, s["A"], s["z"], s["minv"], t, g, H, F,
+                                              want_fp32=False, want_planes=True, planes_lo=with_lo,
+                                              edge_drop=dl.edge if dl else None, want_ds=USE_DS, dst_nz=nz_bits,
+                                              a_term=fold is None)
+            if main_sms is not None:
+                torch.cuda.current_stream(dY.device).wait_stream(_side_stream(dY.device))  # the GEMMs below want the whole chip
+                main_sms = None
             if nz_bits is not None and l > 0:
                 nz_bits = ops.mark_sources(nz_bits, g)  # rows of dP, hence of dL/d out_{l-1}, that can be non-zero
             if table is not None and l == L - 1:
@@ -393,6 +419,33 @@ class RelGATStackFunction(torch.autograd.Function):
                 HR = H * g.R
                 Wd = dPp[0].size(1)
                 dP_c = tuple(None if p_ is None else p_[:, :C] for p_ in dPp)
+                if OVERLAP_SMS > 0 and l > 0 and fold is not None and not TAIL_ON_SIDE:
+                    # dX first (whole chip), then dW + its tail on OVERLAP_SMS SMs of the side stream beside the layer
+                    # below's prep and by-source pass on the others
+                    dX = ops.gemm(dPp, False, fold["Bext"], False, n_src, d_in, Wd)
+                    dx_done = torch.cuda.Event()
+                    dx_done.record(main)
+                    side.wait_event(dx_done)
+                    total = ops.sm_count(dY.device)
+                    k_side = max(2, min(total - 2, OVERLAP_SMS)) // 2 * 2
+                    with torch.cuda.stream(side), ops.sm_limit(k_side):
+                        dW_ext = weight_grad_gemm(dPp, s["xp"], Wd, d_in, n_src, dY.device)
+                        Tp = ops.split_bf16(dW_ext[C:C + HR].contiguous(), with_lo)
+                        dW = dW_ext[:C] + ops.gemm(fold["Abd"], True, Tp, True, C, d_in, HR)
+                        dA_full = ops.gemm(Tp, False, s["Wp"], False, HR, C, d_in)
+                        dA = torch.stack([dA_full[h * g.R:(h + 1) * g.R, h * F:(h + 1) * F] for h in range(H)])
+                        dbeta = ops.edge_bwd_beta(hsum, g, H) if s["has_beta"] else None
+                    for tns in (*dPp, hsum):
+                        if tns is not None:
+                            tns.record_stream(side)
+                    for tns in (dW, dA, dbeta):
+                        if tns is not None:
+                            tns.record_stream(main)
+                    main_sms = total - k_side
+                    grads[3 * l], grads[3 * l + 1], grads[3 * l + 2] = dW, dA, dbeta
+                    dY, owned = dX, True
+                    del G, dPp, dz
+                    continue
                 dW_ext = weight_grad_gemm(dPp, s["xp"], Wd, d_in, n_src, dY.device)
                 dw_ready = torch.cuda.Event()
                 dw_ready.record(main)
@@ -486,6 +539,8 @@ def _backward_compact(ctx, table: torch.Tensor, keys: torch.Tensor) -> List[Opti
             clear_rows = prev_rows
         dPp = None
         fold = s["fold"] if (n_s > 0 and ops.src3_supported(G, F) and ops.src3_supported(s["P"], F)) else None
+        if fold is not None:
+            torch.cuda.current_stream(dev).wait_event(fold["ready"])
         if n_s > 0:
             _, dPp, _ = ops.edge_bwd_src(s["P"], G, s["A"], s["z"], s["minv"], t, g, H, F, want_fp32=False,
                                          want_planes=True, planes_lo=True, edge_drop=dl.edge if dl else None,

@@ -85,11 +85,34 @@ def _out_buf(buf: Optional[torch.Tensor], shape, device, name: str) -> torch.Ten
 _SM_COUNT = {}
 
 
+_SM_LIMIT = [None]
+
+
 def sm_count(device) -> int:
+    """SMs the persistent kernels launched from here may fill: the device's, or the current ``sm_limit``."""
     idx = torch.device(device).index
     if idx not in _SM_COUNT:
         _SM_COUNT[idx] = torch.cuda.get_device_properties(device).multi_processor_count
-    return _SM_COUNT[idx]
+    lim = _SM_LIMIT[0]
+    return _SM_COUNT[idx] if lim is None else max(2, min(_SM_COUNT[idx], lim))
+
+
+class sm_limit:
+    """``with ops.sm_limit(n):`` the persistent kernels (GEMM, edge passes) launched inside size their grids for n SMs.
+    Two such kernels on different streams then share the chip side by side instead of queueing behind each other (every
+    one of them takes a whole SM's shared memory, so their CTAs never share an SM)."""
+
+    def __init__(self, n: Optional[int]):
+        self.n = None if n is None else int(n)
+
+    def __enter__(self):
+        self.prev = _SM_LIMIT[0]
+        _SM_LIMIT[0] = self.n
+        return self
+
+    def __exit__(self, *exc):
+        _SM_LIMIT[0] = self.prev
+        return False
 
 
 # ------------------------------------------------------------------------------------------
