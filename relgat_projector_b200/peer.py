@@ -582,8 +582,12 @@ def forward_steps(part: PeerPartition, planes, params: Sequence[torch.Tensor], w
             want_act=not last, apply_elu=True, act_lo=with_lo, out_buf=T["out"].local[:n] if last else None,
             z_out=T[f"z{l}"].local[:part.E_fwd], minv_out=T[f"minv{l}"].local[:n])
         _mark(f"fwd{l} edge kernel done")
+        # third-generation by-source pass (rows [dPa | dS], dS·A folded into the GEMMs): parameter-only operands
+        fold = None
+        if _RF.SRC_V3 and _RF.USE_DS and with_lo and F % 4 == 0:
+            fold = _RF.fold_operands(A.detach(), Wp, WTp, H, F, part.bwd_graph.R, d_in)
         saved.append(dict(xp=planes, Wp=Wp, WTp=WTp, out=out, bias=bias, A=A.detach(), d_in=d_in,
-                          has_beta=beta is not None))
+                          has_beta=beta is not None, fold=fold))
         planes = act
     return out
 
@@ -679,8 +683,10 @@ def backward_steps(part: PeerPartition, grad_out: torch.Tensor, saved: list, wit
         _mark(f"bwd{l} pulls joined")
         P_loc = T[f"P{l}"].local[:n]
         use_ds = _RF.USE_DS
+        fold = s.get("fold") if (use_ds and ops.src3_supported(P_loc, F) and ops.src3_supported(G_ext, F)) else None
         _, dPp, dz = ops.edge_bwd_src(P_loc, G_ext, s["A"], z, minv_ext, t_ext, g, H, F,
-                                      want_fp32=False, want_planes=True, planes_lo=with_lo, want_ds=use_ds)
+                                      want_fp32=False, want_planes=True, planes_lo=with_lo, want_ds=use_ds,
+                                      a_term=fold is None)
         _mark(f"bwd{l} by-source kernel done")
         # dA / dbeta and dW are off the critical path (dX -> prep -> pull -> by-source pass of the layer below):
         # they run on the side stream, beside the NVLink-bound pulls, and are joined once at the end
@@ -696,9 +702,12 @@ def backward_steps(part: PeerPartition, grad_out: torch.Tensor, saved: list, wit
             def dw_and_tail():
                 dW_ext = _RF.weight_grad_gemm(dPp, s["xp"], Wd, d_in, n, dY.device)
                 Tp = ops.split_bf16(dW_ext[C:C + HR].contiguous(), with_lo)
+                dW_ = dW_ext[:C]
+                if fold is not None:  # rows are [dPa | dS]: dW = dPa^T X + A_bd^T (dS^T X)
+                    dW_ = dW_ + ops.gemm(fold["Abd"], True, Tp, True, C, d_in, HR)
                 dA_full = ops.gemm(Tp, False, s["Wp"], False, HR, C, d_in)
                 dA_ = torch.stack([dA_full[h * g.R:(h + 1) * g.R, h * F:(h + 1) * F] for h in range(H)])
-                return dW_ext[:C], dA_, (ops.edge_bwd_beta(hsum_ext, g, H) if s["has_beta"] else None)
+                return dW_, dA_, (ops.edge_bwd_beta(hsum_ext, g, H) if s["has_beta"] else None)
 
             if deep:
                 with torch.cuda.stream(side):
@@ -721,7 +730,10 @@ def backward_steps(part: PeerPartition, grad_out: torch.Tensor, saved: list, wit
             dPc = dPp
         grads[3 * l], grads[3 * l + 1], grads[3 * l + 2] = dW, dA, dbeta
         if l > 0 or x0_needs_grad:
-            dX = ops.gemm(dPc, False, s["WTp"], False, n, d_in, C)
+            if fold is not None:  # dX = [dPa | dS] · [W ; A_bd·W]
+                dX = ops.gemm(dPp, False, fold["Bext"], False, n, d_in, dPp[0].size(1))
+            else:
+                dX = ops.gemm(dPc, False, s["WTp"], False, n, d_in, C)
             dY = dX
             _mark(f"bwd{l} dX done")
         keep.append((dPp, dz, z, hsum_ext))  # read on the side stream: released only after the join
