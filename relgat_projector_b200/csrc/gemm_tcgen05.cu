@@ -60,6 +60,10 @@ struct GemmParams {
   // accumulators sit side by side in tensor memory (2 x <=256 columns = all of it: the epilogue of a unit is no longer
   // hidden behind the next unit's main loop).
   int nt_unit;
+  // k-block depth: 64 (one 128-byte swizzle atom along K), or 32 when BOTH operands are MN-major (their boxes are
+  // [bk k-rows x 64 MN-columns], any multiple of 8 rows works): half-size stages, so that two-tile units still get a
+  // four-deep pipeline
+  int bk;
 };
 
 constexpr int kEpiStageBytes = 4 * 32 * 64;  // per epilogue warp: 32 rows x 64 bytes
@@ -360,7 +364,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
   const int nt_tiles = (p.N + p.BN - 1) / p.BN;
   // N positions of the unit grid (MC = 2: pairs of N tiles, the host checked evenness; ntu = 2: two tiles per unit)
   const int nt = MC == 2 ? nt_tiles / 2 : (nt_tiles + ntu - 1) / ntu;
-  const int total_kb = (p.K + kBK - 1) / kBK;
+  const int bk = p.bk;
+  const int total_kb = (p.K + bk - 1) / bk;
   const long long units = static_cast<long long>(mt) * nt * p.splits_k;
 
   if (warp == 0 && lane == 0) {
@@ -427,22 +432,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
               // my half (64 rows = one 8 KB box in either layout) of the A rows I share with CTA cta_rank of the
               // other pair, delivered to both of us
               const uint16_t both = static_cast<uint16_t>((1u << cta_rank) | (1u << (cta_rank + 2)));
-              uint8_t* dst = sa + pair_in_cl * (kBK * 128);
+              uint8_t* dst = sa + pair_in_cl * (bk * 128);
               const int r0 = a_row0 + static_cast<int>(pair_in_cl) * 64;
-              if (!p.a_mn) tma_load_2d_mcast(dst, ma, &full_bar[stage], kb * kBK, r0, both);
-              else tma_load_2d_mcast(dst, ma, &full_bar[stage], r0, kb * kBK, both);
+              if (!p.a_mn) tma_load_2d_mcast(dst, ma, &full_bar[stage], kb * bk, r0, both);
+              else tma_load_2d_mcast(dst, ma, &full_bar[stage], r0, kb * bk, both);
             } else if (!p.a_mn) {
-              load(sa, ma, kb * kBK, a_row0);
+              load(sa, ma, kb * bk, a_row0);
             } else {
-              for (int bx = 0; bx < kBM / 64; ++bx) load(sa + bx * (kBK * 128), ma, a_row0 + bx * 64, kb * kBK);
+              for (int bx = 0; bx < kBM / 64; ++bx) load(sa + bx * (bk * 128), ma, a_row0 + bx * 64, kb * bk);
             }
             for (int t = 0; t < tiles_here; ++t) {  // the unit's B tiles, one after the other behind the A planes
               uint8_t* sb = st + planes * p.a_tile_bytes + (t * planes + pl) * p.b_tile_bytes;
               const int br = b_row0 + t * p.BN;
               if (!p.b_mn) {
-                load(sb, mb, kb * kBK, br);
+                load(sb, mb, kb * bk, br);
               } else {
-                for (int bx = 0; bx < p.b_boxes; ++bx) load(sb + bx * (kBK * 128), mb, br + bx * 64, kb * kBK);
+                for (int bx = 0; bx < p.b_boxes; ++bx) load(sb + bx * (bk * 128), mb, br + bx * 64, kb * bk);
               }
             }
           }
@@ -456,7 +461,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(p.a_mn) << 15) |
                              (static_cast<uint32_t>(p.b_mn) << 16) | (static_cast<uint32_t>(p.BN >> 3) << 17) |
                              (static_cast<uint32_t>(kTileM >> 4) << 24);
-      const uint32_t a_lbo = p.a_mn ? kBK * 128 : 16, b_lbo = p.b_mn ? kBK * 128 : 16;
+      const uint32_t a_lbo = p.a_mn ? bk * 128 : 16, b_lbo = p.b_mn ? bk * 128 : 16;
       const uint32_t a_kstep = p.a_mn ? kUmmaK * 128 : kUmmaK * 2;  // bytes per UMMA_K step
       const uint32_t b_kstep = p.b_mn ? kUmmaK * 128 : kUmmaK * 2;
       int stage = 0; uint32_t phase = 0;
@@ -481,8 +486,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
             for (int ps = 0; ps < passes; ++ps) {
               const uint32_t sa = (ps == 2) ? sa_lo : sa_hi;   // hi·hi, hi·lo, lo·hi
               const uint32_t sb = (ps == 1) ? sb_lo : sb_hi;
-#pragma unroll
-              for (int k = 0; k < kBK / kUmmaK; ++k) {
+              for (int k = 0; k < bk / kUmmaK; ++k) {
                 const uint64_t da = make_desc(sa + k * a_kstep, a_lbo, 1024);
                 const uint64_t db = make_desc(sb + k * b_kstep, b_lbo, 1024);
                 const uint32_t accumulate = (kb > kb0 || ps > 0 || k > 0) ? 1u : 0u;
@@ -882,14 +886,18 @@ static int gemm_launch(const void* a_hi, const void* a_lo, long long lda, int a_
   p.nt_unit = plan.ntu;
   p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
   p.split = a_lo ? 1 : 0;
-  const int total_kb = (K + kBK - 1) / kBK;
+  // half-depth k-blocks for the two-tile units of the MN-major (weight-gradient) GEMMs (four pipeline stages instead
+  // of two) are opt-in (RELGAT_GEMM_BK32=1): measured SLOWER (1.43 vs 1.27 ms on [dP|dS]^T X) — twice as many, half as
+  // large TMA boxes per byte cost more than the deeper pipeline returns
+  p.bk = (p.nt_unit == 2 && p.a_mn && p.b_mn && getenv("RELGAT_GEMM_BK32")) ? 32 : kBK;
+  const int total_kb = (K + p.bk - 1) / p.bk;
   if (splits_k > total_kb) splits_k = total_kb;
   p.splits_k = splits_k;
   p.kb_per_split = (total_kb + splits_k - 1) / splits_k;
   const int bn_cta = p.BN / cg;  // BN is a multiple of 16: each CTA's share is a multiple of 8 rows
-  p.a_tile_bytes = kBM * kBK * 2;
+  p.a_tile_bytes = kBM * p.bk * 2;
   p.b_boxes = (bn_cta + 63) / 64;
-  p.b_tile_bytes = p.b_mn ? p.b_boxes * kBK * 128 : bn_cta * kBK * 2;
+  p.b_tile_bytes = p.b_mn ? p.b_boxes * p.bk * 128 : bn_cta * p.bk * 2;
   const int planes = p.split ? 2 : 1;
   const int stage_bytes = planes * (p.a_tile_bytes + p.nt_unit * p.b_tile_bytes);
   // the coalesced epilogue needs whole 16-byte pieces: N and the row stride multiples of the piece width
@@ -930,7 +938,7 @@ static int gemm_launch(const void* a_hi, const void* a_lo, long long lda, int a_
   // K-major: matrix [MN rows, K cols], box rows = tile MN extent.  MN-major: matrix [K rows, MN cols], box rows = BK.
   const long long a_rows = p.a_mn ? K : M, a_cols = p.a_mn ? M : K;
   const long long b_rows = p.b_mn ? K : N, b_cols = p.b_mn ? N : K;
-  const int a_box = p.a_mn ? kBK : (mc == 2 ? kBM / 2 : kBM), b_box = p.b_mn ? kBK : bn_cta;  // multicast: half tiles
+  const int a_box = p.a_mn ? p.bk : (mc == 2 ? kBM / 2 : kBM), b_box = p.b_mn ? p.bk : bn_cta;  // multicast: half tiles
   if ((rc = make_map(&ma_hi, a_hi, a_rows, a_cols, lda, a_box)) != RG_OK) return rc;
   if ((rc = make_map(&mb_hi, b_hi, b_rows, b_cols, ldb, b_box)) != RG_OK) return rc;
   if (p.split) {
