@@ -462,8 +462,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                              (static_cast<uint32_t>(p.b_mn) << 16) | (static_cast<uint32_t>(p.BN >> 3) << 17) |
                              (static_cast<uint32_t>(kTileM >> 4) << 24);
       const uint32_t a_lbo = p.a_mn ? bk * 128 : 16, b_lbo = p.b_mn ? bk * 128 : 16;
-      const uint32_t a_kstep = p.a_mn ? kUmmaK * 128 : kUmmaK * 2;  // bytes per UMMA_K step
-      const uint32_t b_kstep = p.b_mn ? kUmmaK * 128 : kUmmaK * 2;
+      // descriptor address-field increment per UMMA_K step (bytes >> 4)
+      const uint64_t a_dstep = (p.a_mn ? kUmmaK * 128 : kUmmaK * 2) >> 4;
+      const uint64_t b_dstep = (p.b_mn ? kUmmaK * 128 : kUmmaK * 2) >> 4;
+      const int ksteps = bk / kUmmaK;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (long long u = group_id; u < units; u += n_groups) {
@@ -478,20 +480,30 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
           if constexpr (MC == 2) mbar_wait_cluster(&peer_full[stage], phase);  // the odd CTA's stage, forwarded
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t st = smem_u32(smem + static_cast<size_t>(stage) * stage_bytes);
-          const uint32_t sa_hi = st, sa_lo = st + p.a_tile_bytes;
+          // The ONE issuing thread must stay ahead of the tensor pipe (an MMA of this size retires in 80-130 clocks): the
+          // descriptors of a stage are built once, the k-steps add a constant to their address field (the smem window
+          // is < 256 KB, so the 14-bit field never carries), and the 3 x 4 issue sequence is fully unrolled.  (A
+          // run-time trip count here cost 15 % on the 300k-row GEMMs.)
           const int passes = p.split ? 3 : 1;
+          const uint64_t da_hi = make_desc(st, a_lbo, 1024), da_lo = make_desc(st + p.a_tile_bytes, a_lbo, 1024);
+          const uint32_t first_acc = kb > kb0 ? 1u : 0u;  // the unit's very first MMA overwrites the accumulator
           for (int t = 0; t < tiles_here; ++t) {  // the unit's N tiles: same A stage, accumulators side by side
             const uint32_t tmem_d = tmem_base + (acc + t) * 256;
-            const uint32_t sb_hi = st + planes * p.a_tile_bytes + t * planes * p.b_tile_bytes, sb_lo = sb_hi + p.b_tile_bytes;
-            for (int ps = 0; ps < passes; ++ps) {
-              const uint32_t sa = (ps == 2) ? sa_lo : sa_hi;   // hi·hi, hi·lo, lo·hi
-              const uint32_t sb = (ps == 1) ? sb_lo : sb_hi;
-              for (int k = 0; k < bk / kUmmaK; ++k) {
-                const uint64_t da = make_desc(sa + k * a_kstep, a_lbo, 1024);
-                const uint64_t db = make_desc(sb + k * b_kstep, b_lbo, 1024);
-                const uint32_t accumulate = (kb > kb0 || ps > 0 || k > 0) ? 1u : 0u;
-                if constexpr (CG == 2) umma_bf16_pair(tmem_d, da, db, idesc, accumulate);
-                else umma_bf16(tmem_d, da, db, idesc, accumulate);
+            const uint32_t sb_hi = st + planes * p.a_tile_bytes + t * planes * p.b_tile_bytes;
+            const uint64_t db_hi = make_desc(sb_hi, b_lbo, 1024), db_lo = make_desc(sb_hi + p.b_tile_bytes, b_lbo, 1024);
+#pragma unroll
+            for (int ps = 0; ps < 3; ++ps) {
+              if (ps < passes) {
+                const uint64_t da = (ps == 2) ? da_lo : da_hi;   // hi·hi, hi·lo, lo·hi
+                const uint64_t db = (ps == 1) ? db_lo : db_hi;
+#pragma unroll
+                for (int k = 0; k < kBK / kUmmaK; ++k) {
+                  if (k < ksteps) {
+                    const uint32_t accumulate = (ps | k) ? 1u : first_acc;
+                    if constexpr (CG == 2) umma_bf16_pair(tmem_d, da + k * a_dstep, db + k * b_dstep, idesc, accumulate);
+                    else umma_bf16(tmem_d, da + k * a_dstep, db + k * b_dstep, idesc, accumulate);
+                  }
+                }
               }
             }
           }
