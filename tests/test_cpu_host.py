@@ -37,6 +37,32 @@ def test_library_loads_and_exports_header_symbols():
     assert lib.relgat_score_fwd(7, 0, None, None, None, None, None, None, 1, 4, None, None, 0, None, None, None) == -1
 
 
+def test_gemm_plan_host_logic(monkeypatch):
+    """relgat_gemm_plan is pure host logic (no GPU): tile shapes the kernel can run, work units that cover the output,
+    the measured choices of the config-2 shapes, and the experiment knobs."""
+    from relgat_projector_b200 import ops
+    for M, N, b_mn in [(300_000, 800, False), (1000, 1024, True), (1000, 800, True), (800, 1000, True), (200, 800, False),
+                       (128, 64, False), (129, 16, False), (5120, 1024, False), (1_000_000, 2048, False), (513, 1000, True)]:
+        cost, tm, tn, slots = ops.gemm_plan(M, N, b_mn, 148)
+        assert tm == (256 if M > 128 else 128) and cost > 0
+        assert tn % 16 == 0 and 16 <= tn <= 512 and slots == 148 // (tm // 128)
+        if N <= 256:
+            assert tn == (N + 15) // 16 * 16  # one N tile
+    # 300k-row GEMMs: the N tile that moves the fewest operand bytes (4 x 208 rather than 5 x 160 or 4 x 256)
+    assert ops.gemm_plan(300_000, 800, False, 148)[2] == 208
+    # weight-gradient shapes (few row tiles): two 256-column tiles per work unit
+    assert ops.gemm_plan(1000, 1024, True, 148)[2] == 512
+    # both orientations of config 2's second-layer dW cost the same: no transposed product
+    assert ops.gemm_cost_model(800, 1000) >= 0.97 * ops.gemm_cost_model(1000, 800)
+    monkeypatch.setenv("RELGAT_GEMM_NTU", "1")
+    assert ops.gemm_plan(1000, 1024, True, 148)[2] == 256
+    monkeypatch.setenv("RELGAT_GEMM_CG", "1")
+    assert ops.gemm_plan(1000, 1024, True, 148)[1:] == (128, 256, 148)
+    monkeypatch.setenv("RELGAT_GEMM_BN", "160")
+    assert ops.gemm_plan(300_000, 800, False, 148)[2] == 160
+    assert _lib.load().relgat_gemm_plan(0, 5, 0, 148, None, None, None) == -1
+
+
 def _build_model(c: Case, seed):
     torch.manual_seed(seed)
     return R.RelGATModel(
