@@ -99,7 +99,8 @@ int relgat_gemm_bf16(const void* a_hi, const void* a_lo, long long lda, int a_mn
  * bias [M] its relation-bias sums, drop_* its feature-dropout mask (NULL = off), apply_elu: act = ELU else identity.
  * Needs relgat_gemm_tile_n(N) <= F (a tile inside at most two heads), else RG_ERR_SHAPE (use the unfused pair). */
 int relgat_gemm_tile_n(int N);
-/* Work-unit shape relgat_gemm_bf16 uses for an [M, N] output on a device with sm_count SMs (b_mn as in
+/* (Host-side planning for the GEMMs that replace `lin(node_emb)` of reference core/model/layer.py:220 and its autograd.)
+ * Work-unit shape relgat_gemm_bf16 uses for an [M, N] output on a device with sm_count SMs (b_mn as in
  * relgat_gemm_bf16): tile_m = 256 rows when the kernel runs as CTA pairs (tcgen05 cta_group::2, M > 128), else 128;
  * tile_n = columns of one unit (the N tile, chosen by the bytes a tile moves from L2 to shared memory; twice the N tile
  * when clusters of two pairs share their A rows by TMA multicast); slots = units in flight at once.  Returns the
@@ -207,7 +208,8 @@ int relgat_layer_bwd_src2(const float* P, long long ldp, const float* G, const f
                           float* part_acc, void* dP_hi, void* dP_lo, float* coef, long long E,
                           const unsigned int* edge_bits, float edge_scale, long long ldo, int H, int F, int R,
                           int sm_count, int* work_counter, void* stream);
-/* Third-generation by-source pass (csrc/edge_bwd_src3.cu): the gathered rows reach shared memory as bulk async copies
+/* Third-generation by-source pass (csrc/edge_bwd_src3.cu; same role as relgat_layer_bwd_src: the autograd replay of
+ * reference core/model/layer.py:238-318 seen from the source rows): the gathered rows reach shared memory as bulk async copies
  * (cp.async.bulk + mbarrier), several rows deep per warp, and the per-edge term dz * A[rel] is NOT added: the rows are
  * [dPa | dS] with dPa[i] = sum_e alpha_e G[dst_e]; the caller folds dP = dPa + dS·A into the GEMMs that consume them
  * (dW = dPa^T X + A^T (dS^T X); dX = [dPa | dS] · [W ; A·W]), which keeps the attention vectors out of shared memory.
