@@ -150,3 +150,38 @@ def test_negative_sampling_matches_reference_stream():
         assert np.array_equal(s, z[f"batch{bi}_src"])
         assert np.array_equal(rr, z[f"batch{bi}_rel"])
         assert np.array_equal(dd, z[f"batch{bi}_dst"])
+
+
+def test_folded_backward_algebra_matches_closed_form():
+    """The third-generation by-source pass writes rows [dPa | dS] — dPa[i] = sum_e alpha_e G[dst_e] WITHOUT the per-edge
+    dz * A[rel] term, dS[i, h, r] = sum_{e: src = i, rel = r} dz[e, h] — and the product folds dP = dPa + dS·A_bd into its
+    GEMMs (functional.fold_operands).  Here the same algebra in fp64 against the oracle's closed form (which is pinned
+    to the reference by test_closed_form_matches_reference_layer): dW, dX and dA from the folded operands equal the
+    ones from the oracle's dP / dA."""
+    rng = np.random.default_rng(17)
+    n, e, r, h, f, d_in = 90, 700, 5, 3, 8, 20
+    src, dst, rel = rng.integers(0, n, e), rng.integers(0, n, e), rng.integers(0, r, e)
+    gi = O.graph_index_np(src, dst, rel, n, r)
+    X = rng.standard_normal((n, d_in))
+    W = rng.standard_normal((h * f, d_in)) / np.sqrt(d_in)
+    A = rng.standard_normal((h, r, f)) / np.sqrt(f)
+    P = (X @ W.T).reshape(n, h, f)
+    _, z, alpha, _ = O.layer_forward_closed(P, A, np.zeros(r), gi)
+    G = rng.standard_normal((n, h, f))
+    dP, dA, _, dz = O.layer_backward_closed(G, P, A, gi, z, alpha)
+    cs, cr, cd = gi["csr_src"], gi["csr_rel"], gi["csr_dst"]
+    dPa = np.zeros_like(dP)
+    np.add.at(dPa, cs, alpha[:, :, None] * G[cd])                      # what the kernel accumulates per source
+    dS = np.zeros((n, h, r))
+    np.add.at(dS, (cs[:, None], np.arange(h)[None, :], cr[:, None]), dz)
+    A_bd = np.zeros((h * r, h * f))                                   # block-diagonal attention vectors
+    for hh in range(h):
+        A_bd[hh * r:(hh + 1) * r, hh * f:(hh + 1) * f] = A[hh]
+    rows = np.concatenate([dPa.reshape(n, -1), dS.reshape(n, -1)], axis=1)   # [dPa | dS]
+    assert rel_err(dPa.reshape(n, -1) + dS.reshape(n, -1) @ A_bd, dP.reshape(n, -1)) < 1e-12
+    ext = rows.T @ X                                                  # the widened split-K GEMM: [dPa^T X ; dS^T X]
+    T = ext[h * f:]
+    assert rel_err(ext[:h * f] + A_bd.T @ T, dP.reshape(n, -1).T @ X) < 1e-12            # dW
+    assert rel_err(rows @ np.concatenate([W, A_bd @ W], axis=0), dP.reshape(n, -1) @ W) < 1e-12   # dX
+    dA_fold = np.stack([(T[hh * r:(hh + 1) * r] @ W.T)[:, hh * f:(hh + 1) * f] for hh in range(h)])
+    assert rel_err(dA_fold, dA) < 1e-12                                # dA[h] = (dS_h^T X) W_h^T
